@@ -1,0 +1,169 @@
+/*
+ * rscotr.h -- C ABI of librscotr_b200.so: the sm_100a kernels behind the RSCoTr
+ * co-training hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain C: raw DEVICE pointers, explicit int sizes, a dtype enum, a CUDA
+ *     stream passed as void* (cudaStream_t); no torch / C++ types.
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library
+ *     never allocates and keeps no global state besides a thread-local error
+ *     string.  Calls are asynchronous on `stream`.
+ *   - return 0 on success; RSC_ERR_* otherwise, message via rsc_last_error().
+ *   - there is NO CPU path: a call on a machine without a CUDA device fails
+ *     with RSC_ERR_CUDA.
+ *
+ * Each function cites the reference interface it stands in for.  The reference
+ * (Li-Qingyun/RSCoTr) is pure Python over mmcv-full 1.6.1 / mmdet 2.25.1; the
+ * only FFI on its path is mmcv's ext_module (ms_deform_attn_*,
+ * sigmoid_focal_loss_*); the Swin ops are eager ATen chains inside
+ * mmdet/models/backbones/swin.py which the fused kernels below replace.
+ */
+#ifndef RSCOTR_H_
+#define RSCOTR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSC_OK 0
+#define RSC_ERR_INVALID 1 /* bad argument (shape, dtype, alignment, null pointer) */
+#define RSC_ERR_CUDA 2    /* launch / runtime error reported by CUDA */
+
+/* element type of activation tensors ("x" pointers).  Parameters that the
+ * reference keeps in fp32 (sampling locations, attention weights, LayerNorm
+ * statistics, gradient accumulators) are always float. */
+#define RSC_F32 0
+#define RSC_BF16 1
+
+const char *rsc_last_error(void);
+int rsc_version(void);
+/* number of kernels launched by this library in the calling process since the
+ * last rsc_reset_launch_count() (bench.py reports it as gpu_launches). */
+int64_t rsc_launch_count(void);
+void rsc_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Window index maps.  Replaces: mmdet ShiftWindowMSA.forward's
+ *   F.pad -> torch.roll(-shift) -> window_partition   (and the inverse
+ *   window_reverse -> roll(+shift) -> crop), mmdet/models/backbones/swin.py,
+ * reached from models/multi/multitask_learner.py:83 (self.backbone(img)).
+ * SURVEY 8a rows a3/a5.  Integer index arithmetic: bit exact.
+ * ---------------------------------------------------------------------- */
+/* idx_out[B*nW*ws*ws] (int64): flat source token index into (B,H,W) for every
+ * slot of the padded+shifted+partitioned tensor, -1 for a padded slot. */
+int rsc_window_index_partition(int64_t *idx_out, int B, int H, int W, int ws, int shift, void *stream);
+/* idx_out[B*H*W] (int64): for every token of (B,H,W) the flat slot in the
+ * (B*nW, ws, ws) window tensor it is read back from by
+ * window_reverse -> roll(+shift) -> crop. */
+int rsc_window_index_reverse(int64_t *idx_out, int B, int H, int W, int ws, int shift, void *stream);
+/* x (B,H,W,C) -> windows (B*nW, ws*ws, C), zero fill for padded slots. */
+int rsc_window_partition(const void *x, void *windows, int B, int H, int W, int C, int ws, int shift, int dtype,
+                         void *stream);
+/* windows (B*nW, ws*ws, C) -> x (B,H,W,C) (crop fused). */
+int rsc_window_reverse(const void *windows, void *x, int B, int H, int W, int C, int ws, int shift, int dtype,
+                       void *stream);
+
+/* ------------------------------------------------------------------------
+ * Fused (shifted-)window attention core.  Replaces, in one kernel, the chain
+ *   pad, roll, window_partition, reshape/permute qkv, q*scale, q@k^T,
+ *   + relative_position_bias_table[index], + shift mask (0/-100), softmax,
+ *   attn@v, transpose/reshape, window_reverse, roll back, crop
+ * of mmdet ShiftWindowMSA.forward / WindowMSA.forward (SURVEY 8a rows a3-a5;
+ * restated in oracle/swin.py::shift_window_msa).  The qkv and proj Linear
+ * layers stay outside (GEMMs).
+ *
+ *   qkv       (B,H,W,3*C)  un-padded tokens; layout per token [q|k|v] x [head][32]
+ *   qkv_bias  (3*C) float or NULL: value of a zero-padded token's q|k|v row
+ *             (the reference pads AFTER norm1, so a padded row is Linear(0) = bias)
+ *   bias_table((2*ws-1)^2, heads) float   -- relative_position_bias_table
+ *   out       (B,H,W,C)
+ * head_dim = C/heads must be 32, ws must be 7, shift in {0, 3}.
+ * ---------------------------------------------------------------------- */
+int rsc_wmsa_fwd(const void *qkv, const float *qkv_bias, const float *bias_table, void *out, int B, int H, int W,
+                 int C, int heads, int ws, int shift, float scale, int dtype, void *stream);
+/* Backward.  dqkv (B,H,W,3*C) is fully written.  dbias_table ((2*ws-1)^2,heads)
+ * and dqkv_bias (3*C) (gradient reaching the qkv bias through padded rows;
+ * may be NULL iff qkv_bias is NULL) are float and ACCUMULATED into (caller
+ * zero-fills or carries a running gradient). */
+int rsc_wmsa_bwd(const void *qkv, const float *qkv_bias, const float *bias_table, const void *dout, void *dqkv,
+                 float *dbias_table, float *dqkv_bias, int B, int H, int W, int C, int heads, int ws, int shift,
+                 float scale, int dtype, void *stream);
+
+/* ------------------------------------------------------------------------
+ * PatchMerging gather + LayerNorm.  Replaces mmdet PatchMerging.forward up to
+ * (not including) the reduction Linear: NLC->NCHW, corner pad to even,
+ * nn.Unfold(2, stride 2) (merged channel = c*4 + kh*2 + kw), LayerNorm(4C).
+ * SURVEY 8a row a6; oracle/swin.py::patch_merging.
+ *   x (B,H,W,C) -> y (B, ceil(H/2)*ceil(W/2), 4C); mean/rstd (B*L_out) float
+ * ---------------------------------------------------------------------- */
+int rsc_patch_merge_ln_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean, float *rstd,
+                           int B, int H, int W, int C, float eps, int dtype, void *stream);
+/* dx (B,H,W,C) fully written; dgamma/dbeta (4C) float ACCUMULATED. */
+int rsc_patch_merge_ln_bwd(const void *x, const float *gamma, const float *mean, const float *rstd, const void *dy,
+                           void *dx, float *dgamma, float *dbeta, int B, int H, int W, int C, int dtype,
+                           void *stream);
+
+/* ------------------------------------------------------------------------
+ * Multi-scale deformable attention.  Drop-in for mmcv-full 1.6.1
+ *   ext_module.ms_deform_attn_forward / ms_deform_attn_backward
+ * (mmcv/ops/multi_scale_deform_attn.py::MultiScaleDeformableAttnFunction),
+ * reached from models/multi/bbox_head/transformer.py:211,258,
+ * models/multi/seg_head/pixel_decoder.py:134, cls_head/pixel_decoder.py:95.
+ * SURVEY 8a row a11.
+ *   value   (B,Nv,heads,32)          dtype
+ *   spatial_shapes (L,2) int64 (h,w); level_start_index (L) int64   [device]
+ *   sampling_loc (B,Nq,heads,L,P,2) float in [0,1] (x,y)
+ *   attn_weight  (B,Nq,heads,L,P)   float
+ *   out     (B,Nq,heads*32)          dtype
+ * heads*L*P... constraints: head_dim == 32, heads % 4 == 0, L*P == 16 is the
+ * tuned case; any L*P that is a multiple of 2 and <= 64 is accepted.
+ * im2col_step is accepted and ignored (the whole batch is one launch).
+ * ---------------------------------------------------------------------- */
+int rsc_msda_fwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                 const float *sampling_loc, const float *attn_weight, void *out, int B, int Nv, int Nq, int heads,
+                 int L, int P, int im2col_step, int dtype, void *stream);
+/* grad_value (B,Nv,heads,32) is FLOAT regardless of dtype and ACCUMULATED with
+ * atomics (caller zero-fills, as mmcv does); grad_loc / grad_weight are float
+ * and fully written. */
+int rsc_msda_bwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                 const float *sampling_loc, const float *attn_weight, const void *grad_out, float *grad_value,
+                 float *grad_loc, float *grad_weight, int B, int Nv, int Nq, int heads, int L, int P,
+                 int im2col_step, int dtype, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Global average pool.  Replaces mmcls GlobalAveragePooling
+ * (AdaptiveAvgPool2d((1,1))) called from
+ * models/multi/cls_head/slvl_cls_head.py:14-18.  SURVEY 8a row a12.
+ * channels_last = 0: x (B,C,HW) -> y (B,C);  1: x (B,HW,C) -> y (B,C).
+ * ---------------------------------------------------------------------- */
+int rsc_gap_fwd(const void *x, void *y, int B, int C, int HW, int channels_last, int dtype, void *stream);
+int rsc_gap_bwd(const void *dy, void *dx, int B, int C, int HW, int channels_last, int dtype, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Bilinear resize, align_corners=False, NCHW.  Replaces F.interpolate /
+ * mmseg.ops.resize at models/multi/seg_head/mask2former_head.py:126-130 and
+ * mmseg BaseDecodeHead.losses (mask2former_head.py:204).  SURVEY rows a18/a19.
+ *   x (N,Hi,Wi) planes -> y (N,Ho,Wo) planes, N = B*C.
+ * bwd: dx fully written (gather formulation, no atomics).
+ * ---------------------------------------------------------------------- */
+int rsc_bilinear_fwd(const void *x, void *y, int N, int Hi, int Wi, int Ho, int Wo, int dtype, void *stream);
+int rsc_bilinear_bwd(const void *dy, void *dx, int N, int Hi, int Wi, int Ho, int Wo, int dtype, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Sigmoid focal loss.  Drop-in for mmcv ext_module.sigmoid_focal_loss_forward
+ * / _backward (mmdet FocalLoss -> mmcv.ops.sigmoid_focal_loss), reached from
+ * models/multi/bbox_head/mmdet_detr_head/detr_head.py:384 and dino_head.py:272.
+ *   input (N,C) dtype logits; target (N) int64 in [0,C] (C = background);
+ *   output / grad_input (N,C) float, element-wise (reduction by the caller).
+ * ---------------------------------------------------------------------- */
+int rsc_sigmoid_focal_loss_fwd(const void *input, const int64_t *target, float *output, int N, int C, float gamma,
+                               float alpha, int dtype, void *stream);
+int rsc_sigmoid_focal_loss_bwd(const void *input, const int64_t *target, float *grad_input, int N, int C,
+                               float gamma, float alpha, int dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSCOTR_H_ */

@@ -1,0 +1,82 @@
+"""ctypes binding of librscotr_b200.so (the C ABI declared in include/rscotr.h).
+
+No CPU fallback: if the shared library is missing the import of any op raises.
+"""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'librscotr_b200.so')
+HEADER = os.path.join(os.path.dirname(HERE), 'include', 'rscotr.h')
+
+RSC_F32, RSC_BF16 = 0, 1
+
+_lib = None
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+
+_SIGS = {
+    'rsc_window_index_partition': [_P, _I, _I, _I, _I, _I, _P],
+    'rsc_window_index_reverse': [_P, _I, _I, _I, _I, _I, _P],
+    'rsc_window_partition': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'rsc_window_reverse': [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'rsc_wmsa_fwd': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    'rsc_wmsa_bwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
+    'rsc_patch_merge_ln_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
+    'rsc_patch_merge_ln_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'rsc_msda_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'rsc_msda_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'rsc_gap_fwd': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'rsc_gap_bwd': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'rsc_bilinear_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'rsc_bilinear_bwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'rsc_sigmoid_focal_loss_fwd': [_P, _P, _P, _I, _I, _F, _F, _I, _P],
+    'rsc_sigmoid_focal_loss_bwd': [_P, _P, _P, _I, _I, _F, _F, _I, _P],
+}
+
+
+def declared_symbols():
+    """Every function name declared in include/rscotr.h."""
+    txt = open(HEADER).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(rsc_[a-z0-9_]+)\s*\(', txt)))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'librscotr_b200.so not built (%s); run `python -c "import __graft_entry__ as g; g.build()"`. '
+                'There is no CPU fallback.' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = _I
+        L.rsc_last_error.restype = ctypes.c_char_p
+        L.rsc_version.restype = _I
+        L.rsc_launch_count.restype = ctypes.c_int64
+        L.rsc_reset_launch_count.restype = None
+        _lib = L
+    return _lib
+
+
+def check(status, name):
+    if status != 0:
+        raise RuntimeError('%s failed (%d): %s' % (name, status, lib().rsc_last_error().decode()))
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)
+
+
+def launch_count():
+    return int(lib().rsc_launch_count())
+
+
+def reset_launch_count():
+    lib().rsc_reset_launch_count()

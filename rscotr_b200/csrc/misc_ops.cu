@@ -1,0 +1,516 @@
+// Bandwidth-bound helper kernels of the co-training path:
+//   PatchMerging gather + LayerNorm (a6), global average pool (a12),
+//   bilinear resize align_corners=False (a18/a19), sigmoid focal loss (a16).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace rsc {
+
+// ===========================================================================
+// PatchMerging: 2x2 gather in nn.Unfold channel order (c*4 + kh*2 + kw) fused
+// with LayerNorm(4C).  One warp per output token; a lane owns 4 consecutive
+// source channels of each of the 4 source tokens = 16 consecutive output
+// channels, so both sides move as 16 B / 8 B vectors.
+// ===========================================================================
+struct PMGeom {
+  int B, H, W, C, Ho, Wo;
+};
+
+template <typename T>
+__device__ __forceinline__ float4 pm_load(const T *x, const PMGeom &g, int b, int h, int w, int c) {
+  if (h >= g.H || w >= g.W) return make_float4(0.f, 0.f, 0.f, 0.f);  // 'corner' zero padding
+  return load4<T>(x + (((int64_t)b * g.H + h) * g.W + w) * g.C + c);
+}
+
+template <typename T, int ITER>
+__global__ void __launch_bounds__(256)
+    patch_merge_ln_fwd_kernel(const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+                              T *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd, PMGeom g,
+                              float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tokens = (int64_t)g.B * g.Ho * g.Wo;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float invn = 1.0f / (4 * g.C);
+  for (int64_t tok = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tok < tokens; tok += nwarps) {
+    const int j = (int)(tok % g.Wo), i = (int)((tok / g.Wo) % g.Ho), b = (int)(tok / ((int64_t)g.Wo * g.Ho));
+    float4 v[ITER][4];
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int c = it * 128 + lane * 4;
+      if (c < g.C) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[it][k] = pm_load<T>(x, g, b, 2 * i + (k >> 1), 2 * j + (k & 1), c);
+          s += v[it][k].x + v[it][k].y + v[it][k].z + v[it][k].w;
+        }
+      }
+    }
+    const float mu = warp_sum(s) * invn;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int c = it * 128 + lane * 4;
+      if (c < g.C) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = v[it][k].x - mu, b2 = v[it][k].y - mu, c2 = v[it][k].z - mu, d = v[it][k].w - mu;
+          q += a * a + b2 * b2 + c2 * c2 + d * d;
+        }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) * invn + eps);
+    if (lane == 0) {
+      mean[tok] = mu;
+      rstd[tok] = rs;
+    }
+    T *yo = y + tok * 4 * g.C;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int c = it * 128 + lane * 4;
+      if (c < g.C) {
+        const float *vf = reinterpret_cast<const float *>(&v[it][0]);  // vf[k*4 + cc]
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int o = (c + cc) * 4;
+          const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma + o));
+          const float4 be = __ldg(reinterpret_cast<const float4 *>(beta + o));
+          float4 r;
+          r.x = (vf[0 * 4 + cc] - mu) * rs * ga.x + be.x;
+          r.y = (vf[1 * 4 + cc] - mu) * rs * ga.y + be.y;
+          r.z = (vf[2 * 4 + cc] - mu) * rs * ga.z + be.z;
+          r.w = (vf[3 * 4 + cc] - mu) * rs * ga.w + be.w;
+          store4<T>(yo + o, r);
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void pm_store(T *dx, const PMGeom &g, int b, int h, int w, int c, float4 v) {
+  if (h >= g.H || w >= g.W) return;
+  store4<T>(dx + (((int64_t)b * g.H + h) * g.W + w) * g.C + c, v);
+}
+
+template <typename T, int ITER>
+__global__ void __launch_bounds__(256)
+    patch_merge_ln_bwd_kernel(const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ mean,
+                              const float *__restrict__ rstd, const T *__restrict__ dy, T *__restrict__ dx,
+                              float *__restrict__ dgamma, float *__restrict__ dbeta, PMGeom g) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tokens = (int64_t)g.B * g.Ho * g.Wo;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float invn = 1.0f / (4 * g.C);
+  float dg[ITER][16], db[ITER][16];  // [cc*4 + k] = output channel (c+cc)*4 + k
+#pragma unroll
+  for (int it = 0; it < ITER; ++it)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) dg[it][e] = 0.f, db[it][e] = 0.f;
+
+  for (int64_t tok = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tok < tokens; tok += nwarps) {
+    const int j = (int)(tok % g.Wo), i = (int)((tok / g.Wo) % g.Ho), b = (int)(tok / ((int64_t)g.Wo * g.Ho));
+    const float mu = mean[tok], rs = rstd[tok];
+    const T *dyo = dy + tok * 4 * g.C;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int c = it * 128 + lane * 4;
+      if (c < g.C) {
+        float4 xv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xv[k] = pm_load<T>(x, g, b, 2 * i + (k >> 1), 2 * j + (k & 1), c);
+        const float *xf = reinterpret_cast<const float *>(&xv[0]);  // xf[k*4 + cc]
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int o = (c + cc) * 4;
+          const float4 d4 = load4<T>(dyo + o);
+          const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma + o));
+          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+          const float gv[4] = {ga.x, ga.y, ga.z, ga.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float xh = (xf[k * 4 + cc] - mu) * rs;
+            const float dxh = dv[k] * gv[k];
+            s1 += dxh;
+            s2 = fmaf(dxh, xh, s2);
+            dg[it][cc * 4 + k] = fmaf(dv[k], xh, dg[it][cc * 4 + k]);
+            db[it][cc * 4 + k] += dv[k];
+          }
+        }
+      }
+    }
+    s1 = warp_sum(s1) * invn;
+    s2 = warp_sum(s2) * invn;
+    // second sweep: re-read x / dy (L1 hits) and emit dx
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int c = it * 128 + lane * 4;
+      if (c < g.C) {
+        float4 xv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xv[k] = pm_load<T>(x, g, b, 2 * i + (k >> 1), 2 * j + (k & 1), c);
+        float *xf = reinterpret_cast<float *>(&xv[0]);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int o = (c + cc) * 4;
+          const float4 d4 = load4<T>(dyo + o);
+          const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma + o));
+          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+          const float gv[4] = {ga.x, ga.y, ga.z, ga.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float xh = (xf[k * 4 + cc] - mu) * rs;
+            xf[k * 4 + cc] = rs * (dv[k] * gv[k] - s1 - xh * s2);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pm_store<T>(dx, g, b, 2 * i + (k >> 1), 2 * j + (k & 1), c, xv[k]);
+      }
+    }
+  }
+  // per-warp partial sums -> global (4C addresses, one atomic per warp each)
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int c = it * 128 + lane * 4;
+    if (c < g.C) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        atomicAdd(dgamma + c * 4 + e, dg[it][e]);
+        atomicAdd(dbeta + c * 4 + e, db[it][e]);
+      }
+    }
+  }
+}
+
+// ===========================================================================
+// Global average pool
+// ===========================================================================
+template <typename T>
+__global__ void gap_nchw_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, int64_t planes, int HW) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < planes; p += nwarps) {
+    const T *src = x + p * HW;
+    float s = 0.f;
+    for (int i = lane; i < HW; i += 32) s += to_f<T>(src[i]);
+    s = warp_sum(s);
+    if (lane == 0) y[p] = from_f<T>(s / HW);
+  }
+}
+
+// x (B,HW,C): block = 32 channel-quads x 8 row slices; grid (C/128, B)
+template <typename T>
+__global__ void __launch_bounds__(256) gap_nhwc_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, int C, int HW) {
+  __shared__ float4 red[8][32];
+  const int c = blockIdx.x * 128 + threadIdx.x * 4;
+  const int b = blockIdx.y;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    const T *src = x + (int64_t)b * HW * C + c;
+    for (int r = threadIdx.y; r < HW; r += 8) {
+      const float4 v = load4<T>(src + (int64_t)r * C);
+      s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 v = red[k][threadIdx.x];
+      s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    }
+    const float inv = 1.0f / HW;
+    store4<T>(y + (int64_t)b * C + c, make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv));
+  }
+}
+
+template <typename T>
+__global__ void gap_nchw_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int64_t total, int HW) {
+  const float inv = 1.0f / HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = from_f<T>(to_f<T>(dy[i / HW]) * inv);
+}
+
+template <typename T>
+__global__ void gap_nhwc_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int64_t total4, int C, int HW) {
+  const float inv = 1.0f / HW;
+  const int C4 = C / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    const int64_t b = i / ((int64_t)C4 * HW);
+    const float4 v = load4<T>(dy + b * C + c4 * 4);
+    store4<T>(dx + i * 4, make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv));
+  }
+}
+
+// ===========================================================================
+// Bilinear resize (align_corners=False), planes (N,H,W)
+// ===========================================================================
+__device__ __forceinline__ void bil_src(int o, float scale, int in, int &i0, int &i1, float &lam) {
+  float s = scale * (o + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 < in - 1 ? i0 + 1 : i0;
+  lam = s - i0;
+}
+
+template <typename T>
+__global__ void bilinear_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, int64_t total, int Hi, int Wi, int Ho,
+                                    int Wo, float sh, float sw) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
+    const int64_t n = i / ((int64_t)Wo * Ho);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bil_src(oy, sh, Hi, y0, y1, ly);
+    bil_src(ox, sw, Wi, x0, x1, lx);
+    const T *p = x + n * Hi * Wi;
+    const float v00 = to_f<T>(p[y0 * Wi + x0]), v01 = to_f<T>(p[y0 * Wi + x1]);
+    const float v10 = to_f<T>(p[y1 * Wi + x0]), v11 = to_f<T>(p[y1 * Wi + x1]);
+    y[i] = from_f<T>((1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11));
+  }
+}
+
+// weight with which output index o (of an axis) reads input index i
+__device__ __forceinline__ float bil_w(int o, int i, float scale, int in) {
+  int i0, i1;
+  float lam;
+  bil_src(o, scale, in, i0, i1, lam);
+  float w = 0.f;
+  if (i0 == i) w += 1.f - lam;
+  if (i1 == i) w += lam;
+  return w;
+}
+
+// gather formulation: thread per INPUT pixel, loops over the outputs that read it
+template <typename T>
+__global__ void bilinear_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int64_t total, int Hi, int Wi,
+                                    int Ho, int Wo, float sh, float sw) {
+  const float rh = 1.f / sh, rw = 1.f / sw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % Wi), iy = (int)((i / Wi) % Hi);
+    const int64_t n = i / ((int64_t)Wi * Hi);
+    // outputs o with source coordinate in (i-1, i+1) (plus border clamping): conservative range
+    int oy0 = (int)floorf((iy - 1 + 0.5f) * rh - 0.5f) - 1, oy1 = (int)ceilf((iy + 1 + 0.5f) * rh - 0.5f) + 1;
+    int ox0 = (int)floorf((ix - 1 + 0.5f) * rw - 0.5f) - 1, ox1 = (int)ceilf((ix + 1 + 0.5f) * rw - 0.5f) + 1;
+    if (iy == 0) oy0 = 0;
+    if (ix == 0) ox0 = 0;
+    if (iy == Hi - 1) oy1 = Ho - 1;
+    if (ix == Wi - 1) ox1 = Wo - 1;
+    oy0 = max(oy0, 0), ox0 = max(ox0, 0), oy1 = min(oy1, Ho - 1), ox1 = min(ox1, Wo - 1);
+    const T *p = dy + n * Ho * Wo;
+    float acc = 0.f;
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      const float wy = bil_w(oy, iy, sh, Hi);
+      if (wy == 0.f) continue;
+      float row = 0.f;
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        const float wx = bil_w(ox, ix, sw, Wi);
+        if (wx != 0.f) row = fmaf(wx, to_f<T>(p[(int64_t)oy * Wo + ox]), row);
+      }
+      acc = fmaf(wy, row, acc);
+    }
+    dx[i] = from_f<T>(acc);
+  }
+}
+
+// ===========================================================================
+// Sigmoid focal loss (element-wise, mmcv semantics)
+// ===========================================================================
+template <typename T, bool BWD>
+__global__ void focal_kernel(const T *__restrict__ in, const int64_t *__restrict__ target, float *__restrict__ out,
+                             int64_t total, int C, float gamma, float alpha) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t t = target[i / C];
+    const float x = to_f<T>(in[i]);
+    const float p = 1.f / (1.f + expf(-x));
+    const float lp = logf(fmaxf(p, FLT_MIN)), ln = logf(fmaxf(1.f - p, FLT_MIN));
+    const float pw_p = powf(1.f - p, gamma), pw_n = powf(p, gamma);
+    float r;
+    if (!BWD) {
+      r = (t == c) ? -alpha * pw_p * lp : -(1.f - alpha) * pw_n * ln;
+    } else {
+      r = (t == c) ? -alpha * pw_p * (1.f - p - gamma * p * lp) : -(1.f - alpha) * pw_n * (gamma * (1.f - p) * ln - p);
+    }
+    out[i] = r;
+  }
+}
+
+static inline int ew_grid(int64_t n, int per_block) {
+  int64_t blocks = (n + per_block - 1) / per_block;
+  int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+}  // namespace rsc
+
+using namespace rsc;
+
+#define DISPATCH_T(dtype, ...)                    \
+  if (dtype == RSC_F32) {                         \
+    using T = float;                              \
+    __VA_ARGS__;                                  \
+  } else {                                        \
+    using T = __nv_bfloat16;                      \
+    __VA_ARGS__;                                  \
+  }
+
+template <typename T>
+static void pm_fwd_launch(int iters, int grid, cudaStream_t st, const void *x, const float *gamma, const float *beta,
+                          void *y, float *mean, float *rstd, PMGeom g, float eps) {
+#define PM_CASE(N)                                                                                                  \
+  case N:                                                                                                           \
+    patch_merge_ln_fwd_kernel<T, N><<<grid, 256, 0, st>>>((const T *)x, gamma, beta, (T *)y, mean, rstd, g, eps);   \
+    break;
+  switch (iters) { PM_CASE(1) PM_CASE(2) PM_CASE(3) PM_CASE(4) }
+#undef PM_CASE
+}
+template <typename T>
+static void pm_bwd_launch(int iters, int grid, cudaStream_t st, const void *x, const float *gamma, const float *mean,
+                          const float *rstd, const void *dy, void *dx, float *dgamma, float *dbeta, PMGeom g) {
+#define PM_CASE(N)                                                                                                 \
+  case N:                                                                                                          \
+    patch_merge_ln_bwd_kernel<T, N>                                                                                \
+        <<<grid, 256, 0, st>>>((const T *)x, gamma, mean, rstd, (const T *)dy, (T *)dx, dgamma, dbeta, g);         \
+    break;
+  switch (iters) { PM_CASE(1) PM_CASE(2) PM_CASE(3) PM_CASE(4) }
+#undef PM_CASE
+}
+
+static int pm_check(const char *fn, int B, int H, int W, int C, int dtype) {
+  RSC_CHECK_ARG(B > 0 && H > 0 && W > 0, "%s: empty tensor (B=%d,H=%d,W=%d)", fn, B, H, W);
+  RSC_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 512, "%s: C must be a multiple of 4, <= 512 (got %d)", fn, C);
+  RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "%s: bad dtype %d", fn, dtype);
+  return RSC_OK;
+}
+
+extern "C" int rsc_patch_merge_ln_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean,
+                                      float *rstd, int B, int H, int W, int C, float eps, int dtype, void *stream) {
+  if (int e = pm_check("rsc_patch_merge_ln_fwd", B, H, W, C, dtype)) return e;
+  RSC_CHECK_ARG(x && gamma && beta && y && mean && rstd, "rsc_patch_merge_ln_fwd: null pointer");
+  PMGeom g{B, H, W, C, (H + 1) / 2, (W + 1) / 2};
+  int64_t tokens = (int64_t)B * g.Ho * g.Wo;
+  int grid = ew_grid(tokens, 8);
+  DISPATCH_T(dtype, pm_fwd_launch<T>((C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, beta, y, mean, rstd, g, eps));
+  RSC_CHECK_LAUNCH("rsc_patch_merge_ln_fwd");
+  return RSC_OK;
+}
+
+extern "C" int rsc_patch_merge_ln_bwd(const void *x, const float *gamma, const float *mean, const float *rstd,
+                                      const void *dy, void *dx, float *dgamma, float *dbeta, int B, int H, int W,
+                                      int C, int dtype, void *stream) {
+  if (int e = pm_check("rsc_patch_merge_ln_bwd", B, H, W, C, dtype)) return e;
+  RSC_CHECK_ARG(x && gamma && mean && rstd && dy && dx && dgamma && dbeta, "rsc_patch_merge_ln_bwd: null pointer");
+  PMGeom g{B, H, W, C, (H + 1) / 2, (W + 1) / 2};
+  int64_t tokens = (int64_t)B * g.Ho * g.Wo;
+  int64_t blocks = (tokens + 7) / 8;
+  int grid = (int)(blocks < kNumSMs * 4 ? blocks : kNumSMs * 4);  // few warps -> few dgamma atomics
+  DISPATCH_T(dtype, pm_bwd_launch<T>((C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, mean, rstd, dy, dx, dgamma,
+                                     dbeta, g));
+  RSC_CHECK_LAUNCH("rsc_patch_merge_ln_bwd");
+  return RSC_OK;
+}
+
+static int gap_check(const char *fn, int B, int C, int HW, int channels_last, int dtype) {
+  RSC_CHECK_ARG(B > 0 && C > 0 && HW > 0, "%s: empty tensor (B=%d,C=%d,HW=%d)", fn, B, C, HW);
+  RSC_CHECK_ARG(!channels_last || C % 4 == 0, "%s: channels_last needs C %% 4 == 0 (C=%d)", fn, C);
+  RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "%s: bad dtype %d", fn, dtype);
+  return RSC_OK;
+}
+
+extern "C" int rsc_gap_fwd(const void *x, void *y, int B, int C, int HW, int channels_last, int dtype, void *stream) {
+  if (int e = gap_check("rsc_gap_fwd", B, C, HW, channels_last, dtype)) return e;
+  RSC_CHECK_ARG(x && y, "rsc_gap_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (channels_last) {
+    dim3 grid((C + 127) / 128, B), block(32, 8);
+    DISPATCH_T(dtype, gap_nhwc_fwd_kernel<T><<<grid, block, 0, st>>>((const T *)x, (T *)y, C, HW));
+  } else {
+    int64_t planes = (int64_t)B * C;
+    DISPATCH_T(dtype, gap_nchw_fwd_kernel<T><<<ew_grid(planes, 8), 256, 0, st>>>((const T *)x, (T *)y, planes, HW));
+  }
+  RSC_CHECK_LAUNCH("rsc_gap_fwd");
+  return RSC_OK;
+}
+
+extern "C" int rsc_gap_bwd(const void *dy, void *dx, int B, int C, int HW, int channels_last, int dtype,
+                           void *stream) {
+  if (int e = gap_check("rsc_gap_bwd", B, C, HW, channels_last, dtype)) return e;
+  RSC_CHECK_ARG(dy && dx, "rsc_gap_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)B * C * HW;
+  if (channels_last) {
+    DISPATCH_T(dtype,
+               gap_nhwc_bwd_kernel<T><<<ew_grid(total / 4, 256), 256, 0, st>>>((const T *)dy, (T *)dx, total / 4, C, HW));
+  } else {
+    DISPATCH_T(dtype, gap_nchw_bwd_kernel<T><<<ew_grid(total, 256), 256, 0, st>>>((const T *)dy, (T *)dx, total, HW));
+  }
+  RSC_CHECK_LAUNCH("rsc_gap_bwd");
+  return RSC_OK;
+}
+
+static int bil_check(const char *fn, int N, int Hi, int Wi, int Ho, int Wo, int dtype) {
+  RSC_CHECK_ARG(N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "%s: empty tensor (N=%d, %dx%d -> %dx%d)", fn, N, Hi, Wi,
+                Ho, Wo);
+  RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "%s: bad dtype %d", fn, dtype);
+  return RSC_OK;
+}
+
+extern "C" int rsc_bilinear_fwd(const void *x, void *y, int N, int Hi, int Wi, int Ho, int Wo, int dtype,
+                                void *stream) {
+  if (int e = bil_check("rsc_bilinear_fwd", N, Hi, Wi, Ho, Wo, dtype)) return e;
+  RSC_CHECK_ARG(x && y, "rsc_bilinear_fwd: null pointer");
+  int64_t total = (int64_t)N * Ho * Wo;
+  float sh = (float)Hi / Ho, sw = (float)Wi / Wo;
+  DISPATCH_T(dtype, bilinear_fwd_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                        (const T *)x, (T *)y, total, Hi, Wi, Ho, Wo, sh, sw));
+  RSC_CHECK_LAUNCH("rsc_bilinear_fwd");
+  return RSC_OK;
+}
+
+extern "C" int rsc_bilinear_bwd(const void *dy, void *dx, int N, int Hi, int Wi, int Ho, int Wo, int dtype,
+                                void *stream) {
+  if (int e = bil_check("rsc_bilinear_bwd", N, Hi, Wi, Ho, Wo, dtype)) return e;
+  RSC_CHECK_ARG(dy && dx, "rsc_bilinear_bwd: null pointer");
+  int64_t total = (int64_t)N * Hi * Wi;
+  float sh = (float)Hi / Ho, sw = (float)Wi / Wo;
+  DISPATCH_T(dtype, bilinear_bwd_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                        (const T *)dy, (T *)dx, total, Hi, Wi, Ho, Wo, sh, sw));
+  RSC_CHECK_LAUNCH("rsc_bilinear_bwd");
+  return RSC_OK;
+}
+
+static int focal_check(const char *fn, int N, int C, int dtype) {
+  RSC_CHECK_ARG(N >= 0 && C > 0, "%s: bad shape (N=%d,C=%d)", fn, N, C);
+  RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "%s: bad dtype %d", fn, dtype);
+  return RSC_OK;
+}
+
+extern "C" int rsc_sigmoid_focal_loss_fwd(const void *input, const int64_t *target, float *output, int N, int C,
+                                          float gamma, float alpha, int dtype, void *stream) {
+  if (int e = focal_check("rsc_sigmoid_focal_loss_fwd", N, C, dtype)) return e;
+  if (N == 0) return RSC_OK;
+  RSC_CHECK_ARG(input && target && output, "rsc_sigmoid_focal_loss_fwd: null pointer");
+  int64_t total = (int64_t)N * C;
+  DISPATCH_T(dtype, focal_kernel<T, false><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                        (const T *)input, target, output, total, C, gamma, alpha));
+  RSC_CHECK_LAUNCH("rsc_sigmoid_focal_loss_fwd");
+  return RSC_OK;
+}
+
+extern "C" int rsc_sigmoid_focal_loss_bwd(const void *input, const int64_t *target, float *grad_input, int N, int C,
+                                          float gamma, float alpha, int dtype, void *stream) {
+  if (int e = focal_check("rsc_sigmoid_focal_loss_bwd", N, C, dtype)) return e;
+  if (N == 0) return RSC_OK;
+  RSC_CHECK_ARG(input && target && grad_input, "rsc_sigmoid_focal_loss_bwd: null pointer");
+  int64_t total = (int64_t)N * C;
+  DISPATCH_T(dtype, focal_kernel<T, true><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                        (const T *)input, target, grad_input, total, C, gamma, alpha));
+  RSC_CHECK_LAUNCH("rsc_sigmoid_focal_loss_bwd");
+  return RSC_OK;
+}

@@ -1,0 +1,253 @@
+// Multi-scale deformable attention, forward and backward.
+// Drop-in for mmcv-full 1.6.1 ext_module.ms_deform_attn_{forward,backward}.
+//
+// Mapping: one warp = one query x 4 consecutive heads; an 8-lane group owns one
+// head, each lane 4 of its 32 channels (16 B fp32 / 8 B bf16 vector loads, a
+// corner read is one fully used 128 B / 64 B segment per group).  The warp's
+// sampling locations (4*LP*2 floats) and attention weights (4*LP floats) are
+// contiguous in HBM: they are fetched once with coalesced float4 loads into a
+// per-warp smem slab and broadcast from there.  Backward reduces d(loc) and
+// d(weight) over the 32 channels with 3 xor-shuffles inside the 8-lane group
+// and scatters d(value) with vector red.global.add.f32.
+#include "common.cuh"
+
+namespace rsc {
+
+constexpr int MSDA_WARPS = 8;
+constexpr int MSDA_MAX_L = 8;
+constexpr int MSDA_MAX_LP = 64;
+
+struct Levels {
+  int h[MSDA_MAX_L], w[MSDA_MAX_L], start[MSDA_MAX_L];
+};
+
+__device__ __forceinline__ void load_levels(Levels &lv, const int64_t *shapes, const int64_t *starts, int L) {
+  if (threadIdx.x < L) {
+    lv.h[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+    lv.w[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+    lv.start[threadIdx.x] = (int)starts[threadIdx.x];
+  }
+}
+
+__device__ __forceinline__ float group_sum8(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ void fma4(float4 &acc, float s, float4 v) {
+  acc.x = fmaf(s, v.x, acc.x), acc.y = fmaf(s, v.y, acc.y), acc.z = fmaf(s, v.z, acc.z), acc.w = fmaf(s, v.w, acc.w);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MSDA_WARPS * 32)
+    msda_fwd_kernel(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ starts,
+                    const float *__restrict__ loc, const float *__restrict__ aw, T *__restrict__ out, int B, int Nv,
+                    int Nq, int heads, int L, int P) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ Levels lv;
+  load_levels(lv, shapes, starts, L);
+  __syncthreads();
+  const int LP = L * P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *sloc = smem + warp * (12 * LP);  // [4][LP][2]
+  float *sw = sloc + 8 * LP;              // [4][LP]
+  const int g = lane >> 3, t = lane & 7;
+  const int hgroups = heads >> 2;
+  const int64_t total = (int64_t)B * Nq * hgroups;
+  const int64_t nwarps = (int64_t)gridDim.x * MSDA_WARPS;
+  const int vstride = heads * 32;
+  for (int64_t item = (int64_t)blockIdx.x * MSDA_WARPS + warp; item < total; item += nwarps) {
+    const int hg = (int)(item % hgroups);
+    const int64_t bq = item / hgroups;
+    const int b = (int)(bq / Nq);
+    const int64_t slab = (bq * heads + hg * 4) * LP;
+    const float4 *gl = reinterpret_cast<const float4 *>(loc + slab * 2);
+    const float4 *gw = reinterpret_cast<const float4 *>(aw + slab);
+    for (int v = lane; v < 2 * LP; v += 32) reinterpret_cast<float4 *>(sloc)[v] = __ldg(gl + v);
+    for (int v = lane; v < LP; v += 32) reinterpret_cast<float4 *>(sw)[v] = __ldg(gw + v);
+    __syncwarp();
+    const int head = hg * 4 + g;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *ml = sloc + g * 2 * LP;
+    const float *mw = sw + g * LP;
+    for (int l = 0; l < L; ++l) {
+      const int Hl = lv.h[l], Wl = lv.w[l];
+      const T *vb = value + ((int64_t)b * Nv + lv.start[l]) * vstride + head * 32 + t * 4;
+#pragma unroll 4
+      for (int p = 0; p < P; ++p) {
+        const float2 xy = *reinterpret_cast<const float2 *>(ml + (l * P + p) * 2);
+        const float wgt = mw[l * P + p];
+        const float h_im = xy.y * Hl - 0.5f, w_im = xy.x * Wl - 0.5f;
+        if (h_im > -1.f && w_im > -1.f && h_im < Hl && w_im < Wl) {
+          const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+          const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+          const bool h0 = h_low >= 0, h1 = h_low + 1 <= Hl - 1, w0 = w_low >= 0, w1 = w_low + 1 <= Wl - 1;
+          const T *p00 = vb + ((int64_t)h_low * Wl + w_low) * vstride;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (h0 && w0) fma4(v, hh * hw, load4<T>(p00));
+          if (h0 && w1) fma4(v, hh * lw, load4<T>(p00 + vstride));
+          if (h1 && w0) fma4(v, lh * hw, load4<T>(p00 + (int64_t)Wl * vstride));
+          if (h1 && w1) fma4(v, lh * lw, load4<T>(p00 + (int64_t)(Wl + 1) * vstride));
+          fma4(acc, wgt, v);
+        }
+      }
+    }
+    store4<T>(out + bq * vstride + head * 32 + t * 4, acc);
+    __syncwarp();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MSDA_WARPS * 32)
+    msda_bwd_kernel(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ starts,
+                    const float *__restrict__ loc, const float *__restrict__ aw, const T *__restrict__ gout,
+                    float *__restrict__ gvalue, float *__restrict__ gloc, float *__restrict__ gaw, int B, int Nv,
+                    int Nq, int heads, int L, int P) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ Levels lv;
+  load_levels(lv, shapes, starts, L);
+  __syncthreads();
+  const int LP = L * P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *sloc = smem + warp * (24 * LP);  // [4][LP][2]
+  float *sw = sloc + 8 * LP;              // [4][LP]
+  float *sgl = sw + 4 * LP;               // [4][LP][2] grad loc
+  float *sgw = sgl + 8 * LP;              // [4][LP]    grad weight
+  const int g = lane >> 3, t = lane & 7;
+  const int hgroups = heads >> 2;
+  const int64_t total = (int64_t)B * Nq * hgroups;
+  const int64_t nwarps = (int64_t)gridDim.x * MSDA_WARPS;
+  const int vstride = heads * 32;
+  for (int64_t item = (int64_t)blockIdx.x * MSDA_WARPS + warp; item < total; item += nwarps) {
+    const int hg = (int)(item % hgroups);
+    const int64_t bq = item / hgroups;
+    const int b = (int)(bq / Nq);
+    const int64_t slab = (bq * heads + hg * 4) * LP;
+    const float4 *gl = reinterpret_cast<const float4 *>(loc + slab * 2);
+    const float4 *gw = reinterpret_cast<const float4 *>(aw + slab);
+    for (int v = lane; v < 2 * LP; v += 32) reinterpret_cast<float4 *>(sloc)[v] = __ldg(gl + v);
+    for (int v = lane; v < LP; v += 32) reinterpret_cast<float4 *>(sw)[v] = __ldg(gw + v);
+    __syncwarp();
+    const int head = hg * 4 + g;
+    const float4 go = load4<T>(gout + bq * vstride + head * 32 + t * 4);
+    const float *ml = sloc + g * 2 * LP;
+    const float *mw = sw + g * LP;
+    for (int l = 0; l < L; ++l) {
+      const int Hl = lv.h[l], Wl = lv.w[l];
+      const int64_t voff = ((int64_t)b * Nv + lv.start[l]) * vstride + head * 32 + t * 4;
+      for (int p = 0; p < P; ++p) {
+        const float2 xy = *reinterpret_cast<const float2 *>(ml + (l * P + p) * 2);
+        const float wgt = mw[l * P + p];
+        const float h_im = xy.y * Hl - 0.5f, w_im = xy.x * Wl - 0.5f;
+        float gx = 0.f, gy = 0.f, ga = 0.f;
+        if (h_im > -1.f && w_im > -1.f && h_im < Hl && w_im < Wl) {  // uniform within the 8-lane group
+          const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+          const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+          const bool h0 = h_low >= 0, h1 = h_low + 1 <= Hl - 1, w0 = w_low >= 0, w1 = w_low + 1 <= Wl - 1;
+          const int64_t o00 = voff + ((int64_t)h_low * Wl + w_low) * vstride;
+          const float4 tw = make_float4(go.x * wgt, go.y * wgt, go.z * wgt, go.w * wgt);  // top_grad * attn_weight
+          float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+          float gh_w = 0.f, gw_w = 0.f;  // sum_c tw_c * d val_c / d{h,w}
+          auto corner = [&](bool ok, int64_t off, float wc, float dh, float dw) {
+            if (!ok) return;
+            const float4 v = load4<T>(value + off);
+            const float tv = dot4(tw, v);
+            gh_w = fmaf(dh, tv, gh_w);
+            gw_w = fmaf(dw, tv, gw_w);
+            fma4(val, wc, v);
+            atomicAdd(reinterpret_cast<float4 *>(gvalue + off), make_float4(wc * tw.x, wc * tw.y, wc * tw.z, wc * tw.w));
+          };
+          corner(h0 && w0, o00, hh * hw, -hw, -hh);
+          corner(h0 && w1, o00 + vstride, hh * lw, -lw, hh);
+          corner(h1 && w0, o00 + (int64_t)Wl * vstride, lh * hw, hw, -lh);
+          corner(h1 && w1, o00 + (int64_t)(Wl + 1) * vstride, lh * lw, lw, lh);
+          gx = Wl * gw_w;
+          gy = Hl * gh_w;
+          ga = dot4(go, val);
+        }
+        gx = group_sum8(gx);
+        gy = group_sum8(gy);
+        ga = group_sum8(ga);
+        if (t == 0) {
+          sgl[g * 2 * LP + (l * P + p) * 2] = gx;
+          sgl[g * 2 * LP + (l * P + p) * 2 + 1] = gy;
+          sgw[g * LP + l * P + p] = ga;
+        }
+      }
+    }
+    __syncwarp();
+    float4 *ogl = reinterpret_cast<float4 *>(gloc + slab * 2);
+    float4 *ogw = reinterpret_cast<float4 *>(gaw + slab);
+    for (int v = lane; v < 2 * LP; v += 32) ogl[v] = reinterpret_cast<const float4 *>(sgl)[v];
+    for (int v = lane; v < LP; v += 32) ogw[v] = reinterpret_cast<const float4 *>(sgw)[v];
+    __syncwarp();
+  }
+}
+
+static int msda_check(const char *fn, int B, int Nv, int Nq, int heads, int L, int P, int dtype) {
+  RSC_CHECK_ARG(B > 0 && Nv > 0 && Nq > 0, "%s: empty tensor (B=%d,Nv=%d,Nq=%d)", fn, B, Nv, Nq);
+  RSC_CHECK_ARG(heads > 0 && heads % 4 == 0, "%s: num_heads must be a multiple of 4 (got %d)", fn, heads);
+  RSC_CHECK_ARG(L > 0 && L <= MSDA_MAX_L && P > 0 && L * P <= MSDA_MAX_LP, "%s: need L<=%d, L*P<=%d (L=%d,P=%d)", fn,
+                MSDA_MAX_L, MSDA_MAX_LP, L, P);
+  RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "%s: bad dtype %d", fn, dtype);
+  return RSC_OK;
+}
+
+static int msda_grid(int64_t items) {
+  int64_t blocks = (items + MSDA_WARPS - 1) / MSDA_WARPS;
+  int64_t cap = (int64_t)kNumSMs * 32;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace rsc
+
+using namespace rsc;
+
+extern "C" int rsc_msda_fwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                            const float *sampling_loc, const float *attn_weight, void *out, int B, int Nv, int Nq,
+                            int heads, int L, int P, int im2col_step, int dtype, void *stream) {
+  (void)im2col_step;
+  if (int e = msda_check("rsc_msda_fwd", B, Nv, Nq, heads, L, P, dtype)) return e;
+  RSC_CHECK_ARG(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out,
+                "rsc_msda_fwd: null pointer");
+  int64_t items = (int64_t)B * Nq * (heads / 4);
+  size_t smem = sizeof(float) * MSDA_WARPS * 12 * L * P;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RSC_F32)
+    msda_fwd_kernel<float><<<msda_grid(items), MSDA_WARPS * 32, smem, st>>>(
+        (const float *)value, spatial_shapes, level_start_index, sampling_loc, attn_weight, (float *)out, B, Nv, Nq,
+        heads, L, P);
+  else
+    msda_fwd_kernel<__nv_bfloat16><<<msda_grid(items), MSDA_WARPS * 32, smem, st>>>(
+        (const __nv_bfloat16 *)value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+        (__nv_bfloat16 *)out, B, Nv, Nq, heads, L, P);
+  RSC_CHECK_LAUNCH("rsc_msda_fwd");
+  return RSC_OK;
+}
+
+extern "C" int rsc_msda_bwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                            const float *sampling_loc, const float *attn_weight, const void *grad_out,
+                            float *grad_value, float *grad_loc, float *grad_weight, int B, int Nv, int Nq, int heads,
+                            int L, int P, int im2col_step, int dtype, void *stream) {
+  (void)im2col_step;
+  if (int e = msda_check("rsc_msda_bwd", B, Nv, Nq, heads, L, P, dtype)) return e;
+  RSC_CHECK_ARG(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && grad_out &&
+                    grad_value && grad_loc && grad_weight,
+                "rsc_msda_bwd: null pointer");
+  int64_t items = (int64_t)B * Nq * (heads / 4);
+  size_t smem = sizeof(float) * MSDA_WARPS * 24 * L * P;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RSC_F32)
+    msda_bwd_kernel<float><<<msda_grid(items), MSDA_WARPS * 32, smem, st>>>(
+        (const float *)value, spatial_shapes, level_start_index, sampling_loc, attn_weight, (const float *)grad_out,
+        grad_value, grad_loc, grad_weight, B, Nv, Nq, heads, L, P);
+  else
+    msda_bwd_kernel<__nv_bfloat16><<<msda_grid(items), MSDA_WARPS * 32, smem, st>>>(
+        (const __nv_bfloat16 *)value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+        (const __nv_bfloat16 *)grad_out, grad_value, grad_loc, grad_weight, B, Nv, Nq, heads, L, P);
+  RSC_CHECK_LAUNCH("rsc_msda_bwd");
+  return RSC_OK;
+}

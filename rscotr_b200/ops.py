@@ -1,0 +1,360 @@
+"""torch.autograd wrappers over the C-ABI kernels (include/rscotr.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; all arithmetic
+of these ops happens in librscotr_b200.so.  Every op raises on a non-CUDA
+tensor -- there is deliberately no CPU / eager fallback.
+"""
+import torch
+
+from . import _lib
+from ._lib import RSC_BF16, RSC_F32, call
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return RSC_F32
+    if t.dtype == torch.bfloat16:
+        return RSC_BF16
+    raise TypeError('rscotr_b200 kernels take float32 or bfloat16 activations, got %s' % t.dtype)
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('rscotr_b200 ops run on CUDA tensors only (no CPU fallback)')
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+# ---------------------------------------------------------------------------
+# window index maps / partition / reverse        
+# ---------------------------------------------------------------------------
+def _nwin(H, W, ws):
+    return ((H + ws - 1) // ws) * ((W + ws - 1) // ws)
+
+
+def window_index_partition(B, H, W, ws, shift, device='cuda'):
+    out = torch.empty(B * _nwin(H, W, ws) * ws * ws, dtype=torch.int64, device=device)
+    _cuda(out)
+    with torch.cuda.device(out.device):
+        call('rsc_window_index_partition', out.data_ptr(), B, H, W, ws, shift, _stream())
+    return out
+
+
+def window_index_reverse(B, H, W, ws, shift, device='cuda'):
+    out = torch.empty(B * H * W, dtype=torch.int64, device=device)
+    _cuda(out)
+    with torch.cuda.device(out.device):
+        call('rsc_window_index_reverse', out.data_ptr(), B, H, W, ws, shift, _stream())
+    return out
+
+
+def _partition_raw(x, ws, shift):
+    B, H, W, C = x.shape
+    out = torch.empty(B * _nwin(H, W, ws), ws * ws, C, dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        call('rsc_window_partition', x.data_ptr(), out.data_ptr(), B, H, W, C, ws, shift, _dt(x), _stream())
+    return out
+
+
+def _reverse_raw(win, B, H, W, ws, shift):
+    C = win.shape[-1]
+    out = torch.empty(B, H, W, C, dtype=win.dtype, device=win.device)
+    with torch.cuda.device(win.device):
+        call('rsc_window_reverse', win.data_ptr(), out.data_ptr(), B, H, W, C, ws, shift, _dt(win), _stream())
+    return out
+
+
+class _WindowPartition(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ws, shift):
+        _cuda(x)
+        ctx.meta = (x.shape, ws, shift)
+        return _partition_raw(x.contiguous(), ws, shift)
+
+    @staticmethod
+    def backward(ctx, g):
+        (B, H, W, C), ws, shift = ctx.meta
+        return _reverse_raw(g.contiguous(), B, H, W, ws, shift), None, None
+
+
+class _WindowReverse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, win, B, H, W, ws, shift):
+        _cuda(win)
+        ctx.meta = (ws, shift)
+        return _reverse_raw(win.contiguous(), B, H, W, ws, shift)
+
+    @staticmethod
+    def backward(ctx, g):
+        ws, shift = ctx.meta
+        return _partition_raw(g.contiguous(), ws, shift), None, None, None, None, None
+
+
+def window_partition(x, ws, shift=0):
+    """(B,H,W,C) -> (B*nW, ws*ws, C): pad + roll(-shift) + window_partition."""
+    return _WindowPartition.apply(x, ws, shift)
+
+
+def window_reverse(windows, B, H, W, ws, shift=0):
+    """(B*nW, ws*ws, C) -> (B,H,W,C): window_reverse + roll(+shift) + crop."""
+    return _WindowReverse.apply(windows, B, H, W, ws, shift)
+
+
+# ---------------------------------------------------------------------------
+# fused shifted-window attention core            
+# ---------------------------------------------------------------------------
+class _WMSA(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, qkv_bias, table, H, W, heads, ws, shift, scale):
+        _cuda(qkv, table)
+        B = qkv.shape[0]
+        C = qkv.shape[-1] // 3
+        qkv = qkv.contiguous()
+        bias32 = _f32(qkv_bias)
+        table32 = _f32(table)
+        out = torch.empty(B, H * W, C, dtype=qkv.dtype, device=qkv.device)
+        with torch.cuda.device(qkv.device):
+            call('rsc_wmsa_fwd', qkv.data_ptr(), _p(bias32), table32.data_ptr(), out.data_ptr(), B, H, W, C, heads,
+                 ws, shift, scale, _dt(qkv), _stream())
+        ctx.save_for_backward(qkv, bias32, table32)
+        ctx.meta = (B, H, W, C, heads, ws, shift, scale, qkv_bias is not None and qkv_bias.dtype, table.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, bias32, table32 = ctx.saved_tensors
+        B, H, W, C, heads, ws, shift, scale, bias_dtype, table_dtype = ctx.meta
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        dtable = torch.zeros_like(table32)
+        dbias = torch.zeros_like(bias32) if bias32 is not None else None
+        with torch.cuda.device(qkv.device):
+            call('rsc_wmsa_bwd', qkv.data_ptr(), _p(bias32), table32.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
+                 dtable.data_ptr(), _p(dbias), B, H, W, C, heads, ws, shift, scale, _dt(qkv), _stream())
+        if dbias is not None:
+            dbias = dbias.to(bias_dtype)
+        return dqkv, dbias, dtable.to(table_dtype), None, None, None, None, None, None
+
+
+def wmsa(qkv, qkv_bias, table, hw, heads, ws=7, shift=0, scale=None):
+    """qkv (B, H*W, 3C) un-padded tokens -> (B, H*W, C).
+
+    qkv_bias: the qkv Linear's bias (value of a zero-padded token's row) or None;
+    table: relative_position_bias_table ((2ws-1)^2, heads)."""
+    H, W = hw
+    C = qkv.shape[-1] // 3
+    if scale is None:
+        scale = (C // heads) ** -0.5
+    return _WMSA.apply(qkv, qkv_bias, table, H, W, heads, ws, shift, float(scale))
+
+
+# ---------------------------------------------------------------------------
+# PatchMerging gather + LayerNorm                 
+# ---------------------------------------------------------------------------
+class _PatchMergeLN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, H, W, eps):
+        _cuda(x, gamma, beta)
+        B, L, C = x.shape
+        x = x.contiguous()
+        g32, b32 = _f32(gamma), _f32(beta)
+        Ho, Wo = (H + 1) // 2, (W + 1) // 2
+        y = torch.empty(B, Ho * Wo, 4 * C, dtype=x.dtype, device=x.device)
+        mean = torch.empty(B * Ho * Wo, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        with torch.cuda.device(x.device):
+            call('rsc_patch_merge_ln_fwd', x.data_ptr(), g32.data_ptr(), b32.data_ptr(), y.data_ptr(),
+                 mean.data_ptr(), rstd.data_ptr(), B, H, W, C, eps, _dt(x), _stream())
+        ctx.save_for_backward(x, g32, mean, rstd)
+        ctx.meta = (B, H, W, C, gamma.dtype, beta.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g32, mean, rstd = ctx.saved_tensors
+        B, H, W, C, gdt, bdt = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dg = torch.zeros(4 * C, dtype=torch.float32, device=x.device)
+        db = torch.zeros_like(dg)
+        with torch.cuda.device(x.device):
+            call('rsc_patch_merge_ln_bwd', x.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                 dy.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), B, H, W, C, _dt(x), _stream())
+        return dx, dg.to(gdt), db.to(bdt), None, None, None
+
+
+def patch_merge_ln(x, hw, gamma, beta, eps=1e-5):
+    """x (B,H*W,C) -> LayerNorm(unfold2x2(x)) (B, ceil(H/2)*ceil(W/2), 4C)."""
+    return _PatchMergeLN.apply(x, gamma, beta, hw[0], hw[1], float(eps))
+
+
+# ---------------------------------------------------------------------------
+# multi-scale deformable attention                
+# ---------------------------------------------------------------------------
+class MultiScaleDeformableAttnFunction(torch.autograd.Function):
+    """Same call signature as mmcv.ops.multi_scale_deform_attn.
+    MultiScaleDeformableAttnFunction.apply(value, value_spatial_shapes,
+    value_level_start_index, sampling_locations, attention_weights, im2col_step)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                im2col_step=64):
+        _cuda(value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights)
+        B, Nv, heads, D = value.shape
+        _, Nq, _, L, P, _ = sampling_locations.shape
+        if D != 32:
+            raise RuntimeError('rsc_msda: head dim must be 32, got %d' % D)
+        if int(im2col_step) <= 0 or B % min(B, int(im2col_step)) != 0:
+            raise RuntimeError('batch(%d) must divide im2col_step(%d)' % (B, im2col_step))
+        value = value.contiguous()
+        shapes = value_spatial_shapes.to(torch.int64).contiguous()
+        starts = value_level_start_index.to(torch.int64).contiguous()
+        loc = sampling_locations.float().contiguous()
+        aw = attention_weights.float().contiguous()
+        out = torch.empty(B, Nq, heads * D, dtype=value.dtype, device=value.device)
+        with torch.cuda.device(value.device):
+            call('rsc_msda_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), loc.data_ptr(),
+                 aw.data_ptr(), out.data_ptr(), B, Nv, Nq, heads, L, P, int(im2col_step), _dt(value), _stream())
+        ctx.save_for_backward(value, shapes, starts, loc, aw)
+        ctx.meta = (int(im2col_step), sampling_locations.dtype, attention_weights.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        value, shapes, starts, loc, aw = ctx.saved_tensors
+        im2col_step, loc_dt, aw_dt = ctx.meta
+        B, Nv, heads, D = value.shape
+        _, Nq, _, L, P, _ = loc.shape
+        grad_output = grad_output.contiguous()
+        gv = torch.zeros(value.shape, dtype=torch.float32, device=value.device)
+        gl = torch.empty_like(loc)
+        ga = torch.empty_like(aw)
+        with torch.cuda.device(value.device):
+            call('rsc_msda_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), loc.data_ptr(),
+                 aw.data_ptr(), grad_output.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), B, Nv, Nq, heads,
+                 L, P, im2col_step, _dt(value), _stream())
+        return gv.to(value.dtype), None, None, gl.to(loc_dt), ga.to(aw_dt), None
+
+
+def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step=64):
+    return MultiScaleDeformableAttnFunction.apply(value, spatial_shapes, level_start_index, sampling_locations,
+                                                  attention_weights, im2col_step)
+
+
+# ---------------------------------------------------------------------------
+# global average pool                             
+# ---------------------------------------------------------------------------
+class _GAP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, channels_last):
+        _cuda(x)
+        x = x.contiguous()
+        if channels_last:
+            B, HW, C = x.shape
+        else:
+            B, C = x.shape[:2]
+            HW = x[0, 0].numel()
+        y = torch.empty(B, C, dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            call('rsc_gap_fwd', x.data_ptr(), y.data_ptr(), B, C, HW, int(channels_last), _dt(x), _stream())
+        ctx.meta = (x.shape, B, C, HW, channels_last)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, B, C, HW, channels_last = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty(shape, dtype=dy.dtype, device=dy.device)
+        with torch.cuda.device(dy.device):
+            call('rsc_gap_bwd', dy.data_ptr(), dx.data_ptr(), B, C, HW, int(channels_last), _dt(dy), _stream())
+        return dx, None
+
+
+def global_avg_pool(x, channels_last=False):
+    """x (B,C,H,W) [channels_last=False] or (B,L,C) [True] -> (B,C)."""
+    return _GAP.apply(x, channels_last)
+
+
+# ---------------------------------------------------------------------------
+# bilinear resize, align_corners=False            
+# ---------------------------------------------------------------------------
+class _Bilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Ho, Wo):
+        _cuda(x)
+        x = x.contiguous()
+        B, C, Hi, Wi = x.shape
+        y = torch.empty(B, C, Ho, Wo, dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            call('rsc_bilinear_fwd', x.data_ptr(), y.data_ptr(), B * C, Hi, Wi, Ho, Wo, _dt(x), _stream())
+        ctx.meta = (B, C, Hi, Wi, Ho, Wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, C, Hi, Wi, Ho, Wo = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty(B, C, Hi, Wi, dtype=dy.dtype, device=dy.device)
+        with torch.cuda.device(dy.device):
+            call('rsc_bilinear_bwd', dy.data_ptr(), dx.data_ptr(), B * C, Hi, Wi, Ho, Wo, _dt(dy), _stream())
+        return dx, None, None
+
+
+def bilinear_resize(x, size):
+    """F.interpolate(x, size=size, mode='bilinear', align_corners=False) for NCHW x."""
+    return _Bilinear.apply(x, int(size[0]), int(size[1]))
+
+
+# ---------------------------------------------------------------------------
+# sigmoid focal loss (element-wise)               
+# ---------------------------------------------------------------------------
+class SigmoidFocalLossFunction(torch.autograd.Function):
+    """mmcv.ops.focal_loss.SigmoidFocalLossFunction with weight=None, reduction='none'."""
+
+    @staticmethod
+    def forward(ctx, input, target, gamma=2.0, alpha=0.25):
+        _cuda(input, target)
+        input = input.contiguous()
+        target = target.to(torch.int64).contiguous()
+        N, C = input.shape
+        out = torch.empty(N, C, dtype=torch.float32, device=input.device)
+        with torch.cuda.device(input.device):
+            call('rsc_sigmoid_focal_loss_fwd', input.data_ptr(), target.data_ptr(), out.data_ptr(), N, C,
+                 float(gamma), float(alpha), _dt(input), _stream())
+        ctx.save_for_backward(input, target)
+        ctx.meta = (float(gamma), float(alpha))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, target = ctx.saved_tensors
+        gamma, alpha = ctx.meta
+        N, C = input.shape
+        gi = torch.empty(N, C, dtype=torch.float32, device=input.device)
+        with torch.cuda.device(input.device):
+            call('rsc_sigmoid_focal_loss_bwd', input.data_ptr(), target.data_ptr(), gi.data_ptr(), N, C, gamma, alpha,
+                 _dt(input), _stream())
+        return (gi * grad_output).to(input.dtype), None, None, None
+
+
+def sigmoid_focal_loss(input, target, gamma=2.0, alpha=0.25):
+    return SigmoidFocalLossFunction.apply(input, target, gamma, alpha)
+
+
+def launch_count():
+    return _lib.launch_count()
+
+
+def reset_launch_count():
+    _lib.reset_launch_count()

@@ -1,0 +1,331 @@
+"""GPU parity: every C-ABI kernel against the CPU oracle on seeded inputs.
+
+Tolerances: integer index maps bit exact; fp32 kernels within 1e-3 relative of
+the oracle (north_star); bf16 kernels against the oracle evaluated on the
+bf16-rounded inputs, within bf16 rounding of the outputs.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import swin as osw
+from oracle import transformer as otr
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from rscotr_b200 import ops
+    return ops
+
+
+def rel_err(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def assert_rel(a, b, tol, what=''):
+    e = rel_err(a, b)
+    assert e <= tol, '%s: relative error %.3e > %.1e' % (what, e, tol)
+
+
+GEOMS = [(1, 7, 7), (2, 8, 8), (2, 16, 16), (1, 25, 25), (1, 50, 50), (2, 10, 17), (1, 14, 21), (1, 4, 5)]
+
+
+# ---------------------------------------------------------------------------
+# a5: window index maps, bit exact
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('B,H,W', GEOMS + [(1, 200, 200), (3, 100, 100)])
+@pytest.mark.parametrize('shift', [0, 3])
+def test_window_index_bit_exact(B, H, W, shift):
+    ops = _ops()
+    want = osw.window_token_index(B, H, W, 7, shift)
+    got = ops.window_index_partition(B, H, W, 7, shift).cpu()
+    assert torch.equal(got, want)
+    # reverse map is the inverse on valid slots
+    rev = ops.window_index_reverse(B, H, W, 7, shift).cpu()
+    assert torch.equal(want[rev], torch.arange(B * H * W))
+
+
+@pytest.mark.parametrize('B,H,W', GEOMS)
+@pytest.mark.parametrize('shift', [0, 3])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_window_partition_reverse_exact(B, H, W, shift, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(H * 100 + W)
+    x = torch.randn(B, H, W, 32, generator=g).to(dtype)
+    ws = 7
+    pad_r, pad_b = (ws - W % ws) % ws, (ws - H % ws) % ws
+    xp = F.pad(x, (0, 0, 0, pad_r, 0, pad_b))
+    if shift:
+        xp = torch.roll(xp, (-shift, -shift), (1, 2))
+    want = osw.window_partition(xp, ws).view(-1, ws * ws, 32)
+    got = ops.window_partition(x.cuda(), ws, shift)
+    assert torch.equal(got.cpu(), want)          # pure data movement: bit exact
+    # reverse(partition(x)) == x
+    back = ops.window_reverse(got, B, H, W, ws, shift)
+    assert torch.equal(back.cpu(), x)
+    # oracle reverse chain
+    y = osw.window_reverse(want.view(-1, ws, ws, 32), xp.shape[1], xp.shape[2], ws)
+    if shift:
+        y = torch.roll(y, (shift, shift), (1, 2))
+    assert torch.equal(y[:, :H, :W].contiguous(), back.cpu())
+
+
+# ---------------------------------------------------------------------------
+# a3/a4: fused window attention vs oracle ShiftWindowMSA (qkv / proj GEMMs are
+# plain F.linear on both sides)
+# ---------------------------------------------------------------------------
+def _msa_state(C, heads, seed):
+    g = torch.Generator().manual_seed(seed)
+    sd = {
+        'attn.w_msa.qkv.weight': torch.randn(3 * C, C, generator=g) * C ** -0.5,
+        'attn.w_msa.qkv.bias': torch.randn(3 * C, generator=g) * 0.5,
+        'attn.w_msa.proj.weight': torch.randn(C, C, generator=g) * C ** -0.5,
+        'attn.w_msa.proj.bias': torch.randn(C, generator=g) * 0.1,
+        'attn.w_msa.relative_position_bias_table': torch.randn(169, heads, generator=g),
+    }
+    return sd
+
+
+def _run_msa_gpu(sd, x, hw, heads, shift, dtype):
+    ops = _ops()
+    p = {k: v.clone().cuda().requires_grad_(True) for k, v in sd.items()}
+    xg = x.clone().cuda().to(dtype).requires_grad_(True)
+    cast = (lambda t: t.to(dtype))
+    qkv = F.linear(xg, cast(p['attn.w_msa.qkv.weight']), cast(p['attn.w_msa.qkv.bias']))
+    o = ops.wmsa(qkv, p['attn.w_msa.qkv.bias'], p['attn.w_msa.relative_position_bias_table'], hw, heads, 7, shift)
+    y = F.linear(o, cast(p['attn.w_msa.proj.weight']), cast(p['attn.w_msa.proj.bias']))
+    return xg, p, y
+
+
+@pytest.mark.parametrize('B,H,W', GEOMS)
+@pytest.mark.parametrize('shift', [0, 3])
+@pytest.mark.parametrize('heads', [3, 4])
+def test_wmsa_fp32_fwd_bwd(B, H, W, shift, heads):
+    C = heads * 32
+    sd = _msa_state(C, heads, seed=H + W + shift)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, H * W, C, generator=g)
+    gy = torch.randn(B, H * W, C, generator=g)
+    # oracle
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    yo = osw.shift_window_msa(sdo, 'attn.', xo, (H, W), heads, 7, shift)
+    yo.backward(gy)
+    # kernel
+    xg, p, y = _run_msa_gpu(sd, x, (H, W), heads, shift, torch.float32)
+    y.backward(gy.cuda())
+    assert_rel(y, yo, 1e-3, 'out')
+    assert_rel(xg.grad, xo.grad, 1e-3, 'dx')
+    for k in sd:
+        assert_rel(p[k].grad, sdo[k].grad, 1e-3, 'd' + k)
+
+
+@pytest.mark.parametrize('B,H,W', [(2, 16, 16), (1, 25, 25), (2, 10, 17)])
+@pytest.mark.parametrize('shift', [0, 3])
+def test_wmsa_bf16_fwd_bwd(B, H, W, shift):
+    heads, C = 3, 96
+    sd = {k: v.bfloat16().float() for k, v in _msa_state(C, heads, seed=7).items()}
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, H * W, C, generator=g).bfloat16().float()
+    gy = torch.randn(B, H * W, C, generator=g).bfloat16().float()
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    yo = osw.shift_window_msa(sdo, 'attn.', xo, (H, W), heads, 7, shift)
+    yo.backward(gy)
+    xg, p, y = _run_msa_gpu(sd, x, (H, W), heads, shift, torch.bfloat16)
+    y.backward(gy.cuda().bfloat16())
+    assert_rel(y, yo, 2e-2, 'out')
+    assert_rel(xg.grad, xo.grad, 3e-2, 'dx')
+    assert_rel(p['attn.w_msa.relative_position_bias_table'].grad,
+               sdo['attn.w_msa.relative_position_bias_table'].grad, 3e-2, 'dtable')
+
+
+def test_wmsa_large_property():
+    """BASELINE size (stage 0 of 800^2: 200x200, C=96): shifting the INPUT by one
+    whole window (7 tokens) along W on a window-aligned grid permutes windows, so
+    the un-shifted attention output must be the same permutation (size
+    independent property; no oracle needed)."""
+    ops = _ops()
+    torch.manual_seed(0)
+    B, H, W, C, heads = 2, 196, 196, 96, 3
+    qkv = torch.randn(B, H, W, 3 * C, device='cuda')
+    table = torch.randn(169, heads, device='cuda')
+    o1 = ops.wmsa(qkv.view(B, H * W, -1), None, table, (H, W), heads, 7, 0).view(B, H, W, C)
+    o2 = ops.wmsa(torch.roll(qkv, 7, 2).contiguous().view(B, H * W, -1), None, table, (H, W), heads, 7, 0)
+    assert torch.equal(torch.roll(o1, 7, 2), o2.view(B, H, W, C))
+    # rows of softmax sum to one: with v == 1 the output is exactly ~1
+    qkv[..., 2 * C:] = 1.0
+    o3 = ops.wmsa(qkv.view(B, H * W, -1), None, table, (H, W), heads, 7, 3)
+    torch.testing.assert_close(o3, torch.ones_like(o3), rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------
+# a6: PatchMerging gather + LN
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('B,H,W,C', [(2, 8, 8, 96), (1, 9, 7, 96), (2, 10, 6, 192), (1, 5, 5, 384), (1, 4, 4, 512),
+                                     (1, 6, 6, 128)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_patch_merge_ln(B, H, W, C, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, H * W, C, generator=g)
+    gamma = 1 + 0.1 * torch.randn(4 * C, generator=g)
+    beta = 0.1 * torch.randn(4 * C, generator=g)
+    red = torch.randn(2 * C, 4 * C, generator=g) * (4 * C) ** -0.5
+    if dtype == torch.bfloat16:
+        x, red = x.bfloat16().float(), red.bfloat16().float()
+    sd = {'d.norm.weight': gamma.clone().requires_grad_(True), 'd.norm.bias': beta.clone().requires_grad_(True),
+          'd.reduction.weight': red.clone().requires_grad_(True)}
+    xo = x.clone().requires_grad_(True)
+    yo, hw = osw.patch_merging(sd, 'd.', xo, (H, W))
+    gy = torch.randn(yo.shape, generator=g)
+    yo.backward(gy)
+    xg = x.clone().cuda().to(dtype).requires_grad_(True)
+    gg, bg = gamma.clone().cuda().requires_grad_(True), beta.clone().cuda().requires_grad_(True)
+    y = F.linear(ops.patch_merge_ln(xg, (H, W), gg, bg), red.cuda().to(dtype))
+    y.backward(gy.cuda().to(dtype))
+    tol = 1e-3 if dtype == torch.float32 else 3e-2
+    assert hw == ((H + 1) // 2, (W + 1) // 2)
+    assert_rel(y, yo, tol, 'y')
+    assert_rel(xg.grad, xo.grad, tol, 'dx')
+    assert_rel(gg.grad, sd['d.norm.weight'].grad, tol, 'dgamma')
+    assert_rel(bg.grad, sd['d.norm.bias'].grad, tol, 'dbeta')
+
+
+# ---------------------------------------------------------------------------
+# a11: ms_deform_attn
+# ---------------------------------------------------------------------------
+def _msda_inputs(B, Nq, heads, shapes, P, seed, spread=0.25):
+    g = torch.Generator().manual_seed(seed)
+    Nv = sum(h * w for h, w in shapes)
+    L = len(shapes)
+    value = torch.randn(B, Nv, heads, 32, generator=g)
+    loc = torch.rand(B, Nq, heads, L, P, 2, generator=g) * (1 + 2 * spread) - spread
+    w = torch.rand(B, Nq, heads, L, P, generator=g).flatten(-2).softmax(-1).view(B, Nq, heads, L, P)
+    starts = [0]
+    for h, ww in shapes[:-1]:
+        starts.append(starts[-1] + h * ww)
+    return value, loc, w, torch.tensor(shapes), torch.tensor(starts)
+
+
+MSDA_CASES = [
+    (2, 37, 8, [(12, 9), (6, 5), (3, 3), (2, 2)], 4),
+    (1, 5, 4, [(5, 7)], 2),
+    (2, 300, 8, [(25, 25), (13, 13), (7, 7), (4, 4)], 4),
+    (1, 64, 8, [(8, 8), (4, 4)], 8),
+]
+
+
+@pytest.mark.parametrize('B,Nq,heads,shapes,P', MSDA_CASES)
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_msda_fwd_bwd(B, Nq, heads, shapes, P, dtype):
+    ops = _ops()
+    value, loc, w, ss, st = _msda_inputs(B, Nq, heads, shapes, P, seed=Nq)
+    if dtype == torch.bfloat16:
+        value = value.bfloat16().float()
+    vo, lo, wo = (t.clone().requires_grad_(True) for t in (value, loc, w))
+    yo = otr.ms_deform_attn_core(vo, shapes, lo, wo)
+    g = torch.Generator().manual_seed(3)
+    gy = torch.randn(yo.shape, generator=g)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    yo.backward(gy)
+    vg = value.clone().cuda().to(dtype).requires_grad_(True)
+    lg, wg = loc.clone().cuda().requires_grad_(True), w.clone().cuda().requires_grad_(True)
+    y = ops.ms_deform_attn(vg, ss.cuda(), st.cuda(), lg, wg, 64)
+    y.backward(gy.cuda().to(dtype))
+    tol = 1e-3 if dtype == torch.float32 else 1.5e-2
+    assert_rel(y, yo, tol, 'out')
+    assert_rel(vg.grad, vo.grad, tol, 'dvalue')
+    assert_rel(lg.grad, lo.grad, tol, 'dloc')
+    assert_rel(wg.grad, wo.grad, tol, 'dweight')
+
+
+def test_msda_full_size_linearity():
+    """BASELINE size (N = 13294 tokens, 4 levels of an 800^2 image): the op is
+    linear in value and in the attention weights; out-of-range samples give 0."""
+    ops = _ops()
+    shapes = [(100, 100), (50, 50), (25, 25), (13, 13)]
+    value, loc, w, ss, st = _msda_inputs(1, 13294, 8, shapes, 4, seed=11)
+    value, loc, w, ss, st = (t.cuda() for t in (value, loc, w, ss, st))
+    y1 = ops.ms_deform_attn(value, ss, st, loc, w)
+    y2 = ops.ms_deform_attn(2 * value, ss, st, loc, 0.5 * w)
+    torch.testing.assert_close(y1, y2, rtol=1e-5, atol=1e-5)
+    y0 = ops.ms_deform_attn(value, ss, st, loc + 5.0, w)
+    assert torch.count_nonzero(y0) == 0
+    # constant value field + in-range samples + weights summing to 1 -> constant out
+    inr = loc.clamp(0.2, 0.8)
+    yc = ops.ms_deform_attn(torch.ones_like(value), ss, st, inr, w)
+    torch.testing.assert_close(yc, torch.ones_like(yc), rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------
+# a12: GAP,  a18/a19: bilinear,  a16: focal
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_gap(dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 768, 5, 7, generator=g).to(dtype)
+    for cl in (False, True):
+        xi = x.flatten(2).transpose(1, 2).contiguous() if cl else x
+        xo = xi.float().clone().requires_grad_(True)
+        yo = xo.mean(1) if cl else xo.mean((2, 3))
+        gy = torch.randn(yo.shape, generator=g)
+        yo.backward(gy)
+        xg = xi.clone().cuda().requires_grad_(True)
+        y = ops.global_avg_pool(xg, cl)
+        y.backward(gy.cuda().to(dtype))
+        tol = 1e-5 if dtype == torch.float32 else 1e-2
+        assert_rel(y, yo, tol, 'gap')
+        assert_rel(xg.grad, xo.grad, tol, 'dgap')
+
+
+@pytest.mark.parametrize('src,dst', [((13, 13), (25, 25)), ((25, 25), (50, 50)), ((100, 100), (13, 13)),
+                                     ((10, 12), (80, 96)), ((50, 50), (25, 25)), ((7, 9), (7, 9)), ((1, 1), (4, 4))])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_bilinear(src, dst, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(src[0] + dst[0])
+    x = torch.randn(2, 5, *src, generator=g).to(dtype)
+    xo = x.float().clone().requires_grad_(True)
+    yo = F.interpolate(xo, size=dst, mode='bilinear', align_corners=False)
+    gy = torch.randn(yo.shape, generator=g).to(dtype)
+    yo.backward(gy.float())
+    xg = x.clone().cuda().requires_grad_(True)
+    y = ops.bilinear_resize(xg, dst)
+    y.backward(gy.cuda())
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert_rel(y, yo, tol, 'bilinear')
+    assert_rel(xg.grad, xo.grad, tol, 'dbilinear')
+
+
+def _py_sigmoid_focal_loss(pred, target, gamma=2.0, alpha=0.25):
+    """mmdet py_sigmoid_focal_loss (the reference's CPU branch), reduction none."""
+    p = pred.sigmoid()
+    t = F.one_hot(target, pred.shape[1] + 1)[:, :pred.shape[1]].type_as(pred)
+    pt = (1 - p) * t + p * (1 - t)
+    fw = (alpha * t + (1 - alpha) * (1 - t)) * pt.pow(gamma)
+    return F.binary_cross_entropy_with_logits(pred, t, reduction='none') * fw
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_sigmoid_focal_loss(dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(600, 20, generator=g) * 3).to(dtype)
+    t = torch.randint(0, 21, (600,), generator=g)
+    xo = x.float().clone().requires_grad_(True)
+    lo = _py_sigmoid_focal_loss(xo, t)
+    gy = torch.rand(lo.shape, generator=g)
+    lo.backward(gy)
+    xg = x.clone().cuda().requires_grad_(True)
+    l = ops.sigmoid_focal_loss(xg, t.cuda())
+    l.backward(gy.cuda())
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert_rel(l, lo, tol, 'focal')
+    assert_rel(xg.grad, xo.grad, tol, 'dfocal')
