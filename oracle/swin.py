@@ -252,3 +252,58 @@ def swin_init_state(embed_dims=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24)
             sd[f'{pre}norm{i}.weight'] = torch.ones(C)
             sd[f'{pre}norm{i}.bias'] = torch.zeros(C)
     return sd
+
+
+# ----------------------------------------------------------------------------
+# attention core on an externally computed qkv tensor (oracle for rsc_wmsa_*)
+# ----------------------------------------------------------------------------
+def wmsa_core(qkv, qkv_bias, table, hw, num_heads, ws=7, shift=0, scale=None):
+    """qkv (B, H*W, 3C) of the UN-padded tokens -> (B, H*W, C).
+
+    Same chain as shift_window_msa between the qkv and proj Linears: a padded
+    token is a zero row after norm1, so its qkv row equals the qkv bias (zeros
+    if the Linear has no bias)."""
+    B, L, C3 = qkv.shape
+    C = C3 // 3
+    H, W = hw
+    hd = C // num_heads
+    if scale is None:
+        scale = hd ** -0.5
+    x = qkv.view(B, H, W, C3)
+    pad_r = (ws - W % ws) % ws
+    pad_b = (ws - H % ws) % ws
+    if pad_r or pad_b:
+        fill = qkv_bias if qkv_bias is not None else qkv.new_zeros(C3)
+        xp = fill.to(qkv.dtype).view(1, 1, 1, C3).expand(B, H + pad_b, W + pad_r, C3).clone()
+        xp[:, :H, :W] = x
+        x = xp
+    Hp, Wp = x.shape[1], x.shape[2]
+    mask = None
+    if shift > 0:
+        x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
+        mask = shift_attn_mask(Hp, Wp, ws, shift, x.dtype)
+    win = window_partition(x, ws).view(-1, ws * ws, C3)
+    B_, N = win.shape[0], ws * ws
+    q, k, v = win.reshape(B_, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
+    attn = (q * scale) @ k.transpose(-2, -1)
+    index = relative_position_index(ws)
+    attn = attn + table[index.view(-1)].view(N, N, -1).permute(2, 0, 1).unsqueeze(0)
+    if mask is not None:
+        nW = mask.shape[0]
+        attn = (attn.view(B_ // nW, nW, num_heads, N, N) + mask.unsqueeze(1).unsqueeze(0)).view(-1, num_heads, N, N)
+    out = (attn.softmax(-1) @ v).transpose(1, 2).reshape(B_, ws, ws, C)
+    y = window_reverse(out, Hp, Wp, ws)
+    if shift > 0:
+        y = torch.roll(y, shifts=(shift, shift), dims=(1, 2))
+    return y[:, :H, :W, :].reshape(B, H * W, C)
+
+
+def patch_merge_ln(x, hw, gamma, beta, eps=1e-5):
+    """unfold(2,2) in nn.Unfold channel order + LayerNorm(4C) (oracle for rsc_patch_merge_ln_*)."""
+    B, L, C = x.shape
+    H, W = hw
+    x = x.view(B, H, W, C).permute(0, 3, 1, 2)
+    if H % 2 or W % 2:
+        x = F.pad(x, (0, W % 2, 0, H % 2))
+    x = F.unfold(x, kernel_size=2, stride=2).transpose(1, 2)
+    return F.layer_norm(x, (4 * C,), gamma, beta, eps)

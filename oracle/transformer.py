@@ -88,7 +88,7 @@ def msda_init_state(pre, embed_dims=256, num_heads=8, num_levels=4, num_points=4
     return sd
 
 
-def msda(sd, pre, query, value=None, identity=None, query_pos=None, key_padding_mask=None,
+def msda(sd, pre, query, key=None, value=None, identity=None, query_pos=None, key_padding_mask=None,
          reference_points=None, spatial_shapes=None, level_start_index=None,
          num_heads=8, num_levels=4, num_points=4, **_ignored):
     """mmcv MultiScaleDeformableAttention.forward, batch_first=False.

@@ -1,0 +1,456 @@
+"""Transformer bricks with the registry names / state-dict layout the reference
+configs expect (mmcv 1.6.1 `cnn/bricks/transformer.py`, `ops/multi_scale_deform_attn.py`,
+mmdet 2.25.1 `models/utils/{transformer,positional_encoding}.py`,
+`models/necks/channel_mapper.py`).
+
+The ms_deform_attn core runs through the C-ABI kernel (ops.ms_deform_attn);
+Linear / LayerNorm / Conv are library GEMMs.
+"""
+import copy
+import math
+import warnings
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..config import MODELS, build_from_cfg
+
+
+def build_activation(cfg):
+    cfg = dict(cfg or dict(type='ReLU'))
+    t = cfg.pop('type')
+    if t == 'ReLU':
+        return nn.ReLU(inplace=cfg.get('inplace', False))
+    if t == 'GELU':
+        return nn.GELU()
+    raise KeyError('unsupported activation %s' % t)
+
+
+def build_norm(cfg, num_features):
+    cfg = dict(cfg)
+    t = cfg.pop('type')
+    if t == 'LN':
+        return nn.LayerNorm(num_features, **cfg)
+    if t == 'GN':
+        return nn.GroupNorm(cfg.pop('num_groups'), num_features, **cfg)
+    if t in ('BN', 'SyncBN'):      # per-rank BN (no forward-time collectives)
+        return nn.BatchNorm2d(num_features, **{k: v for k, v in cfg.items() if k != 'requires_grad'})
+    raise KeyError('unsupported norm %s' % t)
+
+
+def norm_abbr(cfg):
+    return {'LN': 'ln', 'GN': 'gn', 'BN': 'bn', 'SyncBN': 'bn'}[cfg['type']]
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per sample (mmcv DropPath).  `forced_mask` lets parity
+    tests inject the keep mask."""
+
+    def __init__(self, drop_prob=0.):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.forced_mask = None
+
+    def forward(self, x):
+        if self.forced_mask is not None:
+            m = self.forced_mask.to(x.dtype)
+            return x * m.view(-1, *([1] * (x.dim() - 1)))
+        if self.drop_prob == 0. or not self.training:
+            return x
+        keep = 1 - self.drop_prob
+        shape = (x.shape[0],) + (1,) * (x.dim() - 1)
+        mask = keep + torch.rand(shape, dtype=x.dtype, device=x.device)
+        return x.div(keep) * mask.floor()
+
+
+def build_dropout(cfg):
+    if cfg is None:
+        return nn.Identity()
+    cfg = dict(cfg)
+    t = cfg.pop('type')
+    if t == 'DropPath':
+        return DropPath(cfg.get('drop_prob', 0.))
+    if t == 'Dropout':
+        return nn.Dropout(cfg.get('drop_prob', cfg.get('p', 0.5)))
+    raise KeyError(t)
+
+
+@MODELS.register_module()
+class FFN(nn.Module):
+    def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2, act_cfg=dict(type='ReLU', inplace=True),
+                 ffn_drop=0., dropout_layer=None, add_identity=True, init_cfg=None, **kwargs):
+        super().__init__()
+        assert num_fcs >= 2
+        self.embed_dims = embed_dims
+        layers = []
+        in_ch = embed_dims
+        for _ in range(num_fcs - 1):
+            layers.append(nn.Sequential(nn.Linear(in_ch, feedforward_channels), build_activation(act_cfg),
+                                        nn.Dropout(ffn_drop)))
+            in_ch = feedforward_channels
+        layers.append(nn.Linear(feedforward_channels, embed_dims))
+        layers.append(nn.Dropout(ffn_drop))
+        self.layers = nn.Sequential(*layers)
+        self.dropout_layer = build_dropout(dropout_layer)
+        self.add_identity = add_identity
+
+    def forward(self, x, identity=None):
+        out = self.layers(x)
+        if not self.add_identity:
+            return self.dropout_layer(out)
+        if identity is None:
+            identity = x
+        return identity + self.dropout_layer(out)
+
+
+@MODELS.register_module()
+class MultiheadAttention(nn.Module):
+    def __init__(self, embed_dims, num_heads, attn_drop=0., proj_drop=0., dropout_layer=dict(type='Dropout', drop_prob=0.),
+                 init_cfg=None, batch_first=False, **kwargs):
+        super().__init__()
+        if 'dropout' in kwargs:
+            attn_drop = kwargs['dropout']
+            dropout_layer = dict(dropout_layer or dict(type='Dropout'))
+            dropout_layer['drop_prob'] = kwargs.pop('dropout')
+        self.embed_dims = embed_dims
+        self.num_heads = num_heads
+        self.batch_first = batch_first
+        self.attn = nn.MultiheadAttention(embed_dims, num_heads, attn_drop, **kwargs)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.dropout_layer = build_dropout(dropout_layer)
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None, attn_mask=None,
+                key_padding_mask=None, **kwargs):
+        if key is None:
+            key = query
+        if value is None:
+            value = key
+        if identity is None:
+            identity = query
+        if key_pos is None and query_pos is not None and query_pos.shape == key.shape:
+            key_pos = query_pos
+        if query_pos is not None:
+            query = query + query_pos
+        if key_pos is not None:
+            key = key + key_pos
+        if self.batch_first:
+            query, key, value = (t.transpose(0, 1) for t in (query, key, value))
+        out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask, key_padding_mask=key_padding_mask,
+                        need_weights=False)[0]
+        if self.batch_first:
+            out = out.transpose(0, 1)
+        return identity + self.dropout_layer(self.proj_drop(out))
+
+
+@MODELS.register_module()
+class MultiScaleDeformableAttention(nn.Module):
+    """mmcv MultiScaleDeformableAttention; the sampling core is rsc_msda_{fwd,bwd}."""
+
+    def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=4, im2col_step=64, dropout=0.1,
+                 batch_first=False, norm_cfg=None, init_cfg=None):
+        super().__init__()
+        if embed_dims % num_heads != 0:
+            raise ValueError('embed_dims must be divisible by num_heads, but got %d and %d' % (embed_dims, num_heads))
+        self.norm_cfg = norm_cfg
+        self.dropout = nn.Dropout(dropout)
+        self.batch_first = batch_first
+        self.im2col_step = im2col_step
+        self.embed_dims = embed_dims
+        self.num_levels = num_levels
+        self.num_heads = num_heads
+        self.num_points = num_points
+        self.sampling_offsets = nn.Linear(embed_dims, num_heads * num_levels * num_points * 2)
+        self.attention_weights = nn.Linear(embed_dims, num_heads * num_levels * num_points)
+        self.value_proj = nn.Linear(embed_dims, embed_dims)
+        self.output_proj = nn.Linear(embed_dims, embed_dims)
+        self.init_weights()
+
+    def init_weights(self):
+        nn.init.constant_(self.sampling_offsets.weight, 0.)
+        thetas = torch.arange(self.num_heads, dtype=torch.float32) * (2.0 * math.pi / self.num_heads)
+        grid_init = torch.stack([thetas.cos(), thetas.sin()], -1)
+        grid_init = (grid_init / grid_init.abs().max(-1, keepdim=True)[0]).view(self.num_heads, 1, 1, 2).repeat(
+            1, self.num_levels, self.num_points, 1)
+        for i in range(self.num_points):
+            grid_init[:, :, i, :] *= i + 1
+        self.sampling_offsets.bias.data = grid_init.view(-1)
+        nn.init.constant_(self.attention_weights.weight, 0.)
+        nn.init.constant_(self.attention_weights.bias, 0.)
+        nn.init.xavier_uniform_(self.value_proj.weight)
+        nn.init.constant_(self.value_proj.bias, 0.)
+        nn.init.xavier_uniform_(self.output_proj.weight)
+        nn.init.constant_(self.output_proj.bias, 0.)
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_padding_mask=None,
+                reference_points=None, spatial_shapes=None, level_start_index=None, **kwargs):
+        if value is None:
+            value = query
+        if identity is None:
+            identity = query
+        if query_pos is not None:
+            query = query + query_pos
+        if not self.batch_first:
+            query = query.permute(1, 0, 2)
+            value = value.permute(1, 0, 2)
+        bs, num_query, _ = query.shape
+        bs, num_value, _ = value.shape
+        value = self.value_proj(value)
+        if key_padding_mask is not None:
+            value = value.masked_fill(key_padding_mask[..., None], 0.0)
+        value = value.view(bs, num_value, self.num_heads, -1)
+        sampling_offsets = self.sampling_offsets(query).view(
+            bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
+        attention_weights = self.attention_weights(query).view(
+            bs, num_query, self.num_heads, self.num_levels * self.num_points)
+        attention_weights = attention_weights.float().softmax(-1).view(
+            bs, num_query, self.num_heads, self.num_levels, self.num_points)
+        sampling_offsets = sampling_offsets.float()
+        reference_points = reference_points.float()
+        if reference_points.shape[-1] == 2:
+            offset_normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1).float()
+            sampling_locations = reference_points[:, :, None, :, None, :] + \
+                sampling_offsets / offset_normalizer[None, None, None, :, None, :]
+        elif reference_points.shape[-1] == 4:
+            sampling_locations = reference_points[:, :, None, :, None, :2] + \
+                sampling_offsets / self.num_points * reference_points[:, :, None, :, None, 2:] * 0.5
+        else:
+            raise ValueError('Last dim of reference_points must be 2 or 4, but get %d instead.'
+                             % reference_points.shape[-1])
+        output = ops.ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                                    self.im2col_step)
+        output = self.output_proj(output)
+        if not self.batch_first:
+            output = output.permute(1, 0, 2)
+        return self.dropout(output) + identity
+
+
+@MODELS.register_module()
+class BaseTransformerLayer(nn.Module):
+    def __init__(self, attn_cfgs=None, ffn_cfgs=dict(type='FFN', embed_dims=256, feedforward_channels=1024, num_fcs=2,
+                                                     ffn_drop=0., act_cfg=dict(type='ReLU', inplace=True)),
+                 operation_order=None, norm_cfg=dict(type='LN'), init_cfg=None, batch_first=False, **kwargs):
+        super().__init__()
+        assert set(operation_order) <= {'self_attn', 'norm', 'ffn', 'cross_attn'}
+        num_attn = operation_order.count('self_attn') + operation_order.count('cross_attn')
+        if isinstance(attn_cfgs, dict):
+            attn_cfgs = [copy.deepcopy(attn_cfgs) for _ in range(num_attn)]
+        else:
+            assert num_attn == len(attn_cfgs)
+        self.num_attn = num_attn
+        self.operation_order = tuple(operation_order)
+        self.norm_cfg = norm_cfg
+        self.pre_norm = operation_order[0] == 'norm'
+        self.batch_first = batch_first
+        self.attentions = nn.ModuleList()
+        for cfg in attn_cfgs:
+            cfg = dict(cfg)
+            cfg.setdefault('batch_first', batch_first)
+            self.attentions.append(build_from_cfg(cfg, MODELS))
+        self.embed_dims = self.attentions[0].embed_dims
+        num_ffns = operation_order.count('ffn')
+        if isinstance(ffn_cfgs, dict):
+            ffn_cfgs = [copy.deepcopy(ffn_cfgs) for _ in range(num_ffns)]
+        self.ffns = nn.ModuleList()
+        for cfg in ffn_cfgs:
+            cfg = dict(cfg)
+            cfg.setdefault('type', 'FFN')
+            cfg['embed_dims'] = cfg.get('embed_dims', self.embed_dims) if 'embed_dims' in cfg else self.embed_dims
+            self.ffns.append(build_from_cfg(cfg, MODELS))
+        self.norms = nn.ModuleList([build_norm(norm_cfg, self.embed_dims) for _ in range(operation_order.count('norm'))])
+
+    def forward(self, query, key=None, value=None, query_pos=None, key_pos=None, attn_masks=None,
+                query_key_padding_mask=None, key_padding_mask=None, **kwargs):
+        norm_index = attn_index = ffn_index = 0
+        identity = query
+        if attn_masks is None:
+            attn_masks = [None for _ in range(self.num_attn)]
+        elif isinstance(attn_masks, torch.Tensor):
+            attn_masks = [copy.copy(attn_masks) for _ in range(self.num_attn)]
+        else:
+            assert len(attn_masks) == self.num_attn
+        for layer in self.operation_order:
+            if layer == 'self_attn':
+                temp_key = temp_value = query
+                query = self.attentions[attn_index](
+                    query, temp_key, temp_value, identity if self.pre_norm else None, query_pos=query_pos,
+                    key_pos=query_pos, attn_mask=attn_masks[attn_index], key_padding_mask=query_key_padding_mask,
+                    **kwargs)
+                attn_index += 1
+                identity = query
+            elif layer == 'norm':
+                query = self.norms[norm_index](query)
+                norm_index += 1
+            elif layer == 'cross_attn':
+                query = self.attentions[attn_index](
+                    query, key, value, identity if self.pre_norm else None, query_pos=query_pos, key_pos=key_pos,
+                    attn_mask=attn_masks[attn_index], key_padding_mask=key_padding_mask, **kwargs)
+                attn_index += 1
+                identity = query
+            elif layer == 'ffn':
+                query = self.ffns[ffn_index](query, identity if self.pre_norm else None)
+                ffn_index += 1
+        return query
+
+
+class TransformerLayerSequence(nn.Module):
+    def __init__(self, transformerlayers=None, num_layers=None, init_cfg=None):
+        super().__init__()
+        if isinstance(transformerlayers, dict):
+            transformerlayers = [copy.deepcopy(transformerlayers) for _ in range(num_layers)]
+        else:
+            assert isinstance(transformerlayers, list) and len(transformerlayers) == num_layers
+        self.num_layers = num_layers
+        self.layers = nn.ModuleList([build_from_cfg(dict(c), MODELS) for c in transformerlayers])
+        self.embed_dims = self.layers[0].embed_dims
+        self.pre_norm = self.layers[0].pre_norm
+
+    def forward(self, query, key, value, query_pos=None, key_pos=None, attn_masks=None, query_key_padding_mask=None,
+                key_padding_mask=None, **kwargs):
+        for layer in self.layers:
+            query = layer(query, key, value, query_pos=query_pos, key_pos=key_pos, attn_masks=attn_masks,
+                          query_key_padding_mask=query_key_padding_mask, key_padding_mask=key_padding_mask, **kwargs)
+        return query
+
+
+@MODELS.register_module()
+class DetrTransformerEncoder(TransformerLayerSequence):
+    def __init__(self, *args, post_norm_cfg=dict(type='LN'), **kwargs):
+        super().__init__(*args, **kwargs)
+        if post_norm_cfg is not None:
+            self.post_norm = build_norm(post_norm_cfg, self.embed_dims) if self.pre_norm else None
+        else:
+            assert not self.pre_norm
+            self.post_norm = None
+
+    def forward(self, *args, **kwargs):
+        x = super().forward(*args, **kwargs)
+        if self.post_norm is not None:
+            x = self.post_norm(x)
+        return x
+
+
+@MODELS.register_module()
+class DetrTransformerDecoder(TransformerLayerSequence):
+    def __init__(self, *args, post_norm_cfg=dict(type='LN'), return_intermediate=False, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.return_intermediate = return_intermediate
+        self.post_norm = build_norm(post_norm_cfg, self.embed_dims) if post_norm_cfg is not None else None
+
+    def forward(self, query, *args, **kwargs):
+        if not self.return_intermediate:
+            x = super().forward(query, *args, **kwargs)
+            if self.post_norm:
+                x = self.post_norm(x)[None]
+            return x
+        intermediate = []
+        for layer in self.layers:
+            query = layer(query, *args, **kwargs)
+            intermediate.append(self.post_norm(query) if self.post_norm is not None else query)
+        return torch.stack(intermediate)
+
+
+def build_transformer_layer_sequence(cfg, default_args=None):
+    if isinstance(cfg, nn.Module):
+        return cfg
+    return build_from_cfg(dict(cfg), MODELS, default_args)
+
+
+@MODELS.register_module()
+class SinePositionalEncoding(nn.Module):
+    def __init__(self, num_feats, temperature=10000, normalize=False, scale=2 * math.pi, eps=1e-6, offset=0.,
+                 init_cfg=None):
+        super().__init__()
+        if normalize:
+            assert isinstance(scale, (float, int))
+        self.num_feats, self.temperature, self.normalize = num_feats, temperature, normalize
+        self.scale, self.eps, self.offset = scale, eps, offset
+
+    def forward(self, mask):
+        mask = mask.to(torch.int)
+        not_mask = 1 - mask
+        y_embed = not_mask.cumsum(1, dtype=torch.float32)
+        x_embed = not_mask.cumsum(2, dtype=torch.float32)
+        if self.normalize:
+            y_embed = (y_embed + self.offset) / (y_embed[:, -1:, :] + self.eps) * self.scale
+            x_embed = (x_embed + self.offset) / (x_embed[:, :, -1:] + self.eps) * self.scale
+        dim_t = torch.arange(self.num_feats, dtype=torch.float32, device=mask.device)
+        dim_t = self.temperature ** (2 * (dim_t // 2) / self.num_feats)
+        pos_x = x_embed[:, :, :, None] / dim_t
+        pos_y = y_embed[:, :, :, None] / dim_t
+        B, H, W = mask.size()
+        pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).view(B, H, W, -1)
+        pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).view(B, H, W, -1)
+        return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+
+
+def build_positional_encoding(cfg):
+    return build_from_cfg(dict(cfg), MODELS)
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    x = x.clamp(min=0, max=1)
+    x1 = x.clamp(min=eps)
+    x2 = (1 - x).clamp(min=eps)
+    return torch.log(x1 / x2)
+
+
+class ConvModule(nn.Module):
+    """mmcv ConvModule (conv -> norm -> act); conv bias only without norm."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias='auto', conv_cfg=None,
+                 norm_cfg=None, act_cfg=dict(type='ReLU'), inplace=True):
+        super().__init__()
+        if bias == 'auto':
+            bias = norm_cfg is None
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=bias)
+        self.norm_name = None
+        if norm_cfg is not None:
+            self.norm_name = norm_abbr(norm_cfg)
+            self.add_module(self.norm_name, build_norm(norm_cfg, out_channels))
+        self.activate = build_activation(act_cfg) if act_cfg is not None else None
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.norm_name is not None:
+            x = getattr(self, self.norm_name)(x)
+        if self.activate is not None:
+            x = self.activate(x)
+        return x
+
+
+@MODELS.register_module()
+class ChannelMapper(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size=3, conv_cfg=None, norm_cfg=None,
+                 act_cfg=dict(type='ReLU'), num_outs=None, init_cfg=None):
+        super().__init__()
+        assert isinstance(in_channels, (list, tuple))
+        self.extra_convs = None
+        if num_outs is None:
+            num_outs = len(in_channels)
+        self.convs = nn.ModuleList([
+            ConvModule(c, out_channels, kernel_size, padding=(kernel_size - 1) // 2, norm_cfg=norm_cfg, act_cfg=act_cfg)
+            for c in in_channels])
+        if num_outs > len(in_channels):
+            self.extra_convs = nn.ModuleList()
+            for i in range(len(in_channels), num_outs):
+                c = in_channels[-1] if i == len(in_channels) else out_channels
+                self.extra_convs.append(ConvModule(c, out_channels, 3, stride=2, padding=1, norm_cfg=norm_cfg,
+                                                   act_cfg=act_cfg))
+        self.init_weights()
+
+    def init_weights(self):   # mmdet init_cfg: Xavier uniform on Conv2d
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0.)
+
+    def forward(self, inputs):
+        assert len(inputs) == len(self.convs)
+        outs = [self.convs[i](inputs[i]) for i in range(len(inputs))]
+        if self.extra_convs:
+            for i in range(len(self.extra_convs)):
+                outs.append(self.extra_convs[i](inputs[-1] if i == 0 else outs[-1]))
+        return tuple(outs)

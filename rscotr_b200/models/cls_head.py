@@ -1,0 +1,183 @@
+"""Single-level classification head (reference models/multi/cls_head/slvl_cls_head.py,
+mmcls LinearClsHead / GlobalAveragePooling / LabelSmoothLoss / Augments)."""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..config import MODELS
+
+
+class GlobalAveragePooling(nn.Module):
+    """mmcls GlobalAveragePooling(dim=2) on the rsc_gap kernel.  Accepts logical
+    NCHW tensors; channels-last strides (what SwinTransformer returns) take the
+    coalesced (B,HW,C) path without a layout copy."""
+
+    def _pool(self, x):
+        B, C = x.shape[:2]
+        if x.dim() == 4 and x.permute(0, 2, 3, 1).is_contiguous():
+            return ops.global_avg_pool(x.permute(0, 2, 3, 1).reshape(B, -1, C), channels_last=True)
+        return ops.global_avg_pool(x.contiguous(), channels_last=False)
+
+    def forward(self, inputs):
+        if isinstance(inputs, (tuple, list)):
+            return tuple(self._pool(x) for x in inputs)
+        return self._pool(inputs)
+
+
+class LabelSmoothLoss(nn.Module):
+    """mmcls LabelSmoothLoss(mode='original'): soft-target CE, sum / avg_factor."""
+
+    def __init__(self, label_smooth_val, num_classes=None, mode='original', reduction='mean', loss_weight=1.0):
+        super().__init__()
+        assert mode == 'original' and reduction == 'mean'
+        self.label_smooth_val, self.num_classes, self.loss_weight = label_smooth_val, num_classes, loss_weight
+
+    def forward(self, cls_score, label, avg_factor=None):
+        num_classes = self.num_classes or cls_score.shape[1]
+        if label.dim() == 1 or (label.dim() == 2 and label.shape[1] == 1):
+            one_hot = F.one_hot(label.view(-1), num_classes).float()
+        else:
+            one_hot = label.float()
+        smooth = one_hot * (1 - self.label_smooth_val) + self.label_smooth_val / num_classes
+        loss = -(smooth * F.log_softmax(cls_score.float(), dim=-1)).sum(-1)
+        loss = loss.sum() / avg_factor if avg_factor is not None else loss.mean()
+        return self.loss_weight * loss
+
+
+class CrossEntropyLoss(nn.Module):
+    def __init__(self, loss_weight=1.0, **kwargs):
+        super().__init__()
+        self.loss_weight = loss_weight
+
+    def forward(self, cls_score, label, avg_factor=None):
+        if label.dim() > 1:
+            loss = -(label * F.log_softmax(cls_score.float(), -1)).sum(-1)
+        else:
+            loss = F.cross_entropy(cls_score.float(), label, reduction='none')
+        loss = loss.sum() / avg_factor if avg_factor is not None else loss.mean()
+        return self.loss_weight * loss
+
+
+def one_hot_encoding(gt, num_classes):
+    return F.one_hot(gt.view(-1).long(), num_classes).float()
+
+
+class BatchMixup:
+    def __init__(self, alpha, num_classes, prob=1.0):
+        self.alpha, self.num_classes, self.prob = alpha, num_classes, prob
+
+    def __call__(self, img, gt_label, lam=None, index=None):
+        one_hot = one_hot_encoding(gt_label, self.num_classes)
+        lam = float(np.random.beta(self.alpha, self.alpha)) if lam is None else lam
+        index = torch.randperm(img.size(0), device=img.device) if index is None else index
+        return lam * img + (1 - lam) * img[index], lam * one_hot + (1 - lam) * one_hot[index]
+
+
+class BatchCutMix:
+    def __init__(self, alpha, num_classes, prob=1.0, cutmix_minmax=None, correct_lam=True):
+        self.alpha, self.num_classes, self.prob, self.correct_lam = alpha, num_classes, prob, correct_lam
+
+    def rand_bbox(self, img_shape, lam, margin=0., count=None):
+        ratio = np.sqrt(1 - lam)
+        H, W = img_shape[-2:]
+        cut_h, cut_w = int(H * ratio), int(W * ratio)
+        margin_y, margin_x = int(margin * cut_h), int(margin * cut_w)
+        cy = np.random.randint(0 + margin_y, H - margin_y, size=count)
+        cx = np.random.randint(0 + margin_x, W - margin_x, size=count)
+        yl, yh = np.clip(cy - cut_h // 2, 0, H), np.clip(cy + cut_h // 2, 0, H)
+        xl, xh = np.clip(cx - cut_w // 2, 0, W), np.clip(cx + cut_w // 2, 0, W)
+        return yl, yh, xl, xh
+
+    def __call__(self, img, gt_label):
+        one_hot = one_hot_encoding(gt_label, self.num_classes)
+        lam = float(np.random.beta(self.alpha, self.alpha))
+        index = torch.randperm(img.size(0), device=img.device)
+        yl, yh, xl, xh = self.rand_bbox(img.shape, lam)
+        if self.correct_lam:
+            lam = 1. - (yh - yl) * (xh - xl) / float(img.shape[-2] * img.shape[-1])
+        img = img.clone()
+        img[:, :, yl:yh, xl:xh] = img[index, :, yl:yh, xl:xh]
+        return img, lam * one_hot + (1 - lam) * one_hot[index]
+
+
+class Identity:
+    def __init__(self, num_classes, prob=1.0):
+        self.num_classes, self.prob = num_classes, prob
+
+    def __call__(self, img, gt_label):
+        return img, one_hot_encoding(gt_label, self.num_classes)
+
+
+class Augments:
+    """mmcls Augments: pick ONE batch augment per call with the configured probabilities."""
+    _TYPES = {'BatchMixup': BatchMixup, 'BatchCutMix': BatchCutMix, 'Identity': Identity}
+
+    def __init__(self, augments_cfg):
+        cfgs = [augments_cfg] if isinstance(augments_cfg, dict) else list(augments_cfg)
+        self.augments = []
+        for c in cfgs:
+            c = dict(c)
+            self.augments.append(self._TYPES[c.pop('type')](**c))
+        self.aug_probs = [a.prob for a in self.augments]
+        has_identity = any(isinstance(a, Identity) for a in self.augments)
+        if has_identity:
+            assert sum(self.aug_probs) == 1.0
+        else:
+            assert sum(self.aug_probs) <= 1.0
+            identity_prob = 1 - sum(self.aug_probs)
+            if identity_prob > 0:
+                self.augments.append(Identity(self.augments[0].num_classes, identity_prob))
+                self.aug_probs.append(identity_prob)
+
+    def __call__(self, img, gt_label):
+        if self.augments:
+            aug = self.augments[int(np.random.choice(len(self.augments), p=self.aug_probs))]
+            return aug(img, gt_label)
+        return img, gt_label
+
+
+_CLS_LOSSES = {'LabelSmoothLoss': LabelSmoothLoss, 'CrossEntropyLoss': CrossEntropyLoss}
+
+
+@MODELS.register_module()
+class SlvlClsHead(nn.Module):
+    def __init__(self, num_classes, in_channels, loss=dict(type='CrossEntropyLoss', loss_weight=1.0), topk=(1,),
+                 cal_acc=False, init_cfg=dict(type='Normal', layer='Linear', std=0.01)):
+        super().__init__()
+        if num_classes <= 0:
+            raise ValueError('num_classes=%d must be a positive integer' % num_classes)
+        self.in_channels, self.num_classes, self.cal_acc, self.topk = in_channels, num_classes, cal_acc, topk
+        loss = dict(loss)
+        self.compute_loss = _CLS_LOSSES[loss.pop('type')](**loss)
+        self.fc = nn.Linear(in_channels, num_classes)
+        self.avg_pool = GlobalAveragePooling()
+        nn.init.normal_(self.fc.weight, 0, 0.01)
+        nn.init.constant_(self.fc.bias, 0)
+
+    def pre_logits(self, x):
+        cls_token = self.avg_pool((x[-1],))          # the reference pools every map and keeps the last
+        if isinstance(cls_token, (tuple, list)):
+            cls_token = cls_token[-1]
+        return cls_token
+
+    def loss(self, cls_score, gt_label):
+        num_samples = len(cls_score)
+        losses = dict()
+        losses['loss'] = self.compute_loss(cls_score, gt_label, avg_factor=num_samples)
+        if self.cal_acc:
+            pred = cls_score.argmax(-1)
+            losses['accuracy'] = {'top-1': (pred == gt_label).float().mean() * 100}
+        return losses
+
+    def forward_train(self, neck_feature, backbone_feature, gt_label, shared_encoder, **kwargs):
+        cls_score = self.fc(self.pre_logits(backbone_feature))
+        return self.loss(cls_score, gt_label)
+
+    def simple_test(self, neck_feature, backbone_feature, shared_encoder, softmax=True, post_process=True):
+        cls_score = self.fc(self.pre_logits(backbone_feature))
+        pred = F.softmax(cls_score.float(), dim=1) if softmax else cls_score
+        if post_process:
+            return list(pred.detach().cpu().numpy())
+        return pred

@@ -1,0 +1,782 @@
+"""DINO detection head that threads the SHARED deformable encoder through itself.
+
+Mirrors (names, arguments, outputs, loss keys) the reference's
+models/multi/bbox_head/{dino_head,transformer,query_denoising}.py and the
+vendored mmdet heads in models/multi/bbox_head/mmdet_detr_head/ (SURVEY 8a rows
+a13-a16), with these structural changes for a GPU-resident step:
+  * the 7 Hungarian problems x batch are costed on the GPU in one batched pass
+    and shipped to scipy with ONE device->host copy (reference: one sync per
+    (layer, image), detr_head.py:513);
+  * no .cuda() hard-coding (query_denoising.py:125-180), no per-loss .item().
+"""
+import copy
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..config import MODELS, build_from_cfg
+from .bricks import (TransformerLayerSequence, MultiScaleDeformableAttention, build_positional_encoding,
+                     build_transformer_layer_sequence, inverse_sigmoid)
+
+
+# ------------------------------------------------------------------ box utils
+def bbox_cxcywh_to_xyxy(b):
+    cx, cy, w, h = b.unbind(-1)
+    return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
+
+
+def bbox_xyxy_to_cxcywh(b):
+    x1, y1, x2, y2 = b.unbind(-1)
+    return torch.stack([(x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1], -1)
+
+
+def giou(b1, b2, aligned, eps=1e-6):
+    """mmdet bbox_overlaps(mode='giou'); b1 (..., N, 4), b2 (..., M, 4) xyxy."""
+    a1 = (b1[..., 2] - b1[..., 0]) * (b1[..., 3] - b1[..., 1])
+    a2 = (b2[..., 2] - b2[..., 0]) * (b2[..., 3] - b2[..., 1])
+    if aligned:
+        lt = torch.max(b1[..., :2], b2[..., :2])
+        rb = torch.min(b1[..., 2:], b2[..., 2:])
+        union_base = a1 + a2
+        elt = torch.min(b1[..., :2], b2[..., :2])
+        erb = torch.max(b1[..., 2:], b2[..., 2:])
+    else:
+        lt = torch.max(b1[..., :, None, :2], b2[..., None, :, :2])
+        rb = torch.min(b1[..., :, None, 2:], b2[..., None, :, 2:])
+        union_base = a1[..., None] + a2[..., None, :]
+        elt = torch.min(b1[..., :, None, :2], b2[..., None, :, :2])
+        erb = torch.max(b1[..., :, None, 2:], b2[..., None, :, 2:])
+    wh = (rb - lt).clamp(min=0)
+    overlap = wh[..., 0] * wh[..., 1]
+    eps_t = union_base.new_tensor([eps])
+    union = torch.max(union_base - overlap, eps_t)
+    ious = overlap / union
+    ewh = (erb - elt).clamp(min=0)
+    earea = torch.max(ewh[..., 0] * ewh[..., 1], eps_t)
+    return ious - (earea - union) / earea
+
+
+def build_MLP(input_dim, hidden_dim, output_dim, num_layers):
+    assert num_layers > 1, 'num_layers should be greater than 1 but got %d' % num_layers
+    h = [hidden_dim] * (num_layers - 1)
+    layers = []
+    for n, k in zip([input_dim] + h[:-1], h):
+        layers.extend((nn.Linear(n, k), nn.ReLU()))
+    layers.append(nn.Linear(hidden_dim, output_dim))
+    return nn.Sequential(*layers)
+
+
+# ------------------------------------------------------------------ decoder
+@MODELS.register_module()
+class DinoTransformerDecoder(TransformerLayerSequence):
+    """reference: models/multi/bbox_head/transformer.py:31-131"""
+
+    def __init__(self, *args, return_intermediate=False, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.return_intermediate = return_intermediate
+        self.ref_point_head = build_MLP(self.embed_dims * 2, self.embed_dims, self.embed_dims, 2)
+        self.norm = nn.LayerNorm(self.embed_dims)
+
+    @staticmethod
+    def gen_sineembed_for_position(pos_tensor):
+        scale = 2 * math.pi
+        dim_t = torch.arange(128, dtype=torch.float32, device=pos_tensor.device)
+        dim_t = 10000 ** (2 * (dim_t // 2) / 128)
+
+        def emb(v):
+            p = (v * scale)[:, :, None] / dim_t
+            return torch.stack((p[:, :, 0::2].sin(), p[:, :, 1::2].cos()), dim=3).flatten(2)
+
+        pos_x, pos_y = emb(pos_tensor[:, :, 0]), emb(pos_tensor[:, :, 1])
+        if pos_tensor.size(-1) == 2:
+            return torch.cat((pos_y, pos_x), dim=2)
+        if pos_tensor.size(-1) == 4:
+            return torch.cat((pos_y, pos_x, emb(pos_tensor[:, :, 2]), emb(pos_tensor[:, :, 3])), dim=2)
+        raise ValueError('Unknown pos_tensor shape(-1):{}'.format(pos_tensor.size(-1)))
+
+    def forward(self, query, *args, reference_points=None, valid_ratios=None, reg_branches=None, **kwargs):
+        output = query
+        intermediate = []
+        intermediate_reference_points = [reference_points]
+        for lid, layer in enumerate(self.layers):
+            if reference_points.shape[-1] == 4:
+                reference_points_input = reference_points[:, :, None] * \
+                    torch.cat([valid_ratios, valid_ratios], -1)[:, None]
+            else:
+                assert reference_points.shape[-1] == 2
+                reference_points_input = reference_points[:, :, None] * valid_ratios[:, None]
+            query_sine_embed = self.gen_sineembed_for_position(reference_points_input[:, :, 0, :])
+            query_pos = self.ref_point_head(query_sine_embed).permute(1, 0, 2)
+            output = layer(output, *args, query_pos=query_pos, reference_points=reference_points_input, **kwargs)
+            output = output.permute(1, 0, 2)
+            if reg_branches is not None:
+                tmp = reg_branches[lid](output)
+                assert reference_points.shape[-1] == 4
+                new_reference_points = (tmp.float() + inverse_sigmoid(reference_points, eps=1e-3)).sigmoid()
+                reference_points = new_reference_points.detach()
+            output = output.permute(1, 0, 2)
+            if self.return_intermediate:
+                intermediate.append(self.norm(output))
+                intermediate_reference_points.append(new_reference_points)   # look forward twice
+        if self.return_intermediate:
+            return torch.stack(intermediate), torch.stack(intermediate_reference_points)
+        return output, reference_points
+
+
+@MODELS.register_module()
+class DinoTransformer(nn.Module):
+    """reference: models/multi/bbox_head/transformer.py:134-272 (encoder passed in)."""
+
+    def __init__(self, decoder=None, as_two_stage=False, num_feature_levels=4, two_stage_num_proposals=300,
+                 init_cfg=None):
+        super().__init__()
+        self.decoder = build_transformer_layer_sequence(decoder)
+        self.as_two_stage = as_two_stage
+        self.num_feature_levels = num_feature_levels
+        self.two_stage_num_proposals = two_stage_num_proposals
+        self.embed_dims = self.decoder.embed_dims
+        self.level_embeds = nn.Parameter(torch.Tensor(self.num_feature_levels, self.embed_dims))
+        self.enc_output = nn.Linear(self.embed_dims, self.embed_dims)
+        self.enc_output_norm = nn.LayerNorm(self.embed_dims)
+        self.query_embed = nn.Embedding(self.two_stage_num_proposals, self.embed_dims)
+
+    def init_weights(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MultiScaleDeformableAttention):
+                m.init_weights()
+        nn.init.normal_(self.level_embeds)
+        nn.init.normal_(self.query_embed.weight.data)
+
+    @staticmethod
+    def get_valid_ratio(mask):
+        _, H, W = mask.shape
+        valid_H = torch.sum(~mask[:, :, 0], 1)
+        valid_W = torch.sum(~mask[:, 0, :], 1)
+        return torch.stack([valid_W.float() / W, valid_H.float() / H], -1)
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        ref_list = []
+        for lvl, (H, W) in enumerate(spatial_shapes):
+            ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, H - 0.5, H, dtype=torch.float32, device=device),
+                                          torch.linspace(0.5, W - 0.5, W, dtype=torch.float32, device=device),
+                                          indexing='ij')
+            ref_y = ref_y.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H)
+            ref_x = ref_x.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W)
+            ref_list.append(torch.stack((ref_x, ref_y), -1))
+        reference_points = torch.cat(ref_list, 1)
+        return reference_points[:, :, None] * valid_ratios[:, None]
+
+    def gen_encoder_output_proposals(self, memory, memory_padding_mask, spatial_shapes):
+        N, S, C = memory.shape
+        proposals = []
+        _cur = 0
+        for lvl, (H, W) in enumerate(spatial_shapes):
+            mask_flatten_ = memory_padding_mask[:, _cur:(_cur + H * W)].view(N, H, W, 1)
+            valid_H = torch.sum(~mask_flatten_[:, :, 0, 0], 1)
+            valid_W = torch.sum(~mask_flatten_[:, 0, :, 0], 1)
+            grid_y, grid_x = torch.meshgrid(
+                torch.linspace(0, H - 1, H, dtype=torch.float32, device=memory.device),
+                torch.linspace(0, W - 1, W, dtype=torch.float32, device=memory.device), indexing='ij')
+            grid = torch.cat([grid_x.unsqueeze(-1), grid_y.unsqueeze(-1)], -1)
+            scale = torch.cat([valid_W.unsqueeze(-1), valid_H.unsqueeze(-1)], 1).view(N, 1, 1, 2)
+            grid = (grid.unsqueeze(0).expand(N, -1, -1, -1) + 0.5) / scale
+            wh = torch.ones_like(grid) * 0.05 * (2.0 ** lvl)
+            proposals.append(torch.cat((grid, wh), -1).view(N, -1, 4))
+            _cur += H * W
+        output_proposals = torch.cat(proposals, 1)
+        output_proposals_valid = ((output_proposals > 0.01) & (output_proposals < 0.99)).all(-1, keepdim=True)
+        output_proposals = torch.log(output_proposals / (1 - output_proposals))
+        output_proposals = output_proposals.masked_fill(memory_padding_mask.unsqueeze(-1), float('inf'))
+        output_proposals = output_proposals.masked_fill(~output_proposals_valid, float('inf'))
+        output_memory = memory.masked_fill(memory_padding_mask.unsqueeze(-1), float(0))
+        output_memory = output_memory.masked_fill(~output_proposals_valid, float(0))
+        output_memory = self.enc_output_norm(self.enc_output(output_memory))
+        return output_memory, output_proposals
+
+    def forward(self, mlvl_feats, mlvl_masks, query_embed, mlvl_pos_embeds, dn_label_query, dn_bbox_query, attn_mask,
+                encoder, reg_branches=None, cls_branches=None, **kwargs):
+        assert self.as_two_stage and query_embed is None, 'as_two_stage must be True for DINO'
+        feat_flatten, mask_flatten, lvl_pos_embed_flatten, spatial_shapes = [], [], [], []
+        for lvl, (feat, mask, pos_embed) in enumerate(zip(mlvl_feats, mlvl_masks, mlvl_pos_embeds)):
+            bs, c, h, w = feat.shape
+            spatial_shapes.append((h, w))
+            feat_flatten.append(feat.flatten(2).transpose(1, 2))
+            mask_flatten.append(mask.flatten(1))
+            pos_embed = pos_embed.flatten(2).transpose(1, 2)
+            lvl_pos_embed_flatten.append(pos_embed + self.level_embeds[lvl].view(1, 1, -1))
+        feat_flatten = torch.cat(feat_flatten, 1)
+        mask_flatten = torch.cat(mask_flatten, 1)
+        lvl_pos_embed_flatten = torch.cat(lvl_pos_embed_flatten, 1)
+        shapes_py = spatial_shapes
+        spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long, device=feat_flatten.device)
+        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in mlvl_masks], 1)
+        reference_points = self.get_reference_points(shapes_py, valid_ratios, device=feat_flatten.device)
+
+        feat_flatten = feat_flatten.permute(1, 0, 2)
+        lvl_pos_embed_flatten = lvl_pos_embed_flatten.permute(1, 0, 2)
+        memory = encoder(query=feat_flatten, key=None, value=None, query_pos=lvl_pos_embed_flatten,
+                         query_key_padding_mask=mask_flatten, spatial_shapes=spatial_shapes,
+                         reference_points=reference_points, level_start_index=level_start_index,
+                         valid_ratios=valid_ratios, **kwargs)
+        memory = memory.permute(1, 0, 2)
+        bs, _, c = memory.shape
+
+        output_memory, output_proposals = self.gen_encoder_output_proposals(memory, mask_flatten, shapes_py)
+        enc_outputs_class = cls_branches[self.decoder.num_layers](output_memory)
+        enc_outputs_coord_unact = reg_branches[self.decoder.num_layers](output_memory).float() + output_proposals
+        cls_out_features = cls_branches[self.decoder.num_layers].out_features
+        topk = self.two_stage_num_proposals
+        topk_indices = torch.topk(enc_outputs_class.max(-1)[0], topk, dim=1)[1]
+        topk_score = torch.gather(enc_outputs_class, 1, topk_indices.unsqueeze(-1).repeat(1, 1, cls_out_features))
+        topk_coords_unact = torch.gather(enc_outputs_coord_unact, 1, topk_indices.unsqueeze(-1).repeat(1, 1, 4))
+        topk_anchor = topk_coords_unact.sigmoid()
+        topk_coords_unact = topk_coords_unact.detach()
+
+        query = self.query_embed.weight[:, None, :].repeat(1, bs, 1).transpose(0, 1)
+        if dn_label_query is not None:
+            query = torch.cat([dn_label_query.to(query.dtype), query], dim=1)
+        if dn_bbox_query is not None:
+            reference_points = torch.cat([dn_bbox_query, topk_coords_unact], dim=1)
+        else:
+            reference_points = topk_coords_unact
+        reference_points = reference_points.sigmoid()
+
+        query = query.permute(1, 0, 2)
+        memory = memory.permute(1, 0, 2)
+        inter_states, inter_references = self.decoder(
+            query=query, key=None, value=memory, attn_masks=attn_mask, key_padding_mask=mask_flatten,
+            reference_points=reference_points, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+            valid_ratios=valid_ratios, reg_branches=reg_branches, **kwargs)
+        return inter_states, inter_references, topk_score, topk_anchor
+
+
+# ------------------------------------------------------------------ CDN
+class CdnQueryGenerator:
+    """reference: models/multi/bbox_head/query_denoising.py:8-201 (device agnostic).
+    `forced_noise` (dict with keys p, new_label, rand_sign, rand_part) replaces the
+    RNG draws so parity tests can feed the same noise to the oracle."""
+
+    def __init__(self, num_queries, hidden_dim, num_classes, noise_scale=dict(label=0.5, box=0.4),
+                 group_cfg=dict(dynamic=True, num_groups=None, num_dn_queries=None)):
+        self.num_queries, self.hidden_dim, self.num_classes = num_queries, hidden_dim, num_classes
+        self.label_noise_scale = noise_scale['label']
+        self.box_noise_scale = noise_scale['box']
+        self.dynamic_dn_groups = group_cfg.get('dynamic', False)
+        if self.dynamic_dn_groups:
+            assert 'num_dn_queries' in group_cfg, 'num_dn_queries should be set when using dynamic dn groups'
+            self.num_dn = group_cfg['num_dn_queries']
+        else:
+            assert 'num_groups' in group_cfg, 'num_groups should be set when using static dn groups'
+            self.num_dn = group_cfg['num_groups']
+        assert isinstance(self.num_dn, int) and self.num_dn >= 1, \
+            'Expected the num in group_cfg to have type int. Found %s ' % type(self.num_dn)
+        self.forced_noise = None
+
+    def get_num_groups(self, group_queries=None):
+        if self.dynamic_dn_groups:
+            assert group_queries is not None, 'group_queries should be provided when using dynamic dn groups'
+            num_groups = 1 if group_queries == 0 else self.num_dn // group_queries
+        else:
+            num_groups = self.num_dn
+        return int(max(num_groups, 1))
+
+    def __call__(self, gt_bboxes, gt_labels=None, label_enc=None, img_metas=None):
+        if gt_labels is not None:
+            assert len(gt_bboxes) == len(gt_labels), \
+                'the length of provided gt_labels %d should be equal to that of gt_bboxes %d' % (
+                    len(gt_labels), len(gt_bboxes))
+        assert gt_labels is not None and label_enc is not None and img_metas is not None
+        batch_size = len(gt_bboxes)
+        device = gt_bboxes[0].device
+        boxes_n = []
+        for img_meta, bboxes in zip(img_metas, gt_bboxes):
+            img_h, img_w, _ = img_meta['img_shape']
+            factor = bboxes.new_tensor([img_w, img_h, img_w, img_h]).unsqueeze(0)
+            boxes_n.append(bbox_xyxy_to_cxcywh(bboxes) / factor)
+        known_num = [int(l.numel()) for l in gt_labels]
+        single_pad = int(max(known_num))
+        num_groups = self.get_num_groups(single_pad)
+        labels = torch.cat(gt_labels)
+        boxes = torch.cat(boxes_n)
+        batch_idx = torch.cat([torch.full_like(t.long(), i) for i, t in enumerate(gt_labels)])
+        nbox = len(boxes)
+        known_labels = labels.repeat(2 * num_groups, 1).view(-1)
+        known_bid = batch_idx.repeat(2 * num_groups, 1).view(-1)
+        known_bboxs = boxes.repeat(2 * num_groups, 1)
+        known_labels_expand = known_labels.clone()
+        known_bbox_expand = known_bboxs.clone()
+        fn = self.forced_noise or {}
+        if self.label_noise_scale > 0:
+            p = fn['p'].to(device) if 'p' in fn else torch.rand_like(known_labels_expand.float())
+            new_label = fn['new_label'].to(device) if 'new_label' in fn else \
+                torch.randint_like(known_labels_expand, 0, self.num_classes)
+            # (reference draws new labels only for the chosen indices; drawing one per
+            # slot and selecting is the same distribution and needs no host sync)
+            known_labels_expand = torch.where(p < (self.label_noise_scale * 0.5), new_label, known_labels_expand)
+        pad_size = int(single_pad * 2 * num_groups)
+        positive_idx = torch.arange(nbox, device=device).unsqueeze(0).repeat(num_groups, 1)
+        positive_idx = positive_idx + (torch.arange(num_groups, device=device) * nbox * 2).unsqueeze(1)
+        positive_idx = positive_idx.flatten()
+        negative_idx = positive_idx + nbox
+        if self.box_noise_scale > 0:
+            known_bbox_ = torch.zeros_like(known_bboxs)
+            known_bbox_[:, :2] = known_bboxs[:, :2] - known_bboxs[:, 2:] / 2
+            known_bbox_[:, 2:] = known_bboxs[:, :2] + known_bboxs[:, 2:] / 2
+            diff = torch.zeros_like(known_bboxs)
+            diff[:, :2] = known_bboxs[:, 2:] / 2
+            diff[:, 2:] = known_bboxs[:, 2:] / 2
+            rand_sign = fn['rand_sign'].to(device) if 'rand_sign' in fn else \
+                torch.randint_like(known_bboxs, low=0, high=2, dtype=torch.float32)
+            rand_sign = rand_sign * 2.0 - 1.0
+            rand_part = (fn['rand_part'].to(device) if 'rand_part' in fn else torch.rand_like(known_bboxs)).clone()
+            rand_part[negative_idx] += 1.0
+            rand_part = rand_part * rand_sign
+            known_bbox_ = known_bbox_ + torch.mul(rand_part, diff) * self.box_noise_scale
+            known_bbox_ = known_bbox_.clamp(min=0.0, max=1.0)
+            known_bbox_expand[:, :2] = (known_bbox_[:, :2] + known_bbox_[:, 2:]) / 2
+            known_bbox_expand[:, 2:] = known_bbox_[:, 2:] - known_bbox_[:, :2]
+        input_label_embed = label_enc(known_labels_expand.long())
+        input_bbox_embed = inverse_sigmoid(known_bbox_expand, eps=1e-3)
+        input_query_label = input_label_embed.new_zeros(batch_size, pad_size, self.hidden_dim)
+        input_query_bbox = input_bbox_embed.new_zeros(batch_size, pad_size, 4)
+        if nbox:
+            map_known_indice = torch.cat([torch.arange(num, device=device) for num in known_num])
+            map_known_indice = torch.cat([map_known_indice + single_pad * i for i in range(2 * num_groups)]).long()
+            input_query_label[(known_bid.long(), map_known_indice)] = input_label_embed
+            input_query_bbox[(known_bid.long(), map_known_indice)] = input_bbox_embed
+        tgt_size = pad_size + self.num_queries
+        attn_mask = torch.zeros(tgt_size, tgt_size, dtype=torch.bool, device=device)
+        attn_mask[pad_size:, :pad_size] = True
+        for i in range(num_groups):
+            lo, hi = single_pad * 2 * i, single_pad * 2 * (i + 1)
+            attn_mask[lo:hi, hi:pad_size] = True
+            attn_mask[lo:hi, :lo] = True
+        dn_meta = {'pad_size': pad_size, 'num_dn_group': num_groups}
+        return input_query_label, input_query_bbox, attn_mask, dn_meta
+
+
+def build_dn_generator(dn_args):
+    if dn_args is None:
+        return None
+    dn_args = dict(dn_args)
+    t = dn_args.pop('type')
+    if t == 'CdnQueryGenerator':
+        return CdnQueryGenerator(**dn_args)
+    raise NotImplementedError('%s is not supported yet' % t)
+
+
+# ------------------------------------------------------------------ assigner / losses
+class HungarianAssigner:
+    """mmdet HungarianAssigner (FocalLossCost + BBoxL1Cost(xywh) + IoUCost(giou)), batched
+    over the leading (layer) dimension; scipy solves on the host."""
+
+    def __init__(self, cls_cost=dict(type='FocalLossCost', weight=2.0),
+                 reg_cost=dict(type='BBoxL1Cost', weight=5.0, box_format='xywh'),
+                 iou_cost=dict(type='IoUCost', iou_mode='giou', weight=2.0), **kwargs):
+        assert cls_cost['type'] == 'FocalLossCost' and reg_cost['type'] == 'BBoxL1Cost' and iou_cost['type'] == 'IoUCost'
+        assert reg_cost.get('box_format', 'xyxy') == 'xywh' and iou_cost.get('iou_mode', 'giou') == 'giou'
+        self.w_cls, self.w_reg, self.w_iou = cls_cost.get('weight', 1.), reg_cost.get('weight', 1.), iou_cost.get('weight', 1.)
+        self.alpha, self.gamma, self.eps = cls_cost.get('alpha', 0.25), cls_cost.get('gamma', 2), cls_cost.get('eps', 1e-12)
+
+    def cost(self, bbox_pred, cls_pred, gt_bboxes, gt_labels, img_shape):
+        """bbox_pred (..., Nq, 4) cxcywh normalised, cls_pred (..., Nq, C) logits -> (..., Nq, n_gt)."""
+        img_h, img_w = img_shape[:2]
+        factor = gt_bboxes.new_tensor([img_w, img_h, img_w, img_h]).unsqueeze(0)
+        p = cls_pred.float().sigmoid()
+        neg = -(1 - p + self.eps).log() * (1 - self.alpha) * p.pow(self.gamma)
+        pos = -(p + self.eps).log() * self.alpha * (1 - p).pow(self.gamma)
+        cls_cost = (pos[..., gt_labels] - neg[..., gt_labels]) * self.w_cls
+        gt_n = bbox_xyxy_to_cxcywh(gt_bboxes / factor)
+        bp = bbox_pred.float()
+        reg_cost = (bp[..., :, None, :] - gt_n).abs().sum(-1) * self.w_reg
+        iou_cost = -giou(bbox_cxcywh_to_xyxy(bp) * factor, gt_bboxes, aligned=False) * self.w_iou
+        return cls_cost + reg_cost + iou_cost
+
+    @staticmethod
+    def solve(cost_np):
+        from scipy.optimize import linear_sum_assignment
+        return linear_sum_assignment(cost_np)
+
+
+class FocalLoss(nn.Module):
+    def __init__(self, use_sigmoid=True, gamma=2.0, alpha=0.25, reduction='mean', loss_weight=1.0, activated=False):
+        super().__init__()
+        assert use_sigmoid and not activated and reduction == 'mean'
+        self.use_sigmoid, self.gamma, self.alpha, self.loss_weight = use_sigmoid, gamma, alpha, loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None):
+        loss = ops.sigmoid_focal_loss(pred.contiguous(), target.contiguous(), self.gamma, self.alpha)
+        if weight is not None:
+            loss = loss * weight.view(-1, 1)
+        loss = loss.sum() / avg_factor if avg_factor is not None else loss.mean()
+        return self.loss_weight * loss
+
+
+class L1Loss(nn.Module):
+    def __init__(self, reduction='mean', loss_weight=1.0):
+        super().__init__()
+        self.loss_weight = loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None):
+        if target.numel() == 0:
+            return pred.sum() * 0
+        loss = (pred - target).abs()
+        if weight is not None:
+            loss = loss * weight
+        loss = loss.sum() / avg_factor if avg_factor is not None else loss.mean()
+        return self.loss_weight * loss
+
+
+class GIoULoss(nn.Module):
+    def __init__(self, eps=1e-6, reduction='mean', loss_weight=1.0):
+        super().__init__()
+        self.eps, self.loss_weight = eps, loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, any_positive=True):
+        if weight is not None and not any_positive:
+            return (pred * weight).sum()
+        if weight is not None and weight.dim() > 1:
+            weight = weight.mean(-1)
+        loss = 1 - giou(pred, target, aligned=True, eps=self.eps)
+        if weight is not None:
+            loss = loss * weight
+        loss = loss.sum() / avg_factor if avg_factor is not None else loss.mean()
+        return self.loss_weight * loss
+
+
+_LOSSES = {'FocalLoss': FocalLoss, 'L1Loss': L1Loss, 'GIoULoss': GIoULoss}
+
+
+def build_loss(cfg):
+    cfg = dict(cfg)
+    return _LOSSES[cfg.pop('type')](**cfg)
+
+
+def reduce_mean(t):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return t
+    t = t.clone()
+    dist.all_reduce(t.div_(dist.get_world_size()), op=dist.ReduceOp.SUM)
+    return t
+
+
+# ------------------------------------------------------------------ head
+@MODELS.register_module()
+class DINOHead(nn.Module):
+    """reference: models/multi/bbox_head/dino_head.py (+ DETRHead / DeformableDETRHead
+    in models/multi/bbox_head/mmdet_detr_head/)."""
+
+    def __init__(self, num_classes, in_channels, num_query=100, num_reg_fcs=2, transformer=None,
+                 sync_cls_avg_factor=False, positional_encoding=dict(type='SinePositionalEncoding', num_feats=128,
+                                                                     normalize=True),
+                 loss_cls=None, loss_bbox=dict(type='L1Loss', loss_weight=5.0),
+                 loss_iou=dict(type='GIoULoss', loss_weight=2.0), train_cfg=None, test_cfg=dict(max_per_img=100),
+                 with_box_refine=False, as_two_stage=False, dn_cfg=None, num_feature_levels=4, init_cfg=None,
+                 **kwargs):
+        super().__init__()
+        transformer = copy.deepcopy(dict(transformer))
+        if 'two_stage_num_proposals' in transformer:
+            assert transformer['two_stage_num_proposals'] == num_query, \
+                'two_stage_num_proposals must be equal to num_query for DINO'
+        else:
+            transformer['two_stage_num_proposals'] = num_query
+        self.with_box_refine, self.as_two_stage = with_box_refine, as_two_stage
+        if as_two_stage:
+            transformer['as_two_stage'] = as_two_stage
+        transformer.setdefault('num_feature_levels', num_feature_levels)
+        self.bg_cls_weight = 0
+        self.sync_cls_avg_factor = sync_cls_avg_factor
+        if train_cfg:
+            assert 'assigner' in train_cfg, 'assigner should be provided when train_cfg is set.'
+            a = dict(train_cfg['assigner'])
+            assert a.pop('type') == 'HungarianAssigner'
+            self.assigner = HungarianAssigner(**a)
+        self.num_query, self.num_classes, self.in_channels, self.num_reg_fcs = num_query, num_classes, in_channels, num_reg_fcs
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.loss_cls, self.loss_bbox, self.loss_iou = build_loss(loss_cls), build_loss(loss_bbox), build_loss(loss_iou)
+        self.cls_out_channels = num_classes if self.loss_cls.use_sigmoid else num_classes + 1
+        self.positional_encoding = build_positional_encoding(positional_encoding)
+        self.transformer = build_from_cfg(transformer, MODELS)
+        self.embed_dims = self.transformer.embed_dims
+        num_feats = positional_encoding['num_feats']
+        assert num_feats * 2 == self.embed_dims, \
+            'embed_dims should be exactly 2 times of num_feats. Found %d and %d.' % (self.embed_dims, num_feats)
+        assert self.as_two_stage, 'as_two_stage must be True for DINO'
+        assert self.with_box_refine, 'with_box_refine must be True for DINO'
+        self._init_layers()
+        if dn_cfg is not None:
+            dn_cfg = dict(dn_cfg)
+            dn_cfg['num_classes'], dn_cfg['num_queries'], dn_cfg['hidden_dim'] = num_classes, num_query, self.embed_dims
+        self.dn_generator = build_dn_generator(dn_cfg)
+        self.init_weights()
+
+    def _init_layers(self):
+        fc_cls = nn.Linear(self.embed_dims, self.cls_out_channels)
+        reg_branch = []
+        for _ in range(self.num_reg_fcs):
+            reg_branch.append(nn.Linear(self.embed_dims, self.embed_dims))
+            reg_branch.append(nn.ReLU())
+        reg_branch.append(nn.Linear(self.embed_dims, 4))
+        reg_branch = nn.Sequential(*reg_branch)
+        num_pred = self.transformer.decoder.num_layers + 1
+        self.cls_branches = nn.ModuleList([copy.deepcopy(fc_cls) for _ in range(num_pred)])
+        self.reg_branches = nn.ModuleList([copy.deepcopy(reg_branch) for _ in range(num_pred)])
+        self.label_embedding = nn.Embedding(self.num_classes, self.embed_dims)
+
+    def init_weights(self):
+        self.transformer.init_weights()
+        bias_init = float(-math.log((1 - 0.01) / 0.01))
+        for m in self.cls_branches:
+            nn.init.constant_(m.bias, bias_init)
+        for m in self.reg_branches:
+            nn.init.constant_(m[-1].weight, 0)
+            nn.init.constant_(m[-1].bias, 0)
+        nn.init.constant_(self.reg_branches[0][-1].bias.data[2:], -2.0)
+        for m in self.reg_branches:
+            nn.init.constant_(m[-1].bias.data[2:], 0.0)
+
+    # -- forward ---------------------------------------------------------
+    def forward_train(self, mlvl_feats, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None,
+                      shared_encoder=None, proposal_cfg=None, **kwargs):
+        assert proposal_cfg is None, '"proposal_cfg" must be None'
+        assert self.dn_generator is not None, '"dn_cfg" must be set'
+        dn_label_query, dn_bbox_query, attn_mask, dn_meta = self.dn_generator(
+            gt_bboxes, gt_labels, self.label_embedding, img_metas)
+        outs = self(shared_encoder, mlvl_feats, img_metas, dn_label_query, dn_bbox_query, attn_mask)
+        return self.loss(*outs, gt_bboxes, gt_labels, img_metas, dn_meta, gt_bboxes_ignore=gt_bboxes_ignore)
+
+    def forward(self, encoder, mlvl_feats, img_metas, dn_label_query=None, dn_bbox_query=None, attn_mask=None):
+        batch_size = mlvl_feats[0].size(0)
+        input_img_h, input_img_w = img_metas[0]['batch_input_shape']
+        img_masks = mlvl_feats[0].new_ones((batch_size, input_img_h, input_img_w), dtype=torch.float32)
+        for img_id in range(batch_size):
+            img_h, img_w, _ = img_metas[img_id]['img_shape']
+            img_masks[img_id, :img_h, :img_w] = 0
+        mlvl_masks, mlvl_positional_encodings = [], []
+        for feat in mlvl_feats:
+            mlvl_masks.append(F.interpolate(img_masks[None], size=feat.shape[-2:]).to(torch.bool).squeeze(0))
+            mlvl_positional_encodings.append(self.positional_encoding(mlvl_masks[-1]))
+        hs, inter_references, topk_score, topk_anchor = self.transformer(
+            mlvl_feats, mlvl_masks, None, mlvl_positional_encodings, dn_label_query, dn_bbox_query, attn_mask, encoder,
+            reg_branches=self.reg_branches if self.with_box_refine else None,
+            cls_branches=self.cls_branches if self.as_two_stage else None)
+        hs = hs.permute(0, 2, 1, 3)
+        if dn_label_query is not None and dn_label_query.size(1) == 0:
+            hs[0] += self.label_embedding.weight[0, 0] * 0.0
+        outputs_classes, outputs_coords = [], []
+        for lvl in range(hs.shape[0]):
+            reference = inverse_sigmoid(inter_references[lvl], eps=1e-3)
+            outputs_class = self.cls_branches[lvl](hs[lvl])
+            tmp = self.reg_branches[lvl](hs[lvl]).float()
+            if reference.shape[-1] == 4:
+                tmp = tmp + reference
+            else:
+                assert reference.shape[-1] == 2
+                tmp = torch.cat([tmp[..., :2] + reference, tmp[..., 2:]], -1)
+            outputs_classes.append(outputs_class)
+            outputs_coords.append(tmp.sigmoid())
+        return torch.stack(outputs_classes), torch.stack(outputs_coords), topk_score, topk_anchor
+
+    # -- losses ----------------------------------------------------------
+    @staticmethod
+    def extract_dn_outputs(all_cls_scores, all_bbox_preds, dn_meta):
+        if dn_meta is not None:
+            ps = dn_meta['pad_size']
+            return (all_cls_scores[:, :, ps:, :], all_bbox_preds[:, :, ps:, :], all_cls_scores[:, :, :ps, :],
+                    all_bbox_preds[:, :, :ps, :])
+        return all_cls_scores, all_bbox_preds, None, None
+
+    def loss(self, all_cls_scores, all_bbox_preds, enc_topk_scores, enc_topk_anchors, gt_bboxes_list, gt_labels_list,
+             img_metas, dn_meta=None, gt_bboxes_ignore=None):
+        assert gt_bboxes_ignore is None, \
+            '%s only supports for gt_bboxes_ignore setting to None.' % self.__class__.__name__
+        all_cls_scores, all_bbox_preds = all_cls_scores.float(), all_bbox_preds.float()   # @force_fp32
+        loss_dict = dict()
+        all_cls_scores, all_bbox_preds, dn_cls_scores, dn_bbox_preds = self.extract_dn_outputs(
+            all_cls_scores, all_bbox_preds, dn_meta)
+        # matching part: stack [encoder proposals, decoder layers] -> (1+L, B, Nq, .)
+        stacks_cls, stacks_box = all_cls_scores, all_bbox_preds
+        if enc_topk_scores is not None:
+            stacks_cls = torch.cat([enc_topk_scores.float()[None], all_cls_scores], 0)
+            stacks_box = torch.cat([enc_topk_anchors.float()[None], all_bbox_preds], 0)
+        targets = self.get_targets_batched(stacks_cls, stacks_box, gt_bboxes_list, gt_labels_list, img_metas)
+        dn_t = None
+        pos_counts = [int(x) for x in targets['num_pos']]
+        neg_counts = [targets['num_total'] - x for x in pos_counts]
+        if dn_cls_scores is not None:
+            dn_t = self.get_dn_target(dn_bbox_preds[0], gt_bboxes_list, gt_labels_list, img_metas, dn_meta)
+            pos_counts.append(dn_t['num_pos'])
+            neg_counts.append(dn_t['num_neg'])
+        cls_factors, pos_factors = self._avg_factors(pos_counts, neg_counts, stacks_cls)
+        losses = [self.loss_single(stacks_cls[i], stacks_box[i], targets, i, img_metas, cls_factors[i], pos_factors[i])
+                  for i in range(len(stacks_cls))]
+        if enc_topk_scores is not None:
+            (loss_dict['interm_loss_cls'], loss_dict['interm_loss_bbox'], loss_dict['interm_loss_iou']) = losses[0]
+            losses = losses[1:]
+        loss_dict['loss_cls'], loss_dict['loss_bbox'], loss_dict['loss_iou'] = losses[-1]
+        for n, (lc, lb, li) in enumerate(losses[:-1]):
+            loss_dict['d%d.loss_cls' % n], loss_dict['d%d.loss_bbox' % n], loss_dict['d%d.loss_iou' % n] = lc, lb, li
+        if dn_cls_scores is not None:
+            dn_losses = [self.loss_dn_single(dn_cls_scores[i], dn_bbox_preds[i], dn_t, img_metas, cls_factors[-1],
+                                             pos_factors[-1]) for i in range(len(dn_cls_scores))]
+            loss_dict['dn_loss_cls'], loss_dict['dn_loss_bbox'], loss_dict['dn_loss_iou'] = dn_losses[-1]
+            for n, (lc, lb, li) in enumerate(dn_losses[:-1]):
+                loss_dict['d%d.dn_loss_cls' % n], loss_dict['d%d.dn_loss_bbox' % n], loss_dict['d%d.dn_loss_iou' % n] = lc, lb, li
+        return loss_dict
+
+    @torch.no_grad()
+    def get_targets_batched(self, cls_scores, bbox_preds, gt_bboxes_list, gt_labels_list, img_metas):
+        """Hungarian targets for all (layer, image) pairs: cost on GPU, ONE D2H copy,
+        scipy per problem, ONE H2D copy of the index lists (detr_head.py:475-543)."""
+        nl, B, Nq, _ = cls_scores.shape
+        dev = cls_scores.device
+        costs, sizes = [], []
+        for b in range(B):
+            n = int(gt_labels_list[b].numel())
+            sizes.append(n)
+            if n:
+                c = self.assigner.cost(bbox_preds[:, b], cls_scores[:, b], gt_bboxes_list[b], gt_labels_list[b],
+                                       img_metas[b]['img_shape'])
+                costs.append(c.reshape(-1))
+        flat = torch.cat(costs).cpu().numpy() if costs else np.zeros(0, np.float32)
+        rows, cols, off = [], [], 0
+        for b in range(B):
+            n = sizes[b]
+            if not n:
+                continue
+            cb = flat[off:off + nl * Nq * n].reshape(nl, Nq, n)
+            off += nl * Nq * n
+            for l in range(nl):
+                r, c = HungarianAssigner.solve(cb[l])
+                rows.append(((l * B + b) * Nq + r).astype(np.int64))      # flat index into (nl, B, Nq)
+                cols.append(np.stack([np.full_like(c, b), c]).astype(np.int64))
+        labels = torch.full((nl * B * Nq,), self.num_classes, dtype=torch.long, device=dev)
+        bbox_targets = torch.zeros(nl * B * Nq, 4, device=dev)
+        bbox_weights = torch.zeros(nl * B * Nq, 4, device=dev)
+        num_pos = np.zeros(nl, dtype=np.int64)
+        if rows:
+            rows_t = torch.from_numpy(np.concatenate(rows)).to(dev, non_blocking=True)
+            cols_np = np.concatenate(cols, 1)
+            gt_off = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+            gidx = torch.from_numpy(gt_off[cols_np[0]] + cols_np[1]).to(dev, non_blocking=True)
+            gl = torch.cat(gt_labels_list)
+            factors = torch.cat([gt_bboxes_list[b].new_tensor(
+                [img_metas[b]['img_shape'][1], img_metas[b]['img_shape'][0]] * 2).expand(sizes[b], 4) for b in range(B)])
+            gb = bbox_xyxy_to_cxcywh(torch.cat(gt_bboxes_list) / factors)
+            labels[rows_t] = gl[gidx]
+            bbox_targets[rows_t] = gb[gidx]
+            bbox_weights[rows_t] = 1.0
+            for r in rows:
+                num_pos[r[0] // (B * Nq)] += len(r)
+        return dict(labels=labels.view(nl, B * Nq), bbox_targets=bbox_targets.view(nl, B * Nq, 4),
+                    bbox_weights=bbox_weights.view(nl, B * Nq, 4), num_pos=num_pos, num_total=B * Nq)
+
+    def _avg_factors(self, pos_counts, neg_counts, like):
+        """cls_avg_factor / num_total_pos of every loss_single call of this step
+        (detr_head.py:372-391, dino_head.py:262-284) with ONE packed all-reduce instead of
+        two reduce_mean + .item() per call."""
+        pos = torch.tensor([float(x) for x in pos_counts], dtype=torch.float64)
+        neg = torch.tensor([float(x) for x in neg_counts], dtype=torch.float64)
+        cls_avg = pos * 1.0 + neg * self.bg_cls_weight
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            packed = torch.cat([cls_avg, pos]).to(like.device, torch.float32)
+            dist.all_reduce(packed)
+            packed = (packed / dist.get_world_size()).cpu().double()
+            mean_cls_avg, pos = packed[:len(pos)], packed[len(pos):]
+            if self.sync_cls_avg_factor:
+                cls_avg = mean_cls_avg
+        return [max(float(c), 1) for c in cls_avg], [max(float(p), 1.0) for p in pos]
+
+    def _box_losses(self, bbox_preds, bbox_targets, bbox_weights, img_metas, num_total_pos, any_pos):
+        factors = torch.cat([bbox_preds.new_tensor([m['img_shape'][1], m['img_shape'][0]] * 2).expand(
+            bbox_preds.size(1), 4) for m in img_metas], 0)
+        bp = bbox_preds.reshape(-1, 4)
+        bboxes = bbox_cxcywh_to_xyxy(bp) * factors
+        bboxes_gt = bbox_cxcywh_to_xyxy(bbox_targets) * factors
+        loss_iou = self.loss_iou(bboxes, bboxes_gt, bbox_weights, avg_factor=num_total_pos, any_positive=any_pos)
+        loss_bbox = self.loss_bbox(bp, bbox_targets, bbox_weights, avg_factor=num_total_pos)
+        return loss_bbox, loss_iou
+
+    def loss_single(self, cls_scores, bbox_preds, targets, i, img_metas, cls_avg_factor, num_total_pos):
+        """detr_head.py:333-416 with the targets / averaging factors of layer i precomputed."""
+        npos = int(targets['num_pos'][i])
+        labels = targets['labels'][i]
+        loss_cls = self.loss_cls(cls_scores.reshape(-1, self.cls_out_channels), labels, labels.new_ones(
+            labels.shape, dtype=torch.float32), avg_factor=cls_avg_factor)
+        loss_bbox, loss_iou = self._box_losses(bbox_preds, targets['bbox_targets'][i], targets['bbox_weights'][i],
+                                               img_metas, num_total_pos, npos > 0)
+        return loss_cls, loss_bbox, loss_iou
+
+    @torch.no_grad()
+    def get_dn_target(self, dn_bbox_pred, gt_bboxes_list, gt_labels_list, img_metas, dn_meta):
+        """dino_head.py:311-365: fixed (non-Hungarian) targets of the denoising queries."""
+        num_groups, pad_size = dn_meta['num_dn_group'], dn_meta['pad_size']
+        assert pad_size % num_groups == 0
+        single_pad = pad_size // num_groups
+        B, num_bboxes, _ = dn_bbox_pred.shape
+        dev = dn_bbox_pred.device
+        labels = torch.full((B, num_bboxes), self.num_classes, dtype=torch.long, device=dev)
+        bbox_targets = torch.zeros(B, num_bboxes, 4, device=dev)
+        bbox_weights = torch.zeros(B, num_bboxes, 4, device=dev)
+        npos = nneg = 0
+        for b in range(B):
+            n = int(gt_labels_list[b].numel())
+            if n == 0:
+                continue
+            t = torch.arange(n, device=dev).unsqueeze(0).repeat(num_groups, 1)
+            pos_inds = ((torch.arange(num_groups, device=dev) * single_pad).unsqueeze(1) + t).flatten()
+            labels[b, pos_inds] = gt_labels_list[b][t.flatten()]
+            bbox_weights[b, pos_inds] = 1.0
+            img_h, img_w, _ = img_metas[b]['img_shape']
+            factor = dn_bbox_pred.new_tensor([img_w, img_h, img_w, img_h]).unsqueeze(0)
+            bbox_targets[b, pos_inds] = bbox_xyxy_to_cxcywh(gt_bboxes_list[b] / factor).repeat([num_groups, 1])
+            npos += n * num_groups
+            nneg += n * num_groups
+        return dict(labels=labels.view(-1), bbox_targets=bbox_targets.view(-1, 4), bbox_weights=bbox_weights.view(-1, 4),
+                    num_pos=npos, num_neg=nneg)
+
+    def loss_dn_single(self, dn_cls_scores, dn_bbox_preds, t, img_metas, cls_avg_factor, num_total_pos):
+        cls_scores = dn_cls_scores.reshape(-1, self.cls_out_channels)
+        if len(cls_scores) > 0:
+            loss_cls = self.loss_cls(cls_scores, t['labels'], t['labels'].new_ones(t['labels'].shape, dtype=torch.float32),
+                                     avg_factor=cls_avg_factor)
+        else:
+            loss_cls = torch.zeros(1, dtype=cls_scores.dtype, device=cls_scores.device)
+        loss_bbox, loss_iou = self._box_losses(dn_bbox_preds, t['bbox_targets'], t['bbox_weights'], img_metas,
+                                               num_total_pos, t['num_pos'] > 0)
+        return loss_cls, loss_bbox, loss_iou
+
+    # -- test ------------------------------------------------------------
+    def simple_test(self, feats, img_metas, shared_encoder=None, rescale=False):
+        outs = self.forward(shared_encoder, feats, img_metas)
+        return self.get_bboxes(*outs, img_metas, rescale=rescale)
+
+    def get_bboxes(self, all_cls_scores, all_bbox_preds, enc_cls_scores, enc_bbox_preds, img_metas, rescale=False):
+        """detr_head.py:_get_bboxes_single (sigmoid branch): top max_per_img over Nq*C."""
+        cls_scores, bbox_preds = all_cls_scores[-1].float(), all_bbox_preds[-1].float()
+        results = []
+        max_per_img = self.test_cfg.get('max_per_img', self.num_query)
+        for img_id in range(len(img_metas)):
+            cls_score, bbox_pred = cls_scores[img_id].sigmoid(), bbox_preds[img_id]
+            scores, indexes = cls_score.view(-1).topk(max_per_img)
+            det_labels = indexes % self.num_classes
+            bbox_pred = bbox_pred[indexes // self.num_classes]
+            img_shape = img_metas[img_id]['img_shape']
+            det_bboxes = bbox_cxcywh_to_xyxy(bbox_pred)
+            det_bboxes[:, 0::2] = (det_bboxes[:, 0::2] * img_shape[1]).clamp(min=0, max=img_shape[1])
+            det_bboxes[:, 1::2] = (det_bboxes[:, 1::2] * img_shape[0]).clamp(min=0, max=img_shape[0])
+            if rescale:
+                det_bboxes = det_bboxes / det_bboxes.new_tensor(img_metas[img_id]['scale_factor'])
+            results.append((torch.cat((det_bboxes, scores.unsqueeze(1)), -1), det_labels))
+        return results

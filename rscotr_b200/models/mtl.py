@@ -1,0 +1,260 @@
+"""MTL: shared Swin backbone + neck + shared deformable encoder + three task heads,
+one task per iteration.  Same constructor arguments, method names, train_step
+contract and loss/log keys as the reference's models/multi/multitask_learner.py:34-353."""
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..config import MODELS, build_from_cfg
+from .bricks import MultiScaleDeformableAttention, build_transformer_layer_sequence
+from .cls_head import Augments
+from .seg_head import resize
+
+supported_tasks = ('cls', 'det', 'seg')
+
+
+def add_prefix(inputs, prefix):
+    return {'%s.%s' % (prefix, k): v for k, v in inputs.items()}
+
+
+def _build(cfg):
+    if isinstance(cfg, nn.Module) or cfg is None:
+        return cfg
+    return build_from_cfg(dict(cfg), MODELS)
+
+
+def bbox2result(bboxes, labels, num_classes):
+    if bboxes.shape[0] == 0:
+        import numpy as np
+        return [np.zeros((0, 5), dtype=np.float32) for _ in range(num_classes)]
+    bboxes, labels = bboxes.detach().cpu().numpy(), labels.detach().cpu().numpy()
+    return [bboxes[labels == i, :] for i in range(num_classes)]
+
+
+@MODELS.register_module()
+class MTL(nn.Module):
+    PALETTE = None
+
+    def __init__(self, backbone, neck, shared_encoder, cls_head=None, bbox_head=None, seg_head=None, task_weight=None,
+                 train_cfg=None, test_cfg=None, init_cfg=None):
+        super().__init__()
+        self.backbone = _build(backbone)
+        self.neck = _build(neck)
+        self.shared_encoder = build_transformer_layer_sequence(shared_encoder)
+        self.task_weight = dict(cls=1, det=1, seg=1)
+        if task_weight is not None:
+            assert isinstance(task_weight, dict)
+            self.task_weight.update(task_weight)
+        train_cfg = train_cfg or dict(cls=dict(), det=None, seg=dict())
+        test_cfg = test_cfg or dict(cls=dict(), det=dict(max_per_img=100), seg=dict(mode='whole'))
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.cls_augments = None
+        cls_augments_cfg = (train_cfg.get('cls') or {}).get('augments', None)
+        if cls_augments_cfg is not None:
+            self.cls_augments = Augments(cls_augments_cfg)
+        if bbox_head is not None and not isinstance(bbox_head, nn.Module):
+            bbox_head = dict(bbox_head)
+            bbox_head.update(train_cfg=train_cfg.get('det'))
+            bbox_head.update(test_cfg=test_cfg.get('det'))
+        self.task_pretrain = train_cfg.get('task_pretrain', None)
+        self.cls_head = _build(cls_head)
+        self.bbox_head = _build(bbox_head)
+        self.seg_head = _build(seg_head)
+        self.CLASSES = None
+
+    def init_weights(self):
+        for layer in self.shared_encoder.layers:
+            for attn in layer.attentions:
+                if isinstance(attn, MultiScaleDeformableAttention):
+                    attn.init_weights()
+
+    def extract_feat(self, img):
+        backbone_feature = self.backbone(img)
+        neck_feature = self.neck(backbone_feature[-3:])
+        return neck_feature, backbone_feature
+
+    def forward_train(self, task, *args, **kwargs):
+        assert task in supported_tasks
+        return getattr(self, 'forward_train_%s' % task)(*args, **kwargs)
+
+    def forward_test(self, task, img, img_metas, *args, **kwargs):
+        if isinstance(task, list):
+            task = list(set(task))
+            if len(task) == 1:
+                task = task[0]
+            else:
+                raise NotImplementedError('The current implementation only support same task in a batch')
+        if isinstance(img, list):
+            if len(img) != 1:
+                raise NotImplementedError('The current implementation does not support TTA ')
+            img = img[0]
+        if isinstance(img_metas[0], list):
+            img_metas = img_metas[0]
+        return self.simple_test(task, img, img_metas, *args, **kwargs)
+
+    def simple_test(self, task, *args, **kwargs):
+        assert task in supported_tasks
+        return getattr(self, 'simple_test_%s' % task)(*args, **kwargs)
+
+    def forward_train_cls(self, img, gt_label, **kwargs):
+        if self.cls_augments is not None:
+            img, gt_label = self.cls_augments(img, gt_label)
+        neck_feature, backbone_feature = self.extract_feat(img)
+        losses = dict()
+        losses.update(self.cls_head.forward_train(neck_feature, backbone_feature, gt_label, self.shared_encoder))
+        return losses
+
+    def forward_train_det(self, img, img_metas, gt_bboxes, gt_labels, gt_bboxes_ignore=None):
+        batch_input_shape = tuple(img[0].size()[-2:])
+        for img_meta in img_metas:
+            img_meta['batch_input_shape'] = batch_input_shape
+        x = self.extract_feat(img)[0]
+        return self.bbox_head.forward_train(x, img_metas, gt_bboxes, gt_labels, gt_bboxes_ignore, self.shared_encoder)
+
+    def forward_train_seg(self, img, img_metas, gt_semantic_seg):
+        neck_feature, backbone_feature = self.extract_feat(img)
+        losses = dict()
+        loss_decode = self.seg_head.forward_train(neck_feature, backbone_feature, img_metas, gt_semantic_seg,
+                                                  self.shared_encoder)
+        losses.update(add_prefix(loss_decode, 'seg'))
+        return losses
+
+    def simple_test_cls(self, img, img_metas=None, **kwargs):
+        neck_feature, backbone_feature = self.extract_feat(img)
+        return self.cls_head.simple_test(neck_feature, backbone_feature, shared_encoder=self.shared_encoder, **kwargs)
+
+    def simple_test_det(self, img, img_metas, rescale=False):
+        for m in img_metas:
+            m['batch_input_shape'] = tuple(img.size()[-2:])
+        feat = self.extract_feat(img)[0]
+        results_list = self.bbox_head.simple_test(feat, img_metas, rescale=rescale, shared_encoder=self.shared_encoder)
+        return [bbox2result(b, l, self.bbox_head.num_classes) for b, l in results_list]
+
+    def whole_inference_seg(self, img, img_meta, rescale):
+        neck_feature, backbone_feature = self.extract_feat(img)
+        seg_logit = self.seg_head.forward_test(neck_feature, backbone_feature, img_meta, self.shared_encoder)
+        seg_logit = resize(seg_logit, size=img.shape[2:])
+        if rescale:
+            resize_shape = img_meta[0]['img_shape'][:2]
+            seg_logit = seg_logit[:, :, :resize_shape[0], :resize_shape[1]]
+            seg_logit = resize(seg_logit.contiguous(), size=img_meta[0]['ori_shape'][:2])
+        return seg_logit
+
+    def inference_seg(self, img, img_meta, rescale):
+        assert self.test_cfg['seg']['mode'] in ['whole']
+        ori_shape = img_meta[0]['ori_shape']
+        assert all(_['ori_shape'] == ori_shape for _ in img_meta)
+        seg_logit = self.whole_inference_seg(img, img_meta, rescale)
+        output = F.softmax(seg_logit.float(), dim=1)
+        if img_meta[0].get('flip', False):
+            flip_direction = img_meta[0]['flip_direction']
+            assert flip_direction in ['horizontal', 'vertical']
+            output = output.flip(dims=(3,)) if flip_direction == 'horizontal' else output.flip(dims=(2,))
+        return output
+
+    def simple_test_seg(self, img, img_meta, rescale=True):
+        seg_pred = self.inference_seg(img, img_meta, rescale).argmax(dim=1)
+        return list(seg_pred.cpu().numpy())
+
+    def train_step(self, data, optimizer):
+        losses = self(**data)
+        loss, log_vars = self._parse_losses(losses)
+        task = data.get('task', None)
+        dataset_name = data.get('dataset_name', None)
+        log_vars = add_prefix(log_vars, '%s.%s' % (task, dataset_name))
+        if hasattr(self, 'task_weight'):
+            weight = self.task_weight[task]
+            loss = loss * weight
+            log_vars = {k: v * weight for k, v in log_vars.items()}
+        return dict(loss=loss, log_vars=log_vars, num_samples=len(data['img_metas']))
+
+    def val_step(self, data, optimizer=None):
+        losses = self(**data)
+        loss, log_vars = self._parse_losses(losses)
+        log_vars = add_prefix(log_vars, '%s.%s' % (data.get('task', None), data.get('dataset_name', None)))
+        return dict(loss=loss, log_vars=log_vars, num_samples=len(data['img_metas']))
+
+    def forward(self, task, img, img_metas, return_loss=True, dataset_name=None, **kwargs):
+        if return_loss:
+            return self.forward_train(task=task, img=img, img_metas=img_metas, **kwargs)
+        return self.forward_test(task=task, img=img, img_metas=img_metas, **kwargs)
+
+    def _parse_losses(self, losses):
+        """Same totals / log keys as multitask_learner.py:274-306, but ONE device->host
+        transfer and (distributed) ONE packed all-reduce instead of one per log var."""
+        log_vars = OrderedDict()
+        for loss_name, loss_value in losses.items():
+            if isinstance(loss_value, torch.Tensor):
+                log_vars[loss_name] = loss_value.mean()
+            elif isinstance(loss_value, list):
+                log_vars[loss_name] = sum(_loss.mean() for _loss in loss_value)
+            else:
+                raise TypeError('%s is not a tensor or list of tensors' % loss_name)
+        loss = sum(_value for _key, _value in log_vars.items() if 'loss' in _key)
+        log_vars['loss'] = loss
+        packed = torch.stack([v.detach().float().reshape(()) for v in log_vars.values()])
+        if dist.is_available() and dist.is_initialized():
+            n = torch.cat([packed.new_tensor([float(len(log_vars))]), packed])
+            dist.all_reduce(n)
+            world = dist.get_world_size()
+            assert int(round(float(n[0]))) == len(log_vars) * world, \
+                'loss log variables are different across GPUs!\nrank %d len(log_vars): %d keys: %s' % (
+                    dist.get_rank(), len(log_vars), ','.join(log_vars.keys()))
+            packed = n[1:] / world
+        self._last_log_tensor = packed
+        self._last_log_keys = list(log_vars.keys())
+        return loss, _LazyLogVars(self._last_log_keys, packed)
+
+    def load_task_pretrain(self):
+        if self.task_pretrain is None:
+            print('You did not set task_pretrain, hence it is skipped.')
+            return
+        rule = self.task_pretrain.get('rule', None)
+        sd = torch.load(self.task_pretrain['pretrained'], map_location='cpu')
+        if 'state_dict' in sd:
+            sd = sd['state_dict']
+        if rule == 'dino_mmdet':
+            out = OrderedDict()
+            for name, param in sd.items():
+                if name.startswith('neck') and name.endswith('conv.bias'):
+                    continue
+                new_name = name.replace('bbox_head.transformer.encoder', 'shared_encoder', 1) \
+                    if name.startswith('bbox_head.transformer.encoder') else name
+                assert new_name not in out, '%s-->%s' % (name, new_name)
+                out[new_name] = param
+            sd = out
+        incompatible = self.load_state_dict(sd, strict=False)
+        print('load task pretrain of rule:%s\nincompatiblekeys: %s' % (rule, incompatible))
+
+
+class _LazyLogVars(OrderedDict):
+    """log_vars whose float values are materialised (one D2H copy) on first read, so a
+    training loop that only logs every N iterations never syncs in between."""
+
+    def __init__(self, keys, packed):
+        super().__init__()
+        self._keys, self._packed, self._done = keys, packed, False
+        for k in keys:
+            OrderedDict.__setitem__(self, k, None)
+
+    def _materialise(self):
+        if not self._done:
+            vals = self._packed.tolist()
+            for k, v in zip(self._keys, vals):
+                OrderedDict.__setitem__(self, k, v)
+            self._done = True
+
+    def __getitem__(self, k):
+        self._materialise()
+        return OrderedDict.__getitem__(self, k)
+
+    def items(self):
+        self._materialise()
+        return OrderedDict.items(self)
+
+    def values(self):
+        self._materialise()
+        return OrderedDict.values(self)

@@ -1,0 +1,214 @@
+"""Swin Transformer backbone with the mmdet 2.25.1 `SwinTransformer` signature
+and state-dict layout (reference call site
+models/multi/multitask_learner.py:83, config
+configs/multi/MTL_slvlcls_swin-t-p4-w7_1x1_resisc&dior&potsdam.py:9-25).
+
+Differences from the eager mmdet module are purely structural:
+  * ShiftWindowMSA's pad / roll / partition / attention / reverse / unroll /
+    crop chain is ONE kernel (ops.wmsa); the qkv Linear runs on the un-padded
+    tokens and padded rows are synthesised from the qkv bias inside the kernel.
+  * PatchMerging's unfold + LayerNorm is one kernel (ops.patch_merge_ln).
+  * feature maps are returned as logical (B,C,H,W) tensors with channels-last
+    strides (a view of the token tensor; no transpose copy).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..config import MODELS
+from .bricks import FFN, DropPath
+
+
+class WindowMSA(nn.Module):
+    def __init__(self, embed_dims, num_heads, window_size, qkv_bias=True, qk_scale=None, attn_drop_rate=0.,
+                 proj_drop_rate=0.):
+        super().__init__()
+        assert attn_drop_rate == 0., 'attention dropout is not used by any reference config'
+        self.embed_dims = embed_dims
+        self.window_size = window_size  # (Wh, Ww)
+        self.num_heads = num_heads
+        head_embed_dims = embed_dims // num_heads
+        self.scale = qk_scale or head_embed_dims ** -0.5
+        self.relative_position_bias_table = nn.Parameter(
+            torch.zeros((2 * window_size[0] - 1) * (2 * window_size[1] - 1), num_heads))
+        Wh, Ww = window_size
+        rel_index_coords = self.double_step_seq(2 * Ww - 1, Wh, 1, Ww)
+        rel_position_index = rel_index_coords + rel_index_coords.T
+        self.register_buffer('relative_position_index', rel_position_index.flip(1).contiguous())
+        self.qkv = nn.Linear(embed_dims, embed_dims * 3, bias=qkv_bias)
+        self.proj = nn.Linear(embed_dims, embed_dims)
+        self.proj_drop = nn.Dropout(proj_drop_rate)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+
+    @staticmethod
+    def double_step_seq(step1, len1, step2, len2):
+        seq1 = torch.arange(0, step1 * len1, step1)
+        seq2 = torch.arange(0, step2 * len2, step2)
+        return (seq1[:, None] + seq2[None, :]).reshape(1, -1)
+
+
+class ShiftWindowMSA(nn.Module):
+    def __init__(self, embed_dims, num_heads, window_size, shift_size=0, qkv_bias=True, qk_scale=None,
+                 attn_drop_rate=0, proj_drop_rate=0, dropout_layer=dict(type='DropPath', drop_prob=0.)):
+        super().__init__()
+        self.window_size = window_size
+        self.shift_size = shift_size
+        assert 0 <= self.shift_size < self.window_size
+        self.w_msa = WindowMSA(embed_dims, num_heads, (window_size, window_size), qkv_bias, qk_scale, attn_drop_rate,
+                               proj_drop_rate)
+        self.drop = DropPath(dropout_layer.get('drop_prob', 0.))
+
+    def forward(self, query, hw_shape):
+        B, L, C = query.shape
+        H, W = hw_shape
+        assert L == H * W, 'input feature has wrong size'
+        m = self.w_msa
+        qkv = m.qkv(query)                                   # GEMM on the L real tokens
+        out = ops.wmsa(qkv, m.qkv.bias, m.relative_position_bias_table, (H, W), m.num_heads, self.window_size,
+                       self.shift_size, m.scale)             # fused attention core
+        out = m.proj_drop(m.proj(out))
+        return self.drop(out)
+
+
+class SwinBlock(nn.Module):
+    def __init__(self, embed_dims, num_heads, feedforward_channels, window_size=7, shift=False, qkv_bias=True,
+                 qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0., act_cfg=dict(type='GELU'),
+                 with_cp=False):
+        super().__init__()
+        self.with_cp = with_cp
+        self.norm1 = nn.LayerNorm(embed_dims)
+        self.attn = ShiftWindowMSA(embed_dims, num_heads, window_size, window_size // 2 if shift else 0, qkv_bias,
+                                   qk_scale, attn_drop_rate, drop_rate, dict(type='DropPath', drop_prob=drop_path_rate))
+        self.norm2 = nn.LayerNorm(embed_dims)
+        self.ffn = FFN(embed_dims, feedforward_channels, 2, act_cfg, drop_rate,
+                       dict(type='DropPath', drop_prob=drop_path_rate), add_identity=True)
+
+    def forward(self, x, hw_shape):
+        identity = x
+        x = self.norm1(x)
+        x = self.attn(x, hw_shape)
+        x = x + identity
+        identity = x
+        x = self.norm2(x)
+        return self.ffn(x, identity=identity)
+
+
+class PatchMerging(nn.Module):
+    """mmdet PatchMerging (kernel 2, stride 2, 'corner' padding, nn.Unfold channel order)."""
+
+    def __init__(self, in_channels, out_channels, stride=2):
+        super().__init__()
+        assert stride == 2
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.norm = nn.LayerNorm(4 * in_channels)
+        self.reduction = nn.Linear(4 * in_channels, out_channels, bias=False)
+
+    def forward(self, x, input_size):
+        H, W = input_size
+        x = ops.patch_merge_ln(x, (H, W), self.norm.weight, self.norm.bias, self.norm.eps)
+        return self.reduction(x), ((H + 1) // 2, (W + 1) // 2)
+
+
+class SwinBlockSequence(nn.Module):
+    def __init__(self, embed_dims, num_heads, feedforward_channels, depth, window_size=7, qkv_bias=True, qk_scale=None,
+                 drop_rate=0., attn_drop_rate=0., drop_path_rate=0., downsample=None, act_cfg=dict(type='GELU'),
+                 with_cp=False):
+        super().__init__()
+        dprs = drop_path_rate if isinstance(drop_path_rate, (list, tuple)) else [drop_path_rate] * depth
+        self.blocks = nn.ModuleList([
+            SwinBlock(embed_dims, num_heads, feedforward_channels, window_size, i % 2 == 1, qkv_bias, qk_scale,
+                      drop_rate, attn_drop_rate, dprs[i], act_cfg, with_cp) for i in range(depth)])
+        self.downsample = downsample
+
+    def forward(self, x, hw_shape):
+        for block in self.blocks:
+            x = block(x, hw_shape)
+        if self.downsample:
+            x_down, down_hw_shape = self.downsample(x, hw_shape)
+            return x_down, down_hw_shape, x, hw_shape
+        return x, hw_shape, x, hw_shape
+
+
+class PatchEmbed(nn.Module):
+    def __init__(self, in_channels=3, embed_dims=96, kernel_size=4, stride=4, norm=True):
+        super().__init__()
+        self.kernel = kernel_size
+        self.projection = nn.Conv2d(in_channels, embed_dims, kernel_size, stride)
+        self.norm = nn.LayerNorm(embed_dims) if norm else None
+
+    def forward(self, x):
+        H, W = x.shape[-2:]
+        ph, pw = (self.kernel - H % self.kernel) % self.kernel, (self.kernel - W % self.kernel) % self.kernel
+        if ph or pw:
+            x = F.pad(x, (0, pw, 0, ph))     # AdaptivePadding('corner')
+        x = self.projection(x.contiguous(memory_format=torch.channels_last))
+        hw = (x.shape[2], x.shape[3])
+        x = x.permute(0, 2, 3, 1).reshape(x.shape[0], hw[0] * hw[1], x.shape[1])
+        if self.norm is not None:
+            x = self.norm(x)
+        return x, hw
+
+
+@MODELS.register_module()
+class SwinTransformer(nn.Module):
+    ARCH = {'tiny': (96, (2, 2, 6, 2), (3, 6, 12, 24)), 'small': (96, (2, 2, 18, 2), (3, 6, 12, 24)),
+            'base': (128, (2, 2, 18, 2), (4, 8, 16, 32))}
+
+    def __init__(self, pretrain_img_size=224, in_channels=3, embed_dims=96, patch_size=4, window_size=7, mlp_ratio=4,
+                 depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24), strides=(4, 2, 2, 2), out_indices=(0, 1, 2, 3),
+                 qkv_bias=True, qk_scale=None, patch_norm=True, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.1,
+                 use_abs_pos_embed=False, act_cfg=dict(type='GELU'), norm_cfg=dict(type='LN'), with_cp=False,
+                 pretrained=None, convert_weights=False, frozen_stages=-1, init_cfg=None, arch=None, img_size=None):
+        super().__init__()
+        if arch is not None:       # mmcls-style signature (configs/cls/*)
+            embed_dims, depths, num_heads = self.ARCH[arch]
+            out_indices = (3,) if out_indices == (0, 1, 2, 3) else out_indices
+        assert not use_abs_pos_embed, 'no reference config uses the absolute position embedding'
+        assert strides[0] == patch_size
+        self.out_indices = tuple(out_indices)
+        self.convert_weights = convert_weights
+        self.init_cfg = init_cfg
+        self.patch_embed = PatchEmbed(in_channels, embed_dims, patch_size, strides[0], patch_norm)
+        self.drop_after_pos = nn.Dropout(p=drop_rate)
+        total_depth = sum(depths)
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, total_depth)]
+        self.stages = nn.ModuleList()
+        in_ch = embed_dims
+        for i, depth in enumerate(depths):
+            downsample = PatchMerging(in_ch, 2 * in_ch, strides[i + 1]) if i < len(depths) - 1 else None
+            self.stages.append(SwinBlockSequence(
+                in_ch, num_heads[i], mlp_ratio * in_ch, depth, window_size, qkv_bias, qk_scale, drop_rate,
+                attn_drop_rate, dpr[sum(depths[:i]):sum(depths[:i + 1])], downsample, act_cfg, with_cp))
+            if downsample:
+                in_ch = downsample.out_channels
+        self.num_features = [int(embed_dims * 2 ** i) for i in range(len(depths))]
+        for i in self.out_indices:
+            self.add_module('norm%d' % i, nn.LayerNorm(self.num_features[i]))
+        self.init_weights()
+
+    def init_weights(self):
+        """init_cfg=None branch of mmdet (trunc_normal .02 linears, unit LayerNorm).
+        A `Pretrained` init_cfg needs the checkpoint file; absent (no network) the
+        random init stands (bench uses synthetic weights)."""
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+    def forward(self, x):
+        x, hw_shape = self.patch_embed(x)
+        x = self.drop_after_pos(x)
+        outs = []
+        for i, stage in enumerate(self.stages):
+            x, hw_shape, out, out_hw_shape = stage(x, hw_shape)
+            if i in self.out_indices:
+                out = getattr(self, 'norm%d' % i)(out)
+                # logical NCHW, channels-last strides: a view, no transpose copy
+                out = out.view(-1, *out_hw_shape, self.num_features[i]).permute(0, 3, 1, 2)
+                outs.append(out)
+        return outs

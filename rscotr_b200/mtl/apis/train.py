@@ -1,0 +1,35 @@
+"""train_model with the reference's signature (mtl/apis/train.py:24-120)."""
+import logging
+import os
+
+import torch
+import torch.distributed as dist
+
+from ..data import build_datasets, build_dataloaders, build_multidataloader
+from ..engine import StepEngine
+from ..runner import IterBasedRunner, MultiDatasetsEvalHook
+
+
+def train_model(model, datasets, cfg, distributed=False, validate=False, timestamp=None, meta=None):
+    logger = logging.getLogger('rscotr_b200')
+    data_loader = [build_multidataloader(cfg, distributed, datasets)]
+    if distributed and not dist.is_initialized():
+        dist.init_process_group(cfg.get('dist_params', {}).get('backend', 'nccl'))
+    device = 'cuda:%d' % int(os.environ.get('LOCAL_RANK', 0)) if distributed else cfg.get('device', 'cuda')
+    torch.cuda.set_device(device)
+    optimizer_config = cfg.get('optimizer_config', {}) or {}
+    fp16 = cfg.get('fp16', None)
+    engine = StepEngine(model, cfg.optimizer, grad_clip=optimizer_config.get('grad_clip'), device=device,
+                        compute_dtype=cfg.get('compute_dtype', torch.bfloat16 if fp16 is None else torch.float16),
+                        lr_config=cfg.get('lr_config'))
+    runner = IterBasedRunner(engine, cfg.runner['max_iters'], work_dir=cfg.get('work_dir'), logger=logger, meta=meta,
+                             log_interval=cfg.get('log_config', {}).get('interval', 50))
+    runner.timestamp = timestamp
+    if validate:
+        val_dataset = build_datasets(cfg.data, split='val', synthetic=cfg.get('synthetic'))
+        val_dataloader = build_dataloaders(cfg, distributed, val_dataset, train=False)
+        eval_cfg = dict(cfg.get('evaluation', {}))
+        eval_cfg['by_epoch'] = cfg.runner['type'] != 'IterBasedRunner'
+        runner.register_hook(MultiDatasetsEvalHook(val_dataloader, **eval_cfg), priority='LOW')
+    runner.run(data_loader, cfg.get('workflow', [('train', 1)]))
+    return runner

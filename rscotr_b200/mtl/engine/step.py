@@ -1,0 +1,137 @@
+"""Co-training step engine: one task per iteration through the shared backbone and one
+head (reference hot loop: mmcv IterBasedRunner.train + OptimizerHook, SURVEY 3.1 / D.6;
+rows a21-a23 and 8e).
+
+B200-first structure:
+  * every parameter's .grad is a VIEW into one flat fp32 buffer ordered
+    [backbone | cls_head | neck | shared_encoder | bbox_head | seg_head]: zero_grad is
+    one memset (zero-FILL, which is also what the reference's torch-1.11 zero_grad did,
+    SURVEY 3.4), the global-norm clip is one norm + one scale, and the data-parallel
+    exchange is a flat NCCL all-reduce over the contiguous range(s) the current task
+    touches -- gradients only, nothing in forward except the packed loss factors.
+  * bf16 autocast for the GEMMs / kernels, fp32 master weights, fused AdamW.
+  * inputs arrive in pinned host memory and are copied with non_blocking H2D.
+"""
+import torch
+import torch.distributed as dist
+
+from ..utils.optimizer import build_optimizer
+
+_ORDER = ('backbone', 'cls_head', 'neck', 'shared_encoder', 'bbox_head', 'seg_head')
+
+
+def _to_device(obj, device):
+    if torch.is_tensor(obj):
+        return obj.to(device, non_blocking=True)
+    if isinstance(obj, list):
+        return [_to_device(o, device) for o in obj]
+    if isinstance(obj, tuple):
+        return tuple(_to_device(o, device) for o in obj)
+    if isinstance(obj, dict):
+        return {k: _to_device(v, device) for k, v in obj.items()}
+    return obj
+
+
+def h2d_bytes(obj):
+    if torch.is_tensor(obj):
+        return 0 if obj.is_cuda else obj.numel() * obj.element_size()
+    if isinstance(obj, (list, tuple)):
+        return sum(h2d_bytes(o) for o in obj)
+    if isinstance(obj, dict):
+        return sum(h2d_bytes(v) for v in obj.values())
+    return 0
+
+
+class StepEngine:
+    def __init__(self, model, optimizer_cfg, grad_clip=None, device='cuda', compute_dtype=torch.bfloat16,
+                 lr_config=None):
+        self.device = torch.device(device)
+        self.model = model.to(self.device)
+        self.compute_dtype = compute_dtype
+        self.grad_clip = dict(grad_clip) if grad_clip else None
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._build_flat_grads()
+        self.optimizer = build_optimizer(self.model, optimizer_cfg)
+        self._base_lrs = [g['lr'] for g in self.optimizer.param_groups]
+        self.lr_config = dict(lr_config) if lr_config else None
+        self.iter = 0
+        self._task_ranges = {}
+        self.last_grad_norm = None
+
+    # -- flat gradient buffer --------------------------------------------
+    def _build_flat_grads(self):
+        named = list(self.model.named_parameters())
+        def rank(n):
+            top = n.split('.')[0]
+            return _ORDER.index(top) if top in _ORDER else len(_ORDER)
+        order = sorted(range(len(named)), key=lambda i: (rank(named[i][0]), i))
+        total = sum(named[i][1].numel() for i in order if named[i][1].requires_grad)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self._spans = []          # (name, start, end)
+        off = 0
+        for i in order:
+            n, p = named[i]
+            if not p.requires_grad:
+                continue
+            assert p.dtype == torch.float32, 'master weights are fp32'
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            self._spans.append((n, off, off + p.numel()))
+            off += p.numel()
+
+    def _active_ranges(self, task):
+        """contiguous flat ranges that received a gradient for `task` (found once per task)."""
+        if task not in self._task_ranges:
+            flags = torch.stack([(self.flat_grad[s:e] != 0).any() for _, s, e in self._spans]).tolist()
+            if self.world > 1:    # every rank must agree on the ranges
+                t = torch.tensor(flags, device=self.device, dtype=torch.int32)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                flags = t.bool().tolist()
+            tops = {}
+            for (n, s, e), f in zip(self._spans, flags):
+                top = n.split('.')[0]
+                lo, hi, any_f = tops.get(top, (s, e, False))
+                tops[top] = (min(lo, s), max(hi, e), any_f or f)
+            ranges = []
+            for top, (lo, hi, f) in sorted(tops.items(), key=lambda kv: kv[1][0]):
+                if not f:
+                    continue
+                if ranges and ranges[-1][1] == lo:
+                    ranges[-1] = (ranges[-1][0], hi)
+                else:
+                    ranges.append((lo, hi))
+            self._task_ranges[task] = ranges
+        return self._task_ranges[task]
+
+    # -- lr schedule (mmcv StepLrUpdaterHook, by_epoch=False) --------------
+    def _update_lr(self):
+        if not self.lr_config or self.lr_config.get('policy') != 'step':
+            return
+        steps = self.lr_config['step']
+        steps = [steps] if isinstance(steps, int) else steps
+        gamma = self.lr_config.get('gamma', 0.1)
+        exp = sum(self.iter >= s for s in steps)
+        for g, base in zip(self.optimizer.param_groups, self._base_lrs):
+            g['lr'] = base * gamma ** exp
+
+    # -- one co-training iteration ------------------------------------------
+    def train_iter(self, data_batch):
+        """model.train_step + OptimizerHook.after_train_iter.  Returns train_step's outputs."""
+        data = _to_device(data_batch, self.device)
+        self._update_lr()
+        self.flat_grad.zero_()
+        with torch.autocast('cuda', dtype=self.compute_dtype, enabled=self.compute_dtype != torch.float32):
+            outputs = self.model.train_step(data, self.optimizer)
+        outputs['loss'].backward()
+        if self.world > 1:
+            for lo, hi in self._active_ranges(data['task']):
+                seg = self.flat_grad[lo:hi]
+                dist.all_reduce(seg)
+                seg.div_(self.world)
+        if self.grad_clip:
+            max_norm = float(self.grad_clip['max_norm'])
+            total_norm = torch.linalg.vector_norm(self.flat_grad, float(self.grad_clip.get('norm_type', 2)))
+            self.flat_grad.mul_(torch.clamp(max_norm / (total_norm + 1e-6), max=1.0))
+            self.last_grad_norm = total_norm
+        self.optimizer.step()
+        self.iter += 1
+        return outputs

@@ -1,0 +1,54 @@
+"""build_optimizer with the reference's paramwise rules (mtl/utils/optimizer.py:25-55 +
+mmcv DefaultOptimizerConstructor custom_keys): for each parameter the
+first custom key (sorted by length desc, then alphabetically) that is a SUBSTRING of
+the full parameter name sets lr_mult / decay_mult.  Parameters with identical
+(lr, weight_decay) share one param group (mmcv makes one group per parameter; the
+update is identical, the launch count is not)."""
+import copy
+
+import torch
+
+
+def param_settings(model, optimizer_cfg, paramwise_cfg):
+    base_lr = optimizer_cfg['lr']
+    base_wd = optimizer_cfg.get('weight_decay', None)
+    custom_keys = (paramwise_cfg or {}).get('custom_keys', {})
+    sorted_keys = sorted(sorted(custom_keys.keys()), key=len, reverse=True)
+    out = []
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        lr, wd = base_lr, base_wd
+        for key in sorted_keys:
+            if key in name:
+                lr = base_lr * custom_keys[key].get('lr_mult', 1.)
+                if base_wd is not None:
+                    wd = base_wd * custom_keys[key].get('decay_mult', 1.)
+                break
+        out.append((name, p, lr, wd))
+    return out
+
+
+def build_optimizer(model, cfg):
+    optimizer_cfg = copy.deepcopy(dict(cfg))
+    constructor_type = optimizer_cfg.pop('constructor', 'MTLOptimizerConstructor')
+    if constructor_type not in ('MTLOptimizerConstructor', 'DefaultOptimizerConstructor'):
+        raise KeyError('%s is not registered in the optimizer builder registry.' % constructor_type)
+    paramwise_cfg = optimizer_cfg.pop('paramwise_cfg', None)
+    if hasattr(model, 'module'):
+        model = model.module
+    opt_type = optimizer_cfg.pop('type')
+    groups = {}
+    for name, p, lr, wd in param_settings(model, optimizer_cfg, paramwise_cfg):
+        groups.setdefault((lr, wd), []).append(p)
+    params = []
+    for (lr, wd), ps in groups.items():
+        g = dict(params=ps, lr=lr)
+        if wd is not None:
+            g['weight_decay'] = wd
+        params.append(g)
+    cls = getattr(torch.optim, opt_type)
+    kwargs = dict(optimizer_cfg)
+    if opt_type in ('AdamW', 'Adam') and all(p.is_cuda for g in params for p in g['params']):
+        kwargs.setdefault('fused', True)
+    return cls(params, **kwargs)

@@ -1,0 +1,139 @@
+"""CPU tests of the host-side logic (config loading, registry, MTL wiring, losses,
+Hungarian targets, step engine) with the CUDA ops replaced by the oracle shim."""
+import copy
+import os
+
+import pytest
+import torch
+
+from rscotr_b200.config import Config, MODELS
+import rscotr_b200.models  # noqa: F401  (registers the classes)
+from rscotr_b200.mtl.data import build_datasets, build_multidataloader, load_data_cfg
+from tests.cpu_ops_shim import cpu_ops
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CFG = os.path.join(ROOT, 'configs', 'multi', 'cotrain_swin-t_800.py')
+REF_CFG = '/root/reference/configs/multi/MTL_slvlcls_swin-t-p4-w7_1x1_resisc&dior&potsdam.py'
+
+
+def small_cfg():
+    cfg = Config.fromfile(CFG)
+    m = cfg.model
+    m.bbox_head.num_query = 30
+    m.bbox_head.dn_cfg.group_cfg.num_dn_queries = 10
+    m.seg_head.num_queries = 12
+    m.seg_head.transformer_decoder.num_layers = 5
+    m.shared_encoder.num_layers = 2
+    m.bbox_head.transformer.decoder.num_layers = 2
+    m.train_cfg.cls.augments = None
+    m.backbone.drop_path_rate = 0.0
+    return cfg
+
+
+def _strip(d):
+    if isinstance(d, dict):
+        return {k: _strip(v) for k, v in d.items() if k not in ('init_cfg', 'augments', 'task_pretrain')}
+    if isinstance(d, (list, tuple)):
+        return [_strip(v) for v in d]
+    return d
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason='reference tree not mounted (GPU box)')
+def test_reference_config_loads_unmodified():
+    cfg = Config.fromfile(REF_CFG)
+    assert cfg.model.type == 'MTL' and cfg.model.backbone.depths == [2, 2, 6, 2]
+    assert cfg.optimizer.paramwise_cfg.custom_keys['backbone']['lr_mult'] == 0.1
+    assert cfg.log_config.interval == 300 and cfg.dist_params.backend == 'nccl'     # child overrides base
+    assert list(cfg.data.keys()) == ['resisc', 'dior', 'potsdam']
+    # the repo's own benchmark config describes the same model / optimizer
+    own = Config.fromfile(CFG)
+    assert _strip(dict(own.model)) == _strip(dict(cfg.model))
+    assert dict(own.optimizer) == dict(cfg.optimizer) and dict(own.optimizer_config) == dict(cfg.optimizer_config)
+    assert {k: v['data']['samples_per_gpu'] for k, v in own.data.items()} == \
+        {k: v['data']['samples_per_gpu'] for k, v in cfg.data.items()}
+    # the reference's dataset sub-configs splice in through load_data_cfg as well
+    load_data_cfg(cfg, config_root='/root/reference')
+    assert cfg.data.resisc.task == 'cls' and cfg.data.resisc.config.data.samples_per_gpu == 16
+
+
+def test_own_config_loads():
+    cfg = Config.fromfile(CFG)
+    assert cfg.model.type == 'MTL' and cfg.dist_params.backend == 'nccl' and cfg.log_config.interval == 50
+
+
+def test_state_dict_layout_matches_reference():
+    cfg = Config.fromfile(CFG)
+    model = MODELS.build(cfg.model)
+    keys = set(model.state_dict().keys())
+    for k in ['backbone.patch_embed.projection.weight', 'backbone.stages.2.blocks.5.attn.w_msa.relative_position_index',
+              'backbone.stages.0.downsample.reduction.weight', 'backbone.norm3.bias', 'neck.extra_convs.0.gn.weight',
+              'shared_encoder.layers.5.attentions.0.sampling_offsets.bias', 'shared_encoder.layers.0.ffns.0.layers.0.0.weight',
+              'shared_encoder.layers.0.norms.1.weight', 'cls_head.fc.weight', 'bbox_head.cls_branches.6.bias',
+              'bbox_head.reg_branches.0.4.weight', 'bbox_head.label_embedding.weight', 'bbox_head.transformer.level_embeds',
+              'bbox_head.transformer.enc_output_norm.weight', 'bbox_head.transformer.query_embed.weight',
+              'bbox_head.transformer.decoder.ref_point_head.2.weight', 'bbox_head.transformer.decoder.norm.weight',
+              'bbox_head.transformer.decoder.layers.0.attentions.0.attn.in_proj_weight',
+              'bbox_head.transformer.decoder.layers.0.attentions.1.value_proj.weight',
+              'seg_head.pixel_decoder.level_encoding.weight', 'seg_head.pixel_decoder.mask_feature.bias',
+              'seg_head.transformer_decoder.post_norm.weight', 'seg_head.query_feat.weight', 'seg_head.level_embed.weight',
+              'seg_head.mask_embed.4.bias']:
+        assert k in keys, k
+    n = sum(p.numel() for p in model.parameters())
+    assert 62.0e6 < n < 63.5e6
+
+
+@pytest.mark.parametrize('task', ['cls', 'det', 'seg'])
+def test_train_step_each_task_cpu(task):
+    torch.manual_seed(0)
+    cfg = small_cfg()
+    model = MODELS.build(cfg.model)
+    model.init_weights()
+    model.train()
+    ds = build_datasets({'x': dict(task=task)}, synthetic=dict(img_size=(64, 64), det=dict(num_boxes=3)))['x']
+    g = torch.Generator().manual_seed(1)
+    batch = ds.make_batch(2, g, pin=False)
+    batch.update(task=task, dataset_name='x')
+    with cpu_ops():
+        out = model.train_step(batch, None)
+        out['loss'].backward()
+    assert torch.isfinite(out['loss'])
+    lv = dict(out['log_vars'].items())
+    assert '%s.x.loss' % task in lv
+    if task == 'det':
+        assert len([k for k in lv if k.endswith('loss_cls')]) == 5     # interm, last, d0, dn, d0.dn (2 decoder layers)
+        assert model.seg_head.query_feat.weight.grad is None and model.bbox_head.label_embedding.weight.grad is not None
+    if task == 'seg':
+        assert abs(lv['seg.x.loss'] - lv['seg.x.seg.loss_ce']) < 1e-6      # acc_seg is not part of the total
+        assert 'seg.x.seg.acc_seg' in lv
+    if task == 'cls':
+        assert model.neck.convs[0].conv.weight.grad is None           # neck output is discarded for slvl cls
+        assert model.backbone.stages[0].blocks[0].attn.w_msa.relative_position_bias_table.grad is not None
+
+
+def test_round_robin_multidataloader():
+    cfg = small_cfg()
+    load_data_cfg(cfg, config_root=ROOT)
+    assert cfg.data.dior.task == 'det' and cfg.data.resisc.config.data.samples_per_gpu == 16
+    cfg.synthetic = dict(img_size=(32, 32), length=dict(resisc=2, dior=5, potsdam=3))
+    datasets = build_datasets(cfg.data, synthetic=cfg.synthetic)
+    loader = build_multidataloader(cfg, False, datasets)
+    it = iter(loader)
+    seq = [(b['dataset_name'], b['task'], b['img'].shape[0]) for b in (next(it) for _ in range(9))]
+    assert [s[0] for s in seq] == ['resisc', 'dior', 'potsdam'] * 3        # round robin, re-igniting resisc
+    assert seq[0][2] == 16 and seq[1][2] == 1 and seq[2][2] == 2            # per-dataset samples_per_gpu
+    assert len(loader) == 10
+
+
+def test_optimizer_param_groups():
+    from rscotr_b200.mtl.utils.optimizer import param_settings
+    cfg = Config.fromfile(CFG)
+    model = MODELS.build(small_cfg().model)
+    opt = dict(cfg.optimizer)
+    pw = opt.pop('paramwise_cfg')
+    s = {n: (lr, wd) for n, _, lr, wd in param_settings(model, opt, pw)}
+    assert s['backbone.patch_embed.projection.weight'] == (5e-6, 1e-4)
+    assert s['bbox_head.transformer.query_embed.weight'] == (5e-5, 0.0)
+    assert s['seg_head.query_embed.weight'][1] == 0.0 and s['seg_head.query_feat.weight'][1] == 0.0
+    assert s['bbox_head.transformer.level_embeds'][1] == 0.0 and s['seg_head.level_embed.weight'][1] == 0.0
+    assert s['shared_encoder.layers.0.ffns.0.layers.1.weight'] == (5e-5, 1e-4)
