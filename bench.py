@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Co-training iterations/sec (Swin-T, synthetic 3x800x800, cls 16 / det 1 / seg 2 per GPU,
+round robin) -- BASELINE.json's metric on configs[1] (N=1) / configs[2] (N=8).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One *step* = one co-training iteration: H2D (e2e leg only) -> shared Swin backbone ->
+neck -> shared deformable encoder -> one task head -> losses -> backward -> flat NCCL
+all-reduce of the gradients -> global-norm clip -> AdamW.  Steps cycle cls, det, seg.
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the stand-in
+for the reference's own CPU path, which cannot be installed here: mmcv-full 1.6.1 /
+mmdet / mmcls / mmseg are absent and there is no network) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+CONFIG = os.path.join(ROOT, 'configs', 'multi', 'cotrain_swin-t_800.py')
+METRIC = 'co-training iters/sec (Swin-T, 3x800x800)'
+TASK_ORDER = ('resisc', 'dior', 'potsdam')
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=6)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default=CONFIG)
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-budget-s', type=float, default=240.0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """samples nvidia-smi during the timed region (B200_PROFILING.md 'clocks line')."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1])), pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# ----------------------------------------------------------------------------- helpers
+def build(cfg_path, dtype, device):
+    import torch
+    import rscotr_b200.models  # noqa: F401
+    from rscotr_b200.config import Config, MODELS
+    from rscotr_b200.mtl.data import build_datasets, build_multidataloader, load_data_cfg
+    from rscotr_b200.mtl.engine import StepEngine
+    cfg = Config.fromfile(cfg_path)
+    load_data_cfg(cfg, config_root=ROOT)
+    torch.manual_seed(0)
+    model = MODELS.build(cfg.model)
+    model.init_weights()
+    model.train()
+    engine = StepEngine(model, cfg.optimizer, grad_clip=cfg.optimizer_config.get('grad_clip'), device=device,
+                        compute_dtype=torch.bfloat16 if dtype == 'bf16' else torch.float32, lr_config=cfg.lr_config)
+    datasets = build_datasets(cfg.data, synthetic=cfg.get('synthetic'))
+    loader = build_multidataloader(cfg, int(os.environ.get('WORLD_SIZE', 1)) > 1, datasets)
+    return cfg, model, engine, loader
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ----------------------------------------------------------------------------- CPU oracle arm
+def oracle_step_fn(cfg, img_hw):
+    """Builds a CPU fp32 oracle train step (fwd + bwd + clip + AdamW) per task on batch 1."""
+    import torch
+    import rscotr_b200.models  # noqa: F401
+    from oracle import heads as oh
+    from rscotr_b200.config import MODELS
+    from rscotr_b200.mtl.data.synthetic import SyntheticDataset
+    from rscotr_b200.mtl.utils.optimizer import param_settings
+    torch.manual_seed(0)
+    model = MODELS.build(cfg.model)          # only as a container of identically initialised weights
+    model.init_weights()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    params = {n: sd[n].requires_grad_(True) for n, _ in model.named_parameters()}
+    opt_cfg = dict(cfg.optimizer)
+    pw = opt_cfg.pop('paramwise_cfg', None)
+    opt_cfg.pop('type')
+    groups = {}
+    for n, _, lr, wd in param_settings(model, opt_cfg, pw):
+        groups.setdefault((lr, wd), []).append(params[n])
+    optim = torch.optim.AdamW([dict(params=ps, lr=lr, weight_decay=wd) for (lr, wd), ps in groups.items()])
+    del model
+    g = torch.Generator().manual_seed(3)
+    batches = {}
+    for name in TASK_ORDER:
+        task = cfg.data[name]['task']
+        ds = SyntheticDataset(task, img_size=img_hw, **dict(cfg.get('synthetic', {}).get(task, {})))
+        b = ds.make_batch(1, g, pin=False)
+        b.update(task=task, dataset_name=name)
+        batches[name] = b
+    tw = dict(cls=1, det=1, seg=1)
+    tw.update(cfg.model.get('task_weight') or {})
+    max_norm = cfg.optimizer_config.get('grad_clip', {}).get('max_norm', 0.1)
+
+    def step(name):
+        b = dict(batches[name])
+        task = b['task']
+        noise = oh.cdn_noise(b['gt_labels'], generator=g) if task == 'det' else None
+        optim.zero_grad(set_to_none=True)
+        losses = oh.mtl_losses(sd, task, b, noise=noise)
+        loss, _ = oh.parse_losses(losses, tw[task])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in params.values() if p.grad is not None], max_norm)
+        optim.step()
+        return float(loss)
+
+    return step
+
+
+def per_gpu_batch(cfg):
+    return {n: cfg.data[n]['config']['data']['samples_per_gpu'] for n in TASK_ORDER}
+
+
+def run_reference(args):
+    """Reference arm: the CPU oracle on all host cores.  A step = one co-training iteration
+    on a bounded SAMPLE (batch 1 per task); `value` extrapolates the measured per-image
+    times to the configured per-GPU batches (cls 16 / det 1 / seg 2)."""
+    if int(os.environ.get('RANK', 0)) != 0:
+        return
+    import torch
+    from rscotr_b200.config import Config
+    from rscotr_b200.mtl.data import load_data_cfg
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    cfg = Config.fromfile(args.config)
+    load_data_cfg(cfg, config_root=ROOT)
+    hw = tuple(cfg.synthetic['img_size'])
+    step = oracle_step_fn(cfg, hw)
+    t0 = time.time()
+    step(TASK_ORDER[0])                      # probe the cost of one step
+    probe = time.time() - t0
+    scale = 1.0
+    n_total = args.steps + args.warmup
+    if probe * 2.5 * n_total > args.cpu_budget_s and hw[0] > 400:        # det/seg steps cost ~2.5x a cls step
+        hw = (hw[0] // 2, hw[1] // 2)
+        scale = 4.0
+        step = oracle_step_fn(cfg, hw)
+    times = {n: [] for n in TASK_ORDER}
+    for i in range(n_total):
+        name = TASK_ORDER[i % 3]
+        t0 = time.time()
+        step(name)
+        if i >= args.warmup:
+            times[name].append(time.time() - t0)
+    bs = per_gpu_batch(cfg)
+    per_img = {n: (sum(v) / len(v) if v else float('nan')) * scale for n, v in times.items()}
+    cycle = sum(per_img[n] * bs[n] for n in TASK_ORDER)
+    value = 3.0 / cycle
+    sample = ('oracle (CPU fp32 restatement) train step on batch 1 per task at 3x%dx%d%s; per-image seconds %s; '
+              'extrapolated linearly to per-GPU batches %s') % (
+        hw[0], hw[1], ' (x4 token-count scaling to 800x800)' if scale != 1.0 else '',
+        {k: round(v, 2) for k, v in per_img.items()}, bs)
+    out = dict(metric=METRIC, value=value, unit='iters/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+               ms_per_step=1000.0 / value, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+               data='synthetic', impl='reference',
+               config=dict(workload='Swin-T MTL co-training (cls+seg+det round-robin) 3x800x800, per-GPU batch 16/1/2',
+                           note='reference itself is not installable offline (mmcv-full/mmdet/mmcls/mmseg absent); '
+                                'this arm runs the CPU oracle port'),
+               cpu_baseline=dict(value=value, unit='iters/s', cores=cores, kind='port', sample=sample),
+               e2e=dict(value=value, unit='iters/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+def cpu_baseline(cfg, budget_s=40.0):
+    """Bounded CPU sample inside the default run: one oracle train step per task, batch 1,
+    at 3x400x400 (token count x4 -> 800x800), all host cores."""
+    import torch
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    hw = tuple(cfg.synthetic['img_size'])
+    small = (hw[0] // 2, hw[1] // 2)
+    step = oracle_step_fn(cfg, small)
+    per_img = {}
+    for name in TASK_ORDER:
+        t0 = time.time()
+        step(name)
+        per_img[name] = (time.time() - t0) * 4.0
+    bs = per_gpu_batch(cfg)
+    cycle = sum(per_img[n] * bs[n] for n in TASK_ORDER)
+    return dict(value=3.0 / cycle, unit='iters/s', cores=cores, kind='port',
+                sample=('one oracle (CPU fp32) train step per task, batch 1, 3x%dx%d scaled x4 by token count to '
+                        '800x800 and linearly to per-GPU batches %s; per-image s %s') % (
+                    small[0], small[1], bs, {k: round(v, 2) for k, v in per_img.items()}))
+
+
+# ----------------------------------------------------------------------------- main arm
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    from rscotr_b200 import ops
+    from rscotr_b200.mtl.engine.step import _to_device, h2d_bytes
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    assert world == args.gpus, 'launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)' % (args.gpus, world)
+
+    cfg, model, engine, loader = build(args.config, args.dtype, device)
+    it = iter(loader)
+    host_batches = [next(it) for _ in range(6)]                  # 2 distinct batches per task, pinned host memory
+    dev_batches = [_to_device(b, device) for b in host_batches]
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up (also fixes the per-task all-reduce ranges, cuBLAS heuristics, allocator)
+    for i in range(max(args.warmup, 3)):
+        engine.train_iter(dev_batches[i % 6])
+    barrier()
+
+    # ---- timed region A: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_task = {}
+    with ops.KernelTimer() as kt:
+        barrier()
+        e0.record()
+        evs = []
+        for i in range(args.steps):
+            a = torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = engine.train_iter(dev_batches[i % 6])
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            evs.append((dev_batches[i % 6]['task'], a, b))
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        ksum = kt.summary()
+    launches = ops.launch_count()
+    for t, a, b in evs:
+        per_task.setdefault(t, []).append(a.elapsed_time(b))
+    final_loss = float(out['loss'])
+
+    # ---- timed region B: end to end through the public API, pinned host inputs, loss read back
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    hb = db = 0
+    for i in range(args.steps):
+        batch = host_batches[i % 6]
+        hb += h2d_bytes(batch)
+        o = engine.train_iter(batch)
+        _ = float(o['loss'])                                     # D2H read of the step's result
+        db += 4
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * args.steps / (ms / 1000.0)                   # whole-job iterations (one per rank per step)
+    e2e = world * args.steps / (ms_e2e / 1000.0)
+    peak, peak_src = peaks()
+    mine_ms = sum(d['ms'] for d in ksum.values())
+    top = max(ksum.items(), key=lambda kv: kv[1]['ms']) if ksum else (None, None)
+    roofline = None
+    if top[0]:
+        d = top[1]
+        roofline = dict(kernel=top[0], bound='hbm', achieved=d['gbs'], peak=peak, unit='GB/s', frac=d['gbs'] / peak,
+                        traffic=None, launches=d['launches'], avg_us=1000.0 * d['ms'] / d['launches'],
+                        alg_bytes_per_launch=d['bytes'] / d['launches'], peak_source=peak_src,
+                        share_of_step=d['ms'] / ms, own_kernels_share_of_step=mine_ms / ms)
+    bs = per_gpu_batch(cfg)
+    out = dict(metric=METRIC, value=value, unit='iters/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+               ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+               dtype=args.dtype if args.dtype != 'fp32' else 'f32', data='synthetic',
+               config=dict(workload='Swin-T MTL co-training (cls+seg+det round-robin) 3x800x800 (BASELINE configs[%d])'
+                                    % (1 if world == 1 else 2),
+                           per_gpu_batch=bs, global_batch={k: v * world for k, v in bs.items()},
+                           parallelism='dp%d' % world, strategy='round_robin', config_file=os.path.relpath(args.config, ROOT),
+                           l2='no flush: each step streams >1 GB of activations (inputs alone 123 MB fp32 for the cls '
+                              'batch), far above the 126 MB L2',
+                           weights='random init, 62.6 M params', final_loss=final_loss),
+               clocks=clocks,
+               e2e=dict(value=e2e, unit='iters/s', h2d_bytes_per_step=hb // args.steps, d2h_bytes_per_step=db // args.steps,
+                        ms_per_step=ms_e2e / args.steps),
+               gpu_launches=launches,
+               ms_per_task={k: sum(v) / len(v) for k, v in per_task.items()},
+               roofline=roofline,
+               kernels={k: dict(launches=d['launches'], ms=round(d['ms'], 3), gbs=round(d['gbs'], 1),
+                                frac=round(d['gbs'] / peak, 4)) for k, d in sorted(ksum.items())})
+    if world == 1 and not args.no_cpu_baseline:
+        del engine, model, dev_batches
+        torch.cuda.empty_cache()
+        out['cpu_baseline'] = cpu_baseline(cfg)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

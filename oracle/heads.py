@@ -483,7 +483,7 @@ def parse_losses(losses, task_weight=1.0):
     log_vars = {k: v.mean() for k, v in losses.items()}
     loss = sum(v for k, v in log_vars.items() if 'loss' in k)
     log_vars['loss'] = loss
-    return loss * task_weight, {k: float(v) * task_weight for k, v in log_vars.items()}
+    return loss * task_weight, {k: float(v.detach()) * task_weight for k, v in log_vars.items()}
 
 
 def cdn_noise(gt_labels, num_dn=100, num_classes=20, generator=None):

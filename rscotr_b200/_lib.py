@@ -70,8 +70,48 @@ def check(status, name):
         raise RuntimeError('%s failed (%d): %s' % (name, status, lib().rsc_last_error().decode()))
 
 
-def call(name, *args):
+_timer = None      # set by KernelTimer: collects (name, alg_bytes, start_event, end_event)
+
+
+def call(name, *args, alg_bytes=0):
+    if _timer is None:
+        check(getattr(lib(), name)(*args), name)
+        return
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib(), name)(*args), name)
+    e1.record()
+    _timer.append((name, alg_bytes, e0, e1))
+
+
+class KernelTimer:
+    """with KernelTimer() as kt: ...   -> kt.summary(): per C-ABI entry point the number of
+    launches, summed device time (CUDA events on the launching stream) and summed
+    algorithmic bytes.  Used by bench.py for the roofline object."""
+
+    def __enter__(self):
+        global _timer
+        self.records = []
+        _timer = self.records
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = None
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, nbytes, e0, e1 in self.records:
+            d = out.setdefault(name, dict(launches=0, ms=0.0, bytes=0))
+            d['launches'] += 1
+            d['ms'] += e0.elapsed_time(e1)
+            d['bytes'] += nbytes
+        for d in out.values():
+            d['gbs'] = d['bytes'] / d['ms'] / 1e6 if d['ms'] > 0 else 0.0
+        return out
 
 
 def launch_count():

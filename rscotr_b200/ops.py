@@ -43,6 +43,11 @@ def _nwin(H, W, ws):
     return ((H + ws - 1) // ws) * ((W + ws - 1) // ws)
 
 
+def _padded_tokens(B, H, W, ws):
+    """B * Lp of SURVEY 8d: tokens of the window-padded grid."""
+    return B * _nwin(H, W, ws) * ws * ws
+
+
 def window_index_partition(B, H, W, ws, shift, device='cuda'):
     out = torch.empty(B * _nwin(H, W, ws) * ws * ws, dtype=torch.int64, device=device)
     _cuda(out)
@@ -126,7 +131,7 @@ class _WMSA(torch.autograd.Function):
         out = torch.empty(B, H * W, C, dtype=qkv.dtype, device=qkv.device)
         with torch.cuda.device(qkv.device):
             call('rsc_wmsa_fwd', qkv.data_ptr(), _p(bias32), table32.data_ptr(), out.data_ptr(), B, H, W, C, heads,
-                 ws, shift, scale, _dt(qkv), _stream())
+                 ws, shift, scale, _dt(qkv), _stream(), alg_bytes=4 * _padded_tokens(B, H, W, ws) * C * qkv.element_size())
         ctx.save_for_backward(qkv, bias32, table32)
         ctx.meta = (B, H, W, C, heads, ws, shift, scale, qkv_bias is not None and qkv_bias.dtype, table.dtype)
         return out
@@ -141,7 +146,8 @@ class _WMSA(torch.autograd.Function):
         dbias = torch.zeros_like(bias32) if bias32 is not None else None
         with torch.cuda.device(qkv.device):
             call('rsc_wmsa_bwd', qkv.data_ptr(), _p(bias32), table32.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
-                 dtable.data_ptr(), _p(dbias), B, H, W, C, heads, ws, shift, scale, _dt(qkv), _stream())
+                 dtable.data_ptr(), _p(dbias), B, H, W, C, heads, ws, shift, scale, _dt(qkv), _stream(),
+                 alg_bytes=7 * _padded_tokens(B, H, W, ws) * C * qkv.element_size())
         if dbias is not None:
             dbias = dbias.to(bias_dtype)
         return dqkv, dbias, dtable.to(table_dtype), None, None, None, None, None, None
@@ -175,7 +181,8 @@ class _PatchMergeLN(torch.autograd.Function):
         rstd = torch.empty_like(mean)
         with torch.cuda.device(x.device):
             call('rsc_patch_merge_ln_fwd', x.data_ptr(), g32.data_ptr(), b32.data_ptr(), y.data_ptr(),
-                 mean.data_ptr(), rstd.data_ptr(), B, H, W, C, eps, _dt(x), _stream())
+                 mean.data_ptr(), rstd.data_ptr(), B, H, W, C, eps, _dt(x), _stream(),
+                 alg_bytes=2 * x.numel() * x.element_size())
         ctx.save_for_backward(x, g32, mean, rstd)
         ctx.meta = (B, H, W, C, gamma.dtype, beta.dtype)
         return y
@@ -190,7 +197,8 @@ class _PatchMergeLN(torch.autograd.Function):
         db = torch.zeros_like(dg)
         with torch.cuda.device(x.device):
             call('rsc_patch_merge_ln_bwd', x.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                 dy.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), B, H, W, C, _dt(x), _stream())
+                 dy.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), B, H, W, C, _dt(x), _stream(),
+                 alg_bytes=3 * x.numel() * x.element_size())
         return dx, dg.to(gdt), db.to(bdt), None, None, None
 
 
@@ -225,7 +233,8 @@ class MultiScaleDeformableAttnFunction(torch.autograd.Function):
         out = torch.empty(B, Nq, heads * D, dtype=value.dtype, device=value.device)
         with torch.cuda.device(value.device):
             call('rsc_msda_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), loc.data_ptr(),
-                 aw.data_ptr(), out.data_ptr(), B, Nv, Nq, heads, L, P, int(im2col_step), _dt(value), _stream())
+                 aw.data_ptr(), out.data_ptr(), B, Nv, Nq, heads, L, P, int(im2col_step), _dt(value), _stream(),
+                 alg_bytes=(value.numel() + out.numel()) * value.element_size() + (loc.numel() + aw.numel()) * 4)
         ctx.save_for_backward(value, shapes, starts, loc, aw)
         ctx.meta = (int(im2col_step), sampling_locations.dtype, attention_weights.dtype)
         return out
@@ -243,7 +252,9 @@ class MultiScaleDeformableAttnFunction(torch.autograd.Function):
         with torch.cuda.device(value.device):
             call('rsc_msda_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), loc.data_ptr(),
                  aw.data_ptr(), grad_output.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), B, Nv, Nq, heads,
-                 L, P, im2col_step, _dt(value), _stream())
+                 L, P, im2col_step, _dt(value), _stream(),
+                 alg_bytes=(value.numel() + grad_output.numel()) * value.element_size() + 2 * value.numel() * 4 +
+                 2 * (loc.numel() + aw.numel()) * 4)
         return gv.to(value.dtype), None, None, gl.to(loc_dt), ga.to(aw_dt), None
 
 
@@ -267,7 +278,8 @@ class _GAP(torch.autograd.Function):
             HW = x[0, 0].numel()
         y = torch.empty(B, C, dtype=x.dtype, device=x.device)
         with torch.cuda.device(x.device):
-            call('rsc_gap_fwd', x.data_ptr(), y.data_ptr(), B, C, HW, int(channels_last), _dt(x), _stream())
+            call('rsc_gap_fwd', x.data_ptr(), y.data_ptr(), B, C, HW, int(channels_last), _dt(x), _stream(),
+                 alg_bytes=x.numel() * x.element_size())
         ctx.meta = (x.shape, B, C, HW, channels_last)
         return y
 
@@ -277,7 +289,8 @@ class _GAP(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty(shape, dtype=dy.dtype, device=dy.device)
         with torch.cuda.device(dy.device):
-            call('rsc_gap_bwd', dy.data_ptr(), dx.data_ptr(), B, C, HW, int(channels_last), _dt(dy), _stream())
+            call('rsc_gap_bwd', dy.data_ptr(), dx.data_ptr(), B, C, HW, int(channels_last), _dt(dy), _stream(),
+                 alg_bytes=dx.numel() * dx.element_size())
         return dx, None
 
 
@@ -297,7 +310,8 @@ class _Bilinear(torch.autograd.Function):
         B, C, Hi, Wi = x.shape
         y = torch.empty(B, C, Ho, Wo, dtype=x.dtype, device=x.device)
         with torch.cuda.device(x.device):
-            call('rsc_bilinear_fwd', x.data_ptr(), y.data_ptr(), B * C, Hi, Wi, Ho, Wo, _dt(x), _stream())
+            call('rsc_bilinear_fwd', x.data_ptr(), y.data_ptr(), B * C, Hi, Wi, Ho, Wo, _dt(x), _stream(),
+                 alg_bytes=(x.numel() + y.numel()) * x.element_size())
         ctx.meta = (B, C, Hi, Wi, Ho, Wo)
         return y
 
@@ -307,7 +321,8 @@ class _Bilinear(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty(B, C, Hi, Wi, dtype=dy.dtype, device=dy.device)
         with torch.cuda.device(dy.device):
-            call('rsc_bilinear_bwd', dy.data_ptr(), dx.data_ptr(), B * C, Hi, Wi, Ho, Wo, _dt(dy), _stream())
+            call('rsc_bilinear_bwd', dy.data_ptr(), dx.data_ptr(), B * C, Hi, Wi, Ho, Wo, _dt(dy), _stream(),
+                 alg_bytes=(dx.numel() + dy.numel()) * dy.element_size())
         return dx, None, None
 
 
@@ -331,7 +346,7 @@ class SigmoidFocalLossFunction(torch.autograd.Function):
         out = torch.empty(N, C, dtype=torch.float32, device=input.device)
         with torch.cuda.device(input.device):
             call('rsc_sigmoid_focal_loss_fwd', input.data_ptr(), target.data_ptr(), out.data_ptr(), N, C,
-                 float(gamma), float(alpha), _dt(input), _stream())
+                 float(gamma), float(alpha), _dt(input), _stream(), alg_bytes=input.numel() * (input.element_size() + 4))
         ctx.save_for_backward(input, target)
         ctx.meta = (float(gamma), float(alpha))
         return out
@@ -344,12 +359,15 @@ class SigmoidFocalLossFunction(torch.autograd.Function):
         gi = torch.empty(N, C, dtype=torch.float32, device=input.device)
         with torch.cuda.device(input.device):
             call('rsc_sigmoid_focal_loss_bwd', input.data_ptr(), target.data_ptr(), gi.data_ptr(), N, C, gamma, alpha,
-                 _dt(input), _stream())
+                 _dt(input), _stream(), alg_bytes=input.numel() * (input.element_size() + 4))
         return (gi * grad_output).to(input.dtype), None, None, None
 
 
 def sigmoid_focal_loss(input, target, gamma=2.0, alpha=0.25):
     return SigmoidFocalLossFunction.apply(input, target, gamma, alpha)
+
+
+KernelTimer = _lib.KernelTimer
 
 
 def launch_count():
