@@ -302,7 +302,7 @@ def main():
     launches = ops.launch_count()
     for t, a, b in evs:
         per_task.setdefault(t, []).append(a.elapsed_time(b))
-    final_loss = float(out['loss'])
+    final_loss = float(out['loss'].detach())
 
     # ---- timed region B: end to end through the public API, pinned host inputs, loss read back
     barrier()
@@ -313,7 +313,7 @@ def main():
         batch = host_batches[i % 6]
         hb += h2d_bytes(batch)
         o = engine.train_iter(batch)
-        _ = float(o['loss'])                                     # D2H read of the step's result
+        _ = float(o['loss'].detach())                                     # D2H read of the step's result
         db += 4
     f1.record()
     barrier()

@@ -417,7 +417,3 @@ extern "C" int rsc_wmsa_bwd(const void *qkv, const float *qkv_bias, const float 
   return RSC_OK;
 }
 
-extern "C" int rsc_wmsa_fwd(const void *qkv, const float *qkv_bias, const float *bias_table, void *out, int B, int H,
-                            int W, int C, int heads, int ws, int shift, float scale, int dtype, void *stream) {
-  return rsc_wmsa_fwd_simt(qkv, qkv_bias, bias_table, out, B, H, W, C, heads, ws, shift, scale, dtype, stream);
-}

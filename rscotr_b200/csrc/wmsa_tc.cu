@@ -1,0 +1,263 @@
+// Fused (shifted-)window attention forward on the 5th-gen tensor cores (bf16).
+//
+//   S = Q K^T  and  O = P V  are tcgen05.mma tiles (kind::f16, bf16 x bf16 -> fp32 in TMEM);
+//   two (window, head) units are stacked along M (M = 128 = 2 x 64 rows, 49 valid each):
+//     S[128 x 128] = [Q_a;Q_b] x [K_a;K_b]^T          (only the two diagonal 64x64 blocks are used)
+//     O_a[128 x 32] = P x V_a ,  O_b[128 x 32] = P x V_b   (rows 0-63 of O_a, rows 64-127 of O_b are used)
+//   The softmax (scale, relative-position bias, shift mask -100, exp, row sum) runs on the
+//   SIMT lanes between the two MMAs: thread r owns row r of S (tcgen05.ld 32x32b).
+//   qkv is gathered ONCE from its natural (B,H,W,3C) layout through the padded / cyclically
+//   shifted window coordinates with 16-byte cp.async into the no-swizzle core-matrix smem
+//   layout (tools/tc_probe.cu pins these descriptors); padded tokens are synthesised from the
+//   qkv bias.  The kernel is HBM-bound (24.5 flop/B): the tensor cores only keep the
+//   math off the critical path; 4 CTAs/SM (128 TMEM columns each) overlap load / MMA / softmax.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace rsc {
+namespace wtc {
+
+using namespace tc;
+
+constexpr int WS = 7, NT = 49, HD = 32, TBL = 169;
+constexpr int THREADS = 128;
+constexpr int SM_Q = 0, SM_K = 8192, SM_V = 16384, SM_P = 24576;  // byte offsets
+constexpr int SM_TBL = SM_P + 16384;                               // 169 floats
+constexpr int SM_TOTAL = 50 * 1024;                                // sized so that exactly 4 CTAs fit per SM
+constexpr int TMEM_COLS = 128;
+
+// 16-byte chunk c (8 bf16) of row r of a token-major [rows][32] tile
+__device__ __forceinline__ int tile_off(int r, int c) { return (r >> 3) * 512 + c * 128 + (r & 7) * 16; }
+// P tile (128 rows x 64 keys): chunk kc of row r
+__device__ __forceinline__ int p_off(int r, int kc) { return kc * 2048 + (r >> 3) * 128 + (r & 7) * 16; }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+
+__global__ void __launch_bounds__(THREADS, 4)
+    wmsa_fwd_tc_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ qkv_bias,
+                       const float *__restrict__ table, __nv_bfloat16 *__restrict__ out, WinGeom g, int C, int heads,
+                       float scale, int num_windows, int num_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float *tbl = reinterpret_cast<float *>(smem + SM_TBL);
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  // zero the operand tiles once: rows 49..63 of every unit stay zero for the whole kernel
+  for (int i = tid; i < SM_P / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = tmem_base_s;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
+  const uint32_t idesc_o = make_idesc_bf16(128, 32, false, true);
+  uint32_t phase = 0;
+
+  const int unit = tid >> 6;   // which of the two stacked units this thread's row belongs to
+  const int i = tid & 63;      // row inside the unit (query token), valid if < 49
+  const int ri = i / WS, ci = i % WS;
+
+  for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    const int head = item % heads;
+    const int pair = item / heads;
+    // ---------------- phase 1: gather q|k|v rows of both units into smem ----------------
+    for (int idx = tid; idx < 2 * NT * 12; idx += THREADS) {
+      const int c = idx & 3;                 // 16-byte chunk of the 64-byte head slice
+      const int part = (idx >> 2) % 3;       // q | k | v
+      const int t = (idx / 12) % NT;         // token in window
+      const int u = idx / (12 * NT);         // unit
+      const int win = 2 * pair + u;
+      if (win >= num_windows) continue;
+      int b, wh, ww;
+      ww = win % g.nWw;
+      wh = (win / g.nWw) % g.nWh;
+      b = win / (g.nWw * g.nWh);
+      int h, w;
+      const bool ok = g.source(wh, ww, t / WS, t % WS, h, w);
+      const int col = part * C + head * HD + c * 8;
+      const uint32_t dst = smem_base + part * 8192 + tile_off(u * 64 + t, c);
+      if (ok) {
+        cp_async16(dst, qkv + (((int64_t)b * g.H + h) * g.W + w) * (3 * C) + col);
+      } else {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (qkv_bias) {
+          const float4 f0 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col));
+          const float4 f1 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col + 4));
+          v = make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                     : "memory");
+      }
+    }
+    for (int k = tid; k < TBL; k += THREADS) tbl[k] = __ldg(table + k * heads + head);
+    cp_async_wait_all();
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---------------- phase 2: S = Q K^T ----------------
+    if (tid == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        mma_bf16_ss(tm, make_smem_desc(smem_base + SM_Q + k * 256, 128, 512),
+                    make_smem_desc(smem_base + SM_K + k * 256, 128, 512), idesc_s, k > 0);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    // ---------------- phase 3: softmax on this thread's row ----------------
+    const int win = 2 * pair + unit;
+    const bool unit_ok = win < num_windows;
+    int b = 0, wh = 0, ww = 0;
+    if (unit_ok) {
+      ww = win % g.nWw;
+      wh = (win / g.nWw) % g.nWh;
+      b = win / (g.nWw * g.nWh);
+    }
+    float inv_l = 0.f;
+    {
+      uint32_t s0[32], s1[32];
+      const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16) + unit * 64;
+      tmem_ld32(taddr, s0);
+      tmem_ld32(taddr + 32, s1);
+      tmem_ld_wait();
+      uint32_t pk[32];   // 64 bf16 probabilities, packed
+      if (unit_ok && i < NT) {
+        // shift mask: only the last window row / column has more than one region
+        uint32_t rowbits = 0, colbits = 0;
+        if (g.shift > 0) {
+          const bool lr = wh == g.nWh - 1, lc = ww == g.nWw - 1;
+          const int rh_i = lr ? (ri < WS - g.shift ? 1 : 2) : 0, rw_i = lc ? (ci < WS - g.shift ? 1 : 2) : 0;
+#pragma unroll
+          for (int j = 0; j < WS; ++j) {
+            const int rj = j < WS - g.shift ? 1 : 2;
+            rowbits |= (uint32_t)((lr ? rj : 0) != rh_i) << j;
+            colbits |= (uint32_t)((lc ? rj : 0) != rw_i) << j;
+          }
+        }
+        const float *tb = tbl + (ri + WS - 1) * (2 * WS - 1) + (ci + WS - 1);
+        float sv[NT];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const int jr = j / WS, jc = j % WS;
+          float s = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]) * scale + tb[-(jr * (2 * WS - 1) + jc)];
+          if (((rowbits >> jr) | (colbits >> jc)) & 1u) s += -100.0f;
+          sv[j] = s;
+          m = fmaxf(m, s);
+        }
+        float l = 0.f;
+        const float ml2 = m * 1.4426950408889634f;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float p = exp2f(fmaf(sv[j], 1.4426950408889634f, -ml2));
+          l += p;
+          sv[j] = p;
+        }
+        inv_l = 1.0f / l;
+#pragma unroll
+        for (int j = 0; j < 24; ++j) pk[j] = pack_bf16(sv[2 * j], sv[2 * j + 1]);
+        pk[24] = pack_bf16(sv[48], 0.f);
+#pragma unroll
+        for (int j = 25; j < 32; ++j) pk[j] = 0u;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pk[j] = 0u;
+      }
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {
+        const uint32_t dst = smem_base + SM_P + p_off(tid, kc);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * kc]), "r"(pk[4 * kc + 1]),
+                     "r"(pk[4 * kc + 2]), "r"(pk[4 * kc + 3])
+                     : "memory");
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---------------- phase 4: O_a = P V_a, O_b = P V_b (overwrites S columns 0..63) ----------------
+    if (tid == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_ss(tm + u * 32, make_smem_desc(smem_base + SM_P + k * 4096, 2048, 128),
+                      make_smem_desc(smem_base + SM_V + u * 4096 + k * 1024, 512, 128), idesc_o, k > 0);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    // ---------------- phase 5: normalise and store this thread's output row ----------------
+    {
+      uint32_t o[32];
+      tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + unit * 32, o);
+      tmem_ld_wait();
+      int h, w;
+      if (unit_ok && i < NT && g.source(wh, ww, ri, ci, h, w)) {
+        __nv_bfloat16 *dst = out + (((int64_t)b * g.H + h) * g.W + w) * C + head * HD;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[8 * c + 0]) * inv_l, __uint_as_float(o[8 * c + 1]) * inv_l);
+          v.y = pack_bf16(__uint_as_float(o[8 * c + 2]) * inv_l, __uint_as_float(o[8 * c + 3]) * inv_l);
+          v.z = pack_bf16(__uint_as_float(o[8 * c + 4]) * inv_l, __uint_as_float(o[8 * c + 5]) * inv_l);
+          v.w = pack_bf16(__uint_as_float(o[8 * c + 6]) * inv_l, __uint_as_float(o[8 * c + 7]) * inv_l);
+          *reinterpret_cast<uint4 *>(dst + 8 * c) = v;
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();  // smem tiles and TMEM are free for the next item
+    fence_after_sync();
+  }
+  if (warp == 0) tmem_dealloc(tm, TMEM_COLS);
+}
+
+}  // namespace wtc
+}  // namespace rsc
+
+using namespace rsc;
+
+extern "C" int rsc_wmsa_fwd_simt(const void *qkv, const float *qkv_bias, const float *bias_table, void *out, int B,
+                                 int H, int W, int C, int heads, int ws, int shift, float scale, int dtype,
+                                 void *stream);
+
+extern "C" int rsc_wmsa_fwd(const void *qkv, const float *qkv_bias, const float *bias_table, void *out, int B, int H,
+                            int W, int C, int heads, int ws, int shift, float scale, int dtype, void *stream) {
+  static const bool force_simt = getenv("RSC_WMSA_SIMT") != nullptr;
+  const bool tc_ok = dtype == RSC_BF16 && ws == 7 && (shift == 0 || shift == 3) && heads > 0 && C == heads * 32 &&
+                     B > 0 && H > 0 && W > 0 && qkv && bias_table && out;
+  if (!tc_ok || force_simt)  // fp32 (exact-arithmetic parity path) and argument errors go through the SIMT entry
+    return rsc_wmsa_fwd_simt(qkv, qkv_bias, bias_table, out, B, H, W, C, heads, ws, shift, scale, dtype, stream);
+  WinGeom g(B, H, W, ws, shift);
+  const int num_windows = B * g.nWh * g.nWw;
+  const int num_items = ((num_windows + 1) / 2) * heads;
+  auto kern = wtc::wmsa_fwd_tc_kernel;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::SM_TOTAL);
+  int grid = kNumSMs * 4;
+  if (grid > num_items) grid = num_items;
+  kern<<<grid, wtc::THREADS, wtc::SM_TOTAL, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16 *)qkv, qkv_bias, bias_table, (__nv_bfloat16 *)out, g, C, heads, scale, num_windows,
+      num_items);
+  RSC_CHECK_LAUNCH("rsc_wmsa_fwd");
+  return RSC_OK;
+}

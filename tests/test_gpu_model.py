@@ -14,6 +14,10 @@ from tests.test_host_parity import OCFG, _setup
 
 pytestmark = pytest.mark.gpu
 
+# fp32 parity runs compare against an fp32 CPU oracle: no TF32 in the library GEMMs / convs
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 
 def rel(a, b):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()

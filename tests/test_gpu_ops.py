@@ -124,10 +124,13 @@ def test_wmsa_fp32_fwd_bwd(B, H, W, shift, heads):
         assert_rel(p[k].grad, sdo[k].grad, 1e-3, 'd' + k)
 
 
-@pytest.mark.parametrize('B,H,W', [(2, 16, 16), (1, 25, 25), (2, 10, 17)])
+@pytest.mark.parametrize('B,H,W', GEOMS)
 @pytest.mark.parametrize('shift', [0, 3])
-def test_wmsa_bf16_fwd_bwd(B, H, W, shift):
-    heads, C = 3, 96
+@pytest.mark.parametrize('heads', [3, 4])
+def test_wmsa_bf16_fwd_bwd(B, H, W, shift, heads):
+    """bf16 forward = the tcgen05 kernel (wmsa_tc.cu); includes odd window counts (a lone
+    second unit), padded windows and both shift masks."""
+    C = heads * 32
     sd = {k: v.bfloat16().float() for k, v in _msa_state(C, heads, seed=7).items()}
     g = torch.Generator().manual_seed(2)
     x = torch.randn(B, H * W, C, generator=g).bfloat16().float()
