@@ -386,7 +386,7 @@ extern "C" int rsc_wmsa_fwd_simt(const void *qkv, const float *qkv_bias, const f
   return dispatch_fwd<__nv_bfloat16>(qkv, qkv_bias, bias_table, out, g, C, heads, scale, (cudaStream_t)stream);
 }
 
-extern "C" int rsc_wmsa_bwd(const void *qkv, const float *qkv_bias, const float *bias_table, const void *dout,
+extern "C" int rsc_wmsa_bwd_simt(const void *qkv, const float *qkv_bias, const float *bias_table, const void *dout,
                             void *dqkv, float *dbias_table, float *dqkv_bias, int B, int H, int W, int C, int heads,
                             int ws, int shift, float scale, int dtype, void *stream) {
   if (int e = check_args("rsc_wmsa_bwd", B, H, W, C, heads, ws, shift, dtype)) return e;

@@ -261,3 +261,303 @@ extern "C" int rsc_wmsa_fwd(const void *qkv, const float *qkv_bias, const float 
   RSC_CHECK_LAUNCH("rsc_wmsa_fwd");
   return RSC_OK;
 }
+
+// =====================================================================================
+// Backward on the tensor cores (bf16).  Per pair of (window, head) units, five MMA groups:
+//   S  = [Qa;Qb][Ka;Kb]^T            dP = [dOa;dOb][Va;Vb]^T          (recompute; TMEM 2 x 128 columns)
+//   -- SIMT: P = softmax(scale*S + bias + mask), D = sum_j P*dP, dS = P*(dP - D), both written to smem
+//      as block-diagonal [128 x 128] bf16 tiles (off-diagonal blocks stay zero) --
+//   dV = P^T dO ,  dK = dS^T Q        (A = the same smem tile read MN-major, K = 128 query rows)
+//   dQ = dS K                          (A = dS K-major, K = 128 key columns)
+// d(bias table) is accumulated per thread in registers across the persistent loop (fixed head per
+// CTA) and folded once at the end; gradients of padded rows go to the qkv-bias gradient.
+// =====================================================================================
+namespace rsc {
+namespace wtc {
+
+constexpr int B_Q = 0, B_K = 8192, B_V = 16384, B_DO = 24576, B_P = 32768, B_DS = 65536;
+constexpr int B_TBL = 98304;             // 169 floats (+pad)
+constexpr int B_PAD = B_TBL + 704;       // 3 x 32 floats: qkv-bias gradient of padded rows
+constexpr int B_TOTAL = B_PAD + 384;     // ~97.4 KB -> 2 CTAs / SM
+constexpr int B_TMEM = 256;
+
+// block-diagonal [128 rows][128 cols] bf16 tile: 16-byte chunk kc (8 columns) of row r
+__device__ __forceinline__ int bd_off(int r, int kc) { return kc * 2048 + (r >> 3) * 128 + (r & 7) * 16; }
+
+__global__ void __launch_bounds__(THREADS, 2)
+    wmsa_bwd_tc_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ qkv_bias,
+                       const float *__restrict__ table, const __nv_bfloat16 *__restrict__ dout,
+                       __nv_bfloat16 *__restrict__ dqkv, float *__restrict__ dtable, float *__restrict__ dqkv_bias,
+                       WinGeom g, int C, int heads, float scale, int num_windows, int num_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float *tbl = reinterpret_cast<float *>(smem + B_TBL);
+  float *padacc = reinterpret_cast<float *>(smem + B_PAD);
+  const int head = blockIdx.x % heads;   // gridDim.x is a multiple of heads
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, B_TMEM);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  for (int k = tid; k < B_TBL / 16; k += THREADS) reinterpret_cast<uint4 *>(smem)[k] = make_uint4(0, 0, 0, 0);
+  for (int k = tid; k < TBL; k += THREADS) tbl[k] = __ldg(table + k * heads + head);
+  for (int k = tid; k < 96; k += THREADS) padacc[k] = 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = tmem_base_s;
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
+  const uint32_t idesc_t = make_idesc_bf16(128, 32, true, true);    // A^T (MN-major) x MN-major B
+  const uint32_t idesc_q = make_idesc_bf16(128, 32, false, true);   // K-major A x MN-major B
+  uint32_t phase = 0;
+
+  const int unit = tid >> 6, i = tid & 63;
+  const int ri = i / WS, ci = i % WS;
+  const float *tb = tbl + (ri + WS - 1) * (2 * WS - 1) + (ci + WS - 1);
+  float dbacc[NT];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) dbacc[j] = 0.f;
+
+  for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    const int pair = item / heads;
+    // ---------------- gather q|k|v|dO rows of both units ----------------
+    for (int idx = tid; idx < 2 * NT * 16; idx += THREADS) {
+      const int c = idx & 3;
+      const int part = (idx >> 2) & 3;       // q | k | v | dO
+      const int t = (idx >> 4) % NT;
+      const int u = idx / (16 * NT);
+      const int win = 2 * pair + u;
+      if (win >= num_windows) continue;
+      const int ww = win % g.nWw, wh = (win / g.nWw) % g.nWh, b = win / (g.nWw * g.nWh);
+      int h, w;
+      const bool ok = g.source(wh, ww, t / WS, t % WS, h, w);
+      const uint32_t dst = sb + part * 8192 + tile_off(u * 64 + t, c);
+      const int64_t tok = ((int64_t)b * g.H + h) * g.W + w;
+      if (ok) {
+        if (part < 3)
+          cp_async16(dst, qkv + tok * (3 * C) + part * C + head * HD + c * 8);
+        else
+          cp_async16(dst, dout + tok * C + head * HD + c * 8);
+      } else {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (part < 3 && qkv_bias) {
+          const int col = part * C + head * HD + c * 8;
+          const float4 f0 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col));
+          const float4 f1 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col + 4));
+          v = make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                     : "memory");
+      }
+    }
+    cp_async_wait_all();
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---------------- S = Q K^T (cols 0..127), dP = dO V^T (cols 128..255) ----------------
+    if (tid == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        mma_bf16_ss(tm, make_smem_desc(sb + B_Q + k * 256, 128, 512), make_smem_desc(sb + B_K + k * 256, 128, 512),
+                    idesc_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        mma_bf16_ss(tm + 128, make_smem_desc(sb + B_DO + k * 256, 128, 512),
+                    make_smem_desc(sb + B_V + k * 256, 128, 512), idesc_s, k > 0);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    // ---------------- softmax backward on this thread's row ----------------
+    const int win = 2 * pair + unit;
+    const bool unit_ok = win < num_windows;
+    int b = 0, wh = 0, ww = 0;
+    if (unit_ok) {
+      ww = win % g.nWw;
+      wh = (win / g.nWw) % g.nWh;
+      b = win / (g.nWw * g.nWh);
+    }
+    {
+      uint32_t s0[32], s1[32];
+      const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16) + unit * 64;
+      tmem_ld32(taddr, s0);
+      tmem_ld32(taddr + 32, s1);
+      tmem_ld_wait();
+      uint32_t pp[32], pd[32];   // packed bf16 P row and dS row (64 columns each)
+      // Branch-free on purpose: the TMEM loads below are warp-aligned instructions, so every lane
+      // runs the whole row computation; rows that are not real queries are zeroed by `valid`.
+      const bool valid = unit_ok && i < NT;
+      uint32_t rowbits = 0, colbits = 0;
+      if (g.shift > 0) {
+        const bool lr = wh == g.nWh - 1, lc = ww == g.nWw - 1;
+        const int rh_i = lr ? (ri < WS - g.shift ? 1 : 2) : 0, rw_i = lc ? (ci < WS - g.shift ? 1 : 2) : 0;
+#pragma unroll
+        for (int j = 0; j < WS; ++j) {
+          const int rj = j < WS - g.shift ? 1 : 2;
+          rowbits |= (uint32_t)((lr ? rj : 0) != rh_i) << j;
+          colbits |= (uint32_t)((lc ? rj : 0) != rw_i) << j;
+        }
+      }
+      float p[NT];
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int jr = j / WS, jc = j % WS;
+        float sj = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]) * scale + tb[-(jr * (2 * WS - 1) + jc)];
+        if (((rowbits >> jr) | (colbits >> jc)) & 1u) sj += -100.0f;
+        p[j] = sj;
+        m = fmaxf(m, sj);
+      }
+      float l = 0.f;
+      const float ml2 = m * 1.4426950408889634f;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        p[j] = exp2f(fmaf(p[j], 1.4426950408889634f, -ml2));
+        l += p[j];
+      }
+      const float inv_l = valid ? 1.0f / l : 0.f;
+      tmem_ld32(taddr + 128, s0);   // dP row (reuses the S registers)
+      tmem_ld32(taddr + 160, s1);
+      tmem_ld_wait();
+      float D = 0.f;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        p[j] = valid ? p[j] * inv_l : 0.f;
+        D = fmaf(p[j], __uint_as_float(j < 32 ? s0[j] : s1[j - 32]), D);
+      }
+#pragma unroll
+      for (int j = 0; j < 24; ++j) pp[j] = pack_bf16(p[2 * j], p[2 * j + 1]);
+      pp[24] = pack_bf16(p[48], 0.f);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float ds = valid ? p[j] * (__uint_as_float(j < 32 ? s0[j] : s1[j - 32]) - D) : 0.f;
+        dbacc[j] += ds;
+        p[j] = ds;
+      }
+#pragma unroll
+      for (int j = 0; j < 24; ++j) pd[j] = pack_bf16(p[2 * j], p[2 * j + 1]);
+      pd[24] = pack_bf16(p[48], 0.f);
+#pragma unroll
+      for (int j = 25; j < 32; ++j) pp[j] = 0u, pd[j] = 0u;
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {
+        const uint32_t o = bd_off(tid, unit * 8 + kc);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + B_P + o), "r"(pp[4 * kc]),
+                     "r"(pp[4 * kc + 1]), "r"(pp[4 * kc + 2]), "r"(pp[4 * kc + 3])
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + B_DS + o), "r"(pd[4 * kc]),
+                     "r"(pd[4 * kc + 1]), "r"(pd[4 * kc + 2]), "r"(pd[4 * kc + 3])
+                     : "memory");
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---------------- dV = P^T dO (cols 0..31), dK = dS^T Q (32..63), dQ = dS K (64..95) ----------------
+    if (tid == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)   // K = 128 query rows, 16 per step
+        mma_bf16_ss(tm, make_smem_desc(sb + B_P + k * 256, 128, 2048), make_smem_desc(sb + B_DO + k * 1024, 512, 128),
+                    idesc_t, k > 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        mma_bf16_ss(tm + 32, make_smem_desc(sb + B_DS + k * 256, 128, 2048),
+                    make_smem_desc(sb + B_Q + k * 1024, 512, 128), idesc_t, k > 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)   // K = 128 key columns, 16 per step
+        mma_bf16_ss(tm + 64, make_smem_desc(sb + B_DS + k * 4096, 2048, 128),
+                    make_smem_desc(sb + B_K + k * 1024, 512, 128), idesc_q, k > 0);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    // ---------------- store dq | dk | dv of this thread's token ----------------
+    {
+      uint32_t o[32];
+      const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16);
+      int h = 0, w = 0;
+      const bool row_ok = unit_ok && i < NT;
+      const bool tok_ok = row_ok && g.source(wh, ww, ri, ci, h, w);
+      __nv_bfloat16 *dst = dqkv + (((int64_t)b * g.H + h) * g.W + w) * (3 * C) + head * HD;
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {   // TMEM columns: dV 0, dK 32, dQ 64 -> dqkv parts 2, 1, 0
+        tmem_ld32(taddr + part * 32, o);
+        tmem_ld_wait();
+        const float sc = part == 0 ? 1.0f : scale;
+        const int qpart = 2 - part;
+        if (tok_ok) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(o[8 * c + 0]) * sc, __uint_as_float(o[8 * c + 1]) * sc);
+            v.y = pack_bf16(__uint_as_float(o[8 * c + 2]) * sc, __uint_as_float(o[8 * c + 3]) * sc);
+            v.z = pack_bf16(__uint_as_float(o[8 * c + 4]) * sc, __uint_as_float(o[8 * c + 5]) * sc);
+            v.w = pack_bf16(__uint_as_float(o[8 * c + 6]) * sc, __uint_as_float(o[8 * c + 7]) * sc);
+            *reinterpret_cast<uint4 *>(dst + qpart * C + 8 * c) = v;
+          }
+        } else if (row_ok && dqkv_bias) {
+#pragma unroll
+          for (int d = 0; d < 32; ++d) atomicAdd(padacc + qpart * 32 + d, __uint_as_float(o[d]) * sc);
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
+  // ---------------- fold the bias-table gradient: registers -> smem table -> global ----------------
+  float *fold = reinterpret_cast<float *>(smem + B_P);   // P tile is free now
+  for (int k = tid; k < TBL; k += THREADS) fold[k] = 0.f;
+  __syncthreads();
+  if (i < NT) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) atomicAdd(fold + (ri - j / WS + WS - 1) * (2 * WS - 1) + (ci - j % WS + WS - 1), dbacc[j]);
+  }
+  __syncthreads();
+  for (int k = tid; k < TBL; k += THREADS) atomicAdd(dtable + k * heads + head, fold[k]);
+  if (dqkv_bias)
+    for (int k = tid; k < 96; k += THREADS) {
+      const float v = padacc[k];
+      if (v != 0.f) atomicAdd(dqkv_bias + (k / 32) * C + head * HD + (k % 32), v);
+    }
+  if (warp == 0) tmem_dealloc(tm, B_TMEM);
+}
+
+}  // namespace wtc
+}  // namespace rsc
+
+extern "C" int rsc_wmsa_bwd_simt(const void *qkv, const float *qkv_bias, const float *bias_table, const void *dout,
+                                 void *dqkv, float *dbias_table, float *dqkv_bias, int B, int H, int W, int C,
+                                 int heads, int ws, int shift, float scale, int dtype, void *stream);
+
+extern "C" int rsc_wmsa_bwd(const void *qkv, const float *qkv_bias, const float *bias_table, const void *dout,
+                            void *dqkv, float *dbias_table, float *dqkv_bias, int B, int H, int W, int C, int heads,
+                            int ws, int shift, float scale, int dtype, void *stream) {
+  static const bool force_simt = getenv("RSC_WMSA_SIMT") != nullptr;
+  const bool tc_ok = dtype == RSC_BF16 && ws == 7 && (shift == 0 || shift == 3) && heads > 0 && C == heads * 32 &&
+                     B > 0 && H > 0 && W > 0 && qkv && bias_table && dout && dqkv && dbias_table &&
+                     !(dqkv_bias && !qkv_bias) && heads <= 2 * kNumSMs;
+  if (!tc_ok || force_simt)
+    return rsc_wmsa_bwd_simt(qkv, qkv_bias, bias_table, dout, dqkv, dbias_table, dqkv_bias, B, H, W, C, heads, ws,
+                             shift, scale, dtype, stream);
+  WinGeom g(B, H, W, ws, shift);
+  const int num_windows = B * g.nWh * g.nWw;
+  const int num_items = ((num_windows + 1) / 2) * heads;
+  auto kern = wtc::wmsa_bwd_tc_kernel;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::B_TOTAL);
+  int grid = (kNumSMs * 2) / heads * heads;
+  if (grid > num_items) grid = num_items;   // num_items is a multiple of heads
+  kern<<<grid, wtc::THREADS, wtc::B_TOTAL, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16 *)qkv, qkv_bias, bias_table, (const __nv_bfloat16 *)dout, (__nv_bfloat16 *)dqkv,
+      dbias_table, dqkv_bias, g, C, heads, scale, num_windows, num_items);
+  RSC_CHECK_LAUNCH("rsc_wmsa_bwd");
+  return RSC_OK;
+}

@@ -143,8 +143,8 @@ def test_wmsa_bf16_fwd_bwd(B, H, W, shift, heads):
     y.backward(gy.cuda().bfloat16())
     assert_rel(y, yo, 2e-2, 'out')
     assert_rel(xg.grad, xo.grad, 3e-2, 'dx')
-    assert_rel(p['attn.w_msa.relative_position_bias_table'].grad,
-               sdo['attn.w_msa.relative_position_bias_table'].grad, 3e-2, 'dtable')
+    for k in sd:       # incl. the qkv-bias gradient that flows through the padded rows
+        assert_rel(p[k].grad, sdo[k].grad, 3e-2, 'd' + k)
 
 
 def test_wmsa_large_property():
