@@ -106,6 +106,20 @@ int rsc_patch_merge_ln_bwd(const void *x, const float *gamma, const float *mean,
                            void *stream);
 
 /* ------------------------------------------------------------------------
+ * LayerNorm over the last dimension.  Replaces ATen native_layer_norm(+backward)
+ * behind nn.LayerNorm in mmdet SwinBlock (norm1/norm2), SwinTransformer.norm{i},
+ * PatchEmbed.norm and mmcv BaseTransformerLayer.norms.
+ *   x (rows,C) in_dtype -> y (rows,C) out_dtype; mean/rstd (rows) float.
+ * bwd: dy is out_dtype, dx is in_dtype (fully written); dgamma/dbeta (C) float ACCUMULATED.
+ * C % 4 == 0, C <= 1024.
+ * ---------------------------------------------------------------------- */
+int rsc_layernorm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *mean, float *rstd,
+                      int64_t rows, int C, float eps, int in_dtype, int out_dtype, void *stream);
+int rsc_layernorm_bwd(const void *x, const float *gamma, const float *mean, const float *rstd, const void *dy,
+                      void *dx, float *dgamma, float *dbeta, int64_t rows, int C, int in_dtype, int out_dtype,
+                      void *stream);
+
+/* ------------------------------------------------------------------------
  * Multi-scale deformable attention.  Drop-in for mmcv-full 1.6.1
  *   ext_module.ms_deform_attn_forward / ms_deform_attn_backward
  * (mmcv/ops/multi_scale_deform_attn.py::MultiScaleDeformableAttnFunction),

@@ -404,6 +404,16 @@ __global__ void __launch_bounds__(THREADS, 2)
           colbits |= (uint32_t)((lc ? rj : 0) != rw_i) << j;
         }
       }
+      // key tokens of this window that are zero-padding (their dk/dv flow to the qkv-bias gradient)
+      uint32_t rowpad = 0, colpad = 0;
+#pragma unroll
+      for (int j = 0; j < WS; ++j) {
+        int hh = wh * WS + j + g.shift, wc = ww * WS + j + g.shift;
+        if (hh >= g.Hp) hh -= g.Hp;
+        if (wc >= g.Wp) wc -= g.Wp;
+        rowpad |= (uint32_t)(hh >= g.H) << j;
+        colpad |= (uint32_t)(wc >= g.W) << j;
+      }
       float p[NT];
       float m = -INFINITY;
 #pragma unroll
@@ -425,24 +435,28 @@ __global__ void __launch_bounds__(THREADS, 2)
       tmem_ld32(taddr + 128, s0);   // dP row (reuses the S registers)
       tmem_ld32(taddr + 160, s1);
       tmem_ld_wait();
-      float D = 0.f;
+      // Column 49 of the P / dS tiles (a zero-padding column of the MMA) carries the row's sum over the
+      // PADDED keys: row 49 of dV = P^T dO / dK = dS^T Q then IS the padded-row gradient sum, for free.
+      float D = 0.f, wp = 0.f, wds = 0.f;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         p[j] = valid ? p[j] * inv_l : 0.f;
         D = fmaf(p[j], __uint_as_float(j < 32 ? s0[j] : s1[j - 32]), D);
+        if (((rowpad >> (j / WS)) | (colpad >> (j % WS))) & 1u) wp += p[j];
       }
 #pragma unroll
       for (int j = 0; j < 24; ++j) pp[j] = pack_bf16(p[2 * j], p[2 * j + 1]);
-      pp[24] = pack_bf16(p[48], 0.f);
+      pp[24] = pack_bf16(p[48], wp);
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const float ds = valid ? p[j] * (__uint_as_float(j < 32 ? s0[j] : s1[j - 32]) - D) : 0.f;
         dbacc[j] += ds;
         p[j] = ds;
+        if (((rowpad >> (j / WS)) | (colpad >> (j % WS))) & 1u) wds += ds;
       }
 #pragma unroll
       for (int j = 0; j < 24; ++j) pd[j] = pack_bf16(p[2 * j], p[2 * j + 1]);
-      pd[24] = pack_bf16(p[48], 0.f);
+      pd[24] = pack_bf16(p[48], wds);
 #pragma unroll
       for (int j = 25; j < 32; ++j) pp[j] = 0u, pd[j] = 0u;
 #pragma unroll
@@ -503,9 +517,14 @@ __global__ void __launch_bounds__(THREADS, 2)
             v.w = pack_bf16(__uint_as_float(o[8 * c + 6]) * sc, __uint_as_float(o[8 * c + 7]) * sc);
             *reinterpret_cast<uint4 *>(dst + qpart * C + 8 * c) = v;
           }
-        } else if (row_ok && dqkv_bias) {
+        } else if (unit_ok && i == NT && part < 2 && dqkv_bias) {
+          // row 49 = sum over this window's padded keys (zero when the window has none); dq of padded
+          // queries is identically zero (their output rows are cropped)
 #pragma unroll
-          for (int d = 0; d < 32; ++d) atomicAdd(padacc + qpart * 32 + d, __uint_as_float(o[d]) * sc);
+          for (int d = 0; d < 32; ++d) {
+            const float v = __uint_as_float(o[d]) * sc;
+            if (v != 0.f) atomicAdd(padacc + qpart * 32 + d, v);
+          }
         }
       }
     }

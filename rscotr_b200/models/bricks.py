@@ -28,11 +28,19 @@ def build_activation(cfg):
     raise KeyError('unsupported activation %s' % t)
 
 
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm parameters / state-dict keys, forward on rsc_layernorm_{fwd,bwd}: one pass,
+    fp32 statistics, output already in the compute dtype of the GEMM that follows."""
+
+    def forward(self, x):
+        return ops.layer_norm(x, self.weight, self.bias, self.eps)
+
+
 def build_norm(cfg, num_features):
     cfg = dict(cfg)
     t = cfg.pop('type')
     if t == 'LN':
-        return nn.LayerNorm(num_features, **cfg)
+        return LayerNorm(num_features, **cfg)
     if t == 'GN':
         return nn.GroupNorm(cfg.pop('num_groups'), num_features, **cfg)
     if t in ('BN', 'SyncBN'):      # per-rank BN (SURVEY D.5: no forward-time collectives)

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS, build_from_cfg
-from .bricks import (TransformerLayerSequence, MultiScaleDeformableAttention, build_positional_encoding,
+from .bricks import (LayerNorm, TransformerLayerSequence, MultiScaleDeformableAttention, build_positional_encoding,
                      build_transformer_layer_sequence, inverse_sigmoid)
 
 
@@ -79,7 +79,7 @@ class DinoTransformerDecoder(TransformerLayerSequence):
         super().__init__(*args, **kwargs)
         self.return_intermediate = return_intermediate
         self.ref_point_head = build_MLP(self.embed_dims * 2, self.embed_dims, self.embed_dims, 2)
-        self.norm = nn.LayerNorm(self.embed_dims)
+        self.norm = LayerNorm(self.embed_dims)
 
     @staticmethod
     def gen_sineembed_for_position(pos_tensor):
@@ -141,7 +141,7 @@ class DinoTransformer(nn.Module):
         self.embed_dims = self.decoder.embed_dims
         self.level_embeds = nn.Parameter(torch.Tensor(self.num_feature_levels, self.embed_dims))
         self.enc_output = nn.Linear(self.embed_dims, self.embed_dims)
-        self.enc_output_norm = nn.LayerNorm(self.embed_dims)
+        self.enc_output_norm = LayerNorm(self.embed_dims)
         self.query_embed = nn.Embedding(self.two_stage_num_proposals, self.embed_dims)
 
     def init_weights(self):

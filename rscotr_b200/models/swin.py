@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS
-from .bricks import FFN, DropPath
+from .bricks import FFN, DropPath, LayerNorm
 
 
 class WindowMSA(nn.Module):
@@ -77,10 +77,10 @@ class SwinBlock(nn.Module):
                  with_cp=False):
         super().__init__()
         self.with_cp = with_cp
-        self.norm1 = nn.LayerNorm(embed_dims)
+        self.norm1 = LayerNorm(embed_dims)
         self.attn = ShiftWindowMSA(embed_dims, num_heads, window_size, window_size // 2 if shift else 0, qkv_bias,
                                    qk_scale, attn_drop_rate, drop_rate, dict(type='DropPath', drop_prob=drop_path_rate))
-        self.norm2 = nn.LayerNorm(embed_dims)
+        self.norm2 = LayerNorm(embed_dims)
         self.ffn = FFN(embed_dims, feedforward_channels, 2, act_cfg, drop_rate,
                        dict(type='DropPath', drop_prob=drop_path_rate), add_identity=True)
 
@@ -135,7 +135,7 @@ class PatchEmbed(nn.Module):
         super().__init__()
         self.kernel = kernel_size
         self.projection = nn.Conv2d(in_channels, embed_dims, kernel_size, stride)
-        self.norm = nn.LayerNorm(embed_dims) if norm else None
+        self.norm = LayerNorm(embed_dims) if norm else None
 
     def forward(self, x):
         H, W = x.shape[-2:]
@@ -184,7 +184,7 @@ class SwinTransformer(nn.Module):
                 in_ch = downsample.out_channels
         self.num_features = [int(embed_dims * 2 ** i) for i in range(len(depths))]
         for i in self.out_indices:
-            self.add_module('norm%d' % i, nn.LayerNorm(self.num_features[i]))
+            self.add_module('norm%d' % i, LayerNorm(self.num_features[i]))
         self.init_weights()
 
     def init_weights(self):

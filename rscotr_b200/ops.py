@@ -208,6 +208,51 @@ def patch_merge_ln(x, hw, gamma, beta, eps=1e-5):
 
 
 # ---------------------------------------------------------------------------
+# LayerNorm                                       
+# ---------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, out_dtype):
+        _cuda(x, gamma, beta)
+        C = x.shape[-1]
+        xc = x.contiguous()
+        rows = xc.numel() // C
+        g32, b32 = _f32(gamma), _f32(beta)
+        y = torch.empty(xc.shape, dtype=out_dtype, device=x.device)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        with torch.cuda.device(x.device):
+            call('rsc_layernorm_fwd', xc.data_ptr(), g32.data_ptr(), b32.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                 rstd.data_ptr(), rows, C, eps, _dt(xc), _dt(y), _stream(),
+                 alg_bytes=xc.numel() * (xc.element_size() + y.element_size()))
+        ctx.save_for_backward(xc, g32, mean, rstd)
+        ctx.meta = (rows, C, gamma.dtype, beta.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, g32, mean, rstd = ctx.saved_tensors
+        rows, C, gdt, bdt = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty_like(xc)
+        dg = torch.zeros(C, dtype=torch.float32, device=xc.device)
+        db = torch.zeros_like(dg)
+        with torch.cuda.device(xc.device):
+            call('rsc_layernorm_bwd', xc.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dy.data_ptr(),
+                 dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, C, _dt(xc), _dt(dy), _stream(),
+                 alg_bytes=xc.numel() * (2 * xc.element_size() + dy.element_size()))
+        return dx, dg.to(gdt), db.to(bdt), None, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, out_dtype=None):
+    """LayerNorm over the last dim; output dtype defaults to the active autocast dtype
+    (so the GEMM that follows reads bf16 directly) or x.dtype outside autocast."""
+    if out_dtype is None:
+        out_dtype = torch.get_autocast_dtype('cuda') if torch.is_autocast_enabled('cuda') else x.dtype
+    return _LayerNorm.apply(x, gamma, beta, float(eps), out_dtype)
+
+
+# ---------------------------------------------------------------------------
 # multi-scale deformable attention                (SURVEY 8a row a11)
 # ---------------------------------------------------------------------------
 class MultiScaleDeformableAttnFunction(torch.autograd.Function):

@@ -332,3 +332,32 @@ def test_sigmoid_focal_loss(dtype):
     tol = 1e-4 if dtype == torch.float32 else 1e-2
     assert_rel(l, lo, tol, 'focal')
     assert_rel(xg.grad, xo.grad, tol, 'dfocal')
+
+
+# ---------------------------------------------------------------------------
+# LayerNorm (a1, a2, a7, a9)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('rows,C', [(5, 96), (1000, 96), (333, 192), (64, 256), (77, 384), (31, 768), (9, 1024)])
+@pytest.mark.parametrize('in_dt,out_dt', [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                          (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32)])
+def test_layernorm(rows, C, in_dt, out_dt):
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows + C)
+    x = (torch.randn(rows, C, generator=g) * 2 + 0.5).to(in_dt)
+    gamma = 1 + 0.2 * torch.randn(C, generator=g)
+    beta = 0.2 * torch.randn(C, generator=g)
+    gy = torch.randn(rows, C, generator=g).to(out_dt)
+    xo, go, bo = x.float().clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yo = F.layer_norm(xo, (C,), go, bo)
+    yo.backward(gy.float())
+    xg = x.clone().cuda().requires_grad_(True)
+    gg, bg = gamma.clone().cuda().requires_grad_(True), beta.clone().cuda().requires_grad_(True)
+    y = ops.layer_norm(xg, gg, bg, 1e-5, out_dt)
+    assert y.dtype == out_dt
+    y.backward(gy.cuda())
+    tol_y = 1e-5 if out_dt == torch.float32 else 6e-3
+    tol_g = 2e-5 if in_dt == torch.float32 else 1e-2
+    assert_rel(y, yo, tol_y, 'y')
+    assert_rel(xg.grad, xo.grad, tol_g, 'dx')
+    assert_rel(gg.grad, go.grad, 1e-4, 'dgamma')
+    assert_rel(bg.grad, bo.grad, 1e-4, 'dbeta')
