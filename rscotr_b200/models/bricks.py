@@ -18,6 +18,23 @@ from .. import ops
 from ..config import MODELS, build_from_cfg
 
 
+_CONST_CACHE = {}
+
+
+def const_tensor(values, dtype, device):
+    """Small host-defined constant (image factors, level shapes, ...) as a cached device tensor:
+    created once (one pageable H2D copy), reused afterwards -- no per-step H2D copies and
+    nothing illegal under CUDA-graph capture."""
+    def freeze(v):
+        return tuple(freeze(x) for x in v) if isinstance(v, (list, tuple)) else v
+    key = (freeze(values), dtype, str(device))
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        t = torch.tensor(values, dtype=dtype, device=device)
+        _CONST_CACHE[key] = t
+    return t
+
+
 def build_activation(cfg):
     cfg = dict(cfg or dict(type='ReLU'))
     t = cfg.pop('type')

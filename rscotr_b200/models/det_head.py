@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS, build_from_cfg
-from .bricks import (LayerNorm, TransformerLayerSequence, MultiScaleDeformableAttention, build_positional_encoding,
+from .bricks import (LayerNorm, TransformerLayerSequence, const_tensor, MultiScaleDeformableAttention, build_positional_encoding,
                      build_transformer_layer_sequence, inverse_sigmoid)
 
 
@@ -52,11 +52,10 @@ def giou(b1, b2, aligned, eps=1e-6):
         erb = torch.max(b1[..., :, None, 2:], b2[..., None, :, 2:])
     wh = (rb - lt).clamp(min=0)
     overlap = wh[..., 0] * wh[..., 1]
-    eps_t = union_base.new_tensor([eps])
-    union = torch.max(union_base - overlap, eps_t)
+    union = (union_base - overlap).clamp(min=eps)
     ious = overlap / union
     ewh = (erb - elt).clamp(min=0)
-    earea = torch.max(ewh[..., 0] * ewh[..., 1], eps_t)
+    earea = (ewh[..., 0] * ewh[..., 1]).clamp(min=eps)
     return ious - (earea - union) / earea
 
 
@@ -216,7 +215,7 @@ class DinoTransformer(nn.Module):
         mask_flatten = torch.cat(mask_flatten, 1)
         lvl_pos_embed_flatten = torch.cat(lvl_pos_embed_flatten, 1)
         shapes_py = spatial_shapes
-        spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long, device=feat_flatten.device)
+        spatial_shapes = const_tensor(spatial_shapes, torch.long, feat_flatten.device)
         level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in mlvl_masks], 1)
         reference_points = self.get_reference_points(shapes_py, valid_ratios, device=feat_flatten.device)
@@ -300,7 +299,7 @@ class CdnQueryGenerator:
         boxes_n = []
         for img_meta, bboxes in zip(img_metas, gt_bboxes):
             img_h, img_w, _ = img_meta['img_shape']
-            factor = bboxes.new_tensor([img_w, img_h, img_w, img_h]).unsqueeze(0)
+            factor = const_tensor([[img_w, img_h, img_w, img_h]], bboxes.dtype, bboxes.device)
             boxes_n.append(bbox_xyxy_to_cxcywh(bboxes) / factor)
         known_num = [int(l.numel()) for l in gt_labels]
         single_pad = int(max(known_num))
@@ -390,7 +389,7 @@ class HungarianAssigner:
     def cost(self, bbox_pred, cls_pred, gt_bboxes, gt_labels, img_shape):
         """bbox_pred (..., Nq, 4) cxcywh normalised, cls_pred (..., Nq, C) logits -> (..., Nq, n_gt)."""
         img_h, img_w = img_shape[:2]
-        factor = gt_bboxes.new_tensor([img_w, img_h, img_w, img_h]).unsqueeze(0)
+        factor = const_tensor([[img_w, img_h, img_w, img_h]], gt_bboxes.dtype, gt_bboxes.device)
         p = cls_pred.float().sigmoid()
         neg = -(1 - p + self.eps).log() * (1 - self.alpha) * p.pow(self.gamma)
         pos = -(p + self.eps).log() * self.alpha * (1 - p).pow(self.gamma)
@@ -555,6 +554,15 @@ class DINOHead(nn.Module):
         outs = self(shared_encoder, mlvl_feats, img_metas, dn_label_query, dn_bbox_query, attn_mask)
         return self.loss(*outs, gt_bboxes, gt_labels, img_metas, dn_meta, gt_bboxes_ignore=gt_bboxes_ignore)
 
+    def forward_train_begin(self, mlvl_feats, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None,
+                            shared_encoder=None):
+        """forward_train up to (not including) the host-side matching; finish with
+        loss_assign(pend) + loss_finish(pend)."""
+        dn_label_query, dn_bbox_query, attn_mask, dn_meta = self.dn_generator(
+            gt_bboxes, gt_labels, self.label_embedding, img_metas)
+        outs = self(shared_encoder, mlvl_feats, img_metas, dn_label_query, dn_bbox_query, attn_mask)
+        return self.loss_prepare(*outs, gt_bboxes, gt_labels, img_metas, dn_meta, gt_bboxes_ignore)
+
     def forward(self, encoder, mlvl_feats, img_metas, dn_label_query=None, dn_bbox_query=None, attn_mask=None):
         batch_size = mlvl_feats[0].size(0)
         input_img_h, input_img_w = img_metas[0]['batch_input_shape']
@@ -598,10 +606,20 @@ class DINOHead(nn.Module):
 
     def loss(self, all_cls_scores, all_bbox_preds, enc_topk_scores, enc_topk_anchors, gt_bboxes_list, gt_labels_list,
              img_metas, dn_meta=None, gt_bboxes_ignore=None):
+        """dino_head.py:152-234 in three phases so that a step engine can put the device work of
+        phases 1 and 3 into CUDA graphs around the host-side matching of phase 2."""
+        pend = self.loss_prepare(all_cls_scores, all_bbox_preds, enc_topk_scores, enc_topk_anchors, gt_bboxes_list,
+                                 gt_labels_list, img_metas, dn_meta, gt_bboxes_ignore)
+        self.loss_assign(pend)
+        return self.loss_finish(pend)
+
+    def loss_prepare(self, all_cls_scores, all_bbox_preds, enc_topk_scores, enc_topk_anchors, gt_bboxes_list,
+                     gt_labels_list, img_metas, dn_meta=None, gt_bboxes_ignore=None):
+        """phase 1 (device, sync free): split dn / matching parts, Hungarian cost matrices of all
+        (layer, image) pairs, target buffers initialised to 'background', fixed dn targets."""
         assert gt_bboxes_ignore is None, \
             '%s only supports for gt_bboxes_ignore setting to None.' % self.__class__.__name__
         all_cls_scores, all_bbox_preds = all_cls_scores.float(), all_bbox_preds.float()   # @force_fp32
-        loss_dict = dict()
         all_cls_scores, all_bbox_preds, dn_cls_scores, dn_bbox_preds = self.extract_dn_outputs(
             all_cls_scores, all_bbox_preds, dn_meta)
         # matching part: stack [encoder proposals, decoder layers] -> (1+L, B, Nq, .)
@@ -609,47 +627,39 @@ class DINOHead(nn.Module):
         if enc_topk_scores is not None:
             stacks_cls = torch.cat([enc_topk_scores.float()[None], all_cls_scores], 0)
             stacks_box = torch.cat([enc_topk_anchors.float()[None], all_bbox_preds], 0)
-        targets = self.get_targets_batched(stacks_cls, stacks_box, gt_bboxes_list, gt_labels_list, img_metas)
-        dn_t = None
-        pos_counts = [int(x) for x in targets['num_pos']]
-        neg_counts = [targets['num_total'] - x for x in pos_counts]
-        if dn_cls_scores is not None:
-            dn_t = self.get_dn_target(dn_bbox_preds[0], gt_bboxes_list, gt_labels_list, img_metas, dn_meta)
-            pos_counts.append(dn_t['num_pos'])
-            neg_counts.append(dn_t['num_neg'])
-        cls_factors, pos_factors = self._avg_factors(pos_counts, neg_counts, stacks_cls)
-        losses = [self.loss_single(stacks_cls[i], stacks_box[i], targets, i, img_metas, cls_factors[i], pos_factors[i])
-                  for i in range(len(stacks_cls))]
-        if enc_topk_scores is not None:
-            (loss_dict['interm_loss_cls'], loss_dict['interm_loss_bbox'], loss_dict['interm_loss_iou']) = losses[0]
-            losses = losses[1:]
-        loss_dict['loss_cls'], loss_dict['loss_bbox'], loss_dict['loss_iou'] = losses[-1]
-        for n, (lc, lb, li) in enumerate(losses[:-1]):
-            loss_dict['d%d.loss_cls' % n], loss_dict['d%d.loss_bbox' % n], loss_dict['d%d.loss_iou' % n] = lc, lb, li
-        if dn_cls_scores is not None:
-            dn_losses = [self.loss_dn_single(dn_cls_scores[i], dn_bbox_preds[i], dn_t, img_metas, cls_factors[-1],
-                                             pos_factors[-1]) for i in range(len(dn_cls_scores))]
-            loss_dict['dn_loss_cls'], loss_dict['dn_loss_bbox'], loss_dict['dn_loss_iou'] = dn_losses[-1]
-            for n, (lc, lb, li) in enumerate(dn_losses[:-1]):
-                loss_dict['d%d.dn_loss_cls' % n], loss_dict['d%d.dn_loss_bbox' % n], loss_dict['d%d.dn_loss_iou' % n] = lc, lb, li
-        return loss_dict
+        nl, B, Nq, _ = stacks_cls.shape
+        dev = stacks_cls.device
+        sizes = [int(l.numel()) for l in gt_labels_list]
+        with torch.no_grad():
+            costs = [self.assigner.cost(stacks_box[:, b], stacks_cls[:, b], gt_bboxes_list[b], gt_labels_list[b],
+                                        img_metas[b]['img_shape']).reshape(-1) for b in range(B) if sizes[b]]
+            cost_flat = torch.cat(costs) if costs else None
+            labels = torch.full((nl * B * Nq,), self.num_classes, dtype=torch.long, device=dev)
+            bbox_targets = torch.zeros(nl * B * Nq, 4, device=dev)
+            bbox_weights = torch.zeros(nl * B * Nq, 4, device=dev)
+            gt_cat_labels = torch.cat(gt_labels_list)
+            factors = torch.cat([const_tensor([[img_metas[b]['img_shape'][1], img_metas[b]['img_shape'][0]] * 2],
+                                              gt_bboxes_list[b].dtype, dev).expand(sizes[b], 4) for b in range(B)])
+            gt_cat_boxes = bbox_xyxy_to_cxcywh(torch.cat(gt_bboxes_list) / factors)
+            dn_t = None
+            if dn_cls_scores is not None:
+                dn_t = self.get_dn_target(dn_bbox_preds[0], gt_bboxes_list, gt_labels_list, img_metas, dn_meta)
+        return dict(stacks_cls=stacks_cls, stacks_box=stacks_box, dn_cls=dn_cls_scores, dn_box=dn_bbox_preds,
+                    has_enc=enc_topk_scores is not None, img_metas=img_metas, sizes=sizes, cost_flat=cost_flat,
+                    labels=labels, bbox_targets=bbox_targets, bbox_weights=bbox_weights, gt_cat_labels=gt_cat_labels,
+                    gt_cat_boxes=gt_cat_boxes, dn_t=dn_t)
 
     @torch.no_grad()
-    def get_targets_batched(self, cls_scores, bbox_preds, gt_bboxes_list, gt_labels_list, img_metas):
-        """Hungarian targets for all (layer, image) pairs: cost on GPU, ONE D2H copy,
-        scipy per problem, ONE H2D copy of the index lists (detr_head.py:475-543)."""
-        nl, B, Nq, _ = cls_scores.shape
-        dev = cls_scores.device
-        costs, sizes = [], []
-        for b in range(B):
-            n = int(gt_labels_list[b].numel())
-            sizes.append(n)
-            if n:
-                c = self.assigner.cost(bbox_preds[:, b], cls_scores[:, b], gt_bboxes_list[b], gt_labels_list[b],
-                                       img_metas[b]['img_shape'])
-                costs.append(c.reshape(-1))
-        flat = torch.cat(costs).cpu().numpy() if costs else np.zeros(0, np.float32)
-        rows, cols, off = [], [], 0
+    def loss_assign(self, pend):
+        """phase 2 (host): ONE device->host copy of all cost matrices, scipy per (layer, image)
+        problem, ONE host->device copy of the index lists written into the target buffers
+        (detr_head.py:475-543); then the averaging factors of every loss term."""
+        nl, B, Nq, _ = pend['stacks_cls'].shape
+        dev, sizes = pend['stacks_cls'].device, pend['sizes']
+        flat = pend['cost_flat'].cpu().numpy() if pend['cost_flat'] is not None else np.zeros(0, np.float32)
+        rows, gts, off = [], [], 0
+        num_pos = np.zeros(nl, dtype=np.int64)
+        gt_off = np.concatenate([[0], np.cumsum(sizes)[:-1]]) if sizes else np.zeros(0, np.int64)
         for b in range(B):
             n = sizes[b]
             if not n:
@@ -659,27 +669,47 @@ class DINOHead(nn.Module):
             for l in range(nl):
                 r, c = HungarianAssigner.solve(cb[l])
                 rows.append(((l * B + b) * Nq + r).astype(np.int64))      # flat index into (nl, B, Nq)
-                cols.append(np.stack([np.full_like(c, b), c]).astype(np.int64))
-        labels = torch.full((nl * B * Nq,), self.num_classes, dtype=torch.long, device=dev)
-        bbox_targets = torch.zeros(nl * B * Nq, 4, device=dev)
-        bbox_weights = torch.zeros(nl * B * Nq, 4, device=dev)
-        num_pos = np.zeros(nl, dtype=np.int64)
+                gts.append((gt_off[b] + c).astype(np.int64))
+                num_pos[l] += len(r)
         if rows:
-            rows_t = torch.from_numpy(np.concatenate(rows)).to(dev, non_blocking=True)
-            cols_np = np.concatenate(cols, 1)
-            gt_off = np.concatenate([[0], np.cumsum(sizes)[:-1]])
-            gidx = torch.from_numpy(gt_off[cols_np[0]] + cols_np[1]).to(dev, non_blocking=True)
-            gl = torch.cat(gt_labels_list)
-            factors = torch.cat([gt_bboxes_list[b].new_tensor(
-                [img_metas[b]['img_shape'][1], img_metas[b]['img_shape'][0]] * 2).expand(sizes[b], 4) for b in range(B)])
-            gb = bbox_xyxy_to_cxcywh(torch.cat(gt_bboxes_list) / factors)
-            labels[rows_t] = gl[gidx]
-            bbox_targets[rows_t] = gb[gidx]
-            bbox_weights[rows_t] = 1.0
-            for r in rows:
-                num_pos[r[0] // (B * Nq)] += len(r)
-        return dict(labels=labels.view(nl, B * Nq), bbox_targets=bbox_targets.view(nl, B * Nq, 4),
-                    bbox_weights=bbox_weights.view(nl, B * Nq, 4), num_pos=num_pos, num_total=B * Nq)
+            idx = torch.from_numpy(np.stack([np.concatenate(rows), np.concatenate(gts)]))
+            idx = idx.pin_memory().to(dev, non_blocking=True) if dev.type == 'cuda' else idx
+            rows_t, gidx = idx[0], idx[1]
+            pend['labels'][rows_t] = pend['gt_cat_labels'][gidx]
+            pend['bbox_targets'][rows_t] = pend['gt_cat_boxes'][gidx]
+            pend['bbox_weights'][rows_t] = 1.0
+        pos_counts = [int(x) for x in num_pos]
+        neg_counts = [B * Nq - x for x in pos_counts]
+        if pend['dn_t'] is not None:
+            pos_counts.append(pend['dn_t']['num_pos'])
+            neg_counts.append(pend['dn_t']['num_neg'])
+        pend['num_pos'] = num_pos
+        pend['cls_factors'], pend['pos_factors'] = self._avg_factors(pos_counts, neg_counts, pend['stacks_cls'])
+
+    def loss_finish(self, pend):
+        """phase 3 (device, sync free): the 7 matching losses and 6 denoising losses."""
+        nl, B, Nq, _ = pend['stacks_cls'].shape
+        img_metas = pend['img_metas']
+        targets = dict(labels=pend['labels'].view(nl, B * Nq), bbox_targets=pend['bbox_targets'].view(nl, B * Nq, 4),
+                       bbox_weights=pend['bbox_weights'].view(nl, B * Nq, 4), num_pos=pend['num_pos'])
+        cls_factors, pos_factors = pend['cls_factors'], pend['pos_factors']
+        loss_dict = dict()
+        losses = [self.loss_single(pend['stacks_cls'][i], pend['stacks_box'][i], targets, i, img_metas, cls_factors[i],
+                                   pos_factors[i]) for i in range(nl)]
+        if pend['has_enc']:
+            (loss_dict['interm_loss_cls'], loss_dict['interm_loss_bbox'], loss_dict['interm_loss_iou']) = losses[0]
+            losses = losses[1:]
+        loss_dict['loss_cls'], loss_dict['loss_bbox'], loss_dict['loss_iou'] = losses[-1]
+        for n, (lc, lb, li) in enumerate(losses[:-1]):
+            loss_dict['d%d.loss_cls' % n], loss_dict['d%d.loss_bbox' % n], loss_dict['d%d.loss_iou' % n] = lc, lb, li
+        if pend['dn_cls'] is not None:
+            dn_cls_scores, dn_bbox_preds, dn_t = pend['dn_cls'], pend['dn_box'], pend['dn_t']
+            dn_losses = [self.loss_dn_single(dn_cls_scores[i], dn_bbox_preds[i], dn_t, img_metas, cls_factors[-1],
+                                             pos_factors[-1]) for i in range(len(dn_cls_scores))]
+            loss_dict['dn_loss_cls'], loss_dict['dn_loss_bbox'], loss_dict['dn_loss_iou'] = dn_losses[-1]
+            for n, (lc, lb, li) in enumerate(dn_losses[:-1]):
+                loss_dict['d%d.dn_loss_cls' % n], loss_dict['d%d.dn_loss_bbox' % n], loss_dict['d%d.dn_loss_iou' % n] = lc, lb, li
+        return loss_dict
 
     def _avg_factors(self, pos_counts, neg_counts, like):
         """cls_avg_factor / num_total_pos of every loss_single call of this step
@@ -699,8 +729,8 @@ class DINOHead(nn.Module):
         return [max(float(c), 1) for c in cls_avg], [max(float(p), 1.0) for p in pos]
 
     def _box_losses(self, bbox_preds, bbox_targets, bbox_weights, img_metas, num_total_pos, any_pos):
-        factors = torch.cat([bbox_preds.new_tensor([m['img_shape'][1], m['img_shape'][0]] * 2).expand(
-            bbox_preds.size(1), 4) for m in img_metas], 0)
+        factors = torch.cat([const_tensor([[m['img_shape'][1], m['img_shape'][0]] * 2], bbox_preds.dtype,
+                                          bbox_preds.device).expand(bbox_preds.size(1), 4) for m in img_metas], 0)
         bp = bbox_preds.reshape(-1, 4)
         bboxes = bbox_cxcywh_to_xyxy(bp) * factors
         bboxes_gt = bbox_cxcywh_to_xyxy(bbox_targets) * factors
@@ -739,7 +769,7 @@ class DINOHead(nn.Module):
             labels[b, pos_inds] = gt_labels_list[b][t.flatten()]
             bbox_weights[b, pos_inds] = 1.0
             img_h, img_w, _ = img_metas[b]['img_shape']
-            factor = dn_bbox_pred.new_tensor([img_w, img_h, img_w, img_h]).unsqueeze(0)
+            factor = const_tensor([[img_w, img_h, img_w, img_h]], dn_bbox_pred.dtype, dn_bbox_pred.device)
             bbox_targets[b, pos_inds] = bbox_xyxy_to_cxcywh(gt_bboxes_list[b] / factor).repeat([num_groups, 1])
             npos += n * num_groups
             nneg += n * num_groups

@@ -159,8 +159,35 @@ class MTL(nn.Module):
         seg_pred = self.inference_seg(img, img_meta, rescale).argmax(dim=1)
         return list(seg_pred.cpu().numpy())
 
+    # train_step in three phases (device / host / device) so the step engine can capture the device
+    # phases in CUDA graphs; only the det task has host work (Hungarian matching) in the middle.
+    def train_step_begin(self, data):
+        task = data.get('task', None)
+        if task == 'det' and hasattr(self.bbox_head, 'forward_train_begin'):
+            img, img_metas = data['img'], data['img_metas']
+            batch_input_shape = tuple(img[0].size()[-2:])
+            for img_meta in img_metas:
+                img_meta['batch_input_shape'] = batch_input_shape
+            x = self.extract_feat(img)[0]
+            pend = self.bbox_head.forward_train_begin(x, img_metas, data['gt_bboxes'], data['gt_labels'],
+                                                      data.get('gt_bboxes_ignore'), self.shared_encoder)
+            return dict(data=data, pending=pend, losses=None)
+        return dict(data=data, pending=None, losses=self(**data))
+
+    def train_step_host(self, ctx):
+        if ctx['pending'] is not None:
+            self.bbox_head.loss_assign(ctx['pending'])
+
+    def train_step_finish(self, ctx):
+        data = ctx['data']
+        losses = ctx['losses'] if ctx['pending'] is None else self.bbox_head.loss_finish(ctx['pending'])
+        return self._finish(losses, data)
+
     def train_step(self, data, optimizer):
         losses = self(**data)
+        return self._finish(losses, data)
+
+    def _finish(self, losses, data):
         loss, log_vars = self._parse_losses(losses)
         task = data.get('task', None)
         dataset_name = data.get('dataset_name', None)

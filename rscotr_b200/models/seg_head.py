@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS, build_from_cfg
-from .bricks import ConvModule, build_positional_encoding, build_transformer_layer_sequence
+from .bricks import ConvModule, build_positional_encoding, build_transformer_layer_sequence, const_tensor
 
 
 def resize(input, size=None, mode='bilinear', align_corners=False):
@@ -72,8 +72,8 @@ class MlvlSegPixelDecoder(nn.Module):
             sy = (torch.arange(h, device=dev, dtype=torch.float32) + 0.5) * self.strides[level_idx]
             yy, xx = torch.meshgrid(sy, sx, indexing='ij')
             reference_points = torch.stack([xx.reshape(-1), yy.reshape(-1)], -1)
-            factor = reference_points.new_tensor([[w, h]]) * self.strides[level_idx]
-            reference_points = reference_points / factor
+            reference_points = reference_points / const_tensor(
+                [[float(w * self.strides[level_idx]), float(h * self.strides[level_idx])]], torch.float32, dev)
             encoder_input_list.append(feat_projected.flatten(2).permute(2, 0, 1))
             padding_mask_list.append(padding_mask_resized.flatten(1))
             level_pos_list.append(level_pos_embed.flatten(2).permute(2, 0, 1))
@@ -84,7 +84,7 @@ class MlvlSegPixelDecoder(nn.Module):
         level_positional_encodings = torch.cat(level_pos_list, dim=0)
         device = encoder_inputs.device
         shapes_py = spatial_shapes
-        spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long, device=device)
+        spatial_shapes = const_tensor(spatial_shapes, torch.long, device)
         level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
         reference_points = torch.cat(reference_points_list, dim=0)
         reference_points = reference_points[None, :, None].repeat(batch_size, 1, self.num_encoder_levels, 1)
