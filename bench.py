@@ -24,6 +24,10 @@ sys.path.insert(0, ROOT)
 CONFIG = os.path.join(ROOT, 'configs', 'multi', 'cotrain_swin-t_800.py')
 METRIC = 'co-training iters/sec (Swin-T, 3x800x800)'
 TASK_ORDER = ('resisc', 'dior', 'potsdam')
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r01_ncu_wmsa_tc_stage0_B16.json: stage-0 launch, B=16; the bench's average launch is smaller)
+NCU_TRAFFIC = {'rsc_wmsa_bwd': dict(stage0_B16_bytes=820.8e6, stage0_B16_alg_bytes=860.2e6),
+               'rsc_wmsa_fwd': dict(stage0_B16_bytes=470.0e6, stage0_B16_alg_bytes=491.5e6)}
 
 
 def parse_args():
@@ -282,27 +286,37 @@ def main():
     if rank == 0:
         sampler.start()
     ops.reset_launch_count()
+    engine.replayed_launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     per_task = {}
-    with ops.KernelTimer() as kt:
-        barrier()
-        e0.record()
-        evs = []
-        for i in range(args.steps):
-            a = torch.cuda.Event(enable_timing=True)
-            a.record()
-            out = engine.train_iter(dev_batches[i % 6])
-            b = torch.cuda.Event(enable_timing=True)
-            b.record()
-            evs.append((dev_batches[i % 6]['task'], a, b))
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        ksum = kt.summary()
-    launches = ops.launch_count()
+    barrier()
+    e0.record()
+    evs = []
+    for i in range(args.steps):
+        a = torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = engine.train_iter(dev_batches[i % 6])
+        b = torch.cuda.Event(enable_timing=True)
+        b.record()
+        evs.append((dev_batches[i % 6]['task'], a, b))
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() + engine.replayed_launches      # eager launches + launches inside graph replays
     for t, a, b in evs:
         per_task.setdefault(t, []).append(a.elapsed_time(b))
     final_loss = float(out['loss'].detach())
+    # per-kernel CUDA-event timing of the same steps (two cycles).  The step engine runs eagerly while a
+    # KernelTimer is active: events cannot be recorded per kernel inside a CUDA-graph replay.
+    with ops.KernelTimer() as kt:
+        for i in range(6):
+            engine.train_iter(dev_batches[i % 6])
+        ksum = kt.summary()
+    kscale = args.steps / 6.0                                       # normalise kernel ms to the timed region's steps
+    for d in ksum.values():
+        d['ms'] *= kscale
+        d['launches'] = int(round(d['launches'] * kscale))
+        d['bytes'] *= kscale
 
     # ---- timed region B: end to end through the public API, pinned host inputs, loss read back
     barrier()
@@ -338,7 +352,9 @@ def main():
     if top[0]:
         d = top[1]
         roofline = dict(kernel=top[0], bound='hbm', achieved=d['gbs'], peak=peak, unit='GB/s', frac=d['gbs'] / peak,
-                        traffic=None, launches=d['launches'], avg_us=1000.0 * d['ms'] / d['launches'],
+                        traffic=NCU_TRAFFIC.get(top[0]), launches=d['launches'], avg_us=1000.0 * d['ms'] / d['launches'],
+                        timed='CUDA events around every launch during an eager pass of the same steps (the timed '
+                              'region itself replays CUDA graphs)',
                         alg_bytes_per_launch=d['bytes'] / d['launches'], peak_source=peak_src,
                         share_of_step=d['ms'] / ms, own_kernels_share_of_step=mine_ms / ms)
     bs = per_gpu_batch(cfg)
@@ -355,7 +371,7 @@ def main():
                clocks=clocks,
                e2e=dict(value=e2e, unit='iters/s', h2d_bytes_per_step=hb // args.steps, d2h_bytes_per_step=db // args.steps,
                         ms_per_step=ms_e2e / args.steps),
-               gpu_launches=launches,
+               gpu_launches=launches, cuda_graphs=bool(engine.use_graphs),
                ms_per_task={k: sum(v) / len(v) for k, v in per_task.items()},
                roofline=roofline,
                kernels={k: dict(launches=d['launches'], ms=round(d['ms'], 3), gbs=round(d['gbs'], 1),

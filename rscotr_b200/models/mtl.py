@@ -188,20 +188,19 @@ class MTL(nn.Module):
         return self._finish(losses, data)
 
     def _finish(self, losses, data):
-        loss, log_vars = self._parse_losses(losses)
+        loss, keys, packed = self._parse_losses(losses)
         task = data.get('task', None)
         dataset_name = data.get('dataset_name', None)
-        log_vars = add_prefix(log_vars, '%s.%s' % (task, dataset_name))
-        if hasattr(self, 'task_weight'):
-            weight = self.task_weight[task]
-            loss = loss * weight
-            log_vars = {k: v * weight for k, v in log_vars.items()}
+        weight = self.task_weight[task] if hasattr(self, 'task_weight') else 1
+        loss = loss * weight
+        log_vars = _LazyLogVars(['%s.%s.%s' % (task, dataset_name, k) for k in keys], packed, weight)
         return dict(loss=loss, log_vars=log_vars, num_samples=len(data['img_metas']))
 
     def val_step(self, data, optimizer=None):
         losses = self(**data)
-        loss, log_vars = self._parse_losses(losses)
-        log_vars = add_prefix(log_vars, '%s.%s' % (data.get('task', None), data.get('dataset_name', None)))
+        loss, keys, packed = self._parse_losses(losses)
+        log_vars = _LazyLogVars(['%s.%s.%s' % (data.get('task', None), data.get('dataset_name', None), k)
+                                 for k in keys], packed, 1)
         return dict(loss=loss, log_vars=log_vars, num_samples=len(data['img_metas']))
 
     def forward(self, task, img, img_metas, return_loss=True, dataset_name=None, **kwargs):
@@ -231,9 +230,7 @@ class MTL(nn.Module):
                 'loss log variables are different across GPUs!\nrank %d len(log_vars): %d keys: %s' % (
                     dist.get_rank(), len(log_vars), ','.join(log_vars.keys()))
             packed = n[1:] / world
-        self._last_log_tensor = packed
-        self._last_log_keys = list(log_vars.keys())
-        return loss, _LazyLogVars(self._last_log_keys, packed)
+        return loss, list(log_vars.keys()), packed
 
     def load_task_pretrain(self):
         if self.task_pretrain is None:
@@ -258,25 +255,30 @@ class MTL(nn.Module):
 
 
 class _LazyLogVars(OrderedDict):
-    """log_vars whose float values are materialised (one D2H copy) on first read, so a
-    training loop that only logs every N iterations never syncs in between."""
+    """log_vars (name -> float, the reference's contract) whose values live in ONE packed device
+    tensor and are materialised (one D2H copy) on first read: a training loop that only logs every
+    N iterations never synchronises in between, and the step stays CUDA-graph capturable."""
 
-    def __init__(self, keys, packed):
+    def __init__(self, keys, packed, weight=1):
         super().__init__()
-        self._keys, self._packed, self._done = keys, packed, False
-        for k in keys:
+        self._keys, self._packed, self._weight, self._done = list(keys), packed, weight, False
+        for k in self._keys:
             OrderedDict.__setitem__(self, k, None)
 
     def _materialise(self):
         if not self._done:
             vals = self._packed.tolist()
             for k, v in zip(self._keys, vals):
-                OrderedDict.__setitem__(self, k, v)
+                OrderedDict.__setitem__(self, k, v * self._weight)
             self._done = True
 
     def __getitem__(self, k):
         self._materialise()
         return OrderedDict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        self._materialise()
+        return OrderedDict.get(self, k, default)
 
     def items(self):
         self._materialise()
@@ -285,3 +287,7 @@ class _LazyLogVars(OrderedDict):
     def values(self):
         self._materialise()
         return OrderedDict.values(self)
+
+    def rebind(self):
+        """a fresh, un-materialised view of the same packed tensor (CUDA-graph replays)."""
+        return _LazyLogVars(self._keys, self._packed, self._weight)

@@ -12,9 +12,12 @@ B200-first structure:
   * bf16 autocast for the GEMMs / kernels, fp32 master weights, fused AdamW.
   * inputs arrive in pinned host memory and are copied with non_blocking H2D.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
+from ... import _lib
 from ..utils.optimizer import build_optimizer
 
 _ORDER = ('backbone', 'cls_head', 'neck', 'shared_encoder', 'bbox_head', 'seg_head')
@@ -32,6 +35,19 @@ def _to_device(obj, device):
     return obj
 
 
+def _static_copy(obj, device):
+    """device copy with private storage (never aliases the caller's tensors)."""
+    if torch.is_tensor(obj):
+        return obj.to(device, non_blocking=True) if not obj.is_cuda else obj.clone()
+    if isinstance(obj, list):
+        return [_static_copy(o, device) for o in obj]
+    if isinstance(obj, tuple):
+        return tuple(_static_copy(o, device) for o in obj)
+    if isinstance(obj, dict):
+        return {k: _static_copy(v, device) for k, v in obj.items()}
+    return obj
+
+
 def h2d_bytes(obj):
     if torch.is_tensor(obj):
         return 0 if obj.is_cuda else obj.numel() * obj.element_size()
@@ -44,15 +60,27 @@ def h2d_bytes(obj):
 
 class StepEngine:
     def __init__(self, model, optimizer_cfg, grad_clip=None, device='cuda', compute_dtype=torch.bfloat16,
-                 lr_config=None):
+                 lr_config=None, use_graphs=None):
         self.device = torch.device(device)
         self.model = model.to(self.device)
         self.compute_dtype = compute_dtype
         self.grad_clip = dict(grad_clip) if grad_clip else None
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._build_flat_grads()
+        if use_graphs is None:
+            use_graphs = os.environ.get('RSC_CUDA_GRAPHS', '1') != '0'
+        self.use_graphs = bool(use_graphs) and self.device.type == 'cuda'
+        optimizer_cfg = dict(optimizer_cfg)
+        if self.use_graphs and optimizer_cfg.get('type') in ('AdamW', 'Adam'):
+            optimizer_cfg['capturable'] = True
         self.optimizer = build_optimizer(self.model, optimizer_cfg)
-        self._base_lrs = [g['lr'] for g in self.optimizer.param_groups]
+        self._base_lrs = [float(g['lr']) for g in self.optimizer.param_groups]
+        if self.use_graphs:      # lr lives on the device so a schedule step does not invalidate the graphs
+            for g in self.optimizer.param_groups:
+                g['lr'] = torch.tensor(float(g['lr']), dtype=torch.float32, device=self.device)
+        self._graphs = {}
+        self.graph_warmup = 2            # eager iterations per (task, shapes) before capture
+        self.replayed_launches = 0       # rscotr kernels executed through graph replays
         self.lr_config = dict(lr_config) if lr_config else None
         self.iter = 0
         self._task_ranges = {}
@@ -111,19 +139,19 @@ class StepEngine:
         gamma = self.lr_config.get('gamma', 0.1)
         exp = sum(self.iter >= s for s in steps)
         for g, base in zip(self.optimizer.param_groups, self._base_lrs):
-            g['lr'] = base * gamma ** exp
+            if torch.is_tensor(g['lr']):
+                if exp != getattr(self, '_lr_exp', 0):
+                    g['lr'].fill_(base * gamma ** exp)
+            else:
+                g['lr'] = base * gamma ** exp
+        self._lr_exp = exp
 
     # -- one co-training iteration ------------------------------------------
-    def train_iter(self, data_batch):
-        """model.train_step + OptimizerHook.after_train_iter.  Returns train_step's outputs."""
-        data = _to_device(data_batch, self.device)
-        self._update_lr()
-        self.flat_grad.zero_()
-        with torch.autocast('cuda', dtype=self.compute_dtype, enabled=self.compute_dtype != torch.float32):
-            outputs = self.model.train_step(data, self.optimizer)
+    def _backward_and_step(self, outputs, task):
+        """OptimizerHook.after_train_iter: backward, gradient exchange, global-norm clip, AdamW."""
         outputs['loss'].backward()
         if self.world > 1:
-            for lo, hi in self._active_ranges(data['task']):
+            for lo, hi in self._active_ranges(task):
                 seg = self.flat_grad[lo:hi]
                 dist.all_reduce(seg)
                 seg.div_(self.world)
@@ -133,5 +161,99 @@ class StepEngine:
             self.flat_grad.mul_(torch.clamp(max_norm / (total_norm + 1e-6), max=1.0))
             self.last_grad_norm = total_norm
         self.optimizer.step()
-        self.iter += 1
+
+    def _autocast(self):
+        return torch.autocast('cuda', dtype=self.compute_dtype, enabled=self.compute_dtype != torch.float32)
+
+    def _train_iter_eager(self, data):
+        self.flat_grad.zero_()
+        with self._autocast():
+            outputs = self.model.train_step(data, self.optimizer)
+        self._backward_and_step(outputs, data['task'])
         return outputs
+
+    @staticmethod
+    def _signature(batch):
+        def sig(o):
+            if torch.is_tensor(o):
+                return (tuple(o.shape), str(o.dtype))
+            if isinstance(o, (list, tuple)):
+                return tuple(sig(x) for x in o)
+            if isinstance(o, dict):
+                return tuple((k, sig(v)) for k, v in sorted(o.items()) if k in ('img_shape', 'batch_input_shape') or
+                             torch.is_tensor(v) or isinstance(v, (list, tuple, dict)))
+            return o if isinstance(o, (int, float, str, bool, type(None))) else None
+        return sig(batch)
+
+    @staticmethod
+    def _copy_in(static, batch):
+        if torch.is_tensor(static):
+            static.copy_(batch, non_blocking=True)
+        elif isinstance(static, (list, tuple)):
+            for s_, b_ in zip(static, batch):
+                StepEngine._copy_in(s_, b_)
+        elif isinstance(static, dict):
+            for k in static:
+                StepEngine._copy_in(static[k], batch[k])
+
+    def _capture(self, st, batch):
+        """Record one iteration of this (task, shapes) into CUDA graphs: graph A = zero grads +
+        forward (+ loss/backward/clip/AdamW when the task has no host phase); for det, graph B =
+        losses + backward + clip + AdamW after the host-side Hungarian matching."""
+        static = _static_copy(batch, self.device)
+        task = static['task']
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        gA, gB = torch.cuda.CUDAGraph(), None
+        with torch.cuda.graph(gA):
+            self.flat_grad.zero_()
+            with self._autocast():
+                ctx = self.model.train_step_begin(static)
+                outputs = self.model.train_step_finish(ctx) if ctx['pending'] is None else None
+            if outputs is not None:
+                self._backward_and_step(outputs, task)
+        nA = _lib.launch_count() - n0
+        nB = 0
+        if outputs is None:
+            gA.replay()                                   # real forward so the matching sees real costs
+            self.model.train_step_host(ctx)
+            n1 = _lib.launch_count()
+            gB = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gB, pool=gA.pool()):
+                with self._autocast():
+                    outputs = self.model.train_step_finish(ctx)
+                self._backward_and_step(outputs, task)
+            nB = _lib.launch_count() - n1
+            gB.replay()
+        else:
+            gA.replay()
+        st.update(gA=gA, gB=gB, ctx=ctx, static=static, outputs=outputs, launches=nA + nB)
+
+    def train_iter(self, data_batch):
+        """model.train_step + OptimizerHook.after_train_iter.  Returns train_step's outputs.
+        After `graph_warmup` eager iterations of a (task, shapes) signature the iteration is
+        replayed from CUDA graphs (launch-bound otherwise: ~4000 small kernels per det step)."""
+        self._update_lr()
+        if not self.use_graphs or _lib._timer is not None:
+            outputs = self._train_iter_eager(_to_device(data_batch, self.device))
+            self.iter += 1
+            return outputs
+        key = self._signature(data_batch)
+        st = self._graphs.setdefault(key, dict(eager=0))
+        if 'gA' not in st:
+            if st['eager'] < self.graph_warmup:
+                st['eager'] += 1
+                outputs = self._train_iter_eager(_to_device(data_batch, self.device))
+                self.iter += 1
+                return outputs
+            self._capture(st, data_batch)                 # captures AND performs this iteration
+        else:
+            self._copy_in(st['static'], data_batch)
+            st['gA'].replay()
+            if st['gB'] is not None:
+                self.model.train_step_host(st['ctx'])
+                st['gB'].replay()
+        self.replayed_launches += st['launches']
+        self.iter += 1
+        out = st['outputs']
+        return dict(loss=out['loss'], log_vars=out['log_vars'].rebind(), num_samples=out['num_samples'])

@@ -112,3 +112,26 @@ def test_step_engine_updates_and_clips():
     assert float(model.cls_head.fc.weight.grad.abs().max()) == 0.0
     assert torch.allclose(model.cls_head.fc.weight, c0 * (1 - 1e-3 * 1e-4), rtol=0, atol=1e-7)
     assert model.backbone.patch_embed.projection.weight.grad.data_ptr() >= eng.flat_grad.data_ptr()
+
+
+@pytest.mark.parametrize('task', ['cls', 'det', 'seg'])
+def test_cuda_graph_replay_matches_eager(task):
+    """the same 5 iterations through the eager step and through captured CUDA graphs (fp32)."""
+    from rscotr_b200.mtl.engine import StepEngine
+    finals = []
+    for use_graphs in (False, True):
+        model, batch = _setup(task, seed=7)
+        if task == 'det':
+            noise = oh.cdn_noise(batch['gt_labels'], num_dn=10, generator=torch.Generator().manual_seed(5))
+            model.bbox_head.dn_generator.forced_noise = {k: v.cuda() for k, v in noise.items()}
+        eng = StepEngine(model, dict(type='AdamW', lr=1e-4, weight_decay=1e-4), grad_clip=dict(max_norm=0.1, norm_type=2),
+                         device='cuda', compute_dtype=torch.float32, use_graphs=use_graphs)
+        losses = [float(eng.train_iter(batch)['loss'].detach()) for _ in range(5)]
+        if use_graphs:
+            assert any('gA' in st for st in eng._graphs.values()) and eng.replayed_launches > 0
+        finals.append((losses, {n: p.detach().clone() for n, p in model.named_parameters()}))
+    (l0, p0), (l1, p1) = finals
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (l0, l1)
+    for n in p0:
+        assert rel(p1[n], p0[n]) < 1e-3, n
