@@ -277,7 +277,9 @@ def main():
             torch.cuda.synchronize()
 
     # ---- warm-up (also fixes the per-task all-reduce ranges, cuBLAS heuristics, allocator)
-    for i in range(max(args.warmup, 3)):
+    # (with CUDA graphs every task needs 2 eager iterations + the capturing one before the timed region)
+    n_warm = max(args.warmup, 9 if engine.use_graphs else 3)
+    for i in range(n_warm):
         engine.train_iter(dev_batches[i % 6])
     barrier()
 
@@ -358,7 +360,7 @@ def main():
                         alg_bytes_per_launch=d['bytes'] / d['launches'], peak_source=peak_src,
                         share_of_step=d['ms'] / ms, own_kernels_share_of_step=mine_ms / ms)
     bs = per_gpu_batch(cfg)
-    out = dict(metric=METRIC, value=value, unit='iters/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+    out = dict(metric=METRIC, value=value, unit='iters/s', n_gpus=world, steps=args.steps, warmup=n_warm,
                ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                dtype=args.dtype if args.dtype != 'fp32' else 'f32', data='synthetic',
                config=dict(workload='Swin-T MTL co-training (cls+seg+det round-robin) 3x800x800 (BASELINE configs[%d])'
@@ -371,7 +373,7 @@ def main():
                clocks=clocks,
                e2e=dict(value=e2e, unit='iters/s', h2d_bytes_per_step=hb // args.steps, d2h_bytes_per_step=db // args.steps,
                         ms_per_step=ms_e2e / args.steps),
-               gpu_launches=launches, cuda_graphs=bool(engine.use_graphs),
+               gpu_launches=launches, cuda_graphs=bool(engine.use_graphs), cuda_graph_capture_failures=engine.graph_failures,
                ms_per_task={k: sum(v) / len(v) for k, v in per_task.items()},
                roofline=roofline,
                kernels={k: dict(launches=d['launches'], ms=round(d['ms'], 3), gbs=round(d['gbs'], 1),

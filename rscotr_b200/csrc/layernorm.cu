@@ -8,6 +8,231 @@
 
 namespace rsc {
 
+// Sub-warp mapping: L lanes share one row (L = C / (8*EV), a power of two), a warp handles
+// 32/L rows at a time, every lane owns EV vectors of 8 consecutive channels, interleaved by L so
+// that one load instruction of the L lanes covers 16*L (bf16) contiguous bytes of the row.
+//   C = 96 -> L=4, EV=3 | 192 -> 8,3 | 384 -> 16,3 | 768 -> 32,3 | 256 -> 8,4 | 128 -> 4,4 | 512 -> 16,4 | 1024 -> 32,4
+constexpr int LN_THREADS = 128;
+
+template <typename T>
+__device__ __forceinline__ void load8(const T *p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float *p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16 *p, float (&v)[8]) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[i]));
+    v[2 * i] = f.x, v[2 * i + 1] = f.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T *p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float *p, const float (&v)[8]) {
+  reinterpret_cast<float4 *>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4 *>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16 *p, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t *>(&h);
+  }
+  *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int L>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename TI, typename TO, int EV, int L>
+__global__ void __launch_bounds__(LN_THREADS)
+    ln_fwd_kernel(const TI *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+                  TO *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd, int64_t rows, float eps) {
+  constexpr int C = 8 * EV * L, RPW = 32 / L;
+  const int lane = threadIdx.x & 31, sub = lane % L, rw = lane / L;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float ga[EV][8], be[EV][8];
+#pragma unroll
+  for (int k = 0; k < EV; ++k) {
+    load8<float>(gamma + (sub + k * L) * 8, ga[k]);
+    load8<float>(beta + (sub + k * L) * 8, be[k]);
+  }
+  for (int64_t r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
+    const int64_t r = r0 + rw;
+    const bool ok = r < rows;
+    float v[EV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < EV; ++k) {
+      if (ok) load8<TI>(x + r * C + (sub + k * L) * 8, v[k]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (!ok) v[k][e] = 0.f;
+        s += v[k][e];
+      }
+    }
+    const float mu = group_sum<L>(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < EV; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[k][e] - mu;
+        q = fmaf(d, d, q);
+      }
+    const float rs = rsqrtf(group_sum<L>(q) * (1.0f / C) + eps);
+    if (ok) {
+      if (sub == 0) {
+        mean[r] = mu;
+        rstd[r] = rs;
+      }
+#pragma unroll
+      for (int k = 0; k < EV; ++k) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf((v[k][e] - mu) * rs, ga[k][e], be[k][e]);
+        store8<TO>(y + r * C + (sub + k * L) * 8, o);
+      }
+    }
+  }
+}
+
+template <typename TI, typename TO, int EV, int L>
+__global__ void __launch_bounds__(LN_THREADS)
+    ln_bwd_kernel(const TI *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ mean,
+                  const float *__restrict__ rstd, const TO *__restrict__ dy, TI *__restrict__ dx,
+                  float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t rows) {
+  constexpr int C = 8 * EV * L, RPW = 32 / L;
+  __shared__ float red[2 * C];   // per-CTA partial d(gamma) | d(beta)
+  const int lane = threadIdx.x & 31, sub = lane % L, rw = lane / L;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float ga[EV][8], dg[EV][8], db[EV][8];
+#pragma unroll
+  for (int k = 0; k < EV; ++k) {
+    load8<float>(gamma + (sub + k * L) * 8, ga[k]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dg[k][e] = 0.f, db[k][e] = 0.f;
+  }
+  for (int64_t r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
+    const int64_t r = r0 + rw;
+    const bool ok = r < rows;
+    const float mu = ok ? mean[r] : 0.f, rs = ok ? rstd[r] : 0.f;
+    float xh[EV][8], g[EV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < EV; ++k) {
+      float d[8];
+      if (ok) {
+        load8<TI>(x + r * C + (sub + k * L) * 8, xh[k]);
+        load8<TO>(dy + r * C + (sub + k * L) * 8, d);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (!ok) xh[k][e] = 0.f, d[e] = 0.f;
+        xh[k][e] = (xh[k][e] - mu) * rs;
+        dg[k][e] = fmaf(d[e], xh[k][e], dg[k][e]);
+        db[k][e] += d[e];
+        g[k][e] = d[e] * ga[k][e];
+        s1 += g[k][e];
+        s2 = fmaf(g[k][e], xh[k][e], s2);
+      }
+    }
+    s1 = group_sum<L>(s1) * (1.0f / C);
+    s2 = group_sum<L>(s2) * (1.0f / C);
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < EV; ++k) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rs * (g[k][e] - s1 - xh[k][e] * s2);
+        store8<TI>(dx + r * C + (sub + k * L) * 8, o);
+      }
+    }
+  }
+  // lanes with equal `sub` (different rows of the warp) hold partials of the same channels
+#pragma unroll
+  for (int k = 0; k < EV; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a = dg[k][e], b = db[k][e];
+#pragma unroll
+      for (int o = 16; o >= L; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (rw == 0) {
+        atomicAdd(red + (sub + k * L) * 8 + e, a);
+        atomicAdd(red + C + (sub + k * L) * 8 + e, b);
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[C + i]);
+  }
+}
+
+// (EV, L) for a supported C, or false -> generic warp-per-row kernels below
+static bool ln_shape(int C, int &ev, int &l) {
+  for (int e = 3; e <= 4; ++e)
+    for (int ll = 4; ll <= 32; ll *= 2)
+      if (C == 8 * e * ll) {
+        ev = e, l = ll;
+        return true;
+      }
+  return false;
+}
+
+template <typename TI, typename TO>
+static bool ln_fast_fwd(int C, int grid, cudaStream_t st, const void *x, const float *gamma, const float *beta, void *y,
+                        float *mean, float *rstd, int64_t rows, float eps) {
+  int ev, l;
+  if (!ln_shape(C, ev, l)) return false;
+#define LNF(E, LL)                                                                                         \
+  if (ev == E && l == LL) {                                                                                \
+    ln_fwd_kernel<TI, TO, E, LL><<<grid, LN_THREADS, 0, st>>>((const TI *)x, gamma, beta, (TO *)y, mean, rstd, rows, eps); \
+    return true;                                                                                           \
+  }
+  LNF(3, 4) LNF(3, 8) LNF(3, 16) LNF(3, 32) LNF(4, 4) LNF(4, 8) LNF(4, 16) LNF(4, 32)
+#undef LNF
+  return false;
+}
+
+template <typename TI, typename TO>
+static bool ln_fast_bwd(int C, int grid, cudaStream_t st, const void *x, const float *gamma, const float *mean,
+                        const float *rstd, const void *dy, void *dx, float *dgamma, float *dbeta, int64_t rows) {
+  int ev, l;
+  if (!ln_shape(C, ev, l)) return false;
+#define LNB(E, LL)                                                                                          \
+  if (ev == E && l == LL) {                                                                                 \
+    ln_bwd_kernel<TI, TO, E, LL><<<grid, LN_THREADS, 0, st>>>((const TI *)x, gamma, mean, rstd, (const TO *)dy, \
+                                                               (TI *)dx, dgamma, dbeta, rows);              \
+    return true;                                                                                            \
+  }
+  LNB(3, 4) LNB(3, 8) LNB(3, 16) LNB(3, 32) LNB(4, 4) LNB(4, 8) LNB(4, 16) LNB(4, 32)
+#undef LNB
+  return false;
+}
+
+// ---------------------------------------------------------------------------
+// generic path (any C % 4 == 0, C <= 1024): one warp per row
+// ---------------------------------------------------------------------------
 constexpr int LN_MAX_ITER = 8;   // C <= 1024
 constexpr int LN_WARPS = 8;
 
@@ -193,6 +418,23 @@ extern "C" int rsc_layernorm_fwd(const void *x, const float *gamma, const float 
                                  void *stream) {
   if (int e = ln_check("rsc_layernorm_fwd", rows, C, in_dtype, out_dtype)) return e;
   RSC_CHECK_ARG(x && gamma && beta && y && mean && rstd, "rsc_layernorm_fwd: null pointer");
+  {
+    int ev = 0, l = 32;
+    if (ln_shape(C, ev, l)) {
+      int64_t fb = (rows + (LN_THREADS / 32) * (32 / l) - 1) / ((LN_THREADS / 32) * (32 / l));
+      int fgrid = (int)(fb < kNumSMs * 12 ? fb : kNumSMs * 12);
+      bool done = false;
+      cudaStream_t st = (cudaStream_t)stream;
+      if (in_dtype == RSC_F32 && out_dtype == RSC_F32) done = ln_fast_fwd<float, float>(C, fgrid, st, x, gamma, beta, y, mean, rstd, rows, eps);
+      else if (in_dtype == RSC_F32) done = ln_fast_fwd<float, __nv_bfloat16>(C, fgrid, st, x, gamma, beta, y, mean, rstd, rows, eps);
+      else if (out_dtype == RSC_F32) done = ln_fast_fwd<__nv_bfloat16, float>(C, fgrid, st, x, gamma, beta, y, mean, rstd, rows, eps);
+      else done = ln_fast_fwd<__nv_bfloat16, __nv_bfloat16>(C, fgrid, st, x, gamma, beta, y, mean, rstd, rows, eps);
+      if (done) {
+        RSC_CHECK_LAUNCH("rsc_layernorm_fwd");
+        return RSC_OK;
+      }
+    }
+  }
   int64_t blocks = (rows + LN_WARPS - 1) / LN_WARPS;
   int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
   LN_DISPATCH(in_dtype, out_dtype, ln_fwd_launch, (C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, beta, y, mean,
@@ -206,6 +448,23 @@ extern "C" int rsc_layernorm_bwd(const void *x, const float *gamma, const float 
                                  int in_dtype, int out_dtype, void *stream) {
   if (int e = ln_check("rsc_layernorm_bwd", rows, C, in_dtype, out_dtype)) return e;
   RSC_CHECK_ARG(x && gamma && mean && rstd && dy && dx && dgamma && dbeta, "rsc_layernorm_bwd: null pointer");
+  {
+    int ev = 0, l = 32;
+    if (ln_shape(C, ev, l)) {
+      int64_t fb = (rows + (LN_THREADS / 32) * (32 / l) - 1) / ((LN_THREADS / 32) * (32 / l));
+      int fgrid = (int)(fb < kNumSMs * 6 ? fb : kNumSMs * 6);
+      bool done = false;
+      cudaStream_t st = (cudaStream_t)stream;
+      if (in_dtype == RSC_F32 && out_dtype == RSC_F32) done = ln_fast_bwd<float, float>(C, fgrid, st, x, gamma, mean, rstd, dy, dx, dgamma, dbeta, rows);
+      else if (in_dtype == RSC_F32) done = ln_fast_bwd<float, __nv_bfloat16>(C, fgrid, st, x, gamma, mean, rstd, dy, dx, dgamma, dbeta, rows);
+      else if (out_dtype == RSC_F32) done = ln_fast_bwd<__nv_bfloat16, float>(C, fgrid, st, x, gamma, mean, rstd, dy, dx, dgamma, dbeta, rows);
+      else done = ln_fast_bwd<__nv_bfloat16, __nv_bfloat16>(C, fgrid, st, x, gamma, mean, rstd, dy, dx, dgamma, dbeta, rows);
+      if (done) {
+        RSC_CHECK_LAUNCH("rsc_layernorm_bwd");
+        return RSC_OK;
+      }
+    }
+  }
   int64_t blocks = (rows + LN_WARPS - 1) / LN_WARPS;
   int grid = (int)(blocks < kNumSMs * 4 ? blocks : kNumSMs * 4);
   LN_DISPATCH(in_dtype, out_dtype, ln_bwd_launch, (C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, mean, rstd, dy,

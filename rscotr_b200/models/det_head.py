@@ -767,7 +767,7 @@ class DINOHead(nn.Module):
             t = torch.arange(n, device=dev).unsqueeze(0).repeat(num_groups, 1)
             pos_inds = ((torch.arange(num_groups, device=dev) * single_pad).unsqueeze(1) + t).flatten()
             labels[b, pos_inds] = gt_labels_list[b][t.flatten()]
-            bbox_weights[b, pos_inds] = 1.0
+            bbox_weights[b].index_fill_(0, pos_inds, 1.0)       # (scalar index_put would stage a host tensor)
             img_h, img_w, _ = img_metas[b]['img_shape']
             factor = const_tensor([[img_w, img_h, img_w, img_h]], dn_bbox_pred.dtype, dn_bbox_pred.device)
             bbox_targets[b, pos_inds] = bbox_xyxy_to_cxcywh(gt_bboxes_list[b] / factor).repeat([num_groups, 1])

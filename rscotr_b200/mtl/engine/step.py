@@ -81,6 +81,7 @@ class StepEngine:
         self._graphs = {}
         self.graph_warmup = 2            # eager iterations per (task, shapes) before capture
         self.replayed_launches = 0       # rscotr kernels executed through graph replays
+        self.graph_failures = 0
         self.lr_config = dict(lr_config) if lr_config else None
         self.iter = 0
         self._task_ranges = {}
@@ -246,7 +247,21 @@ class StepEngine:
                 outputs = self._train_iter_eager(_to_device(data_batch, self.device))
                 self.iter += 1
                 return outputs
-            self._capture(st, data_batch)                 # captures AND performs this iteration
+            try:
+                self._capture(st, data_batch)             # captures AND performs this iteration
+            except Exception as e:                        # keep training eagerly, but say so loudly
+                import sys
+                import traceback
+                traceback.print_exc()
+                print('[rscotr_b200] CUDA-graph capture failed for task %r (%s: %s); this signature runs eagerly'
+                      % (data_batch.get('task'), type(e).__name__, e), file=sys.stderr)
+                st.clear()
+                st.update(eager=-(1 << 60))               # never try again
+                self.graph_failures += 1
+                torch.cuda.synchronize()
+                outputs = self._train_iter_eager(_to_device(data_batch, self.device))
+                self.iter += 1
+                return outputs
         else:
             self._copy_in(st['static'], data_batch)
             st['gA'].replay()
