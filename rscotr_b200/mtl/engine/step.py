@@ -124,8 +124,8 @@ class StepEngine:
             for top, (lo, hi, f) in sorted(tops.items(), key=lambda kv: kv[1][0]):
                 if not f:
                     continue
-                if ranges and ranges[-1][1] == lo:
-                    ranges[-1] = (ranges[-1][0], hi)
+                if ranges and lo - ranges[-1][1] <= (1 << 18):     # bridge gaps <= 1 MB (e.g. the 35 k-param cls_head):
+                    ranges[-1] = (ranges[-1][0], hi)                # reducing a few zeros beats one more collective
                 else:
                     ranges.append((lo, hi))
             self._task_ranges[task] = ranges
@@ -181,7 +181,7 @@ class StepEngine:
             if isinstance(o, (list, tuple)):
                 return tuple(sig(x) for x in o)
             if isinstance(o, dict):
-                return tuple((k, sig(v)) for k, v in sorted(o.items()) if k in ('img_shape', 'batch_input_shape') or
+                return tuple((k, sig(v)) for k, v in sorted(o.items()) if k == 'img_shape' or
                              torch.is_tensor(v) or isinstance(v, (list, tuple, dict)))
             return o if isinstance(o, (int, float, str, bool, type(None))) else None
         return sig(batch)
@@ -195,7 +195,8 @@ class StepEngine:
                 StepEngine._copy_in(s_, b_)
         elif isinstance(static, dict):
             for k in static:
-                StepEngine._copy_in(static[k], batch[k])
+                if k in batch:                # (the model may have annotated its static img_metas)
+                    StepEngine._copy_in(static[k], batch[k])
 
     def _capture(self, st, batch):
         """Record one iteration of this (task, shapes) into CUDA graphs: graph A = zero grads +

@@ -1,0 +1,74 @@
+"""world_size-2 (gloo, CPU) test of the data-parallel logic of the step engine: flat-range
+gradient all-reduce per task, packed loss-factor / log-var reductions, identical replicas.
+The CUDA ops are substituted by the oracle shim (tests/cpu_ops_shim.py); NCCL replaces gloo on
+the GPU box, the code path is the same."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import rscotr_b200.models  # noqa: F401
+    from rscotr_b200.config import MODELS
+    from rscotr_b200.mtl.data import build_datasets
+    from rscotr_b200.mtl.engine import StepEngine
+    from tests.cpu_ops_shim import cpu_ops
+    from tests.test_host_model import small_cfg
+    torch.manual_seed(0)                                   # same weights on every rank
+    model = MODELS.build(small_cfg().model)
+    model.init_weights()
+    model.train()
+    eng = StepEngine(model, dict(type='AdamW', lr=1e-3, weight_decay=1e-4), grad_clip=dict(max_norm=0.1, norm_type=2),
+                     device='cpu', compute_dtype=torch.float32, use_graphs=False)
+    assert eng.world == world
+    res = {}
+    with cpu_ops():
+        for task in ('cls', 'det', 'seg'):
+            ds = build_datasets({'x': dict(task=task)}, synthetic=dict(img_size=(64, 64), det=dict(num_boxes=2 + rank)))['x']
+            batch = ds.make_batch(2, torch.Generator().manual_seed(100 + rank), pin=False)     # different shard per rank
+            batch.update(task=task, dataset_name='x')
+            # local (un-reduced) gradient of this rank, for the check below
+            model.zero_grad(set_to_none=False)
+            local = model.train_step(dict(batch), None)
+            local['loss'].backward()
+            g_local = eng.flat_grad.clone()
+            out = eng.train_iter(batch)
+            res[task] = dict(g_local=g_local, loss=float(out['loss'].detach()), log=dict(out['log_vars'].items()),
+                             ranges=list(eng._task_ranges[task]))
+    res['params'] = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    torch.save(res, os.path.join(out_dir, 'rank%d.pt' % rank))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_data_parallel_step(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / 'rank0.pt')
+    r1 = torch.load(tmp_path / 'rank1.pt')
+    # replicas stay identical
+    assert torch.equal(r0['params'], r1['params'])
+    for task in ('cls', 'det', 'seg'):
+        # the logged values are the cross-rank means (packed all-reduce), identical on both ranks
+        assert r0[task]['log'].keys() == r1[task]['log'].keys()
+        for k in r0[task]['log']:
+            assert abs(r0[task]['log'][k] - r1[task]['log'][k]) < 1e-6, (task, k)
+        assert r0[task]['ranges'] == r1[task]['ranges'] and len(r0[task]['ranges']) >= 1
+    # the cls task only touches backbone + cls_head: one contiguous range starting at 0
+    assert r0['cls']['ranges'][0][0] == 0 and len(r0['cls']['ranges']) == 1
+    assert len(r0['seg']['ranges']) == 2          # backbone..shared_encoder | seg_head (bbox_head skipped)
