@@ -170,17 +170,25 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  // per-warp partial sums -> global (4C addresses, one atomic per warp each)
+  // per-lane partial sums -> per-CTA shared table -> ONE global atomic per channel per CTA
+  extern __shared__ float red[];   // [2][4C]
+  for (int i2 = threadIdx.x; i2 < 8 * g.C; i2 += blockDim.x) red[i2] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int it = 0; it < ITER; ++it) {
     const int c = it * 128 + lane * 4;
     if (c < g.C) {
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        atomicAdd(dgamma + c * 4 + e, dg[it][e]);
-        atomicAdd(dbeta + c * 4 + e, db[it][e]);
+        atomicAdd(red + c * 4 + e, dg[it][e]);
+        atomicAdd(red + 4 * g.C + c * 4 + e, db[it][e]);
       }
     }
+  }
+  __syncthreads();
+  for (int i2 = threadIdx.x; i2 < 4 * g.C; i2 += blockDim.x) {
+    atomicAdd(dgamma + i2, red[i2]);
+    atomicAdd(dbeta + i2, red[4 * g.C + i2]);
   }
 }
 
@@ -376,7 +384,8 @@ static void pm_bwd_launch(int iters, int grid, cudaStream_t st, const void *x, c
 #define PM_CASE(N)                                                                                                 \
   case N:                                                                                                          \
     patch_merge_ln_bwd_kernel<T, N>                                                                                \
-        <<<grid, 256, 0, st>>>((const T *)x, gamma, mean, rstd, (const T *)dy, (T *)dx, dgamma, dbeta, g);         \
+        <<<grid, 256, 8 * g.C * sizeof(float), st>>>((const T *)x, gamma, mean, rstd, (const T *)dy, (T *)dx,      \
+                                                     dgamma, dbeta, g);                                            \
     break;
   switch (iters) { PM_CASE(1) PM_CASE(2) PM_CASE(3) PM_CASE(4) }
 #undef PM_CASE

@@ -124,7 +124,9 @@ def test_cuda_graph_replay_matches_eager(task):
         if task == 'det':
             noise = oh.cdn_noise(batch['gt_labels'], num_dn=10, generator=torch.Generator().manual_seed(5))
             model.bbox_head.dn_generator.forced_noise = {k: v.cuda() for k, v in noise.items()}
-        eng = StepEngine(model, dict(type='AdamW', lr=1e-4, weight_decay=1e-4), grad_clip=dict(max_norm=0.1, norm_type=2),
+        # SGD: the update is linear in the gradient, so fp32 atomics noise is not amplified the way
+        # Adam's g/sqrt(v) amplifies it for near-zero gradients
+        eng = StepEngine(model, dict(type='SGD', lr=1e-2, momentum=0.9), grad_clip=dict(max_norm=0.1, norm_type=2),
                          device='cuda', compute_dtype=torch.float32, use_graphs=use_graphs)
         losses = [float(eng.train_iter(batch)['loss'].detach()) for _ in range(5)]
         if use_graphs:
@@ -134,4 +136,4 @@ def test_cuda_graph_replay_matches_eager(task):
     for a, b in zip(l0, l1):
         assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (l0, l1)
     for n in p0:
-        assert rel(p1[n], p0[n]) < 1e-3, n
+        assert rel(p1[n], p0[n]) < 1e-4, n

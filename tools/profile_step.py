@@ -14,6 +14,7 @@ from rscotr_b200.mtl.engine.step import _to_device  # noqa: E402
 
 def main():
     dev = torch.device('cuda', 0)
+    os.environ['RSC_CUDA_GRAPHS'] = '0'      # eager: kernel names are what we are after
     cfg, model, engine, loader = bench.build(bench.CONFIG, 'bf16', dev)
     it = iter(loader)
     batches = [_to_device(next(it), dev) for _ in range(3)]
@@ -26,7 +27,7 @@ def main():
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
             engine.train_iter(b)
             torch.cuda.synchronize()
-        txt = prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=70)
+        txt = prof.key_averages().table(sort_by='self_cuda_time_total', row_limit=40, max_name_column_width=90)
         open('gpurun_out/profile_%s.txt' % b['task'], 'w').write(txt)
         print('=====', b['task'])
         print(txt[-6000:])
