@@ -177,6 +177,21 @@ int rsc_sigmoid_focal_loss_fwd(const void *input, const int64_t *target, float *
 int rsc_sigmoid_focal_loss_bwd(const void *input, const int64_t *target, float *grad_input, int N, int C,
                                float gamma, float alpha, int dtype, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Flat fused AdamW (+ gradient-clip scale).  Replaces mmcv OptimizerHook's
+ * clip_grad_norm_ scaling + torch.optim.AdamW.step over one contiguous fp32 range
+ * (optimizer built by mtl/utils/optimizer.py:25-55).
+ * lr / step / clip_coef are DEVICE scalars (float); step holds the 1-based step
+ * count t; clip_coef may be NULL (= 1).  torch.optim.AdamW arithmetic.
+ * ---------------------------------------------------------------------- */
+int rsc_adamw_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, const float *lr,
+                   float lr_mult, float beta1, float beta2, float eps, float weight_decay, const float *step,
+                   const float *clip_coef, void *stream);
+
+/* y[c] += sum_r x[r][c]  (rows,C) -> (C) float, ACCUMULATED: the bias gradient of a Linear
+ * layer (replaces ATen's sum(0) reduce in AddmmBackward / nn.Linear backward). */
+int rsc_colsum(const void *x, float *y, int64_t rows, int C, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,8 @@ _SIGS = {
     'rsc_patch_merge_ln_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'rsc_layernorm_fwd': [_P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _F, _I, _I, _P],
     'rsc_layernorm_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
+    'rsc_adamw_step': [_P, _P, _P, _P, ctypes.c_int64, _P, _F, _F, _F, _F, _F, _P, _P, _P],
+    'rsc_colsum': [_P, _P, ctypes.c_int64, _I, _I, _P],
     'rsc_msda_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'rsc_msda_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'rsc_gap_fwd': [_P, _P, _I, _I, _I, _I, _I, _P],

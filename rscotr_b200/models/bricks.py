@@ -45,6 +45,14 @@ def build_activation(cfg):
     raise KeyError('unsupported activation %s' % t)
 
 
+class Linear(nn.Linear):
+    """nn.Linear parameters / state-dict keys; forward through ops.linear (library GEMMs, bias
+    gradient on rsc_colsum)."""
+
+    def forward(self, x):
+        return ops.linear(x, self.weight, self.bias)
+
+
 class LayerNorm(nn.LayerNorm):
     """nn.LayerNorm parameters / state-dict keys, forward on rsc_layernorm_{fwd,bwd}: one pass,
     fp32 statistics, output already in the compute dtype of the GEMM that follows."""
@@ -112,10 +120,10 @@ class FFN(nn.Module):
         layers = []
         in_ch = embed_dims
         for _ in range(num_fcs - 1):
-            layers.append(nn.Sequential(nn.Linear(in_ch, feedforward_channels), build_activation(act_cfg),
+            layers.append(nn.Sequential(Linear(in_ch, feedforward_channels), build_activation(act_cfg),
                                         nn.Dropout(ffn_drop)))
             in_ch = feedforward_channels
-        layers.append(nn.Linear(feedforward_channels, embed_dims))
+        layers.append(Linear(feedforward_channels, embed_dims))
         layers.append(nn.Dropout(ffn_drop))
         self.layers = nn.Sequential(*layers)
         self.dropout_layer = build_dropout(dropout_layer)
@@ -186,10 +194,10 @@ class MultiScaleDeformableAttention(nn.Module):
         self.num_levels = num_levels
         self.num_heads = num_heads
         self.num_points = num_points
-        self.sampling_offsets = nn.Linear(embed_dims, num_heads * num_levels * num_points * 2)
-        self.attention_weights = nn.Linear(embed_dims, num_heads * num_levels * num_points)
-        self.value_proj = nn.Linear(embed_dims, embed_dims)
-        self.output_proj = nn.Linear(embed_dims, embed_dims)
+        self.sampling_offsets = Linear(embed_dims, num_heads * num_levels * num_points * 2)
+        self.attention_weights = Linear(embed_dims, num_heads * num_levels * num_points)
+        self.value_proj = Linear(embed_dims, embed_dims)
+        self.output_proj = Linear(embed_dims, embed_dims)
         self.init_weights()
 
     def init_weights(self):

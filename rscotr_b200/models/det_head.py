@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS, build_from_cfg
-from .bricks import (LayerNorm, TransformerLayerSequence, const_tensor, MultiScaleDeformableAttention, build_positional_encoding,
+from .bricks import (LayerNorm, Linear, TransformerLayerSequence, const_tensor, MultiScaleDeformableAttention, build_positional_encoding,
                      build_transformer_layer_sequence, inverse_sigmoid)
 
 
@@ -64,8 +64,8 @@ def build_MLP(input_dim, hidden_dim, output_dim, num_layers):
     h = [hidden_dim] * (num_layers - 1)
     layers = []
     for n, k in zip([input_dim] + h[:-1], h):
-        layers.extend((nn.Linear(n, k), nn.ReLU()))
-    layers.append(nn.Linear(hidden_dim, output_dim))
+        layers.extend((Linear(n, k), nn.ReLU()))
+    layers.append(Linear(hidden_dim, output_dim))
     return nn.Sequential(*layers)
 
 
@@ -139,7 +139,7 @@ class DinoTransformer(nn.Module):
         self.two_stage_num_proposals = two_stage_num_proposals
         self.embed_dims = self.decoder.embed_dims
         self.level_embeds = nn.Parameter(torch.Tensor(self.num_feature_levels, self.embed_dims))
-        self.enc_output = nn.Linear(self.embed_dims, self.embed_dims)
+        self.enc_output = Linear(self.embed_dims, self.embed_dims)
         self.enc_output_norm = LayerNorm(self.embed_dims)
         self.query_embed = nn.Embedding(self.two_stage_num_proposals, self.embed_dims)
 
@@ -520,12 +520,12 @@ class DINOHead(nn.Module):
         self.init_weights()
 
     def _init_layers(self):
-        fc_cls = nn.Linear(self.embed_dims, self.cls_out_channels)
+        fc_cls = Linear(self.embed_dims, self.cls_out_channels)
         reg_branch = []
         for _ in range(self.num_reg_fcs):
-            reg_branch.append(nn.Linear(self.embed_dims, self.embed_dims))
+            reg_branch.append(Linear(self.embed_dims, self.embed_dims))
             reg_branch.append(nn.ReLU())
-        reg_branch.append(nn.Linear(self.embed_dims, 4))
+        reg_branch.append(Linear(self.embed_dims, 4))
         reg_branch = nn.Sequential(*reg_branch)
         num_pred = self.transformer.decoder.num_layers + 1
         self.cls_branches = nn.ModuleList([copy.deepcopy(fc_cls) for _ in range(num_pred)])

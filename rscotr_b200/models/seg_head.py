@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS, build_from_cfg
-from .bricks import ConvModule, build_positional_encoding, build_transformer_layer_sequence, const_tensor
+from .bricks import Linear, ConvModule, build_positional_encoding, build_transformer_layer_sequence, const_tensor
 
 
 def resize(input, size=None, mode='bilinear', align_corners=False):
@@ -136,10 +136,10 @@ class Mask2FormerHead(nn.Module):
         self.query_feat = nn.Embedding(self.num_queries, feat_channels)
         self.level_embed = nn.Embedding(self.num_transformer_feat_level, feat_channels)
         if self.scheme == 1:
-            self.cls_embed = nn.Linear(feat_channels, self.num_classes + 1)
-        self.mask_embed = nn.Sequential(nn.Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
-                                        nn.Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
-                                        nn.Linear(feat_channels, out_channels))
+            self.cls_embed = Linear(feat_channels, self.num_classes + 1)
+        self.mask_embed = nn.Sequential(Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
+                                        Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
+                                        Linear(feat_channels, out_channels))
         assert loss_decode['type'] == 'CrossEntropyLoss' and not loss_decode.get('use_sigmoid', False)
         self.loss_weight = loss_decode.get('loss_weight', 1.0)
         self.init_weights()

@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS
-from .bricks import FFN, DropPath, LayerNorm
+from .bricks import FFN, DropPath, LayerNorm, Linear
 
 
 class WindowMSA(nn.Module):
@@ -36,8 +36,8 @@ class WindowMSA(nn.Module):
         rel_index_coords = self.double_step_seq(2 * Ww - 1, Wh, 1, Ww)
         rel_position_index = rel_index_coords + rel_index_coords.T
         self.register_buffer('relative_position_index', rel_position_index.flip(1).contiguous())
-        self.qkv = nn.Linear(embed_dims, embed_dims * 3, bias=qkv_bias)
-        self.proj = nn.Linear(embed_dims, embed_dims)
+        self.qkv = Linear(embed_dims, embed_dims * 3, bias=qkv_bias)
+        self.proj = Linear(embed_dims, embed_dims)
         self.proj_drop = nn.Dropout(proj_drop_rate)
         nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
 
@@ -102,7 +102,7 @@ class PatchMerging(nn.Module):
         assert stride == 2
         self.in_channels, self.out_channels = in_channels, out_channels
         self.norm = nn.LayerNorm(4 * in_channels)
-        self.reduction = nn.Linear(4 * in_channels, out_channels, bias=False)
+        self.reduction = Linear(4 * in_channels, out_channels, bias=False)
 
     def forward(self, x, input_size):
         H, W = input_size

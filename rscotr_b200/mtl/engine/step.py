@@ -71,13 +71,14 @@ class StepEngine:
             use_graphs = os.environ.get('RSC_CUDA_GRAPHS', '1') != '0'
         self.use_graphs = bool(use_graphs) and self.device.type == 'cuda'
         optimizer_cfg = dict(optimizer_cfg)
-        if self.use_graphs and optimizer_cfg.get('type') in ('AdamW', 'Adam'):
-            optimizer_cfg['capturable'] = True
-        self.optimizer = build_optimizer(self.model, optimizer_cfg)
+        if optimizer_cfg.get('type') == 'AdamW' and self.device.type == 'cuda' and not optimizer_cfg.get('amsgrad'):
+            from .flat_adamw import FlatAdamW
+            self.optimizer = FlatAdamW(self, optimizer_cfg)      # one fused kernel per (lr, wd) run of the flat buffer
+        else:
+            if self.use_graphs and optimizer_cfg.get('type') in ('Adam', 'AdamW'):
+                optimizer_cfg['capturable'] = True
+            self.optimizer = build_optimizer(self.model, optimizer_cfg)
         self._base_lrs = [float(g['lr']) for g in self.optimizer.param_groups]
-        if self.use_graphs:      # lr lives on the device so a schedule step does not invalidate the graphs
-            for g in self.optimizer.param_groups:
-                g['lr'] = torch.tensor(float(g['lr']), dtype=torch.float32, device=self.device)
         self._graphs = {}
         self.graph_warmup = 2            # eager iterations per (task, shapes) before capture
         self.replayed_launches = 0       # rscotr kernels executed through graph replays
@@ -87,25 +88,50 @@ class StepEngine:
         self._task_ranges = {}
         self.last_grad_norm = None
 
-    # -- flat gradient buffer --------------------------------------------
+    # -- flat parameter / gradient buffers ---------------------------------
     def _build_flat_grads(self):
+        """Parameters become views into ONE flat fp32 buffer (and their gradients land in a second
+        one with the same layout), ordered by _ORDER; every tensor starts on a 16-byte boundary."""
         named = list(self.model.named_parameters())
         def rank(n):
             top = n.split('.')[0]
             return _ORDER.index(top) if top in _ORDER else len(_ORDER)
-        order = sorted(range(len(named)), key=lambda i: (rank(named[i][0]), i))
-        total = sum(named[i][1].numel() for i in order if named[i][1].requires_grad)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        order = [i for i in sorted(range(len(named)), key=lambda i: (rank(named[i][0]), i)) if named[i][1].requires_grad]
         self._spans = []          # (name, start, end)
         off = 0
         for i in order:
             n, p = named[i]
-            if not p.requires_grad:
-                continue
             assert p.dtype == torch.float32, 'master weights are fp32'
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
             self._spans.append((n, off, off + p.numel()))
-            off += p.numel()
+            off = (off + p.numel() + 3) // 4 * 4
+        total = off
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self._params, self._grad_views = [], []
+        for (n, s0, e0), i in zip(self._spans, order):
+            p = named[i][1]
+            self.flat_param[s0:e0].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[s0:e0].view_as(p)
+            p.grad = None
+            self._params.append(p)
+            self._grad_views.append(self.flat_grad[s0:e0].view_as(p))
+        self._grad_of = {id(p): v for p, v in zip(self._params, self._grad_views)}
+
+    def grad_view(self, param):
+        """the slice of the flat gradient buffer that belongs to `param`."""
+        return self._grad_of[id(param)]
+
+    def _collect_grads(self):
+        """autograd's per-parameter gradients -> flat buffer (one multi-tensor copy instead of one
+        accumulate kernel per parameter); parameters the task did not touch keep their zero fill."""
+        dst, src = [], []
+        for p, v in zip(self._params, self._grad_views):
+            if p.grad is not None:
+                dst.append(v)
+                src.append(p.grad)
+                p.grad = None
+        if dst:
+            torch._foreach_copy_(dst, src)
 
     def _active_ranges(self, task):
         """contiguous flat ranges that received a gradient for `task` (found once per task)."""
@@ -139,29 +165,42 @@ class StepEngine:
         steps = [steps] if isinstance(steps, int) else steps
         gamma = self.lr_config.get('gamma', 0.1)
         exp = sum(self.iter >= s for s in steps)
-        for g, base in zip(self.optimizer.param_groups, self._base_lrs):
-            if torch.is_tensor(g['lr']):
-                if exp != getattr(self, '_lr_exp', 0):
-                    g['lr'].fill_(base * gamma ** exp)
-            else:
-                g['lr'] = base * gamma ** exp
+        if exp == getattr(self, '_lr_exp', 0):
+            return
         self._lr_exp = exp
+        for g, base in zip(self.optimizer.param_groups, self._base_lrs):
+            g['lr'] = base * gamma ** exp
+        if hasattr(self.optimizer, 'set_lr_scale'):
+            self.optimizer.set_lr_scale(gamma ** exp)            # device scalar: graphs stay valid
+        else:
+            self._graphs.clear()                                 # lr is baked into captured launches: re-capture
 
     # -- one co-training iteration ------------------------------------------
     def _backward_and_step(self, outputs, task):
         """OptimizerHook.after_train_iter: backward, gradient exchange, global-norm clip, AdamW."""
         outputs['loss'].backward()
+        self._collect_grads()
         if self.world > 1:
             for lo, hi in self._active_ranges(task):
                 seg = self.flat_grad[lo:hi]
                 dist.all_reduce(seg)
                 seg.div_(self.world)
+        clip_coef = None
         if self.grad_clip:
             max_norm = float(self.grad_clip['max_norm'])
             total_norm = torch.linalg.vector_norm(self.flat_grad, float(self.grad_clip.get('norm_type', 2)))
-            self.flat_grad.mul_(torch.clamp(max_norm / (total_norm + 1e-6), max=1.0))
+            clip_coef = torch.clamp(max_norm / (total_norm + 1e-6), max=1.0)
             self.last_grad_norm = total_norm
-        self.optimizer.step()
+        if hasattr(self.optimizer, 'step_flat'):
+            self.optimizer.step_flat(clip_coef)                  # clip scale folded into the AdamW kernel
+        else:
+            if clip_coef is not None:
+                self.flat_grad.mul_(clip_coef)
+            for p, v in zip(self._params, self._grad_views):
+                p.grad = v
+            self.optimizer.step()
+            for p in self._params:
+                p.grad = None
 
     def _autocast(self):
         return torch.autocast('cuda', dtype=self.compute_dtype, enabled=self.compute_dtype != torch.float32)

@@ -412,6 +412,62 @@ def sigmoid_focal_loss(input, target, gamma=2.0, alpha=0.25):
     return SigmoidFocalLossFunction.apply(input, target, gamma, alpha)
 
 
+# ---------------------------------------------------------------------------
+# Linear with the bias gradient on rsc_colsum        (GEMMs stay in the library)
+# ---------------------------------------------------------------------------
+def colsum(x2d):
+    """(rows, C) -> (C,) fp32 column sums."""
+    _cuda(x2d)
+    x2d = x2d.contiguous()
+    rows, C = x2d.shape
+    y = torch.zeros(C, dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        call('rsc_colsum', x2d.data_ptr(), y.data_ptr(), rows, C, _dt(x2d), _stream(),
+             alg_bytes=x2d.numel() * x2d.element_size())
+    return y
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b with library GEMMs; backward: dx = dy W, dW = dy^T x (GEMMs), db = rsc_colsum(dy).
+    Runs in the dtype of x (weights are cast once, as autocast would)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        w = weight.to(x.dtype)
+        y = torch.nn.functional.linear(x, w, None if bias is None else bias.to(x.dtype))
+        ctx.save_for_backward(x, w)
+        ctx.meta = (weight.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        wdt, bdt = ctx.meta
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        x2 = x.reshape(-1, x.shape[-1])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.mm(dy2, w).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.mm(dy2.t(), x2).to(wdt)
+        if bdt is not None and ctx.needs_input_grad[2]:
+            db = colsum(dy2).to(bdt)
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    """F.linear in the active compute dtype; on CUDA (out_features % 4 == 0) the bias gradient comes
+    from rsc_colsum instead of a separate ATen reduction.  The GEMMs are library calls either way."""
+    if x.is_cuda and weight.shape[0] % 4 == 0 and (bias is not None):
+        if torch.is_autocast_enabled('cuda'):
+            x = x.to(torch.get_autocast_dtype('cuda'))
+        if x.dtype in (torch.float32, torch.bfloat16):
+            return _Linear.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
 KernelTimer = _lib.KernelTimer
 
 

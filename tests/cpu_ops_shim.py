@@ -31,13 +31,14 @@ def _gap(x, channels_last=False):
 def cpu_ops():
     from rscotr_b200 import ops
     saved = {k: getattr(ops, k) for k in ('wmsa', 'patch_merge_ln', 'ms_deform_attn', 'global_avg_pool',
-                                          'bilinear_resize', 'sigmoid_focal_loss', 'layer_norm')}
+                                          'bilinear_resize', 'sigmoid_focal_loss', 'layer_norm', 'linear')}
     ops.wmsa = lambda qkv, b, t, hw, heads, ws=7, shift=0, scale=None: osw.wmsa_core(qkv, b, t, hw, heads, ws, shift, scale)
     ops.patch_merge_ln = lambda x, hw, g, b, eps=1e-5: osw.patch_merge_ln(x, hw, g, b, eps)
     ops.ms_deform_attn = _msda
     ops.global_avg_pool = _gap
     ops.bilinear_resize = lambda x, size: F.interpolate(x, size=tuple(size), mode='bilinear', align_corners=False)
     ops.sigmoid_focal_loss = _focal
+    ops.linear = F.linear
     ops.layer_norm = lambda x, g, b, eps=1e-5, out_dtype=None: F.layer_norm(x, (x.shape[-1],), g, b, eps)
     try:
         yield

@@ -46,6 +46,7 @@ def _worker(rank, world, port, out_dir):
             model.zero_grad(set_to_none=False)
             local = model.train_step(dict(batch), None)
             local['loss'].backward()
+            eng._collect_grads()
             g_local = eng.flat_grad.clone()
             out = eng.train_iter(batch)
             res[task] = dict(g_local=g_local, loss=float(out['loss'].detach()), log=dict(out['log_vars'].items()),
