@@ -39,7 +39,7 @@ def build_activation(cfg):
     cfg = dict(cfg or dict(type='ReLU'))
     t = cfg.pop('type')
     if t == 'ReLU':
-        return nn.ReLU(inplace=cfg.get('inplace', False))
+        return nn.ReLU(inplace=False)    # (outputs of the custom Linear function must not be modified in place)
     if t == 'GELU':
         return nn.GELU()
     raise KeyError('unsupported activation %s' % t)
@@ -78,24 +78,35 @@ def norm_abbr(cfg):
 
 
 class DropPath(nn.Module):
-    """Stochastic depth per sample (mmcv DropPath).  `forced_mask` lets parity
-    tests inject the keep mask."""
+    """Stochastic depth per sample (mmcv DropPath: x / keep * floor(keep + U[0,1))).  `forced_mask`
+    lets parity tests inject the (already 1/keep-scaled) keep mask.  `add_to` fuses the residual add:
+    identity + drop_path(x) as ONE addcmul pass."""
 
     def __init__(self, drop_prob=0.):
         super().__init__()
         self.drop_prob = drop_prob
         self.forced_mask = None
 
-    def forward(self, x):
-        if self.forced_mask is not None:
-            m = self.forced_mask.to(x.dtype)
-            return x * m.view(-1, *([1] * (x.dim() - 1)))
-        if self.drop_prob == 0. or not self.training:
-            return x
-        keep = 1 - self.drop_prob
+    def _scale(self, x):
+        """per-sample factor (B,1,...,1) or None for identity."""
         shape = (x.shape[0],) + (1,) * (x.dim() - 1)
-        mask = keep + torch.rand(shape, dtype=x.dtype, device=x.device)
-        return x.div(keep) * mask.floor()
+        if self.forced_mask is not None:
+            return self.forced_mask.to(x.dtype).view(shape)
+        if self.drop_prob == 0. or not self.training:
+            return None
+        keep = 1 - self.drop_prob
+        mask = keep + torch.rand(shape, dtype=torch.float32, device=x.device)
+        return (mask.floor() / keep).to(x.dtype)
+
+    def forward(self, x):
+        s = self._scale(x)
+        return x if s is None else x * s
+
+    def add_to(self, identity, x):
+        s = self._scale(x)
+        if s is None:
+            return identity + x
+        return torch.addcmul(identity, x, s)
 
 
 def build_dropout(cfg):
@@ -135,6 +146,8 @@ class FFN(nn.Module):
             return self.dropout_layer(out)
         if identity is None:
             identity = x
+        if isinstance(self.dropout_layer, DropPath):
+            return self.dropout_layer.add_to(identity, out)
         return identity + self.dropout_layer(out)
 
 

@@ -137,8 +137,8 @@ class Mask2FormerHead(nn.Module):
         self.level_embed = nn.Embedding(self.num_transformer_feat_level, feat_channels)
         if self.scheme == 1:
             self.cls_embed = Linear(feat_channels, self.num_classes + 1)
-        self.mask_embed = nn.Sequential(Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
-                                        Linear(feat_channels, feat_channels), nn.ReLU(inplace=True),
+        self.mask_embed = nn.Sequential(Linear(feat_channels, feat_channels), nn.ReLU(),
+                                        Linear(feat_channels, feat_channels), nn.ReLU(),
                                         Linear(feat_channels, out_channels))
         assert loss_decode['type'] == 'CrossEntropyLoss' and not loss_decode.get('use_sigmoid', False)
         self.loss_weight = loss_decode.get('loss_weight', 1.0)

@@ -67,8 +67,7 @@ class ShiftWindowMSA(nn.Module):
         qkv = m.qkv(query)                                   # GEMM on the L real tokens
         out = ops.wmsa(qkv, m.qkv.bias, m.relative_position_bias_table, (H, W), m.num_heads, self.window_size,
                        self.shift_size, m.scale)             # fused attention core
-        out = m.proj_drop(m.proj(out))
-        return self.drop(out)
+        return m.proj_drop(m.proj(out))          # DropPath is applied by the block, fused with the residual add
 
 
 class SwinBlock(nn.Module):
@@ -87,8 +86,7 @@ class SwinBlock(nn.Module):
     def forward(self, x, hw_shape):
         identity = x
         x = self.norm1(x)
-        x = self.attn(x, hw_shape)
-        x = x + identity
+        x = self.attn.drop.add_to(identity, self.attn(x, hw_shape))
         identity = x
         x = self.norm2(x)
         return self.ffn(x, identity=identity)
