@@ -316,9 +316,10 @@ def main():
         ksum = kt.summary()
     kscale = args.steps / 6.0                                       # normalise kernel ms to the timed region's steps
     for d in ksum.values():
-        d['ms'] *= kscale
+        for k in ('ms', 'bytes', 'big_ms', 'big_bytes'):
+            d[k] *= kscale
         d['launches'] = int(round(d['launches'] * kscale))
-        d['bytes'] *= kscale
+        d['big_launches'] = int(round(d['big_launches'] * kscale))
 
     # ---- timed region B: end to end through the public API, pinned host inputs, loss read back
     barrier()
@@ -349,12 +350,16 @@ def main():
     e2e = world * args.steps / (ms_e2e / 1000.0)
     peak, peak_src = peaks()
     mine_ms = sum(d['ms'] for d in ksum.values())
-    top = max(ksum.items(), key=lambda kv: kv[1]['ms']) if ksum else (None, None)
+    # dominant kernel = most device time over launches that move >= 32 MB (for the many tiny launches of the
+    # decoders the question is launch latency, not bandwidth); its roofline numbers are over those launches
+    top = max(ksum.items(), key=lambda kv: kv[1]['big_ms']) if ksum else (None, None)
     roofline = None
-    if top[0]:
-        d = top[1]
+    if top[0] and top[1]['big_launches']:
+        d = dict(top[1])
+        d.update(gbs=d['big_gbs'], ms=d['big_ms'], launches=d['big_launches'], bytes=d['big_bytes'])
         roofline = dict(kernel=top[0], bound='hbm', achieved=d['gbs'], peak=peak, unit='GB/s', frac=d['gbs'] / peak,
                         traffic=NCU_TRAFFIC.get(top[0]), launches=d['launches'], avg_us=1000.0 * d['ms'] / d['launches'],
+                        scope='launches with >= 32 MB of algorithmic bytes',
                         timed='CUDA events around every launch during an eager pass of the same steps (the timed '
                               'region itself replays CUDA graphs)',
                         alg_bytes_per_launch=d['bytes'] / d['launches'], peak_source=peak_src,
@@ -377,7 +382,9 @@ def main():
                ms_per_task={k: sum(v) / len(v) for k, v in per_task.items()},
                roofline=roofline,
                kernels={k: dict(launches=d['launches'], ms=round(d['ms'], 3), gbs=round(d['gbs'], 1),
-                                frac=round(d['gbs'] / peak, 4)) for k, d in sorted(ksum.items())})
+                                big_launches=d['big_launches'], big_ms=round(d['big_ms'], 3),
+                                big_gbs=round(d['big_gbs'], 1), big_frac=round(d['big_gbs'] / peak, 4))
+                        for k, d in sorted(ksum.items())})
     if world == 1 and not args.no_cpu_baseline:
         del engine, model, dev_batches
         torch.cuda.empty_cache()

@@ -109,13 +109,21 @@ class KernelTimer:
         torch.cuda.synchronize()
         out = {}
         for name, nbytes, e0, e1 in self.records:
-            d = out.setdefault(name, dict(launches=0, ms=0.0, bytes=0))
+            d = out.setdefault(name, dict(launches=0, ms=0.0, bytes=0, big_launches=0, big_ms=0.0, big_bytes=0))
+            t = e0.elapsed_time(e1)
             d['launches'] += 1
-            d['ms'] += e0.elapsed_time(e1)
+            d['ms'] += t
             d['bytes'] += nbytes
+            if nbytes >= self.BIG:        # launches large enough for bandwidth to be the question
+                d['big_launches'] += 1
+                d['big_ms'] += t
+                d['big_bytes'] += nbytes
         for d in out.values():
             d['gbs'] = d['bytes'] / d['ms'] / 1e6 if d['ms'] > 0 else 0.0
+            d['big_gbs'] = d['big_bytes'] / d['big_ms'] / 1e6 if d['big_ms'] > 0 else 0.0
         return out
+
+    BIG = 32 << 20
 
 
 def launch_count():
