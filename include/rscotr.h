@@ -178,15 +178,55 @@ int rsc_sigmoid_focal_loss_bwd(const void *input, const int64_t *target, float *
                                float gamma, float alpha, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------
+ * DINO / Deformable-DETR loss hot path.
+ * Replaces, per training step, the 7 x B HungarianAssigner.assign calls of
+ * models/multi/bbox_head/mmdet_detr_head/detr_head.py:475-543 (cost matrix with
+ * mmdet FocalLossCost / BBoxL1Cost(xywh) / IoUCost(giou) + scipy
+ * linear_sum_assignment behind a device->host sync each) and the 13 loss_single /
+ * loss_dn_single calls of detr_head.py:333-416 and dino_head.py:236-365.
+ *
+ * Query element (l, b, q) of a segment lives at row (l*B + b)*NqTot + q0 + q of
+ * cls (rows x C logits, `dtype`) and box (rows x 4 fp32, cxcywh in [0,1]).
+ *
+ * rsc_det_match: P = L*B problems.  gt_labels[G] / gt_boxes[G,4] (xyxy pixels) are
+ *   concatenated over the images, gt_start[B+1] their offsets, img_wh[B,2] = (w,h).
+ *   cost: caller workspace of P*max_gt*Nq floats, receives cost[p][i][q];
+ *   assign[P,Nq]: global gt index matched to query q or -1; gt_norm (optional, [G,4]):
+ *   normalised cxcywh of the gt boxes.  Assignment = exact rectangular linear sum
+ *   assignment (fp64 duals), i.e. what scipy returns whenever the optimum is unique.
+ * rsc_det_loss_fwd: out[row,3] += (loss_cls, loss_bbox, loss_iou) of layer l, already
+ *   multiplied by the loss weights and divided by cls_factor[l] / pos_factor[l] (device
+ *   floats, >= 1); row = out_row0 + (last_first ? (l == L-1 ? 0 : l+1) : l).
+ *   assign is [L,B,Nq] (assign_layer_stride = B*Nq) or [B,Nq] shared by all layers (0).
+ * rsc_det_loss_bwd: dout[rows,3] -> dcls (same layout/dtype as cls), dbox (fp32); writes
+ *   every element of the segment.
+ * ---------------------------------------------------------------------- */
+int rsc_det_match(const void *cls, const float *box, const int64_t *gt_labels, const float *gt_boxes,
+                  const int *gt_start, const float *img_wh, int P, int B, int NqTot, int q0, int Nq, int C, int max_gt,
+                  float w_cls, float w_reg, float w_iou, float alpha, float gamma, float eps, float *cost, int *assign,
+                  float *gt_norm, int dtype, void *stream);
+int rsc_det_loss_fwd(const void *cls, const float *box, const int *assign, const int64_t *gt_labels,
+                     const float *gt_norm, const float *img_wh, const float *cls_factor, const float *pos_factor,
+                     float *out, int L, int B, int NqTot, int q0, int Nq, int C, int assign_layer_stride, int out_row0,
+                     int last_first, float gamma, float alpha, float w_cls, float w_l1, float w_iou, float eps, int dtype,
+                     void *stream);
+int rsc_det_loss_bwd(const void *cls, const float *box, const int *assign, const int64_t *gt_labels,
+                     const float *gt_norm, const float *img_wh, const float *cls_factor, const float *pos_factor,
+                     const float *dout, void *dcls, float *dbox, int L, int B, int NqTot, int q0, int Nq, int C,
+                     int assign_layer_stride, int out_row0, int last_first, float gamma, float alpha, float w_cls,
+                     float w_l1, float w_iou, float eps, int dtype, void *stream);
+
+/* ------------------------------------------------------------------------
  * Flat fused AdamW (+ gradient-clip scale).  Replaces mmcv OptimizerHook's
  * clip_grad_norm_ scaling + torch.optim.AdamW.step over one contiguous fp32 range
  * (optimizer built by mtl/utils/optimizer.py:25-55).
  * lr / step / clip_coef are DEVICE scalars (float); step holds the 1-based step
  * count t; clip_coef may be NULL (= 1).  torch.optim.AdamW arithmetic.
+ * param_bf16 (may be NULL): bf16 shadow of `param`, rewritten in the same pass.
  * ---------------------------------------------------------------------- */
 int rsc_adamw_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, const float *lr,
                    float lr_mult, float beta1, float beta2, float eps, float weight_decay, const float *step,
-                   const float *clip_coef, void *stream);
+                   const float *clip_coef, void *param_bf16, void *stream);
 
 /* y[c] += sum_r x[r][c]  (rows,C) -> (C) float, ACCUMULATED: the bias gradient of a Linear
  * layer (replaces ATen's sum(0) reduce in AddmmBackward / nn.Linear backward). */

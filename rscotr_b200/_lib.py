@@ -29,7 +29,10 @@ _SIGS = {
     'rsc_patch_merge_ln_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'rsc_layernorm_fwd': [_P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _F, _I, _I, _P],
     'rsc_layernorm_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
-    'rsc_adamw_step': [_P, _P, _P, _P, ctypes.c_int64, _P, _F, _F, _F, _F, _F, _P, _P, _P],
+    'rsc_adamw_step': [_P, _P, _P, _P, ctypes.c_int64, _P, _F, _F, _F, _F, _F, _P, _P, _P, _P],
+    'rsc_det_match': [_P] * 6 + [_I] * 7 + [_F] * 6 + [_P, _P, _P, _I, _P],
+    'rsc_det_loss_fwd': [_P] * 9 + [_I] * 9 + [_F] * 6 + [_I, _P],
+    'rsc_det_loss_bwd': [_P] * 11 + [_I] * 9 + [_F] * 6 + [_I, _P],
     'rsc_colsum': [_P, _P, ctypes.c_int64, _I, _I, _P],
     'rsc_msda_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'rsc_msda_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -4,6 +4,8 @@
 // rsc_adamw_step: ONE pass over a contiguous fp32 range of the flat parameter buffer:
 //   g = grad * clip_coef ; p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
 //   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)          (torch.optim.AdamW)
+// and (optionally) refreshes the bf16 shadow of the parameters that the next step's GEMMs read, so no
+// per-weight fp32->bf16 cast kernel ever runs (autocast launches one per weight per step).
 // lr, t and clip_coef are DEVICE scalars so that the launch is CUDA-graph replayable.
 #include "common.cuh"
 
@@ -12,7 +14,8 @@ namespace rsc {
 __global__ void __launch_bounds__(256)
     adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                  int64_t n4, const float *__restrict__ lr_ptr, float lr_mult, float beta1, float beta2, float eps,
-                 float wd, const float *__restrict__ step_ptr, const float *__restrict__ clip_ptr) {
+                 float wd, const float *__restrict__ step_ptr, const float *__restrict__ clip_ptr,
+                 __nv_bfloat16 *__restrict__ p_lp) {
   const float lr = __ldg(lr_ptr) * lr_mult;
   const float t = __ldg(step_ptr);
   const float clip = clip_ptr ? __ldg(clip_ptr) : 1.0f;
@@ -34,6 +37,11 @@ __global__ void __launch_bounds__(256)
       pp[k] = pp[k] * decay - step_size * (mm[k] / denom);
     }
     reinterpret_cast<float4 *>(p)[i] = pv;
+    if (p_lp) {   // compute-dtype shadow of the master weights (what the GEMMs of the next step read)
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+      uint2 pk = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+      reinterpret_cast<uint2 *>(p_lp)[i] = pk;
+    }
     reinterpret_cast<float4 *>(m)[i] = mv;
     reinterpret_cast<float4 *>(v)[i] = vv;
   }
@@ -75,16 +83,19 @@ using namespace rsc;
 
 extern "C" int rsc_adamw_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
                               const float *lr, float lr_mult, float beta1, float beta2, float eps,
-                              float weight_decay, const float *step, const float *clip_coef, void *stream) {
+                              float weight_decay, const float *step, const float *clip_coef, void *param_bf16,
+                              void *stream) {
   RSC_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && lr && step, "rsc_adamw_step: null pointer");
   RSC_CHECK_ARG(n > 0 && n % 4 == 0, "rsc_adamw_step: n must be a positive multiple of 4 (got %lld)", (long long)n);
   RSC_CHECK_ARG(((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0,
                 "rsc_adamw_step: buffers must be 16-byte aligned");
+  RSC_CHECK_ARG((uintptr_t)param_bf16 % 8 == 0, "rsc_adamw_step: param_bf16 must be 8-byte aligned");
   int64_t n4 = n / 4;
   int64_t blocks = (n4 + 255) / 256;
   int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
   adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n4, lr, lr_mult, beta1, beta2,
-                                                        eps, weight_decay, step, clip_coef);
+                                                        eps, weight_decay, step, clip_coef,
+                                                        (__nv_bfloat16 *)param_bf16);
   RSC_CHECK_LAUNCH("rsc_adamw_step");
   return RSC_OK;
 }

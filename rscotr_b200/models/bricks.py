@@ -35,6 +35,40 @@ def const_tensor(values, dtype, device):
     return t
 
 
+class PackedLosses(dict):
+    """A loss dict (name -> scalar tensor, the reference's contract) whose values are the elements of ONE
+    packed 1-D tensor: a fused loss kernel returns all its terms at once, MTL._parse_losses sums `packed`
+    directly (2 kernels instead of ~3 per term), and per-key access still works for callers that want it."""
+
+    def __init__(self, keys, packed):
+        super().__init__()
+        assert packed.dim() == 1 and packed.numel() == len(keys)
+        self.key_list, self.packed = list(keys), packed
+        for k in self.key_list:
+            dict.__setitem__(self, k, None)
+
+    def _fill(self):
+        if self.key_list and dict.__getitem__(self, self.key_list[0]) is None:
+            for k, v in zip(self.key_list, self.packed.unbind(0)):
+                dict.__setitem__(self, k, v)
+
+    def __getitem__(self, k):
+        self._fill()
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        self._fill()
+        return dict.get(self, k, default)
+
+    def items(self):
+        self._fill()
+        return dict.items(self)
+
+    def values(self):
+        self._fill()
+        return dict.values(self)
+
+
 def build_activation(cfg):
     cfg = dict(cfg or dict(type='ReLU'))
     t = cfg.pop('type')
@@ -86,12 +120,16 @@ class DropPath(nn.Module):
         super().__init__()
         self.drop_prob = drop_prob
         self.forced_mask = None
+        self.drawn = None          # set by draw_drop_paths: this call's factor, drawn in one batched launch
 
     def _scale(self, x):
         """per-sample factor (B,1,...,1) or None for identity."""
         shape = (x.shape[0],) + (1,) * (x.dim() - 1)
         if self.forced_mask is not None:
             return self.forced_mask.to(x.dtype).view(shape)
+        if self.drawn is not None:
+            s, self.drawn = self.drawn, None
+            return s.to(x.dtype).view(shape)
         if self.drop_prob == 0. or not self.training:
             return None
         keep = 1 - self.drop_prob
@@ -107,6 +145,18 @@ class DropPath(nn.Module):
         if s is None:
             return identity + x
         return torch.addcmul(identity, x, s)
+
+
+def draw_drop_paths(drop_paths, batch, device, dtype):
+    """Draw the stochastic-depth factors of a whole list of DropPath modules with ONE rand launch
+    (instead of rand / add / floor / div / cast per module): row k = floor(keep_k + U[0,1)) / keep_k."""
+    active = [m for m in drop_paths if m.training and m.drop_prob > 0. and m.forced_mask is None]
+    if not active:
+        return
+    keep = const_tensor([[1.0 - m.drop_prob] for m in active], torch.float32, device)
+    s = ((keep + torch.rand(len(active), batch, dtype=torch.float32, device=device)).floor() / keep).to(dtype)
+    for m, row in zip(active, s.unbind(0)):
+        m.drawn = row
 
 
 def build_dropout(cfg):
@@ -167,6 +217,37 @@ class MultiheadAttention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         self.dropout_layer = build_dropout(dropout_layer)
 
+    def _attend(self, query, key, value, attn_mask, key_padding_mask, same_qk=False):
+        """nn.MultiheadAttention.forward(need_weights=False) on seq-first (L,B,E) tensors with the packed
+        in_proj applied through ops.linear (bf16 shadow weights, gradients accumulated into the flat
+        buffer; q and k share one GEMM when they read the same tensor) and the library SDPA core."""
+        m = self.attn
+        E, H = self.embed_dims, self.num_heads
+        L, B, _ = query.shape
+        S = key.shape[0]
+        W, bias = m.in_proj_weight, m.in_proj_bias
+        if same_qk or key is query:
+            qk = ops.linear(query, W, bias, rows=(0, 2 * E))
+            q, k = qk[..., :E], qk[..., E:]
+        else:
+            q, k = ops.linear(query, W, bias, rows=(0, E)), ops.linear(key, W, bias, rows=(E, 2 * E))
+        v = ops.linear(value, W, bias, rows=(2 * E, 3 * E))
+        q = q.reshape(L, B, H, E // H).permute(1, 2, 0, 3)
+        k = k.reshape(S, B, H, E // H).permute(1, 2, 0, 3)
+        v = v.reshape(S, B, H, E // H).permute(1, 2, 0, 3)
+        mask = None
+        if attn_mask is not None:          # bool, True = masked out (torch MHA convention)
+            assert attn_mask.dtype == torch.bool, 'only boolean attention masks are used by the reference heads'
+            mask = ~attn_mask
+            mask = mask.view(B, H, L, S) if mask.dim() == 3 else mask.view(1, 1, L, S)
+        if key_padding_mask is not None:
+            kp = ~key_padding_mask.view(B, 1, 1, S)
+            mask = kp if mask is None else mask & kp
+        out = F.scaled_dot_product_attention(q, k, v.to(q.dtype), attn_mask=mask,
+                                             dropout_p=m.dropout if self.training else 0.0)
+        out = out.permute(2, 0, 1, 3).reshape(L, B, E)
+        return ops.linear(out, m.out_proj.weight, m.out_proj.bias)
+
     def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None, attn_mask=None,
                 key_padding_mask=None, **kwargs):
         if key is None:
@@ -177,14 +258,17 @@ class MultiheadAttention(nn.Module):
             identity = query
         if key_pos is None and query_pos is not None and query_pos.shape == key.shape:
             key_pos = query_pos
+        same_qk = key is query
         if query_pos is not None:
             query = query + query_pos
-        if key_pos is not None:
+        same_qk = same_qk and key_pos is query_pos
+        if same_qk:
+            key = query
+        elif key_pos is not None:
             key = key + key_pos
         if self.batch_first:
             query, key, value = (t.transpose(0, 1) for t in (query, key, value))
-        out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask, key_padding_mask=key_padding_mask,
-                        need_weights=False)[0]
+        out = self._attend(query, key, value, attn_mask, key_padding_mask, same_qk)
         if self.batch_first:
             out = out.transpose(0, 1)
         return identity + self.dropout_layer(self.proj_drop(out))

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS, build_from_cfg
-from .bricks import (LayerNorm, Linear, TransformerLayerSequence, const_tensor, MultiScaleDeformableAttention, build_positional_encoding,
+from .bricks import (LayerNorm, Linear, PackedLosses, TransformerLayerSequence, const_tensor, MultiScaleDeformableAttention, build_positional_encoding,
                      build_transformer_layer_sequence, inverse_sigmoid)
 
 
@@ -517,6 +517,7 @@ class DINOHead(nn.Module):
             dn_cfg = dict(dn_cfg)
             dn_cfg['num_classes'], dn_cfg['num_queries'], dn_cfg['hidden_dim'] = num_classes, num_query, self.embed_dims
         self.dn_generator = build_dn_generator(dn_cfg)
+        self.fused_loss = True        # CUDA: rsc_det_match + rsc_det_loss_{fwd,bwd} (no host phase); False = ATen + scipy
         self.init_weights()
 
     def _init_layers(self):
@@ -606,12 +607,100 @@ class DINOHead(nn.Module):
 
     def loss(self, all_cls_scores, all_bbox_preds, enc_topk_scores, enc_topk_anchors, gt_bboxes_list, gt_labels_list,
              img_metas, dn_meta=None, gt_bboxes_ignore=None):
-        """dino_head.py:152-234 in three phases so that a step engine can put the device work of
-        phases 1 and 3 into CUDA graphs around the host-side matching of phase 2."""
+        """dino_head.py:152-234.  On CUDA: Hungarian matching and all 13 x 3 loss terms in a handful of
+        kernels (loss_fused).  Otherwise in three phases so that a step engine can put the device work
+        of phases 1 and 3 into CUDA graphs around the host-side matching of phase 2."""
+        if self.fused_loss and all_cls_scores.is_cuda:
+            return self.loss_fused(all_cls_scores, all_bbox_preds, enc_topk_scores, enc_topk_anchors, gt_bboxes_list,
+                                   gt_labels_list, img_metas, dn_meta, gt_bboxes_ignore)
         pend = self.loss_prepare(all_cls_scores, all_bbox_preds, enc_topk_scores, enc_topk_anchors, gt_bboxes_list,
                                  gt_labels_list, img_metas, dn_meta, gt_bboxes_ignore)
         self.loss_assign(pend)
         return self.loss_finish(pend)
+
+    def _avg_factors_dev(self, pos_counts, neg_counts, dev):
+        """device version of _avg_factors: (2, n) tensor [cls_avg_factor; num_total_pos], both >= 1; the
+        cross-rank means are ONE packed all-reduce on the device (no .item(), CUDA-graph capturable)."""
+        pos = [float(x) for x in pos_counts]
+        cls_avg = [p * 1.0 + float(n) * self.bg_cls_weight for p, n in zip(pos, neg_counts)]
+        t = const_tensor([cls_avg, pos], torch.float32, dev)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            r = t.clone()
+            dist.all_reduce(r)
+            r = r / dist.get_world_size()
+            t = r if self.sync_cls_avg_factor else torch.stack([t[0], r[1]])
+        return t.clamp(min=1.0)
+
+    def loss_fused(self, all_cls_scores, all_bbox_preds, enc_topk_scores, enc_topk_anchors, gt_bboxes_list,
+                   gt_labels_list, img_metas, dn_meta=None, gt_bboxes_ignore=None):
+        """Same loss terms / keys as loss_prepare + loss_assign + loss_finish, on the GPU end to end:
+        rsc_det_match (cost matrices + linear sum assignment of all 7 x B problems), then one fused
+        focal + L1 + GIoU kernel per query segment (encoder proposals, decoder layers, denoising part)."""
+        assert gt_bboxes_ignore is None, \
+            '%s only supports for gt_bboxes_ignore setting to None.' % self.__class__.__name__
+        L, B, NqTot, C = all_cls_scores.shape
+        dev = all_cls_scores.device
+        ps = int(dn_meta['pad_size']) if dn_meta is not None else 0
+        Nq = NqTot - ps
+        sizes = [int(l.numel()) for l in gt_labels_list]
+        max_gt, total_gt = (max(sizes) if sizes else 0), sum(sizes)
+        starts = [0]
+        for n in sizes:
+            starts.append(starts[-1] + n)
+        gt_start = const_tensor(starts, torch.int32, dev)
+        img_wh = const_tensor([[float(m['img_shape'][1]), float(m['img_shape'][0])] for m in img_metas],
+                              torch.float32, dev)
+        gt_labels = torch.cat(gt_labels_list) if len(gt_labels_list) > 1 else gt_labels_list[0]
+        gt_boxes = torch.cat(gt_bboxes_list) if len(gt_bboxes_list) > 1 else gt_bboxes_list[0]
+        all_cls = all_cls_scores.contiguous()
+        all_box = all_bbox_preds.float().contiguous()
+        a = self.assigner
+        has_enc = enc_topk_scores is not None
+        with torch.no_grad():
+            assign_dec, _, gt_norm = ops.det_match(all_cls, all_box, ps, Nq, gt_labels, gt_boxes, gt_start, img_wh,
+                                                   max_gt, a.w_cls, a.w_reg, a.w_iou, a.alpha, a.gamma, a.eps)
+            if has_enc:
+                enc_cls, enc_box = enc_topk_scores.contiguous(), enc_topk_anchors.float().contiguous()
+                assign_enc, _, _ = ops.det_match(enc_cls, enc_box, 0, enc_cls.shape[-2], gt_labels, gt_boxes, gt_start,
+                                                 img_wh, max_gt, a.w_cls, a.w_reg, a.w_iou, a.alpha, a.gamma, a.eps,
+                                                 want_gt_norm=False)
+        # averaging factors: every gt is matched (n_gt <= Nq), so the positive counts are known on the host
+        rows_match = (1 if has_enc else 0) + L
+        pos_counts, neg_counts = [total_gt] * rows_match, [B * Nq - total_gt] * rows_match
+        keys, segs, tensors, row = [], [], [all_cls, all_box], 0
+        terms = ('loss_cls', 'loss_bbox', 'loss_iou')
+        if has_enc:
+            tensors += [enc_cls, enc_box]
+            segs.append(dict(t=1, L=1, B=B, NqTot=enc_cls.shape[-2], q0=0, Nq=enc_cls.shape[-2], C=C, assign=assign_enc,
+                             a_ls=B * enc_cls.shape[-2], row0=0, last_first=False, f0=0))
+            keys += ['interm_' + t for t in terms]
+            row = 1
+        segs.append(dict(t=0, L=L, B=B, NqTot=NqTot, q0=ps, Nq=Nq, C=C, assign=assign_dec, a_ls=B * Nq, row0=row,
+                         last_first=True, f0=row))
+        keys += list(terms) + ['d%d.%s' % (n, t) for n in range(L - 1) for t in terms]
+        row += L
+        if dn_meta is not None:
+            num_groups = int(dn_meta['num_dn_group'])
+            single = ps // num_groups if num_groups else 0
+            dn_assign = [[-1] * ps for _ in range(B)]
+            for b in range(B):
+                for g in range(num_groups):
+                    for t in range(sizes[b]):
+                        dn_assign[b][g * single + t] = starts[b] + t
+            assign_dn = const_tensor(dn_assign, torch.int32, dev) if ps else assign_dec
+            npos = total_gt * num_groups
+            pos_counts += [npos] * L
+            neg_counts += [npos] * L
+            segs.append(dict(t=0, L=L, B=B, NqTot=NqTot, q0=0, Nq=ps, C=C, assign=assign_dn, a_ls=0, row0=row,
+                             last_first=True, f0=row))
+            keys += ['dn_' + t for t in terms] + ['d%d.dn_%s' % (n, t) for n in range(L - 1) for t in terms]
+            row += L
+        factors = self._avg_factors_dev(pos_counts, neg_counts, dev)
+        lc = self.loss_cls
+        out = ops.det_loss(segs, tensors, row, gt_labels, gt_norm, img_wh, factors[0], factors[1], lc.gamma, lc.alpha,
+                           lc.loss_weight, self.loss_bbox.loss_weight, self.loss_iou.loss_weight, self.loss_iou.eps)
+        return PackedLosses(keys, out.view(-1))
 
     def loss_prepare(self, all_cls_scores, all_bbox_preds, enc_topk_scores, enc_topk_anchors, gt_bboxes_list,
                      gt_labels_list, img_metas, dn_meta=None, gt_bboxes_ignore=None):

@@ -9,7 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..config import MODELS, build_from_cfg
-from .bricks import MultiScaleDeformableAttention, build_transformer_layer_sequence
+from .bricks import MultiScaleDeformableAttention, PackedLosses, build_transformer_layer_sequence, const_tensor
 from .cls_head import Augments
 from .seg_head import resize
 
@@ -163,7 +163,9 @@ class MTL(nn.Module):
     # phases in CUDA graphs; only the det task has host work (Hungarian matching) in the middle.
     def train_step_begin(self, data):
         task = data.get('task', None)
-        if task == 'det' and hasattr(self.bbox_head, 'forward_train_begin'):
+        if task == 'det' and hasattr(self.bbox_head, 'forward_train_begin') and not (
+                getattr(self.bbox_head, 'fused_loss', False) and data['img'].is_cuda):
+            # (with the GPU matching + fused loss kernels the det step has no host phase at all)
             img, img_metas = data['img'], data['img_metas']
             batch_input_shape = tuple(img[0].size()[-2:])
             for img_meta in img_metas:
@@ -211,6 +213,13 @@ class MTL(nn.Module):
     def _parse_losses(self, losses):
         """Same totals / log keys as multitask_learner.py:274-306, but ONE device->host
         transfer and (distributed) ONE packed all-reduce instead of one per log var."""
+        if isinstance(losses, PackedLosses):        # all terms already in one tensor (fused loss kernels)
+            keys, packed = list(losses.key_list), losses.packed.float()
+            sel = [i for i, k in enumerate(keys) if 'loss' in k]
+            loss = packed.sum() if len(sel) == len(keys) else packed[const_tensor(sel, torch.long, packed.device)].sum()
+            keys.append('loss')
+            packed = torch.cat([packed.detach(), loss.detach().reshape(1)])
+            return loss, keys, self._reduce_log_vars(keys, packed)
         log_vars = OrderedDict()
         for loss_name, loss_value in losses.items():
             if isinstance(loss_value, torch.Tensor):
@@ -222,15 +231,19 @@ class MTL(nn.Module):
         loss = sum(_value for _key, _value in log_vars.items() if 'loss' in _key)
         log_vars['loss'] = loss
         packed = torch.stack([v.detach().float().reshape(()) for v in log_vars.values()])
+        return loss, list(log_vars.keys()), self._reduce_log_vars(list(log_vars.keys()), packed)
+
+    @staticmethod
+    def _reduce_log_vars(keys, packed):
         if dist.is_available() and dist.is_initialized():
-            n = torch.cat([packed.new_tensor([float(len(log_vars))]), packed])
+            n = torch.cat([packed.new_tensor([float(len(keys))]), packed])
             dist.all_reduce(n)
             world = dist.get_world_size()
-            assert int(round(float(n[0]))) == len(log_vars) * world, \
+            assert int(round(float(n[0]))) == len(keys) * world, \
                 'loss log variables are different across GPUs!\nrank %d len(log_vars): %d keys: %s' % (
-                    dist.get_rank(), len(log_vars), ','.join(log_vars.keys()))
+                    dist.get_rank(), len(keys), ','.join(keys))
             packed = n[1:] / world
-        return loss, list(log_vars.keys()), packed
+        return packed
 
     def load_task_pretrain(self):
         if self.task_pretrain is None:

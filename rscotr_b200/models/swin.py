@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS
-from .bricks import FFN, DropPath, LayerNorm, Linear
+from .bricks import FFN, DropPath, LayerNorm, Linear, draw_drop_paths
 
 
 class WindowMSA(nn.Module):
@@ -201,6 +201,10 @@ class SwinTransformer(nn.Module):
     def forward(self, x):
         x, hw_shape = self.patch_embed(x)
         x = self.drop_after_pos(x)
+        if self.training:
+            if not hasattr(self, '_drop_paths'):
+                self._drop_paths = [m for m in self.modules() if isinstance(m, DropPath)]
+            draw_drop_paths(self._drop_paths, x.shape[0], x.device, x.dtype)
         outs = []
         for i, stage in enumerate(self.stages):
             x, hw_shape, out, out_hw_shape = stage(x, hw_shape)

@@ -56,12 +56,14 @@ class FlatAdamW:
         self.step_t += 1
         st = torch.cuda.current_stream().cuda_stream
         clip_ptr = None if clip_coef is None else clip_coef.data_ptr()
+        lp = eng.flat_param_lp.data_ptr() if eng.flat_param_lp is not None else None
         with torch.cuda.device(eng.device):
             for s0, e0, (lr_mult, wd) in self.runs:
                 _lib.call('rsc_adamw_step', eng.flat_param.data_ptr() + 4 * s0, eng.flat_grad.data_ptr() + 4 * s0,
                           self.exp_avg.data_ptr() + 4 * s0, self.exp_avg_sq.data_ptr() + 4 * s0, e0 - s0,
                           self.lr_t.data_ptr(), lr_mult, self.betas[0], self.betas[1], self.eps, wd,
-                          self.step_t.data_ptr(), clip_ptr, st, alg_bytes=28 * (e0 - s0))
+                          self.step_t.data_ptr(), clip_ptr, None if lp is None else lp + 2 * s0, st,
+                          alg_bytes=(28 if lp is None else 30) * (e0 - s0))
 
     def step(self):
         self.step_flat(None)

@@ -91,7 +91,7 @@ class StepEngine:
     # -- flat parameter / gradient buffers ---------------------------------
     def _build_flat_grads(self):
         """Parameters become views into ONE flat fp32 buffer (and their gradients land in a second
-        one with the same layout), ordered by _ORDER; every tensor starts on a 16-byte boundary."""
+        one with the same layout), ordered by _ORDER; every tensor starts on a 64-element boundary."""
         named = list(self.model.named_parameters())
         def rank(n):
             top = n.split('.')[0]
@@ -103,10 +103,14 @@ class StepEngine:
             n, p = named[i]
             assert p.dtype == torch.float32, 'master weights are fp32'
             self._spans.append((n, off, off + p.numel()))
-            off = (off + p.numel() + 3) // 4 * 4
+            off = (off + p.numel() + 63) // 64 * 64      # 128-byte aligned bf16 shadow views (TMA-friendly GEMM operands)
         total = off
         self.flat_param = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        # bf16 shadow of the master weights, refreshed by the AdamW kernel itself: the GEMMs read it
+        # directly (ops.linear), so no fp32->bf16 weight cast kernel runs in the step
+        lp = self.device.type == 'cuda' and self.compute_dtype == torch.bfloat16
+        self.flat_param_lp = torch.zeros(total, dtype=torch.bfloat16, device=self.device) if lp else None
         self._params, self._grad_views = [], []
         for (n, s0, e0), i in zip(self._spans, order):
             p = named[i][1]
@@ -115,7 +119,18 @@ class StepEngine:
             p.grad = None
             self._params.append(p)
             self._grad_views.append(self.flat_grad[s0:e0].view_as(p))
+            # ops.linear & co. accumulate this parameter's gradient straight into the flat buffer (fp32
+            # GEMM output, beta = 1) instead of bf16 dW -> cast -> AccumulateGrad -> copy
+            p._rsc_g = self._grad_views[-1]
+            p._rsc_lp = self.flat_param_lp[s0:e0].view_as(p) if lp else None
         self._grad_of = {id(p): v for p, v in zip(self._params, self._grad_views)}
+        self.sync_lp()
+
+    def sync_lp(self):
+        """refresh the bf16 shadow from the fp32 master weights (after init / load_state_dict / an optimizer
+        other than the flat AdamW kernel)."""
+        if self.flat_param_lp is not None:
+            self.flat_param_lp.copy_(self.flat_param)
 
     def grad_view(self, param):
         """the slice of the flat gradient buffer that belongs to `param`."""
@@ -131,7 +146,7 @@ class StepEngine:
                 src.append(p.grad)
                 p.grad = None
         if dst:
-            torch._foreach_copy_(dst, src)
+            torch._foreach_add_(dst, src)      # (add, not copy: ops.linear may have accumulated into the view already)
 
     def _active_ranges(self, task):
         """contiguous flat ranges that received a gradient for `task` (found once per task)."""
@@ -201,6 +216,7 @@ class StepEngine:
             self.optimizer.step()
             for p in self._params:
                 p.grad = None
+            self.sync_lp()
 
     def _autocast(self):
         return torch.autocast('cuda', dtype=self.compute_dtype, enabled=self.compute_dtype != torch.float32)

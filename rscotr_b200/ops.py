@@ -413,14 +413,94 @@ def sigmoid_focal_loss(input, target, gamma=2.0, alpha=0.25):
 
 
 # ---------------------------------------------------------------------------
+# detection losses: GPU Hungarian matching + fused focal / L1 / GIoU   
+# ---------------------------------------------------------------------------
+def det_match(cls, box, q0, Nq, gt_labels, gt_boxes, gt_start, img_wh, max_gt, w_cls=2.0, w_reg=5.0, w_iou=2.0,
+              alpha=0.25, gamma=2.0, eps=1e-12, want_gt_norm=True):
+    """cls (..., B, NqTot, C) logits, box (..., B, NqTot, 4) fp32 cxcywh; matches queries q0:q0+Nq of every
+    (leading index, image) problem against that image's gt boxes.  Returns (assign int32 (P, Nq) holding the
+    global gt index or -1, cost (P, max_gt, Nq), gt_norm (G, 4))."""
+    _cuda(cls, box, gt_boxes, gt_start, img_wh)
+    assert cls.is_contiguous() and box.is_contiguous() and box.dtype == torch.float32
+    B, NqTot, C = cls.shape[-3:]
+    P = cls.numel() // (NqTot * C)
+    dev = cls.device
+    assign = torch.empty(P, Nq, dtype=torch.int32, device=dev)
+    cost = torch.empty(P, max(max_gt, 1), Nq, dtype=torch.float32, device=dev)
+    G = gt_boxes.shape[0]
+    gt_norm = torch.empty(G, 4, dtype=torch.float32, device=dev) if want_gt_norm else None
+    gt_boxes = gt_boxes.float().contiguous()
+    with torch.cuda.device(dev):
+        call('rsc_det_match', cls.data_ptr(), box.data_ptr(), gt_labels.data_ptr(), gt_boxes.data_ptr(),
+             gt_start.data_ptr(), img_wh.data_ptr(), P, B, NqTot, q0, Nq, C, max_gt, w_cls, w_reg, w_iou, alpha, gamma,
+             eps, cost.data_ptr(), assign.data_ptr(), _p(gt_norm), _dt(cls), _stream())
+    return assign, cost, gt_norm
+
+
+class _DetLoss(torch.autograd.Function):
+    """segs: list of dicts(t=index of the (cls, box) tensor pair, L, B, NqTot, q0, Nq, C, assign, a_ls, row0,
+    last_first); tensors = cls0, box0, cls1, box1, ...; returns (rows, 3) fp32 loss sums."""
+
+    @staticmethod
+    def forward(ctx, segs, common, rows, *tensors):
+        gt_labels, gt_norm, img_wh, cls_factor, pos_factor, hyper = common
+        out = torch.zeros(rows, 3, dtype=torch.float32, device=tensors[0].device)
+        with torch.cuda.device(out.device):
+            for sg in segs:
+                cls, box = tensors[2 * sg['t']], tensors[2 * sg['t'] + 1]
+                call('rsc_det_loss_fwd', cls.data_ptr(), box.data_ptr(), sg['assign'].data_ptr(), _p(gt_labels),
+                     _p(gt_norm), img_wh.data_ptr(), cls_factor.data_ptr() + 4 * sg['f0'],
+                     pos_factor.data_ptr() + 4 * sg['f0'], out.data_ptr(), sg['L'], sg['B'], sg['NqTot'], sg['q0'],
+                     sg['Nq'], sg['C'], sg['a_ls'], sg['row0'], int(sg['last_first']), *hyper, _dt(cls), _stream())
+        ctx.segs, ctx.common = segs, common
+        ctx.save_for_backward(*tensors)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        tensors = ctx.saved_tensors
+        gt_labels, gt_norm, img_wh, cls_factor, pos_factor, hyper = ctx.common
+        dout = dout.contiguous().float()
+        covered = {}
+        for sg in ctx.segs:
+            covered[sg['t']] = covered.get(sg['t'], 0) + sg['Nq']
+        grads = []
+        for k in range(len(tensors) // 2):
+            full = covered.get(k, 0) == tensors[2 * k].shape[-2]
+            mk = torch.empty_like if full else torch.zeros_like
+            grads += [mk(tensors[2 * k]), mk(tensors[2 * k + 1])]
+        with torch.cuda.device(dout.device):
+            for sg in ctx.segs:
+                cls, box = tensors[2 * sg['t']], tensors[2 * sg['t'] + 1]
+                call('rsc_det_loss_bwd', cls.data_ptr(), box.data_ptr(), sg['assign'].data_ptr(), _p(gt_labels),
+                     _p(gt_norm), img_wh.data_ptr(), cls_factor.data_ptr() + 4 * sg['f0'],
+                     pos_factor.data_ptr() + 4 * sg['f0'], dout.data_ptr(), grads[2 * sg['t']].data_ptr(),
+                     grads[2 * sg['t'] + 1].data_ptr(), sg['L'], sg['B'], sg['NqTot'], sg['q0'], sg['Nq'], sg['C'],
+                     sg['a_ls'], sg['row0'], int(sg['last_first']), *hyper, _dt(cls), _stream())
+        return (None, None, None) + tuple(grads)
+
+
+def det_loss(segs, tensors, rows, gt_labels, gt_norm, img_wh, cls_factor, pos_factor, gamma=2.0, alpha=0.25,
+             w_cls=1.0, w_l1=5.0, w_iou=2.0, eps=1e-6):
+    """Fused sigmoid-focal + L1 + GIoU losses of several query segments -> (rows, 3) tensor of
+    (loss_cls, loss_bbox, loss_iou), weighted and averaged (see include/rscotr.h)."""
+    _cuda(*tensors)
+    for k in range(0, len(tensors), 2):
+        assert tensors[k].is_contiguous() and tensors[k + 1].is_contiguous() and tensors[k + 1].dtype == torch.float32
+    hyper = (float(gamma), float(alpha), float(w_cls), float(w_l1), float(w_iou), float(eps))
+    return _DetLoss.apply(segs, (gt_labels, gt_norm, img_wh, cls_factor, pos_factor, hyper), rows, *tensors)
+
+
+# ---------------------------------------------------------------------------
 # Linear with the bias gradient on rsc_colsum        (GEMMs stay in the library)
 # ---------------------------------------------------------------------------
-def colsum(x2d):
-    """(rows, C) -> (C,) fp32 column sums."""
+def colsum(x2d, out=None):
+    """(rows, C) -> (C,) fp32 column sums; with `out` (fp32, contiguous) the sums are ADDED to it."""
     _cuda(x2d)
     x2d = x2d.contiguous()
     rows, C = x2d.shape
-    y = torch.zeros(C, dtype=torch.float32, device=x2d.device)
+    y = torch.zeros(C, dtype=torch.float32, device=x2d.device) if out is None else out
+    assert y.dtype == torch.float32 and y.is_contiguous() and y.numel() == C
     with torch.cuda.device(x2d.device):
         call('rsc_colsum', x2d.data_ptr(), y.data_ptr(), rows, C, _dt(x2d), _stream(),
              alg_bytes=x2d.numel() * x2d.element_size())
@@ -429,20 +509,23 @@ def colsum(x2d):
 
 class _Linear(torch.autograd.Function):
     """y = x W^T + b with library GEMMs; backward: dx = dy W, dW = dy^T x (GEMMs), db = rsc_colsum(dy).
-    Runs in the dtype of x (weights are cast once, as autocast would)."""
+    Runs in the dtype of x.  When the step engine has attached its flat buffers to the parameters
+    (`_rsc_lp` = bf16 shadow, `_rsc_g` = fp32 gradient view) the weight is read from the shadow (no cast
+    kernel) and dW / db are ACCUMULATED straight into the flat gradient buffer in fp32 (GEMM with
+    beta = 1, colsum with atomics) -- autograd then sees no gradient for them."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        w = weight.to(x.dtype)
-        y = torch.nn.functional.linear(x, w, None if bias is None else bias.to(x.dtype))
+    def forward(ctx, x, weight, bias, w, b, gw, gb):
+        # weight / bias: the (master) parameters autograd tracks; w / b: what the GEMM reads
+        y = torch.nn.functional.linear(x, w, b)
         ctx.save_for_backward(x, w)
-        ctx.meta = (weight.dtype, None if bias is None else bias.dtype)
+        ctx.meta = (weight.dtype, None if bias is None else bias.dtype, gw, gb)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        wdt, bdt = ctx.meta
+        wdt, bdt, gw, gb = ctx.meta
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
@@ -451,21 +534,52 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.mm(dy2, w).view(x.shape)
         if ctx.needs_input_grad[1]:
-            dw = torch.mm(dy2.t(), x2).to(wdt)
+            if gw is not None:
+                if dy2.dtype == torch.float32:
+                    torch.addmm(gw, dy2.t(), x2, out=gw)
+                else:
+                    torch.addmm(gw, dy2.t(), x2, out_dtype=torch.float32, out=gw)
+            else:
+                dw = torch.mm(dy2.t(), x2).to(wdt)
         if bdt is not None and ctx.needs_input_grad[2]:
-            db = colsum(dy2).to(bdt)
-        return dx, dw, db
+            if gb is not None:
+                colsum(dy2, out=gb)
+            else:
+                db = colsum(dy2).to(bdt)
+        return dx, dw, db, None, None, None, None
 
 
-def linear(x, weight, bias=None):
+def _rows(t, rows):
+    return t if t is None or rows is None else t[rows[0]:rows[1]]
+
+
+def _compute_copy(p, rows, dtype):
+    """what the GEMM reads for parameter p: the engine's bf16 shadow if there is one, else a cast."""
+    if p is None:
+        return None
+    lp = getattr(p, '_rsc_lp', None)
+    t = _rows(lp if lp is not None and lp.dtype == dtype else p.detach(), rows)
+    return t if t.dtype == dtype else t.to(dtype)
+
+
+def linear(x, weight, bias=None, rows=None):
     """F.linear in the active compute dtype; on CUDA (out_features % 4 == 0) the bias gradient comes
-    from rsc_colsum instead of a separate ATen reduction.  The GEMMs are library calls either way."""
-    if x.is_cuda and weight.shape[0] % 4 == 0 and (bias is not None):
+    from rsc_colsum instead of a separate ATen reduction.  The GEMMs are library calls either way.
+    `rows=(r0, r1)` applies only output rows r0:r1 of weight / bias (the q / k / v thirds of a packed
+    in_proj) without materialising slices of the master weights."""
+    n_out = weight.shape[0] if rows is None else rows[1] - rows[0]
+    if x.is_cuda and (bias is None or n_out % 4 == 0):
         if torch.is_autocast_enabled('cuda'):
             x = x.to(torch.get_autocast_dtype('cuda'))
         if x.dtype in (torch.float32, torch.bfloat16):
-            return _Linear.apply(x, weight, bias)
-    return torch.nn.functional.linear(x, weight, bias)
+            gw, gb = getattr(weight, '_rsc_g', None), getattr(bias, '_rsc_g', None)
+            if not torch.is_grad_enabled():
+                gw = gb = None
+            if rows is not None and (gw is None or (gb is None and bias is not None)):   # no engine: autograd slices
+                weight, bias, rows, gw, gb = _rows(weight, rows), _rows(bias, rows), None, None, None
+            return _Linear.apply(x, weight, bias, _compute_copy(weight, rows, x.dtype),
+                                 _compute_copy(bias, rows, x.dtype), _rows(gw, rows), _rows(gb, rows))
+    return torch.nn.functional.linear(x, _rows(weight, rows), _rows(bias, rows))
 
 
 KernelTimer = _lib.KernelTimer

@@ -38,7 +38,8 @@ def cpu_ops():
     ops.global_avg_pool = _gap
     ops.bilinear_resize = lambda x, size: F.interpolate(x, size=tuple(size), mode='bilinear', align_corners=False)
     ops.sigmoid_focal_loss = _focal
-    ops.linear = F.linear
+    ops.linear = lambda x, w, b=None, rows=None: F.linear(x, w if rows is None else w[rows[0]:rows[1]],
+                                                          b if rows is None or b is None else b[rows[0]:rows[1]])
     ops.layer_norm = lambda x, g, b, eps=1e-5, out_dtype=None: F.layer_norm(x, (x.shape[-1],), g, b, eps)
     try:
         yield

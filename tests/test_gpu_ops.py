@@ -361,3 +361,126 @@ def test_layernorm(rows, C, in_dt, out_dt):
     assert_rel(xg.grad, xo.grad, tol_g, 'dx')
     assert_rel(gg.grad, go.grad, 1e-4, 'dgamma')
     assert_rel(bg.grad, bo.grad, 1e-4, 'dbeta')
+
+
+# ---------------------------------------------------------------------------
+# a16: GPU Hungarian matching + fused detection losses
+# ---------------------------------------------------------------------------
+def _det_case(seed, L, B, Nq, ps, C, sizes, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    cls = (torch.randn(L, B, ps + Nq, C, generator=g) * 2 - 2).to(dtype)
+    cxcy = torch.rand(L, B, ps + Nq, 2, generator=g) * 0.8 + 0.1
+    wh = torch.rand(L, B, ps + Nq, 2, generator=g) * 0.3 + 0.02
+    box = torch.cat([cxcy, wh], -1)
+    shapes = [(640 + 32 * b, 800 - 16 * b, 3) for b in range(B)]
+    gtb, gtl = [], []
+    for b, n in enumerate(sizes):
+        h, w = shapes[b][:2]
+        x1, y1 = torch.rand(n, generator=g) * (w - 120), torch.rand(n, generator=g) * (h - 120)
+        bw, bh = torch.rand(n, generator=g) * 100 + 16, torch.rand(n, generator=g) * 100 + 16
+        gtb.append(torch.stack([x1, y1, x1 + bw, y1 + bh], -1))
+        gtl.append(torch.randint(0, C, (n,), generator=g))
+    return cls, box, gtb, gtl, [dict(img_shape=s) for s in shapes]
+
+
+@pytest.mark.parametrize('sizes', [(5, 3), (8,), (0, 4), (17, 1, 9)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_det_match_cost_and_assignment(sizes, dtype):
+    """cost matrix == mmdet's FocalLossCost + BBoxL1Cost + IoUCost (host-side HungarianAssigner.cost) and the
+    assignment == scipy.optimize.linear_sum_assignment on that matrix, for every (layer, image) problem."""
+    from scipy.optimize import linear_sum_assignment
+    from rscotr_b200.models.det_head import HungarianAssigner
+    ops = _ops()
+    L, B, Nq, ps, C = 3, len(sizes), 60, 12, 20
+    cls, box, gtb, gtl, metas = _det_case(11 + len(sizes), L, B, Nq, ps, C, sizes, dtype)
+    starts = [0]
+    for n in sizes:
+        starts.append(starts[-1] + n)
+    dev = 'cuda'
+    img_wh = torch.tensor([[m['img_shape'][1], m['img_shape'][0]] for m in metas], dtype=torch.float32, device=dev)
+    assign, cost, gt_norm = ops.det_match(cls.to(dev), box.to(dev), ps, Nq, torch.cat(gtl).to(dev), torch.cat(gtb).to(dev),
+                                          torch.tensor(starts, dtype=torch.int32, device=dev), img_wh, max(sizes))
+    assign, cost, gt_norm = assign.cpu().view(L, B, Nq), cost.cpu().view(L, B, max(sizes), Nq), gt_norm.cpu()
+    asg = HungarianAssigner()
+    for b, n in enumerate(sizes):
+        h, w = metas[b]['img_shape'][:2]
+        f = torch.tensor([w, h, w, h], dtype=torch.float32)
+        from rscotr_b200.models.det_head import bbox_xyxy_to_cxcywh
+        if n:
+            assert torch.allclose(gt_norm[starts[b]:starts[b + 1]], bbox_xyxy_to_cxcywh(gtb[b] / f), atol=1e-6)
+        for l in range(L):
+            want_cost = asg.cost(box[l, b, ps:], cls[l, b, ps:].float(), gtb[b], gtl[b], metas[b]['img_shape'])   # (Nq, n)
+            got_cost = cost[l, b, :n].t()
+            if n:
+                assert torch.allclose(got_cost, want_cost, rtol=1e-4, atol=2e-4), (got_cost - want_cost).abs().max()
+            r, c = linear_sum_assignment(got_cost.double().numpy()) if n else ([], [])
+            want = torch.full((Nq,), -1, dtype=torch.int32)
+            for ri, ci in zip(r, c):
+                want[ri] = starts[b] + ci
+            assert torch.equal(assign[l, b], want), (l, b)
+            r2, c2 = linear_sum_assignment(want_cost.double().numpy()) if n else ([], [])
+            assert float(got_cost[r, c].sum()) <= float(got_cost[r2, c2].sum()) + 1e-3 if n else True
+
+
+def test_det_match_large_problem():
+    """DIOR-scale problem: 600 queries x 120 boxes; the device assignment is optimal (same total cost as scipy)."""
+    from scipy.optimize import linear_sum_assignment
+    ops = _ops()
+    cls, box, gtb, gtl, metas = _det_case(3, 2, 1, 600, 0, 20, (120,))
+    dev = 'cuda'
+    img_wh = torch.tensor([[metas[0]['img_shape'][1], metas[0]['img_shape'][0]]], dtype=torch.float32, device=dev)
+    assign, cost, _ = ops.det_match(cls.to(dev), box.to(dev), 0, 600, gtl[0].to(dev), gtb[0].to(dev),
+                                    torch.tensor([0, 120], dtype=torch.int32, device=dev), img_wh, 120)
+    for l in range(2):
+        cm = cost[l].cpu().double().numpy()          # (120, 600)
+        r, c = linear_sum_assignment(cm)
+        a = assign[l].cpu()
+        cols = torch.nonzero(a >= 0).flatten()
+        assert len(cols) == 120 and sorted(a[cols].tolist()) == list(range(120))
+        got_total = sum(cm[int(a[j]), int(j)] for j in cols)
+        assert abs(got_total - cm[r, c].sum()) < 1e-6 * max(1.0, abs(cm[r, c].sum()))
+        want = torch.full((600,), -1, dtype=torch.int32)
+        want[torch.from_numpy(c)] = torch.from_numpy(r).int()
+        assert torch.equal(a, want)
+
+
+@pytest.mark.parametrize('sizes', [(5, 3), (0, 4), (6,)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_det_loss_fused_matches_aten_path(sizes, dtype):
+    """DINOHead.loss through rsc_det_match + rsc_det_loss_{fwd,bwd} == the ATen + scipy path (values and
+    gradients w.r.t. class logits and boxes), incl. the denoising part and an image without boxes."""
+    from rscotr_b200.models.det_head import DINOHead
+    from tests.test_host_parity import OCFG  # noqa: F401  (registers nothing, keeps import order)
+    import rscotr_b200.models  # noqa: F401
+    from rscotr_b200.config import Config
+    import os
+    cfg = Config.fromfile(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'configs', 'multi',
+                                       'cotrain_swin-t_800.py'))
+    hc = dict(cfg.model.bbox_head)
+    hc.pop('type')
+    hc.update(train_cfg=cfg.model.train_cfg.get('det'), test_cfg=cfg.model.test_cfg.get('det'), num_query=40)
+    torch.manual_seed(0)
+    head = DINOHead(**hc).cuda()
+    L, B, C = 6, len(sizes), head.num_classes
+    num_groups = max(1, 10 // max(max(sizes), 1))
+    ps = max(sizes) * 2 * num_groups
+    Nq = 40
+    cls, box, gtb, gtl, metas = _det_case(5, L, B, Nq, ps, C, sizes, dtype)
+    ecls, ebox, _, _, _ = _det_case(6, 1, B, Nq, 0, C, sizes, dtype)
+    dn_meta = dict(pad_size=ps, num_dn_group=num_groups)
+    outs = {}
+    for fused in (False, True):
+        head.fused_loss = fused
+        ins = [t.clone().cuda().requires_grad_(True) for t in (cls, box, ecls[0], ebox[0])]
+        losses = head.loss(ins[0], ins[1], ins[2], ins[3], [t.cuda() for t in gtb], [t.cuda() for t in gtl], metas, dn_meta)
+        keys = list(losses.keys())
+        total = sum((i + 1) * 0.37 * losses[k] for i, k in enumerate(keys))     # distinct upstream gradient per term
+        total.backward()
+        outs[fused] = ({k: float(losses[k]) for k in keys}, [t.grad.float().cpu() for t in ins])
+    assert list(outs[True][0].keys()) == list(outs[False][0].keys())
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    for k, v in outs[False][0].items():
+        assert abs(outs[True][0][k] - v) <= tol * max(1.0, abs(v)), (k, outs[True][0][k], v)
+    for i, (g, w) in enumerate(zip(outs[True][1], outs[False][1])):
+        e = float((g - w).norm() / w.norm().clamp_min(1e-12))
+        assert e <= (1e-4 if dtype == torch.float32 else 2e-2), (i, e)
