@@ -217,6 +217,22 @@ int rsc_det_loss_bwd(const void *cls, const float *box, const int *assign, const
                      float w_l1, float w_iou, float eps, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Fused bilinear up-sampling (align_corners=False) + softmax cross-entropy
+ * (SURVEY 8a row a19, 8f rank 2).  Replaces mmseg 0.28 BaseDecodeHead.losses
+ * (resize(seg_logit, label size) + CrossEntropyLoss(ignore_index) + accuracy) called at
+ * models/multi/seg_head/mask2former_head.py:204; the up-sampled (B,C,H,W) logits are
+ * never materialised.  logits (B,C,h,w) `dtype`, label (B,H,W) int64, H >= h, W >= w,
+ * scale <= 9.5.  fwd: stats[3] += {sum over non-ignored pixels of CE, #pixels whose
+ * argmax == label, #non-ignored pixels}; lse (B,H,W) fp32 receives logsumexp per pixel
+ * (+inf on ignored pixels) for the backward.  bwd: dlogits = gscale[0] *
+ * d(sum CE)/d(logits), gscale a DEVICE float (upstream gradient x loss weight / #pixels).
+ * ---------------------------------------------------------------------- */
+int rsc_upsample_ce_fwd(const void *logits, const int64_t *label, float *lse, float *stats, int B, int C, int h, int w,
+                        int H, int W, int ignore_index, int dtype, void *stream);
+int rsc_upsample_ce_bwd(const void *logits, const int64_t *label, const float *lse, const float *gscale, void *dlogits,
+                        int B, int C, int h, int w, int H, int W, int dtype, void *stream);
+
+/* ------------------------------------------------------------------------
  * Flat fused AdamW (+ gradient-clip scale).  Replaces mmcv OptimizerHook's
  * clip_grad_norm_ scaling + torch.optim.AdamW.step over one contiguous fp32 range
  * (optimizer built by mtl/utils/optimizer.py:25-55).

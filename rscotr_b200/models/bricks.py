@@ -35,6 +35,25 @@ def const_tensor(values, dtype, device):
     return t
 
 
+class GeomCache:
+    """Small shape-keyed cache of no-grad geometry constants of a head (padding masks, sine positional
+    encodings, reference points, proposal grids ...).  The reference recomputes them with ~25-80 tiny
+    kernels each on every iteration although they only depend on the image / feature-map shapes."""
+
+    def __init__(self, capacity=8):
+        self.capacity, self.entries = capacity, {}
+
+    def get(self, key, make):
+        v = self.entries.get(key)
+        if v is None:
+            with torch.no_grad():
+                v = make()
+            if len(self.entries) >= self.capacity:
+                self.entries.pop(next(iter(self.entries)))
+            self.entries[key] = v
+        return v
+
+
 class PackedLosses(dict):
     """A loss dict (name -> scalar tensor, the reference's contract) whose values are the elements of ONE
     packed 1-D tensor: a fused loss kernel returns all its terms at once, MTL._parse_losses sums `packed`

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS, build_from_cfg
-from .bricks import (LayerNorm, Linear, PackedLosses, TransformerLayerSequence, const_tensor, MultiScaleDeformableAttention, build_positional_encoding,
+from .bricks import (GeomCache, LayerNorm, Linear, PackedLosses, TransformerLayerSequence, const_tensor, MultiScaleDeformableAttention, build_positional_encoding,
                      build_transformer_layer_sequence, inverse_sigmoid)
 
 
@@ -173,8 +173,12 @@ class DinoTransformer(nn.Module):
         reference_points = torch.cat(ref_list, 1)
         return reference_points[:, :, None] * valid_ratios[:, None]
 
-    def gen_encoder_output_proposals(self, memory, memory_padding_mask, spatial_shapes):
-        N, S, C = memory.shape
+    @staticmethod
+    def proposal_grid(memory_padding_mask, spatial_shapes):
+        """the memory-independent half of gen_encoder_output_proposals: (output_proposals with inf at padded /
+        invalid positions, drop mask (N,S,1) = padded | invalid)."""
+        N = memory_padding_mask.shape[0]
+        dev = memory_padding_mask.device
         proposals = []
         _cur = 0
         for lvl, (H, W) in enumerate(spatial_shapes):
@@ -182,8 +186,8 @@ class DinoTransformer(nn.Module):
             valid_H = torch.sum(~mask_flatten_[:, :, 0, 0], 1)
             valid_W = torch.sum(~mask_flatten_[:, 0, :, 0], 1)
             grid_y, grid_x = torch.meshgrid(
-                torch.linspace(0, H - 1, H, dtype=torch.float32, device=memory.device),
-                torch.linspace(0, W - 1, W, dtype=torch.float32, device=memory.device), indexing='ij')
+                torch.linspace(0, H - 1, H, dtype=torch.float32, device=dev),
+                torch.linspace(0, W - 1, W, dtype=torch.float32, device=dev), indexing='ij')
             grid = torch.cat([grid_x.unsqueeze(-1), grid_y.unsqueeze(-1)], -1)
             scale = torch.cat([valid_W.unsqueeze(-1), valid_H.unsqueeze(-1)], 1).view(N, 1, 1, 2)
             grid = (grid.unsqueeze(0).expand(N, -1, -1, -1) + 0.5) / scale
@@ -195,30 +199,45 @@ class DinoTransformer(nn.Module):
         output_proposals = torch.log(output_proposals / (1 - output_proposals))
         output_proposals = output_proposals.masked_fill(memory_padding_mask.unsqueeze(-1), float('inf'))
         output_proposals = output_proposals.masked_fill(~output_proposals_valid, float('inf'))
-        output_memory = memory.masked_fill(memory_padding_mask.unsqueeze(-1), float(0))
-        output_memory = output_memory.masked_fill(~output_proposals_valid, float(0))
+        return output_proposals, memory_padding_mask.unsqueeze(-1) | ~output_proposals_valid
+
+    def gen_encoder_output_proposals(self, memory, memory_padding_mask, spatial_shapes, grid=None):
+        output_proposals, drop = grid if grid is not None else self.proposal_grid(memory_padding_mask, spatial_shapes)
+        output_memory = memory.masked_fill(drop, float(0))
         output_memory = self.enc_output_norm(self.enc_output(output_memory))
         return output_memory, output_proposals
+
+    def _geometry(self, mlvl_masks, mlvl_pos_embeds, shapes_py, device):
+        """everything of forward() that depends only on the masks / shapes (cached by GeomCache)."""
+        mask_flatten = torch.cat([m.flatten(1) for m in mlvl_masks], 1)
+        pos_flatten = torch.cat([p.flatten(2).transpose(1, 2) for p in mlvl_pos_embeds], 1)
+        lvl_index = torch.cat([torch.full((h * w,), i, dtype=torch.long, device=device)
+                               for i, (h, w) in enumerate(shapes_py)])
+        spatial_shapes = const_tensor(shapes_py, torch.long, device)
+        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in mlvl_masks], 1)
+        reference_points = self.get_reference_points(shapes_py, valid_ratios, device=device)
+        grid = self.proposal_grid(mask_flatten, shapes_py)
+        return dict(masks=list(mlvl_masks), mask_flatten=mask_flatten, pos_flatten=pos_flatten, lvl_index=lvl_index,
+                    spatial_shapes=spatial_shapes, level_start_index=level_start_index, valid_ratios=valid_ratios,
+                    reference_points=reference_points, grid=grid)
 
     def forward(self, mlvl_feats, mlvl_masks, query_embed, mlvl_pos_embeds, dn_label_query, dn_bbox_query, attn_mask,
                 encoder, reg_branches=None, cls_branches=None, **kwargs):
         assert self.as_two_stage and query_embed is None, 'as_two_stage must be True for DINO'
-        feat_flatten, mask_flatten, lvl_pos_embed_flatten, spatial_shapes = [], [], [], []
-        for lvl, (feat, mask, pos_embed) in enumerate(zip(mlvl_feats, mlvl_masks, mlvl_pos_embeds)):
-            bs, c, h, w = feat.shape
-            spatial_shapes.append((h, w))
-            feat_flatten.append(feat.flatten(2).transpose(1, 2))
-            mask_flatten.append(mask.flatten(1))
-            pos_embed = pos_embed.flatten(2).transpose(1, 2)
-            lvl_pos_embed_flatten.append(pos_embed + self.level_embeds[lvl].view(1, 1, -1))
-        feat_flatten = torch.cat(feat_flatten, 1)
-        mask_flatten = torch.cat(mask_flatten, 1)
-        lvl_pos_embed_flatten = torch.cat(lvl_pos_embed_flatten, 1)
-        shapes_py = spatial_shapes
-        spatial_shapes = const_tensor(spatial_shapes, torch.long, feat_flatten.device)
-        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
-        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in mlvl_masks], 1)
-        reference_points = self.get_reference_points(shapes_py, valid_ratios, device=feat_flatten.device)
+        shapes_py = [tuple(f.shape[-2:]) for f in mlvl_feats]
+        dev = mlvl_feats[0].device
+        # the masks come out of the head's own cache, so their identity is a valid key (the entry keeps them alive)
+        key = (tuple(id(m) for m in mlvl_masks), tuple(id(p) for p in mlvl_pos_embeds), tuple(shapes_py))
+        if not hasattr(self, '_geom'):
+            self._geom = GeomCache()
+        geo = self._geom.get(key, lambda: dict(self._geometry(mlvl_masks, mlvl_pos_embeds, shapes_py, dev),
+                                               pos=list(mlvl_pos_embeds)))
+        feat_flatten = torch.cat([feat.flatten(2).transpose(1, 2) for feat in mlvl_feats], 1)
+        mask_flatten, spatial_shapes = geo['mask_flatten'], geo['spatial_shapes']
+        lvl_pos_embed_flatten = geo['pos_flatten'] + self.level_embeds[geo['lvl_index']].unsqueeze(0)
+        level_start_index, valid_ratios = geo['level_start_index'], geo['valid_ratios']
+        reference_points = geo['reference_points']
 
         feat_flatten = feat_flatten.permute(1, 0, 2)
         lvl_pos_embed_flatten = lvl_pos_embed_flatten.permute(1, 0, 2)
@@ -229,7 +248,8 @@ class DinoTransformer(nn.Module):
         memory = memory.permute(1, 0, 2)
         bs, _, c = memory.shape
 
-        output_memory, output_proposals = self.gen_encoder_output_proposals(memory, mask_flatten, shapes_py)
+        output_memory, output_proposals = self.gen_encoder_output_proposals(memory, mask_flatten, shapes_py,
+                                                                            grid=geo['grid'])
         enc_outputs_class = cls_branches[self.decoder.num_layers](output_memory)
         enc_outputs_coord_unact = reg_branches[self.decoder.num_layers](output_memory).float() + output_proposals
         cls_out_features = cls_branches[self.decoder.num_layers].out_features
@@ -567,14 +587,22 @@ class DINOHead(nn.Module):
     def forward(self, encoder, mlvl_feats, img_metas, dn_label_query=None, dn_bbox_query=None, attn_mask=None):
         batch_size = mlvl_feats[0].size(0)
         input_img_h, input_img_w = img_metas[0]['batch_input_shape']
-        img_masks = mlvl_feats[0].new_ones((batch_size, input_img_h, input_img_w), dtype=torch.float32)
-        for img_id in range(batch_size):
-            img_h, img_w, _ = img_metas[img_id]['img_shape']
-            img_masks[img_id, :img_h, :img_w] = 0
-        mlvl_masks, mlvl_positional_encodings = [], []
-        for feat in mlvl_feats:
-            mlvl_masks.append(F.interpolate(img_masks[None], size=feat.shape[-2:]).to(torch.bool).squeeze(0))
-            mlvl_positional_encodings.append(self.positional_encoding(mlvl_masks[-1]))
+
+        def make():
+            img_masks = mlvl_feats[0].new_ones((batch_size, input_img_h, input_img_w), dtype=torch.float32)
+            for img_id in range(batch_size):
+                img_h, img_w, _ = img_metas[img_id]['img_shape']
+                img_masks[img_id, :img_h, :img_w] = 0
+            masks, pes = [], []
+            for feat in mlvl_feats:
+                masks.append(F.interpolate(img_masks[None], size=feat.shape[-2:]).to(torch.bool).squeeze(0))
+                pes.append(self.positional_encoding(masks[-1]))
+            return masks, pes
+        key = (tuple(tuple(m['img_shape'][:2]) for m in img_metas), (input_img_h, input_img_w),
+               tuple(tuple(f.shape[-2:]) for f in mlvl_feats), str(mlvl_feats[0].device))
+        if not hasattr(self, '_geom'):
+            self._geom = GeomCache()
+        mlvl_masks, mlvl_positional_encodings = self._geom.get(key, make)
         hs, inter_references, topk_score, topk_anchor = self.transformer(
             mlvl_feats, mlvl_masks, None, mlvl_positional_encodings, dn_label_query, dn_bbox_query, attn_mask, encoder,
             reg_branches=self.reg_branches if self.with_box_refine else None,

@@ -9,7 +9,8 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS, build_from_cfg
-from .bricks import Linear, ConvModule, build_positional_encoding, build_transformer_layer_sequence, const_tensor
+from .bricks import (GeomCache, Linear, ConvModule, build_positional_encoding, build_transformer_layer_sequence,
+                     const_tensor)
 
 
 def resize(input, size=None, mode='bilinear', align_corners=False):
@@ -58,37 +59,43 @@ class MlvlSegPixelDecoder(nn.Module):
 
     def forward(self, encoder, neck_feats, backbone_feats):
         batch_size = backbone_feats[0].shape[0]
-        encoder_input_list, padding_mask_list, level_pos_list, spatial_shapes, reference_points_list = [], [], [], [], []
-        for i in range(self.num_encoder_levels):
-            level_idx = self.num_input_levels - i - 1
-            feat_projected = neck_feats[level_idx]
-            h, w = feat_projected.shape[-2:]
-            padding_mask_resized = feat_projected.new_zeros((batch_size, h, w), dtype=torch.bool)
-            pos_embed = self.postional_encoding(padding_mask_resized)
-            level_pos_embed = self.level_encoding.weight[i].view(1, -1, 1, 1) + pos_embed
-            # MlvlPointGenerator.single_level_grid_priors / (w*stride, h*stride)
-            dev = feat_projected.device
-            sx = (torch.arange(w, device=dev, dtype=torch.float32) + 0.5) * self.strides[level_idx]
-            sy = (torch.arange(h, device=dev, dtype=torch.float32) + 0.5) * self.strides[level_idx]
-            yy, xx = torch.meshgrid(sy, sx, indexing='ij')
-            reference_points = torch.stack([xx.reshape(-1), yy.reshape(-1)], -1)
-            reference_points = reference_points / const_tensor(
-                [[float(w * self.strides[level_idx]), float(h * self.strides[level_idx])]], torch.float32, dev)
-            encoder_input_list.append(feat_projected.flatten(2).permute(2, 0, 1))
-            padding_mask_list.append(padding_mask_resized.flatten(1))
-            level_pos_list.append(level_pos_embed.flatten(2).permute(2, 0, 1))
-            spatial_shapes.append((h, w))
-            reference_points_list.append(reference_points)
-        padding_masks = torch.cat(padding_mask_list, dim=1)
-        encoder_inputs = torch.cat(encoder_input_list, dim=0)
-        level_positional_encodings = torch.cat(level_pos_list, dim=0)
-        device = encoder_inputs.device
-        shapes_py = spatial_shapes
-        spatial_shapes = const_tensor(spatial_shapes, torch.long, device)
-        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
-        reference_points = torch.cat(reference_points_list, dim=0)
-        reference_points = reference_points[None, :, None].repeat(batch_size, 1, self.num_encoder_levels, 1)
-        valid_radios = reference_points.new_ones((batch_size, self.num_encoder_levels, 2))
+        dev = neck_feats[0].device
+        levels = [self.num_input_levels - i - 1 for i in range(self.num_encoder_levels)]
+        shapes_py = [tuple(neck_feats[l].shape[-2:]) for l in levels]
+
+        def make():
+            """shape-only constants: all-false padding masks, sine encodings, reference points, level index"""
+            padding_mask_list, pos_list, reference_points_list, lvl_index = [], [], [], []
+            for i, level_idx in enumerate(levels):
+                h, w = shapes_py[i]
+                padding_mask_resized = torch.zeros((batch_size, h, w), dtype=torch.bool, device=dev)
+                pos_list.append(self.postional_encoding(padding_mask_resized).flatten(2).permute(2, 0, 1))
+                # MlvlPointGenerator.single_level_grid_priors / (w*stride, h*stride)
+                sx = (torch.arange(w, device=dev, dtype=torch.float32) + 0.5) * self.strides[level_idx]
+                sy = (torch.arange(h, device=dev, dtype=torch.float32) + 0.5) * self.strides[level_idx]
+                yy, xx = torch.meshgrid(sy, sx, indexing='ij')
+                reference_points = torch.stack([xx.reshape(-1), yy.reshape(-1)], -1)
+                reference_points_list.append(reference_points / const_tensor(
+                    [[float(w * self.strides[level_idx]), float(h * self.strides[level_idx])]], torch.float32, dev))
+                padding_mask_list.append(padding_mask_resized.flatten(1))
+                lvl_index.append(torch.full((h * w,), i, dtype=torch.long, device=dev))
+            spatial_shapes = const_tensor(shapes_py, torch.long, dev)
+            reference_points = torch.cat(reference_points_list, dim=0)
+            reference_points = reference_points[None, :, None].repeat(batch_size, 1, self.num_encoder_levels, 1)
+            return dict(padding_masks=torch.cat(padding_mask_list, dim=1), pos=torch.cat(pos_list, dim=0),
+                        lvl_index=torch.cat(lvl_index), spatial_shapes=spatial_shapes,
+                        level_start_index=torch.cat((spatial_shapes.new_zeros((1,)),
+                                                     spatial_shapes.prod(1).cumsum(0)[:-1])),
+                        reference_points=reference_points,
+                        valid_radios=reference_points.new_ones((batch_size, self.num_encoder_levels, 2)))
+        if not hasattr(self, '_geom'):
+            self._geom = GeomCache()
+        geo = self._geom.get((batch_size, tuple(shapes_py), str(dev)), make)
+        encoder_inputs = torch.cat([neck_feats[l].flatten(2).permute(2, 0, 1) for l in levels], dim=0)
+        level_positional_encodings = geo['pos'] + self.level_encoding.weight[geo['lvl_index']].unsqueeze(1)
+        padding_masks, spatial_shapes = geo['padding_masks'], geo['spatial_shapes']
+        level_start_index, reference_points, valid_radios = geo['level_start_index'], geo['reference_points'], \
+            geo['valid_radios']
         memory = encoder(query=encoder_inputs, key=None, value=None, query_pos=level_positional_encodings,
                          key_pos=None, attn_masks=None, key_padding_mask=None, query_key_padding_mask=padding_masks,
                          spatial_shapes=spatial_shapes, reference_points=reference_points,
@@ -174,15 +181,20 @@ class Mask2FormerHead(nn.Module):
     def forward(self, encoder, neck_feats, backbone_feats, img_metas):
         batch_size = len(img_metas)
         mask_features, multi_scale_memorys = self.pixel_decoder(encoder, neck_feats, backbone_feats)
-        decoder_inputs, decoder_positional_encodings = [], []
+        decoder_inputs = []
+        shapes = tuple(tuple(m.shape[-2:]) for m in multi_scale_memorys[:self.num_transformer_feat_level])
+        dev = mask_features.device
+
+        def make():
+            return [self.decoder_positional_encoding(torch.zeros((batch_size,) + hw, dtype=torch.bool, device=dev))
+                    .flatten(2).permute(2, 0, 1) for hw in shapes]
+        if not hasattr(self, '_geom'):
+            self._geom = GeomCache()
+        decoder_positional_encodings = self._geom.get((batch_size, shapes, str(dev)), make)
         for i in range(self.num_transformer_feat_level):
             decoder_input = self.decoder_input_projs[i](multi_scale_memorys[i])
             decoder_input = decoder_input.flatten(2).permute(2, 0, 1)
-            decoder_input = decoder_input + self.level_embed.weight[i].view(1, 1, -1)
-            mask = decoder_input.new_zeros((batch_size,) + multi_scale_memorys[i].shape[-2:], dtype=torch.bool)
-            pe = self.decoder_positional_encoding(mask).flatten(2).permute(2, 0, 1)
-            decoder_inputs.append(decoder_input)
-            decoder_positional_encodings.append(pe)
+            decoder_inputs.append(decoder_input + self.level_embed.weight[i].view(1, 1, -1))
         query_feat = self.query_feat.weight.unsqueeze(1).repeat((1, batch_size, 1))
         query_embed = self.query_embed.weight.unsqueeze(1).repeat((1, batch_size, 1))
         mask_pred, attn_mask = self.forward_head(query_feat, mask_features, multi_scale_memorys[0].shape[-2:])
@@ -204,6 +216,12 @@ class Mask2FormerHead(nn.Module):
         """mmseg BaseDecodeHead.losses: bilinear resize to the label size, CE mean over all
         pixels (ignore_index contributes 0), top-1 accuracy over non-ignored pixels."""
         loss = dict()
+        if ops.upsample_ce_supported(seg_logit, seg_label):
+            # fused: the (B,C,H,W) up-sampled logits are never materialised (rsc_upsample_ce_{fwd,bwd})
+            stats = ops.upsample_ce(seg_logit, seg_label.squeeze(1), self.ignore_index)
+            loss['loss_ce'] = stats[0] * (self.loss_weight / seg_label.numel())
+            loss['acc_seg'] = stats[1].detach() * (100.0 / stats[2].detach().clamp(min=1))
+            return loss
         seg_logit = resize(seg_logit, size=seg_label.shape[2:])
         seg_label = seg_label.squeeze(1)
         ce = F.cross_entropy(seg_logit.float(), seg_label, reduction='none', ignore_index=self.ignore_index)

@@ -492,6 +492,52 @@ def det_loss(segs, tensors, rows, gt_labels, gt_norm, img_wh, cls_factor, pos_fa
 
 
 # ---------------------------------------------------------------------------
+# fused bilinear upsample + cross-entropy        
+# ---------------------------------------------------------------------------
+class _UpsampleCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, label, ignore_index):
+        _cuda(logits, label)
+        logits, label = logits.contiguous(), label.contiguous()
+        B, C, h, w = logits.shape
+        H, W = label.shape[-2:]
+        stats = torch.zeros(3, dtype=torch.float32, device=logits.device)
+        lse = torch.empty(B, H, W, dtype=torch.float32, device=logits.device)
+        with torch.cuda.device(logits.device):
+            call('rsc_upsample_ce_fwd', logits.data_ptr(), label.data_ptr(), lse.data_ptr(), stats.data_ptr(), B, C, h,
+                 w, H, W, int(ignore_index), _dt(logits), _stream(),
+                 alg_bytes=logits.numel() * logits.element_size() + label.numel() * 8 + lse.numel() * 4)
+        ctx.save_for_backward(logits, label, lse)
+        return stats
+
+    @staticmethod
+    def backward(ctx, dstats):
+        logits, label, lse = ctx.saved_tensors
+        B, C, h, w = logits.shape
+        H, W = label.shape[-2:]
+        g = dstats[:1].float().contiguous()
+        dlogits = torch.empty_like(logits)
+        with torch.cuda.device(logits.device):
+            call('rsc_upsample_ce_bwd', logits.data_ptr(), label.data_ptr(), lse.data_ptr(), g.data_ptr(),
+                 dlogits.data_ptr(), B, C, h, w, H, W, _dt(logits), _stream(),
+                 alg_bytes=2 * logits.numel() * logits.element_size() + label.numel() * 8 + lse.numel() * 4)
+        return dlogits, None, None
+
+
+def upsample_ce(logits, label, ignore_index=255):
+    """logits (B,C,h,w), label (B,H,W) int64 -> stats (3,) = [sum of CE over non-ignored pixels of the
+    bilinearly (align_corners=False) up-sampled logits, #correct (argmax == label), #non-ignored]."""
+    return _UpsampleCE.apply(logits, label, ignore_index)
+
+
+def upsample_ce_supported(logits, label):
+    h, w = logits.shape[-2:]
+    H, W = label.shape[-2:]
+    return logits.is_cuda and H >= h and W >= w and 2.0 * H / h + 5 <= 24 and 2.0 * W / w + 5 <= 24 and \
+        logits.dtype in (torch.float32, torch.bfloat16)
+
+
+# ---------------------------------------------------------------------------
 # Linear with the bias gradient on rsc_colsum        (GEMMs stay in the library)
 # ---------------------------------------------------------------------------
 def colsum(x2d, out=None):

@@ -484,3 +484,32 @@ def test_det_loss_fused_matches_aten_path(sizes, dtype):
     for i, (g, w) in enumerate(zip(outs[True][1], outs[False][1])):
         e = float((g - w).norm() / w.norm().clamp_min(1e-12))
         assert e <= (1e-4 if dtype == torch.float32 else 2e-2), (i, e)
+
+
+# ---------------------------------------------------------------------------
+# a19: fused bilinear upsample + cross-entropy
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(2, 7, 13, 10, 104, 80), (1, 100, 25, 25, 200, 200), (2, 5, 10, 9, 37, 50),
+                                   (1, 33, 12, 12, 12, 12), (1, 3, 1, 1, 8, 8)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_upsample_ce_matches_interpolate_cross_entropy(shape, dtype):
+    ops = _ops()
+    B, C, h, w, H, W = shape
+    g = torch.Generator().manual_seed(H + C)
+    logits = (torch.randn(B, C, h, w, generator=g) * 3).to(dtype)
+    label = torch.randint(0, C, (B, H, W), generator=g)
+    label[torch.rand(B, H, W, generator=g) < 0.1] = 255
+    ref_in = logits.float().clone().requires_grad_(True)
+    up = F.interpolate(ref_in, size=(H, W), mode='bilinear', align_corners=False)
+    ce = F.cross_entropy(up, label, reduction='sum', ignore_index=255)
+    (ce * 0.37).backward()
+    valid = label != 255
+    correct = ((up.argmax(1) == label) & valid).sum()
+    x = logits.cuda().requires_grad_(True)
+    assert ops.upsample_ce_supported(x, label.cuda())
+    stats = ops.upsample_ce(x, label.cuda(), 255)
+    (stats[0] * 0.37).backward()
+    assert abs(float(stats[0]) - float(ce)) <= 2e-5 * abs(float(ce)) + 1e-3
+    assert int(stats[2]) == int(valid.sum())
+    assert abs(int(stats[1]) - int(correct)) <= (0 if dtype == torch.float32 else 2) + int(1e-4 * valid.sum())
+    assert_rel(x.grad, ref_in.grad, 1e-4 if dtype == torch.float32 else 6e-3, 'dlogits')
