@@ -264,11 +264,16 @@ def main():
         dist.init_process_group('nccl', device_id=device)
     assert world == args.gpus, 'launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)' % (args.gpus, world)
 
+    T0 = time.time()
     cfg, model, engine, loader = build(args.config, args.dtype, device)
     it = iter(loader)
     host_batches = [next(it) for _ in range(6)]                  # 2 distinct batches per task, pinned host memory
     dev_batches = [_to_device(b, device) for b in host_batches]
     torch.cuda.synchronize()
+
+    def trace(msg):
+        if os.environ.get('RSC_BENCH_TRACE'):
+            print('[bench rank %d %.1fs] %s' % (rank, time.time() - T0, msg), file=sys.stderr, flush=True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -280,7 +285,11 @@ def main():
     # (with CUDA graphs every task needs 2 eager iterations + the capturing one before the timed region)
     n_warm = max(args.warmup, 9 if engine.use_graphs else 3)
     for i in range(n_warm):
+        trace('warm-up step %d (%s)' % (i, dev_batches[i % 6]['task']))
         engine.train_iter(dev_batches[i % 6])
+        if os.environ.get('RSC_BENCH_TRACE'):
+            torch.cuda.synchronize()
+    trace('warm-up done')
     barrier()
 
     # ---- timed region A: inputs resident in HBM
@@ -302,7 +311,9 @@ def main():
         b.record()
         evs.append((dev_batches[i % 6]['task'], a, b))
     e1.record()
+    trace('timed region A enqueued')
     barrier()
+    trace('timed region A done')
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count() + engine.replayed_launches      # eager launches + launches inside graph replays
     for t, a, b in evs:
@@ -314,6 +325,7 @@ def main():
         for i in range(6):
             engine.train_iter(dev_batches[i % 6])
         ksum = kt.summary()
+    trace('kernel-timer pass done')
     kscale = args.steps / 6.0                                       # normalise kernel ms to the timed region's steps
     for d in ksum.values():
         for k in ('ms', 'bytes', 'big_ms', 'big_bytes'):
@@ -334,6 +346,7 @@ def main():
         db += 4
     f1.record()
     barrier()
+    trace('timed region B done')
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -341,10 +354,26 @@ def main():
         t = torch.tensor([ms, ms_e2e], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
-    if rank != 0:
+    def finish():
+        """Leave together: tearing NCCL down while captured collectives are alive (or while a peer has already
+        gone) can block or abort, so drop the graphs, meet at a barrier AFTER rank 0 has printed, give
+        destroy_process_group a bounded chance and exit."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
-        return
+            import gc
+            engine._graphs.clear()
+            gc.collect()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+            th.start()
+            th.join(15.0)
+            os._exit(0)
+
+    if rank != 0:
+        return finish()
 
     value = world * args.steps / (ms / 1000.0)                   # whole-job iterations (one per rank per step)
     e2e = world * args.steps / (ms_e2e / 1000.0)
@@ -390,8 +419,7 @@ def main():
         torch.cuda.empty_cache()
         out['cpu_baseline'] = cpu_baseline(cfg)
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == '__main__':

@@ -235,14 +235,15 @@ class MTL(nn.Module):
 
     @staticmethod
     def _reduce_log_vars(keys, packed):
+        """cross-rank mean of the log values with ONE packed all-reduce (reference: one all_reduce per log
+        var, multitask_learner.py:289-304).  The reference's "same number of log vars on every rank" assertion
+        rides along as element 0 and is checked when the values are read on the host (_LazyLogVars), so the
+        step stays free of host syncs and CUDA-graph capturable."""
         if dist.is_available() and dist.is_initialized():
-            n = torch.cat([packed.new_tensor([float(len(keys))]), packed])
-            dist.all_reduce(n)
             world = dist.get_world_size()
-            assert int(round(float(n[0]))) == len(keys) * world, \
-                'loss log variables are different across GPUs!\nrank %d len(log_vars): %d keys: %s' % (
-                    dist.get_rank(), len(keys), ','.join(keys))
-            packed = n[1:] / world
+            n = torch.cat([const_tensor([float(len(keys))], torch.float32, packed.device), packed])
+            dist.all_reduce(n)
+            return n / world
         return packed
 
     def load_task_pretrain(self):
@@ -281,6 +282,11 @@ class _LazyLogVars(OrderedDict):
     def _materialise(self):
         if not self._done:
             vals = self._packed.tolist()
+            if len(vals) == len(self._keys) + 1:      # distributed: element 0 = mean number of log vars
+                assert int(round(vals[0])) == len(self._keys), \
+                    'loss log variables are different across GPUs!\nlen(log_vars): %d keys: %s' % (
+                        len(self._keys), ','.join(self._keys))
+                vals = vals[1:]
             for k, v in zip(self._keys, vals):
                 OrderedDict.__setitem__(self, k, v * self._weight)
             self._done = True
