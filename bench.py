@@ -256,6 +256,10 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank = int(os.environ.get('RANK', 0))
     local = int(os.environ.get('LOCAL_RANK', 0))
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local)
@@ -418,7 +422,8 @@ def main():
         del engine, model, dev_batches
         torch.cuda.empty_cache()
         out['cpu_baseline'] = cpu_baseline(cfg)
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + '\n').encode())
     finish()
 
 
