@@ -233,6 +233,30 @@ int rsc_upsample_ce_bwd(const void *logits, const int64_t *label, const float *l
                         int B, int C, int h, int w, int H, int W, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Fused residual-stream passes of the Swin block (mmdet 2.25.1
+ * SwinBlock.forward: x = x + DropPath(attn(LN(x))); x = x + DropPath(FFN(LN(x)))).
+ * rsc_add_ln_fwd:  r = identity + (x + bias) * scale[row / rows_per_sample];
+ *                  n = LayerNorm(r; gamma, beta, eps); mean / rstd saved per row.
+ *   identity, x, r_out, n_out: (rows, C) `dtype`; bias (C) and scale (samples) are fp32
+ *   and may be NULL; C in {96,192,384,768,128,256,512,1024} (rsc_add_ln_supported).
+ * rsc_add_ln_bwd:  dr = dr_ext + LayerNormBackward(dn)  -> d_identity;
+ *                  dx = dr * scale (written only when dx != NULL; dx == NULL means dx = dr);
+ *                  dbias += column sums of dx; dgamma / dbeta accumulated (all fp32).
+ * rsc_bias_gelu_fwd: y = gelu(h + bias), exact erf form (torch.nn.GELU default).
+ * rsc_bias_gelu_bwd: dh = dy * gelu'(h + bias); dbias += column sums of dh.
+ * ---------------------------------------------------------------------- */
+int rsc_add_ln_supported(int C);
+int rsc_add_ln_fwd(const void *identity, const void *x, const float *bias, const float *scale, const float *gamma,
+                   const float *beta, void *r_out, void *n_out, float *mean, float *rstd, int64_t rows,
+                   int64_t rows_per_sample, int C, float eps, int dtype, void *stream);
+int rsc_add_ln_bwd(const void *r, const float *gamma, const float *mean, const float *rstd, const void *dn,
+                   const void *dr_ext, const float *scale, void *d_identity, void *dx, float *dgamma, float *dbeta,
+                   float *dbias, int64_t rows, int64_t rows_per_sample, int C, int dtype, void *stream);
+int rsc_bias_gelu_fwd(const void *h, const float *bias, void *y, int64_t rows, int C, int dtype, void *stream);
+int rsc_bias_gelu_bwd(const void *h, const float *bias, const void *dy, void *dh, float *dbias, int64_t rows, int C,
+                      int dtype, void *stream);
+
+/* ------------------------------------------------------------------------
  * Flat fused AdamW (+ gradient-clip scale).  Replaces mmcv OptimizerHook's
  * clip_grad_norm_ scaling + torch.optim.AdamW.step over one contiguous fp32 range
  * (optimizer built by mtl/utils/optimizer.py:25-55).

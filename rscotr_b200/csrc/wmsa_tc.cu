@@ -43,6 +43,41 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t *>(&v);
 }
 
+constexpr float LOG2E = 1.4426950408889634f;
+
+// softmax numerator row in the exp2 domain: sv[j] = S[j]*scale*log2e + bias2[j] (+ mask), returns the row max
+template <bool MASK>
+__device__ __forceinline__ float score_row(const uint32_t (&s0)[32], const uint32_t (&s1)[32], const float *tb,
+                                           float scale2, uint32_t rowbits, uint32_t colbits, float (&sv)[NT]) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int jr = j / WS, jc = j % WS;
+    float s = fmaf(__uint_as_float(j < 32 ? s0[j] : s1[j - 32]), scale2, tb[-(jr * (2 * WS - 1) + jc)]);
+    if (MASK) {
+      if (((rowbits >> jr) | (colbits >> jc)) & 1u) s += -100.0f * LOG2E;
+    }
+    sv[j] = s;
+    m = fmaxf(m, s);
+  }
+  return m;
+}
+
+// region bits of the shift mask for query slot (ri, ci) of window (wh, ww): bit j of rowbits / colbits is set
+// when key row / column j lies in a different region (only the last window row / column has two regions)
+__device__ __forceinline__ void mask_bits(const WinGeom &g, int wh, int ww, int ri, int ci, uint32_t &rowbits,
+                                          uint32_t &colbits) {
+  rowbits = colbits = 0;
+  const bool lr = wh == g.nWh - 1, lc = ww == g.nWw - 1;
+  const int rh_i = lr ? (ri < WS - g.shift ? 1 : 2) : 0, rw_i = lc ? (ci < WS - g.shift ? 1 : 2) : 0;
+#pragma unroll
+  for (int j = 0; j < WS; ++j) {
+    const int rj = j < WS - g.shift ? 1 : 2;
+    rowbits |= (uint32_t)((lr ? rj : 0) != rh_i) << j;
+    colbits |= (uint32_t)((lc ? rj : 0) != rw_i) << j;
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 4)
     wmsa_fwd_tc_kernel(const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ qkv_bias,
                        const float *__restrict__ table, __nv_bfloat16 *__restrict__ out, WinGeom g, int C, int heads,
@@ -52,6 +87,7 @@ __global__ void __launch_bounds__(THREADS, 4)
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   float *tbl = reinterpret_cast<float *>(smem + SM_TBL);
+  const int head = blockIdx.x % heads;   // gridDim.x is a multiple of heads: the head is fixed per CTA
 
   if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
   if (tid == 0) {
@@ -60,6 +96,7 @@ __global__ void __launch_bounds__(THREADS, 4)
   }
   // zero the operand tiles once: rows 49..63 of every unit stay zero for the whole kernel
   for (int i = tid; i < SM_P / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int k = tid; k < TBL; k += THREADS) tbl[k] = __ldg(table + k * heads + head) * LOG2E;   // exp2 domain
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -68,44 +105,50 @@ __global__ void __launch_bounds__(THREADS, 4)
   const uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
   const uint32_t idesc_o = make_idesc_bf16(128, 32, false, true);
   uint32_t phase = 0;
+  const float scale2 = scale * LOG2E;
 
   const int unit = tid >> 6;   // which of the two stacked units this thread's row belongs to
   const int i = tid & 63;      // row inside the unit (query token), valid if < 49
   const int ri = i / WS, ci = i % WS;
+  const float *tb = tbl + (ri + WS - 1) * (2 * WS - 1) + (ci + WS - 1);
+  const uint32_t my_row = smem_base + tile_off(tid, 0);   // this thread's token row in the q|k|v tiles
 
   for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-    const int head = item % heads;
     const int pair = item / heads;
-    // ---------------- phase 1: gather q|k|v rows of both units into smem ----------------
-    for (int idx = tid; idx < 2 * NT * 12; idx += THREADS) {
-      const int c = idx & 3;                 // 16-byte chunk of the 64-byte head slice
-      const int part = (idx >> 2) % 3;       // q | k | v
-      const int t = (idx / 12) % NT;         // token in window
-      const int u = idx / (12 * NT);         // unit
-      const int win = 2 * pair + u;
-      if (win >= num_windows) continue;
-      int b, wh, ww;
+    // ---------------- phase 1: every thread gathers the q|k|v head slices of ITS token ----------------
+    const int win = 2 * pair + unit;
+    const bool row_ok = win < num_windows && i < NT;
+    int b = 0, wh = 0, ww = 0, h = 0, w = 0;
+    bool tok_ok = false;
+    if (row_ok) {
       ww = win % g.nWw;
       wh = (win / g.nWw) % g.nWh;
       b = win / (g.nWw * g.nWh);
-      int h, w;
-      const bool ok = g.source(wh, ww, t / WS, t % WS, h, w);
-      const int col = part * C + head * HD + c * 8;
-      const uint32_t dst = smem_base + part * 8192 + tile_off(u * 64 + t, c);
-      if (ok) {
-        cp_async16(dst, qkv + (((int64_t)b * g.H + h) * g.W + w) * (3 * C) + col);
-      } else {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (qkv_bias) {
-          const float4 f0 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col));
-          const float4 f1 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col + 4));
-          v = make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                     : "memory");
+      tok_ok = g.source(wh, ww, ri, ci, h, w);
+      if (tok_ok) {
+        const __nv_bfloat16 *src = qkv + (((int64_t)b * g.H + h) * g.W + w) * (3 * C) + head * HD;
+#pragma unroll
+        for (int part = 0; part < 3; ++part)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) cp_async16(my_row + part * 8192 + c * 128, src + part * C + c * 8);
+      } else {   // zero-padded token: its qkv row is the qkv bias
+#pragma unroll
+        for (int part = 0; part < 3; ++part)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (qkv_bias) {
+              const int col = part * C + head * HD + c * 8;
+              const float4 f0 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col));
+              const float4 f1 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col + 4));
+              v = make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + part * 8192 + c * 128), "r"(v.x),
+                         "r"(v.y), "r"(v.z), "r"(v.w)
+                         : "memory");
+          }
       }
     }
-    for (int k = tid; k < TBL; k += THREADS) tbl[k] = __ldg(table + k * heads + head);
     cp_async_wait_all();
     fence_async_smem();
     fence_before_sync();
@@ -123,14 +166,6 @@ __global__ void __launch_bounds__(THREADS, 4)
     phase ^= 1;
     fence_after_sync();
     // ---------------- phase 3: softmax on this thread's row ----------------
-    const int win = 2 * pair + unit;
-    const bool unit_ok = win < num_windows;
-    int b = 0, wh = 0, ww = 0;
-    if (unit_ok) {
-      ww = win % g.nWw;
-      wh = (win / g.nWw) % g.nWh;
-      b = win / (g.nWw * g.nWh);
-    }
     float inv_l = 0.f;
     {
       uint32_t s0[32], s1[32];
@@ -139,35 +174,21 @@ __global__ void __launch_bounds__(THREADS, 4)
       tmem_ld32(taddr + 32, s1);
       tmem_ld_wait();
       uint32_t pk[32];   // 64 bf16 probabilities, packed
-      if (unit_ok && i < NT) {
-        // shift mask: only the last window row / column has more than one region
-        uint32_t rowbits = 0, colbits = 0;
-        if (g.shift > 0) {
-          const bool lr = wh == g.nWh - 1, lc = ww == g.nWw - 1;
-          const int rh_i = lr ? (ri < WS - g.shift ? 1 : 2) : 0, rw_i = lc ? (ci < WS - g.shift ? 1 : 2) : 0;
-#pragma unroll
-          for (int j = 0; j < WS; ++j) {
-            const int rj = j < WS - g.shift ? 1 : 2;
-            rowbits |= (uint32_t)((lr ? rj : 0) != rh_i) << j;
-            colbits |= (uint32_t)((lc ? rj : 0) != rw_i) << j;
-          }
-        }
-        const float *tb = tbl + (ri + WS - 1) * (2 * WS - 1) + (ci + WS - 1);
+      if (row_ok) {
         float sv[NT];
-        float m = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          const int jr = j / WS, jc = j % WS;
-          float s = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]) * scale + tb[-(jr * (2 * WS - 1) + jc)];
-          if (((rowbits >> jr) | (colbits >> jc)) & 1u) s += -100.0f;
-          sv[j] = s;
-          m = fmaxf(m, s);
+        float m;
+        // the shift mask only exists in the last window row / column (warp-uniform branch: a unit = 2 warps)
+        if (g.shift > 0 && (wh == g.nWh - 1 || ww == g.nWw - 1)) {
+          uint32_t rowbits, colbits;
+          mask_bits(g, wh, ww, ri, ci, rowbits, colbits);
+          m = score_row<true>(s0, s1, tb, scale2, rowbits, colbits, sv);
+        } else {
+          m = score_row<false>(s0, s1, tb, scale2, 0u, 0u, sv);
         }
         float l = 0.f;
-        const float ml2 = m * 1.4426950408889634f;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-          const float p = exp2f(fmaf(sv[j], 1.4426950408889634f, -ml2));
+          const float p = exp2f(sv[j] - m);
           l += p;
           sv[j] = p;
         }
@@ -211,8 +232,7 @@ __global__ void __launch_bounds__(THREADS, 4)
       uint32_t o[32];
       tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + unit * 32, o);
       tmem_ld_wait();
-      int h, w;
-      if (unit_ok && i < NT && g.source(wh, ww, ri, ci, h, w)) {
+      if (tok_ok) {
         __nv_bfloat16 *dst = out + (((int64_t)b * g.H + h) * g.W + w) * C + head * HD;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -245,7 +265,7 @@ extern "C" int rsc_wmsa_fwd(const void *qkv, const float *qkv_bias, const float 
                             int W, int C, int heads, int ws, int shift, float scale, int dtype, void *stream) {
   static const bool force_simt = getenv("RSC_WMSA_SIMT") != nullptr;
   const bool tc_ok = dtype == RSC_BF16 && ws == 7 && (shift == 0 || shift == 3) && heads > 0 && C == heads * 32 &&
-                     B > 0 && H > 0 && W > 0 && qkv && bias_table && out;
+                     B > 0 && H > 0 && W > 0 && qkv && bias_table && out && heads <= 4 * kNumSMs;
   if (!tc_ok || force_simt)  // fp32 (exact-arithmetic parity path) and argument errors go through the SIMT entry
     return rsc_wmsa_fwd_simt(qkv, qkv_bias, bias_table, out, B, H, W, C, heads, ws, shift, scale, dtype, stream);
   WinGeom g(B, H, W, ws, shift);
@@ -253,8 +273,8 @@ extern "C" int rsc_wmsa_fwd(const void *qkv, const float *qkv_bias, const float 
   const int num_items = ((num_windows + 1) / 2) * heads;
   auto kern = wtc::wmsa_fwd_tc_kernel;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::SM_TOTAL);
-  int grid = kNumSMs * 4;
-  if (grid > num_items) grid = num_items;
+  int grid = (kNumSMs * 4) / heads * heads;    // a multiple of heads: every CTA keeps one head (bias table loaded once)
+  if (grid > num_items) grid = num_items;      // num_items is a multiple of heads
   kern<<<grid, wtc::THREADS, wtc::SM_TOTAL, (cudaStream_t)stream>>>(
       (const __nv_bfloat16 *)qkv, qkv_bias, bias_table, (__nv_bfloat16 *)out, g, C, heads, scale, num_windows,
       num_items);
@@ -303,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, 2)
     mbar_fence_init();
   }
   for (int k = tid; k < B_TBL / 16; k += THREADS) reinterpret_cast<uint4 *>(smem)[k] = make_uint4(0, 0, 0, 0);
-  for (int k = tid; k < TBL; k += THREADS) tbl[k] = __ldg(table + k * heads + head);
+  for (int k = tid; k < TBL; k += THREADS) tbl[k] = __ldg(table + k * heads + head) * LOG2E;   // exp2 domain
   for (int k = tid; k < 96; k += THREADS) padacc[k] = 0.f;
   fence_before_sync();
   __syncthreads();
@@ -318,40 +338,53 @@ __global__ void __launch_bounds__(THREADS, 2)
   const int unit = tid >> 6, i = tid & 63;
   const int ri = i / WS, ci = i % WS;
   const float *tb = tbl + (ri + WS - 1) * (2 * WS - 1) + (ci + WS - 1);
+  const uint32_t my_row = sb + tile_off(tid, 0);   // this thread's token row in the q|k|v|dO tiles
+  const float scale2 = scale * LOG2E;
   float dbacc[NT];
 #pragma unroll
   for (int j = 0; j < NT; ++j) dbacc[j] = 0.f;
 
   for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
     const int pair = item / heads;
-    // ---------------- gather q|k|v|dO rows of both units ----------------
-    for (int idx = tid; idx < 2 * NT * 16; idx += THREADS) {
-      const int c = idx & 3;
-      const int part = (idx >> 2) & 3;       // q | k | v | dO
-      const int t = (idx >> 4) % NT;
-      const int u = idx / (16 * NT);
-      const int win = 2 * pair + u;
-      if (win >= num_windows) continue;
-      const int ww = win % g.nWw, wh = (win / g.nWw) % g.nWh, b = win / (g.nWw * g.nWh);
-      int h, w;
-      const bool ok = g.source(wh, ww, t / WS, t % WS, h, w);
-      const uint32_t dst = sb + part * 8192 + tile_off(u * 64 + t, c);
-      const int64_t tok = ((int64_t)b * g.H + h) * g.W + w;
-      if (ok) {
-        if (part < 3)
-          cp_async16(dst, qkv + tok * (3 * C) + part * C + head * HD + c * 8);
-        else
-          cp_async16(dst, dout + tok * C + head * HD + c * 8);
-      } else {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (part < 3 && qkv_bias) {
-          const int col = part * C + head * HD + c * 8;
-          const float4 f0 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col));
-          const float4 f1 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col + 4));
-          v = make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                     : "memory");
+    // ---------------- every thread gathers the q|k|v|dO head slices of ITS token ----------------
+    const int win = 2 * pair + unit;
+    const bool unit_ok = win < num_windows;
+    const bool row_ok = unit_ok && i < NT;
+    int b = 0, wh = 0, ww = 0, h = 0, w = 0;
+    bool tok_ok = false;
+    if (unit_ok) {
+      ww = win % g.nWw;
+      wh = (win / g.nWw) % g.nWh;
+      b = win / (g.nWw * g.nWh);
+    }
+    if (row_ok) {
+      tok_ok = g.source(wh, ww, ri, ci, h, w);
+      if (tok_ok) {
+        const int64_t tok = ((int64_t)b * g.H + h) * g.W + w;
+        const __nv_bfloat16 *src = qkv + tok * (3 * C) + head * HD;
+        const __nv_bfloat16 *dsrc = dout + tok * C + head * HD;
+#pragma unroll
+        for (int part = 0; part < 3; ++part)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) cp_async16(my_row + part * 8192 + c * 128, src + part * C + c * 8);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cp_async16(my_row + 3 * 8192 + c * 128, dsrc + c * 8);
+      } else {   // zero-padded token: qkv row = qkv bias, its output row is cropped (dO = 0)
+#pragma unroll
+        for (int part = 0; part < 4; ++part)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (part < 3 && qkv_bias) {
+              const int col = part * C + head * HD + c * 8;
+              const float4 f0 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col));
+              const float4 f1 = __ldg(reinterpret_cast<const float4 *>(qkv_bias + col + 4));
+              v = make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w));
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + part * 8192 + c * 128), "r"(v.x),
+                         "r"(v.y), "r"(v.z), "r"(v.w)
+                         : "memory");
+          }
       }
     }
     cp_async_wait_all();
@@ -375,14 +408,6 @@ __global__ void __launch_bounds__(THREADS, 2)
     phase ^= 1;
     fence_after_sync();
     // ---------------- softmax backward on this thread's row ----------------
-    const int win = 2 * pair + unit;
-    const bool unit_ok = win < num_windows;
-    int b = 0, wh = 0, ww = 0;
-    if (unit_ok) {
-      ww = win % g.nWw;
-      wh = (win / g.nWw) % g.nWh;
-      b = win / (g.nWw * g.nWh);
-    }
     {
       uint32_t s0[32], s1[32];
       const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16) + unit * 64;
@@ -390,75 +415,79 @@ __global__ void __launch_bounds__(THREADS, 2)
       tmem_ld32(taddr + 32, s1);
       tmem_ld_wait();
       uint32_t pp[32], pd[32];   // packed bf16 P row and dS row (64 columns each)
-      // Branch-free on purpose: the TMEM loads below are warp-aligned instructions, so every lane
-      // runs the whole row computation; rows that are not real queries are zeroed by `valid`.
-      const bool valid = unit_ok && i < NT;
-      uint32_t rowbits = 0, colbits = 0;
-      if (g.shift > 0) {
-        const bool lr = wh == g.nWh - 1, lc = ww == g.nWw - 1;
-        const int rh_i = lr ? (ri < WS - g.shift ? 1 : 2) : 0, rw_i = lc ? (ci < WS - g.shift ? 1 : 2) : 0;
+      // The TMEM loads are warp-aligned instructions and stay outside the branches; the row arithmetic runs
+      // only on real query rows (the others store zeros), with warp-uniform fast paths: the shift mask exists
+      // only in the last window row / column, padded keys only where the map is not a multiple of 7.
+      float p[NT];
+      float wp = 0.f, wds = 0.f;
+      uint32_t rowpad = 0, colpad = 0;
+      if (row_ok) {
+        float m;
+        if (g.shift > 0 && (wh == g.nWh - 1 || ww == g.nWw - 1)) {
+          uint32_t rowbits, colbits;
+          mask_bits(g, wh, ww, ri, ci, rowbits, colbits);
+          m = score_row<true>(s0, s1, tb, scale2, rowbits, colbits, p);
+        } else {
+          m = score_row<false>(s0, s1, tb, scale2, 0u, 0u, p);
+        }
+        float l = 0.f;
 #pragma unroll
-        for (int j = 0; j < WS; ++j) {
-          const int rj = j < WS - g.shift ? 1 : 2;
-          rowbits |= (uint32_t)((lr ? rj : 0) != rh_i) << j;
-          colbits |= (uint32_t)((lc ? rj : 0) != rw_i) << j;
+        for (int j = 0; j < NT; ++j) {
+          p[j] = exp2f(p[j] - m);
+          l += p[j];
+        }
+        const float inv_l = 1.0f / l;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) p[j] *= inv_l;
+        // key tokens of this window that are zero-padding (their dk/dv flow to the qkv-bias gradient)
+        if (g.Hp != g.H || g.Wp != g.W) {
+#pragma unroll
+          for (int j = 0; j < WS; ++j) {
+            int hh = wh * WS + j + g.shift, wc = ww * WS + j + g.shift;
+            if (hh >= g.Hp) hh -= g.Hp;
+            if (wc >= g.Wp) wc -= g.Wp;
+            rowpad |= (uint32_t)(hh >= g.H) << j;
+            colpad |= (uint32_t)(wc >= g.W) << j;
+          }
         }
       }
-      // key tokens of this window that are zero-padding (their dk/dv flow to the qkv-bias gradient)
-      uint32_t rowpad = 0, colpad = 0;
-#pragma unroll
-      for (int j = 0; j < WS; ++j) {
-        int hh = wh * WS + j + g.shift, wc = ww * WS + j + g.shift;
-        if (hh >= g.Hp) hh -= g.Hp;
-        if (wc >= g.Wp) wc -= g.Wp;
-        rowpad |= (uint32_t)(hh >= g.H) << j;
-        colpad |= (uint32_t)(wc >= g.W) << j;
-      }
-      float p[NT];
-      float m = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const int jr = j / WS, jc = j % WS;
-        float sj = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]) * scale + tb[-(jr * (2 * WS - 1) + jc)];
-        if (((rowbits >> jr) | (colbits >> jc)) & 1u) sj += -100.0f;
-        p[j] = sj;
-        m = fmaxf(m, sj);
-      }
-      float l = 0.f;
-      const float ml2 = m * 1.4426950408889634f;
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        p[j] = exp2f(fmaf(p[j], 1.4426950408889634f, -ml2));
-        l += p[j];
-      }
-      const float inv_l = valid ? 1.0f / l : 0.f;
       tmem_ld32(taddr + 128, s0);   // dP row (reuses the S registers)
       tmem_ld32(taddr + 160, s1);
       tmem_ld_wait();
-      // Column 49 of the P / dS tiles (a zero-padding column of the MMA) carries the row's sum over the
-      // PADDED keys: row 49 of dV = P^T dO / dK = dS^T Q then IS the padded-row gradient sum, for free.
-      float D = 0.f, wp = 0.f, wds = 0.f;
+      if (row_ok) {
+        // Column 49 of the P / dS tiles (a zero-padding column of the MMA) carries the row's sum over the
+        // PADDED keys: row 49 of dV = P^T dO / dK = dS^T Q then IS the padded-row gradient sum, for free.
+        float D = 0.f;
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        p[j] = valid ? p[j] * inv_l : 0.f;
-        D = fmaf(p[j], __uint_as_float(j < 32 ? s0[j] : s1[j - 32]), D);
-        if (((rowpad >> (j / WS)) | (colpad >> (j % WS))) & 1u) wp += p[j];
+        for (int j = 0; j < NT; ++j) D = fmaf(p[j], __uint_as_float(j < 32 ? s0[j] : s1[j - 32]), D);
+        if (rowpad | colpad) {
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+            if (((rowpad >> (j / WS)) | (colpad >> (j % WS))) & 1u) wp += p[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 24; ++j) pp[j] = pack_bf16(p[2 * j], p[2 * j + 1]);
+        pp[24] = pack_bf16(p[48], wp);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float ds = p[j] * (__uint_as_float(j < 32 ? s0[j] : s1[j - 32]) - D);
+          dbacc[j] += ds;
+          p[j] = ds;
+        }
+        if (rowpad | colpad) {
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+            if (((rowpad >> (j / WS)) | (colpad >> (j % WS))) & 1u) wds += p[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 24; ++j) pd[j] = pack_bf16(p[2 * j], p[2 * j + 1]);
+        pd[24] = pack_bf16(p[48], wds);
+#pragma unroll
+        for (int j = 25; j < 32; ++j) pp[j] = 0u, pd[j] = 0u;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pp[j] = 0u, pd[j] = 0u;
       }
-#pragma unroll
-      for (int j = 0; j < 24; ++j) pp[j] = pack_bf16(p[2 * j], p[2 * j + 1]);
-      pp[24] = pack_bf16(p[48], wp);
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const float ds = valid ? p[j] * (__uint_as_float(j < 32 ? s0[j] : s1[j - 32]) - D) : 0.f;
-        dbacc[j] += ds;
-        p[j] = ds;
-        if (((rowpad >> (j / WS)) | (colpad >> (j % WS))) & 1u) wds += ds;
-      }
-#pragma unroll
-      for (int j = 0; j < 24; ++j) pd[j] = pack_bf16(p[2 * j], p[2 * j + 1]);
-      pd[24] = pack_bf16(p[48], wds);
-#pragma unroll
-      for (int j = 25; j < 32; ++j) pp[j] = 0u, pd[j] = 0u;
 #pragma unroll
       for (int kc = 0; kc < 8; ++kc) {
         const uint32_t o = bd_off(tid, unit * 8 + kc);
@@ -497,9 +526,6 @@ __global__ void __launch_bounds__(THREADS, 2)
     {
       uint32_t o[32];
       const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16);
-      int h = 0, w = 0;
-      const bool row_ok = unit_ok && i < NT;
-      const bool tok_ok = row_ok && g.source(wh, ww, ri, ci, h, w);
       __nv_bfloat16 *dst = dqkv + (((int64_t)b * g.H + h) * g.W + w) * (3 * C) + head * HD;
 #pragma unroll
       for (int part = 0; part < 3; ++part) {   // TMEM columns: dV 0, dK 32, dQ 64 -> dqkv parts 2, 1, 0

@@ -155,6 +155,18 @@ class DropPath(nn.Module):
         mask = keep + torch.rand(shape, dtype=torch.float32, device=x.device)
         return (mask.floor() / keep).to(x.dtype)
 
+    def scale_vec(self, x):
+        """this call's per-sample factor as an fp32 (B,) tensor, or None for identity (fused add_ln path)."""
+        if self.forced_mask is not None:
+            return self.forced_mask.reshape(-1).float()
+        if self.drawn is not None:
+            s, self.drawn = self.drawn, None
+            return s.reshape(-1).float()
+        if self.drop_prob == 0. or not self.training:
+            return None
+        keep = 1 - self.drop_prob
+        return (keep + torch.rand(x.shape[0], dtype=torch.float32, device=x.device)).floor() / keep
+
     def forward(self, x):
         s = self._scale(x)
         return x if s is None else x * s

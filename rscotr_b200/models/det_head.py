@@ -210,15 +210,13 @@ class DinoTransformer(nn.Module):
     def _geometry(self, mlvl_masks, mlvl_pos_embeds, shapes_py, device):
         """everything of forward() that depends only on the masks / shapes (cached by GeomCache)."""
         mask_flatten = torch.cat([m.flatten(1) for m in mlvl_masks], 1)
-        pos_flatten = torch.cat([p.flatten(2).transpose(1, 2) for p in mlvl_pos_embeds], 1)
-        lvl_index = torch.cat([torch.full((h * w,), i, dtype=torch.long, device=device)
-                               for i, (h, w) in enumerate(shapes_py)])
+        pos_levels = [p.flatten(2).transpose(1, 2).contiguous() for p in mlvl_pos_embeds]
         spatial_shapes = const_tensor(shapes_py, torch.long, device)
         level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in mlvl_masks], 1)
         reference_points = self.get_reference_points(shapes_py, valid_ratios, device=device)
         grid = self.proposal_grid(mask_flatten, shapes_py)
-        return dict(masks=list(mlvl_masks), mask_flatten=mask_flatten, pos_flatten=pos_flatten, lvl_index=lvl_index,
+        return dict(masks=list(mlvl_masks), mask_flatten=mask_flatten, pos_levels=pos_levels,
                     spatial_shapes=spatial_shapes, level_start_index=level_start_index, valid_ratios=valid_ratios,
                     reference_points=reference_points, grid=grid)
 
@@ -235,7 +233,10 @@ class DinoTransformer(nn.Module):
                                                pos=list(mlvl_pos_embeds)))
         feat_flatten = torch.cat([feat.flatten(2).transpose(1, 2) for feat in mlvl_feats], 1)
         mask_flatten, spatial_shapes = geo['mask_flatten'], geo['spatial_shapes']
-        lvl_pos_embed_flatten = geo['pos_flatten'] + self.level_embeds[geo['lvl_index']].unsqueeze(0)
+        # (per-level add + cat: the backward is four small reductions; an index gather's backward is a slow
+        # sorted index_put over all 13 294 tokens)
+        lvl_pos_embed_flatten = torch.cat([p + self.level_embeds[l].view(1, 1, -1)
+                                           for l, p in enumerate(geo['pos_levels'])], 1)
         level_start_index, valid_ratios = geo['level_start_index'], geo['valid_ratios']
         reference_points = geo['reference_points']
 

@@ -65,7 +65,7 @@ class MlvlSegPixelDecoder(nn.Module):
 
         def make():
             """shape-only constants: all-false padding masks, sine encodings, reference points, level index"""
-            padding_mask_list, pos_list, reference_points_list, lvl_index = [], [], [], []
+            padding_mask_list, pos_list, reference_points_list = [], [], []
             for i, level_idx in enumerate(levels):
                 h, w = shapes_py[i]
                 padding_mask_resized = torch.zeros((batch_size, h, w), dtype=torch.bool, device=dev)
@@ -78,12 +78,11 @@ class MlvlSegPixelDecoder(nn.Module):
                 reference_points_list.append(reference_points / const_tensor(
                     [[float(w * self.strides[level_idx]), float(h * self.strides[level_idx])]], torch.float32, dev))
                 padding_mask_list.append(padding_mask_resized.flatten(1))
-                lvl_index.append(torch.full((h * w,), i, dtype=torch.long, device=dev))
             spatial_shapes = const_tensor(shapes_py, torch.long, dev)
             reference_points = torch.cat(reference_points_list, dim=0)
             reference_points = reference_points[None, :, None].repeat(batch_size, 1, self.num_encoder_levels, 1)
-            return dict(padding_masks=torch.cat(padding_mask_list, dim=1), pos=torch.cat(pos_list, dim=0),
-                        lvl_index=torch.cat(lvl_index), spatial_shapes=spatial_shapes,
+            return dict(padding_masks=torch.cat(padding_mask_list, dim=1), pos=[p.contiguous() for p in pos_list],
+                        spatial_shapes=spatial_shapes,
                         level_start_index=torch.cat((spatial_shapes.new_zeros((1,)),
                                                      spatial_shapes.prod(1).cumsum(0)[:-1])),
                         reference_points=reference_points,
@@ -92,7 +91,8 @@ class MlvlSegPixelDecoder(nn.Module):
             self._geom = GeomCache()
         geo = self._geom.get((batch_size, tuple(shapes_py), str(dev)), make)
         encoder_inputs = torch.cat([neck_feats[l].flatten(2).permute(2, 0, 1) for l in levels], dim=0)
-        level_positional_encodings = geo['pos'] + self.level_encoding.weight[geo['lvl_index']].unsqueeze(1)
+        level_positional_encodings = torch.cat([p + self.level_encoding.weight[i].view(1, 1, -1)
+                                                for i, p in enumerate(geo['pos'])], dim=0)
         padding_masks, spatial_shapes = geo['padding_masks'], geo['spatial_shapes']
         level_start_index, reference_points, valid_radios = geo['level_start_index'], geo['reference_points'], \
             geo['valid_radios']

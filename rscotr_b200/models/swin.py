@@ -91,6 +91,39 @@ class SwinBlock(nn.Module):
         x = self.norm2(x)
         return self.ffn(x, identity=identity)
 
+    def fusable(self, x):
+        """the fused residual-stream kernels cover GELU FFNs without dropout on CUDA bf16 / fp32 tokens"""
+        ffn = self.ffn
+        return (ops.add_ln_supported(x) and len(ffn.layers) == 3 and isinstance(ffn.layers[0][1], nn.GELU) and
+                ffn.layers[0][1].approximate == 'none' and ffn.layers[0][2].p == 0. and ffn.layers[2].p == 0. and
+                self.attn.w_msa.proj_drop.p == 0. and ffn.add_identity and isinstance(ffn.dropout_layer, DropPath) and
+                ffn.layers[0][0].bias is not None and ffn.layers[1].bias is not None and
+                self.attn.w_msa.proj.bias is not None)
+
+    def forward_fused(self, x, hw_shape, n1, next_norm):
+        """Same arithmetic as forward() with the element-wise passes fused (ops.add_ln / ops.bias_gelu):
+        x is the residual stream, n1 = norm1(x) if the previous fused pass already produced it, next_norm the
+        LayerNorm that consumes this block's output (the next block's norm1 or the stage's output norm) or None.
+        Returns (x_out, next_norm(x_out) or None)."""
+        if n1 is None:
+            n1 = self.norm1(x)
+        m = self.attn.w_msa
+        H, W = hw_shape
+        qkv = m.qkv(n1)
+        a = ops.wmsa(qkv, m.qkv.bias, m.relative_position_bias_table, (H, W), m.num_heads, self.attn.window_size,
+                     self.attn.shift_size, m.scale)
+        a = ops.linear(a, m.proj.weight, None)             # proj bias is added inside add_ln
+        x1, n2 = ops.add_ln(x, a, m.proj.bias, self.attn.drop.scale_vec(x), self.norm2.weight, self.norm2.bias,
+                            self.norm2.eps)
+        fc1, fc2 = self.ffn.layers[0][0], self.ffn.layers[1]
+        g = ops.bias_gelu(ops.linear(n2, fc1.weight, None), fc1.bias)
+        f = ops.linear(g, fc2.weight, None)
+        s2 = self.ffn.dropout_layer.scale_vec(x)
+        if next_norm is not None:
+            return ops.add_ln(x1, f, fc2.bias, s2, next_norm.weight, next_norm.bias, next_norm.eps)
+        f = f + fc2.bias.to(f.dtype)
+        return (x1 + f if s2 is None else torch.addcmul(x1, f, s2.to(f.dtype).view(-1, 1, 1))), None
+
 
 class PatchMerging(nn.Module):
     """mmdet PatchMerging (kernel 2, stride 2, 'corner' padding, nn.Unfold channel order)."""
@@ -119,13 +152,23 @@ class SwinBlockSequence(nn.Module):
                       drop_rate, attn_drop_rate, dprs[i], act_cfg, with_cp) for i in range(depth)])
         self.downsample = downsample
 
-    def forward(self, x, hw_shape):
-        for block in self.blocks:
-            x = block(x, hw_shape)
+    def forward(self, x, hw_shape, out_norm=None):
+        """-> (x_down, down_hw, out, out_hw); with `out_norm` (the stage's output LayerNorm) `out` is already
+        normalised -- on the fused path the last block's residual update and that norm are one kernel."""
+        n = None
+        for k, block in enumerate(self.blocks):
+            if block.fusable(x):
+                nxt = self.blocks[k + 1].norm1 if k + 1 < len(self.blocks) else out_norm
+                x, n = block.forward_fused(x, hw_shape, n, nxt)
+            else:
+                x, n = block(x, hw_shape), None
+        out = x
+        if out_norm is not None:
+            out = n if n is not None else out_norm(x)
         if self.downsample:
             x_down, down_hw_shape = self.downsample(x, hw_shape)
-            return x_down, down_hw_shape, x, hw_shape
-        return x, hw_shape, x, hw_shape
+            return x_down, down_hw_shape, out, hw_shape
+        return x, hw_shape, out, hw_shape
 
 
 class PatchEmbed(nn.Module):
@@ -204,12 +247,12 @@ class SwinTransformer(nn.Module):
         if self.training:
             if not hasattr(self, '_drop_paths'):
                 self._drop_paths = [m for m in self.modules() if isinstance(m, DropPath)]
-            draw_drop_paths(self._drop_paths, x.shape[0], x.device, x.dtype)
+            draw_drop_paths(self._drop_paths, x.shape[0], x.device, torch.float32)
         outs = []
         for i, stage in enumerate(self.stages):
-            x, hw_shape, out, out_hw_shape = stage(x, hw_shape)
+            x, hw_shape, out, out_hw_shape = stage(x, hw_shape,
+                                                   getattr(self, 'norm%d' % i) if i in self.out_indices else None)
             if i in self.out_indices:
-                out = getattr(self, 'norm%d' % i)(out)
                 # logical NCHW, channels-last strides: a view, no transpose copy
                 out = out.view(-1, *out_hw_shape, self.num_features[i]).permute(0, 3, 1, 2)
                 outs.append(out)

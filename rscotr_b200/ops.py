@@ -226,22 +226,131 @@ class _LayerNorm(torch.autograd.Function):
                  rstd.data_ptr(), rows, C, eps, _dt(xc), _dt(y), _stream(),
                  alg_bytes=xc.numel() * (xc.element_size() + y.element_size()))
         ctx.save_for_backward(xc, g32, mean, rstd)
-        ctx.meta = (rows, C, gamma.dtype, beta.dtype)
+        ctx.meta = (rows, C, gamma.dtype, beta.dtype, _flat_grad(gamma), _flat_grad(beta))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xc, g32, mean, rstd = ctx.saved_tensors
-        rows, C, gdt, bdt = ctx.meta
+        rows, C, gdt, bdt, gg, gb = ctx.meta
         dy = dy.contiguous()
         dx = torch.empty_like(xc)
-        dg = torch.zeros(C, dtype=torch.float32, device=xc.device)
-        db = torch.zeros_like(dg)
+        direct = gg is not None and gb is not None     # the kernel ACCUMULATES d(gamma) / d(beta) with atomics
+        dg = gg if direct else torch.zeros(C, dtype=torch.float32, device=xc.device)
+        db = gb if direct else torch.zeros_like(dg)
         with torch.cuda.device(xc.device):
             call('rsc_layernorm_bwd', xc.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dy.data_ptr(),
                  dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, C, _dt(xc), _dt(dy), _stream(),
                  alg_bytes=xc.numel() * (2 * xc.element_size() + dy.element_size()))
+        if direct:
+            return dx, None, None, None, None
         return dx, dg.to(gdt), db.to(bdt), None, None
+
+
+def _flat_grad(p):
+    """the step engine's fp32 gradient view of parameter p (None outside the engine / without autograd)."""
+    g = getattr(p, '_rsc_g', None)
+    if g is None or not torch.is_grad_enabled() or not p.requires_grad or g.dtype != torch.float32:
+        return None
+    return g
+
+
+# ---------------------------------------------------------------------------
+# fused residual-stream passes of the Swin block   (SURVEY 8a row a2)
+# ---------------------------------------------------------------------------
+def add_ln_supported(x):
+    return x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and bool(_lib.lib().rsc_add_ln_supported(x.shape[-1]))
+
+
+class _AddLN(torch.autograd.Function):
+    """(r, n) = (identity + (x + bias) * scale[sample], LayerNorm(r)); see include/rscotr.h."""
+
+    @staticmethod
+    def forward(ctx, identity, x, bias, scale, gamma, beta, eps):
+        _cuda(identity, x, gamma, beta)
+        C = x.shape[-1]
+        idc, xc = identity.contiguous(), x.contiguous()
+        assert idc.dtype == xc.dtype and idc.shape == xc.shape
+        rows = xc.numel() // C
+        rps = rows // xc.shape[0]
+        b32, s32, g32, be32 = _f32(bias), _f32(scale), _f32(gamma), _f32(beta)
+        r = torch.empty_like(xc)
+        n = torch.empty_like(xc)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        with torch.cuda.device(x.device):
+            call('rsc_add_ln_fwd', idc.data_ptr(), xc.data_ptr(), _p(b32), _p(s32), g32.data_ptr(), be32.data_ptr(),
+                 r.data_ptr(), n.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, rps, C, float(eps), _dt(xc), _stream(),
+                 alg_bytes=4 * xc.numel() * xc.element_size())
+        ctx.save_for_backward(r, g32, mean, rstd, s32)
+        ctx.meta = (rows, rps, C, None if bias is None else bias.dtype, gamma.dtype, beta.dtype,
+                    None if bias is None else _flat_grad(bias), _flat_grad(gamma), _flat_grad(beta),
+                    ctx.needs_input_grad[1])
+        return r, n
+
+    @staticmethod
+    def backward(ctx, dr_ext, dn):
+        r, g32, mean, rstd, s32 = ctx.saved_tensors
+        rows, rps, C, bdt, gdt, bedt, gbias, gg, gb, need_dx = ctx.meta
+        dev = r.device
+        if dn is None:
+            dn = torch.zeros_like(r)
+        dn = dn.contiguous()
+        dr_ext = None if dr_ext is None else dr_ext.contiguous()
+        d_id = torch.empty_like(r)
+        dx = torch.empty_like(r) if s32 is not None else None
+        direct = gg is not None and gb is not None
+        dg = gg if direct else torch.zeros(C, dtype=torch.float32, device=dev)
+        db = gb if direct else torch.zeros(C, dtype=torch.float32, device=dev)
+        dbias = None
+        if bdt is not None:
+            dbias = gbias if gbias is not None else torch.zeros(C, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call('rsc_add_ln_bwd', r.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dn.data_ptr(),
+                 _p(dr_ext), _p(s32), d_id.data_ptr(), _p(dx), dg.data_ptr(), db.data_ptr(), _p(dbias), rows, rps, C,
+                 _dt(r), _stream(), alg_bytes=(4 + (dr_ext is not None) + (dx is not None)) * r.numel() * r.element_size())
+        return (d_id, (dx if dx is not None else d_id) if need_dx else None,
+                None if (bdt is None or gbias is not None) else dbias.to(bdt), None,
+                None if direct else dg.to(gdt), None if direct else db.to(bedt), None)
+
+
+def add_ln(identity, x, bias, scale, gamma, beta, eps=1e-5):
+    """r = identity + (x + bias) * scale[b]; n = LayerNorm(r).  bias (C,) / scale (B,) may be None."""
+    return _AddLN.apply(identity, x, bias, scale, gamma, beta, eps)
+
+
+class _BiasGelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, bias):
+        _cuda(h, bias)
+        hc = h.contiguous()
+        C = hc.shape[-1]
+        rows = hc.numel() // C
+        b32 = _f32(bias)
+        y = torch.empty_like(hc)
+        with torch.cuda.device(h.device):
+            call('rsc_bias_gelu_fwd', hc.data_ptr(), b32.data_ptr(), y.data_ptr(), rows, C, _dt(hc), _stream(),
+                 alg_bytes=2 * hc.numel() * hc.element_size())
+        ctx.save_for_backward(hc, b32)
+        ctx.meta = (rows, C, bias.dtype, _flat_grad(bias))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        hc, b32 = ctx.saved_tensors
+        rows, C, bdt, gbias = ctx.meta
+        dy = dy.contiguous()
+        dh = torch.empty_like(hc)
+        dbias = gbias if gbias is not None else torch.zeros(C, dtype=torch.float32, device=hc.device)
+        with torch.cuda.device(hc.device):
+            call('rsc_bias_gelu_bwd', hc.data_ptr(), b32.data_ptr(), dy.data_ptr(), dh.data_ptr(), dbias.data_ptr(), rows, C,
+                 _dt(hc), _stream(), alg_bytes=3 * hc.numel() * hc.element_size())
+        return dh, None if gbias is not None else dbias.to(bdt)
+
+
+def bias_gelu(h, bias):
+    """gelu(h + bias) (erf form); the backward also produces the bias gradient (column sums) in the same pass."""
+    return _BiasGelu.apply(h, bias)
 
 
 def layer_norm(x, gamma, beta, eps=1e-5, out_dtype=None):

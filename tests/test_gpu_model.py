@@ -66,6 +66,9 @@ def test_train_step_matches_oracle_fp32(task):
         if p.grad is None:
             assert go is None or float(go.abs().max()) == 0.0, n
             continue
+        if go is None:      # fused passes return zero gradients where autograd would return none (unused norm outputs)
+            assert float(p.grad.abs().max()) == 0.0, n
+            continue
         e = rel(p.grad, go)
         if float(go.abs().max()) > 1e-7:
             worst = max(worst, e)

@@ -513,3 +513,52 @@ def test_upsample_ce_matches_interpolate_cross_entropy(shape, dtype):
     assert int(stats[2]) == int(valid.sum())
     assert abs(int(stats[1]) - int(correct)) <= (0 if dtype == torch.float32 else 2) + int(1e-4 * valid.sum())
     assert_rel(x.grad, ref_in.grad, 1e-4 if dtype == torch.float32 else 6e-3, 'dlogits')
+
+
+# ---------------------------------------------------------------------------
+# a2: fused residual-stream passes (add + DropPath + bias + LayerNorm, bias + GELU)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('C', [96, 192, 384, 768, 256])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('with_scale', [False, True])
+def test_add_ln_matches_eager(C, dtype, with_scale):
+    ops = _ops()
+    g = torch.Generator().manual_seed(C)
+    B, L = 3, 37
+    ident, x = torch.randn(B, L, C, generator=g).to(dtype), torch.randn(B, L, C, generator=g).to(dtype)
+    bias, gamma, beta = torch.randn(C, generator=g) * .1, torch.rand(C, generator=g) + .5, torch.randn(C, generator=g) * .1
+    scale = torch.tensor([0.0, 1.25, 1.25]) if with_scale else None
+    w_r, w_n = torch.randn(B, L, C, generator=g), torch.randn(B, L, C, generator=g)
+    # eager reference in fp32 on the same (rounded) inputs
+    ri, rx = ident.float().clone().requires_grad_(True), x.float().clone().requires_grad_(True)
+    rb, rg, rbe = bias.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    r = ri + (rx + rb) * (scale.view(B, 1, 1) if with_scale else 1.0)
+    if dtype == torch.bfloat16:
+        r = r + (r.detach().bfloat16().float() - r.detach())      # the stored residual is bf16
+    n = F.layer_norm(r, (C,), rg, rbe, 1e-5)
+    ((r * w_r).sum() + (n * w_n).sum()).backward()
+    ins = [t.detach().cuda().requires_grad_(True) for t in (ident, x, bias, gamma, beta)]
+    gr, gn = ops.add_ln(ins[0], ins[1], ins[2], None if scale is None else scale.cuda(), ins[3], ins[4], 1e-5)
+    ((gr.float() * w_r.cuda()).sum() + (gn.float() * w_n.cuda()).sum()).backward()
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert_rel(gr, r, tol, 'r')
+    assert_rel(gn, n, tol, 'n')
+    for got, want, what in zip(ins, (ri, rx, rb, rg, rbe), ('d_identity', 'dx', 'dbias', 'dgamma', 'dbeta')):
+        assert_rel(got.grad, want.grad, 2e-4 if dtype == torch.float32 else 2e-2, what)
+
+
+@pytest.mark.parametrize('rows,C', [(50, 384), (1000, 768), (33, 3072), (7, 8)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_bias_gelu_matches_eager(rows, C, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows)
+    h, bias, w = (torch.randn(rows, C, generator=g) * 2).to(dtype), torch.randn(C, generator=g), torch.randn(rows, C, generator=g)
+    rh, rb = h.float().clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    y = F.gelu(rh + rb)
+    (y * w).sum().backward()
+    gh, gb = h.detach().cuda().requires_grad_(True), bias.detach().cuda().requires_grad_(True)
+    gy = ops.bias_gelu(gh, gb)
+    (gy.float() * w.cuda()).sum().backward()
+    assert_rel(gy, y, 1e-5 if dtype == torch.float32 else 6e-3, 'y')
+    assert_rel(gh.grad, rh.grad, 1e-4 if dtype == torch.float32 else 1e-2, 'dh')
+    assert_rel(gb.grad, rb.grad, 1e-4 if dtype == torch.float32 else 2e-2, 'dbias')
