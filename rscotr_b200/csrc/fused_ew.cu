@@ -50,6 +50,25 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16 *p, const fl
   *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// VW-element vector access (VW = 8: 16 B bf16 / 2 x 16 B fp32; VW = 4: 8 B bf16 / 16 B fp32)
+template <typename T, int VW>
+__device__ __forceinline__ void loadv(const T *p, float (&v)[VW]) {
+  if constexpr (VW == 8) {
+    load8<T>(p, v);
+  } else {
+    const float4 f = load4<T>(p);
+    v[0] = f.x, v[1] = f.y, v[2] = f.z, v[3] = f.w;
+  }
+}
+template <typename T, int VW>
+__device__ __forceinline__ void storev(T *p, const float (&v)[VW]) {
+  if constexpr (VW == 8) {
+    store8<T>(p, v);
+  } else {
+    store4<T>(p, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
 template <int L>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
@@ -58,42 +77,42 @@ __device__ __forceinline__ float group_sum(float v) {
 }
 
 // Same sub-warp mapping as layernorm.cu: L lanes share a row (C = 8*EV*L), a warp covers 32/L rows per step.
-template <typename T, int EV, int L>
+template <typename T, int VW, int EV, int L>
 __global__ void __launch_bounds__(LN_THREADS)
     add_ln_fwd_kernel(const T *__restrict__ identity, const T *__restrict__ x, const float *__restrict__ bias,
                       const float *__restrict__ scale, const float *__restrict__ gamma, const float *__restrict__ beta,
                       T *__restrict__ r_out, T *__restrict__ n_out, float *__restrict__ mean, float *__restrict__ rstd,
                       int64_t rows, int64_t rows_per_sample, float eps) {
-  constexpr int C = 8 * EV * L, RPW = 32 / L;
+  constexpr int C = VW * EV * L, RPW = 32 / L;
   const int lane = threadIdx.x & 31, sub = lane % L, rw = lane / L;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float ga[EV][8], be[EV][8], bi[EV][8];
+  float ga[EV][VW], be[EV][VW], bi[EV][VW];
 #pragma unroll
   for (int k = 0; k < EV; ++k) {
-    load8<float>(gamma + (sub + k * L) * 8, ga[k]);
-    load8<float>(beta + (sub + k * L) * 8, be[k]);
-    if (bias) load8<float>(bias + (sub + k * L) * 8, bi[k]);
+    loadv<float, VW>(gamma + (sub + k * L) * VW, ga[k]);
+    loadv<float, VW>(beta + (sub + k * L) * VW, be[k]);
+    if (bias) loadv<float, VW>(bias + (sub + k * L) * VW, bi[k]);
     else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) bi[k][e] = 0.f;
+      for (int e = 0; e < VW; ++e) bi[k][e] = 0.f;
     }
   }
   for (int64_t r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
     const int64_t r = r0 + rw;
     const bool ok = r < rows;
     const float sc = (ok && scale) ? __ldg(scale + r / rows_per_sample) : 1.0f;
-    float v[EV][8];
+    float v[EV][VW];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < EV; ++k) {
-      float a[8], b[8];
+      float a[VW], b[VW];
       if (ok) {
-        load8<T>(identity + r * C + (sub + k * L) * 8, a);
-        load8<T>(x + r * C + (sub + k * L) * 8, b);
+        loadv<T, VW>(identity + r * C + (sub + k * L) * VW, a);
+        loadv<T, VW>(x + r * C + (sub + k * L) * VW, b);
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < VW; ++e) {
         v[k][e] = ok ? fmaf(b[e] + bi[k][e], sc, a[e]) : 0.f;
         // the stored residual is the (possibly bf16-rounded) value the rest of the network sees:
         // normalise exactly that value so that forward and backward agree
@@ -106,7 +125,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 #pragma unroll
     for (int k = 0; k < EV; ++k)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < VW; ++e) {
         const float d = v[k][e] - mu;
         q = fmaf(d, d, q);
       }
@@ -118,54 +137,60 @@ __global__ void __launch_bounds__(LN_THREADS)
       }
 #pragma unroll
       for (int k = 0; k < EV; ++k) {
-        float o[8];
+        float o[VW];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaf((v[k][e] - mu) * rs, ga[k][e], be[k][e]);
-        store8<T>(r_out + r * C + (sub + k * L) * 8, v[k]);
-        store8<T>(n_out + r * C + (sub + k * L) * 8, o);
+        for (int e = 0; e < VW; ++e) o[e] = fmaf((v[k][e] - mu) * rs, ga[k][e], be[k][e]);
+        storev<T, VW>(r_out + r * C + (sub + k * L) * VW, v[k]);
+        storev<T, VW>(n_out + r * C + (sub + k * L) * VW, o);
       }
     }
   }
 }
 
 // dr = dr_ext + LNbwd(dn) ; d_identity = dr ; dx = dr * scale ; dbias += colsum(dx) ; dgamma, dbeta
-template <typename T, int EV, int L>
+template <typename T, int VW, int EV, int L>
 __global__ void __launch_bounds__(LN_THREADS)
     add_ln_bwd_kernel(const T *__restrict__ r_in, const float *__restrict__ gamma, const float *__restrict__ mean,
                       const float *__restrict__ rstd, const T *__restrict__ dn, const T *__restrict__ dr_ext,
                       const float *__restrict__ scale, T *__restrict__ d_identity, T *__restrict__ dx,
                       float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ dbias, int64_t rows,
                       int64_t rows_per_sample) {
-  constexpr int C = 8 * EV * L, RPW = 32 / L;
+  constexpr int C = VW * EV * L, RPW = 32 / L;
   __shared__ float red[3 * C];   // per-CTA partial d(gamma) | d(beta) | d(bias)
   const int lane = threadIdx.x & 31, sub = lane % L, rw = lane / L;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  float ga[EV][8], dg[EV][8], db[EV][8], dbi[EV][8];
+  float ga[EV][VW], dg[EV][VW], db[EV][VW], dbi[EV][VW];
 #pragma unroll
   for (int k = 0; k < EV; ++k) {
-    load8<float>(gamma + (sub + k * L) * 8, ga[k]);
+    loadv<float, VW>(gamma + (sub + k * L) * VW, ga[k]);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) dg[k][e] = 0.f, db[k][e] = 0.f, dbi[k][e] = 0.f;
+    for (int e = 0; e < VW; ++e) dg[k][e] = 0.f, db[k][e] = 0.f, dbi[k][e] = 0.f;
   }
   for (int64_t r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
     const int64_t r = r0 + rw;
     const bool ok = r < rows;
     const float mu = ok ? mean[r] : 0.f, rs = ok ? rstd[r] : 0.f;
     const float sc = (ok && scale) ? __ldg(scale + r / rows_per_sample) : 1.0f;
-    float xh[EV][8], g[EV][8];
+    float xh[EV][VW], g[EV][VW], ex[EV][VW];
     float s1 = 0.f, s2 = 0.f;
+    // all loads of the row are issued before the first reduction (memory-level parallelism)
 #pragma unroll
     for (int k = 0; k < EV; ++k) {
-      float d[8];
       if (ok) {
-        load8<T>(r_in + r * C + (sub + k * L) * 8, xh[k]);
-        load8<T>(dn + r * C + (sub + k * L) * 8, d);
+        loadv<T, VW>(r_in + r * C + (sub + k * L) * VW, xh[k]);
+        loadv<T, VW>(dn + r * C + (sub + k * L) * VW, g[k]);
+        if (dr_ext) loadv<T, VW>(dr_ext + r * C + (sub + k * L) * VW, ex[k]);
       }
+    }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+    for (int k = 0; k < EV; ++k) {
+      float d[VW];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        d[e] = g[k][e];
         if (!ok) xh[k][e] = 0.f, d[e] = 0.f;
         xh[k][e] = (xh[k][e] - mu) * rs;
         dg[k][e] = fmaf(d[e], xh[k][e], dg[k][e]);
@@ -180,20 +205,19 @@ __global__ void __launch_bounds__(LN_THREADS)
     if (ok) {
 #pragma unroll
       for (int k = 0; k < EV; ++k) {
-        float o[8], e8[8];
-        if (dr_ext) load8<T>(dr_ext + r * C + (sub + k * L) * 8, e8);
+        float o[VW];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          o[e] = rs * (g[k][e] - s1 - xh[k][e] * s2) + (dr_ext ? e8[e] : 0.f);
+        for (int e = 0; e < VW; ++e) {
+          o[e] = rs * (g[k][e] - s1 - xh[k][e] * s2) + (dr_ext ? ex[k][e] : 0.f);
         }
-        store8<T>(d_identity + r * C + (sub + k * L) * 8, o);
+        storev<T, VW>(d_identity + r * C + (sub + k * L) * VW, o);
         if (dx || dbias) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int e = 0; e < VW; ++e) {
             o[e] = to_f<T>(from_f<T>(o[e])) * sc;   // dx = (stored dr) * scale
             dbi[k][e] += o[e];
           }
-          if (dx) store8<T>(dx + r * C + (sub + k * L) * 8, o);
+          if (dx) storev<T, VW>(dx + r * C + (sub + k * L) * VW, o);
         }
       }
     }
@@ -201,7 +225,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 #pragma unroll
   for (int k = 0; k < EV; ++k)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < VW; ++e) {
       float a = dg[k][e], b = db[k][e], c = dbi[k][e];
 #pragma unroll
       for (int o = 16; o >= L; o >>= 1) {
@@ -210,9 +234,9 @@ __global__ void __launch_bounds__(LN_THREADS)
         c += __shfl_xor_sync(0xffffffffu, c, o);
       }
       if (rw == 0) {
-        atomicAdd(red + (sub + k * L) * 8 + e, a);
-        atomicAdd(red + C + (sub + k * L) * 8 + e, b);
-        atomicAdd(red + 2 * C + (sub + k * L) * 8 + e, c);
+        atomicAdd(red + (sub + k * L) * VW + e, a);
+        atomicAdd(red + C + (sub + k * L) * VW + e, b);
+        atomicAdd(red + 2 * C + (sub + k * L) * VW + e, c);
       }
     }
   __syncthreads();
@@ -223,13 +247,17 @@ __global__ void __launch_bounds__(LN_THREADS)
   }
 }
 
-static bool ln_shape(int C, int &ev, int &l) {
-  for (int e = 3; e <= 4; ++e)
-    for (int ll = 4; ll <= 32; ll *= 2)
-      if (C == 8 * e * ll) {
-        ev = e, l = ll;
-        return true;
-      }
+// (VW, EV, L) with VW*EV*L == C that keeps the fewest elements per lane (registers!) with 16-byte vectors
+// preferred: 96 -> (4,3,8) | 192 -> (4,3,16) | 384 -> (4,3,32) | 768 -> (8,3,32) | 128 -> (8,1,16) | 256 -> (8,1,32)
+// | 512 -> (8,2,32) | 1024 -> (8,4,32)
+static bool ln_shape(int C, int &vw, int &ev, int &l) {
+  static const int table[8][4] = {{96, 4, 3, 8},   {192, 4, 3, 16}, {384, 4, 3, 32}, {768, 8, 3, 32},
+                                  {128, 8, 1, 16}, {256, 8, 1, 32}, {512, 8, 2, 32}, {1024, 8, 4, 32}};
+  for (int i = 0; i < 8; ++i)
+    if (table[i][0] == C) {
+      vw = table[i][1], ev = table[i][2], l = table[i][3];
+      return true;
+    }
   return false;
 }
 
@@ -243,57 +271,80 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return cdf + x * pdf;
 }
 
+// Flat mapping: the (rows, C) tensor is a stream of 8-element vectors; thread t owns vectors t, t + T, t + 2T ...
+// with T = total threads a multiple of C/8, so that a thread always sees the SAME 8 columns (its bias values and
+// its partial d(bias) sums live in registers) and every warp access is a contiguous 512-byte run.
 template <typename T>
 __global__ void __launch_bounds__(256)
-    bias_gelu_fwd_kernel(const T *__restrict__ h, const float *__restrict__ bias, T *__restrict__ y, int64_t rows, int C) {
-  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
-  if (c >= C) return;
+    bias_gelu_fwd_kernel(const T *__restrict__ h, const float *__restrict__ bias, T *__restrict__ y, int64_t nvec, int C8) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x, T_ = (int64_t)gridDim.x * 256;
   float b[8];
-  load8<float>(bias + c, b);
-  for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8) {
-    float v[8];
-    load8<T>(h + r * C + c, v);
+  load8<float>(bias + (t % C8) * 8, b);
+  int64_t v = t;
+  for (; v + T_ < nvec; v += 2 * T_) {   // two independent vectors in flight
+    float a0[8], a1[8];
+    load8<T>(h + v * 8, a0);
+    load8<T>(h + (v + T_) * 8, a1);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = gelu_f(v[e] + b[e]);
-    store8<T>(y + r * C + c, v);
+    for (int e = 0; e < 8; ++e) a0[e] = gelu_f(a0[e] + b[e]), a1[e] = gelu_f(a1[e] + b[e]);
+    store8<T>(y + v * 8, a0);
+    store8<T>(y + (v + T_) * 8, a1);
+  }
+  if (v < nvec) {
+    float a0[8];
+    load8<T>(h + v * 8, a0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a0[e] = gelu_f(a0[e] + b[e]);
+    store8<T>(y + v * 8, a0);
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
     bias_gelu_bwd_kernel(const T *__restrict__ h, const float *__restrict__ bias, const T *__restrict__ dy,
-                         T *__restrict__ dh, float *__restrict__ dbias, int64_t rows, int C) {
-  __shared__ float red[8][32][8 + 1];
-  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
-  float acc[8];
+                         T *__restrict__ dh, float *__restrict__ dbias, int64_t nvec, int C8) {
+  extern __shared__ float red[];   // [C] per-CTA partial d(bias)
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x, T_ = (int64_t)gridDim.x * 256;
+  const int c8 = (int)(t % C8);
+  for (int i = threadIdx.x; i < C8 * 8; i += 256) red[i] = 0.f;
+  __syncthreads();
+  float b[8], acc[8];
+  load8<float>(bias + c8 * 8, b);
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  if (c < C) {
-    float b[8];
-    load8<float>(bias + c, b);
-    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.y * 8) {
-      float v[8], d[8];
-      load8<T>(h + r * C + c, v);
-      load8<T>(dy + r * C + c, d);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        d[e] = to_f<T>(from_f<T>(d[e] * gelu_grad(v[e] + b[e])));
-        acc[e] += d[e];
-      }
-      store8<T>(dh + r * C + c, d);
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) red[threadIdx.y][threadIdx.x][e] = acc[e];
-  __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
+  int64_t v = t;
+  for (; v + T_ < nvec; v += 2 * T_) {
+    float a0[8], d0[8], a1[8], d1[8];
+    load8<T>(h + v * 8, a0);
+    load8<T>(dy + v * 8, d0);
+    load8<T>(h + (v + T_) * 8, a1);
+    load8<T>(dy + (v + T_) * 8, d1);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float s = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x][e];
-      atomicAdd(dbias + c + e, s);
+      d0[e] = to_f<T>(from_f<T>(d0[e] * gelu_grad(a0[e] + b[e])));
+      d1[e] = to_f<T>(from_f<T>(d1[e] * gelu_grad(a1[e] + b[e])));
+      acc[e] += d0[e] + d1[e];
     }
+    store8<T>(dh + v * 8, d0);
+    store8<T>(dh + (v + T_) * 8, d1);
+  }
+  if (v < nvec) {
+    float a0[8], d0[8];
+    load8<T>(h + v * 8, a0);
+    load8<T>(dy + v * 8, d0);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      d0[e] = to_f<T>(from_f<T>(d0[e] * gelu_grad(a0[e] + b[e])));
+      acc[e] += d0[e];
+    }
+    store8<T>(dh + v * 8, d0);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) atomicAdd(red + c8 * 8 + e, acc[e]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C8 * 8; i += 256) {
+    const float s = red[i];
+    if (s != 0.f) atomicAdd(dbias + i, s);
   }
 }
 
@@ -303,8 +354,8 @@ __global__ void __launch_bounds__(256)
 using namespace rsc;
 
 extern "C" int rsc_add_ln_supported(int C) {
-  int ev, l;
-  return few::ln_shape(C, ev, l) ? 1 : 0;
+  int vw, ev, l;
+  return few::ln_shape(C, vw, ev, l) ? 1 : 0;
 }
 
 extern "C" int rsc_add_ln_fwd(const void *identity, const void *x, const float *bias, const float *scale,
@@ -312,20 +363,21 @@ extern "C" int rsc_add_ln_fwd(const void *identity, const void *x, const float *
                               int64_t rows, int64_t rows_per_sample, int C, float eps, int dtype, void *stream) {
   RSC_CHECK_ARG(rows > 0 && rows_per_sample > 0, "rsc_add_ln_fwd: empty tensor");
   RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "rsc_add_ln_fwd: bad dtype %d", dtype);
-  int ev = 0, l = 0;
-  RSC_CHECK_ARG(few::ln_shape(C, ev, l), "rsc_add_ln_fwd: unsupported channel count %d (need 8*{3,4}*{4,8,16,32})", C);
+  int vw = 0, ev = 0, l = 0;
+  RSC_CHECK_ARG(few::ln_shape(C, vw, ev, l), "rsc_add_ln_fwd: unsupported channel count %d (96..1024 Swin / transformer widths)", C);
   RSC_CHECK_ARG(identity && x && gamma && beta && r_out && n_out && mean && rstd, "rsc_add_ln_fwd: null pointer");
   const int rpb = (few::LN_THREADS / 32) * (32 / l);
   int64_t fb = (rows + rpb - 1) / rpb;
   const int grid = (int)(fb < kNumSMs * 12 ? fb : kNumSMs * 12);
   cudaStream_t st = (cudaStream_t)stream;
-#define ALF(T, E, LL)                                                                                                   \
-  if (ev == E && l == LL) {                                                                                             \
-    few::add_ln_fwd_kernel<T, E, LL><<<grid, few::LN_THREADS, 0, st>>>((const T *)identity, (const T *)x, bias, scale,   \
+#define ALF(T, V, E, LL)                                                                                                \
+  if (vw == V && ev == E && l == LL) {                                                                                  \
+    few::add_ln_fwd_kernel<T, V, E, LL><<<grid, few::LN_THREADS, 0, st>>>((const T *)identity, (const T *)x, bias, scale,   \
                                                                         gamma, beta, (T *)r_out, (T *)n_out, mean, rstd, \
                                                                         rows, rows_per_sample, eps);                    \
   }
-#define ALF_ALL(T) ALF(T, 3, 4) ALF(T, 3, 8) ALF(T, 3, 16) ALF(T, 3, 32) ALF(T, 4, 4) ALF(T, 4, 8) ALF(T, 4, 16) ALF(T, 4, 32)
+#define ALF_ALL(T) \
+  ALF(T, 4, 3, 8) ALF(T, 4, 3, 16) ALF(T, 4, 3, 32) ALF(T, 8, 3, 32) ALF(T, 8, 1, 16) ALF(T, 8, 1, 32) ALF(T, 8, 2, 32) ALF(T, 8, 4, 32)
   if (dtype == RSC_F32) { ALF_ALL(float) } else { ALF_ALL(__nv_bfloat16) }
 #undef ALF
 #undef ALF_ALL
@@ -339,21 +391,22 @@ extern "C" int rsc_add_ln_bwd(const void *r, const float *gamma, const float *me
                               void *stream) {
   RSC_CHECK_ARG(rows > 0 && rows_per_sample > 0, "rsc_add_ln_bwd: empty tensor");
   RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "rsc_add_ln_bwd: bad dtype %d", dtype);
-  int ev = 0, l = 0;
-  RSC_CHECK_ARG(few::ln_shape(C, ev, l), "rsc_add_ln_bwd: unsupported channel count %d", C);
+  int vw = 0, ev = 0, l = 0;
+  RSC_CHECK_ARG(few::ln_shape(C, vw, ev, l), "rsc_add_ln_bwd: unsupported channel count %d", C);
   RSC_CHECK_ARG(r && gamma && mean && rstd && dn && d_identity && dgamma && dbeta, "rsc_add_ln_bwd: null pointer");
   RSC_CHECK_ARG(!(scale && !dx), "rsc_add_ln_bwd: a per-sample scale needs a separate dx buffer");
   const int rpb = (few::LN_THREADS / 32) * (32 / l);
   int64_t fb = (rows + rpb - 1) / rpb;
-  const int grid = (int)(fb < kNumSMs * 6 ? fb : kNumSMs * 6);
+  const int grid = (int)(fb < kNumSMs * 8 ? fb : kNumSMs * 8);
   cudaStream_t st = (cudaStream_t)stream;
-#define ALB(T, E, LL)                                                                                                  \
-  if (ev == E && l == LL) {                                                                                            \
-    few::add_ln_bwd_kernel<T, E, LL><<<grid, few::LN_THREADS, 0, st>>>(                                                \
+#define ALB(T, V, E, LL)                                                                                               \
+  if (vw == V && ev == E && l == LL) {                                                                                 \
+    few::add_ln_bwd_kernel<T, V, E, LL><<<grid, few::LN_THREADS, 0, st>>>(                                                \
         (const T *)r, gamma, mean, rstd, (const T *)dn, (const T *)dr_ext, scale, (T *)d_identity, (T *)dx, dgamma,    \
         dbeta, dbias, rows, rows_per_sample);                                                                          \
   }
-#define ALB_ALL(T) ALB(T, 3, 4) ALB(T, 3, 8) ALB(T, 3, 16) ALB(T, 3, 32) ALB(T, 4, 4) ALB(T, 4, 8) ALB(T, 4, 16) ALB(T, 4, 32)
+#define ALB_ALL(T) \
+  ALB(T, 4, 3, 8) ALB(T, 4, 3, 16) ALB(T, 4, 3, 32) ALB(T, 8, 3, 32) ALB(T, 8, 1, 16) ALB(T, 8, 1, 32) ALB(T, 8, 2, 32) ALB(T, 8, 4, 32)
   if (dtype == RSC_F32) { ALB_ALL(float) } else { ALB_ALL(__nv_bfloat16) }
 #undef ALB
 #undef ALB_ALL
@@ -361,11 +414,19 @@ extern "C" int rsc_add_ln_bwd(const void *r, const float *gamma, const float *me
   return RSC_OK;
 }
 
-static int bg_grid_y(int64_t rows, int cblocks) {
-  int64_t want = (int64_t)kNumSMs * 8 / cblocks;
-  if (want < 1) want = 1;
-  int64_t slabs = (rows + 7) / 8;
-  return (int)(slabs < want ? slabs : want);
+// grid of 256-thread CTAs whose total thread count is a multiple of C/8 (see the kernels), ~8 CTAs per SM
+static int bg_grid(int64_t nvec, int C8) {
+  int a = C8, b = 256;
+  while (b) {
+    const int t = a % b;
+    a = b, b = t;
+  }
+  const int m = C8 / a;                                   // grid must be a multiple of m
+  int64_t want = (nvec + 2 * 256 - 1) / (2 * 256);        // two vectors per thread per trip
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (want > cap) want = cap;
+  want = (want + m - 1) / m * m;
+  return (int)(want < m ? m : want);
 }
 
 extern "C" int rsc_bias_gelu_fwd(const void *h, const float *bias, void *y, int64_t rows, int C, int dtype, void *stream) {
@@ -373,31 +434,32 @@ extern "C" int rsc_bias_gelu_fwd(const void *h, const float *bias, void *y, int6
                 (long long)rows, C);
   RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "rsc_bias_gelu_fwd: bad dtype %d", dtype);
   RSC_CHECK_ARG(h && bias && y, "rsc_bias_gelu_fwd: null pointer");
-  const int cblocks = (C + 255) / 256;
-  dim3 grid(cblocks, bg_grid_y(rows, cblocks)), block(32, 8);
+  const int64_t nvec = rows * (C / 8);
+  const int grid = bg_grid(nvec, C / 8);
   if (dtype == RSC_F32)
-    few::bias_gelu_fwd_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float *)h, bias, (float *)y, rows, C);
+    few::bias_gelu_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)h, bias, (float *)y, nvec, C / 8);
   else
-    few::bias_gelu_fwd_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16 *)h, bias, (__nv_bfloat16 *)y, rows, C);
+    few::bias_gelu_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)h, bias, (__nv_bfloat16 *)y, nvec, C / 8);
   RSC_CHECK_LAUNCH("rsc_bias_gelu_fwd");
   return RSC_OK;
 }
 
 extern "C" int rsc_bias_gelu_bwd(const void *h, const float *bias, const void *dy, void *dh, float *dbias, int64_t rows,
                                  int C, int dtype, void *stream) {
-  RSC_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "rsc_bias_gelu_bwd: need rows > 0, C %% 8 == 0 (rows=%lld, C=%d)",
-                (long long)rows, C);
+  RSC_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 8192,
+                "rsc_bias_gelu_bwd: need rows > 0, C %% 8 == 0, C <= 8192 (rows=%lld, C=%d)", (long long)rows, C);
   RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "rsc_bias_gelu_bwd: bad dtype %d", dtype);
   RSC_CHECK_ARG(h && bias && dy && dh && dbias, "rsc_bias_gelu_bwd: null pointer");
-  const int cblocks = (C + 255) / 256;
-  dim3 grid(cblocks, bg_grid_y(rows, cblocks)), block(32, 8);
+  const int64_t nvec = rows * (C / 8);
+  const int grid = bg_grid(nvec, C / 8);
+  const size_t smem = (size_t)C * sizeof(float);
   if (dtype == RSC_F32)
-    few::bias_gelu_bwd_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float *)h, bias, (const float *)dy,
-                                                                                 (float *)dh, dbias, rows, C);
+    few::bias_gelu_bwd_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const float *)h, bias, (const float *)dy,
+                                                                                 (float *)dh, dbias, nvec, C / 8);
   else
-    few::bias_gelu_bwd_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16 *)h, bias, (const __nv_bfloat16 *)dy, (__nv_bfloat16 *)dh, dbias, rows, C);
+    few::bias_gelu_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)h, bias, (const __nv_bfloat16 *)dy, (__nv_bfloat16 *)dh, dbias, nvec, C / 8);
   RSC_CHECK_LAUNCH("rsc_bias_gelu_bwd");
   return RSC_OK;
 }

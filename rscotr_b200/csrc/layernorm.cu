@@ -49,6 +49,25 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16 *p, const fl
   *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// VW-element vector access (VW = 8: 16 B bf16 / 2 x 16 B fp32; VW = 4: 8 B bf16 / 16 B fp32)
+template <typename T, int VW>
+__device__ __forceinline__ void loadv(const T *p, float (&v)[VW]) {
+  if constexpr (VW == 8) {
+    load8<T>(p, v);
+  } else {
+    const float4 f = load4<T>(p);
+    v[0] = f.x, v[1] = f.y, v[2] = f.z, v[3] = f.w;
+  }
+}
+template <typename T, int VW>
+__device__ __forceinline__ void storev(T *p, const float (&v)[VW]) {
+  if constexpr (VW == 8) {
+    store8<T>(p, v);
+  } else {
+    store4<T>(p, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
 template <int L>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
@@ -56,30 +75,30 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-template <typename TI, typename TO, int EV, int L>
+template <typename TI, typename TO, int VW, int EV, int L>
 __global__ void __launch_bounds__(LN_THREADS)
     ln_fwd_kernel(const TI *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
                   TO *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd, int64_t rows, float eps) {
-  constexpr int C = 8 * EV * L, RPW = 32 / L;
+  constexpr int C = VW * EV * L, RPW = 32 / L;
   const int lane = threadIdx.x & 31, sub = lane % L, rw = lane / L;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float ga[EV][8], be[EV][8];
+  float ga[EV][VW], be[EV][VW];
 #pragma unroll
   for (int k = 0; k < EV; ++k) {
-    load8<float>(gamma + (sub + k * L) * 8, ga[k]);
-    load8<float>(beta + (sub + k * L) * 8, be[k]);
+    loadv<float, VW>(gamma + (sub + k * L) * VW, ga[k]);
+    loadv<float, VW>(beta + (sub + k * L) * VW, be[k]);
   }
   for (int64_t r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
     const int64_t r = r0 + rw;
     const bool ok = r < rows;
-    float v[EV][8];
+    float v[EV][VW];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < EV; ++k) {
-      if (ok) load8<TI>(x + r * C + (sub + k * L) * 8, v[k]);
+      if (ok) loadv<TI, VW>(x + r * C + (sub + k * L) * VW, v[k]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < VW; ++e) {
         if (!ok) v[k][e] = 0.f;
         s += v[k][e];
       }
@@ -89,7 +108,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 #pragma unroll
     for (int k = 0; k < EV; ++k)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < VW; ++e) {
         const float d = v[k][e] - mu;
         q = fmaf(d, d, q);
       }
@@ -101,49 +120,49 @@ __global__ void __launch_bounds__(LN_THREADS)
       }
 #pragma unroll
       for (int k = 0; k < EV; ++k) {
-        float o[8];
+        float o[VW];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaf((v[k][e] - mu) * rs, ga[k][e], be[k][e]);
-        store8<TO>(y + r * C + (sub + k * L) * 8, o);
+        for (int e = 0; e < VW; ++e) o[e] = fmaf((v[k][e] - mu) * rs, ga[k][e], be[k][e]);
+        storev<TO, VW>(y + r * C + (sub + k * L) * VW, o);
       }
     }
   }
 }
 
-template <typename TI, typename TO, int EV, int L>
+template <typename TI, typename TO, int VW, int EV, int L>
 __global__ void __launch_bounds__(LN_THREADS)
     ln_bwd_kernel(const TI *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ mean,
                   const float *__restrict__ rstd, const TO *__restrict__ dy, TI *__restrict__ dx,
                   float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t rows) {
-  constexpr int C = 8 * EV * L, RPW = 32 / L;
+  constexpr int C = VW * EV * L, RPW = 32 / L;
   __shared__ float red[2 * C];   // per-CTA partial d(gamma) | d(beta)
   const int lane = threadIdx.x & 31, sub = lane % L, rw = lane / L;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  float ga[EV][8], dg[EV][8], db[EV][8];
+  float ga[EV][VW], dg[EV][VW], db[EV][VW];
 #pragma unroll
   for (int k = 0; k < EV; ++k) {
-    load8<float>(gamma + (sub + k * L) * 8, ga[k]);
+    loadv<float, VW>(gamma + (sub + k * L) * VW, ga[k]);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) dg[k][e] = 0.f, db[k][e] = 0.f;
+    for (int e = 0; e < VW; ++e) dg[k][e] = 0.f, db[k][e] = 0.f;
   }
   for (int64_t r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
     const int64_t r = r0 + rw;
     const bool ok = r < rows;
     const float mu = ok ? mean[r] : 0.f, rs = ok ? rstd[r] : 0.f;
-    float xh[EV][8], g[EV][8];
+    float xh[EV][VW], g[EV][VW];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < EV; ++k) {
-      float d[8];
+      float d[VW];
       if (ok) {
-        load8<TI>(x + r * C + (sub + k * L) * 8, xh[k]);
-        load8<TO>(dy + r * C + (sub + k * L) * 8, d);
+        loadv<TI, VW>(x + r * C + (sub + k * L) * VW, xh[k]);
+        loadv<TO, VW>(dy + r * C + (sub + k * L) * VW, d);
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < VW; ++e) {
         if (!ok) xh[k][e] = 0.f, d[e] = 0.f;
         xh[k][e] = (xh[k][e] - mu) * rs;
         dg[k][e] = fmaf(d[e], xh[k][e], dg[k][e]);
@@ -158,10 +177,10 @@ __global__ void __launch_bounds__(LN_THREADS)
     if (ok) {
 #pragma unroll
       for (int k = 0; k < EV; ++k) {
-        float o[8];
+        float o[VW];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rs * (g[k][e] - s1 - xh[k][e] * s2);
-        store8<TI>(dx + r * C + (sub + k * L) * 8, o);
+        for (int e = 0; e < VW; ++e) o[e] = rs * (g[k][e] - s1 - xh[k][e] * s2);
+        storev<TI, VW>(dx + r * C + (sub + k * L) * VW, o);
       }
     }
   }
@@ -169,7 +188,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 #pragma unroll
   for (int k = 0; k < EV; ++k)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < VW; ++e) {
       float a = dg[k][e], b = db[k][e];
 #pragma unroll
       for (int o = 16; o >= L; o >>= 1) {
@@ -177,8 +196,8 @@ __global__ void __launch_bounds__(LN_THREADS)
         b += __shfl_xor_sync(0xffffffffu, b, o);
       }
       if (rw == 0) {
-        atomicAdd(red + (sub + k * L) * 8 + e, a);
-        atomicAdd(red + C + (sub + k * L) * 8 + e, b);
+        atomicAdd(red + (sub + k * L) * VW + e, a);
+        atomicAdd(red + C + (sub + k * L) * VW + e, b);
       }
     }
   __syncthreads();
@@ -188,28 +207,31 @@ __global__ void __launch_bounds__(LN_THREADS)
   }
 }
 
-// (EV, L) for a supported C, or false -> generic warp-per-row kernels below
-static bool ln_shape(int C, int &ev, int &l) {
-  for (int e = 3; e <= 4; ++e)
-    for (int ll = 4; ll <= 32; ll *= 2)
-      if (C == 8 * e * ll) {
-        ev = e, l = ll;
-        return true;
-      }
+// (VW, EV, L) for a supported C (fewest elements per lane), or false -> generic warp-per-row kernels below
+static bool ln_shape(int C, int &vw, int &ev, int &l) {
+  static const int table[8][4] = {{96, 4, 3, 8},   {192, 4, 3, 16}, {384, 4, 3, 32}, {768, 8, 3, 32},
+                                  {128, 8, 1, 16}, {256, 8, 1, 32}, {512, 8, 2, 32}, {1024, 8, 4, 32}};
+  for (int i = 0; i < 8; ++i)
+    if (table[i][0] == C) {
+      vw = table[i][1], ev = table[i][2], l = table[i][3];
+      return true;
+    }
   return false;
 }
+
+#define LN_SHAPES(M) M(4, 3, 8) M(4, 3, 16) M(4, 3, 32) M(8, 3, 32) M(8, 1, 16) M(8, 1, 32) M(8, 2, 32) M(8, 4, 32)
 
 template <typename TI, typename TO>
 static bool ln_fast_fwd(int C, int grid, cudaStream_t st, const void *x, const float *gamma, const float *beta, void *y,
                         float *mean, float *rstd, int64_t rows, float eps) {
-  int ev, l;
-  if (!ln_shape(C, ev, l)) return false;
-#define LNF(E, LL)                                                                                         \
-  if (ev == E && l == LL) {                                                                                \
-    ln_fwd_kernel<TI, TO, E, LL><<<grid, LN_THREADS, 0, st>>>((const TI *)x, gamma, beta, (TO *)y, mean, rstd, rows, eps); \
+  int vw, ev, l;
+  if (!ln_shape(C, vw, ev, l)) return false;
+#define LNF(V, E, LL)                                                                                      \
+  if (vw == V && ev == E && l == LL) {                                                                     \
+    ln_fwd_kernel<TI, TO, V, E, LL><<<grid, LN_THREADS, 0, st>>>((const TI *)x, gamma, beta, (TO *)y, mean, rstd, rows, eps); \
     return true;                                                                                           \
   }
-  LNF(3, 4) LNF(3, 8) LNF(3, 16) LNF(3, 32) LNF(4, 4) LNF(4, 8) LNF(4, 16) LNF(4, 32)
+  LN_SHAPES(LNF)
 #undef LNF
   return false;
 }
@@ -217,15 +239,15 @@ static bool ln_fast_fwd(int C, int grid, cudaStream_t st, const void *x, const f
 template <typename TI, typename TO>
 static bool ln_fast_bwd(int C, int grid, cudaStream_t st, const void *x, const float *gamma, const float *mean,
                         const float *rstd, const void *dy, void *dx, float *dgamma, float *dbeta, int64_t rows) {
-  int ev, l;
-  if (!ln_shape(C, ev, l)) return false;
-#define LNB(E, LL)                                                                                          \
-  if (ev == E && l == LL) {                                                                                 \
-    ln_bwd_kernel<TI, TO, E, LL><<<grid, LN_THREADS, 0, st>>>((const TI *)x, gamma, mean, rstd, (const TO *)dy, \
-                                                               (TI *)dx, dgamma, dbeta, rows);              \
+  int vw, ev, l;
+  if (!ln_shape(C, vw, ev, l)) return false;
+#define LNB(V, E, LL)                                                                                       \
+  if (vw == V && ev == E && l == LL) {                                                                      \
+    ln_bwd_kernel<TI, TO, V, E, LL><<<grid, LN_THREADS, 0, st>>>((const TI *)x, gamma, mean, rstd, (const TO *)dy, \
+                                                                  (TI *)dx, dgamma, dbeta, rows);           \
     return true;                                                                                            \
   }
-  LNB(3, 4) LNB(3, 8) LNB(3, 16) LNB(3, 32) LNB(4, 4) LNB(4, 8) LNB(4, 16) LNB(4, 32)
+  LN_SHAPES(LNB)
 #undef LNB
   return false;
 }
@@ -419,8 +441,8 @@ extern "C" int rsc_layernorm_fwd(const void *x, const float *gamma, const float 
   if (int e = ln_check("rsc_layernorm_fwd", rows, C, in_dtype, out_dtype)) return e;
   RSC_CHECK_ARG(x && gamma && beta && y && mean && rstd, "rsc_layernorm_fwd: null pointer");
   {
-    int ev = 0, l = 32;
-    if (ln_shape(C, ev, l)) {
+    int vw = 0, ev = 0, l = 32;
+    if (ln_shape(C, vw, ev, l)) {
       int64_t fb = (rows + (LN_THREADS / 32) * (32 / l) - 1) / ((LN_THREADS / 32) * (32 / l));
       int fgrid = (int)(fb < kNumSMs * 12 ? fb : kNumSMs * 12);
       bool done = false;
@@ -449,10 +471,10 @@ extern "C" int rsc_layernorm_bwd(const void *x, const float *gamma, const float 
   if (int e = ln_check("rsc_layernorm_bwd", rows, C, in_dtype, out_dtype)) return e;
   RSC_CHECK_ARG(x && gamma && mean && rstd && dy && dx && dgamma && dbeta, "rsc_layernorm_bwd: null pointer");
   {
-    int ev = 0, l = 32;
-    if (ln_shape(C, ev, l)) {
+    int vw = 0, ev = 0, l = 32;
+    if (ln_shape(C, vw, ev, l)) {
       int64_t fb = (rows + (LN_THREADS / 32) * (32 / l) - 1) / ((LN_THREADS / 32) * (32 / l));
-      int fgrid = (int)(fb < kNumSMs * 6 ? fb : kNumSMs * 6);
+      int fgrid = (int)(fb < kNumSMs * 8 ? fb : kNumSMs * 8);
       bool done = false;
       cudaStream_t st = (cudaStream_t)stream;
       if (in_dtype == RSC_F32 && out_dtype == RSC_F32) done = ln_fast_bwd<float, float>(C, fgrid, st, x, gamma, mean, rstd, dy, dx, dgamma, dbeta, rows);
