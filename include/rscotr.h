@@ -146,6 +146,20 @@ int rsc_msda_bwd(const void *value, const int64_t *spatial_shapes, const int64_t
                  float *grad_loc, float *grad_weight, int B, int Nv, int Nq, int heads, int L, int P,
                  int im2col_step, int dtype, void *stream);
 
+/* Fused tail of mmcv MultiScaleDeformableAttention.forward (ops/multi_scale_deform_attn.py): softmax over the
+ * L*P attention logits + sampling_locations = reference_points + offsets / (W_l, H_l) (2-d references) or
+ * + offsets / P * ref_wh * 0.5 (4-d references) + the sampling op above, in one kernel each way.
+ * offsets (B,Nq,heads,L,P,2) and logits (B,Nq,heads,L*P) are the raw outputs of the two Linears (`off_dtype`),
+ * ref (B,Nq,L,ref_dim) fp32 with ref_dim 2 or 4 (no gradient is produced for it: the reference feeds detached /
+ * constant reference points), L*P must be 16.  grad_value is fp32 and ACCUMULATED (zero it first). */
+int rsc_msda_fused_fwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *offsets, const void *logits, const float *ref, void *out, int B, int Nv, int Nq,
+                       int heads, int L, int P, int ref_dim, int dtype, int off_dtype, void *stream);
+int rsc_msda_fused_bwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *offsets, const void *logits, const float *ref, const void *grad_out,
+                       float *grad_value, void *grad_offsets, void *grad_logits, int B, int Nv, int Nq, int heads,
+                       int L, int P, int ref_dim, int dtype, int off_dtype, void *stream);
+
 /* ------------------------------------------------------------------------
  * Global average pool.  Replaces mmcls GlobalAveragePooling
  * (AdaptiveAvgPool2d((1,1))) called from
@@ -242,8 +256,10 @@ int rsc_upsample_ce_bwd(const void *logits, const int64_t *label, const float *l
  * rsc_add_ln_bwd:  dr = dr_ext + LayerNormBackward(dn)  -> d_identity;
  *                  dx = dr * scale (written only when dx != NULL; dx == NULL means dx = dr);
  *                  dbias += column sums of dx; dgamma / dbeta accumulated (all fp32).
- * rsc_bias_gelu_fwd: y = gelu(h + bias), exact erf form (torch.nn.GELU default).
- * rsc_bias_gelu_bwd: dh = dy * gelu'(h + bias); dbias += column sums of dh.
+ * rsc_bias_act_fwd: y = act(h + bias); act 0 = GELU, exact erf form (torch.nn.GELU default; the
+ *                   bf16 path evaluates erf to 1.5e-7), act 1 = ReLU (the mmcv FFN of the encoder /
+ *                   decoder layers, cnn/bricks/transformer.py FFN).
+ * rsc_bias_act_bwd: dh = dy * act'(h + bias); dbias += column sums of dh.
  * ---------------------------------------------------------------------- */
 int rsc_add_ln_supported(int C);
 int rsc_add_ln_fwd(const void *identity, const void *x, const float *bias, const float *scale, const float *gamma,
@@ -252,9 +268,9 @@ int rsc_add_ln_fwd(const void *identity, const void *x, const float *bias, const
 int rsc_add_ln_bwd(const void *r, const float *gamma, const float *mean, const float *rstd, const void *dn,
                    const void *dr_ext, const float *scale, void *d_identity, void *dx, float *dgamma, float *dbeta,
                    float *dbias, int64_t rows, int64_t rows_per_sample, int C, int dtype, void *stream);
-int rsc_bias_gelu_fwd(const void *h, const float *bias, void *y, int64_t rows, int C, int dtype, void *stream);
-int rsc_bias_gelu_bwd(const void *h, const float *bias, const void *dy, void *dh, float *dbias, int64_t rows, int C,
-                      int dtype, void *stream);
+int rsc_bias_act_fwd(const void *h, const float *bias, void *y, int64_t rows, int C, int act, int dtype, void *stream);
+int rsc_bias_act_bwd(const void *h, const float *bias, const void *dy, void *dh, float *dbias, int64_t rows, int C,
+                     int act, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------
  * Flat fused AdamW (+ gradient-clip scale).  Replaces mmcv OptimizerHook's

@@ -38,11 +38,13 @@ _SIGS = {
     'rsc_add_ln_supported': [_I],
     'rsc_add_ln_fwd': [_P] * 10 + [ctypes.c_int64, ctypes.c_int64, _I, _F, _I, _P],
     'rsc_add_ln_bwd': [_P] * 12 + [ctypes.c_int64, ctypes.c_int64, _I, _I, _P],
-    'rsc_bias_gelu_fwd': [_P, _P, _P, ctypes.c_int64, _I, _I, _P],
-    'rsc_bias_gelu_bwd': [_P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _P],
+    'rsc_bias_act_fwd': [_P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
+    'rsc_bias_act_bwd': [_P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
     'rsc_colsum': [_P, _P, ctypes.c_int64, _I, _I, _P],
     'rsc_msda_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'rsc_msda_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'rsc_msda_fused_fwd': [_P] * 7 + [_I] * 9 + [_P],
+    'rsc_msda_fused_bwd': [_P] * 10 + [_I] * 9 + [_P],
     'rsc_gap_fwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'rsc_gap_bwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'rsc_bilinear_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -264,19 +264,60 @@ static bool ln_shape(int C, int &vw, int &ev, int &l) {
 // ---------------------------------------------------------------------------------------------
 // bias + GELU (erf).  Block = 32 column octets x 8 row lanes over a slab of rows.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+// Activations.  GELU is the exact erf form (torch.nn.GELU default).  These passes are ALU-bound with libm's erff
+// (~45 instructions per element for value + derivative), so the bf16 path evaluates erf with Abramowitz & Stegun
+// 7.1.26 (|error| < 1.5e-7, four orders below bf16 resolution) sharing ONE exponential between erf and the
+// Gaussian density: u = exp(-x^2/2) = exp(-z^2) with z = x/sqrt(2).  fp32 keeps erff (the 1e-3 parity path).
+enum { ACT_GELU = 0, ACT_RELU = 1 };
+
+template <bool FAST>
+__device__ __forceinline__ void gelu_parts(float x, float &cdf, float &u) {
+  if (FAST) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    u = exp2f(-0.72134752044448170f * x * x);                      // exp(-x^2/2)
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float half_erfc = 0.5f * poly * t * u;                    // 0.5 * erfc(|z|)
+    cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+  } else {
+    cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+    u = __expf(-0.5f * x * x);
+  }
 }
+
+template <int ACT, bool FAST>
+__device__ __forceinline__ float act_f(float x) {
+  if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  float cdf, u;
+  gelu_parts<FAST>(x, cdf, u);
+  return x * cdf;
+}
+template <int ACT, bool FAST>
+__device__ __forceinline__ float act_grad(float x) {
+  if (ACT == ACT_RELU) return x > 0.f ? 1.f : 0.f;
+  float cdf, u;
+  gelu_parts<FAST>(x, cdf, u);
+  return fmaf(x * 0.3989422804014327f, u, cdf);
+}
+
+template <typename T>
+struct FastAct {
+  static constexpr bool value = false;
+};
+template <>
+struct FastAct<__nv_bfloat16> {
+  static constexpr bool value = true;
+};
 
 // Flat mapping: the (rows, C) tensor is a stream of 8-element vectors; thread t owns vectors t, t + T, t + 2T ...
 // with T = total threads a multiple of C/8, so that a thread always sees the SAME 8 columns (its bias values and
 // its partial d(bias) sums live in registers) and every warp access is a contiguous 512-byte run.
-template <typename T>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256)
-    bias_gelu_fwd_kernel(const T *__restrict__ h, const float *__restrict__ bias, T *__restrict__ y, int64_t nvec, int C8) {
+    bias_act_fwd_kernel(const T *__restrict__ h, const float *__restrict__ bias, T *__restrict__ y, int64_t nvec, int C8) {
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x, T_ = (int64_t)gridDim.x * 256;
   float b[8];
   load8<float>(bias + (t % C8) * 8, b);
@@ -286,7 +327,7 @@ __global__ void __launch_bounds__(256)
     load8<T>(h + v * 8, a0);
     load8<T>(h + (v + T_) * 8, a1);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) a0[e] = gelu_f(a0[e] + b[e]), a1[e] = gelu_f(a1[e] + b[e]);
+    for (int e = 0; e < 8; ++e) a0[e] = act_f<ACT, FastAct<T>::value>(a0[e] + b[e]), a1[e] = act_f<ACT, FastAct<T>::value>(a1[e] + b[e]);
     store8<T>(y + v * 8, a0);
     store8<T>(y + (v + T_) * 8, a1);
   }
@@ -294,14 +335,14 @@ __global__ void __launch_bounds__(256)
     float a0[8];
     load8<T>(h + v * 8, a0);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) a0[e] = gelu_f(a0[e] + b[e]);
+    for (int e = 0; e < 8; ++e) a0[e] = act_f<ACT, FastAct<T>::value>(a0[e] + b[e]);
     store8<T>(y + v * 8, a0);
   }
 }
 
-template <typename T>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256)
-    bias_gelu_bwd_kernel(const T *__restrict__ h, const float *__restrict__ bias, const T *__restrict__ dy,
+    bias_act_bwd_kernel(const T *__restrict__ h, const float *__restrict__ bias, const T *__restrict__ dy,
                          T *__restrict__ dh, float *__restrict__ dbias, int64_t nvec, int C8) {
   extern __shared__ float red[];   // [C] per-CTA partial d(bias)
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x, T_ = (int64_t)gridDim.x * 256;
@@ -321,8 +362,8 @@ __global__ void __launch_bounds__(256)
     load8<T>(dy + (v + T_) * 8, d1);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      d0[e] = to_f<T>(from_f<T>(d0[e] * gelu_grad(a0[e] + b[e])));
-      d1[e] = to_f<T>(from_f<T>(d1[e] * gelu_grad(a1[e] + b[e])));
+      d0[e] = to_f<T>(from_f<T>(d0[e] * act_grad<ACT, FastAct<T>::value>(a0[e] + b[e])));
+      d1[e] = to_f<T>(from_f<T>(d1[e] * act_grad<ACT, FastAct<T>::value>(a1[e] + b[e])));
       acc[e] += d0[e] + d1[e];
     }
     store8<T>(dh + v * 8, d0);
@@ -334,7 +375,7 @@ __global__ void __launch_bounds__(256)
     load8<T>(dy + v * 8, d0);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      d0[e] = to_f<T>(from_f<T>(d0[e] * gelu_grad(a0[e] + b[e])));
+      d0[e] = to_f<T>(from_f<T>(d0[e] * act_grad<ACT, FastAct<T>::value>(a0[e] + b[e])));
       acc[e] += d0[e];
     }
     store8<T>(dh + v * 8, d0);
@@ -429,37 +470,48 @@ static int bg_grid(int64_t nvec, int C8) {
   return (int)(want < m ? m : want);
 }
 
-extern "C" int rsc_bias_gelu_fwd(const void *h, const float *bias, void *y, int64_t rows, int C, int dtype, void *stream) {
-  RSC_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0, "rsc_bias_gelu_fwd: need rows > 0, C %% 8 == 0 (rows=%lld, C=%d)",
+static int bias_act_check(const char *fn, int64_t rows, int C, int act, int dtype) {
+  RSC_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 8192, "%s: need rows > 0, C %% 8 == 0, C <= 8192 (rows=%lld, C=%d)", fn,
                 (long long)rows, C);
-  RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "rsc_bias_gelu_fwd: bad dtype %d", dtype);
-  RSC_CHECK_ARG(h && bias && y, "rsc_bias_gelu_fwd: null pointer");
-  const int64_t nvec = rows * (C / 8);
-  const int grid = bg_grid(nvec, C / 8);
-  if (dtype == RSC_F32)
-    few::bias_gelu_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)h, bias, (float *)y, nvec, C / 8);
-  else
-    few::bias_gelu_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16 *)h, bias, (__nv_bfloat16 *)y, nvec, C / 8);
-  RSC_CHECK_LAUNCH("rsc_bias_gelu_fwd");
+  RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "%s: bad dtype %d", fn, dtype);
+  RSC_CHECK_ARG(act == few::ACT_GELU || act == few::ACT_RELU, "%s: act must be 0 (gelu) or 1 (relu), got %d", fn, act);
   return RSC_OK;
 }
 
-extern "C" int rsc_bias_gelu_bwd(const void *h, const float *bias, const void *dy, void *dh, float *dbias, int64_t rows,
-                                 int C, int dtype, void *stream) {
-  RSC_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 8192,
-                "rsc_bias_gelu_bwd: need rows > 0, C %% 8 == 0, C <= 8192 (rows=%lld, C=%d)", (long long)rows, C);
-  RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "rsc_bias_gelu_bwd: bad dtype %d", dtype);
-  RSC_CHECK_ARG(h && bias && dy && dh && dbias, "rsc_bias_gelu_bwd: null pointer");
+extern "C" int rsc_bias_act_fwd(const void *h, const float *bias, void *y, int64_t rows, int C, int act, int dtype,
+                                void *stream) {
+  if (int e = bias_act_check("rsc_bias_act_fwd", rows, C, act, dtype)) return e;
+  RSC_CHECK_ARG(h && bias && y, "rsc_bias_act_fwd: null pointer");
+  const int64_t nvec = rows * (C / 8);
+  const int grid = bg_grid(nvec, C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define BAF(T, A) few::bias_act_fwd_kernel<T, A><<<grid, 256, 0, st>>>((const T *)h, bias, (T *)y, nvec, C / 8)
+  if (dtype == RSC_F32) {
+    if (act == few::ACT_GELU) BAF(float, few::ACT_GELU); else BAF(float, few::ACT_RELU);
+  } else {
+    if (act == few::ACT_GELU) BAF(__nv_bfloat16, few::ACT_GELU); else BAF(__nv_bfloat16, few::ACT_RELU);
+  }
+#undef BAF
+  RSC_CHECK_LAUNCH("rsc_bias_act_fwd");
+  return RSC_OK;
+}
+
+extern "C" int rsc_bias_act_bwd(const void *h, const float *bias, const void *dy, void *dh, float *dbias, int64_t rows,
+                                int C, int act, int dtype, void *stream) {
+  if (int e = bias_act_check("rsc_bias_act_bwd", rows, C, act, dtype)) return e;
+  RSC_CHECK_ARG(h && bias && dy && dh && dbias, "rsc_bias_act_bwd: null pointer");
   const int64_t nvec = rows * (C / 8);
   const int grid = bg_grid(nvec, C / 8);
   const size_t smem = (size_t)C * sizeof(float);
-  if (dtype == RSC_F32)
-    few::bias_gelu_bwd_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const float *)h, bias, (const float *)dy,
-                                                                                 (float *)dh, dbias, nvec, C / 8);
-  else
-    few::bias_gelu_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16 *)h, bias, (const __nv_bfloat16 *)dy, (__nv_bfloat16 *)dh, dbias, nvec, C / 8);
-  RSC_CHECK_LAUNCH("rsc_bias_gelu_bwd");
+  cudaStream_t st = (cudaStream_t)stream;
+#define BAB(T, A) \
+  few::bias_act_bwd_kernel<T, A><<<grid, 256, smem, st>>>((const T *)h, bias, (const T *)dy, (T *)dh, dbias, nvec, C / 8)
+  if (dtype == RSC_F32) {
+    if (act == few::ACT_GELU) BAB(float, few::ACT_GELU); else BAB(float, few::ACT_RELU);
+  } else {
+    if (act == few::ACT_GELU) BAB(__nv_bfloat16, few::ACT_GELU); else BAB(__nv_bfloat16, few::ACT_RELU);
+  }
+#undef BAB
+  RSC_CHECK_LAUNCH("rsc_bias_act_bwd");
   return RSC_OK;
 }

@@ -221,8 +221,21 @@ class FFN(nn.Module):
         self.dropout_layer = build_dropout(dropout_layer)
         self.add_identity = add_identity
 
+    def _mlp(self, x):
+        """self.layers(x) with Linear + bias + activation of the hidden layers as GEMM + ONE fused pass
+        (ops.bias_relu / ops.bias_gelu: the bias gradient comes out of the activation's backward pass)."""
+        for layer in list(self.layers)[:-2]:
+            lin, act = layer[0], layer[1]
+            code = ops.ACT_RELU if isinstance(act, nn.ReLU) else (
+                ops.ACT_GELU if isinstance(act, nn.GELU) and act.approximate == 'none' else None)
+            if code is not None and lin.bias is not None and ops.bias_act_supported(x, lin.out_features):
+                x = layer[2](ops._BiasAct.apply(ops.linear(x, lin.weight, None), lin.bias, code))
+            else:
+                x = layer(x)
+        return self.layers[-1](self.layers[-2](x))
+
     def forward(self, x, identity=None):
-        out = self.layers(x)
+        out = self._mlp(x)
         if not self.add_identity:
             return self.dropout_layer(out)
         if identity is None:
@@ -344,6 +357,27 @@ class MultiScaleDeformableAttention(nn.Module):
         nn.init.xavier_uniform_(self.output_proj.weight)
         nn.init.constant_(self.output_proj.bias, 0.)
 
+    def _sample_eager(self, value, sampling_offsets, attention_weights, reference_points, spatial_shapes,
+                      level_start_index):
+        """mmcv's op-by-op tail: softmax, sampling locations, then the sampling kernel."""
+        bs, num_query = sampling_offsets.shape[:2]
+        attention_weights = attention_weights.float().softmax(-1).view(
+            bs, num_query, self.num_heads, self.num_levels, self.num_points)
+        sampling_offsets = sampling_offsets.float()
+        reference_points = reference_points.float()
+        if reference_points.shape[-1] == 2:
+            offset_normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1).float()
+            sampling_locations = reference_points[:, :, None, :, None, :] + \
+                sampling_offsets / offset_normalizer[None, None, None, :, None, :]
+        elif reference_points.shape[-1] == 4:
+            sampling_locations = reference_points[:, :, None, :, None, :2] + \
+                sampling_offsets / self.num_points * reference_points[:, :, None, :, None, 2:] * 0.5
+        else:
+            raise ValueError('Last dim of reference_points must be 2 or 4, but get %d instead.'
+                             % reference_points.shape[-1])
+        return ops.ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                                  self.im2col_step)
+
     def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_padding_mask=None,
                 reference_points=None, spatial_shapes=None, level_start_index=None, **kwargs):
         if value is None:
@@ -365,22 +399,13 @@ class MultiScaleDeformableAttention(nn.Module):
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
         attention_weights = self.attention_weights(query).view(
             bs, num_query, self.num_heads, self.num_levels * self.num_points)
-        attention_weights = attention_weights.float().softmax(-1).view(
-            bs, num_query, self.num_heads, self.num_levels, self.num_points)
-        sampling_offsets = sampling_offsets.float()
-        reference_points = reference_points.float()
-        if reference_points.shape[-1] == 2:
-            offset_normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1).float()
-            sampling_locations = reference_points[:, :, None, :, None, :] + \
-                sampling_offsets / offset_normalizer[None, None, None, :, None, :]
-        elif reference_points.shape[-1] == 4:
-            sampling_locations = reference_points[:, :, None, :, None, :2] + \
-                sampling_offsets / self.num_points * reference_points[:, :, None, :, None, 2:] * 0.5
+        if ops.msda_fused_supported(value, sampling_offsets, reference_points):
+            # softmax, sampling-location arithmetic and the sampling op in one kernel (no fp32 (B,Nq,8,4,4,2) temporaries)
+            output = ops.ms_deform_attn_fused(value, spatial_shapes, level_start_index, sampling_offsets,
+                                              attention_weights, reference_points)
         else:
-            raise ValueError('Last dim of reference_points must be 2 or 4, but get %d instead.'
-                             % reference_points.shape[-1])
-        output = ops.ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
-                                    self.im2col_step)
+            output = self._sample_eager(value, sampling_offsets, attention_weights, reference_points, spatial_shapes,
+                                        level_start_index)
         output = self.output_proj(output)
         if not self.batch_first:
             output = output.permute(1, 0, 2)

@@ -319,9 +319,12 @@ def add_ln(identity, x, bias, scale, gamma, beta, eps=1e-5):
     return _AddLN.apply(identity, x, bias, scale, gamma, beta, eps)
 
 
-class _BiasGelu(torch.autograd.Function):
+ACT_GELU, ACT_RELU = 0, 1
+
+
+class _BiasAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, bias):
+    def forward(ctx, h, bias, act):
         _cuda(h, bias)
         hc = h.contiguous()
         C = hc.shape[-1]
@@ -329,28 +332,38 @@ class _BiasGelu(torch.autograd.Function):
         b32 = _f32(bias)
         y = torch.empty_like(hc)
         with torch.cuda.device(h.device):
-            call('rsc_bias_gelu_fwd', hc.data_ptr(), b32.data_ptr(), y.data_ptr(), rows, C, _dt(hc), _stream(),
+            call('rsc_bias_act_fwd', hc.data_ptr(), b32.data_ptr(), y.data_ptr(), rows, C, act, _dt(hc), _stream(),
                  alg_bytes=2 * hc.numel() * hc.element_size())
         ctx.save_for_backward(hc, b32)
-        ctx.meta = (rows, C, bias.dtype, _flat_grad(bias))
+        ctx.meta = (rows, C, act, bias.dtype, _flat_grad(bias))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         hc, b32 = ctx.saved_tensors
-        rows, C, bdt, gbias = ctx.meta
+        rows, C, act, bdt, gbias = ctx.meta
         dy = dy.contiguous()
         dh = torch.empty_like(hc)
         dbias = gbias if gbias is not None else torch.zeros(C, dtype=torch.float32, device=hc.device)
         with torch.cuda.device(hc.device):
-            call('rsc_bias_gelu_bwd', hc.data_ptr(), b32.data_ptr(), dy.data_ptr(), dh.data_ptr(), dbias.data_ptr(), rows, C,
-                 _dt(hc), _stream(), alg_bytes=3 * hc.numel() * hc.element_size())
-        return dh, None if gbias is not None else dbias.to(bdt)
+            call('rsc_bias_act_bwd', hc.data_ptr(), b32.data_ptr(), dy.data_ptr(), dh.data_ptr(), dbias.data_ptr(), rows, C,
+                 act, _dt(hc), _stream(), alg_bytes=3 * hc.numel() * hc.element_size())
+        return dh, None if gbias is not None else dbias.to(bdt), None
 
 
 def bias_gelu(h, bias):
     """gelu(h + bias) (erf form); the backward also produces the bias gradient (column sums) in the same pass."""
-    return _BiasGelu.apply(h, bias)
+    return _BiasAct.apply(h, bias, ACT_GELU)
+
+
+def bias_relu(h, bias):
+    """relu(h + bias) with the bias gradient out of the same backward pass."""
+    return _BiasAct.apply(h, bias, ACT_RELU)
+
+
+def bias_act_supported(x, out_features):
+    return x.is_cuda and out_features % 8 == 0 and out_features <= 8192 and \
+        (torch.get_autocast_dtype('cuda') if torch.is_autocast_enabled('cuda') else x.dtype) in (torch.float32, torch.bfloat16)
 
 
 def layer_norm(x, gamma, beta, eps=1e-5, out_dtype=None):
@@ -410,6 +423,60 @@ class MultiScaleDeformableAttnFunction(torch.autograd.Function):
                  alg_bytes=(value.numel() + grad_output.numel()) * value.element_size() + 2 * value.numel() * 4 +
                  2 * (loc.numel() + aw.numel()) * 4)
         return gv.to(value.dtype), None, None, gl.to(loc_dt), ga.to(aw_dt), None
+
+
+class _MSDAFused(torch.autograd.Function):
+    """softmax(logits) + sampling locations from (reference points, raw offsets) + ms_deform_attn in one kernel
+    (rsc_msda_fused_{fwd,bwd}); value (B,Nv,heads,32), offsets (B,Nq,heads,L,P,2), logits (B,Nq,heads,L*P),
+    ref (B,Nq,L,2|4) fp32 without gradient."""
+
+    @staticmethod
+    def forward(ctx, value, shapes, starts, offsets, logits, ref):
+        _cuda(value, shapes, starts, offsets, logits, ref)
+        B, Nv, heads, D = value.shape
+        _, Nq, _, L, P, _ = offsets.shape
+        value = value.contiguous()
+        offsets = offsets.contiguous()
+        logits = logits.to(offsets.dtype).contiguous()
+        ref = ref.float().contiguous()
+        shapes = shapes.to(torch.int64).contiguous()
+        starts = starts.to(torch.int64).contiguous()
+        out = torch.empty(B, Nq, heads * D, dtype=value.dtype, device=value.device)
+        with torch.cuda.device(value.device):
+            call('rsc_msda_fused_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
+                 logits.data_ptr(), ref.data_ptr(), out.data_ptr(), B, Nv, Nq, heads, L, P, ref.shape[-1], _dt(value),
+                 _dt(offsets), _stream(),
+                 alg_bytes=(value.numel() + out.numel()) * value.element_size() +
+                 (offsets.numel() + logits.numel()) * offsets.element_size())
+        ctx.save_for_backward(value, shapes, starts, offsets, logits, ref)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        value, shapes, starts, offsets, logits, ref = ctx.saved_tensors
+        B, Nv, heads, D = value.shape
+        _, Nq, _, L, P, _ = offsets.shape
+        grad_output = grad_output.contiguous()
+        gv = torch.zeros(value.shape, dtype=torch.float32, device=value.device)
+        go = torch.empty_like(offsets)
+        gl = torch.empty_like(logits)
+        with torch.cuda.device(value.device):
+            call('rsc_msda_fused_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
+                 logits.data_ptr(), ref.data_ptr(), grad_output.data_ptr(), gv.data_ptr(), go.data_ptr(), gl.data_ptr(),
+                 B, Nv, Nq, heads, L, P, ref.shape[-1], _dt(value), _dt(offsets), _stream(),
+                 alg_bytes=(value.numel() + grad_output.numel()) * value.element_size() + 2 * value.numel() * 4 +
+                 2 * (offsets.numel() + logits.numel()) * offsets.element_size())
+        return gv.to(value.dtype), None, None, go, gl, None
+
+
+def msda_fused_supported(value, offsets, ref):
+    return (value.is_cuda and value.shape[-1] == 32 and value.shape[-2] % 4 == 0 and
+            offsets.shape[-3] * offsets.shape[-2] == 16 and ref.shape[-1] in (2, 4) and not ref.requires_grad and
+            value.dtype in (torch.float32, torch.bfloat16) and offsets.dtype in (torch.float32, torch.bfloat16))
+
+
+def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offsets, logits, reference_points):
+    return _MSDAFused.apply(value, spatial_shapes, level_start_index, offsets, logits, reference_points)
 
 
 def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step=64):

@@ -562,3 +562,57 @@ def test_bias_gelu_matches_eager(rows, C, dtype):
     assert_rel(gy, y, 1e-5 if dtype == torch.float32 else 6e-3, 'y')
     assert_rel(gh.grad, rh.grad, 1e-4 if dtype == torch.float32 else 1e-2, 'dh')
     assert_rel(gb.grad, rb.grad, 1e-4 if dtype == torch.float32 else 2e-2, 'dbias')
+    # ReLU variant (encoder / decoder FFNs)
+    rh2, rb2 = h.float().clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    (F.relu(rh2 + rb2) * w).sum().backward()
+    gh2, gb2 = h.detach().cuda().requires_grad_(True), bias.detach().cuda().requires_grad_(True)
+    gy2 = ops.bias_relu(gh2, gb2)
+    (gy2.float() * w.cuda()).sum().backward()
+    assert_rel(gy2, F.relu(rh2 + rb2), 1e-6 if dtype == torch.float32 else 6e-3, 'relu y')
+    assert_rel(gh2.grad, rh2.grad, 1e-6 if dtype == torch.float32 else 1e-2, 'relu dh')
+    assert_rel(gb2.grad, rb2.grad, 1e-5 if dtype == torch.float32 else 2e-2, 'relu dbias')
+
+
+# ---------------------------------------------------------------------------
+# a10/a11: fused softmax + sampling locations + ms_deform_attn
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('ref_dim', [2, 4])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_msda_fused_matches_oracle_chain(ref_dim, dtype):
+    """rsc_msda_fused_{fwd,bwd} == softmax + location arithmetic (mmcv MultiScaleDeformableAttention.forward)
+    + the oracle sampling op, values and gradients w.r.t. value / offsets / logits, incl. samples that leave
+    the feature maps."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(7 + ref_dim)
+    shapes = [(12, 9), (6, 5), (3, 3), (2, 2)]
+    B, heads, L, P = 2, 8, 4, 4
+    Nv = sum(h * w for h, w in shapes)
+    Nq = 37
+    value = torch.randn(B, Nv, heads, 32, generator=g).to(dtype)
+    offsets = (torch.randn(B, Nq, heads, L, P, 2, generator=g) * 3).to(dtype)
+    logits = torch.randn(B, Nq, heads, L * P, generator=g).to(dtype)
+    ref = torch.rand(B, Nq, L, ref_dim, generator=g)
+    if ref_dim == 4:
+        ref[..., 2:] = ref[..., 2:] * 0.5 + 0.05
+    wout = torch.randn(B, Nq, heads * 32, generator=g)
+    # oracle chain in fp32 on the same (rounded) inputs
+    rv, ro, rl = (t.float().clone().requires_grad_(True) for t in (value, offsets, logits))
+    aw = rl.softmax(-1).view(B, Nq, heads, L, P)
+    if ref_dim == 2:
+        norm = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32)
+        loc = ref[:, :, None, :, None, :] + ro / norm[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None, :, None, :2] + ro / P * ref[:, :, None, :, None, 2:] * 0.5
+    want = otr.ms_deform_attn_core(rv, shapes, loc, aw)
+    (want * wout).sum().backward()
+    gv, go, gl = (t.detach().cuda().requires_grad_(True) for t in (value, offsets, logits))
+    ss = torch.tensor(shapes).cuda()
+    st = torch.tensor([0] + list(torch.tensor([h * w for h, w in shapes]).cumsum(0)[:-1])).cuda()
+    assert ops.msda_fused_supported(gv, go, ref.cuda())
+    got = ops.ms_deform_attn_fused(gv, ss, st, go, gl, ref.cuda())
+    (got.float() * wout.cuda()).sum().backward()
+    f32 = dtype == torch.float32
+    assert_rel(got, want, 1e-5 if f32 else 6e-3, 'out')
+    assert_rel(gv.grad, rv.grad, 1e-4 if f32 else 1e-2, 'd value')
+    assert_rel(go.grad, ro.grad, 1e-4 if f32 else 1.5e-2, 'd offsets')
+    assert_rel(gl.grad, rl.grad, 1e-4 if f32 else 1.5e-2, 'd logits')
