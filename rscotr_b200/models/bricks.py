@@ -229,7 +229,7 @@ class FFN(nn.Module):
             code = ops.ACT_RELU if isinstance(act, nn.ReLU) else (
                 ops.ACT_GELU if isinstance(act, nn.GELU) and act.approximate == 'none' else None)
             if code is not None and lin.bias is not None and ops.bias_act_supported(x, lin.out_features):
-                x = layer[2](ops._BiasAct.apply(ops.linear(x, lin.weight, None), lin.bias, code))
+                x = layer[2](ops.bias_act(ops.linear(x, lin.weight, None), lin.bias, code))
             else:
                 x = layer(x)
         return self.layers[-1](self.layers[-2](x))

@@ -220,7 +220,10 @@ class DinoTransformer(nn.Module):
                     reference_points=reference_points, grid=grid)
 
     def forward(self, mlvl_feats, mlvl_masks, query_embed, mlvl_pos_embeds, dn_label_query, dn_bbox_query, attn_mask,
-                encoder, reg_branches=None, cls_branches=None, **kwargs):
+                encoder, reg_branches=None, cls_branches=None, no_padding=False, **kwargs):
+        """no_padding: the caller knows on the host that no image of the batch is padded (every mask is all-False):
+        the key-padding masks are then not handed to the attention modules at all (mmcv zero-fills `value` under the
+        mask with a clone + masked_fill per layer, forward and backward, even when the mask is empty)."""
         assert self.as_two_stage and query_embed is None, 'as_two_stage must be True for DINO'
         shapes_py = [tuple(f.shape[-2:]) for f in mlvl_feats]
         dev = mlvl_feats[0].device
@@ -241,8 +244,9 @@ class DinoTransformer(nn.Module):
 
         feat_flatten = feat_flatten.permute(1, 0, 2)
         lvl_pos_embed_flatten = lvl_pos_embed_flatten.permute(1, 0, 2)
+        attn_kpm = None if no_padding else mask_flatten
         memory = encoder(query=feat_flatten, key=None, value=None, query_pos=lvl_pos_embed_flatten,
-                         query_key_padding_mask=mask_flatten, spatial_shapes=spatial_shapes,
+                         query_key_padding_mask=attn_kpm, spatial_shapes=spatial_shapes,
                          reference_points=reference_points, level_start_index=level_start_index,
                          valid_ratios=valid_ratios, **kwargs)
         memory = memory.permute(1, 0, 2)
@@ -272,7 +276,7 @@ class DinoTransformer(nn.Module):
         query = query.permute(1, 0, 2)
         memory = memory.permute(1, 0, 2)
         inter_states, inter_references = self.decoder(
-            query=query, key=None, value=memory, attn_masks=attn_mask, key_padding_mask=mask_flatten,
+            query=query, key=None, value=memory, attn_masks=attn_mask, key_padding_mask=attn_kpm,
             reference_points=reference_points, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
             valid_ratios=valid_ratios, reg_branches=reg_branches, **kwargs)
         return inter_states, inter_references, topk_score, topk_anchor
@@ -605,24 +609,26 @@ class DINOHead(nn.Module):
             for feat in mlvl_feats:
                 masks.append(F.interpolate(img_masks[None], size=feat.shape[-2:]).to(torch.bool).squeeze(0))
                 pes.append(self.positional_encoding(masks[-1]))
-            return masks, pes
+            no_pad = all(tuple(m['img_shape'][:2]) == (input_img_h, input_img_w) for m in img_metas)
+            return masks, pes, no_pad
         key = (tuple(tuple(m['img_shape'][:2]) for m in img_metas), (input_img_h, input_img_w),
                tuple(tuple(f.shape[-2:]) for f in mlvl_feats), str(mlvl_feats[0].device))
         if not hasattr(self, '_geom'):
             self._geom = GeomCache()
-        mlvl_masks, mlvl_positional_encodings = self._geom.get(key, make)
+        mlvl_masks, mlvl_positional_encodings, no_pad = self._geom.get(key, make)
         hs, inter_references, topk_score, topk_anchor = self.transformer(
             mlvl_feats, mlvl_masks, None, mlvl_positional_encodings, dn_label_query, dn_bbox_query, attn_mask, encoder,
             reg_branches=self.reg_branches if self.with_box_refine else None,
-            cls_branches=self.cls_branches if self.as_two_stage else None)
+            cls_branches=self.cls_branches if self.as_two_stage else None, no_padding=no_pad)
         hs = hs.permute(0, 2, 1, 3)
         if dn_label_query is not None and dn_label_query.size(1) == 0:
             hs[0] += self.label_embedding.weight[0, 0] * 0.0
         outputs_classes, outputs_coords = [], []
-        for lvl in range(hs.shape[0]):
-            reference = inverse_sigmoid(inter_references[lvl], eps=1e-3)
-            outputs_class = self.cls_branches[lvl](hs[lvl])
-            tmp = self.reg_branches[lvl](hs[lvl]).float()
+        # (unbind once: indexing per level would put one zero-fill + copy + add per level into the backward)
+        for lvl, (hs_l, ref_l) in enumerate(zip(hs.unbind(0), inter_references.unbind(0)[:hs.shape[0]])):
+            reference = inverse_sigmoid(ref_l, eps=1e-3)
+            outputs_class = self.cls_branches[lvl](hs_l)
+            tmp = self.reg_branches[lvl](hs_l).float()
             if reference.shape[-1] == 4:
                 tmp = tmp + reference
             else:

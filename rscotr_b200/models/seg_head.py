@@ -97,7 +97,8 @@ class MlvlSegPixelDecoder(nn.Module):
         level_start_index, reference_points, valid_radios = geo['level_start_index'], geo['reference_points'], \
             geo['valid_radios']
         memory = encoder(query=encoder_inputs, key=None, value=None, query_pos=level_positional_encodings,
-                         key_pos=None, attn_masks=None, key_padding_mask=None, query_key_padding_mask=padding_masks,
+                         key_pos=None, attn_masks=None, key_padding_mask=None,
+                         query_key_padding_mask=None,      # (the reference passes an all-False mask: same result)
                          spatial_shapes=spatial_shapes, reference_points=reference_points,
                          level_start_index=level_start_index, valid_radios=valid_radios)
         memory = memory.permute(1, 2, 0)

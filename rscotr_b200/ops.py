@@ -121,7 +121,7 @@ def window_reverse(windows, B, H, W, ws, shift=0):
 # ---------------------------------------------------------------------------
 class _WMSA(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, qkv_bias, table, H, W, heads, ws, shift, scale):
+    def forward(ctx, qkv, qkv_bias, table, H, W, heads, ws, shift, scale, fg):
         _cuda(qkv, table)
         B = qkv.shape[0]
         C = qkv.shape[-1] // 3
@@ -133,24 +133,29 @@ class _WMSA(torch.autograd.Function):
             call('rsc_wmsa_fwd', qkv.data_ptr(), _p(bias32), table32.data_ptr(), out.data_ptr(), B, H, W, C, heads,
                  ws, shift, scale, _dt(qkv), _stream(), alg_bytes=4 * _padded_tokens(B, H, W, ws) * C * qkv.element_size())
         ctx.save_for_backward(qkv, bias32, table32)
-        ctx.meta = (B, H, W, C, heads, ws, shift, scale, qkv_bias is not None and qkv_bias.dtype, table.dtype)
+        ctx.meta = (B, H, W, C, heads, ws, shift, scale, qkv_bias is not None and qkv_bias.dtype, table.dtype, fg)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         qkv, bias32, table32 = ctx.saved_tensors
-        B, H, W, C, heads, ws, shift, scale, bias_dtype, table_dtype = ctx.meta
+        B, H, W, C, heads, ws, shift, scale, bias_dtype, table_dtype, fg = ctx.meta
         dout = dout.contiguous()
         dqkv = torch.empty_like(qkv)
-        dtable = torch.zeros_like(table32)
-        dbias = torch.zeros_like(bias32) if bias32 is not None else None
+        # the kernel ACCUMULATES d(table) / d(qkv bias) with atomics: straight into the flat gradient buffer when
+        # the step engine attached one
+        direct = fg is not None and fg[1] is not None and (bias32 is None or fg[0] is not None)
+        dtable = fg[1] if direct else torch.zeros_like(table32)
+        dbias = None if bias32 is None else (fg[0] if direct else torch.zeros_like(bias32))
         with torch.cuda.device(qkv.device):
             call('rsc_wmsa_bwd', qkv.data_ptr(), _p(bias32), table32.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
                  dtable.data_ptr(), _p(dbias), B, H, W, C, heads, ws, shift, scale, _dt(qkv), _stream(),
                  alg_bytes=7 * _padded_tokens(B, H, W, ws) * C * qkv.element_size())
+        if direct:
+            return (dqkv,) + (None,) * 10
         if dbias is not None:
             dbias = dbias.to(bias_dtype)
-        return dqkv, dbias, dtable.to(table_dtype), None, None, None, None, None, None
+        return dqkv, dbias, dtable.to(table_dtype), None, None, None, None, None, None, None
 
 
 def wmsa(qkv, qkv_bias, table, hw, heads, ws=7, shift=0, scale=None):
@@ -162,7 +167,8 @@ def wmsa(qkv, qkv_bias, table, hw, heads, ws=7, shift=0, scale=None):
     C = qkv.shape[-1] // 3
     if scale is None:
         scale = (C // heads) ** -0.5
-    return _WMSA.apply(qkv, qkv_bias, table, H, W, heads, ws, shift, float(scale))
+    fg = (None if qkv_bias is None else _flat_grad(qkv_bias), _flat_grad(table))
+    return _WMSA.apply(qkv, qkv_bias, table, H, W, heads, ws, shift, float(scale), fg)
 
 
 # ---------------------------------------------------------------------------
@@ -212,7 +218,7 @@ def patch_merge_ln(x, hw, gamma, beta, eps=1e-5):
 # ---------------------------------------------------------------------------
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, out_dtype):
+    def forward(ctx, x, gamma, beta, eps, out_dtype, fg):
         _cuda(x, gamma, beta)
         C = x.shape[-1]
         xc = x.contiguous()
@@ -226,7 +232,7 @@ class _LayerNorm(torch.autograd.Function):
                  rstd.data_ptr(), rows, C, eps, _dt(xc), _dt(y), _stream(),
                  alg_bytes=xc.numel() * (xc.element_size() + y.element_size()))
         ctx.save_for_backward(xc, g32, mean, rstd)
-        ctx.meta = (rows, C, gamma.dtype, beta.dtype, _flat_grad(gamma), _flat_grad(beta))
+        ctx.meta = (rows, C, gamma.dtype, beta.dtype, fg[0], fg[1])
         return y
 
     @staticmethod
@@ -243,8 +249,8 @@ class _LayerNorm(torch.autograd.Function):
                  dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, C, _dt(xc), _dt(dy), _stream(),
                  alg_bytes=xc.numel() * (2 * xc.element_size() + dy.element_size()))
         if direct:
-            return dx, None, None, None, None
-        return dx, dg.to(gdt), db.to(bdt), None, None
+            return dx, None, None, None, None, None
+        return dx, dg.to(gdt), db.to(bdt), None, None, None
 
 
 def _flat_grad(p):
@@ -266,7 +272,7 @@ class _AddLN(torch.autograd.Function):
     """(r, n) = (identity + (x + bias) * scale[sample], LayerNorm(r)); see include/rscotr.h."""
 
     @staticmethod
-    def forward(ctx, identity, x, bias, scale, gamma, beta, eps):
+    def forward(ctx, identity, x, bias, scale, gamma, beta, eps, fg):
         _cuda(identity, x, gamma, beta)
         C = x.shape[-1]
         idc, xc = identity.contiguous(), x.contiguous()
@@ -284,7 +290,7 @@ class _AddLN(torch.autograd.Function):
                  alg_bytes=4 * xc.numel() * xc.element_size())
         ctx.save_for_backward(r, g32, mean, rstd, s32)
         ctx.meta = (rows, rps, C, None if bias is None else bias.dtype, gamma.dtype, beta.dtype,
-                    None if bias is None else _flat_grad(bias), _flat_grad(gamma), _flat_grad(beta),
+                    fg[0], fg[1], fg[2],
                     ctx.needs_input_grad[1])
         return r, n
 
@@ -311,12 +317,13 @@ class _AddLN(torch.autograd.Function):
                  _dt(r), _stream(), alg_bytes=(4 + (dr_ext is not None) + (dx is not None)) * r.numel() * r.element_size())
         return (d_id, (dx if dx is not None else d_id) if need_dx else None,
                 None if (bdt is None or gbias is not None) else dbias.to(bdt), None,
-                None if direct else dg.to(gdt), None if direct else db.to(bedt), None)
+                None if direct else dg.to(gdt), None if direct else db.to(bedt), None, None)
 
 
 def add_ln(identity, x, bias, scale, gamma, beta, eps=1e-5):
     """r = identity + (x + bias) * scale[b]; n = LayerNorm(r).  bias (C,) / scale (B,) may be None."""
-    return _AddLN.apply(identity, x, bias, scale, gamma, beta, eps)
+    fg = (None if bias is None else _flat_grad(bias), _flat_grad(gamma), _flat_grad(beta))
+    return _AddLN.apply(identity, x, bias, scale, gamma, beta, eps, fg)
 
 
 ACT_GELU, ACT_RELU = 0, 1
@@ -324,7 +331,7 @@ ACT_GELU, ACT_RELU = 0, 1
 
 class _BiasAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, bias, act):
+    def forward(ctx, h, bias, act, fg):
         _cuda(h, bias)
         hc = h.contiguous()
         C = hc.shape[-1]
@@ -335,7 +342,7 @@ class _BiasAct(torch.autograd.Function):
             call('rsc_bias_act_fwd', hc.data_ptr(), b32.data_ptr(), y.data_ptr(), rows, C, act, _dt(hc), _stream(),
                  alg_bytes=2 * hc.numel() * hc.element_size())
         ctx.save_for_backward(hc, b32)
-        ctx.meta = (rows, C, act, bias.dtype, _flat_grad(bias))
+        ctx.meta = (rows, C, act, bias.dtype, fg)
         return y
 
     @staticmethod
@@ -348,17 +355,21 @@ class _BiasAct(torch.autograd.Function):
         with torch.cuda.device(hc.device):
             call('rsc_bias_act_bwd', hc.data_ptr(), b32.data_ptr(), dy.data_ptr(), dh.data_ptr(), dbias.data_ptr(), rows, C,
                  act, _dt(hc), _stream(), alg_bytes=3 * hc.numel() * hc.element_size())
-        return dh, None if gbias is not None else dbias.to(bdt), None
+        return dh, None if gbias is not None else dbias.to(bdt), None, None
 
 
 def bias_gelu(h, bias):
     """gelu(h + bias) (erf form); the backward also produces the bias gradient (column sums) in the same pass."""
-    return _BiasAct.apply(h, bias, ACT_GELU)
+    return _BiasAct.apply(h, bias, ACT_GELU, _flat_grad(bias))
 
 
 def bias_relu(h, bias):
     """relu(h + bias) with the bias gradient out of the same backward pass."""
-    return _BiasAct.apply(h, bias, ACT_RELU)
+    return _BiasAct.apply(h, bias, ACT_RELU, _flat_grad(bias))
+
+
+def bias_act(h, bias, act):
+    return _BiasAct.apply(h, bias, act, _flat_grad(bias))
 
 
 def bias_act_supported(x, out_features):
@@ -371,7 +382,9 @@ def layer_norm(x, gamma, beta, eps=1e-5, out_dtype=None):
     (so the GEMM that follows reads bf16 directly) or x.dtype outside autocast."""
     if out_dtype is None:
         out_dtype = torch.get_autocast_dtype('cuda') if torch.is_autocast_enabled('cuda') else x.dtype
-    return _LayerNorm.apply(x, gamma, beta, float(eps), out_dtype)
+    # (the flat-gradient views are looked up HERE: inside Function.forward the parameters are re-wrapped and lose
+    # the attributes the step engine attached)
+    return _LayerNorm.apply(x, gamma, beta, float(eps), out_dtype, (_flat_grad(gamma), _flat_grad(beta)))
 
 
 # ---------------------------------------------------------------------------

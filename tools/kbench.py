@@ -44,7 +44,7 @@ def main():
                 dout = torch.randn(B, S * S, C, device=dev, dtype=dt)
                 Sp = (S + 6) // 7 * 7
                 alg = 4 * B * Sp * Sp * C * es           # read qkv + write out (padded tokens)
-                t = timeit(lambda: ops._WMSA.apply(qkv, bias, table, S, S, heads, 7, shift, 32 ** -0.5), flush=flush)
+                t = timeit(lambda: ops.wmsa(qkv, bias, table, (S, S), heads, 7, shift, 32 ** -0.5), flush=flush)
                 rows.append(dict(k='wmsa_fwd', dtype=str(dt), S=S, C=C, shift=shift, ms=t, gbs=alg / t / 1e6))
                 q2 = qkv.clone().requires_grad_(True)
                 o = ops.wmsa(q2, bias, table, (S, S), heads, 7, shift)
