@@ -342,10 +342,13 @@ def main():
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     hb = db = 0
+    engine.prefetch(host_batches[0])
     for i in range(args.steps):
         batch = host_batches[i % 6]
         hb += h2d_bytes(batch)
         o = engine.train_iter(batch)
+        if i + 1 < args.steps:
+            engine.prefetch(host_batches[(i + 1) % 6])                    # next step's H2D overlaps this step's compute
         _ = float(o['loss'].detach())                                     # D2H read of the step's result
         db += 4
     f1.record()

@@ -87,6 +87,7 @@ class StepEngine:
         self.iter = 0
         self._task_ranges = {}
         self.last_grad_norm = None
+        self._copy_stream = torch.cuda.Stream(self.device) if self.device.type == 'cuda' else None
 
     # -- flat parameter / gradient buffers ---------------------------------
     def _build_flat_grads(self):
@@ -286,6 +287,28 @@ class StepEngine:
             gA.replay()
         st.update(gA=gA, gB=gB, ctx=ctx, static=static, outputs=outputs, launches=nA + nB)
 
+    def prefetch(self, data_batch):
+        """Start the host->device copy of a (pinned) host batch on the copy stream while the current step is still
+        running; the train_iter call that receives the same batch object then only does a device-to-device copy
+        into the captured graph's input buffers.  (H2D prefetch on a copy stream.)  A no-op
+        until the batch's (task, shapes) signature has been captured."""
+        if self._copy_stream is None:
+            return
+        st = self._graphs.get(self._signature(data_batch))
+        if not st or 'static' not in st:
+            return
+        cs = self._copy_stream
+        if 'stage' not in st:
+            st['stage'] = _static_copy(st['static'], self.device)
+            cs.wait_stream(torch.cuda.current_stream(self.device))     # (the clones above ran on the main stream)
+        if st.get('stage_free') is not None:
+            cs.wait_event(st['stage_free'])              # the previous consumer of the staging buffers is done
+        with torch.cuda.stream(cs):
+            self._copy_in(st['stage'], data_batch)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        st['staged'] = (id(data_batch), ev)
+
     def train_iter(self, data_batch):
         """model.train_step + OptimizerHook.after_train_iter.  Returns train_step's outputs.
         After `graph_warmup` eager iterations of a (task, shapes) signature the iteration is
@@ -319,7 +342,15 @@ class StepEngine:
                 self.iter += 1
                 return outputs
         else:
-            self._copy_in(st['static'], data_batch)
+            staged = st.pop('staged', None)
+            if staged is not None and staged[0] == id(data_batch):
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(staged[1])
+                self._copy_in(st['static'], st['stage'])          # device-to-device
+                st['stage_free'] = torch.cuda.Event()
+                st['stage_free'].record(cur)
+            else:
+                self._copy_in(st['static'], data_batch)
             st['gA'].replay()
             if st['gB'] is not None:
                 self.model.train_step_host(st['ctx'])

@@ -188,3 +188,24 @@ def test_linear_colsum_bias_grad():
         tol = 1e-4 if dt == torch.float32 else 1e-2
         assert rel(y, yo) < tol and rel(x.grad, xo.grad) < tol and rel(w.grad, wo.grad) < tol
         assert rel(b.grad, bo.grad) < 1e-3
+
+
+def test_prefetch_matches_plain_copy():
+    """engine.prefetch (H2D on the copy stream into staging buffers) + train_iter == train_iter alone."""
+    from rscotr_b200.mtl.engine import StepEngine
+    finals = []
+    for use_prefetch in (False, True):
+        model, batch = _setup('cls', seed=11)
+        eng = StepEngine(model, dict(type='AdamW', lr=1e-3, weight_decay=1e-4), grad_clip=dict(max_norm=0.1, norm_type=2),
+                         device='cuda', compute_dtype=torch.float32, use_graphs=True)
+        b2 = {k: (v.clone() * 0.5 if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in batch.items()}
+        hosts = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()} for b in (batch, b2)]
+        for i in range(7):
+            hb = hosts[i % 2]
+            if use_prefetch:
+                eng.prefetch(hb)
+            out = eng.train_iter(hb)
+        finals.append((float(out['loss']), model.cls_head.fc.weight.detach().clone()))
+    # (bit equality is not expected: several gradient reductions use floating-point atomics)
+    assert abs(finals[0][0] - finals[1][0]) <= 1e-4 * abs(finals[0][0]), (finals[0][0], finals[1][0])
+    assert torch.allclose(finals[0][1], finals[1][1], rtol=1e-3, atol=2e-6)
