@@ -304,12 +304,12 @@ class MultiheadAttention(nn.Module):
             key_pos = query_pos
         same_qk = key is query
         if query_pos is not None:
-            query = query + query_pos
+            query = query + query_pos.to(query.dtype)
         same_qk = same_qk and key_pos is query_pos
         if same_qk:
             key = query
         elif key_pos is not None:
-            key = key + key_pos
+            key = key + key_pos.to(key.dtype)
         if self.batch_first:
             query, key, value = (t.transpose(0, 1) for t in (query, key, value))
         out = self._attend(query, key, value, attn_mask, key_padding_mask, same_qk)
@@ -385,8 +385,9 @@ class MultiScaleDeformableAttention(nn.Module):
         if identity is None:
             identity = query
         if query_pos is not None:
-            query = query + query_pos
-        if not self.batch_first:
+            query = query + query_pos.to(query.dtype)
+        batch_first = self.batch_first or kwargs.get('_batch_first', False)
+        if not batch_first:
             query = query.permute(1, 0, 2)
             value = value.permute(1, 0, 2)
         bs, num_query, _ = query.shape
@@ -407,7 +408,7 @@ class MultiScaleDeformableAttention(nn.Module):
             output = self._sample_eager(value, sampling_offsets, attention_weights, reference_points, spatial_shapes,
                                         level_start_index)
         output = self.output_proj(output)
-        if not self.batch_first:
+        if not batch_first:
             output = output.permute(1, 0, 2)
         return self.dropout(output) + identity
 
@@ -510,8 +511,23 @@ class DetrTransformerEncoder(TransformerLayerSequence):
             assert not self.pre_norm
             self.post_norm = None
 
-    def forward(self, *args, **kwargs):
-        x = super().forward(*args, **kwargs)
+    def forward(self, query, key=None, value=None, query_pos=None, **kwargs):
+        """mmdet DetrTransformerEncoder.forward on seq-first (N, B, C) tensors.  When every attention of the stack is
+        a MultiScaleDeformableAttention (the shared deformable encoder) and B > 1, the layers run BATCH-first inside:
+        mmcv permutes query / value / output in every layer, which for B > 1 is three strided copies plus batched
+        (instead of plain) GEMMs per layer; here the stack is transposed once on entry and once on exit."""
+        msda_only = all(isinstance(a, MultiScaleDeformableAttention) and not a.batch_first
+                        for layer in self.layers for a in layer.attentions)
+        if msda_only and query.shape[1] > 1 and key is None and value is None:
+            q = query.transpose(0, 1).contiguous()
+            pos = None if query_pos is None else query_pos.transpose(0, 1).to(q.dtype).contiguous()
+            x = super().forward(q, None, None, query_pos=pos, _batch_first=True, **kwargs)
+            if self.post_norm is not None:
+                x = self.post_norm(x)
+            return x.transpose(0, 1)
+        if query_pos is not None:
+            query_pos = query_pos.to(query.dtype)        # (fp32 sine encodings would promote every q + pos to fp32)
+        x = super().forward(query, key, value, query_pos=query_pos, **kwargs)
         if self.post_norm is not None:
             x = self.post_norm(x)
         return x

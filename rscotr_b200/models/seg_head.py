@@ -196,8 +196,12 @@ class Mask2FormerHead(nn.Module):
             decoder_input = self.decoder_input_projs[i](multi_scale_memorys[i])
             decoder_input = decoder_input.flatten(2).permute(2, 0, 1)
             decoder_inputs.append(decoder_input + self.level_embed.weight[i].view(1, 1, -1))
-        query_feat = self.query_feat.weight.unsqueeze(1).repeat((1, batch_size, 1))
-        query_embed = self.query_embed.weight.unsqueeze(1).repeat((1, batch_size, 1))
+        # (activations are in the compute dtype; fp32 embeddings / sine encodings would promote every q + pos add of
+        # the 9 decoder layers to fp32 and force a cast in front of each GEMM: align the dtype once)
+        adt = mask_features.dtype
+        decoder_positional_encodings = [p.to(adt) for p in decoder_positional_encodings]
+        query_feat = self.query_feat.weight.to(adt).unsqueeze(1).repeat((1, batch_size, 1))
+        query_embed = self.query_embed.weight.to(adt).unsqueeze(1).repeat((1, batch_size, 1))
         mask_pred, attn_mask = self.forward_head(query_feat, mask_features, multi_scale_memorys[0].shape[-2:])
         for i in range(self.num_transformer_decoder_layers):
             level_idx = i % self.num_transformer_feat_level
