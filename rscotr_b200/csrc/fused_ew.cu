@@ -436,7 +436,10 @@ extern "C" int rsc_add_ln_bwd(const void *r, const float *gamma, const float *me
   RSC_CHECK_ARG(few::ln_shape(C, vw, ev, l), "rsc_add_ln_bwd: unsupported channel count %d", C);
   RSC_CHECK_ARG(r && gamma && mean && rstd && dn && d_identity && dgamma && dbeta, "rsc_add_ln_bwd: null pointer");
   RSC_CHECK_ARG(!(scale && !dx), "rsc_add_ln_bwd: a per-sample scale needs a separate dx buffer");
-  const int rpb = (few::LN_THREADS / 32) * (32 / l);
+  // every CTA ends with 3*C global atomics (d gamma | d beta | d bias): keep >= 32 rows per CTA so that small
+  // tensors (13 294-token encoder maps) are not dominated by thousand-way same-address atomic contention
+  int rpb = (few::LN_THREADS / 32) * (32 / l);
+  if (rpb < 32) rpb = 32;
   int64_t fb = (rows + rpb - 1) / rpb;
   const int grid = (int)(fb < kNumSMs * 8 ? fb : kNumSMs * 8);
   cudaStream_t st = (cudaStream_t)stream;
@@ -463,7 +466,8 @@ static int bg_grid(int64_t nvec, int C8) {
     a = b, b = t;
   }
   const int m = C8 / a;                                   // grid must be a multiple of m
-  int64_t want = (nvec + 2 * 256 - 1) / (2 * 256);        // two vectors per thread per trip
+  int64_t want = (nvec + 16 * 256 - 1) / (16 * 256);      // >= 8 trips of two vectors per thread: the backward ends
+                                                          // with C global atomics per CTA
   const int64_t cap = (int64_t)kNumSMs * 8;
   if (want > cap) want = cap;
   want = (want + m - 1) / m * m;

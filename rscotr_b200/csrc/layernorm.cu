@@ -473,7 +473,9 @@ extern "C" int rsc_layernorm_bwd(const void *x, const float *gamma, const float 
   {
     int vw = 0, ev = 0, l = 32;
     if (ln_shape(C, vw, ev, l)) {
-      int64_t fb = (rows + (LN_THREADS / 32) * (32 / l) - 1) / ((LN_THREADS / 32) * (32 / l));
+      int rpb = (LN_THREADS / 32) * (32 / l);
+      if (rpb < 32) rpb = 32;        // >= 32 rows per CTA: each CTA ends with 2*C global atomics (d gamma | d beta)
+      int64_t fb = (rows + rpb - 1) / rpb;
       int fgrid = (int)(fb < kNumSMs * 8 ? fb : kNumSMs * 8);
       bool done = false;
       cudaStream_t st = (cudaStream_t)stream;
@@ -487,7 +489,7 @@ extern "C" int rsc_layernorm_bwd(const void *x, const float *gamma, const float 
       }
     }
   }
-  int64_t blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+  int64_t blocks = (rows + 127) / 128;
   int grid = (int)(blocks < kNumSMs * 4 ? blocks : kNumSMs * 4);
   LN_DISPATCH(in_dtype, out_dtype, ln_bwd_launch, (C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, mean, rstd, dy,
               dx, dgamma, dbeta, rows, C);

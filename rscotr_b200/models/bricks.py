@@ -19,6 +19,7 @@ from ..config import MODELS, build_from_cfg
 
 
 _CONST_CACHE = {}
+_DEFER = __import__('os').environ.get('RSC_NO_DEFER') is None     # A/B switch for the fused post-norm pairs
 
 
 def const_tensor(values, dtype, device):
@@ -234,7 +235,28 @@ class FFN(nn.Module):
                 x = layer(x)
         return self.layers[-1](self.layers[-2](x))
 
-    def forward(self, x, identity=None):
+    def _mlp_deferred(self, x):
+        """(last Linear's output WITHOUT bias, that bias) when the trailing dropouts are inactive, else None."""
+        last, drop = self.layers[-2], self.layers[-1]
+        active = self.training and (drop.p > 0. or (isinstance(self.dropout_layer, nn.Dropout) and self.dropout_layer.p > 0.)
+                                    or (isinstance(self.dropout_layer, DropPath) and self.dropout_layer.drop_prob > 0.))
+        if active or not self.add_identity or last.bias is None:
+            return None
+        for layer in list(self.layers)[:-2]:
+            lin, act = layer[0], layer[1]
+            code = ops.ACT_RELU if isinstance(act, nn.ReLU) else (
+                ops.ACT_GELU if isinstance(act, nn.GELU) and act.approximate == 'none' else None)
+            if code is not None and lin.bias is not None and ops.bias_act_supported(x, lin.out_features):
+                x = layer[2](ops.bias_act(ops.linear(x, lin.weight, None), lin.bias, code))
+            else:
+                x = layer(x)
+        return ops.linear(x, last.weight, None), last.bias
+
+    def forward(self, x, identity=None, _defer=False):
+        if _defer:
+            d = self._mlp_deferred(x)
+            if d is not None:
+                return d[0], d[1], (x if identity is None else identity)
         out = self._mlp(x)
         if not self.add_identity:
             return self.dropout_layer(out)
@@ -261,7 +283,7 @@ class MultiheadAttention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         self.dropout_layer = build_dropout(dropout_layer)
 
-    def _attend(self, query, key, value, attn_mask, key_padding_mask, same_qk=False):
+    def _attend(self, query, key, value, attn_mask, key_padding_mask, same_qk=False, defer=False):
         """nn.MultiheadAttention.forward(need_weights=False) on seq-first (L,B,E) tensors with the packed
         in_proj applied through ops.linear (bf16 shadow weights, gradients accumulated into the flat
         buffer; q and k share one GEMM when they read the same tensor) and the library SDPA core."""
@@ -290,6 +312,8 @@ class MultiheadAttention(nn.Module):
         out = F.scaled_dot_product_attention(q, k, v.to(q.dtype), attn_mask=mask,
                                              dropout_p=m.dropout if self.training else 0.0)
         out = out.permute(2, 0, 1, 3).reshape(L, B, E)
+        if defer:
+            return ops.linear(out, m.out_proj.weight, None)
         return ops.linear(out, m.out_proj.weight, m.out_proj.bias)
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None, attn_mask=None,
@@ -312,9 +336,15 @@ class MultiheadAttention(nn.Module):
             key = key + key_pos.to(key.dtype)
         if self.batch_first:
             query, key, value = (t.transpose(0, 1) for t in (query, key, value))
-        out = self._attend(query, key, value, attn_mask, key_padding_mask, same_qk)
+        drop_active = self.training and (self.proj_drop.p > 0. or (
+            isinstance(self.dropout_layer, nn.Dropout) and self.dropout_layer.p > 0.) or (
+            isinstance(self.dropout_layer, DropPath) and self.dropout_layer.drop_prob > 0.))
+        defer = kwargs.get('_defer', False) and not drop_active and self.attn.out_proj.bias is not None
+        out = self._attend(query, key, value, attn_mask, key_padding_mask, same_qk, defer)
         if self.batch_first:
             out = out.transpose(0, 1)
+        if defer:       # the caller fuses bias + residual + the following LayerNorm (ops.add_ln)
+            return out, self.attn.out_proj.bias, identity
         return identity + self.dropout_layer(self.proj_drop(out))
 
 
@@ -407,9 +437,12 @@ class MultiScaleDeformableAttention(nn.Module):
         else:
             output = self._sample_eager(value, sampling_offsets, attention_weights, reference_points, spatial_shapes,
                                         level_start_index)
-        output = self.output_proj(output)
+        defer = kwargs.get('_defer', False) and not (self.training and self.dropout.p > 0.)
+        output = ops.linear(output, self.output_proj.weight, None) if defer else self.output_proj(output)
         if not batch_first:
             output = output.permute(1, 0, 2)
+        if defer:       # the caller fuses bias + residual + the following LayerNorm (ops.add_ln)
+            return output, self.output_proj.bias, identity
         return self.dropout(output) + identity
 
 
@@ -457,27 +490,44 @@ class BaseTransformerLayer(nn.Module):
             attn_masks = [copy.copy(attn_masks) for _ in range(self.num_attn)]
         else:
             assert len(attn_masks) == self.num_attn
-        for layer in self.operation_order:
+        ops_ = self.operation_order
+        skip_norm = False
+        for pos_, layer in enumerate(ops_):
+            # post-norm pairs (sub-layer, LayerNorm): bias + residual add + LayerNorm in ONE kernel (ops.add_ln);
+            # the sub-layer then returns (output without bias, bias, identity) instead of adding itself
+            nxt_norm = (_DEFER and not self.pre_norm and pos_ + 1 < len(ops_) and ops_[pos_ + 1] == 'norm' and
+                        isinstance(self.norms[norm_index], LayerNorm) and ops.add_ln_supported(query))
             if layer == 'self_attn':
                 temp_key = temp_value = query
-                query = self.attentions[attn_index](
+                out = self.attentions[attn_index](
                     query, temp_key, temp_value, identity if self.pre_norm else None, query_pos=query_pos,
                     key_pos=query_pos, attn_mask=attn_masks[attn_index], key_padding_mask=query_key_padding_mask,
-                    **kwargs)
+                    _defer=nxt_norm, **kwargs)
                 attn_index += 1
-                identity = query
             elif layer == 'norm':
-                query = self.norms[norm_index](query)
+                if skip_norm:
+                    skip_norm = False
+                else:
+                    query = self.norms[norm_index](query)
                 norm_index += 1
+                continue
             elif layer == 'cross_attn':
-                query = self.attentions[attn_index](
+                out = self.attentions[attn_index](
                     query, key, value, identity if self.pre_norm else None, query_pos=query_pos, key_pos=key_pos,
-                    attn_mask=attn_masks[attn_index], key_padding_mask=key_padding_mask, **kwargs)
+                    attn_mask=attn_masks[attn_index], key_padding_mask=key_padding_mask, _defer=nxt_norm, **kwargs)
                 attn_index += 1
-                identity = query
             elif layer == 'ffn':
-                query = self.ffns[ffn_index](query, identity if self.pre_norm else None)
+                out = self.ffns[ffn_index](query, identity if self.pre_norm else None, _defer=nxt_norm)
                 ffn_index += 1
+            if isinstance(out, tuple):
+                x_, bias_, id_ = out
+                norm = self.norms[norm_index]
+                _, query = ops.add_ln(id_.to(x_.dtype), x_, bias_, None, norm.weight, norm.bias, norm.eps)
+                skip_norm = True
+            else:
+                query = out
+            if layer != 'ffn':
+                identity = query
         return query
 
 

@@ -280,8 +280,8 @@ class _AddLN(torch.autograd.Function):
         rows = xc.numel() // C
         rps = rows // xc.shape[0]
         b32, s32, g32, be32 = _f32(bias), _f32(scale), _f32(gamma), _f32(beta)
-        r = torch.empty_like(xc)
-        n = torch.empty_like(xc)
+        r = torch.empty(xc.shape, dtype=xc.dtype, device=xc.device)      # (canonical strides, not xc's)
+        n = torch.empty(xc.shape, dtype=xc.dtype, device=xc.device)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty_like(mean)
         with torch.cuda.device(x.device):
@@ -337,7 +337,7 @@ class _BiasAct(torch.autograd.Function):
         C = hc.shape[-1]
         rows = hc.numel() // C
         b32 = _f32(bias)
-        y = torch.empty_like(hc)
+        y = torch.empty(hc.shape, dtype=hc.dtype, device=hc.device)
         with torch.cuda.device(h.device):
             call('rsc_bias_act_fwd', hc.data_ptr(), b32.data_ptr(), y.data_ptr(), rows, C, act, _dt(hc), _stream(),
                  alg_bytes=2 * hc.numel() * hc.element_size())
@@ -751,8 +751,11 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, w, b, gw, gb):
-        # weight / bias: the (master) parameters autograd tracks; w / b: what the GEMM reads
-        y = torch.nn.functional.linear(x, w, b)
+        # weight / bias: the (master) parameters autograd tracks; w / b: what the GEMM reads.  The GEMM always sees a
+        # plain 2-D row-major operand: tensors like (N, 1, C) with strides (C, N*C, 1) are "contiguous" for torch but
+        # send F.linear's 3-D path to pathological cuBLAS kernels (a 512x8-tile GEMM, 30x slower, was observed)
+        x2 = x.reshape(-1, x.shape[-1])
+        y = torch.nn.functional.linear(x2, w, b).view(*x.shape[:-1], w.shape[0])
         ctx.save_for_backward(x, w)
         ctx.meta = (weight.dtype, None if bias is None else bias.dtype, gw, gb)
         return y
