@@ -273,6 +273,13 @@ int rsc_bias_act_bwd(const void *h, const float *bias, const void *dy, void *dh,
                      int act, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Patch-embedding gather (mmdet PatchEmbed = Conv2d(3, 96, k4, s4) -> LayerNorm).
+ * x (B,Cin,H,W) NCHW `in_dtype`, H % 4 == W % 4 == 0 -> y (B*(H/4)*(W/4), Cin*16) `out_dtype`,
+ * column order (c, kh, kw) = the Conv2d weight layout, so the projection is y @ weight.view(out, Cin*16)^T.
+ * ---------------------------------------------------------------------- */
+int rsc_patchify4(const void *x, void *y, int B, int Cin, int H, int W, int in_dtype, int out_dtype, void *stream);
+
+/* ------------------------------------------------------------------------
  * Flat fused AdamW (+ gradient-clip scale).  Replaces mmcv OptimizerHook's
  * clip_grad_norm_ scaling + torch.optim.AdamW.step over one contiguous fp32 range
  * (optimizer built by mtl/utils/optimizer.py:25-55).

@@ -40,6 +40,7 @@ _SIGS = {
     'rsc_add_ln_bwd': [_P] * 12 + [ctypes.c_int64, ctypes.c_int64, _I, _I, _P],
     'rsc_bias_act_fwd': [_P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
     'rsc_bias_act_bwd': [_P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, _I, _P],
+    'rsc_patchify4': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     'rsc_colsum': [_P, _P, ctypes.c_int64, _I, _I, _P],
     'rsc_msda_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'rsc_msda_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -349,6 +349,30 @@ __global__ void focal_kernel(const T *__restrict__ in, const int64_t *__restrict
   }
 }
 
+// ===========================================================================
+// Patch embedding gather: non-overlapping 4x4 patches of an NCHW image -> token-major (B*Ho*Wo, Cin*16) rows in
+// Conv2d weight order (c, kh, kw), cast to the GEMM dtype on the way.  mmdet PatchEmbed = Conv2d(3, 96, k4, s4):
+// with this gather it is ONE plain GEMM with K = 48 (the reference's cuDNN path converts the 123 MB fp32 batch
+// to channels-last first and runs an implicit-GEMM convolution forward and backward).
+// ===========================================================================
+template <typename TI, typename TO>
+__global__ void patchify4_kernel(const TI *__restrict__ x, TO *__restrict__ y, int64_t total, int Cin, int H, int W) {
+  const int Ho = H >> 2, Wo = W >> 2;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % Wo);
+    const int c = (int)((idx / Wo) % Cin);
+    const int i = (int)((idx / ((int64_t)Wo * Cin)) % Ho);
+    const int64_t b = idx / ((int64_t)Wo * Cin * Ho);
+    const TI *src = x + ((b * Cin + c) * H + 4 * i) * W + 4 * j;
+    TO *dst = y + ((b * Ho + i) * Wo + j) * (Cin * 16) + c * 16;
+    float4 r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = load4<TI>(src + (int64_t)k * W);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) store4<TO>(dst + 4 * k, r[k]);
+  }
+}
+
 static inline int ew_grid(int64_t n, int per_block) {
   int64_t blocks = (n + per_block - 1) / per_block;
   int64_t cap = (int64_t)kNumSMs * 16;
@@ -521,5 +545,28 @@ extern "C" int rsc_sigmoid_focal_loss_bwd(const void *input, const int64_t *targ
   DISPATCH_T(dtype, focal_kernel<T, true><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
                         (const T *)input, target, grad_input, total, C, gamma, alpha));
   RSC_CHECK_LAUNCH("rsc_sigmoid_focal_loss_bwd");
+  return RSC_OK;
+}
+
+extern "C" int rsc_patchify4(const void *x, void *y, int B, int Cin, int H, int W, int in_dtype, int out_dtype,
+                             void *stream) {
+  RSC_CHECK_ARG(B > 0 && Cin > 0 && H > 0 && W > 0, "rsc_patchify4: empty tensor (B=%d,C=%d,H=%d,W=%d)", B, Cin, H, W);
+  RSC_CHECK_ARG(H % 4 == 0 && W % 4 == 0, "rsc_patchify4: H and W must be multiples of 4 (pad first; got %dx%d)", H, W);
+  RSC_CHECK_ARG((in_dtype == RSC_F32 || in_dtype == RSC_BF16) && (out_dtype == RSC_F32 || out_dtype == RSC_BF16),
+                "rsc_patchify4: bad dtype");
+  RSC_CHECK_ARG(x && y, "rsc_patchify4: null pointer");
+  const int64_t total = (int64_t)B * Cin * (H / 4) * (W / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ew_grid(total, 256);
+  if (in_dtype == RSC_F32 && out_dtype == RSC_F32)
+    patchify4_kernel<float, float><<<grid, 256, 0, st>>>((const float *)x, (float *)y, total, Cin, H, W);
+  else if (in_dtype == RSC_F32)
+    patchify4_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float *)x, (__nv_bfloat16 *)y, total, Cin, H, W);
+  else if (out_dtype == RSC_F32)
+    patchify4_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (float *)y, total, Cin, H, W);
+  else
+    patchify4_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y,
+                                                                         total, Cin, H, W);
+  RSC_CHECK_LAUNCH("rsc_patchify4");
   return RSC_OK;
 }

@@ -183,9 +183,17 @@ class PatchEmbed(nn.Module):
         ph, pw = (self.kernel - H % self.kernel) % self.kernel, (self.kernel - W % self.kernel) % self.kernel
         if ph or pw:
             x = F.pad(x, (0, pw, 0, ph))     # AdaptivePadding('corner')
-        x = self.projection(x.contiguous(memory_format=torch.channels_last))
-        hw = (x.shape[2], x.shape[3])
-        x = x.permute(0, 2, 3, 1).reshape(x.shape[0], hw[0] * hw[1], x.shape[1])
+        conv = self.projection
+        if (x.is_cuda and self.kernel == 4 and conv.stride == (4, 4) and conv.padding == (0, 0) and
+                x.dtype in (torch.float32, torch.bfloat16) and not x.requires_grad):
+            # non-overlapping patches: one gather (rsc_patchify4) + ONE plain GEMM with K = 48 instead of a
+            # channels-last conversion of the whole batch + an implicit-GEMM convolution
+            B, hw = x.shape[0], (x.shape[2] // 4, x.shape[3] // 4)
+            x = ops.linear(ops.patchify4(x), conv.weight, conv.bias).view(B, hw[0] * hw[1], conv.out_channels)
+        else:
+            x = conv(x.contiguous(memory_format=torch.channels_last))
+            hw = (x.shape[2], x.shape[3])
+            x = x.permute(0, 2, 3, 1).reshape(x.shape[0], hw[0] * hw[1], x.shape[1])
         if self.norm is not None:
             x = self.norm(x)
         return x, hw

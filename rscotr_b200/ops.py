@@ -727,6 +727,24 @@ def upsample_ce_supported(logits, label):
 
 
 # ---------------------------------------------------------------------------
+# patch-embedding gather                          
+# ---------------------------------------------------------------------------
+def patchify4(x, out_dtype=None):
+    """(B,Cin,H,W) NCHW image (no gradient) -> (B*(H/4)*(W/4), Cin*16) rows in Conv2d weight order (c, kh, kw)."""
+    _cuda(x)
+    assert not x.requires_grad, 'patchify4 is a gather of the input image: no backward'
+    x = x.contiguous()
+    B, Cin, H, W = x.shape
+    if out_dtype is None:
+        out_dtype = torch.get_autocast_dtype('cuda') if torch.is_autocast_enabled('cuda') else x.dtype
+    y = torch.empty(B * (H // 4) * (W // 4), Cin * 16, dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        call('rsc_patchify4', x.data_ptr(), y.data_ptr(), B, Cin, H, W, _dt(x), _dt(y), _stream(),
+             alg_bytes=x.numel() * x.element_size() + y.numel() * y.element_size())
+    return y
+
+
+# ---------------------------------------------------------------------------
 # Linear with the bias gradient on rsc_colsum        (GEMMs stay in the library)
 # ---------------------------------------------------------------------------
 def colsum(x2d, out=None):
@@ -758,6 +776,7 @@ class _Linear(torch.autograd.Function):
         y = torch.nn.functional.linear(x2, w, b).view(*x.shape[:-1], w.shape[0])
         ctx.save_for_backward(x, w)
         ctx.meta = (weight.dtype, None if bias is None else bias.dtype, gw, gb)
+        ctx.wshape = weight.shape
         return y
 
     @staticmethod
@@ -778,7 +797,7 @@ class _Linear(torch.autograd.Function):
                 else:
                     torch.addmm(gw, dy2.t(), x2, out_dtype=torch.float32, out=gw)
             else:
-                dw = torch.mm(dy2.t(), x2).to(wdt)
+                dw = torch.mm(dy2.t(), x2).to(wdt).view(ctx.wshape)
         if bdt is not None and ctx.needs_input_grad[2]:
             if gb is not None:
                 colsum(dy2, out=gb)
@@ -789,6 +808,19 @@ class _Linear(torch.autograd.Function):
 
 def _rows(t, rows):
     return t if t is None or rows is None else t[rows[0]:rows[1]]
+
+
+def _linear_nd(x, weight, bias):
+    n_out = weight.shape[0]
+    if torch.is_autocast_enabled('cuda') and x.is_cuda:
+        x = x.to(torch.get_autocast_dtype('cuda'))
+    if not (x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and (bias is None or n_out % 4 == 0)):
+        return torch.nn.functional.linear(x, weight.reshape(n_out, -1), bias)
+    gw, gb = getattr(weight, '_rsc_g', None), getattr(bias, '_rsc_g', None)
+    if not torch.is_grad_enabled():
+        gw = gb = None
+    w = _compute_copy(weight, None, x.dtype).reshape(n_out, -1)
+    return _Linear.apply(x, weight, bias, w, _compute_copy(bias, None, x.dtype), None if gw is None else gw.view(n_out, -1), gb)
 
 
 def _compute_copy(p, rows, dtype):
@@ -806,6 +838,9 @@ def linear(x, weight, bias=None, rows=None):
     `rows=(r0, r1)` applies only output rows r0:r1 of weight / bias (the q / k / v thirds of a packed
     in_proj) without materialising slices of the master weights."""
     n_out = weight.shape[0] if rows is None else rows[1] - rows[0]
+    if weight.dim() != 2:      # a Conv2d kernel used as the (out, in*kh*kw) matrix of a patch-embedding GEMM
+        assert rows is None
+        return _linear_nd(x, weight, bias)
     if x.is_cuda and (bias is None or n_out % 4 == 0):
         if torch.is_autocast_enabled('cuda'):
             x = x.to(torch.get_autocast_dtype('cuda'))

@@ -616,3 +616,23 @@ def test_msda_fused_matches_oracle_chain(ref_dim, dtype):
     assert_rel(gv.grad, rv.grad, 1e-4 if f32 else 1e-2, 'd value')
     assert_rel(go.grad, ro.grad, 1e-4 if f32 else 1.5e-2, 'd offsets')
     assert_rel(gl.grad, rl.grad, 1e-4 if f32 else 1.5e-2, 'd logits')
+
+
+# ---------------------------------------------------------------------------
+# a1: patch-embedding gather
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('dtype,odt', [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                       (torch.bfloat16, torch.bfloat16)])
+def test_patchify4_matches_unfold_and_conv(dtype, odt):
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 24, 36, generator=g).to(dtype)
+    want = F.unfold(x.float(), kernel_size=4, stride=4).transpose(1, 2).reshape(-1, 48)      # (c, kh, kw) order
+    got = ops.patchify4(x.cuda(), odt)
+    assert got.dtype == odt and tuple(got.shape) == (2 * 6 * 9, 48)
+    assert torch.equal(got.float().cpu(), want.to(odt).float())
+    # the projection as a GEMM over the gathered rows == Conv2d(k4, s4)
+    conv = torch.nn.Conv2d(3, 96, 4, 4)
+    ref = conv(x.float()).flatten(2).transpose(1, 2).reshape(-1, 96)
+    y = F.linear(want, conv.weight.view(96, 48), conv.bias)
+    assert_rel(y, ref, 1e-5, 'conv as gemm')
