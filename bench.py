@@ -26,8 +26,14 @@ METRIC = 'co-training iters/sec (Swin-T, 3x800x800)'
 TASK_ORDER = ('resisc', 'dior', 'potsdam')
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
 # (profiles/r01_ncu_wmsa_tc_stage0_B16.json: stage-0 launch, B=16; the bench's average launch is smaller)
-NCU_TRAFFIC = {'rsc_wmsa_bwd': dict(stage0_B16_bytes=820.8e6, stage0_B16_alg_bytes=860.2e6),
-               'rsc_wmsa_fwd': dict(stage0_B16_bytes=470.0e6, stage0_B16_alg_bytes=491.5e6)}
+NCU_TRAFFIC = {   # per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the profiled shape
+    'rsc_wmsa_bwd': dict(stage0_B16_bytes=817.7e6, stage0_B16_alg_bytes=860.2e6,
+                         source='profiles/r01_ncu_wmsa_tc_v3_stage0_B16.json'),
+    'rsc_wmsa_fwd': dict(stage0_B16_bytes=470.0e6, stage0_B16_alg_bytes=491.5e6,
+                         source='profiles/r01_ncu_wmsa_tc_v3_stage0_B16.json'),
+    'rsc_msda_fused_bwd': dict(encoder_B2_bytes=129.9e6, note='L2-resident gather / atomics: DRAM traffic is 4 % of '
+                               'peak (ncu capture of the un-fused kernel at the same shape, gpurun prof_msda)'),
+}
 
 
 def parse_args():
@@ -342,15 +348,32 @@ def main():
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     hb = db = 0
+    # The loss of every step is read back into pinned host memory (4 bytes, async D2H + event) and consumed ONE step
+    # later, after the next step has been enqueued -- the logging lag of any real training loop -- so the host never
+    # leaves the GPU idle between steps; the next batch's H2D copy runs on the copy stream meanwhile.
+    loss_host = torch.empty(args.steps, dtype=torch.float32).pin_memory()
+    read_ev = [None] * args.steps
+    losses_read = []
+
+    def consume(k):
+        read_ev[k].synchronize()
+        losses_read.append(float(loss_host[k]))
+
     engine.prefetch(host_batches[0])
     for i in range(args.steps):
         batch = host_batches[i % 6]
         hb += h2d_bytes(batch)
         o = engine.train_iter(batch)
+        loss_host[i:i + 1].copy_(o['loss'].detach().reshape(1).float(), non_blocking=True)   # D2H of the step's result
+        read_ev[i] = torch.cuda.Event()
+        read_ev[i].record()
+        db += 4
         if i + 1 < args.steps:
             engine.prefetch(host_batches[(i + 1) % 6])                    # next step's H2D overlaps this step's compute
-        _ = float(o['loss'].detach())                                     # D2H read of the step's result
-        db += 4
+        if i > 0:
+            consume(i - 1)
+    consume(args.steps - 1)
+    assert len(losses_read) == args.steps and all(v == v for v in losses_read), 'e2e: missing / NaN loss read-back'
     f1.record()
     barrier()
     trace('timed region B done')
@@ -413,7 +436,9 @@ def main():
                            weights='random init, 62.6 M params', final_loss=final_loss),
                clocks=clocks,
                e2e=dict(value=e2e, unit='iters/s', h2d_bytes_per_step=hb // args.steps, d2h_bytes_per_step=db // args.steps,
-                        ms_per_step=ms_e2e / args.steps),
+                        ms_per_step=ms_e2e / args.steps,
+                        pipeline='pinned host inputs, H2D of step i+1 on a copy stream during step i; loss of step i '
+                                 'copied to pinned host memory and read after step i+1 is enqueued'),
                gpu_launches=launches, cuda_graphs=bool(engine.use_graphs), cuda_graph_capture_failures=engine.graph_failures,
                ms_per_task={k: sum(v) / len(v) for k, v in per_task.items()},
                roofline=roofline,
