@@ -103,7 +103,12 @@ class SizeProportionalIterationStrategy(IterationStrategy):
 
     def __init__(self, dataloaders, config=None, *args, **kwargs):
         super().__init__(dataloaders, config, *args, **kwargs)
-        sizes = np.array([max(len(l), 1) for l in dataloaders.values()], dtype=np.float64)
+        # the reference weighs by DATASET size (len(loader.dataset), iteration_strategies.py:219-246), not by the
+        # number of batches; loaders without a sized dataset fall back to their own length
+        def size(l):
+            ds = getattr(l, 'dataset', None)
+            return len(ds) if ds is not None and hasattr(ds, '__len__') else len(l)
+        sizes = np.array([max(size(l), 1) for l in dataloaders.values()], dtype=np.float64)
         self._p = sizes / sizes.sum()
 
     @property
