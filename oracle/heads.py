@@ -480,7 +480,14 @@ def mtl_losses(sd, task, batch, *, cfg=None, noise=None):
 
 def parse_losses(losses, task_weight=1.0):
     """MTL._parse_losses + train_step weighting (multitask_learner.py:229-306), single process."""
-    log_vars = {k: v.mean() for k, v in losses.items()}
+    log_vars = {}
+    for k, v in losses.items():
+        if isinstance(v, torch.Tensor):
+            log_vars[k] = v.mean()
+        elif isinstance(v, list):                     # multitask_learner.py:279-281
+            log_vars[k] = sum(x.mean() for x in v)
+        else:
+            raise TypeError('%s is not a tensor or list of tensors' % k)
     loss = sum(v for k, v in log_vars.items() if 'loss' in k)
     log_vars['loss'] = loss
     return loss * task_weight, {k: float(v.detach()) * task_weight for k, v in log_vars.items()}

@@ -674,6 +674,23 @@ class DINOHead(nn.Module):
             t = r if self.sync_cls_avg_factor else torch.stack([t[0], r[1]])
         return t.clamp(min=1.0)
 
+    @staticmethod
+    def dn_assign_table(sizes, num_groups, pad_size):
+        """fixed targets of the denoising queries (dino_head.py:323-365 _get_dn_target_single) as a (B, pad_size)
+        table: entry = global index (into the concatenated gt lists) of the gt box the query reconstructs, -1 for
+        the negative / padding queries.  Group g occupies [g*single, (g+1)*single) with single = pad_size // groups;
+        its first n_b slots are the positives of image b's n_b boxes."""
+        single = pad_size // num_groups if num_groups else 0
+        starts = [0]
+        for n in sizes:
+            starts.append(starts[-1] + n)
+        table = [[-1] * pad_size for _ in sizes]
+        for b, n in enumerate(sizes):
+            for g in range(num_groups):
+                for t in range(n):
+                    table[b][g * single + t] = starts[b] + t
+        return table
+
     def loss_fused(self, all_cls_scores, all_bbox_preds, enc_topk_scores, enc_topk_anchors, gt_bboxes_list,
                    gt_labels_list, img_metas, dn_meta=None, gt_bboxes_ignore=None):
         """Same loss terms / keys as loss_prepare + loss_assign + loss_finish, on the GPU end to end:
@@ -724,12 +741,7 @@ class DINOHead(nn.Module):
         row += L
         if dn_meta is not None:
             num_groups = int(dn_meta['num_dn_group'])
-            single = ps // num_groups if num_groups else 0
-            dn_assign = [[-1] * ps for _ in range(B)]
-            for b in range(B):
-                for g in range(num_groups):
-                    for t in range(sizes[b]):
-                        dn_assign[b][g * single + t] = starts[b] + t
+            dn_assign = self.dn_assign_table(sizes, num_groups, ps)
             assign_dn = const_tensor(dn_assign, torch.int32, dev) if ps else assign_dec
             npos = total_gt * num_groups
             pos_counts += [npos] * L

@@ -224,6 +224,182 @@ def golden_sineembed():
     return cases
 
 
+# ----------------------------------------------------------------------------- DINO head: denoising targets
+class _AutoStubModule(types.ModuleType):
+    """a module whose every attribute is an inert stand-in: usable as a base class, as a registry
+    (`X.register_module()`), as a decorator factory (`@force_fp32(apply_to=...)`) -- enough to IMPORT the
+    reference's head modules; none of the stand-ins is executed by the functions the goldens call."""
+
+    def __getattr__(self, name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+
+        class _Stub(torch.nn.Module):
+            def __init__(self, *a, **k):
+                super().__init__()
+
+            def __call__(self, f=None, *a, **k):      # decorator use: @stub(...)(fn) -> fn
+                return f
+
+            @classmethod
+            def register_module(cls, *a, **k):
+                return lambda c: c
+        _Stub.__name__ = name
+        setattr(self, name, _Stub)
+        return _Stub
+
+
+def golden_dn_targets():
+    """models/multi/bbox_head/dino_head.py::DINOHead.get_dn_target / _get_dn_target_single (rows a16, dn part):
+    the fixed (non-Hungarian) targets of the denoising queries.  Called UNBOUND on a bare namespace carrying
+    num_classes: the class itself cannot be constructed without mmdet."""
+    install_mmdet_shim()
+
+    def multi_apply(func, *args, **kwargs):        # mmdet 2.25.1 core/utils/misc.py
+        from functools import partial
+        pfunc = partial(func, **kwargs) if kwargs else func
+        return tuple(map(list, zip(*map(pfunc, *args))))
+    for name in ('mmcv', 'mmcv.cnn', 'mmcv.cnn.bricks', 'mmcv.cnn.bricks.transformer', 'mmcv.runner', 'mmdet.models.builder',
+                 'mmdet.models.utils', 'mmdet.models.dense_heads', 'mmdet.models.dense_heads.anchor_free_head'):
+        if not isinstance(sys.modules.get(name), _AutoStubModule):
+            old = sys.modules.get(name)
+            new = _AutoStubModule(name)
+            if old is not None:
+                new.__dict__.update({k: v for k, v in old.__dict__.items() if not k.startswith('__')})
+            sys.modules[name] = new
+    core = _AutoStubModule('mmdet.core')
+    core.__dict__.update({k: v for k, v in sys.modules['mmdet.core'].__dict__.items() if not k.startswith('__')})
+    core.multi_apply = multi_apply
+    sys.modules['mmdet.core'] = core
+    pkg = types.ModuleType('ref_bbox_head')
+    pkg.__path__ = [os.path.join(REF, 'models', 'multi', 'bbox_head')]
+    sys.modules['ref_bbox_head'] = pkg
+    sub = types.ModuleType('ref_bbox_head.mmdet_detr_head')
+    sub.__path__ = [os.path.join(REF, 'models', 'multi', 'bbox_head', 'mmdet_detr_head')]
+    sys.modules['ref_bbox_head.mmdet_detr_head'] = sub
+    detr = load('models/multi/bbox_head/mmdet_detr_head/detr_head.py', 'ref_bbox_head.mmdet_detr_head.detr_head')
+    ddetr = load('models/multi/bbox_head/mmdet_detr_head/deformable_detr_head.py',
+                 'ref_bbox_head.mmdet_detr_head.deformable_detr_head')
+    sub.DETRHead, sub.DeformableDETRHead = detr.DETRHead, ddetr.DeformableDETRHead
+    load('models/multi/bbox_head/query_denoising.py', 'ref_bbox_head.query_denoising')
+    dino = load('models/multi/bbox_head/dino_head.py', 'ref_bbox_head.dino_head')
+    H = dino.DINOHead
+    fake = types.SimpleNamespace(num_classes=20)
+    fake._get_dn_target_single = lambda *a: H._get_dn_target_single(fake, *a)
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    cases = []
+    try:
+        for sizes, num_groups in [((3, 5), 2), ((8,), 12), ((0, 4), 3)]:
+            g = torch.Generator().manual_seed(sum(sizes) + num_groups)
+            single = max(sizes) * 2
+            dn_meta = dict(pad_size=single * num_groups, num_dn_group=num_groups)
+            shapes = [(640 + 32 * b, 800 - 16 * b, 3) for b in range(len(sizes))]
+            gtb, gtl, preds = [], [], []
+            for b, n in enumerate(sizes):
+                h, w = shapes[b][:2]
+                x1, y1 = torch.rand(n, generator=g) * (w - 150), torch.rand(n, generator=g) * (h - 150)
+                gtb.append(torch.stack([x1, y1, x1 + 40 + 80 * torch.rand(n, generator=g), y1 + 30 + 90 * torch.rand(n, generator=g)], -1))
+                gtl.append(torch.randint(0, 20, (n,), generator=g))
+                preds.append(torch.rand(dn_meta['pad_size'], 4, generator=g))
+            metas = [dict(img_shape=s) for s in shapes]
+            out = H.get_dn_target(fake, preds, gtb, gtl, metas, [dn_meta for _ in sizes])
+            cases.append(dict(sizes=list(sizes), dn_meta=dn_meta, img_shapes=shapes, gt_bboxes=gtb, gt_labels=gtl,
+                              dn_bbox_preds=preds, labels=out[0], label_weights=out[1], bbox_targets=out[2],
+                              bbox_weights=out[3], num_total_pos=int(out[4]), num_total_neg=int(out[5])))
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    torch.save(dict(source='models/multi/bbox_head/dino_head.py::DINOHead.get_dn_target (reference, run in place, unbound)',
+                    cases=cases), os.path.join(OUT, 'reference_dn_targets.pt'))
+    return cases
+
+
+# ----------------------------------------------------------------------------- MTL.train_step / _parse_losses, seg forward_head
+def _stub_packages(names):
+    for name in names:
+        parts = name.split('.')
+        for k in range(1, len(parts) + 1):
+            n = '.'.join(parts[:k])
+            if not isinstance(sys.modules.get(n), _AutoStubModule):
+                old, new = sys.modules.get(n), _AutoStubModule(n)
+                if old is not None:
+                    new.__dict__.update({kk: v for kk, v in old.__dict__.items() if not kk.startswith('__')})
+                new.__path__ = []
+                sys.modules[n] = new
+
+
+def golden_train_step():
+    """models/multi/multitask_learner.py::MTL.train_step + _parse_losses (row a21), called UNBOUND on a small
+    callable object that returns preset loss dicts: total = sum of the '*loss*' means, log_vars prefixed with
+    '<task>.<dataset>' and multiplied by the task weight."""
+    _stub_packages(['matplotlib.font_manager', 'matplotlib.pyplot', 'matplotlib.collections', 'matplotlib.patches',
+                    'mmcv.runner', 'mmcv.cnn.bricks.transformer', 'mmcv.cnn', 'mmcls.models.utils.augment', 'mmdet.core',
+                    'mmdet.core.visualization', 'mmseg.core', 'mmseg.ops', 'mtl.model.build', 'mmdet.models.utils.transformer'])
+    sys.modules['mmseg.core'].add_prefix = lambda inputs, prefix: {'%s.%s' % (prefix, k): v for k, v in inputs.items()}  # mmseg 0.28 core/utils/misc.py
+    ref = load('models/multi/multitask_learner.py', 'ref_multitask_learner')
+    MTL = ref.MTL
+
+    class Fake:
+        task_weight = dict(cls=1, det=1, seg=0.1)
+
+        def __init__(self, losses):
+            self.losses = losses
+
+        def __call__(self, **data):
+            return self.losses
+
+        def _parse_losses(self, losses):
+            return MTL._parse_losses(self, losses)
+    g = torch.Generator().manual_seed(11)
+    cases = []
+    for task, ds, keys in [('cls', 'resisc', ['loss']), ('seg', 'potsdam', ['seg.loss_ce', 'seg.acc_seg']),
+                           ('det', 'dior', ['interm_loss_cls', 'loss_cls', 'loss_bbox', 'd0.loss_iou', 'dn_loss_cls', 'list_loss'])]:
+        losses = {}
+        for k in keys:
+            losses[k] = [torch.rand(3, generator=g), torch.rand((), generator=g)] if k == 'list_loss' else \
+                torch.rand((2,) if k == 'loss_bbox' else (), generator=g) * 3
+        data = dict(task=task, dataset_name=ds, img_metas=[{}] * (2 if task != 'det' else 1))
+        out = MTL.train_step(Fake({k: (v if isinstance(v, list) else v.clone()) for k, v in losses.items()}), data, None)
+        cases.append(dict(task=task, dataset_name=ds, losses=losses, loss=out['loss'].clone(),
+                          log_vars={k: float(v) for k, v in out['log_vars'].items()}, num_samples=out['num_samples']))
+    torch.save(dict(source='models/multi/multitask_learner.py::MTL.train_step/_parse_losses (reference, run in place, unbound)',
+                    cases=cases), os.path.join(OUT, 'reference_train_step.pt'))
+    return cases
+
+
+def golden_seg_forward_head():
+    """models/multi/seg_head/mask2former_head.py::Mask2FormerHead.forward_head (row a18), called UNBOUND on a namespace
+    holding plain torch modules (post_norm LayerNorm, mask_embed MLP): mask prediction einsum, bilinear resize to
+    the next level and the sigmoid < 0.5 attention mask repeated over heads."""
+    _stub_packages(['mmcv.cnn', 'mmcv.cnn.bricks.transformer', 'mmcv.runner', 'mmseg.models.builder',
+                    'mmseg.models.decode_heads.decode_head', 'mmdet.models.utils.transformer'])
+    pkg = types.ModuleType('ref_seg_head')
+    pkg.__path__ = [os.path.join(REF, 'models', 'multi', 'seg_head')]
+    sys.modules['ref_seg_head'] = pkg
+    try:
+        ref = load('models/multi/seg_head/mask2former_head.py', 'ref_seg_head.mask2former_head')
+    except Exception:
+        _stub_packages(['ref_seg_head.pixel_decoder'])
+        ref = load('models/multi/seg_head/mask2former_head.py', 'ref_seg_head.mask2former_head')
+    H = ref.Mask2FormerHead
+    torch.manual_seed(3)
+    C = 32
+    fake = types.SimpleNamespace(scheme=2, num_heads=4,
+                                 transformer_decoder=types.SimpleNamespace(post_norm=torch.nn.LayerNorm(C)),
+                                 mask_embed=torch.nn.Sequential(torch.nn.Linear(C, C), torch.nn.ReLU(), torch.nn.Linear(C, C),
+                                                                torch.nn.ReLU(), torch.nn.Linear(C, C)))
+    decoder_out = torch.randn(7, 2, C)                # (queries, batch, C)
+    mask_feature = torch.randn(2, C, 12, 10)
+    with torch.no_grad():
+        seg_mask, attn_mask = H.forward_head(fake, decoder_out, mask_feature, (5, 6))
+    sd = {'post_norm.' + k: v for k, v in fake.transformer_decoder.post_norm.state_dict().items()}
+    sd.update({'mask_embed.' + k: v for k, v in fake.mask_embed.state_dict().items()})
+    torch.save(dict(source='models/multi/seg_head/mask2former_head.py::Mask2FormerHead.forward_head (reference, run in place, unbound)',
+                    state=sd, decoder_out=decoder_out, mask_feature=mask_feature, target_size=(5, 6), num_heads=4,
+                    seg_mask=seg_mask, attn_mask=attn_mask), os.path.join(OUT, 'reference_seg_forward_head.pt'))
+    return seg_mask.shape, attn_mask.shape
+
+
 # ----------------------------------------------------------------------------- MultiDataLoader
 class _ToyDataset(torch.utils.data.Dataset):
     """n samples {'idx': i}; `task` is what MultiDataLoader tags batches with"""
@@ -278,6 +454,11 @@ def golden_multi_data_loader():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    t = golden_train_step()
+    print('train_step:', [(c['task'], float(c['loss']), len(c['log_vars'])) for c in t])
+    print('seg forward_head:', golden_seg_forward_head())
+    d = golden_dn_targets()
+    print('dn targets:', [(c['sizes'], c['num_total_pos'], c['num_total_neg']) for c in d])
     m = golden_multi_data_loader()
     print('multi data loader:', [(c['strategy'], c['sequence'][:4]) for c in m])
     e = golden_sineembed()
