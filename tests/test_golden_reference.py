@@ -15,6 +15,27 @@ from rscotr_b200.mtl.data import iteration_strategies as strategies
 from rscotr_b200.models.det_head import CdnQueryGenerator
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+# the CUDA variants compare fp32 kernels with CPU-generated fixtures: no TF32 in the library GEMMs / convs
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+DEVICES = ['cpu', pytest.param('cuda', marks=pytest.mark.gpu)]
+
+
+def _to(obj, device):
+    if torch.is_tensor(obj) or isinstance(obj, torch.nn.Module):
+        return obj.to(device)
+    if isinstance(obj, dict):
+        return {k: _to(v, device) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to(v, device) for v in obj)
+    return obj
+
+
+def _ctx(device):
+    """CPU: the CUDA ops are substituted by the oracle (test shim); CUDA: the real kernels through the C ABI."""
+    import contextlib
+    from tests.cpu_ops_shim import cpu_ops
+    return cpu_ops() if device == 'cpu' else contextlib.nullcontext()
 
 
 class _Loader:
@@ -179,24 +200,229 @@ def test_train_step_postprocessing_matches_reference_run(idx):
         assert {k: round(v, 6) for k, v in out2['log_vars'].items()} == {k: round(v, 6) for k, v in got.items()}
 
 
-def test_seg_forward_head_matches_reference_run():
+@pytest.mark.parametrize('device', DEVICES)
+def test_seg_forward_head_matches_reference_run(device):
     """row a18: Mask2FormerHead.forward_head of the reference (run in place, unbound) against this repo's method
     (CPU through the test shim of the CUDA ops): mask prediction and the boolean attention mask."""
     import types
     from rscotr_b200.models import bricks
     from rscotr_b200.models.seg_head import Mask2FormerHead
     from tests.cpu_ops_shim import cpu_ops
-    c = torch.load(os.path.join(GOLDEN, 'reference_seg_forward_head.pt'), weights_only=False)
+    c = _to(torch.load(os.path.join(GOLDEN, 'reference_seg_forward_head.pt'), weights_only=False), device)
     C = c['decoder_out'].shape[-1]
     post_norm = bricks.LayerNorm(C)
     mask_embed = torch.nn.Sequential(bricks.Linear(C, C), torch.nn.ReLU(), bricks.Linear(C, C), torch.nn.ReLU(),
                                      bricks.Linear(C, C))
     post_norm.load_state_dict({k[len('post_norm.'):]: v for k, v in c['state'].items() if k.startswith('post_norm.')})
     mask_embed.load_state_dict({k[len('mask_embed.'):]: v for k, v in c['state'].items() if k.startswith('mask_embed.')})
-    fake = types.SimpleNamespace(scheme=2, num_heads=c['num_heads'], mask_embed=mask_embed,
-                                 transformer_decoder=types.SimpleNamespace(post_norm=post_norm))
-    with cpu_ops(), torch.no_grad():
+    fake = types.SimpleNamespace(scheme=2, num_heads=c['num_heads'], mask_embed=mask_embed.to(device),
+                                 transformer_decoder=types.SimpleNamespace(post_norm=post_norm.to(device)))
+    with _ctx(device), torch.no_grad():
         seg_mask, attn_mask = Mask2FormerHead.forward_head(fake, c['decoder_out'], c['mask_feature'], tuple(c['target_size']))
     assert torch.allclose(seg_mask, c['seg_mask'], rtol=1e-5, atol=1e-5)
     assert attn_mask.shape == c['attn_mask'].shape and attn_mask.dtype == torch.bool
     assert float((attn_mask != c['attn_mask']).float().mean()) <= 1e-3      # (values within 1e-6 of the 0.5 threshold)
+
+
+def _tools():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), '..', 'tools'))
+    import make_golden
+    return make_golden
+
+
+@pytest.mark.parametrize('device', DEVICES)
+def test_seg_head_forward_control_flow_matches_reference_run(device):
+    """row a18: Mask2FormerHead.forward of the reference (level cycling, reset of fully masked rows, forward_head after
+    every layer), run in place with toy decoder layers, against this repo's forward with the SAME toy parts."""
+    import types
+    from rscotr_b200.models import bricks
+    from rscotr_b200.models.seg_head import Mask2FormerHead
+    from tests.cpu_ops_shim import cpu_ops
+    mg = _tools()
+    t = _to(mg.toy_seg_parts(), device)
+    want = torch.load(os.path.join(GOLDEN, 'reference_seg_forward.pt'), weights_only=False)['out'].to(device)
+    C = t['C']
+    post_norm = bricks.LayerNorm(C)
+    mask_embed = torch.nn.Sequential(bricks.Linear(C, C), torch.nn.ReLU(), bricks.Linear(C, C), torch.nn.ReLU(),
+                                     bricks.Linear(C, C))
+    with torch.no_grad():
+        post_norm.weight.copy_(t['post_norm_w']), post_norm.bias.copy_(t['post_norm_b'])
+        for k, i in enumerate((0, 2, 4)):
+            mask_embed[i].weight.copy_(t['mlp'][k]), mask_embed[i].bias.copy_(t['mlp_b'][k])
+    emb = lambda w: torch.nn.Embedding.from_pretrained(w.clone(), freeze=False)
+    fake = types.SimpleNamespace(
+        scheme=2, num_heads=2, num_transformer_feat_level=4, num_transformer_decoder_layers=9,
+        pixel_decoder=lambda enc, neck, bb: (t['mask_features'], t['memories']),
+        decoder_input_projs=[torch.nn.Identity() for _ in range(4)], level_embed=emb(t['level_embed']),
+        decoder_positional_encoding=lambda mask: t['pos'][tuple(mask.shape[-2:])],
+        query_feat=emb(t['query_feat']), query_embed=emb(t['query_embed']), mask_embed=mask_embed.to(device),
+        transformer_decoder=types.SimpleNamespace(post_norm=post_norm.to(device),
+                                                  layers=[mg.ToyDecoderLayer() for _ in range(9)]))
+    fake.forward_head = lambda *a: Mask2FormerHead.forward_head(fake, *a)
+    with _ctx(device), torch.no_grad():
+        got = Mask2FormerHead.forward(fake, None, None, None, [{}] * t['B'])
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-4), float((got - want).abs().max())
+
+
+@pytest.mark.parametrize('device', DEVICES)
+def test_dino_decoder_and_head_control_flow_match_reference_run(device):
+    """rows a14 / a13: DinoTransformerDecoder.forward and DINOHead.forward of the reference, run in place with toy
+    decoder layers / a toy transformer, against this repo's methods with the SAME toy parts."""
+    import types
+    from rscotr_b200.models import bricks
+    from rscotr_b200.models.det_head import DINOHead, DinoTransformerDecoder
+    from tests.cpu_ops_shim import cpu_ops
+    mg = _tools()
+    t = _to(mg.toy_det_parts(), device)
+    c = _to(torch.load(os.path.join(GOLDEN, 'reference_dino_decoder_head.pt'), weights_only=False), device)
+    C, L = t['C'], t['L']
+    rph = [(c['rph0'], t['ref_point_head'][0][1]), t['ref_point_head'][1]]
+    norm = bricks.LayerNorm(C)
+    with torch.no_grad():
+        norm.weight.copy_(t['norm'][0]), norm.bias.copy_(t['norm'][1])
+    reg = [mg._mlp_from(ws).to(device) for ws in t['reg']]
+    cls = [mg._mlp_from([w]).to(device) for w in t['cls']]
+    dec = types.SimpleNamespace(layers=[mg.ToyDecoderLayer() for _ in range(L)], ref_point_head=mg._mlp_from(rph).to(device),
+                                norm=norm.to(device), return_intermediate=True,
+                                gen_sineembed_for_position=DinoTransformerDecoder.gen_sineembed_for_position)
+    with _ctx(device), torch.no_grad():
+        hs, refs = DinoTransformerDecoder.forward(dec, t['query'], None, t['memory'], reference_points=t['reference_points'],
+                                                  valid_ratios=t['valid_ratios'], reg_branches=reg)
+    assert torch.allclose(hs, c['hs'], rtol=1e-4, atol=1e-5), float((hs - c['hs']).abs().max())
+    assert torch.allclose(refs, c['refs'], rtol=1e-4, atol=1e-5)
+    seen = {}
+
+    def toy_transformer(mlvl_feats, mlvl_masks, query_embeds, mlvl_pos, dn_label_query, dn_bbox_query, attn_mask, encoder,
+                        reg_branches=None, cls_branches=None, **kw):
+        seen['masks'] = [m.clone() for m in mlvl_masks]
+        return c['hs'], c['refs'], t['topk_score'], t['topk_anchor']
+    head = types.SimpleNamespace(transformer=toy_transformer, positional_encoding=lambda m: m.float().unsqueeze(1),
+                                 with_box_refine=True, as_two_stage=True, reg_branches=reg, cls_branches=cls,
+                                 label_embedding=torch.nn.Embedding(t['classes'], C).to(device))
+    with _ctx(device), torch.no_grad():
+        oc, ob, ts, ta = DINOHead.forward(head, None, t['feats'], c['metas'], torch.zeros(t['B'], t['pad'], C, device=device),
+                                          torch.zeros(t['B'], t['pad'], 4, device=device), None)
+    assert all(torch.equal(a, b) for a, b in zip(seen['masks'], c['masks']))
+    assert torch.allclose(oc, c['outputs_classes'], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ob, c['outputs_coords'], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('device', DEVICES)
+def test_dino_transformer_control_flow_matches_reference_run(device):
+    """row a13: DinoTransformer.forward of the reference (flattening, level embeddings, two-stage top-k proposals,
+    dn / matching query concatenation), run in place with a toy encoder / decoder, against this repo's forward with
+    the SAME toy parts -- incl. what is handed to the decoder (queries, reference points, memory, padding mask)."""
+    import types
+    from rscotr_b200.models import bricks
+    from rscotr_b200.models.det_head import DinoTransformer
+    from tests.cpu_ops_shim import cpu_ops
+    mg = _tools()
+    t = _to(mg.toy_two_stage_parts(), device)
+    c = _to(torch.load(os.path.join(GOLDEN, 'reference_dino_transformer.pt'), weights_only=False), device)
+    C = t['C']
+    enc_out = mg._mlp_from([t['enc_output']], cls=bricks.Linear).to(device)
+    enc_norm = bricks.LayerNorm(C).to(device)
+    with torch.no_grad():
+        enc_norm.weight.copy_(t['enc_norm'][0]), enc_norm.bias.copy_(t['enc_norm'][1])
+    dec = mg.ToyDecoder()
+    fake = types.SimpleNamespace(as_two_stage=True, level_embeds=t['level_embeds'], decoder=dec, two_stage_num_proposals=t['K'],
+                                 query_embed=torch.nn.Embedding.from_pretrained(t['query_embed'].clone()).to(device),
+                                 enc_output=enc_out, enc_output_norm=enc_norm, get_valid_ratio=DinoTransformer.get_valid_ratio,
+                                 get_reference_points=DinoTransformer.get_reference_points,
+                                 proposal_grid=DinoTransformer.proposal_grid)
+    fake.gen_encoder_output_proposals = lambda *a, **k: DinoTransformer.gen_encoder_output_proposals(fake, *a, **k)
+    fake._geometry = lambda *a: DinoTransformer._geometry(fake, *a)
+    cls = [None, mg._mlp_from([t['cls']]).to(device)]
+    reg = [None, mg._mlp_from(t['reg']).to(device)]
+    with _ctx(device), torch.no_grad():
+        out = DinoTransformer.forward(fake, t['feats'], t['masks'], None, t['pos'], t['dn_label'], t['dn_bbox'], None,
+                                      mg.toy_encoder, reg_branches=reg, cls_branches=cls)
+    for got, want in zip(out, c['out']):
+        assert got.shape == want.shape and torch.allclose(got, want, rtol=1e-5, atol=1e-5), float((got - want).abs().max())
+    for k in ('query', 'reference_points', 'value'):
+        assert torch.allclose(dec.seen[k], c['decoder_saw'][k], rtol=1e-5, atol=1e-5), k
+    assert torch.equal(dec.seen['key_padding_mask'], c['decoder_saw']['key_padding_mask'])
+
+
+@pytest.mark.parametrize('device', DEVICES)
+def test_seg_pixel_decoder_control_flow_matches_reference_run(device):
+    """row a17: MlvlSegPixelDecoder.forward of the reference, run in place with a toy encoder / positional encoding /
+    point generator, against this repo's forward with the SAME toy parts -- incl. what the shared encoder is
+    called with (inputs, level positional encodings, reference points, level shapes / start indices)."""
+    import types
+    from rscotr_b200.models.seg_head import MlvlSegPixelDecoder
+    from tests.cpu_ops_shim import cpu_ops
+    mg = _tools()
+    t = _to(mg.toy_pixel_decoder_parts(), device)
+    c = _to(torch.load(os.path.join(GOLDEN, 'reference_seg_pixel_decoder.pt'), weights_only=False), device)
+    C = t['C']
+    mask_feature = torch.nn.Conv2d(C, C, 1).to(device)
+    with torch.no_grad():
+        mask_feature.weight.copy_(t['mask_w']), mask_feature.bias.copy_(t['mask_b'])
+    enc = mg.ToyEncoder()
+    fake = types.SimpleNamespace(num_encoder_levels=4, num_input_levels=4, strides=t['strides'], num_outs=4,
+                                 postional_encoding=lambda m: t['pos'][tuple(m.shape[-2:])],
+                                 level_encoding=torch.nn.Embedding.from_pretrained(t['level_encoding'].clone()).to(device),
+                                 lateral_convs=[], output_convs=[], mask_feature=mask_feature)
+    with _ctx(device), torch.no_grad():
+        mf, feats = MlvlSegPixelDecoder.forward(fake, enc, t['neck'], t['backbone'])
+    assert torch.allclose(mf, c['mask_feature'], rtol=1e-5, atol=1e-6)
+    assert len(feats) == len(c['feats']) and all(torch.allclose(a, b, rtol=1e-5, atol=1e-6) for a, b in zip(feats, c['feats']))
+    for k in ('query', 'query_pos', 'reference_points'):
+        assert torch.allclose(enc.seen[k], c['encoder_saw'][k], rtol=1e-6, atol=1e-6), k
+    assert torch.equal(enc.seen['spatial_shapes'], c['encoder_saw']['spatial_shapes'])
+    assert torch.equal(enc.seen['level_start_index'], c['encoder_saw']['level_start_index'])
+
+
+def _dino_head():
+    import rscotr_b200.models  # noqa: F401
+    from rscotr_b200.config import Config
+    from rscotr_b200.models.det_head import DINOHead
+    cfg = Config.fromfile(os.path.join(os.path.dirname(GOLDEN), '..', 'configs', 'multi', 'cotrain_swin-t_800.py'))
+    hc = dict(cfg.model.bbox_head)
+    hc.pop('type')
+    hc.update(train_cfg=cfg.model.train_cfg.get('det'), test_cfg=cfg.model.test_cfg.get('det'), num_query=12)
+    return DINOHead(**hc)
+
+
+def _loss_case(device='cpu'):
+    mg = _tools()
+    t = mg.toy_loss_parts()
+    want = json.load(open(os.path.join(GOLDEN, 'reference_dino_loss.json')))
+    metas = [dict(img_shape=tuple(s)) for s in t['img_shapes']]
+    args = [t['all_cls'].to(device), t['all_box'].to(device), t['enc_cls'].to(device), t['enc_box'].to(device),
+            [b.to(device) for b in t['gt_bboxes']], [l.to(device) for l in t['gt_labels']], metas, t['dn_meta']]
+    return args, want
+
+
+def test_dino_loss_flow_matches_reference_run():
+    """row a16: DINOHead.loss / DETRHead.loss_single of the reference, run in place (third-party assigner / sampler /
+    loss modules restated from the oracle), against this repo's ATen + scipy path (CPU) and the oracle: same 21
+    keys in the same order, same values."""
+    from tests.cpu_ops_shim import cpu_ops
+    args, want = _loss_case()
+    head = _dino_head()
+    head.fused_loss = False
+    with cpu_ops(), torch.no_grad():
+        got = head.loss(*args)
+    assert list(got.keys()) == want['keys']
+    for k, v in want['losses'].items():
+        assert abs(float(got[k]) - v) <= 2e-5 * max(1.0, abs(v)), (k, float(got[k]), v)
+    ora = oh.det_loss(*args[:4], args[4], args[5], args[6], args[7])
+    for k, v in want['losses'].items():
+        assert abs(float(ora[k]) - v) <= 1e-6 * max(1.0, abs(v)), (k, float(ora[k]), v)
+
+
+@pytest.mark.gpu
+def test_dino_loss_cuda_kernels_match_reference_run_golden():
+    """the CUDA path (rsc_det_match + rsc_det_loss_fwd through the C ABI) against the SAME committed fixture."""
+    args, want = _loss_case('cuda')
+    head = _dino_head().cuda()
+    assert head.fused_loss
+    with torch.no_grad():
+        got = head.loss(*args)
+    assert list(got.keys()) == want['keys']
+    for k, v in want['losses'].items():
+        assert abs(float(got[k]) - v) <= 5e-5 * max(1.0, abs(v)), (k, float(got[k]), v)

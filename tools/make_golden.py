@@ -400,6 +400,349 @@ def golden_seg_forward_head():
     return seg_mask.shape, attn_mask.shape
 
 
+# ----------------------------------------------------------------------------- control flow of the heads with toy sub-modules
+class ToyDecoderLayer(torch.nn.Module):
+    """Deterministic stand-in for an mmcv BaseTransformerLayer (third-party): mixes the query with a masked mean of
+    value (+ key_pos) and with query_pos, so the output depends on which level / mask / positions it is handed.
+    Used IDENTICALLY by the reference run (tools/make_golden.py) and by the tests of this repo."""
+
+    def forward(self, query, key=None, value=None, query_pos=None, key_pos=None, attn_masks=None,
+                query_key_padding_mask=None, key_padding_mask=None, reference_points=None, **kwargs):
+        out = query
+        if value is not None:
+            v = value.float() + (key_pos.float() if key_pos is not None and key_pos.shape == value.shape else 0)
+            mask = attn_masks[0] if isinstance(attn_masks, (list, tuple)) else attn_masks
+            if mask is not None and mask.dim() == 3:           # (B*heads, Q, K): use head 0 of every image
+                B = value.shape[1]
+                w = (~mask.view(B, -1, mask.shape[-2], mask.shape[-1])[:, 0]).float()      # (B, Q, K)
+                w = w / w.sum(-1, keepdim=True).clamp(min=1.0)
+                out = out + 0.5 * torch.einsum('bqk,kbc->qbc', w, v).to(out.dtype)
+            else:
+                out = out + 0.5 * v.mean(0, keepdim=True).to(out.dtype)
+        if query_pos is not None:
+            out = out + 0.1 * query_pos.to(out.dtype)
+        if reference_points is not None:                        # (B, Q, L, 2|4) -> (Q, B, 1)
+            out = out + 0.05 * reference_points.float().mean((2, 3)).transpose(0, 1).unsqueeze(-1).to(out.dtype)
+        return torch.tanh(out)
+
+
+def toy_seg_parts(C=16, Q=6, B=2):
+    g = torch.Generator().manual_seed(21)
+    shapes = [(3, 3), (4, 5), (7, 6), (9, 8)]                  # low -> high resolution
+    memories = [torch.randn(B, C, h, w, generator=g) for h, w in shapes]
+    mask_features = torch.randn(B, C, 9, 8, generator=g)
+    pos = {hw: torch.randn(B, C, hw[0], hw[1], generator=g) for hw in shapes}
+    emb = lambda n: torch.randn(n, C, generator=g)
+    return dict(C=C, Q=Q, B=B, shapes=shapes, memories=memories, mask_features=mask_features, pos=pos,
+                level_embed=emb(4), query_feat=emb(Q), query_embed=emb(Q), post_norm_w=torch.rand(C, generator=g) + 0.5,
+                post_norm_b=torch.randn(C, generator=g) * 0.1,
+                mlp=[torch.randn(C, C, generator=g) * 0.3 for _ in range(3)], mlp_b=[torch.randn(C, generator=g) * 0.1 for _ in range(3)])
+
+
+def golden_seg_forward():
+    """models/multi/seg_head/mask2former_head.py::Mask2FormerHead.forward (row a18: level cycling, all-masked-row reset,
+    forward_head after every layer) with toy decoder layers / pixel decoder / positional encoding."""
+    ref = sys.modules['ref_seg_head.mask2former_head']
+    H = ref.Mask2FormerHead
+    t = toy_seg_parts()
+    C = t['C']
+    post_norm = torch.nn.LayerNorm(C)
+    mask_embed = torch.nn.Sequential(torch.nn.Linear(C, C), torch.nn.ReLU(), torch.nn.Linear(C, C), torch.nn.ReLU(),
+                                     torch.nn.Linear(C, C))
+    with torch.no_grad():
+        post_norm.weight.copy_(t['post_norm_w']), post_norm.bias.copy_(t['post_norm_b'])
+        for k, i in enumerate((0, 2, 4)):
+            mask_embed[i].weight.copy_(t['mlp'][k]), mask_embed[i].bias.copy_(t['mlp_b'][k])
+    emb = lambda w: torch.nn.Embedding.from_pretrained(w.clone(), freeze=False)
+    fake = types.SimpleNamespace(
+        scheme=2, num_heads=2, num_transformer_feat_level=4, num_transformer_decoder_layers=9,
+        pixel_decoder=lambda enc, neck, bb: (t['mask_features'], t['memories']),
+        decoder_input_projs=[torch.nn.Identity() for _ in range(4)], level_embed=emb(t['level_embed']),
+        decoder_positional_encoding=lambda mask: t['pos'][tuple(mask.shape[-2:])],
+        query_feat=emb(t['query_feat']), query_embed=emb(t['query_embed']), mask_embed=mask_embed,
+        transformer_decoder=types.SimpleNamespace(post_norm=post_norm, layers=[ToyDecoderLayer() for _ in range(9)]))
+    fake.forward_head = lambda *a: H.forward_head(fake, *a)
+    with torch.no_grad():
+        out = H.forward(fake, None, None, None, [{}] * t['B'])
+    torch.save(dict(source='models/multi/seg_head/mask2former_head.py::Mask2FormerHead.forward (reference, run in place, toy layers)',
+                    out=out), os.path.join(OUT, 'reference_seg_forward.pt'))
+    return tuple(out.shape)
+
+
+def toy_det_parts(C=16, B=2, Q=9, pad=4, L=3, classes=5):
+    g = torch.Generator().manual_seed(33)
+    lin = lambda o, i: (torch.randn(o, i, generator=g) * 0.3, torch.randn(o, generator=g) * 0.1)
+    return dict(C=C, B=B, Q=Q, pad=pad, L=L, classes=classes,
+                query=torch.randn(pad + Q, B, C, generator=g), memory=torch.randn(20, B, C, generator=g),
+                reference_points=torch.rand(B, pad + Q, 4, generator=g) * 0.8 + 0.1,
+                valid_ratios=torch.rand(B, 4, 2, generator=g) * 0.3 + 0.7,
+                ref_point_head=[lin(C, 32 * 4 * 4), lin(C, C)], norm=(torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1),
+                reg=[[lin(C, C), lin(C, C), lin(4, C)] for _ in range(L + 1)], cls=[lin(classes, C) for _ in range(L + 1)],
+                topk_score=torch.randn(B, Q, classes, generator=g), topk_anchor=torch.rand(B, Q, 4, generator=g),
+                feats=[torch.randn(B, C, 8, 8, generator=g), torch.randn(B, C, 4, 4, generator=g)])
+
+
+def _mlp_from(ws, cls=torch.nn.Linear):
+    layers = []
+    for k, (w, b) in enumerate(ws):
+        l = cls(w.shape[1], w.shape[0])
+        with torch.no_grad():
+            l.weight.copy_(w), l.bias.copy_(b)
+        layers.append(l)
+        if k + 1 < len(ws):
+            layers.append(torch.nn.ReLU())
+    return torch.nn.Sequential(*layers) if len(layers) > 1 else layers[0]
+
+
+def golden_dino_decoder_and_head():
+    """models/multi/bbox_head/transformer.py::DinoTransformerDecoder.forward (row a14: reference-point scaling, sine
+    embedding -> ref_point_head, box refinement with detach, look-forward-twice outputs) and
+    models/multi/bbox_head/dino_head.py::DINOHead.forward (row a13: padding masks, per-level class / box branches on
+    inverse_sigmoid(reference)), both run in place with toy decoder layers / a toy transformer."""
+    tr = sys.modules['ref_dino_transformer']
+    dino = sys.modules['ref_bbox_head.dino_head']
+    t = toy_det_parts()
+    C, L = t['C'], t['L']
+    # NB: the sine embedding is 4 x 128 = 512 wide by construction
+    rph = [(torch.randn(C, 512, generator=torch.Generator().manual_seed(1)) * 0.05, t['ref_point_head'][0][1]), t['ref_point_head'][1]]
+    norm = torch.nn.LayerNorm(C)
+    with torch.no_grad():
+        norm.weight.copy_(t['norm'][0]), norm.bias.copy_(t['norm'][1])
+    reg = [_mlp_from(ws) for ws in t['reg']]
+    cls = [_mlp_from([w]) for w in t['cls']]
+    dec = types.SimpleNamespace(layers=[ToyDecoderLayer() for _ in range(L)], ref_point_head=_mlp_from(rph), norm=norm,
+                                return_intermediate=True,
+                                gen_sineembed_for_position=tr.DinoTransformerDecoder.gen_sineembed_for_position)
+    with torch.no_grad():
+        hs, refs = tr.DinoTransformerDecoder.forward(dec, t['query'], None, t['memory'], reference_points=t['reference_points'],
+                                                     valid_ratios=t['valid_ratios'], reg_branches=reg)
+    # head: toy transformer returns the decoder outputs above
+    metas = [dict(img_shape=(28, 32, 3), batch_input_shape=(32, 32)), dict(img_shape=(32, 30, 3), batch_input_shape=(32, 32))]
+    seen = {}
+
+    def toy_transformer(mlvl_feats, mlvl_masks, query_embeds, mlvl_pos, dn_label_query, dn_bbox_query, attn_mask, encoder,
+                        reg_branches=None, cls_branches=None, **kw):
+        seen['masks'] = [m.clone() for m in mlvl_masks]
+        return hs, refs, t['topk_score'], t['topk_anchor']
+    head = types.SimpleNamespace(transformer=toy_transformer, positional_encoding=lambda m: m.float().unsqueeze(1),
+                                 with_box_refine=True, as_two_stage=True, reg_branches=reg, cls_branches=cls,
+                                 label_embedding=torch.nn.Embedding(t['classes'], C))
+    with torch.no_grad():
+        oc, ob, ts, ta = dino.DINOHead.forward(head, None, t['feats'], metas, torch.zeros(t['B'], t['pad'], C),
+                                               torch.zeros(t['B'], t['pad'], 4), None)
+    torch.save(dict(source='DinoTransformerDecoder.forward + DINOHead.forward (reference, run in place, toy layers)',
+                    rph0=rph[0][0], hs=hs, refs=refs, masks=seen['masks'], outputs_classes=oc, outputs_coords=ob, metas=metas),
+               os.path.join(OUT, 'reference_dino_decoder_head.pt'))
+    return tuple(hs.shape), tuple(refs.shape), tuple(oc.shape), tuple(ob.shape)
+
+
+def toy_loss_parts(L=3, B=2, Q=12, pad=8, classes=20, sizes=(3, 2), groups=2):
+    g = torch.Generator().manual_seed(66)
+    shapes = [(640, 800, 3), (608, 736, 3)]
+    gtb, gtl = [], []
+    for b, n in enumerate(sizes):
+        h, w = shapes[b][:2]
+        x1, y1 = torch.rand(n, generator=g) * (w - 200), torch.rand(n, generator=g) * (h - 200)
+        gtb.append(torch.stack([x1, y1, x1 + 30 + 150 * torch.rand(n, generator=g), y1 + 30 + 150 * torch.rand(n, generator=g)], -1))
+        gtl.append(torch.randint(0, classes, (n,), generator=g))
+    box = lambda *s_: torch.cat([torch.rand(*s_, 2, generator=g) * 0.8 + 0.1, torch.rand(*s_, 2, generator=g) * 0.3 + 0.05], -1)
+    return dict(L=L, B=B, Q=Q, pad=pad, classes=classes, sizes=sizes, img_shapes=shapes, gt_bboxes=gtb, gt_labels=gtl,
+                all_cls=torch.randn(L, B, pad + Q, classes, generator=g) - 2.0, all_box=box(L, B, pad + Q),
+                enc_cls=torch.randn(B, Q, classes, generator=g) - 2.0, enc_box=box(B, Q),
+                dn_meta=dict(pad_size=pad, num_dn_group=groups))
+
+
+def golden_dino_loss():
+    """models/multi/bbox_head/dino_head.py::DINOHead.loss (+ loss_dn, loss_dn_single, get_dn_target) and
+    mmdet_detr_head/detr_head.py::DETRHead.loss_single / get_targets / _get_target_single (row a16), run in place,
+    UNBOUND on a namespace.  The mmdet objects those methods call (HungarianAssigner, PseudoSampler, FocalLoss,
+    L1Loss, GIoULoss, reduce_mean, box converters) are third-party and absent: they are restated from the oracle
+    (oracle/heads.py) and therefore NOT pinned by this fixture -- the in-tree flow is: target construction,
+    cls_avg_factor / num_total_pos, the per-image rescale factors, loss weights, dn handling and the 39 keys."""
+    sys.path.insert(0, ROOT)
+    from oracle import heads as oh
+    core = sys.modules['mmdet.core']
+    core.bbox_cxcywh_to_xyxy, core.bbox_xyxy_to_cxcywh = oh.bbox_cxcywh_to_xyxy, oh.bbox_xyxy_to_cxcywh
+    core.reduce_mean = lambda t: t                       # single process
+    detr = sys.modules['ref_bbox_head.mmdet_detr_head.detr_head']
+    dino = sys.modules['ref_bbox_head.dino_head']
+    for mod in (detr, dino):                             # names the modules imported before the shim was complete
+        mod.reduce_mean, mod.bbox_cxcywh_to_xyxy, mod.bbox_xyxy_to_cxcywh = core.reduce_mean, oh.bbox_cxcywh_to_xyxy, oh.bbox_xyxy_to_cxcywh
+        mod.multi_apply = core.multi_apply
+
+    class ToyAssigner:       # mmdet HungarianAssigner.assign -> AssignResult(num_gts, gt_inds, max_overlaps, labels)
+        def assign(self, bbox_pred, cls_pred, gt_bboxes, gt_labels, img_meta, gt_bboxes_ignore=None, eps=1e-7):
+            gt_inds = oh.hungarian_assign(bbox_pred, cls_pred, gt_bboxes, gt_labels, img_meta['img_shape'])
+            return types.SimpleNamespace(gt_inds=gt_inds, num_gts=gt_bboxes.size(0))
+
+    class ToySampler:        # mmdet PseudoSampler.sample -> SamplingResult
+        def sample(self, assign_result, bboxes, gt_bboxes, **kw):
+            pos_inds = torch.nonzero(assign_result.gt_inds > 0, as_tuple=False).squeeze(-1).unique()
+            neg_inds = torch.nonzero(assign_result.gt_inds == 0, as_tuple=False).squeeze(-1).unique()
+            pos_gt = assign_result.gt_inds[pos_inds] - 1
+            pos_gt_bboxes = gt_bboxes[pos_gt.long(), :] if gt_bboxes.numel() else torch.empty_like(gt_bboxes).view(-1, 4)
+            return types.SimpleNamespace(pos_inds=pos_inds, neg_inds=neg_inds, pos_assigned_gt_inds=pos_gt,
+                                         pos_gt_bboxes=pos_gt_bboxes)
+
+    def loss_cls(pred, target, weight=None, avg_factor=None):              # mmdet FocalLoss(gamma 2, alpha .25, w 1)
+        return 1.0 * oh.py_sigmoid_focal_loss(pred, target, weight, 2.0, 0.25, avg_factor)
+
+    def loss_bbox(pred, target, weight=None, avg_factor=None):             # mmdet L1Loss(loss_weight 5)
+        if target.numel() == 0:
+            return pred.sum() * 0
+        return 5.0 * ((pred - target).abs() * weight).sum() / avg_factor
+
+    def loss_iou(pred, target, weight=None, avg_factor=None):              # mmdet GIoULoss(loss_weight 2)
+        if weight is not None and not torch.any(weight > 0):
+            return (pred * weight).sum()
+        w = weight.mean(-1)
+        return 2.0 * ((1 - oh.bbox_overlaps_giou(pred, target, True)) * w).sum() / avg_factor
+    t = toy_loss_parts()
+    H, D = dino.DINOHead, detr.DETRHead
+    class FakeHead(types.SimpleNamespace):        # (the reference formats self.__class__.__name__ into an assert message)
+        pass
+    fake = FakeHead(num_classes=t['classes'], cls_out_channels=t['classes'], bg_cls_weight=0, sync_cls_avg_factor=True,
+                                 assigner=ToyAssigner(), sampler=ToySampler(), loss_cls=loss_cls, loss_bbox=loss_bbox,
+                                 loss_iou=loss_iou, extract_dn_outputs=H.extract_dn_outputs)
+    for name, owner in [('loss_single', D), ('get_targets', D), ('_get_target_single', D), ('loss_dn', H),
+                        ('loss_dn_single', H), ('get_dn_target', H), ('_get_dn_target_single', H)]:
+        setattr(fake, name, (lambda f: (lambda *a, **k: f(fake, *a, **k)))(getattr(owner, name)))
+    metas = [dict(img_shape=s) for s in t['img_shapes']]
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        with torch.no_grad():
+            losses = H.loss(fake, t['all_cls'], t['all_box'], t['enc_cls'], t['enc_box'], t['gt_bboxes'], t['gt_labels'], metas,
+                            t['dn_meta'])
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    out = {k: float(v) for k, v in losses.items()}
+    json.dump(dict(source='DINOHead.loss / DETRHead.loss_single (reference, run in place; third-party assigner / sampler / '
+                          'loss modules restated from the oracle)', keys=list(out.keys()), losses=out),
+              open(os.path.join(OUT, 'reference_dino_loss.json'), 'w'), indent=1)
+    return len(out), sum(out.values())
+
+
+def toy_two_stage_parts(C=16, B=2, K=7, classes=5, pad=3):
+    g = torch.Generator().manual_seed(44)
+    lin = lambda o, i: (torch.randn(o, i, generator=g) * 0.3, torch.randn(o, generator=g) * 0.1)
+    shapes = [(6, 5), (3, 3)]
+    masks = [torch.zeros(B, h, w, dtype=torch.bool) for h, w in shapes]
+    masks[0][1, :, 4:] = True                      # image 1 is padded on the right
+    masks[1][1, :, 2:] = True
+    return dict(C=C, B=B, K=K, classes=classes, pad=pad, shapes=shapes, masks=masks,
+                feats=[torch.randn(B, C, h, w, generator=g) for h, w in shapes],
+                pos=[torch.randn(B, C, h, w, generator=g) for h, w in shapes], level_embeds=torch.randn(2, C, generator=g),
+                enc_output=lin(C, C), enc_norm=(torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1),
+                cls=lin(classes, C), reg=[lin(C, C), lin(C, C), lin(4, C)], query_embed=torch.randn(K, C, generator=g),
+                dn_label=torch.randn(B, pad, C, generator=g), dn_bbox=torch.randn(B, pad, 4, generator=g))
+
+
+def toy_encoder(query=None, query_pos=None, **kw):
+    return torch.tanh(query + 0.1 * query_pos.to(query.dtype))
+
+
+class ToyDecoder:
+    num_layers = 1
+
+    def __call__(self, query=None, value=None, reference_points=None, **kw):
+        self.seen = dict(query=query.clone(), reference_points=reference_points.clone(), value=value.clone(),
+                         key_padding_mask=kw.get('key_padding_mask'), attn_masks=kw.get('attn_masks'))
+        return torch.stack([query, query * 0.5]), torch.stack([reference_points, reference_points * 0.9])
+
+
+def golden_dino_transformer():
+    """models/multi/bbox_head/transformer.py::DinoTransformer.forward (row a13: flattening, level embeddings, the
+    two-stage top-k proposal selection, dn / matching query concatenation), run in place with a toy encoder and
+    decoder.  Its three mmdet BASE-CLASS methods (get_valid_ratio, get_reference_points,
+    gen_encoder_output_proposals; third-party, not in /root/reference) are taken from this repo's restatement, so
+    THEY are not pinned by this fixture -- the in-tree control flow around them is."""
+    sys.path.insert(0, ROOT)
+    from rscotr_b200.models.det_head import DinoTransformer as Mine
+    tr = sys.modules['ref_dino_transformer']
+    t = toy_two_stage_parts()
+    C = t['C']
+    enc_out = _mlp_from([t['enc_output']])
+    enc_norm = torch.nn.LayerNorm(C)
+    with torch.no_grad():
+        enc_norm.weight.copy_(t['enc_norm'][0]), enc_norm.bias.copy_(t['enc_norm'][1])
+    dec = ToyDecoder()
+    fake = types.SimpleNamespace(as_two_stage=True, level_embeds=t['level_embeds'], decoder=dec, two_stage_num_proposals=t['K'],
+                                 query_embed=torch.nn.Embedding.from_pretrained(t['query_embed'].clone()), enc_output=enc_out,
+                                 enc_output_norm=enc_norm, get_valid_ratio=Mine.get_valid_ratio,
+                                 get_reference_points=lambda ss, vr, device=None: Mine.get_reference_points(
+                                     [tuple(x) for x in ss.tolist()], vr, device))
+    fake.gen_encoder_output_proposals = lambda mem, mask, ss: Mine.gen_encoder_output_proposals(
+        fake, mem, mask, [tuple(x) for x in ss.tolist()])
+    fake.proposal_grid = Mine.proposal_grid
+    cls = [None, _mlp_from([t['cls']])]
+    reg = [None, _mlp_from(t['reg'])]
+    with torch.no_grad():
+        out = tr.DinoTransformer.forward(fake, t['feats'], t['masks'], None, t['pos'], t['dn_label'], t['dn_bbox'], None,
+                                         toy_encoder, reg_branches=reg, cls_branches=cls)
+    torch.save(dict(source='models/multi/bbox_head/transformer.py::DinoTransformer.forward (reference, run in place, toy encoder/decoder)',
+                    out=[o.clone() for o in out], decoder_saw={k: v for k, v in dec.seen.items()}),
+               os.path.join(OUT, 'reference_dino_transformer.pt'))
+    return [tuple(o.shape) for o in out]
+
+
+def toy_pixel_decoder_parts(C=8, B=2):
+    g = torch.Generator().manual_seed(55)
+    sizes = [(16, 12), (8, 6), (4, 3), (2, 2)]                 # neck levels, strides 8 / 16 / 32 / 64 (high -> low resolution)
+    return dict(C=C, B=B, sizes=sizes, strides=[8, 16, 32, 64], neck=[torch.randn(B, C, h, w, generator=g) for h, w in sizes],
+                pos={hw: torch.randn(B, C, hw[0], hw[1], generator=g) for hw in sizes},
+                level_encoding=torch.randn(4, C, generator=g), mask_w=torch.randn(C, C, 1, 1, generator=g) * 0.3,
+                mask_b=torch.randn(C, generator=g) * 0.1, backbone=[torch.randn(B, C, 4, 4, generator=g)])
+
+
+class ToyPointGenerator:
+    """mmdet 2.25.1 core/anchor/point_generator.py MlvlPointGenerator.single_level_grid_priors, offset 0.5, restated
+    (third-party; NOT pinned by the fixture)."""
+
+    def __init__(self, strides):
+        self.strides = strides
+
+    def single_level_grid_priors(self, featmap_size, level_idx, device='cpu'):
+        h, w = featmap_size
+        s = self.strides[level_idx]
+        sx = (torch.arange(0, w, device=device) + 0.5) * s
+        sy = (torch.arange(0, h, device=device) + 0.5) * s
+        xx = sx.repeat(len(sy))
+        yy = sy.view(-1, 1).repeat(1, len(sx)).view(-1)
+        return torch.stack([xx, yy], dim=-1).float()
+
+
+class ToyEncoder:
+    def __call__(self, query=None, query_pos=None, **kw):
+        self.seen = dict(query=query.clone(), query_pos=query_pos.clone(), reference_points=kw['reference_points'].clone(),
+                         spatial_shapes=kw['spatial_shapes'].clone(), level_start_index=kw['level_start_index'].clone())
+        return torch.tanh(query + 0.1 * query_pos.to(query.dtype))
+
+
+def golden_seg_pixel_decoder():
+    """models/multi/seg_head/pixel_decoder.py::MlvlSegPixelDecoder.forward (row a17: level order low -> high
+    resolution, level encodings, normalised reference points, what the shared encoder is called with, memory split,
+    mask_feature conv), run in place with a toy encoder / positional encoding / point generator."""
+    _stub_packages(['mmcv.cnn', 'mmcv.cnn.bricks.transformer', 'mmcv.runner', 'mmdet.core.anchor'])
+    ref = load('models/multi/seg_head/pixel_decoder.py', 'ref_seg_head.pixel_decoder')
+    t = toy_pixel_decoder_parts()
+    C = t['C']
+    mask_feature = torch.nn.Conv2d(C, C, 1)
+    with torch.no_grad():
+        mask_feature.weight.copy_(t['mask_w']), mask_feature.bias.copy_(t['mask_b'])
+    enc = ToyEncoder()
+    fake = types.SimpleNamespace(num_encoder_levels=4, num_input_levels=4, strides=t['strides'], num_outs=4,
+                                 postional_encoding=lambda m: t['pos'][tuple(m.shape[-2:])],
+                                 level_encoding=torch.nn.Embedding.from_pretrained(t['level_encoding'].clone()),
+                                 point_generator=ToyPointGenerator(t['strides']), lateral_convs=[], output_convs=[],
+                                 mask_feature=mask_feature)
+    with torch.no_grad():
+        mf, feats = ref.MlvlSegPixelDecoder.forward(fake, enc, t['neck'], t['backbone'])
+    torch.save(dict(source='models/multi/seg_head/pixel_decoder.py::MlvlSegPixelDecoder.forward (reference, run in place, toy parts)',
+                    mask_feature=mf, feats=list(feats), encoder_saw=enc.seen), os.path.join(OUT, 'reference_seg_pixel_decoder.pt'))
+    return tuple(mf.shape), [tuple(f.shape) for f in feats]
+
+
 # ----------------------------------------------------------------------------- MultiDataLoader
 class _ToyDataset(torch.utils.data.Dataset):
     """n samples {'idx': i}; `task` is what MultiDataLoader tags batches with"""
@@ -457,8 +800,14 @@ if __name__ == '__main__':
     t = golden_train_step()
     print('train_step:', [(c['task'], float(c['loss']), len(c['log_vars'])) for c in t])
     print('seg forward_head:', golden_seg_forward_head())
+    print('seg forward:', golden_seg_forward())
+    print('seg pixel decoder:', golden_seg_pixel_decoder())
     d = golden_dn_targets()
     print('dn targets:', [(c['sizes'], c['num_total_pos'], c['num_total_neg']) for c in d])
+    e0 = golden_sineembed()
+    print('dino decoder + head:', golden_dino_decoder_and_head())
+    print('dino transformer:', golden_dino_transformer())
+    print('dino loss:', golden_dino_loss())
     m = golden_multi_data_loader()
     print('multi data loader:', [(c['strategy'], c['sequence'][:4]) for c in m])
     e = golden_sineembed()
