@@ -6,12 +6,13 @@ imported only by ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``; nothing under
 ``rscotr_b200/`` may import it.
 
-PARITY PINNED ONLY IN PART.  Pinned against outputs of the reference's OWN code run in this container
-(``tools/make_golden.py`` -> ``tests/golden/reference_*.{pt,json}``, checked by
-``tests/test_golden_reference.py``): the contrastive-denoising query generator
-(models/multi/bbox_head/query_denoising.py, row a15), the DINO decoder sine embedding
-(models/multi/bbox_head/transformer.py:43-76, row a14), the iteration strategies and the MultiDataLoader
-(mtl/data/*.py, row a22).  Everything else is PARITY UNPINNED: the arithmetic of the path lives in un-vendored third-party
+PARITY PINNED ONLY IN PART.  Pinned against outputs of the reference's OWN in-tree code run in this container
+(``tools/make_golden.py`` -> ``tests/golden/reference_*``, checked by ``tests/test_golden_reference.py`` on CPU and,
+with the same fixtures, on the CUDA path): CdnQueryGenerator (a15), the DINO decoder / sine embedding (a14),
+DinoTransformer.forward and DINOHead.forward (a13), DINOHead.loss / DETRHead.loss_single / dn targets (a16, in-tree
+flow), MlvlSegPixelDecoder.forward (a17), Mask2FormerHead.forward / forward_head (a18), MTL.train_step /
+_parse_losses (a21), the iteration strategies and MultiDataLoader (a22).
+Everything else is PARITY UNPINNED: the arithmetic of the path lives in un-vendored third-party
 packages (mmcv-full 1.6.1, mmdet 2.25.1, mmsegmentation 0.28.0, mmcls) that are
 not installable in this image, and the reference ships no tests, golden vectors
 or fixtures.  The restatement follows the reference's
