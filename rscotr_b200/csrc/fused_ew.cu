@@ -274,7 +274,7 @@ template <bool FAST>
 __device__ __forceinline__ void gelu_parts(float x, float &cdf, float &u) {
   if (FAST) {
     const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));   // MUFU.RCP (an IEEE reciprocal is ~8 instructions; these passes are issue-bound)
     u = exp2f(-0.72134752044448170f * x * x);                      // exp(-x^2/2)
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);

@@ -4,9 +4,11 @@ Mirrors (names, arguments, outputs, loss keys) the reference's
 models/multi/bbox_head/{dino_head,transformer,query_denoising}.py and the
 vendored mmdet heads in models/multi/bbox_head/mmdet_detr_head/ (SURVEY 8a rows
 a13-a16), with these structural changes for a GPU-resident step:
-  * the 7 Hungarian problems x batch are costed on the GPU in one batched pass
-    and shipped to scipy with ONE device->host copy (reference: one sync per
-    (layer, image), detr_head.py:513);
+  * on CUDA the 7 x B Hungarian problems (cost matrices + linear sum assignment) run in ONE kernel launch
+    (rsc_det_match) and the 13 x 3 loss terms in fused kernels (rsc_det_loss_*): the det step has no host phase
+    and is one CUDA graph (reference: scipy behind a device->host sync per (layer, image), detr_head.py:513).
+    `fused_loss = False` keeps the reference's structure (ATen losses, scipy on the host with one batched
+    device->host copy) -- used by the tests as the independent implementation the kernels are checked against;
   * no .cuda() hard-coding (query_denoising.py:125-180), no per-loss .item().
 """
 import copy
