@@ -51,6 +51,9 @@ def _worker(rank, world, port, out_dir):
             out = eng.train_iter(batch)
             res[task] = dict(g_local=g_local, loss=float(out['loss'].detach()), log=dict(out['log_vars'].items()),
                              ranges=list(eng._task_ranges[task]))
+    # packed device-side averaging factors of the fused det loss (one all-reduce, no .item())
+    res['factors'] = model.bbox_head._avg_factors_dev([2 + rank, 0], [10, 5], 'cpu').clone()
+    res['sync'] = bool(model.bbox_head.sync_cls_avg_factor)
     res['params'] = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     torch.save(res, os.path.join(out_dir, 'rank%d.pt' % rank))
     dist.destroy_process_group()
@@ -62,6 +65,11 @@ def test_two_rank_data_parallel_step(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0 = torch.load(tmp_path / 'rank0.pt')
     r1 = torch.load(tmp_path / 'rank1.pt')
+    # cls_avg_factor / num_total_pos: cross-rank means (pos 2 and 3 -> 2.5), clamped to >= 1 (pos 0 -> 1)
+    for r in (r0, r1):
+        assert torch.allclose(r['factors'][1], torch.tensor([2.5, 1.0]))
+        if r['sync']:
+            assert torch.allclose(r['factors'][0], torch.tensor([2.5, 1.0]))
     # replicas stay identical
     assert torch.equal(r0['params'], r1['params'])
     for task in ('cls', 'det', 'seg'):

@@ -1,0 +1,95 @@
+"""CPU unit tests of the small host-side helpers the step relies on: shape-keyed geometry cache,
+packed loss dicts, batched stochastic-depth draws, the static denoising-target table, flat buffer
+layout of the step engine."""
+import torch
+
+import rscotr_b200.models  # noqa: F401
+from rscotr_b200.models.bricks import DropPath, GeomCache, PackedLosses, draw_drop_paths
+from rscotr_b200.models.det_head import DINOHead
+
+
+def test_geom_cache_evicts_oldest_and_runs_without_grad():
+    c = GeomCache(capacity=2)
+    calls = []
+
+    def make(k):
+        def f():
+            calls.append(k)
+            assert not torch.is_grad_enabled()
+            return torch.full((1,), float(k))
+        return f
+
+    a = c.get(('s', 1), make(1))
+    assert c.get(('s', 1), make(1)) is a and calls == [1]
+    c.get(('s', 2), make(2))
+    c.get(('s', 3), make(3))                       # evicts key 1 (insertion order)
+    assert set(c.entries) == {('s', 2), ('s', 3)}
+    c.get(('s', 1), make(1))
+    assert calls == [1, 2, 3, 1]
+
+
+def test_packed_losses_behaves_like_the_reference_loss_dict():
+    packed = torch.tensor([1., 2., 3.], requires_grad=True)
+    d = PackedLosses(['loss_cls', 'loss_bbox', 'loss_iou'], packed * 2)
+    assert list(d.keys()) == ['loss_cls', 'loss_bbox', 'loss_iou'] and len(d) == 3 and 'loss_bbox' in d
+    assert float(d['loss_bbox']) == 4. and float(d.get('loss_iou')) == 6. and d.get('nope') is None
+    assert [float(v) for v in d.values()] == [2., 4., 6.]
+    assert {k: float(v) for k, v in d.items()} == dict(loss_cls=2., loss_bbox=4., loss_iou=6.)
+    # per-key tensors are views of the packed tensor: gradients flow back to it
+    sum(v for k, v in d.items() if 'loss' in k).backward()
+    assert torch.equal(packed.grad, torch.full((3,), 2.))
+
+
+def test_drop_path_forced_mask_and_batched_draws():
+    x = torch.arange(12.).view(3, 2, 2)
+    m = DropPath(0.5).train()
+    m.forced_mask = torch.tensor([0., 2., 2.])
+    assert torch.equal(m(x), x * m.forced_mask.view(3, 1, 1))
+    assert torch.equal(m.scale_vec(x), m.forced_mask)
+    idn = torch.ones_like(x)
+    assert torch.equal(m.add_to(idn, x), idn + x * m.forced_mask.view(3, 1, 1))
+    # eval / p = 0: identity, no tensor made
+    assert DropPath(0.5).eval().scale_vec(x) is None and DropPath(0.).train().scale_vec(x) is None
+    # one batched draw for a list of modules: factors are 0 or 1/keep, consumed exactly once
+    mods = [DropPath(0.).train(), DropPath(0.25).train(), DropPath(0.5).train(), m]
+    torch.manual_seed(0)
+    draw_drop_paths(mods, 64, 'cpu', torch.float32)
+    assert mods[0].drawn is None and mods[3].drawn is None        # p = 0 and forced masks are skipped
+    for mod in mods[1:3]:
+        keep = 1 - mod.drop_prob
+        s = mod.scale_vec(torch.zeros(64, 1))
+        assert s.shape == (64,) and bool(((s == 0) | ((s - 1 / keep).abs() < 1e-6)).all())
+        assert mod.drawn is None
+    # the draw keeps roughly `keep` of the samples
+    big = [DropPath(0.3).train()]
+    draw_drop_paths(big, 20000, 'cpu', torch.float32)
+    assert abs(float((big[0].drawn > 0).float().mean()) - 0.7) < 0.02
+
+
+def test_dn_assign_table_layout():
+    # 2 images with 2 and 1 boxes, 3 groups, pad_size = 3 groups * 2 * max_gt(2) = 12 -> single = 4
+    t = DINOHead.dn_assign_table([2, 1], 3, 12)
+    assert t[0] == [0, 1, -1, -1] * 3
+    assert t[1] == [2, -1, -1, -1] * 3
+    assert DINOHead.dn_assign_table([0, 0], 2, 0) == [[], []]
+    assert DINOHead.dn_assign_table([], 0, 0) == []
+
+
+def test_step_engine_flat_layout_and_cpu_prefetch_noop():
+    from rscotr_b200.config import MODELS
+    from rscotr_b200.mtl.engine import StepEngine
+    from tests.test_host_model import small_cfg
+    torch.manual_seed(0)
+    model = MODELS.build(small_cfg().model)
+    model.init_weights()
+    eng = StepEngine(model, dict(type='AdamW', lr=1e-3, weight_decay=1e-4), device='cpu',
+                     compute_dtype=torch.float32, use_graphs=False)
+    # every parameter is a view of the flat buffer, spans are 64-element aligned and do not overlap
+    base = eng.flat_param.data_ptr()
+    spans = sorted(((p.data_ptr() - base) // 4, p.numel()) for p in model.parameters())
+    end = 0
+    for off, n in spans:
+        assert off % 64 == 0 and off >= end
+        end = off + n
+    assert end <= eng.flat_param.numel() == eng.flat_grad.numel()
+    eng.prefetch(dict(task='cls'))                 # no copy stream on CPU: must be a no-op, not an error
