@@ -218,6 +218,7 @@ class SwinTransformer(nn.Module):
         self.out_indices = tuple(out_indices)
         self.convert_weights = convert_weights
         self.init_cfg = init_cfg
+        self.pretrained = pretrained
         self.patch_embed = PatchEmbed(in_channels, embed_dims, patch_size, strides[0], patch_norm)
         self.drop_after_pos = nn.Dropout(p=drop_rate)
         total_depth = sum(depths)
@@ -234,12 +235,27 @@ class SwinTransformer(nn.Module):
         self.num_features = [int(embed_dims * 2 ** i) for i in range(len(depths))]
         for i in self.out_indices:
             self.add_module('norm%d' % i, LayerNorm(self.num_features[i]))
-        self.init_weights()
+        self._random_init()
 
     def init_weights(self):
-        """init_cfg=None branch of mmdet (trunc_normal .02 linears, unit LayerNorm).
-        A `Pretrained` init_cfg needs the checkpoint file; absent (no network) the
-        random init stands (bench uses synthetic weights)."""
+        """mmdet SwinTransformer.init_weights: init_cfg=None -> trunc_normal .02 linears, unit LayerNorm;
+        init_cfg=dict(type='Pretrained', checkpoint=...) -> load (and, with convert_weights, convert) the
+        checkpoint (mtl/utils/checkpoint.py).  The reference cfg names a URL; there is no network here, so a
+        checkpoint that is not a local file leaves the random init in place and says so."""
+        self._random_init()
+        ckpt = self.pretrained
+        if isinstance(self.init_cfg, dict) and self.init_cfg.get('type') == 'Pretrained':
+            ckpt = self.init_cfg.get('checkpoint', ckpt)
+        if ckpt:
+            import os
+            if os.path.isfile(str(ckpt)):
+                from ..mtl.utils.checkpoint import load_swin_pretrained
+                load_swin_pretrained(self, ckpt, self.convert_weights)
+            else:
+                import warnings
+                warnings.warn('backbone checkpoint %r is not a local file (no network): keeping the random init' % (ckpt,))
+
+    def _random_init(self):
         for m in self.modules():
             if isinstance(m, nn.Linear):
                 nn.init.trunc_normal_(m.weight, std=.02)

@@ -7,7 +7,8 @@ import torch.distributed as dist
 
 from ..data import build_datasets, build_dataloaders, build_multidataloader
 from ..engine import StepEngine
-from ..runner import IterBasedRunner, MultiDatasetsEvalHook
+from ..runner import CheckpointHook, IterBasedRunner, MultiDatasetsEvalHook
+from ..utils.checkpoint import find_latest_checkpoint
 
 
 def train_model(model, datasets, cfg, distributed=False, validate=False, timestamp=None, meta=None):
@@ -25,11 +26,22 @@ def train_model(model, datasets, cfg, distributed=False, validate=False, timesta
     runner = IterBasedRunner(engine, cfg.runner['max_iters'], work_dir=cfg.get('work_dir'), logger=logger, meta=meta,
                              log_interval=cfg.get('log_config', {}).get('interval', 50))
     runner.timestamp = timestamp
+    if cfg.get('checkpoint_config'):
+        ck = dict(cfg.checkpoint_config)
+        ck.setdefault('by_epoch', False)
+        runner.register_hook(CheckpointHook(**ck), priority='NORMAL')
     if validate:
         val_dataset = build_datasets(cfg.data, split='val', synthetic=cfg.get('synthetic'))
         val_dataloader = build_dataloaders(cfg, distributed, val_dataset, train=False)
         eval_cfg = dict(cfg.get('evaluation', {}))
         eval_cfg['by_epoch'] = cfg.runner['type'] != 'IterBasedRunner'
         runner.register_hook(MultiDatasetsEvalHook(val_dataloader, **eval_cfg), priority='LOW')
+    resume_from = cfg.get('resume_from')
+    if resume_from is None and cfg.get('auto_resume') and cfg.get('work_dir'):
+        resume_from = find_latest_checkpoint(cfg.work_dir)
+    if resume_from:
+        runner.resume(resume_from)
+    elif cfg.get('load_from'):
+        runner.load_checkpoint(cfg.load_from)
     runner.run(data_loader, cfg.get('workflow', [('train', 1)]))
     return runner

@@ -1,2 +1,2 @@
 from .iter_runner import IterBasedRunner  # noqa: F401
-from .hooks import MultiDatasetsEvalHook  # noqa: F401
+from .hooks import MultiDatasetsEvalHook, CheckpointHook  # noqa: F401

@@ -1,1 +1,2 @@
 from .evaluation import MultiDatasetsEvalHook  # noqa: F401
+from .checkpoint import CheckpointHook  # noqa: F401

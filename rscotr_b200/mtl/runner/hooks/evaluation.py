@@ -1,6 +1,8 @@
 """MultiDatasetsEvalHook (reference mtl/runner/hooks/evaluation.py:29-148): every
 `interval` iterations run all val loaders, call each dataset's evaluate(), log
 "{dataset}.{metric}", keep the best weighted mean of the configured keys."""
+import torch.distributed as dist
+
 from ...engine.test import single_gpu_test
 
 
@@ -12,6 +14,7 @@ class MultiDatasetsEvalHook:
         self.test_fn = test_fn or single_gpu_test
         self.eval_kwargs = eval_kwargs
         self.best_score = None
+        self.best_ckpt_path = None
 
     def after_train_iter(self, runner):
         if self.by_epoch or (runner.iter + 1) % self.interval != 0:
@@ -23,7 +26,24 @@ class MultiDatasetsEvalHook:
         if score is not None and (self.best_score is None or score > self.best_score):
             self.best_score = score
             runner.meta['best_score'] = score
+            self._save_best(runner)
         runner.model.train()
+
+    def _save_best(self, runner):
+        """EvalHook._save_ckpt: keep ONE `best_<keys>_iter_N.pth` next to the periodic checkpoints
+        (reference evaluation.py:124-128; file stem = KeyIndicator.__repr__, evaluation.py:18-21)."""
+        import os
+        work_dir = getattr(runner, 'work_dir', None)
+        if not work_dir or not hasattr(runner, 'save_checkpoint') or not isinstance(self.save_best, dict):
+            return
+        if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
+            return
+        stem = '_'.join(k.replace('.', '_') for k in self.save_best)
+        if self.best_ckpt_path and os.path.isfile(self.best_ckpt_path):
+            os.remove(self.best_ckpt_path)
+        name = 'best_%s_iter_%d.pth' % (stem, runner.iter)
+        self.best_ckpt_path = runner.save_checkpoint(work_dir, name, create_symlink=False)
+        runner.meta.setdefault('hook_msgs', {}).update(best_score=self.best_score, best_ckpt=self.best_ckpt_path)
 
     def evaluate(self, runner, results):
         logs = {}

@@ -23,6 +23,31 @@ class IterBasedRunner:
     def register_hook(self, hook, priority='NORMAL'):
         self.hooks.append(hook)
 
+    # -- checkpoints (mmcv BaseRunner.save_checkpoint / load_checkpoint / IterBasedRunner.resume) ------------
+    def save_checkpoint(self, out_dir, filename_tmpl='iter_{}.pth', meta=None, save_optimizer=True, create_symlink=True):
+        import os
+        import shutil
+        from ..utils.checkpoint import save_checkpoint
+        m = dict(self.meta or {})
+        m.update(meta or {})
+        name = filename_tmpl.format(self.iter) if '{}' in filename_tmpl else filename_tmpl
+        path = save_checkpoint(self.engine, os.path.join(out_dir, name), meta=m, save_optimizer=save_optimizer)
+        if create_symlink:
+            shutil.copyfile(path, os.path.join(out_dir, 'latest.pth'))      # (mmcv links; a copy also works on any fs)
+        return path
+
+    def load_checkpoint(self, filename, map_location='cpu', strict=False, revise_keys=((r'^module\.', ''),)):
+        from ..utils.checkpoint import load_checkpoint
+        return load_checkpoint(self.model, filename, strict=strict, revise_keys=revise_keys, engine=self.engine)[0]
+
+    def resume(self, checkpoint, resume_optimizer=True, map_location='default'):
+        from ..utils.checkpoint import resume
+        meta = resume(self.engine, checkpoint, resume_optimizer)
+        self.meta.update({k: v for k, v in meta.items() if k in ('hook_msgs',)})
+        if self.logger:
+            self.logger.info('resumed from %s, iter %d', checkpoint, self.iter)
+        return meta
+
     def run(self, data_loaders, workflow=(('train', 1),), **kwargs):
         loader = data_loaders[0]
         it = iter(loader)
