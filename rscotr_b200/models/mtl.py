@@ -26,6 +26,29 @@ def _build(cfg):
     return build_from_cfg(dict(cfg), MODELS)
 
 
+def normalize_on_device(img, img_metas):
+    """Device half of a deferred `Normalize` (mtl/data/transforms.py, defer=True): the loader ships the batch
+    as uint8 BGR (4x fewer H2D bytes than fp32); here (x[RGB] - mean) / std is applied on the device and the
+    right/bottom padding is re-zeroed (the reference pads AFTER normalising, with 0).  A float batch passes
+    through untouched."""
+    if not torch.is_tensor(img) or img.dtype != torch.uint8:
+        return img
+    cfg = img_metas[0]['img_norm_cfg']
+    mean = const_tensor([float(v) for v in cfg['mean']], torch.float32, img.device).view(1, -1, 1, 1)
+    inv = const_tensor([1.0 / float(v) for v in cfg['std']], torch.float32, img.device).view(1, -1, 1, 1)
+    x = img.flip(1) if cfg.get('to_rgb', True) else img
+    x = (x.float() - mean) * inv
+    H, W = img.shape[-2:]
+    shapes = [tuple(m.get('img_shape', (H, W))[:2]) for m in img_metas]
+    if any(s != (H, W) for s in shapes):
+        hs = const_tensor([s[0] for s in shapes], torch.int64, img.device).view(-1, 1, 1, 1)
+        ws = const_tensor([s[1] for s in shapes], torch.int64, img.device).view(-1, 1, 1, 1)
+        ys = torch.arange(H, device=img.device).view(1, 1, H, 1)
+        xs = torch.arange(W, device=img.device).view(1, 1, 1, W)
+        x = x * ((ys < hs) & (xs < ws))
+    return x
+
+
 def bbox2result(bboxes, labels, num_classes):
     if bboxes.shape[0] == 0:
         import numpy as np
@@ -163,6 +186,8 @@ class MTL(nn.Module):
     # phases in CUDA graphs; only the det task has host work (Hungarian matching) in the middle.
     def train_step_begin(self, data):
         task = data.get('task', None)
+        if torch.is_tensor(data['img']) and data['img'].dtype == torch.uint8:
+            data = dict(data, img=normalize_on_device(data['img'], data['img_metas']))
         if task == 'det' and hasattr(self.bbox_head, 'forward_train_begin') and not (
                 getattr(self.bbox_head, 'fused_loss', False) and data['img'].is_cuda):
             # (with the GPU matching + fused loss kernels the det step has no host phase at all)
@@ -206,6 +231,10 @@ class MTL(nn.Module):
         return dict(loss=loss, log_vars=log_vars, num_samples=len(data['img_metas']))
 
     def forward(self, task, img, img_metas, return_loss=True, dataset_name=None, **kwargs):
+        if isinstance(img, list):
+            img = [normalize_on_device(i, m) for i, m in zip(img, img_metas)]
+        else:
+            img = normalize_on_device(img, img_metas)
         if return_loss:
             return self.forward_train(task=task, img=img, img_metas=img_metas, **kwargs)
         return self.forward_test(task=task, img=img, img_metas=img_metas, **kwargs)

@@ -17,9 +17,10 @@ class MultiDatasetsEvalHook:
         self.best_ckpt_path = None
 
     def after_train_iter(self, runner):
-        if self.by_epoch or (runner.iter + 1) % self.interval != 0:
+        # (runner.iter already counts the iteration that just finished: mmcv's `iter + 1`)
+        if self.by_epoch or runner.iter % self.interval != 0:
             return
-        if self.start is not None and runner.iter + 1 < self.start:
+        if self.start is not None and runner.iter < self.start:
             return
         results = self.test_fn(runner.model, self.dataloaders)
         score = self.evaluate(runner, results)
