@@ -23,8 +23,10 @@ class _SyntheticLoader:
     def __iter__(self):
         if self._cache is None:
             self._cache = self._make()
+        self.dataset._served = []                      # ground truth in serving order, for dataset.evaluate()
         for i in range(self.length):
             b = self._cache[i % len(self._cache)]
+            self.dataset._served.append(b)
             yield dict(b)
 
 
@@ -39,6 +41,27 @@ class SyntheticDataset:
     def __init__(self, task, img_size=(800, 800), num_classes=None, num_boxes=8, dtype=torch.float32):
         self.task, self.img_size, self.num_boxes, self.dtype = task, tuple(img_size), num_boxes, dtype
         self.num_classes = num_classes or dict(cls=45, det=20, seg=5)[task]
+
+    def evaluate(self, results, metric=None, **kwargs):
+        """same metric code as the real datasets (mtl/data/metrics.py), against the batches the loader served."""
+        from . import metrics as M
+        served = getattr(self, '_served', [])
+        if self.task == 'cls':
+            gt = torch.cat([b['gt_label'] for b in served]).numpy()
+            return M.evaluate_cls(results, gt, metric or 'accuracy', kwargs.get('metric_options'))
+        if self.task == 'det':
+            gts, n = [], 0
+            for b in served:
+                for boxes, labels in zip(b['gt_bboxes'], b['gt_labels']):
+                    for (x1, y1, x2, y2), l in zip(boxes.tolist(), labels.tolist()):
+                        gts.append(dict(image_id=n, category_id=l + 1, bbox=[x1, y1, x2 - x1, y2 - y1],
+                                        area=(x2 - x1) * (y2 - y1), iscrowd=0))
+                    n += 1
+            return M.evaluate_det(results, gts, list(range(n)), list(range(1, self.num_classes + 1)), None, metric or 'bbox',
+                                  kwargs.get('iou_thrs'), kwargs.get('classwise', False))
+        labels = [l[0] for b in served for l in b['gt_semantic_seg']]
+        pre = [M.intersect_and_union(torch.as_tensor(p), l, self.num_classes, 255) for p, l in zip(results, labels)]
+        return M.evaluate_seg(pre, [str(c) for c in range(self.num_classes)], metric or 'mIoU')
 
     def _metas(self, B):
         H, W = self.img_size

@@ -93,3 +93,30 @@ def test_step_engine_flat_layout_and_cpu_prefetch_noop():
         end = off + n
     assert end <= eng.flat_param.numel() == eng.flat_grad.numel()
     eng.prefetch(dict(task='cls'))                 # no copy stream on CPU: must be a no-op, not an error
+
+
+def test_eval_hook_on_synthetic_loaders():
+    """MultiDatasetsEvalHook / single_gpu_test over the synthetic val loaders (what a GPU box without data runs)."""
+    from rscotr_b200.config import MODELS
+    from rscotr_b200.mtl.data import build_datasets
+    from rscotr_b200.mtl.data.synthetic import _SyntheticLoader
+    from rscotr_b200.mtl.engine.test import single_gpu_test
+    from tests.cpu_ops_shim import cpu_ops
+    from tests.test_host_model import small_cfg
+    torch.manual_seed(0)
+    model = MODELS.build(small_cfg().model)
+    model.init_weights()
+    sets = build_datasets({'c': dict(task='cls'), 'd': dict(task='det'), 's': dict(task='seg')},
+                          split='val', synthetic=dict(img_size=(64, 64), det=dict(num_boxes=2)))
+    loaders = {k: _SyntheticLoader(v, 2, 2, seed=3, pin=False) for k, v in sets.items()}
+    with cpu_ops():
+        results = single_gpu_test(model, loaders)
+    assert len(results['c']) == 4 and results['c'][0].shape == (45,)
+    assert len(results['d']) == 4 and len(results['d'][0]) == 20 and results['d'][0][0].shape[1] == 5
+    assert len(results['s']) == 4 and results['s'][0].shape == (64, 64)
+    acc = sets['c'].evaluate(results['c'], metric='accuracy')
+    assert set(acc) == {'accuracy_top-1', 'accuracy_top-5'}
+    ap = sets['d'].evaluate(results['d'], metric='bbox', iou_thrs=[0.5])
+    assert -1 <= ap['bbox_mAP'] <= 1 and ap['bbox_mAP_75'] == -1.0
+    seg = sets['s'].evaluate(results['s'], metric=['mFscore', 'mIoU'])
+    assert 0 <= seg['mIoU'] <= 1 and 'mFscore' in seg
