@@ -78,5 +78,11 @@ optimizer = dict(type='AdamW', lr=5e-5, weight_decay=0.0001,
 optimizer_config = dict(grad_clip=dict(max_norm=0.1, norm_type=2))
 lr_config = dict(policy='step', step=[240000, 285000])
 runner = dict(type='IterBasedRunner', max_iters=300000)
-evaluation = dict(interval=15000)
+evaluation = dict(
+    interval=15000,
+    save_best={'resisc.accuracy_top-1': 1, 'dior.bbox_mAP': 100, 'potsdam.mFscore': 100},
+    cls=dict(metric='accuracy'),
+    det=dict(metric='bbox', iou_thrs=[0.5], classwise=True),
+    seg=dict(metric=['mFscore', 'mIoU'], pre_eval=True, classwise=True))
+checkpoint_config = dict(interval=100000)
 custom_imports = dict(imports='models.multi', allow_failed_imports=False)

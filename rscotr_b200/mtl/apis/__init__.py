@@ -1,1 +1,2 @@
 from .train import train_model  # noqa: F401
+from .test import test_model  # noqa: F401

@@ -11,6 +11,7 @@ class _SyntheticLoader:
     def __init__(self, dataset, batch_size, length, seed, pin=True):
         self.dataset, self.batch_size, self.length, self.seed, self.pin = dataset, batch_size, length, seed, pin
         self._cache = None
+        dataset._loader = self
 
     def __len__(self):
         return self.length
@@ -20,13 +21,14 @@ class _SyntheticLoader:
         n_distinct = min(self.length, self.dataset.distinct)
         return [self.dataset.make_batch(self.batch_size, g, self.pin) for _ in range(n_distinct)]
 
-    def __iter__(self):
+    def served(self):
+        """the batches of one pass, in serving order (ground truth for dataset.evaluate())."""
         if self._cache is None:
             self._cache = self._make()
-        self.dataset._served = []                      # ground truth in serving order, for dataset.evaluate()
-        for i in range(self.length):
-            b = self._cache[i % len(self._cache)]
-            self.dataset._served.append(b)
+        return [self._cache[i % len(self._cache)] for i in range(self.length)]
+
+    def __iter__(self):
+        for b in self.served():
             yield dict(b)
 
 
@@ -45,7 +47,7 @@ class SyntheticDataset:
     def evaluate(self, results, metric=None, **kwargs):
         """same metric code as the real datasets (mtl/data/metrics.py), against the batches the loader served."""
         from . import metrics as M
-        served = getattr(self, '_served', [])
+        served = self._loader.served()
         if self.task == 'cls':
             gt = torch.cat([b['gt_label'] for b in served]).numpy()
             return M.evaluate_cls(results, gt, metric or 'accuracy', kwargs.get('metric_options'))

@@ -177,3 +177,25 @@ def test_runner_checkpoint_hook_and_resume(tmp_path):
     IterBasedRunner(eng3, max_iters=4, log_interval=0).load_checkpoint(str(tmp_path / 'iter_4.pth'))
     assert eng3.iter == 0
     assert torch.equal(eng3.model.cls_head.fc.weight, eng.model.cls_head.fc.weight)
+
+
+@pytest.mark.timeout(600)
+def test_test_model_api_from_checkpoint(tmp_path):
+    """mtl.apis.test_model (the body of the reference's tools/test.py): checkpoint -> per-dataset metrics."""
+    from rscotr_b200.mtl.apis import test_model
+    eng = _engine()
+    path = C.save_checkpoint(eng, str(tmp_path / 'iter_0.pth'))
+    cfg = small_cfg()
+    cfg.synthetic = dict(img_size=(64, 64), det=dict(num_boxes=2), length=dict(resisc=1, dior=2, potsdam=1))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for v in cfg.data.values():
+        v['config'] = os.path.join(root, v['config'])
+    with cpu_ops():
+        metrics, outputs = test_model(cfg, path, tasks=('cls', 'seg'), split='val', device='cpu', synthetic=cfg.synthetic)
+    assert set(metrics) == {'resisc', 'potsdam'} and len(outputs['resisc']) == 16 and len(outputs['potsdam']) == 2
+    assert 'accuracy_top-1' in metrics['resisc'] and 'mFscore' in metrics['potsdam'] and 'mIoU' in metrics['potsdam']
+    # a second run from the stored outputs (tools/test.py --test-outputs) reproduces the metrics without the model
+    with cpu_ops():
+        again, _ = test_model(cfg, path, tasks=('cls', 'seg'), split='val', device='cpu', synthetic=cfg.synthetic,
+                              test_outputs=outputs)
+    assert again['resisc'] == metrics['resisc']
