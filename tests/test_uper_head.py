@@ -180,5 +180,5 @@ def test_gpu_encoder_decoder_graph_replay_matches_eager():
     assert l0[-1] < l0[0]                                      # it learns the fixed batch
     for a, b in zip(l0, l1):
         assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (l0, l1)
-    for n in p0:
-        assert _rel(p1[n], p0[n]) < 1e-3, n
+    for n in p0:      # (absolute floor: biases in front of a norm / the k-bias of softmax attention stay ~1e-13 noise)
+        assert float((p1[n] - p0[n]).norm()) <= 1e-3 * float(p0[n].norm()) + 1e-8, n
