@@ -181,3 +181,95 @@ class SlvlClsHead(nn.Module):
         if post_process:
             return list(pred.detach().cpu().numpy())
         return pred
+
+
+@MODELS.register_module()
+class MlvlClsPixelDecoder(nn.Module):
+    """reference models/multi/cls_head/pixel_decoder.py:14-116: the neck levels go through the SHARED encoder
+    (low -> high resolution, sine + level encodings, normalised grid reference points) and come back as maps."""
+
+    def __init__(self, num_encoder_levels=4, strides=[4, 8, 16, 32], feat_channels=256, num_outs=4,
+                 positional_encoding=dict(type='SinePositionalEncoding', num_feats=128, normalize=True), init_cfg=None):
+        super().__init__()
+        from .bricks import build_positional_encoding
+        self.strides, self.num_encoder_levels, self.num_outs = strides, num_encoder_levels, num_outs
+        self.postional_encoding = build_positional_encoding(positional_encoding)
+        self.level_encoding = nn.Embedding(num_encoder_levels, feat_channels)
+
+    def init_weights(self):
+        nn.init.normal_(self.level_encoding.weight, mean=0, std=1)
+
+    def forward(self, encoder, neck_feats):
+        from .seg_head import encode_neck_levels
+        return encode_neck_levels(self, encoder, neck_feats, neck_feats[0].shape[0], len(neck_feats))
+
+
+@MODELS.register_module()
+class MlvlClsHead(SlvlClsHead):
+    """reference models/multi/cls_head/mlvl_cls_head.py:13-126: classification token from the shared encoder's
+    multi-level memory, by one of eight pooling `scheme`s (1/2: GAP of level 0/1; 3: mean over all tokens;
+    4: mean of the per-level GAPs; 5/6: learned token weights on level 0/1; 7: learned weights over all tokens;
+    8: learned weights over the per-level GAPs).  Levels are ordered low -> high resolution."""
+    _FEAT_LEN = {5: (4,), 6: (7,), 7: (4, 7, 14, 28)}
+
+    def __init__(self, *args, pixel_decoder=None, scheme=5, **kwargs):
+        init_cfg = kwargs.pop('init_cfg', None)
+        super().__init__(*args, **kwargs)
+        assert scheme in range(1, 9), 'scheme must be 1..8 (0 is the reference\'s self-test mode)'
+        self.scheme = scheme
+        self.pixel_decoder = pixel_decoder if isinstance(pixel_decoder, nn.Module) else MODELS.build(pixel_decoder)
+        if scheme in (5, 6, 7):
+            n = sum(x ** 2 for x in self._FEAT_LEN[scheme])
+            self.out_proj = nn.Linear(n, 1)
+        elif scheme == 8:
+            n = self.pixel_decoder.num_encoder_levels
+            self.out_proj = nn.Linear(n, 1)
+        if hasattr(self, 'out_proj'):
+            nn.init.constant_(self.out_proj.weight, 1.0 / n)        # starts as the plain mean
+            nn.init.constant_(self.out_proj.bias, 0)
+        self.pixel_decoder.init_weights()
+        # mmcv BaseModule.init_weights applies the head's init_cfg to EVERY matching layer below it, so with the
+        # reference's `TruncNormal(layer='Linear')` entry (cfg MTL_swin-t...:66-69) fc and out_proj are both re-drawn
+        for c in ([init_cfg] if isinstance(init_cfg, dict) else (init_cfg or [])):
+            layers = c.get('layer')
+            layers = [layers] if isinstance(layers, str) else list(layers or [])
+            for m in self.modules():
+                if type(m).__name__ not in layers:
+                    continue
+                if c['type'] == 'TruncNormal':
+                    nn.init.trunc_normal_(m.weight, mean=c.get('mean', 0.), std=c.get('std', 1.), a=c.get('a', -2.), b=c.get('b', 2.))
+                elif c['type'] == 'Normal':
+                    nn.init.normal_(m.weight, c.get('mean', 0.), c.get('std', 1.))
+                elif c['type'] == 'Constant':
+                    nn.init.constant_(m.weight, c['val'])
+                else:
+                    raise KeyError('init type %s' % c['type'])
+                if getattr(m, 'bias', None) is not None:
+                    nn.init.constant_(m.bias, c.get('bias', 0.))
+
+    def pre_logits(self, mlvl_feats):
+        s = self.scheme
+        if s in (1, 2):
+            return self.avg_pool(mlvl_feats[s - 1])
+        if s in (5, 6):
+            return self.out_proj(mlvl_feats[s - 5].flatten(2)).squeeze(-1)
+        if s in (3, 7):
+            seq = torch.cat([f.flatten(2) for f in mlvl_feats], dim=2)
+            return seq.mean(dim=2) if s == 3 else self.out_proj(seq).squeeze(-1)
+        tokens = self.avg_pool(tuple(mlvl_feats))
+        if s == 4:
+            return sum(tokens) / len(tokens)
+        return self.out_proj(torch.stack(tokens, -1)).squeeze(-1)
+
+    def forward_encoder(self, encoder, neck_feature, backbone_feature):
+        return self.pixel_decoder(encoder, neck_feature)
+
+    def forward_train(self, neck_feature, backbone_feature, gt_label, shared_encoder, **kwargs):
+        x = self.forward_encoder(shared_encoder, neck_feature, backbone_feature)
+        return self.loss(self.fc(self.pre_logits(x)), gt_label)
+
+    def simple_test(self, neck_feature, backbone_feature, shared_encoder, softmax=True, post_process=True):
+        x = self.forward_encoder(shared_encoder, neck_feature, backbone_feature)
+        cls_score = self.fc(self.pre_logits(x))
+        pred = F.softmax(cls_score.float(), dim=1) if softmax else cls_score
+        return list(pred.detach().cpu().numpy()) if post_process else pred

@@ -89,6 +89,12 @@ class MTL(nn.Module):
         self.CLASSES = None
 
     def init_weights(self):
+        # (every sub-module initialises itself on construction; what mmcv's recursive init_weights adds on top is
+        # the backbone's `Pretrained` checkpoint)
+        bb = self.backbone
+        if getattr(bb, 'pretrained', None) or (isinstance(getattr(bb, 'init_cfg', None), dict)
+                                               and bb.init_cfg.get('type') == 'Pretrained'):
+            bb.init_weights()
         for layer in self.shared_encoder.layers:
             for attn in layer.attentions:
                 if isinstance(attn, MultiScaleDeformableAttention):

@@ -27,6 +27,59 @@ def caffe2_xavier_init(conv, bias=0):
         nn.init.constant_(conv.bias, bias)
 
 
+def encode_neck_levels(self, encoder, neck_feats, batch_size, num_input_levels):
+    """The part the seg and the multi-level cls pixel decoders share (seg_head/pixel_decoder.py:80-160,
+    cls_head/pixel_decoder.py:40-116): neck levels from low to high resolution -> flattened tokens + sine / level
+    positional encodings + normalised reference points -> shared encoder -> memory split back into (B,C,h,w) maps."""
+    dev = neck_feats[0].device
+    levels = [num_input_levels - i - 1 for i in range(self.num_encoder_levels)]
+    shapes_py = [tuple(neck_feats[l].shape[-2:]) for l in levels]
+
+    def make():
+        """shape-only constants: all-false padding masks, sine encodings, reference points, level index"""
+        padding_mask_list, pos_list, reference_points_list = [], [], []
+        for i, level_idx in enumerate(levels):
+            h, w = shapes_py[i]
+            padding_mask_resized = torch.zeros((batch_size, h, w), dtype=torch.bool, device=dev)
+            pos_list.append(self.postional_encoding(padding_mask_resized).flatten(2).permute(2, 0, 1))
+            # MlvlPointGenerator.single_level_grid_priors / (w*stride, h*stride)
+            sx = (torch.arange(w, device=dev, dtype=torch.float32) + 0.5) * self.strides[level_idx]
+            sy = (torch.arange(h, device=dev, dtype=torch.float32) + 0.5) * self.strides[level_idx]
+            yy, xx = torch.meshgrid(sy, sx, indexing='ij')
+            reference_points = torch.stack([xx.reshape(-1), yy.reshape(-1)], -1)
+            reference_points_list.append(reference_points / const_tensor(
+                [[float(w * self.strides[level_idx]), float(h * self.strides[level_idx])]], torch.float32, dev))
+            padding_mask_list.append(padding_mask_resized.flatten(1))
+        spatial_shapes = const_tensor(shapes_py, torch.long, dev)
+        reference_points = torch.cat(reference_points_list, dim=0)
+        reference_points = reference_points[None, :, None].repeat(batch_size, 1, self.num_encoder_levels, 1)
+        return dict(padding_masks=torch.cat(padding_mask_list, dim=1), pos=[p.contiguous() for p in pos_list],
+                    spatial_shapes=spatial_shapes,
+                    level_start_index=torch.cat((spatial_shapes.new_zeros((1,)),
+                                                 spatial_shapes.prod(1).cumsum(0)[:-1])),
+                    reference_points=reference_points,
+                    valid_radios=reference_points.new_ones((batch_size, self.num_encoder_levels, 2)))
+    if not hasattr(self, '_geom'):
+        self._geom = GeomCache()
+    geo = self._geom.get((batch_size, tuple(shapes_py), str(dev)), make)
+    encoder_inputs = torch.cat([neck_feats[l].flatten(2).permute(2, 0, 1) for l in levels], dim=0)
+    level_positional_encodings = torch.cat([p + self.level_encoding.weight[i].view(1, 1, -1)
+                                            for i, p in enumerate(geo['pos'])], dim=0)
+    padding_masks, spatial_shapes = geo['padding_masks'], geo['spatial_shapes']
+    level_start_index, reference_points, valid_radios = geo['level_start_index'], geo['reference_points'], \
+        geo['valid_radios']
+    memory = encoder(query=encoder_inputs, key=None, value=None, query_pos=level_positional_encodings,
+                     key_pos=None, attn_masks=None, key_padding_mask=None,
+                     query_key_padding_mask=None,      # (the reference passes an all-False mask: same result)
+                     spatial_shapes=spatial_shapes, reference_points=reference_points,
+                     level_start_index=level_start_index, valid_radios=valid_radios)
+    memory = memory.permute(1, 2, 0)
+    num_query_per_level = [h * w for h, w in shapes_py]
+    outs = torch.split(memory, num_query_per_level, dim=-1)
+    outs = [x.reshape(batch_size, -1, shapes_py[i][0], shapes_py[i][1]) for i, x in enumerate(outs)]
+    return outs
+
+
 @MODELS.register_module()
 class MlvlSegPixelDecoder(nn.Module):
     def __init__(self, num_encoder_levels=4, in_channels=[256, 512, 1024, 2048], strides=[4, 8, 16, 32],
@@ -59,52 +112,7 @@ class MlvlSegPixelDecoder(nn.Module):
 
     def forward(self, encoder, neck_feats, backbone_feats):
         batch_size = backbone_feats[0].shape[0]
-        dev = neck_feats[0].device
-        levels = [self.num_input_levels - i - 1 for i in range(self.num_encoder_levels)]
-        shapes_py = [tuple(neck_feats[l].shape[-2:]) for l in levels]
-
-        def make():
-            """shape-only constants: all-false padding masks, sine encodings, reference points, level index"""
-            padding_mask_list, pos_list, reference_points_list = [], [], []
-            for i, level_idx in enumerate(levels):
-                h, w = shapes_py[i]
-                padding_mask_resized = torch.zeros((batch_size, h, w), dtype=torch.bool, device=dev)
-                pos_list.append(self.postional_encoding(padding_mask_resized).flatten(2).permute(2, 0, 1))
-                # MlvlPointGenerator.single_level_grid_priors / (w*stride, h*stride)
-                sx = (torch.arange(w, device=dev, dtype=torch.float32) + 0.5) * self.strides[level_idx]
-                sy = (torch.arange(h, device=dev, dtype=torch.float32) + 0.5) * self.strides[level_idx]
-                yy, xx = torch.meshgrid(sy, sx, indexing='ij')
-                reference_points = torch.stack([xx.reshape(-1), yy.reshape(-1)], -1)
-                reference_points_list.append(reference_points / const_tensor(
-                    [[float(w * self.strides[level_idx]), float(h * self.strides[level_idx])]], torch.float32, dev))
-                padding_mask_list.append(padding_mask_resized.flatten(1))
-            spatial_shapes = const_tensor(shapes_py, torch.long, dev)
-            reference_points = torch.cat(reference_points_list, dim=0)
-            reference_points = reference_points[None, :, None].repeat(batch_size, 1, self.num_encoder_levels, 1)
-            return dict(padding_masks=torch.cat(padding_mask_list, dim=1), pos=[p.contiguous() for p in pos_list],
-                        spatial_shapes=spatial_shapes,
-                        level_start_index=torch.cat((spatial_shapes.new_zeros((1,)),
-                                                     spatial_shapes.prod(1).cumsum(0)[:-1])),
-                        reference_points=reference_points,
-                        valid_radios=reference_points.new_ones((batch_size, self.num_encoder_levels, 2)))
-        if not hasattr(self, '_geom'):
-            self._geom = GeomCache()
-        geo = self._geom.get((batch_size, tuple(shapes_py), str(dev)), make)
-        encoder_inputs = torch.cat([neck_feats[l].flatten(2).permute(2, 0, 1) for l in levels], dim=0)
-        level_positional_encodings = torch.cat([p + self.level_encoding.weight[i].view(1, 1, -1)
-                                                for i, p in enumerate(geo['pos'])], dim=0)
-        padding_masks, spatial_shapes = geo['padding_masks'], geo['spatial_shapes']
-        level_start_index, reference_points, valid_radios = geo['level_start_index'], geo['reference_points'], \
-            geo['valid_radios']
-        memory = encoder(query=encoder_inputs, key=None, value=None, query_pos=level_positional_encodings,
-                         key_pos=None, attn_masks=None, key_padding_mask=None,
-                         query_key_padding_mask=None,      # (the reference passes an all-False mask: same result)
-                         spatial_shapes=spatial_shapes, reference_points=reference_points,
-                         level_start_index=level_start_index, valid_radios=valid_radios)
-        memory = memory.permute(1, 2, 0)
-        num_query_per_level = [h * w for h, w in shapes_py]
-        outs = torch.split(memory, num_query_per_level, dim=-1)
-        outs = [x.reshape(batch_size, -1, shapes_py[i][0], shapes_py[i][1]) for i, x in enumerate(outs)]
+        outs = encode_neck_levels(self, encoder, neck_feats, batch_size, self.num_input_levels)
         for i in range(self.num_input_levels - self.num_encoder_levels - 1, -1, -1):
             x = backbone_feats[i]
             cur_feat = self.lateral_convs[i](x)

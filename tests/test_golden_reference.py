@@ -376,6 +376,40 @@ def test_seg_pixel_decoder_control_flow_matches_reference_run(device):
     assert torch.equal(enc.seen['level_start_index'], c['encoder_saw']['level_start_index'])
 
 
+@pytest.mark.parametrize('device', DEVICES)
+def test_cls_mlvl_head_matches_reference_run(device):
+    """8f rank 4: MlvlClsPixelDecoder.forward and MlvlClsHead.pre_logits_1..8 of the reference, run in place
+    (tools/make_golden.py::golden_cls_mlvl), against this repo's classes with the SAME toy parts."""
+    import types
+    from rscotr_b200.models.cls_head import GlobalAveragePooling, MlvlClsHead, MlvlClsPixelDecoder
+    mg = _tools()
+    t = _to(mg.toy_pixel_decoder_parts(), device)
+    c = _to(torch.load(os.path.join(GOLDEN, 'reference_cls_mlvl.pt'), weights_only=False), device)
+    enc = mg.ToyEncoder()
+    fake = types.SimpleNamespace(num_encoder_levels=4, strides=t['strides'], num_outs=4,
+                                 postional_encoding=lambda m: t['pos'][tuple(m.shape[-2:])],
+                                 level_encoding=torch.nn.Embedding.from_pretrained(t['level_encoding'].clone()).to(device))
+    with _ctx(device), torch.no_grad():
+        outs = MlvlClsPixelDecoder.forward(fake, enc, t['neck'])
+    assert len(outs) == len(c['outs']) and all(torch.allclose(a, b, rtol=1e-5, atol=1e-6) for a, b in zip(outs, c['outs']))
+    for k in ('query', 'query_pos', 'reference_points'):
+        assert torch.allclose(enc.seen[k], c['encoder_saw'][k], rtol=1e-6, atol=1e-6), k
+    assert torch.equal(enc.seen['spatial_shapes'], c['encoder_saw']['spatial_shapes'])
+    assert torch.equal(enc.seen['level_start_index'], c['encoder_saw']['level_start_index'])
+    m = _to(mg.toy_mlvl_cls_parts(), device)
+    for k in range(1, 9):
+        self_ = types.SimpleNamespace(scheme=k, avg_pool=GlobalAveragePooling())
+        if k in m['proj']:
+            w, b = m['proj'][k]
+            lin = torch.nn.Linear(w.shape[1], 1).to(device)
+            with torch.no_grad():
+                lin.weight.copy_(w), lin.bias.copy_(b)
+            self_.out_proj = lin
+        with _ctx(device), torch.no_grad():
+            tok = MlvlClsHead.pre_logits(self_, m['feats'])
+        assert tok.shape == c['tokens'][k].shape and torch.allclose(tok, c['tokens'][k], rtol=1e-5, atol=1e-5), k
+
+
 def _dino_head():
     import rscotr_b200.models  # noqa: F401
     from rscotr_b200.config import Config

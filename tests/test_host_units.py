@@ -120,3 +120,49 @@ def test_eval_hook_on_synthetic_loaders():
     assert -1 <= ap['bbox_mAP'] <= 1 and ap['bbox_mAP_75'] == -1.0
     seg = sets['s'].evaluate(results['s'], metric=['mFscore', 'mIoU'])
     assert 0 <= seg['mIoU'] <= 1 and 'mFscore' in seg
+
+
+def test_mlvl_cls_head_in_the_cotraining_model():
+    """the reference's second co-training config (MTL_swin-t-p4-w7_1x1_resisc&dior&potsdam.py:54-69): cls goes through
+    neck + SHARED encoder + MlvlClsHead; gradients reach all of them and the engine's cls range grows accordingly."""
+    import pytest
+    from rscotr_b200.config import MODELS
+    from rscotr_b200.mtl.data import build_datasets
+    from rscotr_b200.mtl.engine import StepEngine
+    from tests.cpu_ops_shim import cpu_ops
+    from tests.test_host_model import small_cfg
+    for scheme in (2, 8):
+        cfg = small_cfg()
+        cfg.model.cls_head = dict(
+            type='MlvlClsHead', scheme=scheme, num_classes=45, in_channels=256,
+            pixel_decoder=dict(type='MlvlClsPixelDecoder', num_encoder_levels=4, num_outs=4),
+            loss=dict(type='LabelSmoothLoss', label_smooth_val=0.1, mode='original'), cal_acc=False,
+            init_cfg=[dict(type='TruncNormal', layer='Linear', std=0.02, bias=0.), dict(type='Constant', layer='LayerNorm', val=1., bias=0.)])
+        torch.manual_seed(0)
+        model = MODELS.build(cfg.model)
+        model.init_weights()
+        model.train()
+        head = model.cls_head
+        assert abs(float(head.fc.weight.detach().std()) - 0.02) < 0.002      # the config's TruncNormal(std=.02), not LinearClsHead's .01
+        if scheme == 8:
+            assert head.out_proj.weight.shape == (1, 4)
+        eng = StepEngine(model, dict(type='AdamW', lr=1e-3, weight_decay=1e-4), device='cpu', compute_dtype=torch.float32,
+                         use_graphs=False)
+        ds = build_datasets({'x': dict(task='cls')}, synthetic=dict(img_size=(64, 64)))['x']
+        batch = ds.make_batch(2, torch.Generator().manual_seed(1), pin=False)
+        batch.update(task='cls', dataset_name='x')
+        with cpu_ops():
+            out = model.train_step(dict(batch), None)
+            out['loss'].backward()
+            eng._collect_grads()
+        def gnorm(p):
+            return float(eng.grad_view(p).norm())
+        # (level_encoding only feeds the offset / attention-weight projections, which start at zero weight: no grad yet)
+        assert gnorm(model.neck.convs[0].conv.weight) > 0
+        assert gnorm(model.shared_encoder.layers[0].ffns[0].layers[1].weight) > 0 and gnorm(head.fc.weight) > 0
+        assert gnorm(model.bbox_head.fc_cls.weight if hasattr(model.bbox_head, 'fc_cls') else next(model.bbox_head.parameters())) == 0
+        assert out['log_vars']['cls.x.loss'] == pytest.approx(float(out['loss']))
+        with cpu_ops():
+            model.eval()
+            pred = model(task='cls', img=[batch['img']], img_metas=[batch['img_metas']], return_loss=False)
+        assert len(pred) == 2 and pred[0].shape == (45,) and abs(float(pred[0].sum()) - 1) < 1e-4

@@ -743,6 +743,51 @@ def golden_seg_pixel_decoder():
     return tuple(mf.shape), [tuple(f.shape) for f in feats]
 
 
+def toy_mlvl_cls_parts(C=8, B=3):
+    g = torch.Generator().manual_seed(77)
+    sizes = (4, 7, 14, 28)                                     # low -> high resolution, what the cls pixel decoder returns
+    feats = [torch.randn(B, C, x, x, generator=g) for x in sizes]
+    n = {5: 16, 6: 49, 7: sum(x * x for x in sizes), 8: 4}
+    proj = {k: (torch.randn(1, v, generator=g) * 0.2, torch.randn(1, generator=g) * 0.1) for k, v in n.items()}
+    return dict(C=C, B=B, feats=feats, proj=proj)
+
+
+def golden_cls_mlvl():
+    """models/multi/cls_head/pixel_decoder.py::MlvlClsPixelDecoder.forward and mlvl_cls_head.py::MlvlClsHead.pre_logits_1..8
+    (reference, run in place, unbound on a stand-in `self`): what the shared encoder is called with for the cls task and the
+    eight pooling schemes.  mmcls GlobalAveragePooling (third-party) is restated as mean over (H, W)."""
+    _stub_packages(['mmcv.cnn', 'mmcv.cnn.bricks.transformer', 'mmcv.runner', 'mmdet.core.anchor', 'mmcls.models.builder',
+                    'mmcls.models.heads.linear_head', 'mmcls.models.necks.gap'])
+    dec = load('models/multi/cls_head/pixel_decoder.py', 'ref_cls_head.pixel_decoder')
+    head = load('models/multi/cls_head/mlvl_cls_head.py', 'ref_cls_head.mlvl_cls_head')
+    t = toy_pixel_decoder_parts()
+    enc = ToyEncoder()
+    fake = types.SimpleNamespace(num_encoder_levels=4, strides=t['strides'], num_outs=4,
+                                 postional_encoding=lambda m: t['pos'][tuple(m.shape[-2:])],
+                                 level_encoding=torch.nn.Embedding.from_pretrained(t['level_encoding'].clone()),
+                                 point_generator=ToyPointGenerator(t['strides']))
+    with torch.no_grad():
+        outs = dec.MlvlClsPixelDecoder.forward(fake, enc, t['neck'])
+    m = toy_mlvl_cls_parts()
+
+    def gap(x):
+        return tuple(f.mean(dim=(2, 3)) for f in x) if isinstance(x, tuple) else x.mean(dim=(2, 3))
+    tokens = {}
+    for k in range(1, 9):
+        self_ = types.SimpleNamespace(avg_pool=gap)
+        if k in m['proj']:
+            w, b = m['proj'][k]
+            lin = torch.nn.Linear(w.shape[1], 1)
+            with torch.no_grad():
+                lin.weight.copy_(w), lin.bias.copy_(b)
+            self_.out_proj = lin
+        with torch.no_grad():
+            tokens[k] = getattr(head.MlvlClsHead, 'pre_logits_%d' % k)(self_, m['feats'])
+    torch.save(dict(source='models/multi/cls_head/{pixel_decoder,mlvl_cls_head}.py (reference, run in place, toy parts)',
+                    outs=list(outs), encoder_saw=enc.seen, tokens=tokens), os.path.join(OUT, 'reference_cls_mlvl.pt'))
+    return [tuple(o.shape) for o in outs], {k: tuple(v.shape) for k, v in tokens.items()}
+
+
 # ----------------------------------------------------------------------------- MultiDataLoader
 class _ToyDataset(torch.utils.data.Dataset):
     """n samples {'idx': i}; `task` is what MultiDataLoader tags batches with"""
@@ -802,6 +847,7 @@ if __name__ == '__main__':
     print('seg forward_head:', golden_seg_forward_head())
     print('seg forward:', golden_seg_forward())
     print('seg pixel decoder:', golden_seg_pixel_decoder())
+    print('cls mlvl:', golden_cls_mlvl())
     d = golden_dn_targets()
     print('dn targets:', [(c['sizes'], c['num_total_pos'], c['num_total_neg']) for c in d])
     e0 = golden_sineembed()
