@@ -1,0 +1,13 @@
+#!/bin/bash
+# One-shot hardware probes (B200): builds tools/tc_probe_m64.cu and runs every mode in its own process
+# (a faulting variant must not poison the others).  Output: gpurun_out/probe_m64_<mode>.txt
+#   gpurun --timeout 300 -- 'bash tools/run_probes.sh'
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o /tmp/tc_probe_m64 tools/tc_probe_m64.cu || exit 1
+for mode in m64 ld16x256 ld16x128 ld16x64 m64_lane16 m64_lane64 m128_lane64; do
+  timeout 30 /tmp/tc_probe_m64 $mode > gpurun_out/probe_m64_$mode.txt 2>&1
+  echo "$mode: exit $? ($(wc -l < gpurun_out/probe_m64_$mode.txt) lines)"
+done
+head -40 gpurun_out/probe_m64_m64.txt
