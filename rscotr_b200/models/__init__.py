@@ -2,3 +2,4 @@
 (the reference does it with custom_imports=dict(imports='models.multi'))."""
 from . import bricks, swin, cls_head, det_head, seg_head, mtl, uper_head  # noqa: F401
 from .mtl import MTL  # noqa: F401
+ImageClassifier = cls_head._make_image_classifier()

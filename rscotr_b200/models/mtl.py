@@ -345,3 +345,36 @@ class _LazyLogVars(OrderedDict):
     def rebind(self):
         """a fresh, un-materialised view of the same packed tensor (CUDA-graph replays)."""
         return _LazyLogVars(self._keys, self._packed, self._weight)
+
+
+class SingleTaskModel(nn.Module):
+    """step-engine interface (train_step / train_step_begin / _host / _finish, same contract as MTL) for the
+    single-task models of the reference's configs/cls and the UPerNet configuration: `forward(return_loss=True)`
+    returns a loss dict, terms whose key contains 'loss' are summed, everything is logged."""
+    default_task = None
+
+    def _parse_losses(self, losses):
+        keys = list(losses.keys())
+        vals = torch.stack([losses[k].mean().float() for k in keys])
+        mask = const_tensor([1.0 if 'loss' in k else 0.0 for k in keys], torch.float32, vals.device)
+        loss = (vals * mask).sum()
+        packed = torch.cat([vals.detach(), loss.detach().view(1)])
+        return loss, keys + ['loss'], packed
+
+    def train_step(self, data, optimizer=None):
+        data = dict(data)
+        task, name = data.pop('task', self.default_task), data.pop('dataset_name', None)
+        losses = self(**data)
+        loss, keys, packed = self._parse_losses(losses)
+        packed = MTL._reduce_log_vars(keys, packed)
+        prefix = '%s.%s.' % (task, name) if name is not None else ''
+        return dict(loss=loss, log_vars=_LazyLogVars([prefix + k for k in keys], packed, 1), num_samples=len(data['img_metas']))
+
+    def train_step_begin(self, data):
+        return dict(data=data, pending=None, outputs=self.train_step(data))
+
+    def train_step_host(self, ctx):
+        pass
+
+    def train_step_finish(self, ctx):
+        return ctx['outputs']

@@ -14,8 +14,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS, build_from_cfg
-from .bricks import const_tensor
-from .mtl import _LazyLogVars, add_prefix
+from .mtl import SingleTaskModel, add_prefix
 from .seg_head import resize
 
 
@@ -137,9 +136,10 @@ class FCNHead(_DecodeHead):
 
 
 @MODELS.register_module()
-class EncoderDecoder(nn.Module):
+class EncoderDecoder(SingleTaskModel):
     """mmseg EncoderDecoder(backbone, decode_head, auxiliary_head): single-task segmentation with the step engine's
     model interface (train_step / train_step_begin / _host / _finish, forward(return_loss=...))."""
+    default_task = 'seg'
 
     def __init__(self, backbone, decode_head, neck=None, auxiliary_head=None, train_cfg=None, test_cfg=None, pretrained=None,
                  init_cfg=None):
@@ -195,31 +195,3 @@ class EncoderDecoder(nn.Module):
         if isinstance(img, list):
             img, img_metas = img[0], img_metas[0]
         return self.simple_test(normalize_on_device(img, img_metas), img_metas, **kwargs)
-
-    # -- step-engine interface (same contract as MTL) -------------------------------------------------------
-    def _parse_losses(self, losses):
-        keys = list(losses.keys())
-        vals = torch.stack([losses[k].mean().float() for k in keys])
-        mask = const_tensor([1.0 if 'loss' in k else 0.0 for k in keys], torch.float32, vals.device)
-        loss = (vals * mask).sum()
-        packed = torch.cat([vals.detach(), loss.detach().view(1)])
-        return loss, keys + ['loss'], packed
-
-    def train_step(self, data, optimizer=None):
-        data = dict(data)
-        task, name = data.pop('task', 'seg'), data.pop('dataset_name', None)
-        losses = self(**data)
-        loss, keys, packed = self._parse_losses(losses)
-        from .mtl import MTL
-        packed = MTL._reduce_log_vars(keys, packed)
-        prefix = '%s.%s.' % (task, name) if name is not None else ''
-        return dict(loss=loss, log_vars=_LazyLogVars([prefix + k for k in keys], packed, 1), num_samples=len(data['img_metas']))
-
-    def train_step_begin(self, data):
-        return dict(data=data, pending=None, outputs=self.train_step(data))
-
-    def train_step_host(self, ctx):
-        pass
-
-    def train_step_finish(self, ctx):
-        return ctx['outputs']

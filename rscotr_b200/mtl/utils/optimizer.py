@@ -10,10 +10,25 @@ import torch
 
 
 def param_settings(model, optimizer_cfg, paramwise_cfg):
+    """(name, param, lr, weight_decay) per trainable parameter with mmcv's DefaultOptimizerConstructor rules:
+    custom_keys first (longest key that is a substring of the name wins and ends the search), otherwise
+    bias_lr_mult / bias_decay_mult for biases outside norm layers, norm_decay_mult for norm layers,
+    dwconv_decay_mult for depth-wise convolutions."""
     base_lr = optimizer_cfg['lr']
     base_wd = optimizer_cfg.get('weight_decay', None)
-    custom_keys = (paramwise_cfg or {}).get('custom_keys', {})
+    pw = paramwise_cfg or {}
+    custom_keys = pw.get('custom_keys', {})
     sorted_keys = sorted(sorted(custom_keys.keys()), key=len, reverse=True)
+    bias_lr_mult, bias_decay_mult = pw.get('bias_lr_mult', 1.), pw.get('bias_decay_mult', 1.)
+    norm_decay_mult, dwconv_decay_mult = pw.get('norm_decay_mult', 1.), pw.get('dwconv_decay_mult', 1.)
+    norms = (torch.nn.modules.batchnorm._BatchNorm, torch.nn.modules.instancenorm._InstanceNorm, torch.nn.GroupNorm,
+             torch.nn.LayerNorm)
+    kind = {}
+    for module in model.modules():
+        is_norm = isinstance(module, norms)
+        is_dw = isinstance(module, torch.nn.Conv2d) and module.in_channels == module.groups and module.groups > 1
+        for local, p in module.named_parameters(recurse=False):
+            kind[id(p)] = (is_norm, is_dw, local)
     out = []
     for name, p in model.named_parameters():
         if not p.requires_grad:
@@ -25,6 +40,17 @@ def param_settings(model, optimizer_cfg, paramwise_cfg):
                 if base_wd is not None:
                     wd = base_wd * custom_keys[key].get('decay_mult', 1.)
                 break
+        else:
+            is_norm, is_dw, local = kind.get(id(p), (False, False, name.rsplit('.', 1)[-1]))
+            if local == 'bias' and not is_norm:
+                lr = base_lr * bias_lr_mult
+            if base_wd is not None:
+                if is_norm:
+                    wd = base_wd * norm_decay_mult
+                elif is_dw:
+                    wd = base_wd * dwconv_decay_mult
+                elif local == 'bias':
+                    wd = base_wd * bias_decay_mult
         out.append((name, p, lr, wd))
     return out
 

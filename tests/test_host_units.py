@@ -166,3 +166,84 @@ def test_mlvl_cls_head_in_the_cotraining_model():
             model.eval()
             pred = model(task='cls', img=[batch['img']], img_metas=[batch['img_metas']], return_loss=False)
         assert len(pred) == 2 and pred[0].shape == (45,) and abs(float(pred[0].sum()) - 1) < 1e-4
+
+
+def test_detection_only_configuration():
+    """BASELINE configs[3]: the MTL schema with only the det head, Swin-S depths, constant strategy."""
+    import os
+    from rscotr_b200.config import Config, MODELS
+    from rscotr_b200.mtl.data import build_datasets, build_multidataloader, load_data_cfg
+    from rscotr_b200.mtl.engine import StepEngine
+    from tests.cpu_ops_shim import cpu_ops
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = Config.fromfile(os.path.join(root, 'configs/multi/det_only_swin-s_800.py'))
+    assert cfg.model.backbone.depths == [2, 2, 18, 2] and cfg.model.cls_head is None and list(cfg.data.keys()) == ['dior']
+    m = cfg.model
+    m.backbone.depths = [2, 2, 2, 2]                       # (CPU-sized; the graded shape runs on the GPU)
+    m.backbone.drop_path_rate = 0.0
+    m.bbox_head.num_query, m.bbox_head.dn_cfg.group_cfg.num_dn_queries = 30, 10
+    m.shared_encoder.num_layers, m.bbox_head.transformer.decoder.num_layers = 2, 2
+    torch.manual_seed(0)
+    model = MODELS.build(m)
+    model.init_weights()
+    model.train()
+    assert model.cls_head is None and model.seg_head is None
+    for v in cfg.data.values():
+        v['config'] = os.path.join(root, v['config'])
+    load_data_cfg(cfg)
+    cfg.synthetic = dict(img_size=(64, 64), det=dict(num_boxes=2), length=dict(dior=3))
+    loader = build_multidataloader(cfg, False, build_datasets(cfg.data, synthetic=cfg.synthetic))
+    eng = StepEngine(model, dict(cfg.optimizer), grad_clip=dict(cfg.optimizer_config.grad_clip), device='cpu',
+                     compute_dtype=torch.float32, use_graphs=False)
+    it = iter(loader)
+    with cpu_ops():
+        for _ in range(2):
+            b = next(it)
+            assert b['task'] == 'det' and b['dataset_name'] == 'dior' and b['img'].shape[0] == 2
+            out = eng.train_iter(b)
+    assert float(out['loss']) > 0 and any(k.startswith('det.dior.') for k in out['log_vars'])
+
+
+def test_single_task_classifier():
+    """BASELINE configs[0]: Swin-T single-task classification, 2 x 3 x 256 x 256, on CPU: the reference's
+    configs/cls file builds unmodified (when mounted), the repo's own config describes the same model / optimizer,
+    one engine step runs, the param groups follow mmcv's norm / bias / custom-key rules."""
+    import os
+    import pytest
+    from rscotr_b200.config import Config, MODELS
+    from rscotr_b200.mtl.data import build_datasets
+    from rscotr_b200.mtl.engine import StepEngine
+    from rscotr_b200.mtl.utils.optimizer import param_settings
+    from tests.cpu_ops_shim import cpu_ops
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = Config.fromfile(os.path.join(root, 'configs/cls/swin-tiny_resisc.py'))
+    ref_path = '/root/reference/configs/cls/swin-tiny_1xb16_resisc.py'
+    if os.path.exists(ref_path):
+        ref = Config.fromfile(ref_path)
+        strip = lambda d: {k: v for k, v in dict(d).items() if k != 'init_cfg'}
+        assert strip(ref.model.backbone) == strip(cfg.model.backbone) and dict(ref.model.head) == dict(cfg.model.head)
+        assert dict(ref.optimizer) == dict(cfg.optimizer) and dict(ref.optimizer_config) == dict(cfg.optimizer_config)
+        assert MODELS.build(ref.model).__class__.__name__ == 'ImageClassifier'
+    torch.manual_seed(0)
+    model = MODELS.build(cfg.model)
+    model.init_weights()
+    model.train()
+    assert sum(p.numel() for p in model.parameters()) == 27_553_959          # Swin-T + Linear(768, 45)
+    settings = {n: (lr, wd) for n, _, lr, wd in param_settings(model, dict(lr=2e-4, weight_decay=1e-4), cfg.optimizer.paramwise_cfg)}
+    assert settings['backbone.stages.0.blocks.0.norm1.weight'][1] == 0.0                     # norm_decay_mult
+    assert settings['backbone.stages.0.blocks.0.attn.w_msa.qkv.bias'][1] == 0.0              # bias_decay_mult
+    assert settings['backbone.stages.0.blocks.0.attn.w_msa.relative_position_bias_table'][1] == 0.0   # custom key
+    assert settings['backbone.stages.0.blocks.0.attn.w_msa.qkv.weight'] == (2e-4, 1e-4)
+    eng = StepEngine(model, dict(cfg.optimizer), grad_clip=dict(cfg.optimizer_config.grad_clip), device='cpu',
+                     compute_dtype=torch.float32, use_graphs=False)
+    ds = build_datasets({'resisc': dict(task='cls')}, synthetic=dict(cfg.synthetic))['resisc']
+    batch = ds.make_batch(2, torch.Generator().manual_seed(0), pin=False)
+    assert batch['img'].shape == (2, 3, 256, 256)
+    batch.update(task='cls', dataset_name='resisc')
+    with cpu_ops():
+        out = eng.train_iter(batch)
+        logs = dict(out['log_vars'].items())
+        assert set(logs) == {'cls.resisc.loss'} and logs['cls.resisc.loss'] == pytest.approx(float(out['loss'].detach()), rel=1e-5)
+        model.eval()
+        pred = model(img=batch['img'], img_metas=batch['img_metas'], return_loss=False)
+    assert len(pred) == 2 and pred[0].shape == (45,)
