@@ -268,7 +268,20 @@ static bool ln_shape(int C, int &vw, int &ev, int &l) {
 // (~45 instructions per element for value + derivative), so the bf16 path evaluates erf with Abramowitz & Stegun
 // 7.1.26 (|error| < 1.5e-7, four orders below bf16 resolution) sharing ONE exponential between erf and the
 // Gaussian density: u = exp(-x^2/2) = exp(-z^2) with z = x/sqrt(2).  fp32 keeps erff (the 1e-3 parity path).
-enum { ACT_GELU = 0, ACT_RELU = 1 };
+// ACT_GELU_SIG (bf16 only, opt-in): Phi(x) ~ 1 / (1 + 2^(-x (c0 + c1 x^2 + c2 x^4))) -- a tanh-form fit of the normal CDF
+// written as a logistic, |GELU error| < 2.6e-5 (two orders below bf16 resolution), a few percent relative accuracy
+// in the left tail down to x = -5 (the exponential carries it), 9 instructions instead of 17 for the value.  x^2 is clamped at 49 (the
+// quartic fit turns over beyond |x| ~ 8; at the clamp the argument is already +-35, i.e. Phi = 0 or 1 to 1e-11).
+enum { ACT_GELU = 0, ACT_RELU = 1, ACT_GELU_SIG = 2 };
+
+__device__ __forceinline__ float gelu_sig_cdf(float x) {
+  const float x2 = fminf(x * x, 49.0f);
+  float p = fmaf(x2, 0.0010142630552444944f, -0.10677572400272597f);
+  p = fmaf(x2, p, -2.3011213394566354f);                            // -(c0 + c1 x^2 + c2 x^4)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + exp2f(x * p)));
+  return r;
+}
 
 template <bool FAST>
 __device__ __forceinline__ void gelu_parts(float x, float &cdf, float &u) {
@@ -291,6 +304,7 @@ __device__ __forceinline__ void gelu_parts(float x, float &cdf, float &u) {
 template <int ACT, bool FAST>
 __device__ __forceinline__ float act_f(float x) {
   if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == ACT_GELU_SIG && FAST) return x * gelu_sig_cdf(x);
   float cdf, u;
   gelu_parts<FAST>(x, cdf, u);
   return x * cdf;
@@ -298,6 +312,7 @@ __device__ __forceinline__ float act_f(float x) {
 template <int ACT, bool FAST>
 __device__ __forceinline__ float act_grad(float x) {
   if (ACT == ACT_RELU) return x > 0.f ? 1.f : 0.f;
+  if (ACT == ACT_GELU_SIG && FAST) return fmaf(x * 0.3989422804014327f, exp2f(-0.72134752044448170f * x * x), gelu_sig_cdf(x));
   float cdf, u;
   gelu_parts<FAST>(x, cdf, u);
   return fmaf(x * 0.3989422804014327f, u, cdf);
@@ -478,7 +493,8 @@ static int bias_act_check(const char *fn, int64_t rows, int C, int act, int dtyp
   RSC_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 8192, "%s: need rows > 0, C %% 8 == 0, C <= 8192 (rows=%lld, C=%d)", fn,
                 (long long)rows, C);
   RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "%s: bad dtype %d", fn, dtype);
-  RSC_CHECK_ARG(act == few::ACT_GELU || act == few::ACT_RELU, "%s: act must be 0 (gelu) or 1 (relu), got %d", fn, act);
+  RSC_CHECK_ARG(act == few::ACT_GELU || act == few::ACT_RELU || (act == few::ACT_GELU_SIG && dtype == RSC_BF16),
+                "%s: act must be 0 (gelu), 1 (relu) or 2 (gelu, logistic fit, bf16 only), got %d", fn, act);
   return RSC_OK;
 }
 
@@ -493,7 +509,9 @@ extern "C" int rsc_bias_act_fwd(const void *h, const float *bias, void *y, int64
   if (dtype == RSC_F32) {
     if (act == few::ACT_GELU) BAF(float, few::ACT_GELU); else BAF(float, few::ACT_RELU);
   } else {
-    if (act == few::ACT_GELU) BAF(__nv_bfloat16, few::ACT_GELU); else BAF(__nv_bfloat16, few::ACT_RELU);
+    if (act == few::ACT_GELU) BAF(__nv_bfloat16, few::ACT_GELU);
+    else if (act == few::ACT_GELU_SIG) BAF(__nv_bfloat16, few::ACT_GELU_SIG);
+    else BAF(__nv_bfloat16, few::ACT_RELU);
   }
 #undef BAF
   RSC_CHECK_LAUNCH("rsc_bias_act_fwd");
@@ -513,7 +531,9 @@ extern "C" int rsc_bias_act_bwd(const void *h, const float *bias, const void *dy
   if (dtype == RSC_F32) {
     if (act == few::ACT_GELU) BAB(float, few::ACT_GELU); else BAB(float, few::ACT_RELU);
   } else {
-    if (act == few::ACT_GELU) BAB(__nv_bfloat16, few::ACT_GELU); else BAB(__nv_bfloat16, few::ACT_RELU);
+    if (act == few::ACT_GELU) BAB(__nv_bfloat16, few::ACT_GELU);
+    else if (act == few::ACT_GELU_SIG) BAB(__nv_bfloat16, few::ACT_GELU_SIG);
+    else BAB(__nv_bfloat16, few::ACT_RELU);
   }
 #undef BAB
   RSC_CHECK_LAUNCH("rsc_bias_act_bwd");

@@ -573,6 +573,32 @@ def test_bias_gelu_matches_eager(rows, C, dtype):
     assert_rel(gb2.grad, rb2.grad, 1e-5 if dtype == torch.float32 else 2e-2, 'relu dbias')
 
 
+EXPERIMENTAL = pytest.mark.skipif(__import__('os').environ.get('RSC_TEST_EXPERIMENTAL') != '1',
+                                  reason='opt-in kernel variants that are not on the default path (RSC_TEST_EXPERIMENTAL=1)')
+
+
+@EXPERIMENTAL
+@pytest.mark.parametrize('rows,C', [(50, 384), (1000, 768), (7, 8)])
+def test_bias_gelu_logistic_fit_variant(rows, C):
+    """act=2 (RSC_GELU_SIG=1): same tolerances as the default bf16 GELU; fp32 inputs are refused."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows)
+    h, bias, w = (torch.randn(rows, C, generator=g) * 3).bfloat16(), torch.randn(C, generator=g), torch.randn(rows, C, generator=g)
+    h[0, :8] = torch.tensor([-60., -9., -7., -5., 5., 7., 9., 60.]).bfloat16()          # the clamp and the tails
+    rh, rb = h.float().clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    y = F.gelu(rh + rb)
+    (y * w).sum().backward()
+    gh, gb = h.detach().cuda().requires_grad_(True), bias.detach().cuda().requires_grad_(True)
+    gy = ops.bias_act(gh, gb, ops.ACT_GELU_SIG)
+    (gy.float() * w.cuda()).sum().backward()
+    assert torch.isfinite(gy).all()
+    assert_rel(gy, y, 6e-3, 'y')
+    assert_rel(gh.grad, rh.grad, 1e-2, 'dh')
+    assert_rel(gb.grad, rb.grad, 2e-2, 'dbias')
+    with pytest.raises(RuntimeError):
+        ops.bias_act(h.float().cuda(), bias.cuda(), ops.ACT_GELU_SIG)
+
+
 # ---------------------------------------------------------------------------
 # a10/a11: fused softmax + sampling locations + ms_deform_attn
 # ---------------------------------------------------------------------------

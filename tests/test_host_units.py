@@ -247,3 +247,24 @@ def test_single_task_classifier():
         model.eval()
         pred = model(img=batch['img'], img_metas=batch['img_metas'], return_loss=False)
     assert len(pred) == 2 and pred[0].shape == (45,)
+
+
+def test_logistic_gelu_fit_is_within_bf16_resolution():
+    """the opt-in act=2 of rsc_bias_act_* (csrc/fused_ew.cu::gelu_sig_cdf), restated in float32 numpy: error of the value
+    and of the derivative against the exact erf form, behaviour for large |x| (the clamp), relative accuracy of the left tail."""
+    import numpy as np
+    from scipy.special import erf
+    x = np.concatenate([np.linspace(-40, 40, 400001), [-1e4, 1e4]]).astype(np.float32)
+    x2 = np.minimum(x * x, np.float32(49.0))
+    p = x2 * np.float32(0.0010142630552444944) + np.float32(-0.10677572400272597)
+    p = x2 * p + np.float32(-2.3011213394566354)
+    with np.errstate(over='ignore'):
+        cdf = (np.float32(1) / (np.float32(1) + np.exp2(x * p).astype(np.float32))).astype(np.float32)
+    xd = x.astype(np.float64)
+    phi = 0.5 * (1 + erf(xd / np.sqrt(2)))
+    assert np.max(np.abs(x * cdf - xd * phi)) < 3e-5
+    pdf = np.exp(-0.5 * xd * xd) / np.sqrt(2 * np.pi)
+    assert np.max(np.abs((cdf + xd * pdf) - (phi + xd * pdf))) < 6e-5
+    assert cdf[-1] == 1.0 and cdf[-2] == 0.0 and np.all(np.isfinite(cdf))
+    tail = (xd > -5) & (xd < -3)
+    assert np.max(np.abs(cdf[tail] - phi[tail]) / phi[tail]) < 0.05         # a few percent RELATIVE down to x = -5 (Phi = 3e-7)
