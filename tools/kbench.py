@@ -75,6 +75,26 @@ def main():
         xs = torch.randn(1, 100, 100, 100, device=dev, dtype=dt)
         t = timeit(lambda: ops.bilinear_resize(xs, (800, 800)), flush=flush)
         rows.append(dict(k='bilinear_up8', dtype=str(dt), ms=t, gbs=xs.numel() * 65 * es / t / 1e6))
+    # fused element-wise passes at the stage-0 sizes of the cls task (B x 40000 tokens): bias + GELU on the 4C hidden
+    # activations (default erf form and the opt-in logistic fit, act=2), add + bias + LayerNorm on C
+    Bc = int(os.environ.get('KB_BC', 16))
+    for C, hid in ((96, 384), (192, 768)):
+        ntok = Bc * (40000 if C == 96 else 10000)
+        h = torch.randn(ntok, hid, device=dev, dtype=torch.bfloat16)
+        hb = torch.randn(hid, device=dev)
+        dy = torch.randn_like(h)
+        for act, name in ((ops.ACT_GELU, 'gelu_erf'), (ops.ACT_GELU_SIG, 'gelu_logistic')):
+            t = timeit(lambda: ops.bias_act(h, hb, act), flush=flush)
+            rows.append(dict(k='bias_act_fwd', variant=name, C=hid, ms=t, gbs=2 * h.numel() * 2 / t / 1e6))
+            h2, b2 = h.clone().requires_grad_(True), hb.clone().requires_grad_(True)
+            y = ops.bias_act(h2, b2, act)
+            tb = timeit(lambda: torch.autograd.grad(y, (h2, b2), dy, retain_graph=True), flush=flush)
+            rows.append(dict(k='bias_act_bwd', variant=name, C=hid, ms=tb, gbs=3 * h.numel() * 2 / tb / 1e6))
+        idn = torch.randn(Bc, ntok // Bc, C, device=dev, dtype=torch.bfloat16)
+        xx = torch.randn_like(idn)
+        gam, bet, bia = torch.ones(C, device=dev), torch.zeros(C, device=dev), torch.randn(C, device=dev)
+        t = timeit(lambda: ops.add_ln(idn, xx, bia, None, gam, bet, 1e-5), flush=flush)
+        rows.append(dict(k='add_ln_fwd', C=C, ms=t, gbs=4 * idn.numel() * 2 / t / 1e6))
     for r in rows:
         print(json.dumps(r))
     os.makedirs('gpurun_out', exist_ok=True)
