@@ -6,12 +6,14 @@ import torch
 import torch.distributed as dist
 
 from ..data import build_datasets, build_dataloaders, build_multidataloader
+from ..data.multi_eval_dataset import MultiEvalDatasets
+from ..data.synthetic import SyntheticDataset
 from ..engine import StepEngine
 from ..runner import CheckpointHook, IterBasedRunner, MultiDatasetsEvalHook
 from ..utils.checkpoint import find_latest_checkpoint
 
 
-def train_model(model, datasets, cfg, distributed=False, validate=False, timestamp=None, meta=None):
+def train_model(model, datasets, cfg, distributed=False, validate=False, timestamp=None, meta=None, _skip_eval_tasks=()):
     logger = logging.getLogger('rscotr_b200')
     data_loader = [build_multidataloader(cfg, distributed, datasets)]
     if distributed and not dist.is_initialized():
@@ -32,7 +34,9 @@ def train_model(model, datasets, cfg, distributed=False, validate=False, timesta
         runner.register_hook(CheckpointHook(**ck), priority='NORMAL')
     if validate:
         val_dataset = build_datasets(cfg.data, split='val', synthetic=cfg.get('synthetic'))
+        val_dataset = {name: (ds if isinstance(ds, SyntheticDataset) else MultiEvalDatasets(ds)) for name, ds in val_dataset.items()}
         val_dataloader = build_dataloaders(cfg, distributed, val_dataset, train=False)
+        val_dataloader = {n: l for n, l in val_dataloader.items() if l.dataset.task not in _skip_eval_tasks}
         eval_cfg = dict(cfg.get('evaluation', {}))
         eval_cfg['by_epoch'] = cfg.runner['type'] != 'IterBasedRunner'
         runner.register_hook(MultiDatasetsEvalHook(val_dataloader, **eval_cfg), priority='LOW')
@@ -45,3 +49,8 @@ def train_model(model, datasets, cfg, distributed=False, validate=False, timesta
         runner.load_checkpoint(cfg.load_from)
     runner.run(data_loader, cfg.get('workflow', [('train', 1)]))
     return runner
+
+
+def train_model_without_det_eval(model, datasets, cfg, distributed=False, validate=False, timestamp=None, meta=None):
+    """reference mtl/apis/train.py:123-222: train_model, with the detection datasets left out of the validation loaders."""
+    return train_model(model, datasets, cfg, distributed, validate, timestamp, meta, _skip_eval_tasks=('det',))

@@ -6,6 +6,25 @@ import torch.distributed as dist
 from ...engine.test import single_gpu_test
 
 
+class KeyIndicator:
+    """the `save_best` keys and weights (reference evaluation.py:9-26); repr() = the best-checkpoint file stem."""
+
+    def __init__(self, **kwargs):
+        self.key_indicator = dict(**kwargs)
+
+    def __getitem__(self, item):
+        return self.key_indicator[item]
+
+    def __repr__(self):
+        return '_'.join(k.replace('.', '_') for k in self.key_indicator)
+
+    def __len__(self):
+        return len(self.key_indicator)
+
+    def items(self):
+        return self.key_indicator.items()
+
+
 class MultiDatasetsEvalHook:
     def __init__(self, dataloaders, start=None, interval=1, by_epoch=False, save_best=None, test_fn=None,
                  **eval_kwargs):
@@ -39,7 +58,7 @@ class MultiDatasetsEvalHook:
             return
         if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
             return
-        stem = '_'.join(k.replace('.', '_') for k in self.save_best)
+        stem = repr(KeyIndicator(**self.save_best))
         if self.best_ckpt_path and os.path.isfile(self.best_ckpt_path):
             os.remove(self.best_ckpt_path)
         name = 'best_%s_iter_%d.pth' % (stem, runner.iter)

@@ -1,1 +1,1 @@
-from .optimizer import build_optimizer  # noqa: F401
+from .optimizer import build_optimizer, build_optimizer_constructor, MTLOptimizerConstructor  # noqa: F401

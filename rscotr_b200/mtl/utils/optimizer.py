@@ -78,3 +78,24 @@ def build_optimizer(model, cfg):
     if opt_type in ('AdamW', 'Adam') and all(p.is_cuda for g in params for p in g['params']):
         kwargs.setdefault('fused', True)
     return cls(params, **kwargs)
+
+
+class MTLOptimizerConstructor:
+    """reference mtl/utils/optimizer.py:40-55 (an mmcv DefaultOptimizerConstructor): `constructor(model)` -> optimizer."""
+
+    def __init__(self, optimizer_cfg, paramwise_cfg=None):
+        self.optimizer_cfg, self.paramwise_cfg = dict(optimizer_cfg), paramwise_cfg
+
+    def __call__(self, model):
+        cfg = dict(self.optimizer_cfg)
+        if self.paramwise_cfg:
+            cfg['paramwise_cfg'] = self.paramwise_cfg
+        return build_optimizer(model, cfg)
+
+
+def build_optimizer_constructor(cfg):
+    cfg = dict(cfg)
+    t = cfg.pop('type')
+    if t not in ('MTLOptimizerConstructor', 'DefaultOptimizerConstructor'):
+        raise KeyError('%s is not registered in the optimizer builder registry.' % t)
+    return MTLOptimizerConstructor(**cfg)

@@ -344,8 +344,9 @@ def test_cotraining_and_evaluation_on_real_files(resisc, dior, potsdam, tmp_path
     eng = StepEngine(model, dict(type='AdamW', lr=1e-4, weight_decay=1e-4), grad_clip=dict(max_norm=0.1, norm_type=2),
                      device='cpu', compute_dtype=torch.float32, use_graphs=False)
     runner = IterBasedRunner(eng, max_iters=3, work_dir=str(tmp_path), log_interval=0)
-    val_sets = build_datasets(cfg.data, split='val')
-    assert all(d.test_mode for d in val_sets.values())
+    from rscotr_b200.mtl.data.multi_eval_dataset import MultiEvalDatasets
+    val_sets = {k: MultiEvalDatasets(v) for k, v in build_datasets(cfg.data, split='val').items()}   # as train_model does
+    assert all(d.test_mode for d in val_sets.values()) and val_sets['dior'][0]['task'] == 'det'
     val_loaders = build_dataloaders(cfg, False, val_sets, train=False)
     hook = MultiDatasetsEvalHook(val_loaders, interval=3, by_epoch=False,
                                  save_best={'resisc.accuracy_top-1': 1, 'dior.bbox_mAP': 100, 'potsdam.mFscore': 100},
