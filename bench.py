@@ -208,8 +208,13 @@ def run_reference(args):
         step(name)
         if i >= args.warmup:
             times[name].append(time.time() - t0)
+    for name in TASK_ORDER:                  # fewer than 3 timed steps: every task still needs one sample for the cycle time
+        if not times[name]:
+            t0 = time.time()
+            step(name)
+            times[name].append(time.time() - t0)
     bs = per_gpu_batch(cfg)
-    per_img = {n: (sum(v) / len(v) if v else float('nan')) * scale for n, v in times.items()}
+    per_img = {n: sum(v) / len(v) * scale for n, v in times.items()}
     cycle = sum(per_img[n] * bs[n] for n in TASK_ORDER)
     value = 3.0 / cycle
     sample = ('oracle (CPU fp32 restatement) train step on batch 1 per task at 3x%dx%d%s; per-image seconds %s; '
