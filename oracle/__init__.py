@@ -12,7 +12,8 @@ with the same fixtures, on the CUDA path): CdnQueryGenerator (a15), the DINO dec
 DinoTransformer.forward and DINOHead.forward (a13), DINOHead.loss / DETRHead.loss_single / dn targets (a16, in-tree
 flow), MlvlSegPixelDecoder.forward (a17), Mask2FormerHead.forward / forward_head (a18), MTL.train_step /
 _parse_losses (a21), the iteration strategies and MultiDataLoader (a22), MlvlClsPixelDecoder.forward and
-MlvlClsHead.pre_logits_1..8 (8f rank 4).  ``oracle/metrics.py`` (evaluators) and ``oracle/uper.py`` (UPerNet, a20) restate
+MlvlClsHead.pre_logits_1..8 (8f rank 4), the evaluation path DeformableDETRHead.get_bboxes / DETRHead._get_bboxes_single and
+MTL.simple_test_{det,seg} / inference_seg / whole_inference_seg / forward_test (8f rank 4).  ``oracle/metrics.py`` (evaluators) and ``oracle/uper.py`` (UPerNet, a20) restate
 third-party code only and say PARITY UNPINNED in their own headers.
 Everything else is PARITY UNPINNED: the arithmetic of the path lives in un-vendored third-party
 packages (mmcv-full 1.6.1, mmdet 2.25.1, mmsegmentation 0.28.0, mmcls) that are

@@ -410,6 +410,67 @@ def test_cls_mlvl_head_matches_reference_run(device):
         assert tok.shape == c['tokens'][k].shape and torch.allclose(tok, c['tokens'][k], rtol=1e-5, atol=1e-5), k
 
 
+@pytest.mark.parametrize('device', DEVICES)
+def test_inference_path_matches_reference_run(device):
+    """8f rank 4 (evaluation path): the reference's get_bboxes / _get_bboxes_single and MTL.simple_test_seg / inference_seg /
+    whole_inference_seg / simple_test_det / forward_test, run in place (tools/make_golden.py::golden_inference), against
+    this repo's DINOHead.get_bboxes and MTL methods on the same inputs."""
+    import types
+    import numpy as np
+    from rscotr_b200.models.det_head import DINOHead
+    from rscotr_b200.models.mtl import MTL
+    mg = _tools()
+    t = mg.toy_inference_parts()
+    c = torch.load(os.path.join(GOLDEN, 'reference_inference.pt'), weights_only=False)
+    for rescale in (False, True):
+        fake = types.SimpleNamespace(test_cfg=dict(max_per_img=t['max_per_img']), num_query=t['num_query'], num_classes=t['num_classes'])
+        with torch.no_grad():
+            res = DINOHead.get_bboxes(fake, t['all_cls'].to(device), t['all_box'].to(device), None, None, t['metas'], rescale=rescale)
+        for (b, l), (wb, wl) in zip(res, c['det_rescale_%s' % rescale]):
+            assert torch.equal(l.cpu(), wl) and torch.allclose(b.cpu(), wb, rtol=1e-5, atol=1e-5)
+
+    class Seg:
+        align_corners = False
+
+        def forward_test(self, neck, backbone, img_meta, enc):
+            return t['seg_logit'].to(device)
+
+    class Box:
+        num_classes = t['num_classes']
+
+        def simple_test(self, feat, img_metas, rescale=False, shared_encoder=None):
+            self.saw = dict(rescale=rescale, batch_input_shape=[m['batch_input_shape'] for m in img_metas])
+            return c['det_rescale_%s' % rescale]
+
+    class Fake:
+        test_cfg = dict(seg=dict(mode='whole'))
+        shared_encoder = None
+        seg_head, bbox_head = Seg(), Box()
+
+        def extract_feat(self, img):
+            return ([img], [img])
+        whole_inference_seg, inference_seg, simple_test_seg = MTL.whole_inference_seg, MTL.inference_seg, MTL.simple_test_seg
+        simple_test_det, simple_test, forward_test = MTL.simple_test_det, MTL.simple_test, MTL.forward_test
+    fk = Fake()
+    img = t['img'].to(device)
+    with _ctx(device), torch.no_grad():
+        for k, meta in enumerate(t['seg_metas']):
+            for rescale in (True, False):
+                prob = fk.inference_seg(img, [dict(meta), dict(meta)], rescale)
+                assert torch.allclose(prob.cpu(), c['seg_prob_%d_rescale_%s' % (k, rescale)], rtol=1e-4, atol=1e-5), (k, rescale)
+                pred = fk.simple_test_seg(img, [dict(meta), dict(meta)], rescale)
+                want = c['seg_%d_rescale_%s' % (k, rescale)]
+                assert len(pred) == len(want) == 2
+                for a, b in zip(pred, want):
+                    assert a.shape == b.shape and (a != b).mean() < 0.002          # (argmax ties at fp32 rounding level)
+        det = fk.forward_test('det', [img], [[dict(m) for m in t['metas']]], rescale=True)
+        assert fk.bbox_head.saw == c['det_saw']
+        for a, b in zip(det, c['det_results']):
+            assert len(a) == len(b) == t['num_classes'] and all(np.allclose(x, y) for x, y in zip(a, b))
+        seg = fk.forward_test(['seg', 'seg'], [img], [[dict(t['seg_metas'][0])] * 2])
+        assert all((a != b).mean() < 0.002 for a, b in zip(seg, c['seg_via_forward_test']))
+
+
 def _dino_head():
     import rscotr_b200.models  # noqa: F401
     from rscotr_b200.config import Config

@@ -23,6 +23,7 @@ import types
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get('RSC_REFERENCE', '/root/reference')
@@ -788,6 +789,101 @@ def golden_cls_mlvl():
     return [tuple(o.shape) for o in outs], {k: tuple(v.shape) for k, v in tokens.items()}
 
 
+def toy_inference_parts():
+    g = torch.Generator().manual_seed(91)
+    L, B, Q, C = 2, 2, 9, 5
+    return dict(all_cls=torch.randn(L, B, Q, C, generator=g) * 2, all_box=torch.rand(L, B, Q, 4, generator=g) * 0.5 + 0.2,
+                metas=[dict(img_shape=(60, 80, 3), scale_factor=np.array([1.25, 1.2, 1.25, 1.2], dtype=np.float32)),
+                       dict(img_shape=(48, 64, 3), scale_factor=np.array([0.5, 0.5, 0.5, 0.5], dtype=np.float32))],
+                num_classes=C, num_query=Q, max_per_img=7,
+                seg_logit=torch.randn(2, 4, 12, 16, generator=g), img=torch.zeros(2, 3, 48, 64),
+                seg_metas=[dict(img_shape=(40, 60, 3), ori_shape=(80, 120, 3), flip=f, flip_direction='horizontal') for f in (False, True)])
+
+
+def golden_inference():
+    """the evaluation path (8f rank 4): mmdet_detr_head/deformable_detr_head.py::get_bboxes + detr_head.py::_get_bboxes_single
+    (sigmoid top-k over queries x classes, cxcywh -> xyxy, clamp, rescale) and multitask_learner.py::simple_test_seg /
+    inference_seg / whole_inference_seg / simple_test_det / forward_test, run in place (unbound) on stand-in objects."""
+    install_mmdet_shim()
+    _stub_packages(['mmcv.cnn', 'mmcv.cnn.bricks.transformer', 'mmcv.runner', 'mmdet.core', 'mmdet.models.utils', 'mmdet.models.builder',
+                    'mmdet.models.dense_heads.anchor_free_head', 'mmdet.models.utils.transformer'])
+    core = sys.modules['mmdet.core']
+
+    def bbox_cxcywh_to_xyxy(bbox):          # mmdet 2.25.1 core/bbox/transforms.py
+        cx, cy, w, h = bbox.split((1, 1, 1, 1), dim=-1)
+        return torch.cat([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
+    core.bbox_cxcywh_to_xyxy = bbox_cxcywh_to_xyxy
+    detr = load('models/multi/bbox_head/mmdet_detr_head/detr_head.py', 'ref_bbox_head.mmdet_detr_head.detr_head')
+    sys.modules['ref_bbox_head.mmdet_detr_head'] = types.ModuleType('ref_bbox_head.mmdet_detr_head')
+    ddetr = load('models/multi/bbox_head/mmdet_detr_head/deformable_detr_head.py', 'ref_bbox_head.mmdet_detr_head.deformable_detr_head')
+    t = toy_inference_parts()
+    out = dict(source='reference get_bboxes / simple_test_* (run in place, unbound)')
+    for rescale in (False, True):
+        fake = types.SimpleNamespace(test_cfg=dict(max_per_img=t['max_per_img']), num_query=t['num_query'], num_classes=t['num_classes'],
+                                     loss_cls=types.SimpleNamespace(use_sigmoid=True))
+        fake._get_bboxes_single = lambda *a, **k: detr.DETRHead._get_bboxes_single(fake, *a, **k)
+        with torch.no_grad():
+            res = ddetr.DeformableDETRHead.get_bboxes(fake, t['all_cls'].clone(), t['all_box'].clone(), None, None, t['metas'], rescale=rescale)
+        out['det_rescale_%s' % rescale] = [(b.clone(), l.clone()) for b, l in res]
+    # ---- MTL inference methods
+    _stub_packages(['matplotlib.font_manager', 'matplotlib.pyplot', 'matplotlib.collections', 'matplotlib.patches',
+                    'mmcv.runner', 'mmcv.cnn.bricks.transformer', 'mmcv.cnn', 'mmcls.models.utils.augment', 'mmdet.core',
+                    'mmdet.core.visualization', 'mmseg.core', 'mmseg.ops', 'mtl.model.build', 'mmdet.models.utils.transformer'])
+
+    def resize(input, size=None, scale_factor=None, mode='nearest', align_corners=None, warning=True):   # mmseg 0.28 ops/wrappers.py
+        return F.interpolate(input, size, scale_factor, mode, align_corners)
+
+    def bbox2result(bboxes, labels, num_classes):                                                  # mmdet 2.25.1 core/bbox/transforms.py
+        if bboxes.shape[0] == 0:
+            return [np.zeros((0, 5), dtype=np.float32) for _ in range(num_classes)]
+        bboxes, labels = bboxes.detach().cpu().numpy(), labels.detach().cpu().numpy()
+        return [bboxes[labels == i, :] for i in range(num_classes)]
+    sys.modules['mmseg.ops'].resize = resize
+    sys.modules['mmdet.core'].bbox2result = bbox2result
+    ref = load('models/multi/multitask_learner.py', 'ref_multitask_learner_inf')
+    ref.resize, ref.bbox2result = resize, bbox2result
+    MTL = ref.MTL
+
+    class Seg:
+        align_corners = False
+
+        def forward_test(self, neck, backbone, img_meta, enc):
+            return t['seg_logit']
+
+    class Box:
+        num_classes = t['num_classes']
+
+        def simple_test(self, feat, img_metas, rescale=False, shared_encoder=None):
+            self.saw = dict(rescale=rescale, batch_input_shape=[m['batch_input_shape'] for m in img_metas])
+            return out['det_rescale_%s' % rescale]
+
+    class Fake:
+        test_cfg = dict(seg=types.SimpleNamespace(mode='whole'))
+        shared_encoder = None
+        seg_head, bbox_head = Seg(), Box()
+
+        def extract_feat(self, img):
+            return ([img], [img])
+        whole_inference_seg = MTL.whole_inference_seg
+        inference_seg = MTL.inference_seg
+        simple_test_seg = MTL.simple_test_seg
+        simple_test_det = MTL.simple_test_det
+        simple_test = MTL.simple_test
+        forward_test = MTL.forward_test
+    fk = Fake()
+    with torch.no_grad():
+        for k, meta in enumerate(t['seg_metas']):
+            for rescale in (True, False):
+                out['seg_%d_rescale_%s' % (k, rescale)] = fk.simple_test_seg(t['img'], [dict(meta), dict(meta)], rescale)
+                out['seg_prob_%d_rescale_%s' % (k, rescale)] = fk.inference_seg(t['img'], [dict(meta), dict(meta)], rescale).clone()
+        metas = [dict(m) for m in t['metas']]
+        out['det_results'] = fk.forward_test('det', [t['img']], [metas], rescale=True)
+        out['det_saw'] = fk.bbox_head.saw
+        out['seg_via_forward_test'] = fk.forward_test(['seg', 'seg'], [t['img']], [[dict(t['seg_metas'][0])] * 2])
+    torch.save(out, os.path.join(OUT, 'reference_inference.pt'))
+    return sorted(out.keys())
+
+
 # ----------------------------------------------------------------------------- MultiDataLoader
 class _ToyDataset(torch.utils.data.Dataset):
     """n samples {'idx': i}; `task` is what MultiDataLoader tags batches with"""
@@ -848,6 +944,7 @@ if __name__ == '__main__':
     print('seg forward:', golden_seg_forward())
     print('seg pixel decoder:', golden_seg_pixel_decoder())
     print('cls mlvl:', golden_cls_mlvl())
+    print('inference:', golden_inference())
     d = golden_dn_targets()
     print('dn targets:', [(c['sizes'], c['num_total_pos'], c['num_total_neg']) for c in d])
     e0 = golden_sineembed()
