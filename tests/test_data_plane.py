@@ -367,3 +367,20 @@ def test_cotraining_and_evaluation_on_real_files(resisc, dior, potsdam, tmp_path
     assert hook.best_score is not None
     best = [f for f in os.listdir(tmp_path) if f.startswith('best_')]
     assert best == ['best_resisc_accuracy_top-1_dior_bbox_mAP_potsdam_mFscore_iter_3.pth']
+
+
+def test_worker_processes_and_seeding(resisc):
+    """DataLoader workers (fork): the dynamically built RandAugment policy classes and the per-(rank, worker) seeding work
+    in worker processes; the same loader seed reproduces the same first batch."""
+    ds = build_dataset(_cls_cfg(resisc), 'cls')
+
+    def first(seed):
+        loader = build_dataloader(ds, samples_per_gpu=3, workers_per_gpu=2, dist=False, seed=seed, pin_memory=False)
+        it = iter(loader)
+        b = next(it)
+        del it
+        return b
+    a, b, c = first(5), first(5), first(6)
+    assert a['img'].shape == (3, 3, 224, 224)
+    assert torch.equal(a['gt_label'], b['gt_label']) and torch.equal(a['img'], b['img'])
+    assert not torch.equal(a['img'], c['img'])
