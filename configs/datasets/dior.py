@@ -1,45 +1,32 @@
-# DIOR (20 classes) through the COCO-json reader of rscotr_b200/mtl/data/datasets.py.
-# Same dataset / pipeline settings as the reference's configs/_base_/det/dior.py
-# (tests/test_data_plane.py compares the two `data` dicts when the reference tree is mounted).
-dataset_type = 'CocoDataset'
-data_root = 'data/DIOR/'
-classes = ('airplane', 'airport', 'baseballfield', 'basketballcourt', 'bridge', 'chimney', 'dam', 'Expressway-Service-area',
-           'Expressway-toll-station', 'golffield', 'groundtrackfield', 'harbor', 'overpass', 'ship', 'stadium', 'storagetank',
-           'tenniscourt', 'trainstation', 'vehicle', 'windmill')
-img_norm_cfg = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True)
-_scale = (1333, 800)
-
-train_pipeline = [
-    dict(type='LoadImageFromFile'),
-    dict(type='LoadAnnotations', with_bbox=True),
-    dict(type='Resize', img_scale=_scale, keep_ratio=True),
-    dict(type='RandomFlip', flip_ratio=0.5),
-    dict(type='Normalize', **img_norm_cfg),
-    dict(type='Pad', size_divisor=32),
-    dict(type='DefaultFormatBundle'),
-    dict(type='Collect', keys=['img', 'gt_bboxes', 'gt_labels'])]
-
-_test_steps = [
-    dict(type='Resize', keep_ratio=True),
-    dict(type='RandomFlip'),
-    dict(type='Normalize', **img_norm_cfg),
-    dict(type='Pad', size_divisor=32),
-    dict(type='ImageToTensor', keys=['img']),
-    dict(type='Collect', keys=['img'])]
-test_pipeline = [
-    dict(type='LoadImageFromFile'),
-    dict(type='MultiScaleFlipAug', img_scale=_scale, flip=False, transforms=_test_steps)]
+# DIOR (20 classes) through the COCO-json reader of rscotr_b200/mtl/data/datasets.py.  The resulting `data` /
+# `evaluation` dicts are checked (tests/test_data_plane.py) to equal the reference's DIOR dataset settings.
+NORM = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True)
+ROOT = 'data/DIOR/'
+SCALE = (1333, 800)          # long edge, short edge
+NAMES = ('airplane airport baseballfield basketballcourt bridge chimney dam Expressway-Service-area Expressway-toll-station '
+         'golffield groundtrackfield harbor overpass ship stadium storagetank tenniscourt trainstation vehicle windmill').split()
 
 
-def _split(ann, prefix, pipeline):
-    return dict(type=dataset_type, ann_file=data_root + 'coco_ann/DIOR_%s_coco.json' % ann, img_prefix=data_root + prefix,
-                pipeline=pipeline, classes=classes)
+def step(kind, **kw):
+    return dict(type=kind, **kw)
 
 
-data = dict(
-    samples_per_gpu=1,
-    workers_per_gpu=2,
-    train=_split('train', 'JPEGImages-trainval', train_pipeline),
-    val=_split('val', 'JPEGImages-trainval/', test_pipeline),
-    test=_split('test', 'JPEGImages-test/', test_pipeline))
+def pipeline(train):
+    tail = [step('Normalize', **NORM), step('Pad', size_divisor=32)]
+    if train:
+        return [step('LoadImageFromFile'), step('LoadAnnotations', with_bbox=True), step('Resize', img_scale=SCALE, keep_ratio=True),
+                step('RandomFlip', flip_ratio=0.5)] + tail + [step('DefaultFormatBundle'),
+                                                              step('Collect', keys=['img', 'gt_bboxes', 'gt_labels'])]
+    inner = [step('Resize', keep_ratio=True), step('RandomFlip')] + tail + [step('ImageToTensor', keys=['img']),
+                                                                            step('Collect', keys=['img'])]
+    return [step('LoadImageFromFile'), step('MultiScaleFlipAug', img_scale=SCALE, flip=False, transforms=inner)]
+
+
+def split(name, images, train=False):
+    return dict(type='CocoDataset', ann_file='%scoco_ann/DIOR_%s_coco.json' % (ROOT, name), img_prefix=ROOT + images,
+                pipeline=pipeline(train), classes=tuple(NAMES))
+
+
+data = dict(samples_per_gpu=1, workers_per_gpu=2, train=split('train', 'JPEGImages-trainval', True),
+            val=split('val', 'JPEGImages-trainval/'), test=split('test', 'JPEGImages-test/'))
 evaluation = dict(interval=1, metric='bbox', iou_thrs=[0.5], save_best='bbox_mAP_50', classwise=True)
