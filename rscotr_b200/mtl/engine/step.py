@@ -81,6 +81,8 @@ class StepEngine:
         self._base_lrs = [float(g['lr']) for g in self.optimizer.param_groups]
         self._graphs = {}
         self.graph_warmup = 2            # eager iterations per (task, shapes) before capture
+        self.max_graphs = int(os.environ.get('RSC_MAX_GRAPHS', 12))
+        self.graph_idle_iters = 512
         self.replayed_launches = 0       # rscotr kernels executed through graph replays
         self.graph_failures = 0
         self.lr_config = dict(lr_config) if lr_config else None
@@ -309,6 +311,28 @@ class StepEngine:
             ev.record(cs)
         st['staged'] = (id(data_batch), ev)
 
+    def _graph_slot(self, key):
+        """Bookkeeping entry of a (task, shapes) signature, or None when it may not get a CUDA graph.  Every captured
+        graph pins its activations, so their number is bounded (`max_graphs`, RSC_MAX_GRAPHS): real detection batches
+        have a different signature per ground-truth count.  A signature is captured only after `graph_warmup` eager
+        runs (rare ones never are); when the bound is reached a new signature takes the slot of a captured one that
+        has not been replayed for `graph_idle_iters` iterations, and runs eagerly otherwise."""
+        st = self._graphs.get(key)
+        if st is not None:
+            st['last'] = self.iter
+            return st
+        captured = [(v.get('last', 0), k) for k, v in self._graphs.items() if 'gA' in v]
+        if len(captured) >= self.max_graphs:
+            last, victim = min(captured)
+            if self.iter - last < self.graph_idle_iters:
+                return None
+            del self._graphs[victim]
+        if len(self._graphs) > 4096:                      # forget the oldest never-captured signatures
+            for k in sorted((k for k, v in self._graphs.items() if 'gA' not in v), key=lambda k: self._graphs[k].get('last', 0))[:2048]:
+                del self._graphs[k]
+        st = self._graphs[key] = dict(eager=0, last=self.iter)
+        return st
+
     def train_iter(self, data_batch):
         """model.train_step + OptimizerHook.after_train_iter.  Returns train_step's outputs.
         After `graph_warmup` eager iterations of a (task, shapes) signature the iteration is
@@ -319,7 +343,11 @@ class StepEngine:
             self.iter += 1
             return outputs
         key = self._signature(data_batch)
-        st = self._graphs.setdefault(key, dict(eager=0))
+        st = self._graph_slot(key)
+        if st is None:                                    # too many distinct (task, shapes) signatures: no graph for this one
+            outputs = self._train_iter_eager(_to_device(data_batch, self.device))
+            self.iter += 1
+            return outputs
         if 'gA' not in st:
             if st['eager'] < self.graph_warmup:
                 st['eager'] += 1

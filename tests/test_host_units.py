@@ -268,3 +268,25 @@ def test_logistic_gelu_fit_is_within_bf16_resolution():
     assert cdf[-1] == 1.0 and cdf[-2] == 0.0 and np.all(np.isfinite(cdf))
     tail = (xd > -5) & (xd < -3)
     assert np.max(np.abs(cdf[tail] - phi[tail]) / phi[tail]) < 0.05         # a few percent RELATIVE down to x = -5 (Phi = 3e-7)
+
+
+def test_graph_cache_is_bounded():
+    """StepEngine._graph_slot: at most `max_graphs` captured signatures; a new signature replaces a captured one only when
+    that one has been idle for `graph_idle_iters` iterations, otherwise it runs eagerly (None)."""
+    from rscotr_b200.mtl.engine import StepEngine
+    eng = StepEngine(torch.nn.Linear(4, 2), dict(type='SGD', lr=0.1), device='cpu', compute_dtype=torch.float32, use_graphs=False)
+    eng.max_graphs, eng.graph_idle_iters = 2, 10
+    a = eng._graph_slot('a')
+    assert a == dict(eager=0, last=0) and eng._graph_slot('a') is a
+    a['gA'] = object()                                    # "captured"
+    eng.iter = 3
+    b = eng._graph_slot('b')
+    b['gA'] = object()
+    eng.iter = 5
+    assert eng._graph_slot('c') is None and set(eng._graphs) == {'a', 'b'}      # full, nobody idle long enough
+    assert eng._graph_slot('b')['last'] == 5
+    eng.iter = 12
+    c = eng._graph_slot('c')                               # 'a' idle since iteration 0 -> evicted
+    assert c is not None and set(eng._graphs) == {'b', 'c'}
+    eng.iter = 13
+    assert eng._graph_slot('d') is not None               # 'c' is not captured yet: it does not count against the bound
