@@ -50,16 +50,23 @@ class IterBasedRunner:
 
     def run(self, data_loaders, workflow=(('train', 1),), **kwargs):
         loader = data_loaders[0]
-        it = iter(loader)
+        state = dict(it=iter(loader))
+
+        def next_batch():
+            try:
+                return next(state['it'])
+            except StopIteration:                       # mmcv IterLoader: start the next epoch
+                state['it'] = iter(loader)
+                return next(state['it'])
         self.model.train()
         t0 = time.time()
+        batch = next_batch() if self.engine.iter < self.max_iters else None
         while self.engine.iter < self.max_iters:
-            try:
-                batch = next(it)
-            except StopIteration:
-                it = iter(loader)
-                batch = next(it)
-            self.outputs = self.engine.train_iter(batch)
+            self.outputs = self.engine.train_iter(batch)        # enqueues the step (asynchronous on the GPU)
+            # fetch the next batch while the GPU works and start its host->device copy on the copy stream
+            batch = next_batch() if self.engine.iter < self.max_iters else None
+            if batch is not None:
+                self.engine.prefetch(batch)
             if self.log_interval and self.engine.iter % self.log_interval == 0:
                 self.log_buffer.update(dict(self.outputs['log_vars'].items()), self.outputs['num_samples'])
                 if self.logger:
