@@ -19,6 +19,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 DEVICES = ['cpu', pytest.param('cuda', marks=pytest.mark.gpu)]
+# CUDA variants that have not yet run on hardware stay opt-in (RSC_TEST_EXPERIMENTAL=1) until the next GPU session
+DEVICES_NEW = ['cpu', pytest.param('cuda', marks=[pytest.mark.gpu, pytest.mark.skipif(
+    os.environ.get('RSC_TEST_EXPERIMENTAL') != '1', reason='not yet validated on a GPU (RSC_TEST_EXPERIMENTAL=1)')])]
 
 
 def _to(obj, device):
@@ -410,7 +413,7 @@ def test_cls_mlvl_head_matches_reference_run(device):
         assert tok.shape == c['tokens'][k].shape and torch.allclose(tok, c['tokens'][k], rtol=1e-5, atol=1e-5), k
 
 
-@pytest.mark.parametrize('device', DEVICES)
+@pytest.mark.parametrize('device', DEVICES_NEW)
 def test_inference_path_matches_reference_run(device):
     """8f rank 4 (evaluation path): the reference's get_bboxes / _get_bboxes_single and MTL.simple_test_seg / inference_seg /
     whole_inference_seg / simple_test_det / forward_test, run in place (tools/make_golden.py::golden_inference), against

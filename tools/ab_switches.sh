@@ -11,6 +11,7 @@ export PYTHONUNBUFFERED=1
 echo "== parity with the switches on"
 RSC_TEST_EXPERIMENTAL=1 RSC_GELU_SIG=1 RSC_ADD_LN_LEAN=1 timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -q -x \
   -k "bias_gelu or add_ln or logistic" 2>&1 | tail -3
+RSC_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_golden_reference.py -m gpu -q -k inference 2>&1 | tail -2
 echo "== kbench (default switches)"
 KB_B=4 timeout 300 python tools/kbench.py 2>/dev/null | grep -E "bias_act|add_ln" | tee gpurun_out/ab_kbench_default.jsonl
 echo "== kbench (RSC_ADD_LN_LEAN=1)"
