@@ -1,5 +1,5 @@
 """Importing this package registers every class the reference configs name
 (the reference does it with custom_imports=dict(imports='models.multi'))."""
-from . import bricks, swin, cls_head, det_head, seg_head, mtl, uper_head  # noqa: F401
+from . import bricks, swin, cls_head, det_head, seg_head, mtl, uper_head, classifier  # noqa: F401
 from .mtl import MTL  # noqa: F401
-ImageClassifier = cls_head._make_image_classifier()
+from .classifier import ImageClassifier  # noqa: F401

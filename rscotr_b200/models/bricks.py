@@ -36,6 +36,27 @@ def const_tensor(values, dtype, device):
     return t
 
 
+def apply_init_cfg(module, init_cfg):
+    """mmcv BaseModule.init_weights for the layer-wise entries the reference configs use (`TruncNormal` / `Normal` /
+    `Constant` with a `layer` filter): every sub-module whose class name is listed is re-initialised."""
+    for c in ([init_cfg] if isinstance(init_cfg, dict) else (init_cfg or [])):
+        layers = c.get('layer')
+        layers = [layers] if isinstance(layers, str) else list(layers or [])
+        for m in module.modules():
+            if type(m).__name__ not in layers or getattr(m, 'weight', None) is None:
+                continue
+            if c['type'] == 'TruncNormal':
+                nn.init.trunc_normal_(m.weight, mean=c.get('mean', 0.), std=c.get('std', 1.), a=c.get('a', -2.), b=c.get('b', 2.))
+            elif c['type'] == 'Normal':
+                nn.init.normal_(m.weight, c.get('mean', 0.), c.get('std', 1.))
+            elif c['type'] == 'Constant':
+                nn.init.constant_(m.weight, c['val'])
+            else:
+                raise KeyError('init_cfg type %s is not supported' % c['type'])
+            if getattr(m, 'bias', None) is not None:
+                nn.init.constant_(m.bias, c.get('bias', 0.))
+
+
 class GeomCache:
     """Small shape-keyed cache of no-grad geometry constants of a head (padding masks, sine positional
     encodings, reference points, proposal grids ...).  The reference recomputes them with ~25-80 tiny

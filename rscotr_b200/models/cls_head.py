@@ -230,22 +230,8 @@ class MlvlClsHead(SlvlClsHead):
         self.pixel_decoder.init_weights()
         # mmcv BaseModule.init_weights applies the head's init_cfg to EVERY matching layer below it, so with the
         # reference's `TruncNormal(layer='Linear')` entry (cfg MTL_swin-t...:66-69) fc and out_proj are both re-drawn
-        for c in ([init_cfg] if isinstance(init_cfg, dict) else (init_cfg or [])):
-            layers = c.get('layer')
-            layers = [layers] if isinstance(layers, str) else list(layers or [])
-            for m in self.modules():
-                if type(m).__name__ not in layers:
-                    continue
-                if c['type'] == 'TruncNormal':
-                    nn.init.trunc_normal_(m.weight, mean=c.get('mean', 0.), std=c.get('std', 1.), a=c.get('a', -2.), b=c.get('b', 2.))
-                elif c['type'] == 'Normal':
-                    nn.init.normal_(m.weight, c.get('mean', 0.), c.get('std', 1.))
-                elif c['type'] == 'Constant':
-                    nn.init.constant_(m.weight, c['val'])
-                else:
-                    raise KeyError('init type %s' % c['type'])
-                if getattr(m, 'bias', None) is not None:
-                    nn.init.constant_(m.bias, c.get('bias', 0.))
+        from .bricks import apply_init_cfg
+        apply_init_cfg(self, init_cfg)
 
     def pre_logits(self, mlvl_feats):
         s = self.scheme
@@ -296,70 +282,3 @@ class LinearClsHead(SlvlClsHead):
         cls_score = self.fc(self.pre_logits(x))
         pred = F.softmax(cls_score.float(), dim=1) if softmax else cls_score
         return list(pred.detach().cpu().numpy()) if post_process else pred
-
-
-def _single_task_base():
-    from .mtl import SingleTaskModel          # (mtl imports this module: resolved when models/__init__ finishes)
-    return SingleTaskModel
-
-
-def _make_image_classifier():
-    Base = _single_task_base()
-
-    @MODELS.register_module()
-    class ImageClassifier(Base):
-        """mmcls ImageClassifier(backbone, neck, head, train_cfg.augments) -- the reference's single-task classification
-        configs (configs/cls/*.py; BASELINE configs[0]) -- with the step engine's model interface."""
-        default_task = 'cls'
-
-        def __init__(self, backbone, neck=None, head=None, pretrained=None, train_cfg=None, init_cfg=None):
-            super().__init__()
-            from ..config import build_from_cfg
-            self.backbone = build_from_cfg(backbone, MODELS)
-            self.neck = build_from_cfg(neck, MODELS) if neck is not None else None
-            self.head = build_from_cfg(head, MODELS) if head is not None else None
-            self.augments = None
-            aug = (train_cfg or {}).get('augments', None)
-            if aug is not None:
-                self.augments = Augments(aug)
-            # mmcv applies the model-level init_cfg (TruncNormal Linear / Constant LayerNorm) to every layer below
-            for c in ([init_cfg] if isinstance(init_cfg, dict) else (init_cfg or [])):
-                layers = c.get('layer')
-                layers = [layers] if isinstance(layers, str) else list(layers or [])
-                for m in self.modules():
-                    if type(m).__name__ in layers and getattr(m, 'weight', None) is not None:
-                        if c['type'] == 'TruncNormal':
-                            nn.init.trunc_normal_(m.weight, std=c.get('std', 1.), a=c.get('a', -2.), b=c.get('b', 2.))
-                        elif c['type'] == 'Constant':
-                            nn.init.constant_(m.weight, c['val'])
-                        if getattr(m, 'bias', None) is not None:
-                            nn.init.constant_(m.bias, c.get('bias', 0.))
-
-        def init_weights(self):
-            bb = self.backbone
-            if isinstance(getattr(bb, 'init_cfg', None), dict) and bb.init_cfg.get('type') == 'Pretrained':
-                bb.init_weights()
-
-        def extract_feat(self, img):
-            x = self.backbone(img)
-            x = tuple(x) if isinstance(x, (list, tuple)) else (x,)
-            return self.neck(x) if self.neck is not None else x
-
-        def forward_train(self, img, gt_label, **kwargs):
-            if self.augments is not None:
-                img, gt_label = self.augments(img, gt_label)
-            return self.head.forward_train(self.extract_feat(img), gt_label)
-
-        def simple_test(self, img, img_metas=None, **kwargs):
-            return self.head.simple_test(self.extract_feat(img), **kwargs)
-
-        def forward(self, img, img_metas=None, return_loss=True, task=None, dataset_name=None, **kwargs):
-            from .mtl import normalize_on_device
-            if isinstance(img, list):
-                img, img_metas = img[0], (img_metas[0] if img_metas else None)
-            if img_metas:
-                img = normalize_on_device(img, img_metas)
-            if return_loss:
-                return self.forward_train(img, **kwargs)
-            return self.simple_test(img, img_metas, **kwargs)
-    return ImageClassifier
