@@ -132,10 +132,57 @@ class Augments:
                 self.aug_probs.append(identity_prob)
 
     def __call__(self, img, gt_label):
-        if self.augments:
-            aug = self.augments[int(np.random.choice(len(self.augments), p=self.aug_probs))]
-            return aug(img, gt_label)
-        return img, gt_label
+        if not self.augments:
+            return img, gt_label
+        if img.is_cuda or self.device_rng:
+            return self.call_on_device(img, gt_label)
+        aug = self.augments[int(np.random.choice(len(self.augments), p=self.aug_probs))]
+        return aug(img, gt_label)
+
+    device_rng = False       # CPU tensors: the host-RNG path above unless a test asks for the device formulation
+
+    def call_on_device(self, img, gt_label):
+        """The same draw (which augment, Beta(alpha, alpha) mixing factor, permutation, CutMix box) with the DEVICE
+        generator and static shapes, so the call can sit inside a captured CUDA graph: a host-side np.random draw
+        would be frozen into the graph and replayed forever.  One blend for all cases:
+            img' = w * img + (1 - w) * img[perm],   label' = lam * onehot + (1 - lam) * onehot[perm]
+        with w = lam (Mixup), w = 1 outside / 0 inside the box and lam = 1 - box area / image area (CutMix), w = lam = 1
+        (no augment)."""
+        from .bricks import const_tensor
+        dev, B, H, W = img.device, img.shape[0], img.shape[-2], img.shape[-1]
+        nc = self.augments[0].num_classes
+        one_hot = one_hot_encoding(gt_label, nc)
+        perm = torch.rand(B, device=dev).argsort()
+        u = torch.rand((), device=dev)
+        w = torch.ones((1, 1), device=dev)
+        lam = torch.ones((), device=dev)
+        lo = 0.0
+        for aug, p in zip(self.augments, self.aug_probs):
+            sel = (u >= lo) & (u < lo + p)
+            lo += p
+            if isinstance(aug, Identity):
+                continue
+            g = torch._standard_gamma(const_tensor([float(aug.alpha), float(aug.alpha)], torch.float32, dev))
+            lam_a = g[0] / (g[0] + g[1])                                   # Beta(alpha, alpha)
+            if isinstance(aug, BatchMixup):
+                w_a = lam_a.view(1, 1)
+            else:
+                ratio = (1 - lam_a).sqrt()
+                half_h, half_w = (H * ratio).floor().long() // 2, (W * ratio).floor().long() // 2
+                c = torch.rand(2, device=dev)
+                cy, cx = (c[0] * H).long().clamp(max=H - 1), (c[1] * W).long().clamp(max=W - 1)
+                yl, yh = (cy - half_h).clamp(0, H), (cy + half_h).clamp(0, H)
+                xl, xh = (cx - half_w).clamp(0, W), (cx + half_w).clamp(0, W)
+                ys, xs = torch.arange(H, device=dev).view(H, 1), torch.arange(W, device=dev).view(1, W)
+                inside = (ys >= yl) & (ys < yh) & (xs >= xl) & (xs < xh)
+                w_a = 1.0 - inside.float()
+                if aug.correct_lam:
+                    lam_a = 1.0 - ((yh - yl) * (xh - xl)).float() / float(H * W)
+            w = torch.where(sel, w_a, w)
+            lam = torch.where(sel, lam_a, lam)
+        w = w.to(img.dtype)
+        img = w * img + (1 - w) * img[perm]
+        return img, lam * one_hot + (1 - lam) * one_hot[perm]
 
 
 _CLS_LOSSES = {'LabelSmoothLoss': LabelSmoothLoss, 'CrossEntropyLoss': CrossEntropyLoss}

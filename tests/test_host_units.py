@@ -290,3 +290,52 @@ def test_graph_cache_is_bounded():
     assert c is not None and set(eng._graphs) == {'b', 'c'}
     eng.iter = 13
     assert eng._graph_slot('d') is not None               # 'c' is not captured yet: it does not count against the bound
+
+
+def test_batch_augments_device_formulation():
+    """Augments.call_on_device (graph-capturable Mixup / CutMix): same distributions and formulas as the host-RNG path."""
+    from rscotr_b200.models.cls_head import Augments
+    aug = Augments([dict(type='BatchMixup', alpha=0.8, num_classes=5, prob=0.5), dict(type='BatchCutMix', alpha=1.0, num_classes=5, prob=0.3)])
+    assert len(aug.augments) == 3                                           # + Identity with the remaining 0.2
+    torch.manual_seed(0)
+    B, H, W = 6, 24, 32
+    img = torch.arange(B, dtype=torch.float32).view(B, 1, 1, 1).expand(B, 3, H, W).contiguous() + 10     # image b is the constant 10 + b
+    label = torch.arange(B) % 5
+    kinds = dict(mixup=0, cutmix=0, none=0)
+    lams = []
+    for _ in range(600):
+        out, soft = aug.call_on_device(img, label)
+        assert out.shape == img.shape and soft.shape == (B, 5) and torch.allclose(soft.sum(1), torch.ones(B), atol=1e-6)
+        # recover the permutation partner and the mixing weight of sample 0
+        per_pixel = out[0, 0]
+        vals = per_pixel.unique()
+        if len(vals) == 1 and float(vals[0]) == 10.0 and float(soft[0].max()) == 1.0:
+            kinds['none'] += 1
+            continue
+        if len(vals) == 2 or (len(vals) == 1 and float(vals[0]) == float(int(vals[0])) and float(soft[0].max()) < 1.0):
+            # CutMix: every pixel is exactly one of the two source images; label weight = 1 - pasted area / image area
+            kinds['cutmix'] += 1
+            src = out[:, 0] - 10
+            partner_pixels = (src != torch.arange(B, dtype=torch.float32).view(B, 1, 1)).float().mean((1, 2))
+            lam = 1 - partner_pixels
+            for b in range(B):
+                if partner_pixels[b] > 0:      # (a sample whose partner is itself is unchanged)
+                    assert abs(float(soft[b, label[b]]) - float(lam[b])) < 1e-5 or float(soft[b].max()) == 1.0
+            rows = (src[0] != 0).any(1).nonzero().flatten()
+            cols = (src[0] != 0).any(0).nonzero().flatten()
+            if len(rows):                       # the pasted region is ONE axis-aligned rectangle
+                box = src[0][rows[0]:rows[-1] + 1, cols[0]:cols[-1] + 1]
+                assert (box != 0).all() and (src[0] != 0).sum() == box.numel()
+            continue
+        kinds['mixup'] += 1
+        assert len(vals) == 1                                               # a constant blend of two constant images
+        lams.append(float(soft[0].max()))
+    n = sum(kinds.values())
+    # (sample 0 is its own partner with probability 1/6, which hides an augmentation as 'none')
+    assert abs(kinds['mixup'] / n - 0.5 * 5 / 6) < 0.07 and abs(kinds['cutmix'] / n - 0.3 * 5 / 6) < 0.07, kinds
+    assert 0.5 <= min(lams) and max(lams) <= 1.0 and np_std(lams) > 0.05
+
+
+def np_std(v):
+    import numpy as np
+    return float(np.std(v))
