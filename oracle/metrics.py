@@ -5,7 +5,8 @@ PARITY UNPINNED: the evaluators are third-party and absent from /root/reference 
 `models/losses/accuracy.py`); the reference holds no golden metric values.  Each function restates
 the published algorithm, loop for loop, and is anchored on the reference's call site
 (mtl/runner/hooks/evaluation.py:130-142) and eval kwargs (configs/multi/MTL_slvlcls_swin-t-p4-w7_1x1_
-resisc&dior&potsdam.py:222-238).  Known-answer cases in tests/test_metrics.py pin the easy facts."""
+resisc&dior&potsdam.py:222-238).  Known-answer cases and scikit-learn (top-k accuracy, confusion-matrix IoU / precision / recall / F1, a rebuilt PR
+curve for single-class AP) cross-check it in tests/test_metrics.py."""
 import numpy as np
 
 

@@ -121,3 +121,64 @@ def test_coco_bbox_known_answers():
     assert M.evaluate_det(none, gts, img_ids, cat_ids, iou_thrs=[0.5])['bbox_mAP'] == 0.0
     with pytest.raises(KeyError):
         M.evaluate_det(none, gts, img_ids, cat_ids, metric='segm')
+
+
+# ------------------------------------------------------------------------------------------ independent cross-checks
+def test_cls_and_seg_metrics_against_sklearn():
+    """scikit-learn as an independent implementation: top-k accuracy, per-class IoU / precision / recall / F1 from the
+    confusion matrix (the evaluators themselves are absent from this image, see oracle/metrics.py)."""
+    sk = pytest.importorskip('sklearn.metrics')
+    rng = np.random.default_rng(3)
+    scores = rng.normal(size=(400, 12))
+    gt = rng.integers(0, 12, size=400)
+    ours = M.accuracy(scores, gt, (1, 3, 5), thr=None)
+    for k, a in zip((1, 3, 5), ours):
+        assert a == pytest.approx(100 * sk.top_k_accuracy_score(gt, scores, k=k, labels=np.arange(12)))
+    C = 6
+    pred = rng.integers(0, C, size=(3, 50, 60))
+    lab = rng.integers(0, C + 1, size=(3, 50, 60))                  # label C = ignore
+    pre = [M.intersect_and_union(torch.from_numpy(p), torch.from_numpy(l), C, ignore_index=C) for p, l in zip(pred, lab)]
+    out = M.evaluate_seg(pre, [str(c) for c in range(C)], metric=['mIoU', 'mFscore'])
+    keep = lab.reshape(-1) != C
+    y, p = lab.reshape(-1)[keep], pred.reshape(-1)[keep]
+    iou = sk.jaccard_score(y, p, average=None, labels=np.arange(C))
+    prec, rec, f1, _ = sk.precision_recall_fscore_support(y, p, labels=np.arange(C), zero_division=0)
+    for c in range(C):
+        assert out['IoU.%d' % c] == pytest.approx(round(iou[c] * 100, 2) / 100)
+        assert out['Precision.%d' % c] == pytest.approx(round(prec[c] * 100, 2) / 100)
+        assert out['Recall.%d' % c] == pytest.approx(round(rec[c] * 100, 2) / 100)
+        assert out['Fscore.%d' % c] == pytest.approx(round(f1[c] * 100, 2) / 100)
+    assert out['aAcc'] == pytest.approx(round(sk.accuracy_score(y, p) * 100, 2) / 100)
+    assert out['mIoU'] == pytest.approx(round(iou.mean() * 100, 2) / 100)
+
+
+def test_coco_ap_single_class_against_sklearn_style_pr_curve():
+    """one category, IoU 0.5, no crowds: COCO AP = mean over the 101 recall thresholds of the monotone precision envelope of the
+    score-ranked PR curve -- rebuilt here from scikit-learn's precision_recall_curve on the matched / unmatched flags."""
+    sk = pytest.importorskip('sklearn.metrics')
+    rng = np.random.default_rng(5)
+    gts, dts = [], []
+    for img in range(8):
+        for k in range(3):
+            x, y = rng.uniform(0, 200, 2)
+            gts.append(dict(image_id=img, category_id=1, bbox=[x, y, 40, 40], area=1600, iscrowd=0))
+            if rng.random() < 0.7:                                   # a good detection of this gt
+                dts.append(dict(image_id=img, category_id=1, bbox=[x + 2, y - 1, 40, 40], score=float(rng.random())))
+        for k in range(2):                                            # false positives far away
+            dts.append(dict(image_id=img, category_id=1, bbox=[500 + 50 * k, 500, 30, 30], score=float(rng.random())))
+    ev = M.coco_eval_bbox(gts, dts, [1], list(range(8)), [0.5], (100, 300, 1000))
+    ap = M.coco_summarize(ev)[0]
+    flags = np.array([1 if d['bbox'][0] < 400 else 0 for d in dts])                 # by construction: near boxes match, far ones do not
+    scores = np.array([d['score'] for d in dts])
+    npos = len(gts)
+    order = np.argsort(-scores, kind='mergesort')
+    tp = np.cumsum(flags[order])
+    prec = tp / (np.arange(len(order)) + 1)
+    rec = tp / npos
+    env = np.maximum.accumulate(prec[::-1])[::-1]
+    want = np.mean([env[np.searchsorted(rec, r, side='left')] if np.searchsorted(rec, r, side='left') < len(env) else 0.0
+                    for r in np.linspace(0, 1, 101)])
+    assert ap == pytest.approx(want, abs=1e-9)
+    # scikit-learn's curve gives the same (precision, recall) points
+    p_sk, r_sk, _ = sk.precision_recall_curve(flags, scores)
+    assert np.allclose(sorted(set(np.round(r_sk * flags.sum() / npos, 9))), sorted(set(np.round(np.r_[0, rec], 9))))
