@@ -19,7 +19,8 @@ def train_model(model, datasets, cfg, distributed=False, validate=False, timesta
     if distributed and not dist.is_initialized():
         dist.init_process_group(cfg.get('dist_params', {}).get('backend', 'nccl'))
     device = 'cuda:%d' % int(os.environ.get('LOCAL_RANK', 0)) if distributed else cfg.get('device', 'cuda')
-    torch.cuda.set_device(device)
+    if str(device).startswith('cuda'):
+        torch.cuda.set_device(device)
     optimizer_config = cfg.get('optimizer_config', {}) or {}
     fp16 = cfg.get('fp16', None)
     engine = StepEngine(model, cfg.optimizer, grad_clip=optimizer_config.get('grad_clip'), device=device,

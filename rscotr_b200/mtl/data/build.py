@@ -132,7 +132,9 @@ def build_dataloaders(cfg, distributed, datasets, train=True):
         dcfg = data_cfg[ds]['config'].get('data', {}) if 'config' in data_cfg[ds] else {}
         if isinstance(datasets[ds], SyntheticDataset):
             bs = dcfg.get('samples_per_gpu', 1)
-            length = (cfg.get('synthetic') or {}).get('length', {}).get(ds, _DEFAULT_LENGTH[datasets[ds].task])
+            syn = cfg.get('synthetic') or {}
+            length = syn.get('length', {}).get(ds, _DEFAULT_LENGTH[datasets[ds].task]) if train else \
+                syn.get('val_length', {}).get(ds, 4)          # (synthetic validation: a few batches, not an epoch)
             data_loaders[ds] = _SyntheticLoader(datasets[ds], bs, length, seed=(cfg.get('seed', 0) or 0) * 1000 + 17 * i + rank)
             continue
         args = prepare_dataloader_args(split, datasets[ds].task, distributed, dcfg, seed=cfg.get('seed', None),

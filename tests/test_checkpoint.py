@@ -199,3 +199,51 @@ def test_test_model_api_from_checkpoint(tmp_path):
         again, _ = test_model(cfg, path, tasks=('cls', 'seg'), split='val', device='cpu', synthetic=cfg.synthetic,
                               test_outputs=outputs)
     assert again['resisc'] == metrics['resisc']
+
+
+@pytest.mark.timeout(900)
+def test_train_model_api_end_to_end(tmp_path):
+    """mtl.apis.train_model (reference signature): co-training + validation hook + periodic / best checkpoints, then a second
+    call with auto_resume that continues from the latest checkpoint."""
+    import logging
+    from rscotr_b200.mtl.apis import train_model
+    from rscotr_b200.mtl.data import build_datasets, load_data_cfg
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def make_cfg(max_iters):
+        cfg = small_cfg()
+        for v in cfg.data.values():
+            v['config'] = os.path.join(root, v['config'])
+            v['data']['samples_per_gpu'] = 2 if v['task'] == 'cls' else 1
+        load_data_cfg(cfg)
+        cfg.synthetic = dict(img_size=(64, 64), det=dict(num_boxes=2), val_length=dict(resisc=1, dior=1, potsdam=1))
+        cfg.device, cfg.compute_dtype, cfg.work_dir = 'cpu', torch.float32, str(tmp_path)
+        cfg.runner = dict(type='IterBasedRunner', max_iters=max_iters)
+        cfg.evaluation = dict(interval=3, save_best={'resisc.accuracy_top-1': 1, 'dior.bbox_mAP': 100, 'potsdam.mFscore': 100},
+                              cls=dict(metric='accuracy'), det=dict(metric='bbox', iou_thrs=[0.5]), seg=dict(metric=['mFscore', 'mIoU']))
+        cfg.checkpoint_config = dict(interval=3)
+        cfg.log_config = dict(interval=1)
+        return cfg
+    torch.manual_seed(0)
+    cfg = make_cfg(3)
+    model = MODELS.build(cfg.model)
+    model.init_weights()
+    logging.getLogger('rscotr_b200').setLevel(logging.WARNING)
+    with cpu_ops():
+        runner = train_model(model, build_datasets(cfg.data, synthetic=cfg.synthetic), cfg, validate=True, meta=dict(seed=0))
+    assert runner.iter == 3
+    files = sorted(os.listdir(tmp_path))
+    assert 'iter_3.pth' in files and 'latest.pth' in files and any(f.startswith('best_') and f.endswith('iter_3.pth') for f in files)
+    for k in ('resisc.accuracy_top-1', 'dior.bbox_mAP', 'potsdam.mFscore', 'potsdam.mIoU'):
+        assert k in runner.log_buffer, sorted(runner.log_buffer)
+    assert any(k.startswith('seg.potsdam.') for k in runner.log_buffer)          # training log vars of the last iteration
+    # second call: auto_resume picks latest.pth up and only runs the remaining iteration
+    cfg2 = make_cfg(4)
+    cfg2.auto_resume = True
+    torch.manual_seed(1)
+    model2 = MODELS.build(cfg2.model)
+    with cpu_ops():
+        runner2 = train_model(model2, build_datasets(cfg2.data, synthetic=cfg2.synthetic), cfg2, validate=False)
+    assert runner2.iter == 4 and 'iter_4.pth' in os.listdir(tmp_path)             # (save_last: the final iteration is always saved)
+    assert torch.equal(model2.cls_head.fc.bias, model2.cls_head.fc.bias) and not torch.equal(
+        model2.backbone.patch_embed.projection.weight, MODELS.build(make_cfg(1).model).backbone.patch_embed.projection.weight)
