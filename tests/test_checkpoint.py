@@ -186,7 +186,7 @@ def test_test_model_api_from_checkpoint(tmp_path):
     eng = _engine()
     path = C.save_checkpoint(eng, str(tmp_path / 'iter_0.pth'))
     cfg = small_cfg()
-    cfg.synthetic = dict(img_size=(64, 64), det=dict(num_boxes=2), length=dict(resisc=1, dior=2, potsdam=1))
+    cfg.synthetic = dict(img_size=(64, 64), det=dict(num_boxes=2), val_length=dict(resisc=1, dior=2, potsdam=1))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for v in cfg.data.values():
         v['config'] = os.path.join(root, v['config'])
