@@ -316,6 +316,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     per_task = {}
     barrier()
+    torch.cuda.nvtx.range_push('timed_region')       # lets `ncu --nvtx --nvtx-include "timed_region/"` profile only these steps
     e0.record()
     evs = []
     for i in range(args.steps):
@@ -326,6 +327,7 @@ def main():
         b.record()
         evs.append((dev_batches[i % 6]['task'], a, b))
     e1.record()
+    torch.cuda.nvtx.range_pop()
     trace('timed region A enqueued')
     barrier()
     trace('timed region A done')
