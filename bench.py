@@ -177,6 +177,16 @@ def per_gpu_batch(cfg):
     return {n: cfg.data[n]['config']['data']['samples_per_gpu'] for n in TASK_ORDER}
 
 
+def _nvtx_range(name):
+    """push an NVTX range, return the function that pops it (a no-op pair if NVTX is unavailable)."""
+    try:
+        import torch
+        torch.cuda.nvtx.range_push(name)
+        return torch.cuda.nvtx.range_pop
+    except Exception:
+        return lambda: None
+
+
 def run_reference(args):
     """Reference arm: the CPU oracle on all host cores.  A step = one co-training iteration
     on a bounded SAMPLE (batch 1 per task); `value` extrapolates the measured per-image
@@ -316,7 +326,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     per_task = {}
     barrier()
-    torch.cuda.nvtx.range_push('timed_region')       # lets `ncu --nvtx --nvtx-include "timed_region/"` profile only these steps
+    nvtx = _nvtx_range('timed_region')               # lets `ncu --nvtx --nvtx-include "timed_region/"` profile only these steps
     e0.record()
     evs = []
     for i in range(args.steps):
@@ -327,7 +337,7 @@ def main():
         b.record()
         evs.append((dev_batches[i % 6]['task'], a, b))
     e1.record()
-    torch.cuda.nvtx.range_pop()
+    nvtx()
     trace('timed region A enqueued')
     barrier()
     trace('timed region A done')
