@@ -4,9 +4,45 @@ import time
 
 
 class _LogBuffer(dict):
+    """mmcv LogBuffer semantics (values logged every `interval` iterations are the MEANS over the iterations of the
+    window in which the key appeared) without a host sync per iteration: the packed device tensors of the steps'
+    log vars are summed on the device per key set, and read back once when the window is logged."""
+
+    def __init__(self):
+        super().__init__()
+        self._acc = {}                         # tuple(keys) -> [device sum, count, weight]
+
     def update(self, vars, count=1):
         for k, v in vars.items():
             self[k] = v
+
+    def accumulate(self, log_vars):
+        keys, packed = getattr(log_vars, '_keys', None), getattr(log_vars, '_packed', None)
+        if keys is None:                       # a plain dict of floats
+            keys, packed = list(log_vars.keys()), None
+        slot = self._acc.get(tuple(keys))
+        vals = packed.detach() if packed is not None else None
+        if slot is None:
+            self._acc[tuple(keys)] = [vals.clone() if vals is not None else [float(v) for v in log_vars.values()], 1,
+                                      getattr(log_vars, '_weight', 1)]
+        else:
+            if vals is not None:
+                slot[0] += vals
+            else:
+                slot[0] = [a + float(b) for a, b in zip(slot[0], log_vars.values())]
+            slot[1] += 1
+
+    def average(self):
+        """-> {key: mean over the window}; clears the window."""
+        out = {}
+        for keys, (total, n, weight) in self._acc.items():
+            vals = total.tolist() if hasattr(total, 'tolist') else list(total)
+            vals = vals[len(vals) - len(keys):]                # (distributed: element 0 is the log-var count check)
+            for k, v in zip(keys, vals):
+                out[k] = v * weight / n
+        self._acc.clear()
+        self.update(out)
+        return out
 
 
 class IterBasedRunner:
@@ -67,8 +103,9 @@ class IterBasedRunner:
             batch = next_batch() if self.engine.iter < self.max_iters else None
             if batch is not None:
                 self.engine.prefetch(batch)
+            self.log_buffer.accumulate(self.outputs['log_vars'])
             if self.log_interval and self.engine.iter % self.log_interval == 0:
-                self.log_buffer.update(dict(self.outputs['log_vars'].items()), self.outputs['num_samples'])
+                self.log_buffer.average()
                 if self.logger:
                     self.logger.info('iter %d  %.3fs/iter  %s', self.engine.iter,
                                      (time.time() - t0) / self.log_interval, dict(self.log_buffer))

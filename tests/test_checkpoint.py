@@ -247,3 +247,19 @@ def test_train_model_api_end_to_end(tmp_path):
     assert runner2.iter == 4 and 'iter_4.pth' in os.listdir(tmp_path)             # (save_last: the final iteration is always saved)
     assert torch.equal(model2.cls_head.fc.bias, model2.cls_head.fc.bias) and not torch.equal(
         model2.backbone.patch_embed.projection.weight, MODELS.build(make_cfg(1).model).backbone.patch_embed.projection.weight)
+
+
+def test_log_buffer_averages_over_the_window():
+    from rscotr_b200.models.mtl import _LazyLogVars
+    from rscotr_b200.mtl.runner.iter_runner import _LogBuffer
+    lb = _LogBuffer()
+    lb.accumulate(_LazyLogVars(['cls.x.loss'], torch.tensor([2.0]), 1))
+    lb.accumulate(_LazyLogVars(['seg.y.loss_ce', 'seg.y.loss'], torch.tensor([1.0, 3.0]), 0.1))
+    lb.accumulate(_LazyLogVars(['cls.x.loss'], torch.tensor([4.0]), 1))
+    lb.accumulate(dict(grad_norm=2.0))
+    avg = lb.average()
+    assert avg['cls.x.loss'] == 3.0 and avg['seg.y.loss'] == pytest.approx(0.3) and avg['grad_norm'] == 2.0
+    assert lb['cls.x.loss'] == 3.0 and lb._acc == {}
+    # distributed packing: element 0 carries the number of log vars and is not a value
+    lb.accumulate(_LazyLogVars(['a', 'b'], torch.tensor([2.0, 5.0, 7.0]), 1))
+    assert lb.average() == dict(a=5.0, b=7.0)
