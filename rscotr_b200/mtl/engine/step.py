@@ -287,7 +287,7 @@ class StepEngine:
             gB.replay()
         else:
             gA.replay()
-        st.update(gA=gA, gB=gB, ctx=ctx, static=static, outputs=outputs, launches=nA + nB)
+        st.update(gA=gA, gB=gB, ctx=ctx, static=static, outputs=outputs, launches=nA + nB, grad_norm=self.last_grad_norm)
 
     def prefetch(self, data_batch):
         """Start the host->device copy of a (pinned) host batch on the copy stream while the current step is still
@@ -384,6 +384,7 @@ class StepEngine:
                 self.model.train_step_host(st['ctx'])
                 st['gB'].replay()
         self.replayed_launches += st['launches']
+        self.last_grad_norm = st.get('grad_norm')         # (the norm tensor this signature's graph writes)
         self.iter += 1
         out = st['outputs']
         return dict(loss=out['loss'], log_vars=out['log_vars'].rebind(), num_samples=out['num_samples'])

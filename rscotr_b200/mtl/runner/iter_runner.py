@@ -45,6 +45,13 @@ class _LogBuffer(dict):
         return out
 
 
+class _GradNorm:
+    """the step's gradient norm in the (keys, packed device tensor, weight) form `_LogBuffer.accumulate` sums."""
+
+    def __init__(self, t):
+        self._keys, self._packed, self._weight = ['grad_norm'], t.detach().reshape(1).float(), 1
+
+
 class IterBasedRunner:
     def __init__(self, engine, max_iters, work_dir=None, logger=None, meta=None, log_interval=50):
         self.engine, self.model, self.optimizer = engine, engine.model, engine.optimizer
@@ -104,6 +111,9 @@ class IterBasedRunner:
             if batch is not None:
                 self.engine.prefetch(batch)
             self.log_buffer.accumulate(self.outputs['log_vars'])
+            gn = self.engine.last_grad_norm                 # mmcv OptimizerHook logs the pre-clip gradient norm
+            if gn is not None:
+                self.log_buffer.accumulate(_GradNorm(gn))
             if self.log_interval and self.engine.iter % self.log_interval == 0:
                 self.log_buffer.average()
                 if self.logger:

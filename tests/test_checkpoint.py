@@ -237,6 +237,7 @@ def test_train_model_api_end_to_end(tmp_path):
     for k in ('resisc.accuracy_top-1', 'dior.bbox_mAP', 'potsdam.mFscore', 'potsdam.mIoU'):
         assert k in runner.log_buffer, sorted(runner.log_buffer)
     assert any(k.startswith('seg.potsdam.') for k in runner.log_buffer)          # training log vars of the last iteration
+    assert runner.log_buffer['grad_norm'] > 0                                    # (mmcv OptimizerHook logs the pre-clip norm)
     # second call: auto_resume picks latest.pth up and only runs the remaining iteration
     cfg2 = make_cfg(4)
     cfg2.auto_resume = True
