@@ -25,7 +25,7 @@ optimizer = dict(type='AdamW', lr=6e-5, betas=(0.9, 0.999), weight_decay=0.01,
                  paramwise_cfg=dict(custom_keys={'absolute_pos_embed': dict(decay_mult=0.), 'relative_position_bias_table': dict(decay_mult=0.),
                                                  'norm': dict(decay_mult=0.)}))
 optimizer_config = dict()
-lr_config = dict(policy='step', step=[64000, 72000])
+lr_config = dict(policy='poly', warmup='linear', warmup_iters=1500, warmup_ratio=1e-6, power=1.0, min_lr=0.0, by_epoch=False)
 runner = dict(type='IterBasedRunner', max_iters=80000)
 checkpoint_config = dict(interval=8000)
 evaluation = dict(interval=8000, save_best={'potsdam.mFscore': 100}, seg=dict(metric=['mFscore', 'mIoU'], pre_eval=True, classwise=True))

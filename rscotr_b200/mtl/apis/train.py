@@ -26,6 +26,7 @@ def train_model(model, datasets, cfg, distributed=False, validate=False, timesta
     engine = StepEngine(model, cfg.optimizer, grad_clip=optimizer_config.get('grad_clip'), device=device,
                         compute_dtype=cfg.get('compute_dtype', torch.bfloat16 if fp16 is None else torch.float16),
                         lr_config=cfg.get('lr_config'))
+    engine.max_iters = (cfg.get('lr_config') or {}).get('max_iters', cfg.runner['max_iters'])
     runner = IterBasedRunner(engine, cfg.runner['max_iters'], work_dir=cfg.get('work_dir'), logger=logger, meta=meta,
                              log_interval=cfg.get('log_config', {}).get('interval', 50))
     runner.timestamp = timestamp

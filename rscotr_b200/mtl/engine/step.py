@@ -12,6 +12,7 @@ B200-first structure:
   * bf16 autocast for the GEMMs / kernels, fp32 master weights, fused AdamW.
   * inputs arrive in pinned host memory and are copied with non_blocking H2D.
 """
+import math
 import os
 
 import torch
@@ -86,6 +87,7 @@ class StepEngine:
         self.replayed_launches = 0       # rscotr kernels executed through graph replays
         self.graph_failures = 0
         self.lr_config = dict(lr_config) if lr_config else None
+        self.max_iters = (self.lr_config or {}).get('max_iters', 1)     # (poly / cosine horizons; train_model sets it)
         self.iter = 0
         self._task_ranges = {}
         self.last_grad_norm = None
@@ -175,21 +177,58 @@ class StepEngine:
             self._task_ranges[task] = ranges
         return self._task_ranges[task]
 
-    # -- lr schedule (mmcv StepLrUpdaterHook, by_epoch=False) --------------
+    # -- lr schedule (mmcv LrUpdaterHook family, by_epoch=False) ------------
+    def lr_scale(self, it):
+        """lr(it) / base_lr for the policies the reference's configs use (mmcv 1.6 runner/hooks/lr_updater.py):
+        'step' (gamma, step list), 'CosineAnnealing' (min_lr_ratio), 'poly' (power, min_lr = 0), 'fixed'; optional
+        'constant' / 'linear' / 'exp' warm-up over `warmup_iters` iterations starting at `warmup_ratio`.  Every
+        param group scales by the same factor, so the flat AdamW kernel needs ONE device scalar."""
+        c = self.lr_config
+        if not c:
+            return 1.0
+        policy = c.get('policy', 'fixed')
+        max_iters = c.get('max_iters', self.max_iters)
+        if policy == 'step':
+            steps = c['step']
+            steps = [steps] if isinstance(steps, int) else steps
+            scale = c.get('gamma', 0.1) ** sum(it >= s for s in steps)
+        elif policy in ('CosineAnnealing', 'cosine'):
+            if c.get('min_lr'):
+                raise NotImplementedError('CosineAnnealing with an absolute min_lr is group dependent; use min_lr_ratio')
+            r = c.get('min_lr_ratio', 0.0)
+            scale = r + 0.5 * (1 - r) * (math.cos(math.pi * it / max_iters) + 1)
+        elif policy == 'poly':
+            if c.get('min_lr'):
+                raise NotImplementedError('poly with a non-zero absolute min_lr is group dependent')
+            scale = (1 - it / max_iters) ** c.get('power', 1.0)
+        elif policy == 'fixed':
+            scale = 1.0
+        else:
+            raise KeyError('lr policy %r is not supported' % policy)
+        warm = c.get('warmup')
+        if warm and it < c.get('warmup_iters', 0):
+            ratio, n = c.get('warmup_ratio', 0.1), c['warmup_iters']
+            if warm == 'constant':
+                scale *= ratio
+            elif warm == 'linear':
+                scale *= 1 - (1 - it / n) * (1 - ratio)
+            elif warm == 'exp':
+                scale *= ratio ** (1 - it / n)
+            else:
+                raise KeyError('warmup %r is not supported' % warm)
+        return scale
+
     def _update_lr(self):
-        if not self.lr_config or self.lr_config.get('policy') != 'step':
+        if not self.lr_config:
             return
-        steps = self.lr_config['step']
-        steps = [steps] if isinstance(steps, int) else steps
-        gamma = self.lr_config.get('gamma', 0.1)
-        exp = sum(self.iter >= s for s in steps)
-        if exp == getattr(self, '_lr_exp', 0):
+        scale = self.lr_scale(self.iter)
+        if scale == getattr(self, '_lr_scale_now', 1.0):
             return
-        self._lr_exp = exp
+        self._lr_scale_now = scale
         for g, base in zip(self.optimizer.param_groups, self._base_lrs):
-            g['lr'] = base * gamma ** exp
+            g['lr'] = base * scale
         if hasattr(self.optimizer, 'set_lr_scale'):
-            self.optimizer.set_lr_scale(gamma ** exp)            # device scalar: graphs stay valid
+            self.optimizer.set_lr_scale(scale)                   # device scalar: graphs stay valid
         else:
             self._graphs.clear()                                 # lr is baked into captured launches: re-capture
 

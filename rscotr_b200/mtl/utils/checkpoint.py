@@ -219,7 +219,7 @@ def resume(engine, filename, resume_optimizer=True):
     engine.iter = int(ckpt['meta']['iter'])
     if resume_optimizer and 'optimizer' in ckpt:
         load_optimizer_state_dict(engine, ckpt['optimizer'])
-    engine._lr_exp = 0                                   # the step schedule is re-derived from engine.iter
+    engine._lr_scale_now = None                          # the schedule is re-derived from engine.iter
     return ckpt['meta']
 
 

@@ -339,3 +339,35 @@ def test_batch_augments_device_formulation():
 def np_std(v):
     import numpy as np
     return float(np.std(v))
+
+
+def test_lr_policies_match_mmcv_closed_forms():
+    import math
+    from rscotr_b200.mtl.engine import StepEngine
+    def eng(cfg, max_iters=100):
+        e = StepEngine(torch.nn.Linear(2, 2), dict(type='SGD', lr=0.5), device='cpu', compute_dtype=torch.float32, use_graphs=False,
+                       lr_config=cfg)
+        e.max_iters = max_iters
+        return e
+    e = eng(dict(policy='step', step=[10, 20], gamma=0.1))
+    assert [e.lr_scale(i) for i in (0, 9, 10, 19, 20, 99)] == pytest_approx([1, 1, .1, .1, .01, .01])
+    e = eng(dict(policy='poly', power=1.0, min_lr=0.0, warmup='linear', warmup_iters=10, warmup_ratio=1e-6))
+    assert e.lr_scale(50) == 0.5 and e.lr_scale(0) == pytest_approx(1e-6) and e.lr_scale(5) == pytest_approx(0.95 * (1 - 0.5 * (1 - 1e-6)))
+    e = eng(dict(policy='CosineAnnealing', min_lr_ratio=1e-2, warmup='exp', warmup_iters=4, warmup_ratio=0.1))
+    assert e.lr_scale(100) == pytest_approx(1e-2) and e.lr_scale(50) == pytest_approx(0.01 + 0.5 * 0.99)
+    assert e.lr_scale(2) == pytest_approx((0.01 + 0.495 * (math.cos(math.pi * 0.02) + 1)) * 0.1 ** 0.5)
+    e = eng(dict(policy='fixed', warmup='constant', warmup_iters=3, warmup_ratio=0.25))
+    assert [e.lr_scale(i) for i in range(5)] == [0.25, 0.25, 0.25, 1.0, 1.0]
+    # the engine applies it to the optimizer's groups
+    e = eng(dict(policy='step', step=[1]))
+    e.iter = 1
+    e._update_lr()
+    assert e.optimizer.param_groups[0]['lr'] == pytest_approx(0.05)
+    import pytest
+    with pytest.raises(KeyError):
+        eng(dict(policy='cyclic')).lr_scale(0)
+
+
+def pytest_approx(v):
+    import pytest
+    return pytest.approx(v, rel=1e-9, abs=1e-15)
