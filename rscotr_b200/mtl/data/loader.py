@@ -44,6 +44,11 @@ def collate(samples):
 
 def worker_init_fn(worker_id, num_workers, rank, seed):
     """mmdet/mmcls/mmseg worker_init_fn: a distinct seed per (rank, worker)."""
+    try:                                   # (mmdet setup_multi_processes: OpenCV threads off inside loader workers)
+        import cv2
+        cv2.setNumThreads(0)
+    except ImportError:
+        pass
     s = num_workers * rank + worker_id + seed
     np.random.seed(s)
     random.seed(s)
