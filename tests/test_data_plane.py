@@ -384,3 +384,25 @@ def test_worker_processes_and_seeding(resisc):
     assert a['img'].shape == (3, 3, 224, 224)
     assert torch.equal(a['gt_label'], b['gt_label']) and torch.equal(a['img'], b['img'])
     assert not torch.equal(a['img'], c['img'])
+
+
+def test_distributed_sampler_partitions_and_reshuffles():
+    from rscotr_b200.mtl.data.loader import DistributedSampler
+    data = list(range(10))
+    parts = [list(DistributedSampler(data, num_replicas=4, rank=r, shuffle=True, seed=7)) for r in range(4)]
+    assert all(len(p) == 3 for p in parts)                                   # rounded up to 12 = 4 x 3
+    flat = sorted(i for p in parts for i in p)
+    assert set(flat) == set(range(10)) and len(flat) == 12                   # every sample seen, two repeated
+    s = DistributedSampler(data, num_replicas=2, rank=0, shuffle=True, seed=7)
+    first = list(s)
+    s.set_epoch(1)
+    assert list(s) != first and sorted(list(s) + list(_other(s))) == list(range(10))
+    assert list(DistributedSampler(data, num_replicas=2, rank=1, shuffle=False)) == [1, 3, 5, 7, 9]
+    assert len(list(DistributedSampler(data, num_replicas=4, rank=3, shuffle=False, round_up=False))) == 2
+
+
+def _other(s):
+    from rscotr_b200.mtl.data.loader import DistributedSampler
+    o = DistributedSampler(list(range(s.n)), num_replicas=2, rank=1, shuffle=True, seed=s.seed)
+    o.set_epoch(s.epoch)
+    return o
