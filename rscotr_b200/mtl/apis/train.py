@@ -18,7 +18,9 @@ def train_model(model, datasets, cfg, distributed=False, validate=False, timesta
     data_loader = [build_multidataloader(cfg, distributed, datasets)]
     if distributed and not dist.is_initialized():
         dist.init_process_group(cfg.get('dist_params', {}).get('backend', 'nccl'))
-    device = 'cuda:%d' % int(os.environ.get('LOCAL_RANK', 0)) if distributed else cfg.get('device', 'cuda')
+    device = cfg.get('device', 'cuda')
+    if distributed and str(device) == 'cuda':
+        device = 'cuda:%d' % int(os.environ.get('LOCAL_RANK', 0))
     if str(device).startswith('cuda'):
         torch.cuda.set_device(device)
     optimizer_config = cfg.get('optimizer_config', {}) or {}

@@ -81,3 +81,49 @@ def test_two_rank_data_parallel_step(tmp_path):
     # the cls task only touches backbone + cls_head: one contiguous range starting at 0
     assert r0['cls']['ranges'][0][0] == 0 and len(r0['cls']['ranges']) == 1
     assert len(r0['seg']['ranges']) == 2          # backbone..shared_encoder | seg_head (bbox_head skipped)
+
+
+def _train_model_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import rscotr_b200.models  # noqa: F401
+    from rscotr_b200.config import MODELS
+    from rscotr_b200.mtl.apis import train_model
+    from rscotr_b200.mtl.data import build_datasets, load_data_cfg
+    from tests.cpu_ops_shim import cpu_ops
+    from tests.test_host_model import small_cfg
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = small_cfg()
+    for v in cfg.data.values():
+        v['config'] = os.path.join(root, v['config'])
+        v['data']['samples_per_gpu'] = 2 if v['task'] == 'cls' else 1
+    load_data_cfg(cfg)
+    cfg.synthetic = dict(img_size=(64, 64), det=dict(num_boxes=2))
+    cfg.device, cfg.compute_dtype, cfg.work_dir = 'cpu', torch.float32, os.path.join(out_dir, 'work')
+    cfg.runner = dict(type='IterBasedRunner', max_iters=3)
+    cfg.checkpoint_config = dict(interval=3)
+    cfg.log_config = dict(interval=3)
+    torch.manual_seed(0)
+    model = MODELS.build(cfg.model)
+    model.init_weights()
+    with cpu_ops():
+        runner = train_model(model, build_datasets(cfg.data, synthetic=cfg.synthetic), cfg, distributed=True, validate=False)
+    torch.save(dict(params=torch.cat([p.detach().reshape(-1) for p in model.parameters()]), logs=dict(runner.log_buffer),
+                    iter=runner.iter), os.path.join(out_dir, 'tm_rank%d.pt' % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_train_model(tmp_path):
+    """mtl.apis.train_model(distributed=True) on 2 gloo ranks: different data shards, identical replicas and logged
+    values afterwards, the checkpoint written once (rank 0)."""
+    port = _free_port()
+    mp.spawn(_train_model_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / 'tm_rank0.pt'), torch.load(tmp_path / 'tm_rank1.pt')
+    assert r0['iter'] == r1['iter'] == 3 and torch.equal(r0['params'], r1['params'])
+    assert r0['logs'].keys() == r1['logs'].keys() and any(k.startswith('seg.') for k in r0['logs'])
+    for k in r0['logs']:
+        assert abs(r0['logs'][k] - r1['logs'][k]) < 1e-6, k
+    assert sorted(os.listdir(tmp_path / 'work')) == ['iter_3.pth', 'latest.pth']
