@@ -190,6 +190,8 @@ _CLS_LOSSES = {'LabelSmoothLoss': LabelSmoothLoss, 'CrossEntropyLoss': CrossEntr
 
 @MODELS.register_module()
 class SlvlClsHead(nn.Module):
+    uses_neck = False          # reads the last backbone stage only (lets MTL skip the neck on cls iterations)
+
     def __init__(self, num_classes, in_channels, loss=dict(type='CrossEntropyLoss', loss_weight=1.0), topk=(1,),
                  cal_acc=False, init_cfg=dict(type='Normal', layer='Linear', std=0.01)):
         super().__init__()
@@ -257,6 +259,7 @@ class MlvlClsHead(SlvlClsHead):
     multi-level memory, by one of eight pooling `scheme`s (1/2: GAP of level 0/1; 3: mean over all tokens;
     4: mean of the per-level GAPs; 5/6: learned token weights on level 0/1; 7: learned weights over all tokens;
     8: learned weights over the per-level GAPs).  Levels are ordered low -> high resolution."""
+    uses_neck = True
     _FEAT_LEN = {5: (4,), 6: (7,), 7: (4, 7, 14, 28)}
 
     def __init__(self, *args, pixel_decoder=None, scheme=5, **kwargs):
@@ -315,6 +318,7 @@ MODELS.register_module()(GlobalAveragePooling)
 class LinearClsHead(SlvlClsHead):
     """mmcls LinearClsHead (reference configs/_base_/cls/swin-tiny.py:12-19): fc on the last element of the neck's
     output tuple (already pooled to (B, C))."""
+    uses_neck = True
 
     def __init__(self, *args, init_cfg=None, **kwargs):
         super().__init__(*args, **kwargs)

@@ -128,10 +128,18 @@ class MTL(nn.Module):
         assert task in supported_tasks
         return getattr(self, 'simple_test_%s' % task)(*args, **kwargs)
 
+    def _extract_feat_cls(self, img):
+        """The reference runs the neck for every task and the single-level cls head then discards its output
+        (multitask_learner.py:122 -> :84).  The neck has no buffers, so skipping it when the head does
+        not read it changes no result and no gradient."""
+        if getattr(self.cls_head, 'uses_neck', True):
+            return self.extract_feat(img)
+        return None, self.backbone(img)
+
     def forward_train_cls(self, img, gt_label, **kwargs):
         if self.cls_augments is not None:
             img, gt_label = self.cls_augments(img, gt_label)
-        neck_feature, backbone_feature = self.extract_feat(img)
+        neck_feature, backbone_feature = self._extract_feat_cls(img)
         losses = dict()
         losses.update(self.cls_head.forward_train(neck_feature, backbone_feature, gt_label, self.shared_encoder))
         return losses
@@ -152,7 +160,7 @@ class MTL(nn.Module):
         return losses
 
     def simple_test_cls(self, img, img_metas=None, **kwargs):
-        neck_feature, backbone_feature = self.extract_feat(img)
+        neck_feature, backbone_feature = self._extract_feat_cls(img)
         return self.cls_head.simple_test(neck_feature, backbone_feature, shared_encoder=self.shared_encoder, **kwargs)
 
     def simple_test_det(self, img, img_metas, rescale=False):
