@@ -326,7 +326,10 @@ class MultiheadAttention(nn.Module):
         if attn_mask is not None:          # bool, True = masked out (torch MHA convention)
             assert attn_mask.dtype == torch.bool, 'only boolean attention masks are used by the reference heads'
             mask = ~attn_mask
-            mask = mask.view(B, H, L, S) if mask.dim() == 3 else mask.view(1, 1, L, S)
+            if mask.dim() == 4:
+                pass                       # (B, 1, L, S): one mask per image, broadcast over the heads by the SDPA call
+            else:
+                mask = mask.view(B, H, L, S) if mask.dim() == 3 else mask.view(1, 1, L, S)
         if key_padding_mask is not None:
             kp = ~key_padding_mask.view(B, 1, 1, S)
             mask = kp if mask is None else mask & kp

@@ -80,6 +80,9 @@ def encode_neck_levels(self, encoder, neck_feats, batch_size, num_input_levels):
     return outs
 
 
+_COMPACT_ATTN_MASK = __import__('os').environ.get('RSC_COMPACT_ATTN_MASK') == '1'
+
+
 @MODELS.register_module()
 class MlvlSegPixelDecoder(nn.Module):
     def __init__(self, num_encoder_levels=4, in_channels=[256, 512, 1024, 2048], strides=[4, 8, 16, 32],
@@ -183,8 +186,14 @@ class Mask2FormerHead(nn.Module):
             raise NotImplementedError
         with torch.no_grad():
             attn_mask = resize(mask_pred.detach(), attn_mask_target_size)
-            attn_mask = attn_mask.flatten(2).unsqueeze(1).repeat((1, self.num_heads, 1, 1)).flatten(0, 1)
-            attn_mask = attn_mask.float().sigmoid() < 0.5
+            if _COMPACT_ATTN_MASK:
+                # opt-in (RSC_COMPACT_ATTN_MASK=1): the reference repeats the resized logits over the heads BEFORE the
+                # sigmoid / compare (8x redundant element-wise work and an 8x larger boolean mask); the decision is the same
+                # for every head, so keep one (B, 1, Q, K) mask and let the attention call broadcast it
+                attn_mask = (attn_mask.flatten(2).float().sigmoid() < 0.5).unsqueeze(1)
+            else:
+                attn_mask = attn_mask.flatten(2).unsqueeze(1).repeat((1, self.num_heads, 1, 1)).flatten(0, 1)
+                attn_mask = attn_mask.float().sigmoid() < 0.5
         return seg_mask, attn_mask
 
     def forward(self, encoder, neck_feats, backbone_feats, img_metas):

@@ -371,3 +371,30 @@ def test_lr_policies_match_mmcv_closed_forms():
 def pytest_approx(v):
     import pytest
     return pytest.approx(v, rel=1e-9, abs=1e-15)
+
+
+def test_compact_attention_mask_is_equivalent(monkeypatch):
+    """RSC_COMPACT_ATTN_MASK=1 (one (B,1,Q,K) mask broadcast over the heads) gives the same seg losses and gradients as the
+    reference's per-head (B*heads, Q, K) mask."""
+    import rscotr_b200.models.seg_head as sh
+    from rscotr_b200.config import MODELS
+    from rscotr_b200.mtl.data import build_datasets
+    from tests.cpu_ops_shim import cpu_ops
+    from tests.test_host_model import small_cfg
+    ds = build_datasets({'x': dict(task='seg')}, synthetic=dict(img_size=(64, 64)))['x']
+    batch = ds.make_batch(2, torch.Generator().manual_seed(2), pin=False)
+    batch.update(task='seg', dataset_name='x')
+    outs = []
+    for compact in (False, True):
+        monkeypatch.setattr(sh, '_COMPACT_ATTN_MASK', compact)
+        torch.manual_seed(0)
+        model = MODELS.build(small_cfg().model)
+        model.init_weights()
+        model.train()
+        with cpu_ops():
+            out = model.train_step(dict(batch), None)
+            out['loss'].backward()
+        outs.append((float(out['loss']), model.seg_head.query_feat.weight.grad.clone(),
+                     model.backbone.patch_embed.projection.weight.grad.clone()))
+    assert outs[0][0] == outs[1][0]
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-8) and torch.allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-8)
