@@ -20,6 +20,7 @@ from ..config import MODELS, build_from_cfg
 
 _CONST_CACHE = {}
 _DEFER = __import__('os').environ.get('RSC_NO_DEFER') is None     # A/B switch for the fused post-norm pairs
+_CONST_ATTN_BIAS = __import__('os').environ.get('RSC_CONST_ATTN_BIAS') == '1'
 
 
 def const_tensor(values, dtype, device):
@@ -323,7 +324,16 @@ class MultiheadAttention(nn.Module):
         k = k.reshape(S, B, H, E // H).permute(1, 2, 0, 3)
         v = v.reshape(S, B, H, E // H).permute(1, 2, 0, 3)
         mask = None
-        if attn_mask is not None:          # bool, True = masked out (torch MHA convention)
+        if attn_mask is not None and _CONST_ATTN_BIAS and key_padding_mask is None and hasattr(attn_mask, '_rsc_add'):
+            # opt-in (RSC_CONST_ATTN_BIAS=1): a shape-only constant mask (the denoising mask of the DINO decoder, the same
+            # object for all 6 layers of every step) is turned into the additive 0 / -inf bias ONCE per dtype instead of
+            # an invert + masked_fill per layer call inside the attention op
+            mask = attn_mask._rsc_add.get(q.dtype)
+            if mask is None:
+                mask = torch.zeros(attn_mask.shape, dtype=q.dtype, device=attn_mask.device).masked_fill_(attn_mask, float('-inf'))
+                attn_mask._rsc_add[q.dtype] = mask
+            mask = mask.view(B, H, L, S) if mask.dim() == 3 else mask.view(1, 1, L, S)
+        elif attn_mask is not None:          # bool, True = masked out (torch MHA convention)
             assert attn_mask.dtype == torch.bool, 'only boolean attention masks are used by the reference heads'
             mask = ~attn_mask
             if mask.dim() == 4:

@@ -356,6 +356,7 @@ class CdnQueryGenerator:
                 lo, hi = single_pad * 2 * i, single_pad * 2 * (i + 1)
                 attn_mask[lo:hi, hi:pad_size] = True
                 attn_mask[lo:hi, :lo] = True
+            attn_mask._rsc_add = {}        # (marks a shape-only constant: bricks._attend may cache its additive form)
             return dict(known_bid=known_bid, neg_add=neg_add, map_known_indice=map_known_indice, attn_mask=attn_mask)
         if not hasattr(self, '_geom'):
             self._geom = GeomCache()

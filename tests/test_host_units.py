@@ -398,3 +398,35 @@ def test_compact_attention_mask_is_equivalent(monkeypatch):
                      model.backbone.patch_embed.projection.weight.grad.clone()))
     assert outs[0][0] == outs[1][0]
     assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-8) and torch.allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-8)
+
+
+def test_constant_attention_bias_is_equivalent(monkeypatch):
+    """RSC_CONST_ATTN_BIAS=1: the DINO denoising mask as a cached additive bias gives the same det losses / gradients as the
+    boolean mask, and the cache is actually hit (the marker survives the per-attention shallow copies)."""
+    import rscotr_b200.models.bricks as br
+    from rscotr_b200.config import MODELS
+    from rscotr_b200.mtl.data import build_datasets
+    from oracle import heads as oh
+    from tests.cpu_ops_shim import cpu_ops
+    from tests.test_host_model import small_cfg
+    ds = build_datasets({'x': dict(task='det')}, synthetic=dict(img_size=(64, 64), det=dict(num_boxes=2)))['x']
+    batch = ds.make_batch(2, torch.Generator().manual_seed(2), pin=False)
+    batch.update(task='det', dataset_name='x')
+    noise = oh.cdn_noise(batch['gt_labels'], num_dn=10, generator=torch.Generator().manual_seed(5))
+    outs, caches = [], []
+    for const in (False, True):
+        monkeypatch.setattr(br, '_CONST_ATTN_BIAS', const)
+        torch.manual_seed(0)
+        model = MODELS.build(small_cfg().model)
+        model.init_weights()
+        model.train()
+        model.bbox_head.dn_generator.forced_noise = noise
+        with cpu_ops():
+            out = model.train_step(dict(batch), None)
+            out['loss'].backward()
+        outs.append((float(out['loss']), model.bbox_head.transformer.decoder.layers[0].attentions[0].attn.in_proj_weight.grad.clone()))
+        masks = [v['attn_mask'] for v in model.bbox_head.dn_generator._geom.entries.values()]
+        caches.append(sum(len(m._rsc_add) for m in masks))
+    assert outs[0][0] == __import__('pytest').approx(outs[1][0], rel=1e-6)
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-8)
+    assert masks and caches[0] == 0 and caches[1] >= 1

@@ -16,7 +16,7 @@ echo "== kbench (default switches)"
 KB_B=4 timeout 300 python tools/kbench.py 2>/dev/null | grep -E "bias_act|add_ln" | tee gpurun_out/ab_kbench_default.jsonl
 echo "== kbench (RSC_ADD_LN_LEAN=1)"
 RSC_ADD_LN_LEAN=1 KB_B=4 timeout 300 python tools/kbench.py 2>/dev/null | grep -E "add_ln" | tee gpurun_out/ab_kbench_lean.jsonl
-for sw in "" "RSC_GELU_SIG=1" "RSC_ADD_LN_LEAN=1" "RSC_COMPACT_ATTN_MASK=1" "RSC_GELU_SIG=1 RSC_ADD_LN_LEAN=1 RSC_COMPACT_ATTN_MASK=1"; do
+for sw in "" "RSC_GELU_SIG=1" "RSC_ADD_LN_LEAN=1" "RSC_COMPACT_ATTN_MASK=1" "RSC_CONST_ATTN_BIAS=1" "RSC_GELU_SIG=1 RSC_ADD_LN_LEAN=1 RSC_COMPACT_ATTN_MASK=1 RSC_CONST_ATTN_BIAS=1"; do
   tag=$(echo "${sw:-default}" | tr ' =' '__')
   echo "== bench [$sw]"
   env $sw timeout 240 python bench.py --steps 15 --warmup 6 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/ab_bench_$tag.json
