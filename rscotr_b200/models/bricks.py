@@ -8,7 +8,6 @@ Linear / LayerNorm / Conv are library GEMMs.
 """
 import copy
 import math
-import warnings
 
 import torch
 import torch.nn as nn

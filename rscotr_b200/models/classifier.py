@@ -1,7 +1,5 @@
 """Single-task image classifier of the reference's configs/cls/*.py (mmcls ImageClassifier: backbone -> neck -> head,
 batch augments from train_cfg), with the step engine's model interface (BASELINE configs[0])."""
-import torch.nn as nn
-
 from ..config import MODELS, build_from_cfg
 from .bricks import apply_init_cfg
 from .cls_head import Augments

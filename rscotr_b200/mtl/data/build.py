@@ -5,7 +5,6 @@ splice, dataset / dataloader builders, strategy registry, MultiDataLoader.
 exist, and seeded SYNTHETIC datasets of the configured shapes otherwise (this environment has no data on disk
 and no network; bench.py and the tests ask for synthetic data explicitly).  Pass `synthetic=False` to
 insist on the real data (missing files then raise)."""
-import copy
 import os
 import warnings
 
