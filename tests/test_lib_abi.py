@@ -56,3 +56,17 @@ def test_ops_refuse_cpu_tensors():
         ops.wmsa(torch.zeros(1, 49, 288), None, torch.zeros(169, 3), (7, 7), 3)
     with pytest.raises(RuntimeError, match='CUDA tensors only'):
         ops.global_avg_pool(torch.zeros(1, 4, 2, 2))
+
+
+def test_fused_entry_points_validate_arguments_without_gpu(lib):
+    """the fused element-wise / loss entry points: argument errors come back as status 1 + message, before any CUDA call."""
+    F32, BF16 = 0, 1
+    st = lib.rsc_bias_act_fwd(None, None, None, 10, 100, 0, BF16, None)            # C % 8
+    assert st == 1 and b'C % 8' in lib.rsc_last_error()
+    st = lib.rsc_bias_act_fwd(None, None, None, 10, 96, 3, BF16, None)             # unknown activation
+    assert st == 1 and b'act must be' in lib.rsc_last_error()
+    st = lib.rsc_bias_act_fwd(None, None, None, 10, 96, 2, F32, None)              # the logistic-fit GELU is bf16 only
+    assert st == 1 and b'bf16 only' in lib.rsc_last_error()
+    st = lib.rsc_bias_act_fwd(None, None, None, 10, 96, 2, BF16, None)             # accepted combination: next check is the pointers
+    assert st == 1 and b'null pointer' in lib.rsc_last_error()
+    assert lib.rsc_add_ln_supported(96) == 1 and lib.rsc_add_ln_supported(100) == 0
