@@ -406,3 +406,35 @@ def _other(s):
     o = DistributedSampler(list(range(s.n)), num_replicas=2, rank=1, shuffle=True, seed=s.seed)
     o.set_epoch(s.epoch)
     return o
+
+
+def test_geometric_transform_properties():
+    """property checks with hypothesis: horizontal flip of boxes is an involution and keeps widths; keep-ratio resize maps the
+    boxes with the image (same relative position), never leaves the image, and respects the (long, short) edge limits."""
+    hyp = pytest.importorskip('hypothesis')
+    st = pytest.importorskip('hypothesis.strategies')
+
+    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.given(h=st.integers(20, 200), w=st.integers(20, 200), seed=st.integers(0, 10 ** 6),
+               long_edge=st.integers(64, 400), short_edge=st.integers(32, 300))
+    def run(h, w, seed, long_edge, short_edge):
+        hyp.assume(long_edge >= short_edge)
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(1, 5))
+        x1, y1 = rng.uniform(0, w - 2, n), rng.uniform(0, h - 2, n)
+        boxes = np.stack([x1, y1, x1 + rng.uniform(1, w - x1), y1 + rng.uniform(1, h - y1)], 1).astype(np.float32)
+        img = np.zeros((h, w, 3), dtype=np.uint8)
+        base = dict(img=img, img_shape=img.shape, gt_bboxes=boxes.copy(), bbox_fields=['gt_bboxes'], img_fields=['img'])
+        flip = T.RandomFlip(flip_ratio=None, task='det')
+        once = flip(dict(base, flip=True, flip_direction='horizontal'))
+        twice = flip(dict(once, flip=True))
+        assert np.allclose(twice['gt_bboxes'], boxes, atol=1e-4)
+        assert np.allclose(once['gt_bboxes'][:, 2] - once['gt_bboxes'][:, 0], boxes[:, 2] - boxes[:, 0], atol=1e-4)
+        r = T.Resize(img_scale=(long_edge, short_edge), keep_ratio=True, task='det')(dict(base, gt_bboxes=boxes.copy()))
+        nh, nw = r['img'].shape[:2]
+        assert max(nh, nw) <= long_edge + 1 and min(nh, nw) <= short_edge + 1
+        assert abs(nw / w - nh / h) < 0.06 * max(nw / w, nh / h) + 2.0 / min(h, w)       # aspect kept up to pixel rounding
+        b = r['gt_bboxes']
+        assert (b[:, 0::2] >= 0).all() and (b[:, 0::2] <= nw).all() and (b[:, 1::2] >= 0).all() and (b[:, 1::2] <= nh).all()
+        assert np.allclose(b[:, 0] / nw, boxes[:, 0] / w, atol=1e-5) and np.allclose(b[:, 3] / nh, boxes[:, 3] / h, atol=1e-5)
+    run()
