@@ -137,3 +137,26 @@ def test_optimizer_param_groups():
     assert s['seg_head.query_embed.weight'][1] == 0.0 and s['seg_head.query_feat.weight'][1] == 0.0
     assert s['bbox_head.transformer.level_embeds'][1] == 0.0 and s['seg_head.level_embed.weight'][1] == 0.0
     assert s['shared_encoder.layers.0.ffns.0.layers.1.weight'] == (5e-5, 1e-4)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason='reference tree not mounted (GPU box)')
+def test_every_reference_multi_and_cls_config_builds_unmodified():
+    """drop-in at the config level: every configs/multi/**/*.py (incl. the strategy variants and the MlvlClsHead model) and
+    configs/cls/*.py of the reference loads with this repo's Config and builds through its registry, and the iteration
+    strategy each one names exists.  (configs/det and configs/seg are the reference's broken stand-alone variants, SURVEY App. B.)"""
+    import glob
+    import warnings
+    from rscotr_b200.mtl.data import strategies_map
+    paths = sorted(glob.glob('/root/reference/configs/multi/**/*.py', recursive=True)) + sorted(glob.glob('/root/reference/configs/cls/*.py'))
+    assert len(paths) >= 14
+    built = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for p in paths:
+            cfg = Config.fromfile(p)
+            if cfg.get('strategy'):
+                assert cfg.strategy['type'] in strategies_map, p
+            if cfg.get('model') is not None:
+                built[os.path.basename(p)] = type(MODELS.build(cfg.model)).__name__
+    assert built['MTL_swin-t-p4-w7_1x1_resisc&dior&potsdam.py'] == 'MTL' and built['swin-tiny_1xb16_resisc.py'] == 'ImageClassifier'
+    assert set(built.values()) == {'MTL', 'ImageClassifier'}
