@@ -365,6 +365,14 @@ def test_cotraining_and_evaluation_on_real_files(resisc, dior, potsdam, tmp_path
         assert k in logs, (k, sorted(logs))
     assert 0 <= logs['resisc.accuracy_top-1'] <= 100 and -1 <= logs['dior.bbox_mAP'] <= 1 and 0 <= logs['potsdam.mIoU'] <= 1
     assert hook.best_score is not None
+    # single-image inference through the val pipelines (tools/inference_one_img.py)
+    from rscotr_b200.mtl.apis import inference_one_img
+    with cpu_ops():
+        scores = inference_one_img(model, val_sets['resisc'], 'airport/airport_000.jpg')
+        boxes = inference_one_img(model, val_sets['dior'], '00000.png')
+        labels = inference_one_img(model, val_sets['potsdam'], 'tile_0.png')
+    assert scores.shape == (45,) and len(boxes) == 20 and boxes[0].shape[1] == 5 and labels.shape == (96, 96)
+    assert model.training                                                       # (the call restores the mode)
     best = [f for f in os.listdir(tmp_path) if f.startswith('best_')]
     assert best == ['best_resisc_accuracy_top-1_dior_bbox_mAP_potsdam_mFscore_iter_3.pth']
 
