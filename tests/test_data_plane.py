@@ -446,3 +446,23 @@ def test_geometric_transform_properties():
         assert (b[:, 0::2] >= 0).all() and (b[:, 0::2] <= nw).all() and (b[:, 1::2] >= 0).all() and (b[:, 1::2] <= nh).all()
         assert np.allclose(b[:, 0] / nw, boxes[:, 0] / w, atol=1e-5) and np.allclose(b[:, 3] / nh, boxes[:, 3] / h, atol=1e-5)
     run()
+
+
+def test_image_ops_against_independent_implementations():
+    """mmcv-style image ops (cv2) against torch / torchvision: normalisation (incl. BGR -> RGB), bilinear up-scaling with the
+    half-pixel convention, zero padding, horizontal flip."""
+    import torch.nn.functional as F
+    tvf = pytest.importorskip('torchvision.transforms.functional')
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (23, 31, 3), dtype=np.uint8)                       # BGR, HWC
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    ours = T.imnormalize(img, np.array(mean, dtype=np.float32), np.array(std, dtype=np.float32), to_rgb=True)
+    rgb = torch.from_numpy(img[..., ::-1].copy()).permute(2, 0, 1).float()
+    want = tvf.normalize(rgb, mean, std).permute(1, 2, 0).numpy()
+    assert np.allclose(ours, want, atol=1e-5)
+    up = T.imresize(img, (62, 46), 'bilinear')                                   # (w, h) = exactly 2x
+    ref = F.interpolate(torch.from_numpy(img).permute(2, 0, 1)[None].float(), size=(46, 62), mode='bilinear', align_corners=False)
+    assert np.abs(up.astype(np.float32) - ref[0].permute(1, 2, 0).numpy()).max() <= 1.0      # cv2 rounds to uint8 (fixed point)
+    pad = T.impad_to_multiple(img, 32)
+    assert pad.shape == (32, 32, 3) and (pad[23:] == 0).all() and (pad[:, 31:] == 0).all() and np.array_equal(pad[:23, :31], img)
+    assert np.array_equal(T.imflip(img), tvf.hflip(torch.from_numpy(img).permute(2, 0, 1)).permute(1, 2, 0).numpy())
