@@ -466,3 +466,22 @@ def test_image_ops_against_independent_implementations():
     pad = T.impad_to_multiple(img, 32)
     assert pad.shape == (32, 32, 3) and (pad[23:] == 0).all() and (pad[:, 31:] == 0).all() and np.array_equal(pad[:23, :31], img)
     assert np.array_equal(T.imflip(img), tvf.hflip(torch.from_numpy(img).permute(2, 0, 1)).permute(1, 2, 0).numpy())
+
+
+def test_random_resized_crop_distribution_matches_torchvision():
+    """same sampling scheme as torchvision.transforms.RandomResizedCrop.get_params (area ~ U(0.08, 1), log-uniform aspect in
+    [3/4, 4/3], 10 attempts, centre fallback): compare the first two moments of area fraction and log aspect over many draws."""
+    tvt = pytest.importorskip('torchvision.transforms')
+    img = np.zeros((120, 200, 3), dtype=np.uint8)
+    rrc = T.RandomResizedCrop(size=32)
+    random.seed(0)
+    torch.manual_seed(0)
+    ours = np.array([rrc._params(img) for _ in range(4000)], dtype=np.float64)              # (y, x, h, w)
+    ref = np.array([tvt.RandomResizedCrop.get_params(torch.zeros(3, 120, 200), (0.08, 1.0), (3 / 4, 4 / 3)) for _ in range(4000)],
+                   dtype=np.float64)                                                        # (i, j, h, w)
+    for a in (ours, ref):
+        assert (a[:, 0] >= 0).all() and (a[:, 1] >= 0).all() and (a[:, 0] + a[:, 2] <= 120).all() and (a[:, 1] + a[:, 3] <= 200).all()
+    area_o, area_r = ours[:, 2] * ours[:, 3] / (120 * 200), ref[:, 2] * ref[:, 3] / (120 * 200)
+    asp_o, asp_r = np.log(ours[:, 3] / ours[:, 2]), np.log(ref[:, 3] / ref[:, 2])
+    assert abs(area_o.mean() - area_r.mean()) < 0.02 and abs(area_o.std() - area_r.std()) < 0.02
+    assert abs(asp_o.mean() - asp_r.mean()) < 0.02 and abs(asp_o.std() - asp_r.std()) < 0.02
