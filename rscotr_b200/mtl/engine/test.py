@@ -14,6 +14,10 @@ def _run(model, loader, task, show=False, out_dir=None, pre_eval=None, **kwargs)
     dataset = loader.dataset
     reduce_seg = task == 'seg' and hasattr(dataset, 'pre_eval') and pre_eval is not False
     n = 0
+    # mmseg.apis.single_gpu_test: the dataset indices of every batch come from the loader's batch sampler (a sharded
+    # validation loader does not visit 0, 1, 2, ...); loaders without one (synthetic) are sequential
+    sampler = getattr(loader, 'batch_sampler', None)
+    index_iter = iter(sampler) if sampler is not None and not getattr(loader, 'infinite', False) else None
     for data in loader:
         data = _to_device(dict(data), device)
         data.pop('dataset_name', None)
@@ -28,8 +32,9 @@ def _run(model, loader, task, show=False, out_dir=None, pre_eval=None, **kwargs)
         with torch.no_grad():
             result = model(return_loss=False, task=task, img=img, img_metas=metas, **data)
         result = list(result) if isinstance(result, (list, tuple)) else list(result.unbind(0)) if torch.is_tensor(result) else [result]
+        indices = list(next(index_iter)) if index_iter is not None else list(range(n, n + len(result)))
         if reduce_seg:
-            result = dataset.pre_eval(result, list(range(n, n + len(result))))
+            result = dataset.pre_eval(result, indices[:len(result)])
         n += len(result)
         results.extend(result)
     return results
@@ -47,6 +52,24 @@ def single_gpu_test(model, data_loaders, show=False, out_dir=None, kwargs_dict=N
 
 
 def multi_gpu_test(model, data_loaders, tmpdir=None, gpu_collect=False, kwargs_dict=None):
-    """The reference raises NotImplementedError for distributed validation
-    (mtl/apis/train.py:100-101); each rank evaluates its own shard here."""
-    return single_gpu_test(model, data_loaders, kwargs_dict=kwargs_dict)
+    """mm{cls,det,seg}.apis.multi_gpu_test: every rank runs its shard of each validation loader (rank-strided, not
+    shuffled, padded to equal length), the per-sample results are gathered and re-interleaved into dataset order on rank 0
+    (the other ranks get None), as `collect_results_cpu/gpu` do."""
+    import torch.distributed as dist
+    results = single_gpu_test(model, data_loaders, kwargs_dict=kwargs_dict)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return results
+    world, rank = dist.get_world_size(), dist.get_rank()
+    out = {}
+    for name, part in results.items():
+        if not hasattr(data_loaders[name].dataset, '__len__'):      # synthetic loaders are per-rank streams, not shards
+            out[name] = part
+            continue
+        parts = [None] * world
+        dist.all_gather_object(parts, part)
+        if rank == 0:
+            size = len(data_loaders[name].dataset)
+            out[name] = [r for group in zip(*parts) for r in group][:size]
+        else:
+            out[name] = None
+    return out

@@ -3,7 +3,7 @@
 "{dataset}.{metric}", keep the best weighted mean of the configured keys."""
 import torch.distributed as dist
 
-from ...engine.test import single_gpu_test
+from ...engine.test import multi_gpu_test, single_gpu_test
 
 
 class KeyIndicator:
@@ -30,7 +30,7 @@ class MultiDatasetsEvalHook:
                  **eval_kwargs):
         self.dataloaders, self.start, self.interval, self.by_epoch = dataloaders, start, interval, by_epoch
         self.save_best = dict(save_best) if isinstance(save_best, dict) else save_best
-        self.test_fn = test_fn or single_gpu_test
+        self.test_fn = test_fn          # default: single process -> single_gpu_test; distributed -> multi_gpu_test (rank 0 evaluates)
         self.eval_kwargs = eval_kwargs
         self.best_score = None
         self.best_ckpt_path = None
@@ -41,7 +41,12 @@ class MultiDatasetsEvalHook:
             return
         if self.start is not None and runner.iter < self.start:
             return
-        results = self.test_fn(runner.model, self.dataloaders)
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        test_fn = self.test_fn or (multi_gpu_test if distributed else single_gpu_test)
+        results = test_fn(runner.model, self.dataloaders)
+        if any(v is None for v in results.values()):       # (gathered on rank 0: the other ranks only helped to compute)
+            runner.model.train()
+            return
         score = self.evaluate(runner, results)
         if score is not None and (self.best_score is None or score > self.best_score):
             self.best_score = score

@@ -127,3 +127,66 @@ def test_two_rank_train_model(tmp_path):
     for k in r0['logs']:
         assert abs(r0['logs'][k] - r1['logs'][k]) < 1e-6, k
     assert sorted(os.listdir(tmp_path / 'work')) == ['iter_3.pth', 'latest.pth']
+
+
+def _eval_worker(rank, world, port, out_dir, resisc, potsdam):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    if world > 1:
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import rscotr_b200.models  # noqa: F401
+    from rscotr_b200.config import Config, MODELS
+    from rscotr_b200.mtl.data.datasets import build_dataset
+    from rscotr_b200.mtl.data.loader import build_dataloader
+    from rscotr_b200.mtl.engine.test import multi_gpu_test
+    from tests.cpu_ops_shim import cpu_ops
+    from tests.test_host_model import small_cfg
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def shrink(pipeline, **over):
+        out = []
+        for t in pipeline:
+            t = dict(t)
+            if t['type'] in over:
+                t.update(over[t['type']])
+            if 'transforms' in t:
+                t['transforms'] = shrink(t['transforms'], **over)
+            out.append(t)
+        return out
+    c = dict(Config.fromfile(os.path.join(root, 'configs/datasets/resisc45.py'))._cfg_dict['data']['val'])
+    c.update(data_prefix=os.path.join(resisc, 'val'), pipeline=shrink(c['pipeline'], Resize=dict(size=(64, 64))))
+    s = dict(Config.fromfile(os.path.join(root, 'configs/datasets/potsdam.py'))._cfg_dict['data']['val'])
+    s.update(data_root=potsdam, pipeline=shrink(s['pipeline'], MultiScaleFlipAug=dict(img_scale=(64, 64))))
+    sets = dict(resisc=build_dataset(c, 'cls', dict(test_mode=True)), potsdam=build_dataset(s, 'seg', dict(test_mode=True)))
+    loaders = {k: build_dataloader(v, samples_per_gpu=2, workers_per_gpu=0, dist=world > 1, shuffle=False) for k, v in sets.items()}
+    torch.manual_seed(0)
+    model = MODELS.build(small_cfg().model)
+    model.init_weights()
+    with cpu_ops():
+        res = multi_gpu_test(model, loaders)
+    if rank == 0:
+        metrics = dict(resisc=sets['resisc'].evaluate(res['resisc'], metric='accuracy'),
+                       potsdam=sets['potsdam'].evaluate(res['potsdam'], metric=['mIoU', 'mFscore']))
+        torch.save(dict(n={k: len(v) for k, v in res.items()}, scores=[r.tolist() for r in res['resisc']], metrics=metrics),
+                   os.path.join(out_dir, 'eval_world%d.pt' % world))
+    else:
+        assert all(v is None for v in res.values())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_evaluation_equals_single_process(tmp_path):
+    """multi_gpu_test: shards by rank, gathers and re-interleaves the per-sample results on rank 0 -- same results and
+    metrics as one process over the whole validation sets (12 images / 3 tiles: the padded duplicate is trimmed)."""
+    from tests import data_fixtures as FX
+    resisc, potsdam = FX.make_resisc(str(tmp_path / 'resisc')), FX.make_potsdam(str(tmp_path / 'potsdam'))
+    _eval_worker(0, 1, 0, str(tmp_path), resisc, potsdam)
+    mp.spawn(_eval_worker, args=(2, _free_port(), str(tmp_path), resisc, potsdam), nprocs=2, join=True)
+    one, two = torch.load(tmp_path / 'eval_world1.pt', weights_only=False), torch.load(tmp_path / 'eval_world2.pt', weights_only=False)
+    assert one['n'] == two['n'] == dict(resisc=12, potsdam=3)
+    assert torch.allclose(torch.tensor(one['scores']), torch.tensor(two['scores']), atol=1e-6)
+    assert one['metrics']['resisc'] == two['metrics']['resisc']
+    for k, v in one['metrics']['potsdam'].items():
+        assert v == pytest.approx(two['metrics']['potsdam'][k], nan_ok=True), k
