@@ -24,9 +24,12 @@ def train_model(model, datasets, cfg, distributed=False, validate=False, timesta
     if str(device).startswith('cuda'):
         torch.cuda.set_device(device)
     optimizer_config = cfg.get('optimizer_config', {}) or {}
-    fp16 = cfg.get('fp16', None)
+    if cfg.get('fp16', None) is not None:
+        # the reference's Fp16OptimizerHook (fp16 + dynamic loss scaling); on B200 the mixed-precision type is bf16, which has
+        # fp32's exponent range and needs no loss scaling
+        logger.warning('cfg.fp16 is set: running bf16 mixed precision (no loss scaling needed) instead of fp16')
     engine = StepEngine(model, cfg.optimizer, grad_clip=optimizer_config.get('grad_clip'), device=device,
-                        compute_dtype=cfg.get('compute_dtype', torch.bfloat16 if fp16 is None else torch.float16),
+                        compute_dtype=cfg.get('compute_dtype', torch.bfloat16),
                         lr_config=cfg.get('lr_config'))
     engine.max_iters = (cfg.get('lr_config') or {}).get('max_iters', cfg.runner['max_iters'])
     runner = IterBasedRunner(engine, cfg.runner['max_iters'], work_dir=cfg.get('work_dir'), logger=logger, meta=meta,
