@@ -45,6 +45,11 @@ class _LogBuffer(dict):
         return out
 
 
+def dist_rank():
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
 class _GradNorm:
     """the step's gradient norm in the (keys, packed device tensor, weight) form `_LogBuffer.accumulate` sums."""
 
@@ -91,6 +96,27 @@ class IterBasedRunner:
             self.logger.info('resumed from %s, iter %d', checkpoint, self.iter)
         return meta
 
+    def _write_json_log(self, sec_per_iter):
+        """mmcv TextLoggerHook's `<timestamp>.log.json`: one JSON object per log interval (mode, iter, lr, memory in MB,
+        time per iteration, the window means of the log vars) -- the format the mm* analysis tools read."""
+        if not self.work_dir:
+            return
+        if dist_rank() != 0:
+            return
+        import json
+        import os
+        import torch
+        os.makedirs(self.work_dir, exist_ok=True)
+        lrs = sorted({round(float(g['lr']), 12) for g in self.optimizer.param_groups})
+        rec = dict(mode='train', epoch=1, iter=int(self.engine.iter), lr=lrs[-1] if lrs else None,
+                   memory=int(torch.cuda.max_memory_allocated() // (1 << 20)) if torch.cuda.is_available() else 0,
+                   time=round(float(sec_per_iter), 5))
+        rec.update({k: (round(v, 5) if isinstance(v, float) else v) for k, v in self.log_buffer.items()
+                    if isinstance(v, (int, float))})
+        name = '%s.log.json' % (getattr(self, 'timestamp', None) or 'train')
+        with open(os.path.join(self.work_dir, name), 'a') as f:
+            f.write(json.dumps(rec) + '\n')
+
     def run(self, data_loaders, workflow=(('train', 1),), **kwargs):
         loader = data_loaders[0]
         state = dict(it=iter(loader))
@@ -116,6 +142,7 @@ class IterBasedRunner:
                 self.log_buffer.accumulate(_GradNorm(gn))
             if self.log_interval and self.engine.iter % self.log_interval == 0:
                 self.log_buffer.average()
+                self._write_json_log((time.time() - t0) / self.log_interval)
                 if self.logger:
                     self.logger.info('iter %d  %.3fs/iter  %s', self.engine.iter,
                                      (time.time() - t0) / self.log_interval, dict(self.log_buffer))

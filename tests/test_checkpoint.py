@@ -238,6 +238,9 @@ def test_train_model_api_end_to_end(tmp_path):
         assert k in runner.log_buffer, sorted(runner.log_buffer)
     assert any(k.startswith('seg.potsdam.') for k in runner.log_buffer)          # training log vars of the last iteration
     assert runner.log_buffer['grad_norm'] > 0                                    # (mmcv OptimizerHook logs the pre-clip norm)
+    import json
+    recs = [json.loads(l) for l in open(tmp_path / 'train.log.json')]
+    assert [r['iter'] for r in recs] == [1, 2, 3] and recs[0]['mode'] == 'train' and 'cls.resisc.loss' in recs[0] and recs[-1]['lr'] > 0
     # second call: auto_resume picks latest.pth up and only runs the remaining iteration
     cfg2 = make_cfg(4)
     cfg2.auto_resume = True

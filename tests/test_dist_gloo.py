@@ -126,7 +126,7 @@ def test_two_rank_train_model(tmp_path):
     assert r0['logs'].keys() == r1['logs'].keys() and any(k.startswith('seg.') for k in r0['logs'])
     for k in r0['logs']:
         assert abs(r0['logs'][k] - r1['logs'][k]) < 1e-6, k
-    assert sorted(os.listdir(tmp_path / 'work')) == ['iter_3.pth', 'latest.pth']
+    assert sorted(os.listdir(tmp_path / 'work')) == ['iter_3.pth', 'latest.pth', 'train.log.json']          # written by rank 0 only
 
 
 def _eval_worker(rank, world, port, out_dir, resisc, potsdam):
