@@ -422,7 +422,7 @@ def test_geometric_transform_properties():
     hyp = pytest.importorskip('hypothesis')
     st = pytest.importorskip('hypothesis.strategies')
 
-    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.settings(max_examples=60, deadline=None, derandomize=True, database=None)
     @hyp.given(h=st.integers(20, 200), w=st.integers(20, 200), seed=st.integers(0, 10 ** 6),
                long_edge=st.integers(64, 400), short_edge=st.integers(32, 300))
     def run(h, w, seed, long_edge, short_edge):
