@@ -147,6 +147,67 @@ def test_wmsa_bf16_fwd_bwd(B, H, W, shift, heads):
         assert_rel(p[k].grad, sdo[k].grad, 3e-2, 'd' + k)
 
 
+# Geometries at which every CTA of the tcgen05 kernels walks MANY (window, head) units (the persistent loop with its
+# prefetch, buffer flip, phase carry and the cross-unit bias-gradient accumulation): the T800 stage-0..3 maps
+# (200->203, 100->105, 50->56, 25->28 padded) at their head counts.  40 368 units at (16,200,200,3) is the bench
+# launch; (1,200,200,3) = 2 523 units on <= 888 CTAs already loops, (2,100,100,3) = 1 350, (2,50,50,12) = 1 536,
+# (4,25,25,24) = 1 536.
+PERSISTENT_GEOMS = [(2, 100, 100, 3), (1, 200, 200, 3), (2, 50, 50, 12), (4, 25, 25, 24), (3, 100, 100, 6)]
+
+
+@pytest.mark.parametrize('B,H,W,heads', PERSISTENT_GEOMS)
+@pytest.mark.parametrize('shift', [0, 3])
+def test_wmsa_bf16_persistent_loop_vs_oracle(B, H, W, heads, shift):
+    """The production (bf16 tensor-core) window attention at BASELINE stage geometries: forward and ALL gradients
+    (dx through dqkv, d(qkv weight / bias), d(bias table), d(proj)) against the CPU oracle."""
+    C = heads * 32
+    sd = {k: v.bfloat16().float() for k, v in _msa_state(C, heads, seed=11 + heads).items()}
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, H * W, C, generator=g).bfloat16().float()
+    gy = torch.randn(B, H * W, C, generator=g).bfloat16().float()
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    yo = osw.shift_window_msa(sdo, 'attn.', xo, (H, W), heads, 7, shift)
+    yo.backward(gy)
+    xg, p, y = _run_msa_gpu(sd, x, (H, W), heads, shift, torch.bfloat16)
+    y.backward(gy.cuda().bfloat16())
+    assert_rel(y, yo, 2e-2, 'out')
+    assert_rel(xg.grad, xo.grad, 3e-2, 'dx')
+    for k in sd:
+        assert_rel(p[k].grad, sdo[k].grad, 3e-2, 'd' + k)
+
+
+@pytest.mark.parametrize('B,H,W,heads', [(1, 200, 200, 3), (2, 50, 50, 12)])
+@pytest.mark.parametrize('shift', [0, 3])
+def test_wmsa_bf16_core_tight(B, H, W, heads, shift):
+    """The attention core alone (no GEMMs around it) against the oracle core evaluated in fp32 on the same
+    bf16-rounded q|k|v: only the kernel's own roundings (P and the outputs to bf16) remain -> 1e-2 of the output
+    norm and elementwise |err| <= 3 bf16 ulps of the largest output."""
+    ops = _ops()
+    C = heads * 32
+    g = torch.Generator().manual_seed(13)
+    qkv = torch.randn(B, H * W, 3 * C, generator=g).bfloat16()
+    bias = (torch.randn(3 * C, generator=g) * 0.5)
+    table = torch.randn(169, heads, generator=g)
+    gy = torch.randn(B, H * W, C, generator=g).bfloat16()
+    qo = qkv.float().clone().requires_grad_(True)
+    bo = bias.clone().requires_grad_(True)
+    to = table.clone().requires_grad_(True)
+    want = osw.wmsa_core(qo, bo, to, (H, W), heads, 7, shift)
+    want.backward(gy.float())
+    qg = qkv.cuda().requires_grad_(True)
+    bg = bias.cuda().requires_grad_(True)
+    tg = table.cuda().requires_grad_(True)
+    got = ops.wmsa(qg, bg, tg, (H, W), heads, 7, shift)
+    got.backward(gy.cuda())
+    assert_rel(got, want, 1e-2, 'out')
+    assert (got.float().cpu() - want).abs().max() <= 3 * 2 ** -8 * want.abs().max()
+    assert_rel(qg.grad, qo.grad, 1.5e-2, 'dqkv')
+    assert_rel(tg.grad, to.grad, 1.5e-2, 'd table')
+    if H % 7 or W % 7:
+        assert_rel(bg.grad, bo.grad, 2e-2, 'd qkv bias (padded rows)')
+
+
 def test_wmsa_large_property():
     """BASELINE size (stage 0 of 800^2: 200x200, C=96): shifting the INPUT by one
     whole window (7 tokens) along W on a window-aligned grid permutes windows, so
@@ -246,6 +307,74 @@ def test_msda_fwd_bwd(B, Nq, heads, shapes, P, dtype):
     assert_rel(vg.grad, vo.grad, tol, 'dvalue')
     assert_rel(lg.grad, lo.grad, tol, 'dloc')
     assert_rel(wg.grad, wo.grad, tol, 'dweight')
+
+
+MSDA_T800 = [(100, 100), (50, 50), (25, 25), (13, 13)]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_msda_encoder_shape_vs_oracle(dtype):
+    """mmcv-signature op at the BASELINE encoder shape (B=2, Nq = Nv = 13 294, 8 heads, 4 levels x 4 points):
+    values and all three gradients against the oracle's grid_sample restatement."""
+    ops = _ops()
+    value, loc, w, ss, st = _msda_inputs(2, 13294, 8, MSDA_T800, 4, seed=21, spread=0.1)
+    if dtype == torch.bfloat16:
+        value = value.bfloat16().float()
+    vo, lo, wo = (t.clone().requires_grad_(True) for t in (value, loc, w))
+    yo = otr.ms_deform_attn_core(vo, MSDA_T800, lo, wo)
+    g = torch.Generator().manual_seed(3)
+    gy = torch.randn(yo.shape, generator=g)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    yo.backward(gy)
+    vg = value.clone().cuda().to(dtype).requires_grad_(True)
+    lg, wg = loc.clone().cuda().requires_grad_(True), w.clone().cuda().requires_grad_(True)
+    y = ops.ms_deform_attn(vg, ss.cuda(), st.cuda(), lg, wg, 64)
+    y.backward(gy.cuda().to(dtype))
+    tol = 1e-3 if dtype == torch.float32 else 1.5e-2
+    assert_rel(y, yo, tol, 'out')
+    assert_rel(vg.grad, vo.grad, tol, 'dvalue')
+    assert_rel(lg.grad, lo.grad, tol, 'dloc')
+    assert_rel(wg.grad, wo.grad, tol, 'dweight')
+
+
+@pytest.mark.parametrize('Nq,ref_dim', [(13294, 2), (792, 4)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_msda_fused_t800_shapes_vs_oracle(Nq, ref_dim, dtype):
+    """The fused module tail (softmax + sampling locations + op) at the BASELINE encoder shape (13 294 queries,
+    2-d reference points) and decoder shape (792 queries = 600 + 192 denoising, 4-d reference boxes), B = 2."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(17 + ref_dim)
+    shapes = MSDA_T800
+    B, heads, L, P = 2, 8, 4, 4
+    Nv = sum(h * w for h, w in shapes)
+    value = torch.randn(B, Nv, heads, 32, generator=g).to(dtype)
+    offsets = (torch.randn(B, Nq, heads, L, P, 2, generator=g) * 3).to(dtype)
+    logits = torch.randn(B, Nq, heads, L * P, generator=g).to(dtype)
+    ref = torch.rand(B, Nq, L, ref_dim, generator=g)
+    if ref_dim == 4:
+        ref[..., 2:] = ref[..., 2:] * 0.5 + 0.05
+    wout = torch.randn(B, Nq, heads * 32, generator=g)
+    rv, ro, rl = (t.float().clone().requires_grad_(True) for t in (value, offsets, logits))
+    aw = rl.softmax(-1).view(B, Nq, heads, L, P)
+    if ref_dim == 2:
+        norm = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32)
+        loc = ref[:, :, None, :, None, :] + ro / norm[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None, :, None, :2] + ro / P * ref[:, :, None, :, None, 2:] * 0.5
+    want = otr.ms_deform_attn_core(rv, shapes, loc, aw)
+    (want * wout).sum().backward()
+    gv, go, gl = (t.detach().cuda().requires_grad_(True) for t in (value, offsets, logits))
+    ss = torch.tensor(shapes).cuda()
+    st = torch.tensor([0] + list(torch.tensor([h * w for h, w in shapes]).cumsum(0)[:-1])).cuda()
+    assert ops.msda_fused_supported(gv, go, ref.cuda())
+    got = ops.ms_deform_attn_fused(gv, ss, st, go, gl, ref.cuda())
+    (got.float() * wout.cuda()).sum().backward()
+    f32 = dtype == torch.float32
+    assert_rel(got, want, 1e-4 if f32 else 6e-3, 'out')
+    assert_rel(gv.grad, rv.grad, 1e-3 if f32 else 1e-2, 'd value')
+    assert_rel(go.grad, ro.grad, 1e-3 if f32 else 1.5e-2, 'd offsets')
+    assert_rel(gl.grad, rl.grad, 1e-3 if f32 else 1.5e-2, 'd logits')
 
 
 def test_msda_full_size_linearity():
