@@ -296,6 +296,9 @@ extern "C" int rsc_wmsa_fwd_simt(const void *qkv, const float *qkv_bias, const f
                                  int H, int W, int C, int heads, int ws, int shift, float scale, int dtype,
                                  void *stream);
 
+int rsc_wmsa_fwd_tma(const void *qkv, const float *qkv_bias, const float *bias_table, void *out, int B, int H, int W, int C,
+                     int heads, int shift, float scale, void *stream);
+
 extern "C" int rsc_wmsa_fwd(const void *qkv, const float *qkv_bias, const float *bias_table, void *out, int B, int H,
                             int W, int C, int heads, int ws, int shift, float scale, int dtype, void *stream) {
   static const bool force_simt = getenv("RSC_WMSA_SIMT") != nullptr;
@@ -303,6 +306,11 @@ extern "C" int rsc_wmsa_fwd(const void *qkv, const float *qkv_bias, const float 
                      B > 0 && H > 0 && W > 0 && qkv && bias_table && out && heads <= 6 * kNumSMs;
   if (!tc_ok || force_simt)  // fp32 (exact-arithmetic parity path) and argument errors go through the SIMT entry
     return rsc_wmsa_fwd_simt(qkv, qkv_bias, bias_table, out, B, H, W, C, heads, ws, shift, scale, dtype, stream);
+  static const bool v3 = getenv("RSC_WMSA_V3") != nullptr;   // the round-1 cp.async kernel (kept for A/B runs)
+  if (!v3) {
+    const int rc = rsc_wmsa_fwd_tma(qkv, qkv_bias, bias_table, out, B, H, W, C, heads, shift, scale, stream);
+    if (rc >= 0) return rc;
+  }
   WinGeom g(B, H, W, ws, shift);
   const int num_items = B * g.nWh * g.nWw * heads;
   auto kern = wtc::wmsa_fwd_tc_kernel;

@@ -1,0 +1,484 @@
+// Fused (shifted-)window attention, bf16, TMA-staged (round-2 kernels; tools/wmsa_probe.cu pins every layout used here).
+//
+// Unit = one (window, head): 49 tokens x 32 dims.  The window is staged as a 56-SLOT tile
+//     slot s = half*28 + i*4 + jj      (i = window row 0..6, window column j = half*4 + jj, jj = 0..3)
+// of 64-byte rows (32 bf16), so that TWO TMA boxes of (32 channels, 4 tokens, 7 rows) fetch one operand of one unit
+// straight from the natural (B,H,W,3C) activation: no per-thread gathers, no address arithmetic, out-of-bounds
+// tokens (the zero padding mmdet applies after norm1) arrive as zeros.  Column j = 7 (slot jj = 3 of half 1) is a
+// neighbour's token: it is loaded but never a valid key / query.  Windows of a shifted block that wrap around the
+// rolled map use (4 rows) + (3 rows) boxes per half (two more tensor maps).  TMA writes the tiles with
+// SWIZZLE_64B; the same bytes are read by tcgen05.mma as K-major operands (S = Q K^T, dP = dO V^T) and as
+// MN-major B operands (O = P V, dV = P^T dO, dK = dS^T Q, dQ = dS K).
+//
+// Slot 56 of the K / V tiles (never written by TMA) holds the k / v slice of the qkv BIAS = the k / v row of every
+// zero-padded token: S[:,56] = q . b_k and dP[:,56] = dO . b_v come out of the same MMAs, the softmax reads column
+// 56 in place of every padded key, P[:,56] / dS[:,56] carry the row sums over the padded keys, and row 56 of
+// dV / dK is the gradient that reaches the qkv bias through the padded rows.
+//
+// CTA = 64 threads (thread = slot = query row = TMEM lane), persistent over the units of ONE head, 8 (forward) /
+// 4 (backward) CTAs per SM; thread 0 also drives TMA (two-stage ring, prefetch distance one unit) and issues the
+// MMAs.  Relative-position bias of the thread's row lives in 49 registers.  HBM-bound: SURVEY 8d.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace rsc {
+namespace wtm {
+
+using namespace tc;
+
+constexpr int WS = 7, NT = 49, HD = 32;
+constexpr int THREADS = 64;
+constexpr uint32_t TILE = 4096;   // 64 slots x 64 bytes
+constexpr uint32_t HALF = 1792;   // 28 slots
+constexpr int PADSLOT = 56;       // (backward) column of P / dS that carries the row sums over the padded keys
+constexpr float LOG2E = 1.4426950408889634f;
+
+// n-th valid key (0..48) -> slot, and slot -> (window row, window column)
+__host__ __device__ constexpr int kslot(int n) { return n < 28 ? n : 28 + ((n - 28) / 3) * 4 + (n - 28) % 3; }
+__host__ __device__ constexpr int slot_r(int s) { return (s % 28) / 4; }
+__host__ __device__ constexpr int slot_c(int s) { return (s / 28) * 4 + s % 4; }
+__host__ __device__ constexpr bool slot_ok(int s) { return s < 56 && slot_c(s) < WS; }
+// slot -> index among the valid keys (only for valid slots)
+__host__ __device__ constexpr int kidx(int s) { return s < 28 ? s : 28 + ((s - 28) / 4) * 3 + (s - 28) % 4; }
+
+// P / dS tile (64 query slots x 64 key slots), no-swizzle core matrices: 16-byte chunk kc (8 keys) of row r
+__device__ __forceinline__ uint32_t p_off(int r, int kc) { return kc * 1024 + (r >> 3) * 128 + (r & 7) * 16; }
+
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t saddr) {   // rows of 64 B, 8-row groups 512 B apart
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;   // SWIZZLE_64B
+  return d;
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void st_shared16(uint32_t dst, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// window walk: (b, wh, ww) advanced by a constant number of windows per trip, no divisions in the loop
+struct WinPos {
+  int b, wh, ww;
+};
+struct WinStep {
+  int db, dwh, dww;
+};
+__device__ __forceinline__ void advance(WinPos &p, const WinStep &s, const WinGeom &g) {
+  p.ww += s.dww;
+  if (p.ww >= g.nWw) p.ww -= g.nWw, ++p.wh;
+  p.wh += s.dwh;
+  if (p.wh >= g.nWh) p.wh -= g.nWh, ++p.b;
+  p.b += s.db;
+}
+
+// one operand tile of one unit: channels [c0, c0+32) of window (b, wh, ww)
+__device__ __forceinline__ void tma_window(uint32_t dst, uint64_t *bar, const CUtensorMap *m7, const CUtensorMap *m4,
+                                           const CUtensorMap *m3, const WinGeom &g, const WinPos &p, int c0) {
+  const int hs = p.wh * WS + g.shift, ws0 = p.ww * WS + g.shift;
+  const int w1 = ws0 + WS > g.Wp ? 0 : ws0 + 4;   // wrap in w: columns 4..6 come from w = 0..2
+  if (hs + WS > g.Hp) {                            // wrap in h: rows 0..3 <- Hp-4.., rows 4..6 <- 0..2
+    tma_load_4d(dst, m4, bar, c0, ws0, hs, p.b);
+    tma_load_4d(dst + HALF, m4, bar, c0, w1, hs, p.b);
+    tma_load_4d(dst + 1024, m3, bar, c0, ws0, 0, p.b);
+    tma_load_4d(dst + HALF + 1024, m3, bar, c0, w1, 0, p.b);
+  } else {
+    tma_load_4d(dst, m7, bar, c0, ws0, hs, p.b);
+    tma_load_4d(dst + HALF, m7, bar, c0, w1, hs, p.b);
+  }
+}
+
+// shift-mask region bits of query (ri, ci) in window p: bit j of rowbits / colbits = key row / column j lies in
+// another region (only the last window row / column of a shifted block has two regions)
+__device__ __forceinline__ void mask_bits(const WinGeom &g, const WinPos &p, int ri, int ci, uint32_t &rowbits,
+                                          uint32_t &colbits) {
+  rowbits = colbits = 0;
+  if (g.shift == 0) return;
+  const bool lr = p.wh == g.nWh - 1, lc = p.ww == g.nWw - 1;
+  const int rh_i = lr ? (ri < WS - g.shift ? 1 : 2) : 0, rw_i = lc ? (ci < WS - g.shift ? 1 : 2) : 0;
+#pragma unroll
+  for (int j = 0; j < WS; ++j) {
+    const int rj = j < WS - g.shift ? 1 : 2;
+    rowbits |= (uint32_t)((lr ? rj : 0) != rh_i) << j;
+    colbits |= (uint32_t)((lc ? rj : 0) != rw_i) << j;
+  }
+}
+// bit j of rowpad / colpad = window row / column j is zero padding
+__device__ __forceinline__ void pad_bits(const WinGeom &g, const WinPos &p, uint32_t &rowpad, uint32_t &colpad) {
+  rowpad = colpad = 0;
+  if (g.Hp == g.H && g.Wp == g.W) return;
+#pragma unroll
+  for (int j = 0; j < WS; ++j) {
+    int hh = p.wh * WS + j + g.shift, wc = p.ww * WS + j + g.shift;
+    if (hh >= g.Hp) hh -= g.Hp;
+    if (wc >= g.Wp) wc -= g.Wp;
+    rowpad |= (uint32_t)(hh >= g.H) << j;
+    colpad |= (uint32_t)(wc >= g.W) << j;
+  }
+}
+
+// Score of key slot c of this thread's row in the exp2 domain: S[c] * scale2 + bias (+ shift mask); `sv` = the
+// accumulator value of column c; msk bit n = the n-th valid key lies in another shift region (-100 in the reference).
+// MASK only in the last window row / column of a shifted block.
+template <bool MASK>
+__device__ __forceinline__ float score(int c, uint32_t sv, const float (&bj)[NT], float scale2, uint64_t msk) {
+  float v = fmaf(__uint_as_float(sv), scale2, bj[kidx(c)]);
+  if (MASK) {
+    if ((msk >> kidx(c)) & 1ull) v += -100.0f * LOG2E;
+  }
+  return v;
+}
+// 49-bit key mask from the 7-bit row / column masks
+__device__ __forceinline__ uint64_t key_mask(uint32_t rowbits, uint32_t colbits) {
+  uint64_t m = 0;
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+    m |= (uint64_t)(((rowbits >> slot_r(kslot(n))) | (colbits >> slot_c(kslot(n)))) & 1u) << n;
+  return m;
+}
+// running maximum over the valid keys of one 32-column half (HALF_ID 0: slots 0..31, 1: slots 32..63)
+template <bool MASK, int HALF_ID>
+__device__ __forceinline__ float half_max(const uint32_t (&x)[32], const float (&bj)[NT], float scale2, uint64_t msk, float m) {
+  float m1 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int c = HALF_ID * 32 + k;
+    if (slot_ok(c)) {
+      const float v = score<MASK>(c, x[k], bj, scale2, msk);
+      if (k & 1) m1 = fmaxf(m1, v);
+      else m = fmaxf(m, v);
+    }
+  }
+  return fmaxf(m, m1);
+}
+// softmax numerators of one half as 16 packed bf16 words (key slots 2w, 2w+1), straight into the P tile row;
+// accumulates the row sum l
+template <bool MASK, int HALF_ID>
+__device__ __forceinline__ void half_probs(const uint32_t (&x)[32], const float (&bj)[NT], float scale2, uint64_t msk, float m,
+                                           bool row_ok, float &l, uint32_t prow) {
+  float l1 = 0.f;
+  uint32_t pk[16];
+#pragma unroll
+  for (int w = 0; w < 16; ++w) {
+    const int c0 = HALF_ID * 32 + 2 * w, c1 = c0 + 1;
+    float p0 = 0.f, p1 = 0.f;
+    if (slot_ok(c0)) {
+      p0 = ex2(score<MASK>(c0, x[2 * w], bj, scale2, msk) - m);
+      l += p0;
+    }
+    if (slot_ok(c1)) {
+      p1 = ex2(score<MASK>(c1, x[2 * w + 1], bj, scale2, msk) - m);
+      l1 += p1;
+    }
+    pk[w] = row_ok ? pack_bf16(p0, p1) : 0u;
+  }
+  l += l1;
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc)
+    st_shared16(prow + (HALF_ID * 4 + kc) * 1024, make_uint4(pk[4 * kc], pk[4 * kc + 1], pk[4 * kc + 2], pk[4 * kc + 3]));
+}
+
+// Softmax of this thread's row: accumulator row at TMEM address taddr (64 columns) -> bf16 numerators in the P tile
+// row at shared address prow; returns the row sum.  Executed by all 32 lanes of the warp (tcgen05.ld is
+// warp-collective); rows that are not real queries write zeros.  The row is read from TMEM half a row at a time,
+// once for the maximum and once more for the exponentials: 32 accumulator + 49 bias registers live instead of
+// 64 + 49 + 49 (the budget is 128 registers at 8 CTAs / SM).
+template <bool MASK>
+__device__ __forceinline__ float softmax_row(uint32_t taddr, const float (&bj)[NT], float scale2, uint64_t msk, bool row_ok,
+                                             uint32_t prow) {
+  uint32_t x[32];
+  tmem_ld32(taddr + 32, x);
+  tmem_ld_wait();
+  float m = half_max<MASK, 1>(x, bj, scale2, msk, -INFINITY);
+  tmem_ld32(taddr, x);
+  tmem_ld_wait();
+  m = half_max<MASK, 0>(x, bj, scale2, msk, m);
+  float l = 0.f;
+  tmem_ld32(taddr, x);   // (a fresh copy: keeps the first-pass scores from being held in registers)
+  tmem_ld_wait();
+  half_probs<MASK, 0>(x, bj, scale2, msk, m, row_ok, l, prow);
+  tmem_ld32(taddr + 32, x);
+  tmem_ld_wait();
+  half_probs<MASK, 1>(x, bj, scale2, msk, m, row_ok, l, prow);
+  return l;
+}
+
+// ---- forward ------------------------------------------------------------------------------------------------
+// smem: [Q0 | K0 | Q1 | K1 | V0 | V1 | k,v bias rows | barriers].  The P tile (8 KB) overwrites Q | K of its own stage
+// once S is in TMEM.  Every M = 128 over-read (8 KB behind Q, 16 KB behind P) stays inside the tiles; rows 64..127
+// of D are never read.
+constexpr uint32_t F_QK = 2 * TILE;                 // Q | K of one stage (= its P tile)
+constexpr uint32_t F_V0 = 2 * F_QK;
+constexpr uint32_t F_BIAS = F_V0 + 2 * TILE;        // 24 KB of tiles, then 2 x 64 bytes: k / v bias of this head (bf16)
+constexpr uint32_t F_BAR = F_BIAS + 128;
+constexpr uint32_t F_TOTAL = F_BAR + 64;            // -> 8 CTAs / SM (8 x 64 TMEM columns = all 512)
+constexpr int F_TMEM = 64;
+
+// A zero-padded token's k / v row is the qkv bias (mmdet pads after norm1): the thread that owns a padded slot
+// overwrites the zeros TMA delivered (swizzled 16-byte chunks of row `slot`).
+__device__ __forceinline__ void fix_padded_row(uint32_t tile, uint32_t bias_row, int slot) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(bias_row + c * 16));
+    st_shared16(tile + slot * 64 + ((c ^ ((slot >> 1) & 3)) * 16), v);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 8)
+    wmsa_fwd_tma_kernel(const __grid_constant__ CUtensorMap m7, const __grid_constant__ CUtensorMap m4,
+                        const __grid_constant__ CUtensorMap m3, const float *__restrict__ qkv_bias,
+                        const float *__restrict__ table, __nv_bfloat16 *__restrict__ out, WinGeom g, int C, int heads,
+                        float scale, int num_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + F_BAR);   // full[0], full[1]
+  uint64_t &mbar = full[2];
+  uint32_t &tmem_base_s = *reinterpret_cast<uint32_t *>(smem + F_BAR + 32);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t sb = smem_u32(smem);
+  if (sb & 1023u) __trap();   // the swizzled tiles need the 1024-byte alignment the declaration asks for
+  const int head = blockIdx.x % heads;   // gridDim.x is a multiple of heads: the head is fixed per CTA
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, F_TMEM);
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(&mbar, 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < (int)F_BAR / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (qkv_bias && tid < 8) {   // k (tid 0..3) and v (4..7) bias slices of this head, bf16
+    const float *src = qkv_bias + (1 + (tid >> 2)) * C + head * HD + (tid & 3) * 8;
+    const float4 f0 = __ldg(reinterpret_cast<const float4 *>(src)), f1 = __ldg(reinterpret_cast<const float4 *>(src + 4));
+    st_shared16(sb + F_BIAS + tid * 16,
+                make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w)));
+  }
+  // this thread's query slot and its 49 relative-position biases (exp2 domain)
+  const bool row_ok = slot_ok(tid);
+  const int ri = slot_r(tid), ci = slot_c(tid);
+  float bj[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const int c = kslot(n);
+    const int idx = (ri - slot_r(c) + WS - 1) * (2 * WS - 1) + (ci - slot_c(c) + WS - 1);
+    bj[n] = row_ok ? __ldg(table + idx * heads + head) * LOG2E : 0.f;
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = tmem_base_s;
+  const uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
+  const uint32_t idesc_o = make_idesc_bf16(128, 32, false, true);
+  const float scale2 = scale * LOG2E;
+  const bool any_pad = g.Hp != g.H || g.Wp != g.W;
+  uint32_t phase = 0;
+
+  // window walk
+  const int wstep = gridDim.x / heads;
+  WinStep st;
+  st.dww = wstep % g.nWw;
+  st.dwh = (wstep / g.nWw) % g.nWh;
+  st.db = wstep / (g.nWw * g.nWh);
+  WinPos cur;
+  {
+    const int win = blockIdx.x / heads;
+    cur.ww = win % g.nWw;
+    cur.wh = (win / g.nWw) % g.nWh;
+    cur.b = win / (g.nWw * g.nWh);
+  }
+  const int step = gridDim.x;
+  int item = blockIdx.x;
+  WinPos pf = cur;   // (thread 0) window of the next unit to prefetch
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (item + s * step < num_items) {
+        mbar_expect_tx(&full[s], 6 * HALF);
+#pragma unroll
+        for (int part = 0; part < 3; ++part)
+          tma_window(sb + (part < 2 ? s * F_QK + part * TILE : F_V0 + s * TILE), &full[s], &m7, &m4, &m3, g, pf,
+                     part * C + head * HD);
+      }
+      advance(pf, st, g);
+    }
+  }
+
+  for (int it = 0; item < num_items; ++it, item += step) {
+    const int buf = it & 1;
+    const uint32_t in = sb + buf * F_QK, inV = sb + F_V0 + buf * TILE;   // Q | K (later P) and V of this stage
+    // geometry of this thread's token
+    int h = cur.wh * WS + ri + g.shift, w = cur.ww * WS + ci + g.shift;
+    if (h >= g.Hp) h -= g.Hp;
+    if (w >= g.Wp) w -= g.Wp;
+    const bool tok_ok = row_ok && h < g.H && w < g.W;
+    const bool rim = cur.wh == g.nWh - 1 || cur.ww == g.nWw - 1;   // CTA-uniform
+    // does the window hold zero-padded tokens?  (its last un-wrapped source row / column reaches the padding; with
+    // pad + shift > 7 that already happens in the second-to-last window row / column)
+    const bool has_pad = any_pad && (min(cur.wh * WS + WS - 1 + g.shift, g.Hp - 1) >= g.H ||
+                                     min(cur.ww * WS + WS - 1 + g.shift, g.Wp - 1) >= g.W);
+    if (has_pad) {   // padded keys of this window: zeros -> bias rows, before the MMAs read the tiles
+      mbar_wait(&full[buf], (it >> 1) & 1);
+      if (row_ok && !tok_ok) {
+        fix_padded_row(in + TILE, sb + F_BIAS, tid);
+        fix_padded_row(inV, sb + F_BIAS + 64, tid);
+      }
+      fence_async_smem();
+    }
+    // (the TMEM reads of the previous unit are ordered before this unit's MMAs)
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      mbar_wait(&full[buf], (it >> 1) & 1);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)   // K = 32 channels: +32 bytes inside the swizzled 64-byte rows
+        mma_bf16_ss(tm, desc_sw64(in + k * 32), desc_sw64(in + TILE + k * 32), idesc_s, k > 0);
+      mma_commit(&mbar);
+    }
+    uint64_t msk = 0;
+    const bool masked = rim && g.shift > 0;
+    if (masked) {
+      uint32_t rowbits, colbits;
+      mask_bits(g, cur, ri, ci, rowbits, colbits);
+      msk = key_mask(rowbits, colbits);
+    }
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    // ---- softmax on this thread's row; P goes where Q | K were ----
+    float inv_l;
+    {
+      const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16), prow = in + p_off(tid, 0);
+      const float l = masked ? softmax_row<true>(taddr, bj, scale2, msk, row_ok, prow)
+                             : softmax_row<false>(taddr, bj, scale2, 0ull, row_ok, prow);
+      inv_l = 1.0f / l;
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- O = P V (overwrites S columns 0..31) ----
+    if (tid == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)   // K = 64 key slots, 16 per step
+        mma_bf16_ss(tm, make_smem_desc(in + k * 2048, 1024, 128), desc_sw64(inV + k * 1024), idesc_o, k > 0);
+      mma_commit(&mbar);
+    }
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    uint32_t o[32];
+    tmem_ld32(tm + ((uint32_t)(warp * 32) << 16), o);
+    // the stage is free again: refill it with the unit after next
+    if (tid == 0) {
+      if (item + 2 * step < num_items) {
+        mbar_expect_tx(&full[buf], 6 * HALF);
+#pragma unroll
+        for (int part = 0; part < 3; ++part)
+          tma_window(part < 2 ? in + part * TILE : inV, &full[buf], &m7, &m4, &m3, g, pf, part * C + head * HD);
+      }
+      advance(pf, st, g);
+    }
+    tmem_ld_wait();
+    // ---- normalise and store this thread's output row ----
+    if (tok_ok) {
+      __nv_bfloat16 *dst = out + (((int64_t)cur.b * g.H + h) * g.W + w) * C + head * HD;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 v;
+        v.x = pack_bf16(__uint_as_float(o[8 * c + 0]) * inv_l, __uint_as_float(o[8 * c + 1]) * inv_l);
+        v.y = pack_bf16(__uint_as_float(o[8 * c + 2]) * inv_l, __uint_as_float(o[8 * c + 3]) * inv_l);
+        v.z = pack_bf16(__uint_as_float(o[8 * c + 4]) * inv_l, __uint_as_float(o[8 * c + 5]) * inv_l);
+        v.w = pack_bf16(__uint_as_float(o[8 * c + 6]) * inv_l, __uint_as_float(o[8 * c + 7]) * inv_l);
+        *reinterpret_cast<uint4 *>(dst + 8 * c) = v;
+      }
+    }
+    advance(cur, st, g);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, F_TMEM);
+}
+
+// ---- host side: tensor maps ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiled get_encode() {
+  static EncodeTiled fn = []() -> EncodeTiled {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiled)p;
+  }();
+  return fn;
+}
+
+// maps over a (B, H, W, ch) bf16 tensor with boxes (32 channels, 4 tokens, rows, 1)
+static bool window_maps(const void *base, int B, int H, int W, int ch, CUtensorMap *m7, CUtensorMap *m4, CUtensorMap *m3) {
+  EncodeTiled enc = get_encode();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)ch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)ch * 2, (cuuint64_t)W * ch * 2, (cuuint64_t)H * W * ch * 2};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap *maps[3] = {m7, m4, m3};
+  const cuuint32_t rows[3] = {7, 4, 3};
+  for (int i = 0; i < 3; ++i) {
+    const cuuint32_t box[4] = {HD, 4, rows[i], 1};
+    if (enc(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
+}
+
+}  // namespace wtm
+}  // namespace rsc
+
+using namespace rsc;
+
+// returns RSC_OK, or -1 when the TMA path does not apply (caller falls back to the cp.async kernel)
+int rsc_wmsa_fwd_tma(const void *qkv, const float *qkv_bias, const float *bias_table, void *out, int B, int H, int W, int C,
+                     int heads, int shift, float scale, void *stream) {
+  if (((uintptr_t)qkv & 15) || heads > 8 * kNumSMs) return -1;
+  WinGeom g(B, H, W, wtm::WS, shift);
+  CUtensorMap m7, m4, m3;
+  if (!wtm::window_maps(qkv, B, H, W, 3 * C, &m7, &m4, &m3)) return -1;
+  const int num_items = B * g.nWh * g.nWw * heads;
+  auto kern = wtm::wmsa_fwd_tma_kernel;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wtm::F_TOTAL);
+  int grid = (kNumSMs * 8) / heads * heads;   // a multiple of heads: every CTA keeps one head
+  if (grid > num_items) grid = num_items;     // num_items is a multiple of heads
+  kern<<<grid, wtm::THREADS, wtm::F_TOTAL, (cudaStream_t)stream>>>(m7, m4, m3, qkv_bias, bias_table, (__nv_bfloat16 *)out, g, C,
+                                                                   heads, scale, num_items);
+  RSC_CHECK_LAUNCH("rsc_wmsa_fwd(tma)");
+  return RSC_OK;
+}
