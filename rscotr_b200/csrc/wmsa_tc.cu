@@ -593,6 +593,10 @@ extern "C" int rsc_wmsa_bwd_simt(const void *qkv, const float *qkv_bias, const f
                                  void *dqkv, float *dbias_table, float *dqkv_bias, int B, int H, int W, int C,
                                  int heads, int ws, int shift, float scale, int dtype, void *stream);
 
+int rsc_wmsa_bwd_tma(const void *qkv, const float *qkv_bias, const float *bias_table, const void *dout, void *dqkv,
+                     float *dbias_table, float *dqkv_bias, int B, int H, int W, int C, int heads, int shift, float scale,
+                     void *stream);
+
 extern "C" int rsc_wmsa_bwd(const void *qkv, const float *qkv_bias, const float *bias_table, const void *dout,
                             void *dqkv, float *dbias_table, float *dqkv_bias, int B, int H, int W, int C, int heads,
                             int ws, int shift, float scale, int dtype, void *stream) {
@@ -603,6 +607,12 @@ extern "C" int rsc_wmsa_bwd(const void *qkv, const float *qkv_bias, const float 
   if (!tc_ok || force_simt)
     return rsc_wmsa_bwd_simt(qkv, qkv_bias, bias_table, dout, dqkv, dbias_table, dqkv_bias, B, H, W, C, heads, ws,
                              shift, scale, dtype, stream);
+  static const bool v3 = getenv("RSC_WMSA_V3") != nullptr;   // the round-1 cp.async kernel (kept for A/B runs)
+  if (!v3) {
+    const int rc = rsc_wmsa_bwd_tma(qkv, qkv_bias, bias_table, dout, dqkv, dbias_table, dqkv_bias, B, H, W, C, heads, shift,
+                                    scale, stream);
+    if (rc >= 0) return rc;
+  }
   WinGeom g(B, H, W, ws, shift);
   const int num_items = B * g.nWh * g.nWw * heads;
   auto kern = wtc::wmsa_bwd_tc_kernel;

@@ -424,6 +424,370 @@ __global__ void __launch_bounds__(THREADS, 8)
   if (warp == 0) tmem_dealloc(tm, F_TMEM);
 }
 
+// ---- backward -----------------------------------------------------------------------------------------------
+// Per unit, two MMA groups around the SIMT softmax backward (S is recomputed):
+//   S  = Q K^T (TMEM cols 0..63)          dP = dO V^T (cols 64..127)
+//   -- SIMT: P = softmax(scale*S + bias + mask), D = sum_j P*dP, dS' = scale * P*(dP - D); P and dS' rows -> smem --
+//   dV = P^T dO (cols 0..31), dK = dS'^T Q (32..63)   (A = the P / dS' tile read MN-major, K = 64 query slots)
+//   dQ = dS' K  (cols 64..95)                          (A = dS' K-major, K = 64 key slots)
+// d(bias table) accumulates per thread in 49 registers across the persistent loop (in units of `scale`) and is
+// folded once per CTA.  Windows with zero-padded tokens: the padded key rows of K / V are set to the qkv bias before
+// the MMAs, column 56 of P / dS' carries the row sums over the padded keys, and row 56 of dV / dK is then the
+// gradient that reaches the k / v bias through the padded rows (summed by the tensor core).
+// smem: [P 8 KB | dS 8 KB | stage 0: dO Q K V | stage 1 | k,v bias rows | padded-row sums | barriers]; every
+// M = 128 over-read (8 KB behind P / dS / dO / Q) lands in the tile that follows.
+constexpr uint32_t B_P = 0;
+constexpr uint32_t B_DS = 8192;
+constexpr uint32_t B_IN0 = 16384;
+constexpr uint32_t B_STAGE = 4 * TILE;              // dO | Q | K | V of one unit
+constexpr uint32_t B_BIAS = B_IN0 + 2 * B_STAGE;    // 48 KB of tiles, then 2 x 64 bytes of bias rows
+constexpr uint32_t B_PADACC = B_BIAS + 128;         // 64 floats: d(k bias), d(v bias) of this head from padded rows
+constexpr uint32_t B_BAR = B_PADACC + 256;
+constexpr uint32_t B_TOTAL = B_BAR + 64;            // ~48.5 KB -> 4 CTAs / SM (4 x 128 TMEM columns = all 512)
+constexpr int B_TMEM = 128;
+
+// scores of one 32-column half of the row -> t[n] (exp2 domain), running maximum
+template <bool RIM, int HALF_ID>
+__device__ __forceinline__ float half_scores(const uint32_t (&x)[32], const float (&bj)[NT], float scale2, uint64_t msk,
+                                             float (&t)[NT], float m) {
+  float m1 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int c = HALF_ID * 32 + k;
+    if (slot_ok(c)) {
+      const float v = score<RIM>(c, x[k], bj, scale2, msk);
+      t[kidx(c)] = v;
+      if (k & 1) m1 = fmaxf(m1, v);
+      else m = fmaxf(m, v);
+    }
+  }
+  return fmaxf(m, m1);
+}
+// one row of a P / dS tile: values v[n] of the valid keys, `pad` in slot 56, zeros elsewhere
+__device__ __forceinline__ void store_row(uint32_t row_addr, const float (&v)[NT], float pad, bool row_ok) {
+#pragma unroll
+  for (int kc = 0; kc < 8; ++kc) {
+    uint32_t w4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = kc * 8 + 2 * j, c1 = c0 + 1;
+      const float v0 = slot_ok(c0) ? v[kidx(c0)] : (c0 == PADSLOT ? pad : 0.f);
+      const float v1 = slot_ok(c1) ? v[kidx(c1)] : 0.f;
+      w4[j] = row_ok ? pack_bf16(v0, v1) : 0u;
+    }
+    st_shared16(row_addr + kc * 1024, make_uint4(w4[0], w4[1], w4[2], w4[3]));
+  }
+}
+
+// Softmax backward of this thread's row.  S at TMEM taddr (64 cols), dP at taddr + 64.  Writes the P and dS' rows,
+// accumulates the bias-table gradient.  pad = 49-bit mask of the zero-padded keys, msk = of the shift-masked keys.
+template <bool RIM>
+__device__ __forceinline__ void softmax_bwd_row(uint32_t taddr, const float (&bj)[NT], float scale2, float scale, uint64_t msk,
+                                                uint64_t pad, bool row_ok, uint32_t prow, uint32_t dsrow, float (&dbacc)[NT]) {
+  float p[NT];
+  uint32_t x[32];
+  tmem_ld32(taddr, x);
+  tmem_ld_wait();
+  float m = half_scores<RIM, 0>(x, bj, scale2, msk, p, -INFINITY);
+  tmem_ld32(taddr + 32, x);
+  tmem_ld_wait();
+  m = half_scores<RIM, 1>(x, bj, scale2, msk, p, m);
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    p[n] = ex2(p[n] - m);
+    if ((n & 3) == 0) l0 += p[n];
+    else if ((n & 3) == 1) l1 += p[n];
+    else if ((n & 3) == 2) l2 += p[n];
+    else l3 += p[n];
+  }
+  const float inv_l = 1.0f / ((l0 + l1) + (l2 + l3));
+  float wp = 0.f;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    p[n] *= inv_l;
+    if (RIM) {
+      if ((pad >> n) & 1ull) wp += p[n];
+    }
+  }
+  store_row(prow, p, wp, row_ok);
+  // D = sum_j P * dP
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+  tmem_ld32(taddr + 64, x);
+  tmem_ld_wait();
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int c = k;
+    if (slot_ok(c)) {
+      const float dp = __uint_as_float(x[k]);
+      if ((k & 3) == 0) d0 = fmaf(p[kidx(c)], dp, d0);
+      else if ((k & 3) == 1) d1 = fmaf(p[kidx(c)], dp, d1);
+      else if ((k & 3) == 2) d2 = fmaf(p[kidx(c)], dp, d2);
+      else d3 = fmaf(p[kidx(c)], dp, d3);
+    }
+  }
+  uint32_t y[32];
+  tmem_ld32(taddr + 96, y);
+  tmem_ld_wait();
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int c = 32 + k;
+    if (slot_ok(c)) {
+      const float dp = __uint_as_float(y[k]);
+      if ((k & 3) == 0) d0 = fmaf(p[kidx(c)], dp, d0);
+      else if ((k & 3) == 1) d1 = fmaf(p[kidx(c)], dp, d1);
+      else if ((k & 3) == 2) d2 = fmaf(p[kidx(c)], dp, d2);
+      else d3 = fmaf(p[kidx(c)], dp, d3);
+    }
+  }
+  const float nDs = -((d0 + d1) + (d2 + d3)) * scale;
+  // dS' = scale * P * (dP - D), in place of p
+  float wds = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int c = k;
+    if (slot_ok(c)) {
+      const int n = kidx(c);
+      const float ds = p[n] * fmaf(__uint_as_float(x[k]), scale, nDs);
+      if (row_ok) dbacc[n] += ds;
+      p[n] = ds;
+      if (RIM) {
+        if ((pad >> n) & 1ull) wds += ds;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int c = 32 + k;
+    if (slot_ok(c)) {
+      const int n = kidx(c);
+      const float ds = p[n] * fmaf(__uint_as_float(y[k]), scale, nDs);
+      if (row_ok) dbacc[n] += ds;
+      p[n] = ds;
+      if (RIM) {
+        if ((pad >> n) & 1ull) wds += ds;
+      }
+    }
+  }
+  store_row(dsrow, p, wds, row_ok);
+}
+
+__global__ void __launch_bounds__(THREADS, 4)
+    wmsa_bwd_tma_kernel(const __grid_constant__ CUtensorMap m7, const __grid_constant__ CUtensorMap m4,
+                        const __grid_constant__ CUtensorMap m3, const __grid_constant__ CUtensorMap d7,
+                        const __grid_constant__ CUtensorMap d4, const __grid_constant__ CUtensorMap d3,
+                        const float *__restrict__ qkv_bias, const float *__restrict__ table, __nv_bfloat16 *__restrict__ dqkv,
+                        float *__restrict__ dtable, float *__restrict__ dqkv_bias, WinGeom g, int C, int heads, float scale,
+                        int num_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + B_BAR);   // full[0], full[1]
+  uint64_t &mbar = full[2];
+  uint32_t &tmem_base_s = *reinterpret_cast<uint32_t *>(smem + B_BAR + 32);
+  float *padacc = reinterpret_cast<float *>(smem + B_PADACC);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t sb = smem_u32(smem);
+  if (sb & 1023u) __trap();
+  const int head = blockIdx.x % heads;   // gridDim.x is a multiple of heads
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, B_TMEM);
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(&mbar, 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < (int)B_BAR / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (qkv_bias && tid < 8) {   // k (tid 0..3) and v (4..7) bias slices of this head, bf16
+    const float *src = qkv_bias + (1 + (tid >> 2)) * C + head * HD + (tid & 3) * 8;
+    const float4 f0 = __ldg(reinterpret_cast<const float4 *>(src)), f1 = __ldg(reinterpret_cast<const float4 *>(src + 4));
+    st_shared16(sb + B_BIAS + tid * 16,
+                make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w)));
+  }
+  const bool row_ok = slot_ok(tid);
+  const int ri = slot_r(tid), ci = slot_c(tid);
+  float bj[NT], dbacc[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const int c = kslot(n);
+    const int idx = (ri - slot_r(c) + WS - 1) * (2 * WS - 1) + (ci - slot_c(c) + WS - 1);
+    bj[n] = row_ok ? __ldg(table + idx * heads + head) * LOG2E : 0.f;
+    dbacc[n] = 0.f;
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = tmem_base_s;
+  const uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
+  const uint32_t idesc_t = make_idesc_bf16(128, 32, true, true);    // A^T (MN-major) x MN-major B
+  const uint32_t idesc_q = make_idesc_bf16(128, 32, false, true);   // K-major A x MN-major B
+  const float scale2 = scale * LOG2E;
+  const bool any_pad = g.Hp != g.H || g.Wp != g.W;
+  uint32_t phase = 0;
+
+  const int wstep = gridDim.x / heads;
+  WinStep st;
+  st.dww = wstep % g.nWw;
+  st.dwh = (wstep / g.nWw) % g.nWh;
+  st.db = wstep / (g.nWw * g.nWh);
+  WinPos cur;
+  {
+    const int win = blockIdx.x / heads;
+    cur.ww = win % g.nWw;
+    cur.wh = (win / g.nWw) % g.nWh;
+    cur.b = win / (g.nWw * g.nWh);
+  }
+  const int step = gridDim.x;
+  int item = blockIdx.x;
+  WinPos pf = cur;
+  auto load_unit = [&](int s) {   // thread 0: the four operand tiles of the unit at `pf` into stage s
+    const uint32_t base = sb + B_IN0 + s * B_STAGE;
+    mbar_expect_tx(&full[s], 8 * HALF);
+    tma_window(base, &full[s], &d7, &d4, &d3, g, pf, head * HD);
+#pragma unroll
+    for (int part = 0; part < 3; ++part)
+      tma_window(base + (1 + part) * TILE, &full[s], &m7, &m4, &m3, g, pf, part * C + head * HD);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (item + s * step < num_items) load_unit(s);
+      advance(pf, st, g);
+    }
+  }
+
+  for (int it = 0; item < num_items; ++it, item += step) {
+    const int buf = it & 1;
+    const uint32_t in = sb + B_IN0 + buf * B_STAGE;
+    const uint32_t inDO = in, inQ = in + TILE, inK = in + 2 * TILE, inV = in + 3 * TILE;
+    int h = cur.wh * WS + ri + g.shift, w = cur.ww * WS + ci + g.shift;
+    if (h >= g.Hp) h -= g.Hp;
+    if (w >= g.Wp) w -= g.Wp;
+    const bool tok_ok = row_ok && h < g.H && w < g.W;
+    const bool rim = cur.wh == g.nWh - 1 || cur.ww == g.nWw - 1;   // CTA-uniform
+    const bool has_pad = any_pad && (min(cur.wh * WS + WS - 1 + g.shift, g.Hp - 1) >= g.H ||
+                                     min(cur.ww * WS + WS - 1 + g.shift, g.Wp - 1) >= g.W);
+    if (has_pad) {   // padded keys: zeros -> bias rows
+      mbar_wait(&full[buf], (it >> 1) & 1);
+      if (row_ok && !tok_ok) {
+        fix_padded_row(inK, sb + B_BIAS, tid);
+        fix_padded_row(inV, sb + B_BIAS + 64, tid);
+      }
+      fence_async_smem();
+    }
+    fence_before_sync();
+    __syncthreads();
+    // ---------------- S = Q K^T (cols 0..63), dP = dO V^T (cols 64..127) ----------------
+    if (tid == 0) {
+      fence_after_sync();
+      mbar_wait(&full[buf], (it >> 1) & 1);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) mma_bf16_ss(tm, desc_sw64(inQ + k * 32), desc_sw64(inK + k * 32), idesc_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) mma_bf16_ss(tm + 64, desc_sw64(inDO + k * 32), desc_sw64(inV + k * 32), idesc_s, k > 0);
+      mma_commit(&mbar);
+    }
+    uint64_t msk = 0, pad = 0;
+    const bool slow = has_pad || (rim && g.shift > 0);
+    if (slow) {
+      uint32_t rowbits, colbits;
+      mask_bits(g, cur, ri, ci, rowbits, colbits);
+      if (rim) msk = key_mask(rowbits, colbits);
+      pad_bits(g, cur, rowbits, colbits);
+      pad = key_mask(rowbits, colbits);
+    }
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    // ---------------- softmax backward on this thread's row ----------------
+    {
+      const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16);
+      const uint32_t prow = sb + B_P + p_off(tid, 0), dsrow = sb + B_DS + p_off(tid, 0);
+      if (slow) softmax_bwd_row<true>(taddr, bj, scale2, scale, msk, pad, row_ok, prow, dsrow, dbacc);
+      else softmax_bwd_row<false>(taddr, bj, scale2, scale, 0ull, 0ull, row_ok, prow, dsrow, dbacc);
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---------------- dV = P^T dO (cols 0..31), dK = dS'^T Q (32..63), dQ = dS' K (64..95) ----------------
+    if (tid == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)   // K = 64 query slots, 16 per step
+        mma_bf16_ss(tm, make_smem_desc(sb + B_P + k * 256, 128, 1024), desc_sw64(inDO + k * 1024), idesc_t, k > 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        mma_bf16_ss(tm + 32, make_smem_desc(sb + B_DS + k * 256, 128, 1024), desc_sw64(inQ + k * 1024), idesc_t, k > 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)   // K = 64 key slots, 16 per step
+        mma_bf16_ss(tm + 64, make_smem_desc(sb + B_DS + k * 2048, 1024, 128), desc_sw64(inK + k * 1024), idesc_q, k > 0);
+      mma_commit(&mbar);
+    }
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    // the stage is free again: refill it with the unit after next
+    if (tid == 0) {
+      if (item + 2 * step < num_items) load_unit(buf);
+      advance(pf, st, g);
+    }
+    // ---------------- store dv | dk | dq of this thread's token ----------------
+    {
+      const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16);
+      __nv_bfloat16 *dst = dqkv + (((int64_t)cur.b * g.H + h) * g.W + w) * (3 * C) + head * HD;
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {   // TMEM columns: dV 0, dK 32, dQ 64 -> dqkv parts 2, 1, 0
+        uint32_t o[32];
+        tmem_ld32(taddr + part * 32, o);
+        tmem_ld_wait();
+        const int qpart = 2 - part;
+        if (tok_ok) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(o[8 * c + 0]), __uint_as_float(o[8 * c + 1]));
+            v.y = pack_bf16(__uint_as_float(o[8 * c + 2]), __uint_as_float(o[8 * c + 3]));
+            v.z = pack_bf16(__uint_as_float(o[8 * c + 4]), __uint_as_float(o[8 * c + 5]));
+            v.w = pack_bf16(__uint_as_float(o[8 * c + 6]), __uint_as_float(o[8 * c + 7]));
+            *reinterpret_cast<uint4 *>(dst + qpart * C + 8 * c) = v;
+          }
+        } else if (tid == PADSLOT && part < 2 && has_pad) {
+          // row 56 = sum over this window's padded keys (only this thread touches padacc: no atomics)
+#pragma unroll
+          for (int d = 0; d < 32; ++d) padacc[(1 - part) * 32 + d] += __uint_as_float(o[d]);
+        }
+      }
+    }
+    advance(cur, st, g);
+  }
+  fence_before_sync();
+  __syncthreads();
+  // ---------------- fold the bias-table gradient: registers -> [slot][key] matrix -> 169 table entries ----------------
+  float *mat = reinterpret_cast<float *>(smem);   // 64 x 49 floats over the (now idle) P / dS tiles
+  if (row_ok) {
+#pragma unroll
+    for (int n = 0; n < NT; ++n) mat[tid * NT + n] = dbacc[n];
+  }
+  __syncthreads();
+  const float inv_scale = 1.0f / scale;
+  for (int k = tid; k < (2 * WS - 1) * (2 * WS - 1); k += THREADS) {
+    const int dr = k / (2 * WS - 1) - (WS - 1), dc = k % (2 * WS - 1) - (WS - 1);   // query - key offsets
+    float acc = 0.f;
+    for (int qr = max(0, dr); qr < min(WS, WS + dr); ++qr)
+      for (int qc = max(0, dc); qc < min(WS, WS + dc); ++qc) {
+        const int kr = qr - dr, kc = qc - dc;
+        const int qs = (qc >> 2) * 28 + qr * 4 + (qc & 3), ks = (kc >> 2) * 28 + kr * 4 + (kc & 3);
+        acc += mat[qs * NT + kidx(ks)];
+      }
+    atomicAdd(dtable + k * heads + head, acc * inv_scale);
+  }
+  if (dqkv_bias && any_pad && tid < 64) {
+    const float v = padacc[tid];   // [0,32): k part, [32,64): v part
+    if (v != 0.f) atomicAdd(dqkv_bias + (1 + (tid >> 5)) * C + head * HD + (tid & 31), v);
+  }
+  if (warp == 0) tmem_dealloc(tm, B_TMEM);
+}
+
 // ---- host side: tensor maps ----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -480,5 +844,24 @@ int rsc_wmsa_fwd_tma(const void *qkv, const float *qkv_bias, const float *bias_t
   kern<<<grid, wtm::THREADS, wtm::F_TOTAL, (cudaStream_t)stream>>>(m7, m4, m3, qkv_bias, bias_table, (__nv_bfloat16 *)out, g, C,
                                                                    heads, scale, num_items);
   RSC_CHECK_LAUNCH("rsc_wmsa_fwd(tma)");
+  return RSC_OK;
+}
+
+int rsc_wmsa_bwd_tma(const void *qkv, const float *qkv_bias, const float *bias_table, const void *dout, void *dqkv,
+                     float *dbias_table, float *dqkv_bias, int B, int H, int W, int C, int heads, int shift, float scale,
+                     void *stream) {
+  if (((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) || heads > 4 * kNumSMs) return -1;
+  WinGeom g(B, H, W, wtm::WS, shift);
+  CUtensorMap m7, m4, m3, d7, d4, d3;
+  if (!wtm::window_maps(qkv, B, H, W, 3 * C, &m7, &m4, &m3) || !wtm::window_maps(dout, B, H, W, C, &d7, &d4, &d3)) return -1;
+  const int num_items = B * g.nWh * g.nWw * heads;
+  auto kern = wtm::wmsa_bwd_tma_kernel;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wtm::B_TOTAL);
+  int grid = (kNumSMs * 4) / heads * heads;
+  if (grid > num_items) grid = num_items;
+  kern<<<grid, wtm::THREADS, wtm::B_TOTAL, (cudaStream_t)stream>>>(m7, m4, m3, d7, d4, d3, qkv_bias, bias_table,
+                                                                   (__nv_bfloat16 *)dqkv, dbias_table, dqkv_bias, g, C, heads,
+                                                                   scale, num_items);
+  RSC_CHECK_LAUNCH("rsc_wmsa_bwd(tma)");
   return RSC_OK;
 }
