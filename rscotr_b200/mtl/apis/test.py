@@ -32,7 +32,11 @@ def test_model(cfg, checkpoint=None, tasks=('cls', 'det', 'seg'), split='test', 
     eval_kwargs = {k: v for k, v in dict(cfg.get('evaluation', {}) or {}).items() if k not in _HOOK_ARGS}
     metrics = {}
     for name, ds in datasets.items():
+        results = test_outputs.get(name)
+        if results is None:      # multi_gpu_test gathers on rank 0: the other ranks have nothing to evaluate
+            metrics[name] = None
+            continue
         kw = dict(eval_kwargs.get(ds.task, {}) or {})
         kw.update((eval_override or {}).get(ds.task, {}))
-        metrics[name] = ds.evaluate(test_outputs[name], **kw)
+        metrics[name] = ds.evaluate(results, **kw)
     return metrics, test_outputs

@@ -15,9 +15,10 @@ from ..utils.checkpoint import find_latest_checkpoint
 
 def train_model(model, datasets, cfg, distributed=False, validate=False, timestamp=None, meta=None, _skip_eval_tasks=()):
     logger = logging.getLogger('rscotr_b200')
-    data_loader = [build_multidataloader(cfg, distributed, datasets)]
+    # the process group must exist BEFORE the loaders are built: their samplers read (rank, world) at construction
     if distributed and not dist.is_initialized():
         dist.init_process_group(cfg.get('dist_params', {}).get('backend', 'nccl'))
+    data_loader = [build_multidataloader(cfg, distributed, datasets)]
     device = cfg.get('device', 'cuda')
     if distributed and str(device) == 'cuda':
         device = 'cuda:%d' % int(os.environ.get('LOCAL_RANK', 0))

@@ -129,6 +129,13 @@ class StepEngine:
             p._rsc_g = self._grad_views[-1]
             p._rsc_lp = self.flat_param_lp[s0:e0].view_as(p) if lp else None
         self._grad_of = {id(p): v for p, v in zip(self._params, self._grad_views)}
+        if self.world > 1:
+            # what the reference's DDP wrapper does at construction (mtl/apis/train.py:37-46): rank 0's weights
+            # (and buffers) win, so per-rank init differences (--diff-seed, nondeterministic init) cannot leave the
+            # replicas silently different -- only gradients are exchanged afterwards
+            dist.broadcast(self.flat_param, src=0)
+            for b in self.model.buffers():
+                dist.broadcast(b.data, src=0)
         self.sync_lp()
 
     def sync_lp(self):

@@ -29,6 +29,11 @@ class MultiDatasetsEvalHook:
     def __init__(self, dataloaders, start=None, interval=1, by_epoch=False, save_best=None, test_fn=None,
                  **eval_kwargs):
         self.dataloaders, self.start, self.interval, self.by_epoch = dataloaders, start, interval, by_epoch
+        # reference evaluation.py: a str / list save_best is normalised to {key: 1} weights
+        if isinstance(save_best, str):
+            save_best = {save_best: 1}
+        elif isinstance(save_best, (list, tuple)):
+            save_best = {k: 1 for k in save_best}
         self.save_best = dict(save_best) if isinstance(save_best, dict) else save_best
         self.test_fn = test_fn          # default: single process -> single_gpu_test; distributed -> multi_gpu_test (rank 0 evaluates)
         self.eval_kwargs = eval_kwargs

@@ -131,6 +131,12 @@ def optimizer_state_dict(engine):
                                 exp_avg_sq=opt.exp_avg_sq[s:e].view_as(p).detach().cpu().clone())
         elif p in opt.state and opt.state[p]:
             state[i] = {k: (v.detach().cpu().clone() if torch.is_tensor(v) else v) for k, v in opt.state[p].items()}
+    # mmcv's DefaultOptimizerConstructor builds ONE group over model.parameters() when the config has no paramwise_cfg
+    # and one group per parameter otherwise (mtl/utils/optimizer.py:40-55): identical hyper-parameters everywhere means the
+    # former, so the checkpoint resumes in the reference's optimizer as well
+    hyper = [{k: v for k, v in g.items() if k != 'params'} for g in groups]
+    if len(groups) > 1 and all(h == hyper[0] for h in hyper[1:]):
+        groups = [dict(hyper[0], params=[i for g in groups for i in g['params']])]
     return dict(state=state, param_groups=groups)
 
 
