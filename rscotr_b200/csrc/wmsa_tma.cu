@@ -159,43 +159,64 @@ __device__ __forceinline__ uint64_t key_mask(uint32_t rowbits, uint32_t colbits)
     m |= (uint64_t)(((rowbits >> slot_r(kslot(n))) | (colbits >> slot_c(kslot(n)))) & 1u) << n;
   return m;
 }
-// running maximum over the valid keys of one 32-column half (HALF_ID 0: slots 0..31, 1: slots 32..63)
-template <bool MASK, int HALF_ID>
-__device__ __forceinline__ float half_max(const uint32_t (&x)[32], const float (&bj)[NT], float scale2, uint64_t msk, float m) {
-  float m1 = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const int c = HALF_ID * 32 + k;
-    if (slot_ok(c)) {
-      const float v = score<MASK>(c, x[k], bj, scale2, msk);
-      if (k & 1) m1 = fmaxf(m1, v);
-      else m = fmaxf(m, v);
+// ---- forward softmax: packed fp32x2 arithmetic (FFMA2 / FADD2) on key-slot PAIRS (2w, 2w+1) --------------------
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  uint64_t ra = *reinterpret_cast<uint64_t *>(&a), rb = *reinterpret_cast<uint64_t *>(&b), rc = *reinterpret_cast<uint64_t *>(&c), rd;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  uint64_t ra = *reinterpret_cast<uint64_t *>(&a), rb = *reinterpret_cast<uint64_t *>(&b), rd;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2 *>(&rd);
+}
+constexpr int NP = 28;   // slot pairs 0..27 cover slots 0..55; the odd slot of a pair may be the never-valid column 7
+
+// scores (exp2 domain) of slot pair P: S * scale2 + bias (+ shift mask)
+template <bool MASK>
+__device__ __forceinline__ float2 score2(int P, uint32_t s0, uint32_t s1, const float2 (&bp)[NP], float scale2, uint64_t msk) {
+  float2 t = fma2(make_float2(__uint_as_float(s0), __uint_as_float(s1)), make_float2(scale2, scale2), bp[P]);
+  if (MASK) {
+    if ((msk >> kidx(2 * P)) & 1ull) t.x += -100.0f * LOG2E;
+    if (slot_ok(2 * P + 1)) {
+      if ((msk >> kidx(2 * P + 1)) & 1ull) t.y += -100.0f * LOG2E;
     }
   }
-  return fmaxf(m, m1);
+  return t;
 }
-// softmax numerators of one half as 16 packed bf16 words (key slots 2w, 2w+1), straight into the P tile row;
-// accumulates the row sum l
+// running maximum over one 32-column half (HALF_ID 0: slots 0..31, 1: slots 32..63)
 template <bool MASK, int HALF_ID>
-__device__ __forceinline__ void half_probs(const uint32_t (&x)[32], const float (&bj)[NT], float scale2, uint64_t msk, float m,
-                                           bool row_ok, float &l, uint32_t prow) {
-  float l1 = 0.f;
-  uint32_t pk[16];
+__device__ __forceinline__ float half_max(const uint32_t (&x)[32], const float2 (&bp)[NP], float scale2, uint64_t msk, float m) {
 #pragma unroll
   for (int w = 0; w < 16; ++w) {
-    const int c0 = HALF_ID * 32 + 2 * w, c1 = c0 + 1;
-    float p0 = 0.f, p1 = 0.f;
-    if (slot_ok(c0)) {
-      p0 = ex2(score<MASK>(c0, x[2 * w], bj, scale2, msk) - m);
-      l += p0;
+    const int P = HALF_ID * 16 + w;
+    if (P < NP) {
+      const float2 t = score2<MASK>(P, x[2 * w], x[2 * w + 1], bp, scale2, msk);
+      m = slot_ok(2 * P + 1) ? fmaxf(m, fmaxf(t.x, t.y)) : fmaxf(m, t.x);
     }
-    if (slot_ok(c1)) {
-      p1 = ex2(score<MASK>(c1, x[2 * w + 1], bj, scale2, msk) - m);
-      l1 += p1;
-    }
-    pk[w] = row_ok ? pack_bf16(p0, p1) : 0u;
   }
-  l += l1;
+  return m;
+}
+// softmax numerators of one half as 16 packed bf16 words, straight into the P tile row; accumulates the row sum
+template <bool MASK, int HALF_ID>
+__device__ __forceinline__ void half_probs(const uint32_t (&x)[32], const float2 (&bp)[NP], float scale2, uint64_t msk, float m,
+                                           float2 &l, uint32_t prow) {
+  uint32_t pk[16];
+  const float2 nm = make_float2(-m, -m);
+#pragma unroll
+  for (int w = 0; w < 16; ++w) {
+    const int P = HALF_ID * 16 + w;
+    if (P < NP) {
+      const float2 d = add2(score2<MASK>(P, x[2 * w], x[2 * w + 1], bp, scale2, msk), nm);
+      float2 p;
+      p.x = ex2(d.x);
+      p.y = slot_ok(2 * P + 1) ? ex2(d.y) : 0.f;
+      l = add2(l, p);
+      pk[w] = pack_bf16(p.x, p.y);
+    } else {
+      pk[w] = 0u;
+    }
+  }
 #pragma unroll
   for (int kc = 0; kc < 4; ++kc)
     st_shared16(prow + (HALF_ID * 4 + kc) * 1024, make_uint4(pk[4 * kc], pk[4 * kc + 1], pk[4 * kc + 2], pk[4 * kc + 3]));
@@ -203,27 +224,39 @@ __device__ __forceinline__ void half_probs(const uint32_t (&x)[32], const float 
 
 // Softmax of this thread's row: accumulator row at TMEM address taddr (64 columns) -> bf16 numerators in the P tile
 // row at shared address prow; returns the row sum.  Executed by all 32 lanes of the warp (tcgen05.ld is
-// warp-collective); rows that are not real queries write zeros.  The row is read from TMEM half a row at a time,
-// once for the maximum and once more for the exponentials: 32 accumulator + 49 bias registers live instead of
-// 64 + 49 + 49 (the budget is 128 registers at 8 CTAs / SM).
+// warp-collective).  The row is read from TMEM half a row at a time, once for the maximum and once more for the
+// exponentials: 32 accumulator + 56 bias registers live instead of 64 + 56 + 49.  Rows that are not real queries
+// (slots 56..63, window column 7) produce finite junk: in the forward pass such rows of P only reach rows of O
+// that are never stored.
 template <bool MASK>
-__device__ __forceinline__ float softmax_row(uint32_t taddr, const float (&bj)[NT], float scale2, uint64_t msk, bool row_ok,
-                                             uint32_t prow) {
+__device__ __forceinline__ float softmax_row(uint32_t taddr, const float2 (&bp)[NP], float scale2, uint64_t msk, uint32_t prow) {
   uint32_t x[32];
   tmem_ld32(taddr + 32, x);
   tmem_ld_wait();
-  float m = half_max<MASK, 1>(x, bj, scale2, msk, -INFINITY);
+  float m = half_max<MASK, 1>(x, bp, scale2, msk, -INFINITY);
   tmem_ld32(taddr, x);
   tmem_ld_wait();
-  m = half_max<MASK, 0>(x, bj, scale2, msk, m);
-  float l = 0.f;
+  m = half_max<MASK, 0>(x, bp, scale2, msk, m);
+  float2 l = make_float2(0.f, 0.f);
   tmem_ld32(taddr, x);   // (a fresh copy: keeps the first-pass scores from being held in registers)
   tmem_ld_wait();
-  half_probs<MASK, 0>(x, bj, scale2, msk, m, row_ok, l, prow);
+  half_probs<MASK, 0>(x, bp, scale2, msk, m, l, prow);
   tmem_ld32(taddr + 32, x);
   tmem_ld_wait();
-  half_probs<MASK, 1>(x, bj, scale2, msk, m, row_ok, l, prow);
-  return l;
+  half_probs<MASK, 1>(x, bp, scale2, msk, m, l, prow);
+  return l.x + l.y;
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- forward ------------------------------------------------------------------------------------------------
@@ -248,7 +281,8 @@ __device__ __forceinline__ void fix_padded_row(uint32_t tile, uint32_t bias_row,
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 8)
+template <int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS)
     wmsa_fwd_tma_kernel(const __grid_constant__ CUtensorMap m7, const __grid_constant__ CUtensorMap m4,
                         const __grid_constant__ CUtensorMap m3, const float *__restrict__ qkv_bias,
                         const float *__restrict__ table, __nv_bfloat16 *__restrict__ out, WinGeom g, int C, int heads,
@@ -257,7 +291,9 @@ __global__ void __launch_bounds__(THREADS, 8)
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + F_BAR);   // full[0], full[1]
   uint64_t &mbar = full[2];
   uint32_t &tmem_base_s = *reinterpret_cast<uint32_t *>(smem + F_BAR + 32);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction: the control code of
+                                                            // warp 0 (TMA, MMA issue) runs on the uniform datapath
   const uint32_t sb = smem_u32(smem);
   if (sb & 1023u) __trap();   // the swizzled tiles need the 1024-byte alignment the declaration asks for
   const int head = blockIdx.x % heads;   // gridDim.x is a multiple of heads: the head is fixed per CTA
@@ -277,15 +313,20 @@ __global__ void __launch_bounds__(THREADS, 8)
     st_shared16(sb + F_BIAS + tid * 16,
                 make_uint4(pack_bf16(f0.x, f0.y), pack_bf16(f0.z, f0.w), pack_bf16(f1.x, f1.y), pack_bf16(f1.z, f1.w)));
   }
-  // this thread's query slot and its 49 relative-position biases (exp2 domain)
+  // this thread's query slot and the relative-position biases of its row (exp2 domain), as slot pairs
   const bool row_ok = slot_ok(tid);
   const int ri = slot_r(tid), ci = slot_c(tid);
-  float bj[NT];
+  float2 bp[NP];
 #pragma unroll
-  for (int n = 0; n < NT; ++n) {
-    const int c = kslot(n);
-    const int idx = (ri - slot_r(c) + WS - 1) * (2 * WS - 1) + (ci - slot_c(c) + WS - 1);
-    bj[n] = row_ok ? __ldg(table + idx * heads + head) * LOG2E : 0.f;
+  for (int P = 0; P < NP; ++P) {
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = 2 * P + e;
+      const int idx = (ri - slot_r(c) + WS - 1) * (2 * WS - 1) + (ci - slot_c(c) + WS - 1);
+      v[e] = (row_ok && slot_ok(c)) ? __ldg(table + idx * heads + head) * LOG2E : 0.f;
+    }
+    bp[P] = make_float2(v[0], v[1]);
   }
   fence_before_sync();
   __syncthreads();
@@ -312,19 +353,20 @@ __global__ void __launch_bounds__(THREADS, 8)
   }
   const int step = gridDim.x;
   int item = blockIdx.x;
-  WinPos pf = cur;   // (thread 0) window of the next unit to prefetch
-  if (tid == 0) {
+  WinPos pf = cur;   // window of the next unit to prefetch (tracked by every lane: all of it is warp-uniform)
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (item + s * step < num_items) {
+  for (int s = 0; s < 2; ++s) {
+    if (warp == 0 && item + s * step < num_items) {
+      if (elect_one()) {
         mbar_expect_tx(&full[s], 6 * HALF);
 #pragma unroll
         for (int part = 0; part < 3; ++part)
           tma_window(sb + (part < 2 ? s * F_QK + part * TILE : F_V0 + s * TILE), &full[s], &m7, &m4, &m3, g, pf,
                      part * C + head * HD);
       }
-      advance(pf, st, g);
+      __syncwarp();
     }
+    advance(pf, st, g);
   }
 
   for (int it = 0; item < num_items; ++it, item += step) {
@@ -351,13 +393,16 @@ __global__ void __launch_bounds__(THREADS, 8)
     // (the TMEM reads of the previous unit are ordered before this unit's MMAs)
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      mbar_wait(&full[buf], (it >> 1) & 1);
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        mbar_wait(&full[buf], (it >> 1) & 1);
 #pragma unroll
-      for (int k = 0; k < 2; ++k)   // K = 32 channels: +32 bytes inside the swizzled 64-byte rows
-        mma_bf16_ss(tm, desc_sw64(in + k * 32), desc_sw64(in + TILE + k * 32), idesc_s, k > 0);
-      mma_commit(&mbar);
+        for (int k = 0; k < 2; ++k)   // K = 32 channels: +32 bytes inside the swizzled 64-byte rows
+          mma_bf16_ss(tm, desc_sw64(in + k * 32), desc_sw64(in + TILE + k * 32), idesc_s, k > 0);
+        mma_commit(&mbar);
+      }
+      __syncwarp();
     }
     uint64_t msk = 0;
     const bool masked = rim && g.shift > 0;
@@ -373,20 +418,22 @@ __global__ void __launch_bounds__(THREADS, 8)
     float inv_l;
     {
       const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16), prow = in + p_off(tid, 0);
-      const float l = masked ? softmax_row<true>(taddr, bj, scale2, msk, row_ok, prow)
-                             : softmax_row<false>(taddr, bj, scale2, 0ull, row_ok, prow);
+      const float l = masked ? softmax_row<true>(taddr, bp, scale2, msk, prow) : softmax_row<false>(taddr, bp, scale2, 0ull, prow);
       inv_l = 1.0f / l;
     }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     // ---- O = P V (overwrites S columns 0..31) ----
-    if (tid == 0) {
-      fence_after_sync();
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
 #pragma unroll
-      for (int k = 0; k < 4; ++k)   // K = 64 key slots, 16 per step
-        mma_bf16_ss(tm, make_smem_desc(in + k * 2048, 1024, 128), desc_sw64(inV + k * 1024), idesc_o, k > 0);
-      mma_commit(&mbar);
+        for (int k = 0; k < 4; ++k)   // K = 64 key slots, 16 per step
+          mma_bf16_ss(tm, make_smem_desc(in + k * 2048, 1024, 128), desc_sw64(inV + k * 1024), idesc_o, k > 0);
+        mma_commit(&mbar);
+      }
+      __syncwarp();
     }
     mbar_wait(&mbar, phase);
     phase ^= 1;
@@ -394,15 +441,16 @@ __global__ void __launch_bounds__(THREADS, 8)
     uint32_t o[32];
     tmem_ld32(tm + ((uint32_t)(warp * 32) << 16), o);
     // the stage is free again: refill it with the unit after next
-    if (tid == 0) {
-      if (item + 2 * step < num_items) {
+    if (warp == 0 && item + 2 * step < num_items) {
+      if (elect_one()) {
         mbar_expect_tx(&full[buf], 6 * HALF);
 #pragma unroll
         for (int part = 0; part < 3; ++part)
           tma_window(part < 2 ? in + part * TILE : inV, &full[buf], &m7, &m4, &m3, g, pf, part * C + head * HD);
       }
-      advance(pf, st, g);
+      __syncwarp();
     }
+    advance(pf, st, g);
     tmem_ld_wait();
     // ---- normalise and store this thread's output row ----
     if (tok_ok) {
@@ -584,7 +632,8 @@ __global__ void __launch_bounds__(THREADS, 4)
   uint64_t &mbar = full[2];
   uint32_t &tmem_base_s = *reinterpret_cast<uint32_t *>(smem + B_BAR + 32);
   float *padacc = reinterpret_cast<float *>(smem + B_PADACC);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction (control code of warp 0)
   const uint32_t sb = smem_u32(smem);
   if (sb & 1023u) __trap();
   const int head = blockIdx.x % heads;   // gridDim.x is a multiple of heads
@@ -640,7 +689,7 @@ __global__ void __launch_bounds__(THREADS, 4)
   const int step = gridDim.x;
   int item = blockIdx.x;
   WinPos pf = cur;
-  auto load_unit = [&](int s) {   // thread 0: the four operand tiles of the unit at `pf` into stage s
+  auto load_unit = [&](int s) {   // one elected lane: the four operand tiles of the unit at `pf` into stage s
     const uint32_t base = sb + B_IN0 + s * B_STAGE;
     mbar_expect_tx(&full[s], 8 * HALF);
     tma_window(base, &full[s], &d7, &d4, &d3, g, pf, head * HD);
@@ -648,12 +697,13 @@ __global__ void __launch_bounds__(THREADS, 4)
     for (int part = 0; part < 3; ++part)
       tma_window(base + (1 + part) * TILE, &full[s], &m7, &m4, &m3, g, pf, part * C + head * HD);
   };
-  if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (item + s * step < num_items) load_unit(s);
-      advance(pf, st, g);
+  for (int s = 0; s < 2; ++s) {
+    if (warp == 0 && item + s * step < num_items) {
+      if (elect_one()) load_unit(s);
+      __syncwarp();
     }
+    advance(pf, st, g);
   }
 
   for (int it = 0; item < num_items; ++it, item += step) {
@@ -678,14 +728,17 @@ __global__ void __launch_bounds__(THREADS, 4)
     fence_before_sync();
     __syncthreads();
     // ---------------- S = Q K^T (cols 0..63), dP = dO V^T (cols 64..127) ----------------
-    if (tid == 0) {
-      fence_after_sync();
-      mbar_wait(&full[buf], (it >> 1) & 1);
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        mbar_wait(&full[buf], (it >> 1) & 1);
 #pragma unroll
-      for (int k = 0; k < 2; ++k) mma_bf16_ss(tm, desc_sw64(inQ + k * 32), desc_sw64(inK + k * 32), idesc_s, k > 0);
+        for (int k = 0; k < 2; ++k) mma_bf16_ss(tm, desc_sw64(inQ + k * 32), desc_sw64(inK + k * 32), idesc_s, k > 0);
 #pragma unroll
-      for (int k = 0; k < 2; ++k) mma_bf16_ss(tm + 64, desc_sw64(inDO + k * 32), desc_sw64(inV + k * 32), idesc_s, k > 0);
-      mma_commit(&mbar);
+        for (int k = 0; k < 2; ++k) mma_bf16_ss(tm + 64, desc_sw64(inDO + k * 32), desc_sw64(inV + k * 32), idesc_s, k > 0);
+        mma_commit(&mbar);
+      }
+      __syncwarp();
     }
     uint64_t msk = 0, pad = 0;
     const bool slow = has_pad || (rim && g.shift > 0);
@@ -710,27 +763,31 @@ __global__ void __launch_bounds__(THREADS, 4)
     fence_before_sync();
     __syncthreads();
     // ---------------- dV = P^T dO (cols 0..31), dK = dS'^T Q (32..63), dQ = dS' K (64..95) ----------------
-    if (tid == 0) {
-      fence_after_sync();
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
 #pragma unroll
-      for (int k = 0; k < 4; ++k)   // K = 64 query slots, 16 per step
-        mma_bf16_ss(tm, make_smem_desc(sb + B_P + k * 256, 128, 1024), desc_sw64(inDO + k * 1024), idesc_t, k > 0);
+        for (int k = 0; k < 4; ++k)   // K = 64 query slots, 16 per step
+          mma_bf16_ss(tm, make_smem_desc(sb + B_P + k * 256, 128, 1024), desc_sw64(inDO + k * 1024), idesc_t, k > 0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        mma_bf16_ss(tm + 32, make_smem_desc(sb + B_DS + k * 256, 128, 1024), desc_sw64(inQ + k * 1024), idesc_t, k > 0);
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_ss(tm + 32, make_smem_desc(sb + B_DS + k * 256, 128, 1024), desc_sw64(inQ + k * 1024), idesc_t, k > 0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)   // K = 64 key slots, 16 per step
-        mma_bf16_ss(tm + 64, make_smem_desc(sb + B_DS + k * 2048, 1024, 128), desc_sw64(inK + k * 1024), idesc_q, k > 0);
-      mma_commit(&mbar);
+        for (int k = 0; k < 4; ++k)   // K = 64 key slots, 16 per step
+          mma_bf16_ss(tm + 64, make_smem_desc(sb + B_DS + k * 2048, 1024, 128), desc_sw64(inK + k * 1024), idesc_q, k > 0);
+        mma_commit(&mbar);
+      }
+      __syncwarp();
     }
     mbar_wait(&mbar, phase);
     phase ^= 1;
     fence_after_sync();
     // the stage is free again: refill it with the unit after next
-    if (tid == 0) {
-      if (item + 2 * step < num_items) load_unit(buf);
-      advance(pf, st, g);
+    if (warp == 0 && item + 2 * step < num_items) {
+      if (elect_one()) load_unit(buf);
+      __syncwarp();
     }
+    advance(pf, st, g);
     // ---------------- store dv | dk | dq of this thread's token ----------------
     {
       const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16);
@@ -837,7 +894,7 @@ int rsc_wmsa_fwd_tma(const void *qkv, const float *qkv_bias, const float *bias_t
   CUtensorMap m7, m4, m3;
   if (!wtm::window_maps(qkv, B, H, W, 3 * C, &m7, &m4, &m3)) return -1;
   const int num_items = B * g.nWh * g.nWw * heads;
-  auto kern = wtm::wmsa_fwd_tma_kernel;
+  auto kern = wtm::wmsa_fwd_tma_kernel<8>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wtm::F_TOTAL);
   int grid = (kNumSMs * 8) / heads * heads;   // a multiple of heads: every CTA keeps one head
   if (grid > num_items) grid = num_items;     // num_items is a multiple of heads
