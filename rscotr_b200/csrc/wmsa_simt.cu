@@ -374,8 +374,8 @@ static int dispatch_fwd(const void *qkv, const float *qkv_bias, const float *tab
 
 using namespace rsc;
 
-// The tensor-core (tcgen05) bf16 forward lives in wmsa_tc.cu; returns <0 if it
-// does not take the case.
+// The tensor-core (tcgen05) bf16 kernels and the rsc_wmsa_{fwd,bwd} dispatch live in wmsa_tma.cu; these entries take
+// fp32 (the exact-arithmetic parity path), RSC_WMSA_SIMT=1 and every argument error.
 extern "C" int rsc_wmsa_fwd_simt(const void *qkv, const float *qkv_bias, const float *bias_table, void *out, int B,
                                  int H, int W, int C, int heads, int ws, int shift, float scale, int dtype,
                                  void *stream) {

@@ -1,4 +1,5 @@
-// Fused (shifted-)window attention, bf16, TMA-staged (round-2 kernels; tools/wmsa_probe.cu pins every layout used here).
+// Fused (shifted-)window attention on the 5th-gen tensor cores (bf16), forward and backward, TMA-staged.
+// tools/wmsa_probe.cu pins every shared-memory layout / descriptor used here against a host reference.
 //
 // Unit = one (window, head): 49 tokens x 32 dims.  The window is staged as a 56-SLOT tile
 //     slot s = half*28 + i*4 + jj      (i = window row 0..6, window column j = half*4 + jj, jj = 0..3)
@@ -8,16 +9,19 @@
 // neighbour's token: it is loaded but never a valid key / query.  Windows of a shifted block that wrap around the
 // rolled map use (4 rows) + (3 rows) boxes per half (two more tensor maps).  TMA writes the tiles with
 // SWIZZLE_64B; the same bytes are read by tcgen05.mma as K-major operands (S = Q K^T, dP = dO V^T) and as
-// MN-major B operands (O = P V, dV = P^T dO, dK = dS^T Q, dQ = dS K).
+// MN-major B operands (O = P V, dV = P^T dO, dK = dS^T Q, dQ = dS K).  All contractions are kind::f16 MMAs with
+// M = 128 whose accumulator rows 64..127 are never read (the A descriptors run on into the following tile).
 //
-// Slot 56 of the K / V tiles (never written by TMA) holds the k / v slice of the qkv BIAS = the k / v row of every
-// zero-padded token: S[:,56] = q . b_k and dP[:,56] = dO . b_v come out of the same MMAs, the softmax reads column
-// 56 in place of every padded key, P[:,56] / dS[:,56] carry the row sums over the padded keys, and row 56 of
-// dV / dK is the gradient that reaches the qkv bias through the padded rows.
+// Zero-padded tokens: mmdet pads AFTER norm1, so the k / v row of a padded token is the qkv bias.  In windows that
+// hold padding, the threads that own padded slots overwrite the zeros TMA delivered with the bias rows before the
+// MMAs read the tiles; in the backward pass column 56 of the P / dS tiles carries the row sums over the padded keys,
+// so row 56 of dV / dK (summed by the tensor core) is the gradient that reaches the qkv bias through them.
 //
 // CTA = 64 threads (thread = slot = query row = TMEM lane), persistent over the units of ONE head, 8 (forward) /
-// 4 (backward) CTAs per SM; thread 0 also drives TMA (two-stage ring, prefetch distance one unit) and issues the
-// MMAs.  Relative-position bias of the thread's row lives in 49 registers.  HBM-bound: SURVEY 8d.
+// 4 (backward) CTAs per SM.  One elected lane of warp 0 drives TMA (two-stage ring, prefetch distance one unit) and
+// issues the MMAs on the uniform datapath.  The relative-position biases of the thread's row live in registers as
+// slot pairs; softmax and its backward run in packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2).  HBM-bound
+// (24.5 flop/B forward): SURVEY 8d.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -29,7 +33,7 @@ namespace wtm {
 
 using namespace tc;
 
-constexpr int WS = 7, NT = 49, HD = 32;
+constexpr int WS = 7, NT = 49, HD = 32;   // NT: valid keys per window
 constexpr int THREADS = 64;
 constexpr uint32_t TILE = 4096;   // 64 slots x 64 bytes
 constexpr uint32_t HALF = 1792;   // 28 slots
@@ -140,17 +144,6 @@ __device__ __forceinline__ void pad_bits(const WinGeom &g, const WinPos &p, uint
   }
 }
 
-// Score of key slot c of this thread's row in the exp2 domain: S[c] * scale2 + bias (+ shift mask); `sv` = the
-// accumulator value of column c; msk bit n = the n-th valid key lies in another shift region (-100 in the reference).
-// MASK only in the last window row / column of a shifted block.
-template <bool MASK>
-__device__ __forceinline__ float score(int c, uint32_t sv, const float (&bj)[NT], float scale2, uint64_t msk) {
-  float v = fmaf(__uint_as_float(sv), scale2, bj[kidx(c)]);
-  if (MASK) {
-    if ((msk >> kidx(c)) & 1ull) v += -100.0f * LOG2E;
-  }
-  return v;
-}
 // 49-bit key mask from the 7-bit row / column masks
 __device__ __forceinline__ uint64_t key_mask(uint32_t rowbits, uint32_t colbits) {
   uint64_t m = 0;
@@ -494,130 +487,103 @@ constexpr uint32_t B_BAR = B_PADACC + 256;
 constexpr uint32_t B_TOTAL = B_BAR + 64;            // ~48.5 KB -> 4 CTAs / SM (4 x 128 TMEM columns = all 512)
 constexpr int B_TMEM = 128;
 
-// scores of one 32-column half of the row -> t[n] (exp2 domain), running maximum
-template <bool RIM, int HALF_ID>
-__device__ __forceinline__ float half_scores(const uint32_t (&x)[32], const float (&bj)[NT], float scale2, uint64_t msk,
-                                             float (&t)[NT], float m) {
-  float m1 = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const int c = HALF_ID * 32 + k;
-    if (slot_ok(c)) {
-      const float v = score<RIM>(c, x[k], bj, scale2, msk);
-      t[kidx(c)] = v;
-      if (k & 1) m1 = fmaxf(m1, v);
-      else m = fmaxf(m, v);
-    }
-  }
-  return fmaxf(m, m1);
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  uint64_t ra = *reinterpret_cast<uint64_t *>(&a), rb = *reinterpret_cast<uint64_t *>(&b), rd;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2 *>(&rd);
 }
-// one row of a P / dS tile: values v[n] of the valid keys, `pad` in slot 56, zeros elsewhere
-__device__ __forceinline__ void store_row(uint32_t row_addr, const float (&v)[NT], float pad, bool row_ok) {
+
+// one row of a P / dS tile from its slot pairs (pair w = packed bf16 word w); `pad` goes to slot 56
+__device__ __forceinline__ void store_row(uint32_t row_addr, const float2 (&v)[NP], float pad) {
 #pragma unroll
   for (int kc = 0; kc < 8; ++kc) {
     uint32_t w4[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c0 = kc * 8 + 2 * j, c1 = c0 + 1;
-      const float v0 = slot_ok(c0) ? v[kidx(c0)] : (c0 == PADSLOT ? pad : 0.f);
-      const float v1 = slot_ok(c1) ? v[kidx(c1)] : 0.f;
-      w4[j] = row_ok ? pack_bf16(v0, v1) : 0u;
+      const int w = kc * 4 + j;
+      w4[j] = w < NP ? pack_bf16(v[w].x, v[w].y) : (w == NP ? pack_bf16(pad, 0.f) : 0u);
     }
     st_shared16(row_addr + kc * 1024, make_uint4(w4[0], w4[1], w4[2], w4[3]));
   }
 }
 
-// Softmax backward of this thread's row.  S at TMEM taddr (64 cols), dP at taddr + 64.  Writes the P and dS' rows,
-// accumulates the bias-table gradient.  pad = 49-bit mask of the zero-padded keys, msk = of the shift-masked keys.
+// Softmax backward of this thread's row, packed fp32x2 arithmetic on slot pairs.  S at TMEM taddr (64 cols), dP at
+// taddr + 64.  Writes the P and dS' = scale * P * (dP - D) rows and accumulates the bias-table gradient (in units of
+// scale).  pad = 49-bit mask of the zero-padded keys, msk = of the shift-masked keys (RIM only).  Rows that are not
+// real queries (row_ok false) write zeros: dV / dK sum over ALL 64 query slots.
 template <bool RIM>
-__device__ __forceinline__ void softmax_bwd_row(uint32_t taddr, const float (&bj)[NT], float scale2, float scale, uint64_t msk,
-                                                uint64_t pad, bool row_ok, uint32_t prow, uint32_t dsrow, float (&dbacc)[NT]) {
-  float p[NT];
+__device__ __forceinline__ void softmax_bwd_row(uint32_t taddr, const float2 (&bp)[NP], float scale2, float scale, uint64_t msk,
+                                                uint64_t pad, bool row_ok, uint32_t prow, uint32_t dsrow, float2 (&dbacc)[NP]) {
+  float2 p[NP];
   uint32_t x[32];
+  float m = -INFINITY;
   tmem_ld32(taddr, x);
   tmem_ld_wait();
-  float m = half_scores<RIM, 0>(x, bj, scale2, msk, p, -INFINITY);
+#pragma unroll
+  for (int w = 0; w < 16; ++w) {
+    p[w] = score2<RIM>(w, x[2 * w], x[2 * w + 1], bp, scale2, msk);
+    m = slot_ok(2 * w + 1) ? fmaxf(m, fmaxf(p[w].x, p[w].y)) : fmaxf(m, p[w].x);
+  }
   tmem_ld32(taddr + 32, x);
   tmem_ld_wait();
-  m = half_scores<RIM, 1>(x, bj, scale2, msk, p, m);
-  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-  for (int n = 0; n < NT; ++n) {
-    p[n] = ex2(p[n] - m);
-    if ((n & 3) == 0) l0 += p[n];
-    else if ((n & 3) == 1) l1 += p[n];
-    else if ((n & 3) == 2) l2 += p[n];
-    else l3 += p[n];
+  for (int w = 16; w < NP; ++w) {
+    p[w] = score2<RIM>(w, x[2 * w - 32], x[2 * w - 31], bp, scale2, msk);
+    m = slot_ok(2 * w + 1) ? fmaxf(m, fmaxf(p[w].x, p[w].y)) : fmaxf(m, p[w].x);
   }
-  const float inv_l = 1.0f / ((l0 + l1) + (l2 + l3));
+  const float2 nm = make_float2(-m, -m);
+  float2 l = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int w = 0; w < NP; ++w) {
+    const float2 d = add2(p[w], nm);
+    p[w].x = ex2(d.x);
+    p[w].y = slot_ok(2 * w + 1) ? ex2(d.y) : 0.f;
+    l = add2(l, p[w]);
+  }
+  const float inv_l = row_ok ? 1.0f / (l.x + l.y) : 0.f;   // (rows that are no queries become zero rows)
+  const float2 il = make_float2(inv_l, inv_l);
   float wp = 0.f;
 #pragma unroll
-  for (int n = 0; n < NT; ++n) {
-    p[n] *= inv_l;
+  for (int w = 0; w < NP; ++w) {
+    p[w] = mul2(p[w], il);
     if (RIM) {
-      if ((pad >> n) & 1ull) wp += p[n];
+      if ((pad >> kidx(2 * w)) & 1ull) wp += p[w].x;
+      if (slot_ok(2 * w + 1)) {
+        if ((pad >> kidx(2 * w + 1)) & 1ull) wp += p[w].y;
+      }
     }
   }
-  store_row(prow, p, wp, row_ok);
+  store_row(prow, p, wp);
   // D = sum_j P * dP
-  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+  float2 D2 = make_float2(0.f, 0.f);
   tmem_ld32(taddr + 64, x);
   tmem_ld_wait();
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const int c = k;
-    if (slot_ok(c)) {
-      const float dp = __uint_as_float(x[k]);
-      if ((k & 3) == 0) d0 = fmaf(p[kidx(c)], dp, d0);
-      else if ((k & 3) == 1) d1 = fmaf(p[kidx(c)], dp, d1);
-      else if ((k & 3) == 2) d2 = fmaf(p[kidx(c)], dp, d2);
-      else d3 = fmaf(p[kidx(c)], dp, d3);
-    }
-  }
+  for (int w = 0; w < 16; ++w) D2 = fma2(p[w], make_float2(__uint_as_float(x[2 * w]), __uint_as_float(x[2 * w + 1])), D2);
   uint32_t y[32];
   tmem_ld32(taddr + 96, y);
   tmem_ld_wait();
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const int c = 32 + k;
-    if (slot_ok(c)) {
-      const float dp = __uint_as_float(y[k]);
-      if ((k & 3) == 0) d0 = fmaf(p[kidx(c)], dp, d0);
-      else if ((k & 3) == 1) d1 = fmaf(p[kidx(c)], dp, d1);
-      else if ((k & 3) == 2) d2 = fmaf(p[kidx(c)], dp, d2);
-      else d3 = fmaf(p[kidx(c)], dp, d3);
-    }
-  }
-  const float nDs = -((d0 + d1) + (d2 + d3)) * scale;
-  // dS' = scale * P * (dP - D), in place of p
+  for (int w = 16; w < NP; ++w)
+    D2 = fma2(p[w], make_float2(__uint_as_float(y[2 * w - 32]), __uint_as_float(y[2 * w - 31])), D2);
+  const float nDs = -(D2.x + D2.y) * scale;
+  const float2 nD = make_float2(nDs, nDs), sc = make_float2(scale, scale);
+  // dS' = P * (scale * dP - scale * D), in place of p
   float wds = 0.f;
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const int c = k;
-    if (slot_ok(c)) {
-      const int n = kidx(c);
-      const float ds = p[n] * fmaf(__uint_as_float(x[k]), scale, nDs);
-      if (row_ok) dbacc[n] += ds;
-      p[n] = ds;
-      if (RIM) {
-        if ((pad >> n) & 1ull) wds += ds;
+  for (int w = 0; w < NP; ++w) {
+    const float2 dp = w < 16 ? make_float2(__uint_as_float(x[2 * w]), __uint_as_float(x[2 * w + 1]))
+                             : make_float2(__uint_as_float(y[2 * w - 32]), __uint_as_float(y[2 * w - 31]));
+    p[w] = mul2(p[w], fma2(dp, sc, nD));
+    dbacc[w] = add2(dbacc[w], p[w]);
+    if (RIM) {
+      if ((pad >> kidx(2 * w)) & 1ull) wds += p[w].x;
+      if (slot_ok(2 * w + 1)) {
+        if ((pad >> kidx(2 * w + 1)) & 1ull) wds += p[w].y;
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const int c = 32 + k;
-    if (slot_ok(c)) {
-      const int n = kidx(c);
-      const float ds = p[n] * fmaf(__uint_as_float(y[k]), scale, nDs);
-      if (row_ok) dbacc[n] += ds;
-      p[n] = ds;
-      if (RIM) {
-        if ((pad >> n) & 1ull) wds += ds;
-      }
-    }
-  }
-  store_row(dsrow, p, wds, row_ok);
+  store_row(dsrow, p, wds);
 }
 
 __global__ void __launch_bounds__(THREADS, 4)
@@ -655,13 +621,18 @@ __global__ void __launch_bounds__(THREADS, 4)
   }
   const bool row_ok = slot_ok(tid);
   const int ri = slot_r(tid), ci = slot_c(tid);
-  float bj[NT], dbacc[NT];
+  float2 bp[NP], dbacc[NP];
 #pragma unroll
-  for (int n = 0; n < NT; ++n) {
-    const int c = kslot(n);
-    const int idx = (ri - slot_r(c) + WS - 1) * (2 * WS - 1) + (ci - slot_c(c) + WS - 1);
-    bj[n] = row_ok ? __ldg(table + idx * heads + head) * LOG2E : 0.f;
-    dbacc[n] = 0.f;
+  for (int P = 0; P < NP; ++P) {
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = 2 * P + e;
+      const int idx = (ri - slot_r(c) + WS - 1) * (2 * WS - 1) + (ci - slot_c(c) + WS - 1);
+      v[e] = (row_ok && slot_ok(c)) ? __ldg(table + idx * heads + head) * LOG2E : 0.f;
+    }
+    bp[P] = make_float2(v[0], v[1]);
+    dbacc[P] = make_float2(0.f, 0.f);
   }
   fence_before_sync();
   __syncthreads();
@@ -756,8 +727,8 @@ __global__ void __launch_bounds__(THREADS, 4)
     {
       const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16);
       const uint32_t prow = sb + B_P + p_off(tid, 0), dsrow = sb + B_DS + p_off(tid, 0);
-      if (slow) softmax_bwd_row<true>(taddr, bj, scale2, scale, msk, pad, row_ok, prow, dsrow, dbacc);
-      else softmax_bwd_row<false>(taddr, bj, scale2, scale, 0ull, 0ull, row_ok, prow, dsrow, dbacc);
+      if (slow) softmax_bwd_row<true>(taddr, bp, scale2, scale, msk, pad, row_ok, prow, dsrow, dbacc);
+      else softmax_bwd_row<false>(taddr, bp, scale2, scale, 0ull, 0ull, row_ok, prow, dsrow, dbacc);
     }
     fence_async_smem();
     fence_before_sync();
@@ -791,28 +762,30 @@ __global__ void __launch_bounds__(THREADS, 4)
     // ---------------- store dv | dk | dq of this thread's token ----------------
     {
       const uint32_t taddr = tm + ((uint32_t)(warp * 32) << 16);
-      __nv_bfloat16 *dst = dqkv + (((int64_t)cur.b * g.H + h) * g.W + w) * (3 * C) + head * HD;
+      uint32_t o[3][32];   // three register sets: a store still reading its registers never blocks the next TMEM load
 #pragma unroll
-      for (int part = 0; part < 3; ++part) {   // TMEM columns: dV 0, dK 32, dQ 64 -> dqkv parts 2, 1, 0
-        uint32_t o[32];
-        tmem_ld32(taddr + part * 32, o);
-        tmem_ld_wait();
-        const int qpart = 2 - part;
-        if (tok_ok) {
+      for (int part = 0; part < 3; ++part) tmem_ld32(taddr + part * 32, o[part]);   // TMEM columns: dV 0, dK 32, dQ 64
+      tmem_ld_wait();
+      if (tok_ok) {
+        __nv_bfloat16 *dst = dqkv + (((int64_t)cur.b * g.H + h) * g.W + w) * (3 * C) + head * HD;
+#pragma unroll
+        for (int part = 0; part < 3; ++part) {   // -> dqkv parts 2, 1, 0
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4 v;
-            v.x = pack_bf16(__uint_as_float(o[8 * c + 0]), __uint_as_float(o[8 * c + 1]));
-            v.y = pack_bf16(__uint_as_float(o[8 * c + 2]), __uint_as_float(o[8 * c + 3]));
-            v.z = pack_bf16(__uint_as_float(o[8 * c + 4]), __uint_as_float(o[8 * c + 5]));
-            v.w = pack_bf16(__uint_as_float(o[8 * c + 6]), __uint_as_float(o[8 * c + 7]));
-            *reinterpret_cast<uint4 *>(dst + qpart * C + 8 * c) = v;
+            v.x = pack_bf16(__uint_as_float(o[part][8 * c + 0]), __uint_as_float(o[part][8 * c + 1]));
+            v.y = pack_bf16(__uint_as_float(o[part][8 * c + 2]), __uint_as_float(o[part][8 * c + 3]));
+            v.z = pack_bf16(__uint_as_float(o[part][8 * c + 4]), __uint_as_float(o[part][8 * c + 5]));
+            v.w = pack_bf16(__uint_as_float(o[part][8 * c + 6]), __uint_as_float(o[part][8 * c + 7]));
+            *reinterpret_cast<uint4 *>(dst + (2 - part) * C + 8 * c) = v;
           }
-        } else if (tid == PADSLOT && part < 2 && has_pad) {
-          // row 56 = sum over this window's padded keys (only this thread touches padacc: no atomics)
-#pragma unroll
-          for (int d = 0; d < 32; ++d) padacc[(1 - part) * 32 + d] += __uint_as_float(o[d]);
         }
+      } else if (tid == PADSLOT && has_pad) {
+        // row 56 = sum over this window's padded keys (only this thread touches padacc: no atomics)
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+          for (int d = 0; d < 32; ++d) padacc[(1 - part) * 32 + d] += __uint_as_float(o[part][d]);
       }
     }
     advance(cur, st, g);
@@ -823,7 +796,10 @@ __global__ void __launch_bounds__(THREADS, 4)
   float *mat = reinterpret_cast<float *>(smem);   // 64 x 49 floats over the (now idle) P / dS tiles
   if (row_ok) {
 #pragma unroll
-    for (int n = 0; n < NT; ++n) mat[tid * NT + n] = dbacc[n];
+    for (int P = 0; P < NP; ++P) {
+      mat[tid * NT + kidx(2 * P)] = dbacc[P].x;
+      if (slot_ok(2 * P + 1)) mat[tid * NT + kidx(2 * P + 1)] = dbacc[P].y;
+    }
   }
   __syncthreads();
   const float inv_scale = 1.0f / scale;
@@ -886,13 +862,26 @@ static bool window_maps(const void *base, int B, int H, int W, int ch, CUtensorM
 
 using namespace rsc;
 
-// returns RSC_OK, or -1 when the TMA path does not apply (caller falls back to the cp.async kernel)
-int rsc_wmsa_fwd_tma(const void *qkv, const float *qkv_bias, const float *bias_table, void *out, int B, int H, int W, int C,
-                     int heads, int shift, float scale, void *stream) {
-  if (((uintptr_t)qkv & 15) || heads > 8 * kNumSMs) return -1;
+extern "C" int rsc_wmsa_fwd_simt(const void *qkv, const float *qkv_bias, const float *bias_table, void *out, int B, int H,
+                                 int W, int C, int heads, int ws, int shift, float scale, int dtype, void *stream);
+extern "C" int rsc_wmsa_bwd_simt(const void *qkv, const float *qkv_bias, const float *bias_table, const void *dout, void *dqkv,
+                                 float *dbias_table, float *dqkv_bias, int B, int H, int W, int C, int heads, int ws, int shift,
+                                 float scale, int dtype, void *stream);
+
+static bool tc_shape_ok(int dtype, int ws, int shift, int heads, int C, int B, int H, int W) {
+  return dtype == RSC_BF16 && ws == 7 && (shift == 0 || shift == 3) && heads > 0 && C == heads * 32 && B > 0 && H > 0 && W > 0;
+}
+
+extern "C" int rsc_wmsa_fwd(const void *qkv, const float *qkv_bias, const float *bias_table, void *out, int B, int H, int W,
+                            int C, int heads, int ws, int shift, float scale, int dtype, void *stream) {
+  static const bool force_simt = getenv("RSC_WMSA_SIMT") != nullptr;
+  if (force_simt || !tc_shape_ok(dtype, ws, shift, heads, C, B, H, W) || !qkv || !bias_table || !out || heads > 8 * kNumSMs)
+    // fp32 (the exact-arithmetic parity path) and argument errors go through the SIMT entry, which validates
+    return rsc_wmsa_fwd_simt(qkv, qkv_bias, bias_table, out, B, H, W, C, heads, ws, shift, scale, dtype, stream);
+  RSC_CHECK_ARG(((uintptr_t)qkv & 15) == 0, "rsc_wmsa_fwd: qkv must be 16-byte aligned (TMA)");
   WinGeom g(B, H, W, wtm::WS, shift);
   CUtensorMap m7, m4, m3;
-  if (!wtm::window_maps(qkv, B, H, W, 3 * C, &m7, &m4, &m3)) return -1;
+  RSC_CHECK_ARG(wtm::window_maps(qkv, B, H, W, 3 * C, &m7, &m4, &m3), "rsc_wmsa_fwd: cuTensorMapEncodeTiled failed");
   const int num_items = B * g.nWh * g.nWw * heads;
   auto kern = wtm::wmsa_fwd_tma_kernel<8>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wtm::F_TOTAL);
@@ -900,17 +889,23 @@ int rsc_wmsa_fwd_tma(const void *qkv, const float *qkv_bias, const float *bias_t
   if (grid > num_items) grid = num_items;     // num_items is a multiple of heads
   kern<<<grid, wtm::THREADS, wtm::F_TOTAL, (cudaStream_t)stream>>>(m7, m4, m3, qkv_bias, bias_table, (__nv_bfloat16 *)out, g, C,
                                                                    heads, scale, num_items);
-  RSC_CHECK_LAUNCH("rsc_wmsa_fwd(tma)");
+  RSC_CHECK_LAUNCH("rsc_wmsa_fwd");
   return RSC_OK;
 }
 
-int rsc_wmsa_bwd_tma(const void *qkv, const float *qkv_bias, const float *bias_table, const void *dout, void *dqkv,
-                     float *dbias_table, float *dqkv_bias, int B, int H, int W, int C, int heads, int shift, float scale,
-                     void *stream) {
-  if (((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) || heads > 4 * kNumSMs) return -1;
+extern "C" int rsc_wmsa_bwd(const void *qkv, const float *qkv_bias, const float *bias_table, const void *dout, void *dqkv,
+                            float *dbias_table, float *dqkv_bias, int B, int H, int W, int C, int heads, int ws, int shift,
+                            float scale, int dtype, void *stream) {
+  static const bool force_simt = getenv("RSC_WMSA_SIMT") != nullptr;
+  if (force_simt || !tc_shape_ok(dtype, ws, shift, heads, C, B, H, W) || !qkv || !bias_table || !dout || !dqkv || !dbias_table ||
+      (dqkv_bias && !qkv_bias) || heads > 4 * kNumSMs)
+    return rsc_wmsa_bwd_simt(qkv, qkv_bias, bias_table, dout, dqkv, dbias_table, dqkv_bias, B, H, W, C, heads, ws, shift, scale,
+                             dtype, stream);
+  RSC_CHECK_ARG((((uintptr_t)qkv | (uintptr_t)dout) & 15) == 0, "rsc_wmsa_bwd: qkv / dout must be 16-byte aligned (TMA)");
   WinGeom g(B, H, W, wtm::WS, shift);
   CUtensorMap m7, m4, m3, d7, d4, d3;
-  if (!wtm::window_maps(qkv, B, H, W, 3 * C, &m7, &m4, &m3) || !wtm::window_maps(dout, B, H, W, C, &d7, &d4, &d3)) return -1;
+  RSC_CHECK_ARG(wtm::window_maps(qkv, B, H, W, 3 * C, &m7, &m4, &m3) && wtm::window_maps(dout, B, H, W, C, &d7, &d4, &d3),
+                "rsc_wmsa_bwd: cuTensorMapEncodeTiled failed");
   const int num_items = B * g.nWh * g.nWw * heads;
   auto kern = wtm::wmsa_bwd_tma_kernel;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, wtm::B_TOTAL);
@@ -919,6 +914,6 @@ int rsc_wmsa_bwd_tma(const void *qkv, const float *qkv_bias, const float *bias_t
   kern<<<grid, wtm::THREADS, wtm::B_TOTAL, (cudaStream_t)stream>>>(m7, m4, m3, d7, d4, d3, qkv_bias, bias_table,
                                                                    (__nv_bfloat16 *)dqkv, dbias_table, dqkv_bias, g, C, heads,
                                                                    scale, num_items);
-  RSC_CHECK_LAUNCH("rsc_wmsa_bwd(tma)");
+  RSC_CHECK_LAUNCH("rsc_wmsa_bwd");
   return RSC_OK;
 }

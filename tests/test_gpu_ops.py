@@ -128,8 +128,8 @@ def test_wmsa_fp32_fwd_bwd(B, H, W, shift, heads):
 @pytest.mark.parametrize('shift', [0, 3])
 @pytest.mark.parametrize('heads', [3, 4])
 def test_wmsa_bf16_fwd_bwd(B, H, W, shift, heads):
-    """bf16 forward = the tcgen05 kernel (wmsa_tc.cu); includes odd window counts (a lone
-    second unit), padded windows and both shift masks."""
+    """bf16 = the TMA-staged tcgen05 kernels (wmsa_tma.cu); includes odd window counts, padded windows
+    (also with pad + shift > 7: padding in the second-to-last window row) and both shift masks."""
     C = heads * 32
     sd = {k: v.bfloat16().float() for k, v in _msa_state(C, heads, seed=7).items()}
     g = torch.Generator().manual_seed(2)

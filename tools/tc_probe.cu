@@ -1,4 +1,4 @@
-// Stand-alone probe of the tcgen05 building blocks used by wmsa_tc.cu:
+// Stand-alone probe of the no-swizzle tcgen05 building blocks (round 1; the P / dS tiles of wmsa_tma.cu still use them):
 //   S = [Q_A;Q_B] (128x32, K-major) x [K_A;K_B]^T (128x32, K-major) -> TMEM 128x128 fp32
 //   O = P (128x64, K-major)  x  V (64 keys x 32 dims, MN-major B)   -> TMEM 128x32 fp32
 // with the no-swizzle core-matrix smem layouts, checked against a host fp32

@@ -1,6 +1,6 @@
 """Window-attention micro-benchmark (bf16, BASELINE stage geometries): CUDA-event medians with an L2 flush between
 iterations, achieved algorithmic GB/s (4 / 7 x B x Lp x C x 2 bytes) and the fraction of the measured HBM peak.
-  python tools/wbench.py [tag]     env: KB_B (batch, default 16), RSC_WMSA_V3=1 (round-1 cp.async kernels)"""
+  python tools/wbench.py [tag]     env: KB_B (batch, default 16)"""
 import json
 import os
 import sys

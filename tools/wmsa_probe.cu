@@ -75,7 +75,7 @@ struct Plan {   // up to 4 boxes per operand
 
 __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap m7, const __grid_constant__ CUtensorMap m4,
                                              const __grid_constant__ CUtensorMap m3, Plan plan, const __nv_bfloat16 *P,
-                                             float *S_out, float *O_out, float *T_out, uint8_t *raw) {
+                                             float *S_out, float *O_out, float *T_out, uint8_t *raw, long long *clk) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // [Q | K | V | P 8 KB | guard 8 KB]
   __shared__ uint64_t bar_tma, bar_mma;
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  long long t0 = clock64();
   if (tid == 0) {
     uint32_t total = 0;
     for (int k = 0; k < plan.n; ++k) total += 3 * plan.bytes[k];
@@ -111,10 +112,41 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
       }
   }
   mbar_wait(&bar_tma, 0);
+  long long t1 = clock64();
   for (int i = tid; i < (int)TILE; i += 128) raw[i] = smem[i];
   fence_before_sync();
   __syncthreads();
   const uint32_t tm = tmem_base;
+  // latency of a minimal MMA batch (2 x M128 N64 K16 + commit -> mbarrier wake-up), measured 3 times
+  __shared__ uint64_t bar_lat;
+  if (tid == 0) {
+    mbar_init(&bar_lat, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  for (int rep = 0; rep < 3; ++rep) {
+    long long a = clock64();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
+      for (int k = 0; k < 2; ++k)
+        mma_bf16_ss(tm, desc_sw64(sQ + k * 32, 16, 512), desc_sw64(sK + k * 32, 16, 512), idesc_s, k > 0);
+      mma_commit(&bar_lat);
+    }
+    mbar_wait(&bar_lat, rep & 1);
+    long long b = clock64();
+    fence_after_sync();
+    uint32_t r[32];
+    if (warp < 4) {
+      tmem_ld32(tm + ((uint32_t)((warp & 3) * 32) << 16), r);
+      tmem_ld_wait();
+    }
+    long long c = clock64();
+    if (tid == 0) clk[2 + 2 * rep] = b - a, clk[3 + 2 * rep] = c - b;
+    fence_before_sync();
+    __syncthreads();
+  }
+  if (tid == 0) clk[0] = t1 - t0;
   if (tid == 0) {
     fence_after_sync();
     const uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
@@ -183,6 +215,9 @@ int main(int argc, char **argv) {
   CHECK(cudaMalloc(&dO, 64 * 32 * 4));
   CHECK(cudaMalloc(&dT, 64 * 32 * 4));
   CHECK(cudaMalloc(&draw, TILE));
+  long long *dclk;
+  CHECK(cudaMalloc(&dclk, 16 * sizeof(long long)));
+  CHECK(cudaMemset(dclk, 0, 16 * sizeof(long long)));
   EncodeTiled encode = nullptr;
   cudaDriverEntryPointQueryResult qres;
   CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres));
@@ -243,11 +278,15 @@ int main(int argc, char **argv) {
     }
   }
   CHECK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE + 16384));
-  probe<<<1, 128, 3 * TILE + 16384>>>(maps[0], maps[1], maps[2], plan, dP, dS, dO, dT, draw);
+  probe<<<1, 128, 3 * TILE + 16384>>>(maps[0], maps[1], maps[2], plan, dP, dS, dO, dT, draw, dclk);
   CHECK(cudaGetLastError());
   CHECK(cudaDeviceSynchronize());
   std::vector<float> S(64 * 64), O(64 * 32), T(64 * 32);
   std::vector<uint8_t> raw(TILE);
+  long long clk[16];
+  CHECK(cudaMemcpy(clk, dclk, sizeof(clk), cudaMemcpyDeviceToHost));
+  printf("CLOCKS : TMA issue->landed %lld | MMA batch issue->wake-up %lld %lld %lld | tcgen05.ld+wait %lld %lld %lld\n", clk[0], clk[2],
+         clk[4], clk[6], clk[3], clk[5], clk[7]);
   CHECK(cudaMemcpy(S.data(), dS, S.size() * 4, cudaMemcpyDeviceToHost));
   CHECK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
   CHECK(cudaMemcpy(T.data(), dT, T.size() * 4, cudaMemcpyDeviceToHost));
