@@ -296,6 +296,31 @@ int rsc_adamw_step(float *param, const float *grad, float *exp_avg, float *exp_a
  * layer (replaces ATen's sum(0) reduce in AddmmBackward / nn.Linear backward). */
 int rsc_colsum(const void *x, float *y, int64_t rows, int C, int dtype, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Linear layers as tcgen05 GEMMs with the surrounding element-wise passes in the
+ * epilogue.  Replaces, for the bf16 compute path, nn.Linear (ATen addmm -> cuBLAS)
+ * + the activation kernel behind mmcv FFN / the Swin MLP / qkv / proj
+ * (cfg MTL_slvlcls_...py:9-25, :34-50) and their
+ * autograd backward (mm, mm, sum(0), GeluBackward / threshold_backward).
+ * All matrices are row-major bf16 with leading dimensions in ELEMENTS (multiples
+ * of 8), 16-byte aligned; accumulation is fp32; bias / db are float.
+ *
+ * rsc_linear_fwd:  Y (M,N) = act(X (M,K) W (N,K)^T + bias)
+ *     act 0: none.  act 1: GELU (torch's erf form); the pre-activation
+ *     H = X W^T + bias is ALSO written (bf16) to `h` for the backward.  act 2: ReLU.
+ * rsc_linear_dx:   dX (M,K) = (dY (M,N) W (N,K)) * act'(aux)
+ *     act 1: aux = the saved H; act 2: aux = the saved Y (sign only); aux (M,K)
+ *     shares dX's leading dimension.  act 0: aux ignored.
+ * rsc_linear_dw:   dW (N,K) += dY (M,N)^T X (M,K)   (float, ACCUMULATED),
+ *                  db (N)   += column sums of dY     (float, ACCUMULATED; may be NULL)
+ * ---------------------------------------------------------------------- */
+int rsc_linear_fwd(const void *x, const void *w, const float *bias, void *y, void *h, int64_t M, int N, int K, int64_t ldx,
+                   int64_t ldw, int64_t ldy, int act, void *stream);
+int rsc_linear_dx(const void *dy, const void *w, const void *aux, void *dx, int64_t M, int N, int K, int64_t lddy,
+                  int64_t ldw, int64_t lddx, int act, void *stream);
+int rsc_linear_dw(const void *dy, const void *x, float *dw, float *db, int64_t M, int N, int K, int64_t lddy, int64_t ldx,
+                  int64_t lddw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,120 @@
+"""GPU parity of the tcgen05 Linear kernels (csrc/gemm_tc.cu) through the C ABI: rsc_linear_fwd / rsc_linear_dx /
+rsc_linear_dw against fp32 torch on the same bf16-rounded operands.  Tolerances: the outputs are bf16 (relative
+rounding 2^-9) and the GELU is the one-tanh fit of the erf form (|error| < 3e-4 absolute)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (M, N, K): Swin stage widths (96..768, x3 for qkv, x4 for the MLP), encoder FFN 256 <-> 2048, ragged token counts,
+# N / K that are not multiples of the tile (288 = 3 x 96, 96 < 128, 48 = patch embedding)
+SHAPES = [(300, 96, 96), (1000, 288, 96), (257, 384, 96), (640, 96, 384), (512, 192, 768), (130, 2048, 256),
+          (1000, 256, 2048), (333, 768, 3072), (129, 3072, 768), (77, 96, 48), (4000, 576, 192), (128, 128, 64),
+          (1, 256, 256), (5000, 1152, 384)]
+
+
+def _call(name, *args):
+    from rscotr_b200 import _lib
+    _lib.call(name, *args)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def _mk(M, N, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(M, K, generator=g)).bfloat16()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, generator=g)
+    return x, w, b
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES)
+@pytest.mark.parametrize('act', [0, 1, 2])
+@pytest.mark.parametrize('with_bias', [True, False])
+def test_linear_fwd(M, N, K, act, with_bias):
+    x, w, b = _mk(M, N, K, M + N + K + act)
+    h_ref = x.float() @ w.float().t() + (b if with_bias else 0)
+    hb = h_ref.bfloat16().float()
+    y_ref = F.gelu(hb) if act == 1 else (h_ref.relu() if act == 2 else h_ref)
+    xg, wg, bg = x.cuda(), w.cuda(), b.cuda()
+    y = torch.full((M, N), float('nan'), dtype=torch.bfloat16, device='cuda')
+    h = torch.full((M, N), float('nan'), dtype=torch.bfloat16, device='cuda') if act == 1 else None
+    _call('rsc_linear_fwd', xg.data_ptr(), wg.data_ptr(), bg.data_ptr() if with_bias else None, y.data_ptr(),
+          h.data_ptr() if h is not None else None, M, N, K, K, K, N, act, _stream())
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    assert rel(y, y_ref) < (6e-3 if act == 1 else 4e-3)
+    if act == 1:
+        assert rel(h, h_ref) < 4e-3
+        # |GELU error| bound of the one-tanh fit, evaluated on the kernel's own (rounded) pre-activation
+        assert (y.float().cpu() - F.gelu(h.float().cpu())).abs().max() < 3e-4 + 2 ** -8 * y.float().abs().max().item()
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES)
+@pytest.mark.parametrize('act', [0, 1, 2])
+def test_linear_dx(M, N, K, act):
+    """dX (M,K) = (dY (M,N) W (N,K)) * act'(aux)"""
+    g = torch.Generator().manual_seed(M * 7 + N + K + act)
+    dy = torch.randn(M, N, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) * N ** -0.5).bfloat16()
+    aux = (torch.randn(M, K, generator=g) * 1.5).bfloat16()
+    ref = dy.float() @ w.float()
+    if act == 1:
+        a = aux.float().clone().requires_grad_(True)
+        F.gelu(a).sum().backward()
+        ref = ref * a.grad
+    elif act == 2:
+        ref = ref * (aux.float() > 0)
+    dx = torch.full((M, K), float('nan'), dtype=torch.bfloat16, device='cuda')
+    dyg, wg, auxg = dy.cuda(), w.cuda(), aux.cuda()          # (named: a temporary would be freed before the launch)
+    _call('rsc_linear_dx', dyg.data_ptr(), wg.data_ptr(), auxg.data_ptr() if act else None, dx.data_ptr(),
+          M, N, K, N, K, K, act, _stream())
+    torch.cuda.synchronize()
+    assert torch.isfinite(dx).all()
+    assert rel(dx, ref) < (8e-3 if act == 1 else 4e-3)
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES + [(40000, 384, 96), (26588, 2048, 256)])
+@pytest.mark.parametrize('with_db', [True, False])
+def test_linear_dw(M, N, K, with_db):
+    """dW (N,K) += dY^T X, db (N) += colsum(dY): accumulated on top of existing values"""
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    dy = torch.randn(M, N, generator=g).bfloat16()
+    x = torch.randn(M, K, generator=g).bfloat16()
+    dw0 = torch.randn(N, K, generator=g)
+    db0 = torch.randn(N, generator=g)
+    dw_ref = dw0.double() + dy.double().t() @ x.double()
+    db_ref = db0.double() + dy.double().sum(0)
+    dw, db = dw0.cuda(), db0.cuda()
+    dyg, xg = dy.cuda(), x.cuda()
+    _call('rsc_linear_dw', dyg.data_ptr(), xg.data_ptr(), dw.data_ptr(), db.data_ptr() if with_db else None,
+          M, N, K, N, K, K, _stream())
+    torch.cuda.synchronize()
+    assert rel(dw, dw_ref) < 1e-4
+    if with_db:
+        assert rel(db, db_ref) < 1e-4
+    else:
+        assert torch.equal(db.cpu(), db0)
+
+
+def test_linear_leading_dimensions():
+    """operands that are column slices of wider matrices (the q / k / v thirds of a packed projection)"""
+    M, N, K = 500, 192, 96
+    g = torch.Generator().manual_seed(5)
+    xw = torch.randn(M, 3 * K, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16().cuda()
+    yw = torch.zeros(M, 2 * N, dtype=torch.bfloat16, device='cuda')
+    x = xw[:, K:2 * K]
+    y = yw[:, N:]
+    _call('rsc_linear_fwd', x.data_ptr(), w.data_ptr(), None, y.data_ptr(), None, M, N, K, 3 * K, K, 2 * N, 0, _stream())
+    torch.cuda.synchronize()
+    assert rel(y, x.float() @ w.float().t()) < 4e-3
+    assert torch.count_nonzero(yw[:, :N]) == 0
