@@ -151,17 +151,23 @@ struct Params {
   int n_store;             // outputs: 1 (D) or 2 (D and D2 = the pre-activation H of EPI_BIAS_GELU)
 };
 
-// smem carve-up (all tile bases 1024-byte aligned)
-template <int BN, int STAGES>
+// smem carve-up (all tile bases 1024-byte aligned).  Every epilogue warp owns a private staging area for its
+// (32 rows x BN/2 columns) part of the output tile: [BN/64 blocks of 32 columns][32 rows][64 B], SWIZZLE_64B, stored
+// with its own TMA ops -- the eight warps never meet at a barrier.  One-output epilogues double-buffer it (the store
+// of tile i is still reading while tile i+1 is written); the two-tile epilogues (GELU forward: Y and H; activation
+// backward: aux in, dX out) keep one buffer per tile.
+template <int BN, int STAGES, int EPI>
 struct Smem {
+  static constexpr bool TWO = EPI == EPI_BIAS_GELU || EPI == EPI_DGELU || EPI == EPI_DRELU;
   static constexpr uint32_t A_BYTES = BM * BK * 2;            // 16 KB
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
-  static constexpr uint32_t STAGING = BM * BN * 2;            // bf16 output tile: [BN/32 blocks][128 rows][64 B]
+  static constexpr uint32_t WARP_STAGING = 32 * (BN / 2) * 2; // one warp, one buffer
+  static constexpr uint32_t STAGING = EPI_WARPS * WARP_STAGING;       // = one bf16 output tile
   static constexpr uint32_t OFF_STAGING = STAGES * STAGE;
-  static constexpr uint32_t OFF_STAGING2 = OFF_STAGING + STAGING;     // second output / aux input tile
-  static constexpr uint32_t OFF_BIAS = OFF_STAGING2 + STAGING;
-  static constexpr uint32_t OFF_BAR = OFF_BIAS + BN * 4;
+  static constexpr uint32_t OFF_STAGING2 = OFF_STAGING + STAGING;     // second buffer / second output / aux input
+  static constexpr uint32_t OFF_BIAS = OFF_STAGING2 + STAGING;        // [2 tile parities][BN] floats
+  static constexpr uint32_t OFF_BAR = OFF_BIAS + 2 * BN * 4;
   static constexpr uint32_t TOTAL = OFF_BAR + 256;
 };
 
@@ -170,7 +176,7 @@ template <int BN, int STAGES, bool B_MN, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, Params p) {
-  using S = Smem<BN, STAGES>;
+  using S = Smem<BN, STAGES, EPI>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
   if (sb & 1023u) __trap();
@@ -178,8 +184,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint64_t *empty = full + STAGES;
   uint64_t *tfull = empty + STAGES;      // [2] accumulator ready
   uint64_t *tempty = tfull + 2;          // [2] accumulator drained
-  uint64_t *auxbar = tempty + 2;         // aux tile landed (EPI_DGELU / EPI_DRELU)
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(auxbar + 1);
+  uint64_t *auxbar = tempty + 2;         // [EPI_WARPS] aux part landed (EPI_DGELU / EPI_DRELU), one per warp
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(auxbar + EPI_WARPS);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
@@ -188,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
     for (int a = 0; a < 2; ++a) mbar_init(&tfull[a], 1), mbar_init(&tempty[a], EPI_WARPS);
-    mbar_init(auxbar, 1);
+    for (int e = 0; e < EPI_WARPS; ++e) mbar_init(&auxbar[e], 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -251,104 +257,103 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   } else {
-    // ===== epilogue: warp e owns TMEM lanes 32 (e % 4) .. +31 (its hardware quadrant) and column half e / 4 =====
-    const int q = warp & 3, half = (warp - 2) >> 2;
-    const int row = q * 32 + lane;                              // row of the tile
+    // ===== epilogue: warp e owns TMEM lanes 32 (e % 4) .. +31 (its hardware quadrant) and column half e / 4;
+    //       it stages and stores its (32 rows x BN/2 columns) part on its own: no barrier between the warps =====
+    const int q = warp & 3, half = (warp - 2) >> 2, e = warp - 2;
     constexpr int HC = BN / 2;                                  // columns per warp
-    static_assert(HC % 16 == 0, "BN must be a multiple of 32");
-    float *sbias = reinterpret_cast<float *>(smem + S::OFF_BIAS);
-    const int et = threadIdx.x - 64;                            // 0..255
+    static_assert(HC % 32 == 0, "BN must be a multiple of 64");
+    const uint32_t stg0 = sb + S::OFF_STAGING + e * S::WARP_STAGING, stg1 = sb + S::OFF_STAGING2 + e * S::WARP_STAGING;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
-      const int m0 = (tile / n_blks) * BM, n0 = (tile % n_blks) * BN;
-      // staging is free once the previous tile's stores have read it
-      if (et == 0) tma_store_wait_read();
-      epi_barrier();
-      for (int c = et; c < BN; c += EPI_WARPS * 32) sbias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
-      if (AUX_IN && et == 0) {                                  // the saved H (or Y) tile of this output tile
-        mbar_expect_tx(auxbar, S::STAGING);
-#pragma unroll
-        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + S::OFF_STAGING2 + j * (BM * 64), &tmD2, auxbar, n0 + j * 32, m0);
+      const int m0 = (tile / n_blks) * BM + q * 32, n0 = (tile % n_blks) * BN + half * HC;   // this warp's part
+      // which staging buffer; it is free once the stores that last read it are done reading
+      const uint32_t out = (!S::TWO && (local & 1)) ? stg1 : stg0;
+      if (lane == 0) {
+        if (S::TWO) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       }
-      epi_barrier();
+      __syncwarp();
+      if (AUX_IN) {                                             // the saved H (or Y) values of this part
+        if (lane == 0) {
+          mbar_expect_tx(&auxbar[e], S::WARP_STAGING);
+#pragma unroll
+          for (int j = 0; j < HC / 32; ++j) tma_load_2d(stg1 + j * 2048, &tmD2, &auxbar[e], n0 + j * 32, m0);
+        }
+      }
       mbar_wait(&tfull[acc], (local >> 1) & 1);
       fence_after_sync();
-      if (AUX_IN) mbar_wait(auxbar, local & 1);
+      // bias slice of this warp's columns.  The four warps of a column half write the SAME values; the slot alternates
+      // with the tile parity: once this tile's accumulator is ready, every warp has drained the tile before last (the
+      // MMA of this tile waited for that), i.e. nobody still reads this slot
+      float *sbias = reinterpret_cast<float *>(smem + S::OFF_BIAS) + (local & 1) * BN + half * HC;
+      for (int c = lane; c < HC; c += 32) sbias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      __syncwarp();
+      if (AUX_IN) mbar_wait(&auxbar[e], local & 1);
       const uint32_t taddr = tm + ((uint32_t)(q * 32) << 16) + acc * BN + half * HC;
 #pragma unroll 1
       for (int c0 = 0; c0 < HC; c0 += 32) {
-        // (HC may be 48, 96: the last chunk is 16 columns wide)
-        const int w = HC - c0 >= 32 ? 32 : 16;
+        if (n0 + c0 >= p.N) break;                              // ragged last tile: nothing to store from here on
         uint32_t r[32];
-        if (w == 32) {
-          tmem_ld32(taddr + c0, r);
-        } else {
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-              : "r"(taddr + c0)
-              : "memory");
-        }
+        tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                           // 8-column groups = 16-byte chunks of the bf16 row
-          if (j * 8 >= w) break;
-          const int col = half * HC + c0 + j * 8;               // column inside the tile
-          const int blk = col >> 5, chunk = (col & 31) >> 3;    // 32-column store block, 16-byte chunk in its 64-byte row
-          const uint32_t soff = blk * (BM * 64) + row * 64 + ((chunk ^ ((row >> 1) & 3)) * 16);
+          const int col = c0 + j * 8;                           // column inside this warp's part
+          // 32-column store block (2 KB: 32 rows x 64 B, SWIZZLE_64B), 16-byte chunk j of this lane's row
+          const uint32_t soff = (c0 >> 5) * 2048 + lane * 64 + ((j ^ ((lane >> 1) & 3)) * 16);
           float2 v[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 b2 = *reinterpret_cast<const float2 *>(sbias + col + 2 * e);
-            v[e] = add2(make_float2(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1])), b2);
+          for (int k = 0; k < 4; ++k) {
+            const float2 b2 = *reinterpret_cast<const float2 *>(sbias + col + 2 * k);
+            v[k] = add2(make_float2(__uint_as_float(r[j * 8 + 2 * k]), __uint_as_float(r[j * 8 + 2 * k + 1])), b2);
           }
           if (EPI == EPI_BIAS_GELU) {
             uint4 hq;
             hq.x = pack_bf16(v[0].x, v[0].y), hq.y = pack_bf16(v[1].x, v[1].y), hq.z = pack_bf16(v[2].x, v[2].y),
             hq.w = pack_bf16(v[3].x, v[3].y);
-            st_shared16(sb + S::OFF_STAGING2 + soff, hq);       // H (pre-activation, bf16) is kept for the backward
+            st_shared16(stg1 + soff, hq);                       // H (pre-activation, bf16) is kept for the backward
             // the activation sees the ROUNDED pre-activation: forward and backward differentiate the same function
             v[0] = gelu2(unpack_bf16(hq.x)), v[1] = gelu2(unpack_bf16(hq.y)), v[2] = gelu2(unpack_bf16(hq.z)),
             v[3] = gelu2(unpack_bf16(hq.w));
           } else if (EPI == EPI_BIAS_RELU) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e].x = fmaxf(v[e].x, 0.f), v[e].y = fmaxf(v[e].y, 0.f);
+            for (int k = 0; k < 4; ++k) v[k].x = fmaxf(v[k].x, 0.f), v[k].y = fmaxf(v[k].y, 0.f);
           } else if (EPI == EPI_DGELU || EPI == EPI_DRELU) {
-            const uint4 aq = ld_shared16(sb + S::OFF_STAGING2 + soff);
+            const uint4 aq = ld_shared16(stg1 + soff);
             const uint32_t aw[4] = {aq.x, aq.y, aq.z, aq.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 a = unpack_bf16(aw[e]);
-              if (EPI == EPI_DGELU) v[e] = mul2(v[e], gelu_grad2(a));
-              else v[e].x = a.x > 0.f ? v[e].x : 0.f, v[e].y = a.y > 0.f ? v[e].y : 0.f;
+            for (int k = 0; k < 4; ++k) {
+              const float2 a = unpack_bf16(aw[k]);
+              if (EPI == EPI_DGELU) v[k] = mul2(v[k], gelu_grad2(a));
+              else v[k].x = a.x > 0.f ? v[k].x : 0.f, v[k].y = a.y > 0.f ? v[k].y : 0.f;
             }
           }
           uint4 o;
           o.x = pack_bf16(v[0].x, v[0].y), o.y = pack_bf16(v[1].x, v[1].y), o.z = pack_bf16(v[2].x, v[2].y),
           o.w = pack_bf16(v[3].x, v[3].y);
-          st_shared16(sb + S::OFF_STAGING + soff, o);
+          st_shared16(out + soff, o);
         }
       }
-      // this warp has drained its part of the accumulator
+      // this warp has drained its part of the accumulator; its staged rows go out through TMA
       fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
       fence_async_smem();
-      epi_barrier();
-      if (et == 0) {
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tempty[acc]);
+        if (m0 < p.M) {
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
-          if (n0 + j * 32 < p.N) {
-            tma_store_2d(&tmD, sb + S::OFF_STAGING + j * (BM * 64), n0 + j * 32, m0);
-            if (EPI == EPI_BIAS_GELU) tma_store_2d(&tmD2, sb + S::OFF_STAGING2 + j * (BM * 64), n0 + j * 32, m0);
+          for (int j = 0; j < HC / 32; ++j) {
+            if (n0 + j * 32 < p.N) {
+              tma_store_2d(&tmD, out + j * 2048, n0 + j * 32, m0);
+              if (EPI == EPI_BIAS_GELU) tma_store_2d(&tmD2, stg1 + j * 2048, n0 + j * 32, m0);
+            }
           }
         }
         tma_store_commit();
       }
     }
-    if (et == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
   fence_before_sync();
   __syncthreads();
@@ -385,7 +390,7 @@ static bool map2d(CUtensorMap *m, const void *base, int64_t rows, int64_t cols, 
 template <int BN, int STAGES, bool B_MN, int EPI>
 static int launch(const CUtensorMap &tA, const CUtensorMap &tB, const CUtensorMap &tD, const CUtensorMap &tD2, const Params &p,
                   cudaStream_t st) {
-  using S = Smem<BN, STAGES>;
+  using S = Smem<BN, STAGES, EPI>;
   static_assert(S::TOTAL <= 227 * 1024, "shared memory");
   auto kern = gemm_kernel<BN, STAGES, B_MN, EPI>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -403,21 +408,21 @@ static int dispatch_bn(int BN, const CUtensorMap &tA, const CUtensorMap &tB, con
     case 128: return launch<128, 4, B_MN, EPI>(tA, tB, tD, tD2, p, st);
     case 192: return launch<192, 3, B_MN, EPI>(tA, tB, tD, tD2, p, st);
     case 256: return launch<256, 2, B_MN, EPI>(tA, tB, tD, tD2, p, st);
-    case 96:
-      if (!B_MN) return launch<96, 5, false, EPI>(tA, tB, tD, tD2, p, st);
   }
   return -1;
 }
 
-// largest tile width that wastes no columns; MN-major B needs 64-column atoms
-static int pick_bn(int N, bool b_mn) {
-  if (!b_mn && N % 96 == 0 && N % 192 != 0 && N % 128 != 0) return 96;
-  for (int bn : {256, 192, 128, 64})
-    if (N % bn == 0) return bn;
-  if (!b_mn && N % 96 == 0) return 96;
-  for (int bn : {64, 128, 192, 256})   // one ragged tile (TMA zero-fills / clips the overhang)
-    if (N <= bn) return bn;
-  return 128;
+// tile width: the candidate (256, 192, 128; 64 for narrow outputs) with the least padded columns, the wider one on a
+// tie.  A ragged last tile costs nothing but idle MMA columns: TMA zero-fills the loads and the epilogue skips the
+// column blocks beyond N.
+static int pick_bn(int N) {
+  if (N <= 64) return 64;
+  int best = 128, waste = 1 << 30;
+  for (int bn : {128, 192, 256}) {
+    const int w = (N + bn - 1) / bn * bn - N;
+    if (w <= waste) best = bn, waste = w;
+  }
+  return best;
 }
 
 }  // namespace gemm
@@ -434,12 +439,12 @@ extern "C" int rsc_linear_fwd(const void *x, const void *w, const float *bias, v
   RSC_CHECK_ARG(N % 8 == 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && ldy % 8 == 0 && M < (1ll << 31),
                 "rsc_linear_fwd: N, K and the leading dimensions must be multiples of 8 (16-byte TMA strides)");
   RSC_CHECK_ARG((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)h) & 15) == 0, "rsc_linear_fwd: 16-byte alignment");
-  const int BN = gemm::pick_bn(N, false);
+  const int BN = gemm::pick_bn(N);
   CUtensorMap tA, tB, tD, tD2;
   bool ok = gemm::map2d(&tA, x, M, K, ldx, gemm::BK, gemm::BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
             gemm::map2d(&tB, w, N, K, ldw, gemm::BK, BN, CU_TENSOR_MAP_SWIZZLE_128B) &&
-            gemm::map2d(&tD, y, M, N, ldy, 32, gemm::BM, CU_TENSOR_MAP_SWIZZLE_64B) &&
-            gemm::map2d(&tD2, act == 1 ? h : y, M, N, ldy, 32, gemm::BM, CU_TENSOR_MAP_SWIZZLE_64B);
+            gemm::map2d(&tD, y, M, N, ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+            gemm::map2d(&tD2, act == 1 ? h : y, M, N, ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   RSC_CHECK_ARG(ok, "rsc_linear_fwd: cuTensorMapEncodeTiled failed");
   gemm::Params p{(int)M, N, K, bias, act == 1 ? 2 : 1};
   int rc;
@@ -461,12 +466,12 @@ extern "C" int rsc_linear_dx(const void *dy, const void *w, const void *aux, voi
                 "rsc_linear_dx: N, K and the leading dimensions must be multiples of 8 (16-byte TMA strides)");
   RSC_CHECK_ARG((((uintptr_t)dy | (uintptr_t)w | (uintptr_t)dx | (uintptr_t)aux) & 15) == 0, "rsc_linear_dx: 16-byte alignment");
   // GEMM view: D (M, K) = sum_n dY(m, n) W(n, k): contraction length N, output width K, B read MN-major
-  const int BN = gemm::pick_bn(K, true);
+  const int BN = gemm::pick_bn(K);
   CUtensorMap tA, tB, tD, tD2;
   bool ok = gemm::map2d(&tA, dy, M, N, lddy, gemm::BK, gemm::BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
             gemm::map2d(&tB, w, N, K, ldw, 64, gemm::BK, CU_TENSOR_MAP_SWIZZLE_128B) &&
-            gemm::map2d(&tD, dx, M, K, lddx, 32, gemm::BM, CU_TENSOR_MAP_SWIZZLE_64B) &&
-            gemm::map2d(&tD2, act ? aux : dx, M, K, lddx, 32, gemm::BM, CU_TENSOR_MAP_SWIZZLE_64B);
+            gemm::map2d(&tD, dx, M, K, lddx, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+            gemm::map2d(&tD2, act ? aux : dx, M, K, lddx, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   RSC_CHECK_ARG(ok, "rsc_linear_dx: cuTensorMapEncodeTiled failed");
   gemm::Params p{(int)M, K, N, nullptr, 1};
   int rc;
