@@ -243,9 +243,23 @@ class FFN(nn.Module):
         self.dropout_layer = build_dropout(dropout_layer)
         self.add_identity = add_identity
 
+    def _fused(self, x, with_last_bias):
+        """the two-Linear FFN as ops.mlp (activation and its gradient in the GEMM epilogues) when it applies, else None"""
+        if len(self.layers) != 3:
+            return None
+        (lin, act, drop), last = self.layers[0], self.layers[1]
+        code = ops.ACT_RELU if isinstance(act, nn.ReLU) else (
+            ops.ACT_GELU if isinstance(act, nn.GELU) and act.approximate == 'none' else None)
+        if code is None or (self.training and drop.p > 0.) or not ops.mlp_supported(x, lin.weight, lin.bias, last.weight):
+            return None
+        return ops.mlp(x, lin.weight, lin.bias, last.weight, last.bias if with_last_bias else None, code)
+
     def _mlp(self, x):
         """self.layers(x) with Linear + bias + activation of the hidden layers as GEMM + ONE fused pass
         (ops.bias_relu / ops.bias_gelu: the bias gradient comes out of the activation's backward pass)."""
+        z = self._fused(x, True)
+        if z is not None:
+            return self.layers[-1](z)
         for layer in list(self.layers)[:-2]:
             lin, act = layer[0], layer[1]
             code = ops.ACT_RELU if isinstance(act, nn.ReLU) else (
@@ -263,6 +277,9 @@ class FFN(nn.Module):
                                     or (isinstance(self.dropout_layer, DropPath) and self.dropout_layer.drop_prob > 0.))
         if active or not self.add_identity or last.bias is None:
             return None
+        z = self._fused(x, False)
+        if z is not None:
+            return z, last.bias
         for layer in list(self.layers)[:-2]:
             lin, act = layer[0], layer[1]
             code = ops.ACT_RELU if isinstance(act, nn.ReLU) else (

@@ -116,8 +116,12 @@ class SwinBlock(nn.Module):
         x1, n2 = ops.add_ln(x, a, m.proj.bias, self.attn.drop.scale_vec(x), self.norm2.weight, self.norm2.bias,
                             self.norm2.eps)
         fc1, fc2 = self.ffn.layers[0][0], self.ffn.layers[1]
-        g = ops.bias_gelu(ops.linear(n2, fc1.weight, None), fc1.bias)
-        f = ops.linear(g, fc2.weight, None)
+        if ops.mlp_supported(n2, fc1.weight, fc1.bias, fc2.weight):
+            # both Linears on the tcgen05 GEMMs: bias + GELU in fc1's epilogue, GELU' in the epilogue of fc2's dX
+            f = ops.mlp(n2, fc1.weight, fc1.bias, fc2.weight, None, ops.ACT_GELU)
+        else:
+            g = ops.bias_gelu(ops.linear(n2, fc1.weight, None), fc1.bias)
+            f = ops.linear(g, fc2.weight, None)
         s2 = self.ffn.dropout_layer.scale_vec(x)
         if next_norm is not None:
             return ops.add_ln(x1, f, fc2.bias, s2, next_norm.weight, next_norm.bias, next_norm.eps)

@@ -763,12 +763,108 @@ def colsum(x2d, out=None):
     return y
 
 
+# ---- tcgen05 GEMM entry points (csrc/gemm_tc.cu) ----------------------------------------------------------
+# RSC_OWN_GEMM=0 sends every Linear back to the library GEMMs (A/B switch for the benchmarks)
+_OWN_GEMM = __import__('os').environ.get('RSC_OWN_GEMM', '1') != '0'
+
+
+def _tc2d(t):
+    """a bf16 matrix the TMA descriptors can address: last dim contiguous, 16-byte aligned rows"""
+    return (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 8 == 0 and
+            t.shape[1] % 8 == 0 and t.data_ptr() % 16 == 0 and t.shape[0] > 0)
+
+
+_TC_MIN_ROWS = 4096     # fewer token rows than this: the fixed cost of a persistent 200 KB-smem kernel (TMEM allocation,
+                        # descriptor fetch, pipeline fill) outweighs the fused epilogue; the decoders' small GEMMs stay on
+                        # the library
+
+
+def _tc_linear_ok(x2, w):
+    return _OWN_GEMM and _tc2d(x2) and _tc2d(w) and w.shape[0] % 8 == 0 and x2.shape[0] >= _TC_MIN_ROWS
+
+
+# Measured on B200 (profiles/r02_gbench_*.jsonl): the single-CTA kernels match or beat the library where the GEMM is
+# memory-bound and wherever an element-wise pass rides in the epilogue; a PLAIN GEMM with a long contraction
+# (>= 512) is tensor-bound and the library's 2-CTA kernels are ~1.5x faster there.
+def _own_plain(contraction):
+    return contraction < 512
+
+
+def _own_dw(M, N, K):
+    return not (M <= 16384 and N * K >= (1 << 20))
+
+
+def gemm_fwd(x2, w, bias32, act=0):
+    """act(x2 w^T + bias) -> (y, h); act: 0 none, 1 GELU (h = pre-activation, kept for the backward), 2 ReLU"""
+    M, K = x2.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=torch.bfloat16, device=x2.device)
+    h = torch.empty_like(y) if act == 1 else None
+    with torch.cuda.device(x2.device):
+        call('rsc_linear_fwd', x2.data_ptr(), w.data_ptr(), _p(bias32), y.data_ptr(), _p(h), M, N, K, x2.stride(0),
+             w.stride(0), N, act, _stream(), alg_bytes=2 * (M * K + N * K + M * N * (2 if act == 1 else 1)))
+    return y, h
+
+
+def gemm_dx(dy2, w, aux=None, act=0):
+    """(dy2 w) * act'(aux): act 1 -> aux = saved pre-activation, act 2 -> aux = saved ReLU output"""
+    M, N = dy2.shape
+    K = w.shape[1]
+    dx = torch.empty(M, K, dtype=torch.bfloat16, device=dy2.device)
+    with torch.cuda.device(dy2.device):
+        call('rsc_linear_dx', dy2.data_ptr(), w.data_ptr(), _p(aux), dx.data_ptr(), M, N, K, dy2.stride(0), w.stride(0), K,
+             act, _stream(), alg_bytes=2 * (M * N + N * K + M * K * (2 if act else 1)))
+    return dx
+
+
+def gemm_dw(dy2, x2, dw32, db32):
+    """dw32 (N,K fp32, row stride dw32.stride(0)) += dy2^T x2; db32 (N fp32, or None) += column sums of dy2"""
+    M, N = dy2.shape
+    K = x2.shape[1]
+    with torch.cuda.device(dy2.device):
+        call('rsc_linear_dw', dy2.data_ptr(), x2.data_ptr(), dw32.data_ptr(), _p(db32), M, N, K, dy2.stride(0), x2.stride(0),
+             dw32.stride(0), _stream(), alg_bytes=2 * (M * N + M * K))
+
+
+def _accumulate_dw(dy2, x2, gw, gb, wdt, bdt, wshape, want_db):
+    """weight / bias gradient of y = x W^T + b: into the flat fp32 views when present (returns None, None), else fresh"""
+    M, N = dy2.shape
+    K = x2.shape[1]
+    dw = db = None
+    tc = _OWN_GEMM and _tc2d(x2) and _tc2d(dy2) and M >= _TC_MIN_ROWS and _own_dw(M, N, K)
+    if tc and (gw is None or (gw.dtype == torch.float32 and gw.stride(1) == 1 and gw.stride(0) % 4 == 0 and gw.data_ptr() % 16 == 0)):
+        tw = gw if gw is not None else torch.zeros(N, K, dtype=torch.float32, device=dy2.device)
+        tb = None
+        if want_db:
+            tb = gb if gb is not None else torch.zeros(N, dtype=torch.float32, device=dy2.device)
+        gemm_dw(dy2, x2, tw, tb)
+        if gw is None:
+            dw = tw.to(wdt).view(wshape)
+        if want_db and gb is None:
+            db = tb.to(bdt)
+        return dw, db
+    if gw is not None:
+        if dy2.dtype == torch.float32:
+            torch.addmm(gw, dy2.t(), x2, out=gw)
+        else:
+            torch.addmm(gw, dy2.t(), x2, out_dtype=torch.float32, out=gw)
+    else:
+        dw = torch.mm(dy2.t(), x2).to(wdt).view(wshape)
+    if want_db:
+        if gb is not None:
+            colsum(dy2, out=gb)
+        else:
+            db = colsum(dy2).to(bdt)
+    return dw, db
+
+
 class _Linear(torch.autograd.Function):
-    """y = x W^T + b with library GEMMs; backward: dx = dy W, dW = dy^T x (GEMMs), db = rsc_colsum(dy).
-    Runs in the dtype of x.  When the step engine has attached its flat buffers to the parameters
-    (`_rsc_lp` = bf16 shadow, `_rsc_g` = fp32 gradient view) the weight is read from the shadow (no cast
-    kernel) and dW / db are ACCUMULATED straight into the flat gradient buffer in fp32 (GEMM with
-    beta = 1, colsum with atomics) -- autograd then sees no gradient for them."""
+    """y = x W^T + b.  bf16: the tcgen05 kernels of csrc/gemm_tc.cu (forward with the bias in the epilogue, dX with the
+    weight read MN-major, dW + db in one kernel) where they are at least as fast as the library, see _own_plain;
+    otherwise library GEMMs with db from rsc_colsum.  Runs in the dtype of x.  When the step engine has attached its
+    flat buffers to the parameters (`_rsc_lp` = bf16 shadow, `_rsc_g` = fp32 gradient view) the weight is read from
+    the shadow (no cast kernel) and dW / db are ACCUMULATED straight into the flat gradient buffer in fp32 --
+    autograd then sees no gradient for them."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, w, b, gw, gb):
@@ -776,7 +872,11 @@ class _Linear(torch.autograd.Function):
         # plain 2-D row-major operand: tensors like (N, 1, C) with strides (C, N*C, 1) are "contiguous" for torch but
         # send F.linear's 3-D path to pathological cuBLAS kernels (a 512x8-tile GEMM, 30x slower, was observed)
         x2 = x.reshape(-1, x.shape[-1])
-        y = torch.nn.functional.linear(x2, w, b).view(*x.shape[:-1], w.shape[0])
+        if _tc_linear_ok(x2, w) and _own_plain(x2.shape[1]):
+            b32 = None if bias is None else (bias.detach() if bias.dtype == torch.float32 else bias.detach().float())
+            y = gemm_fwd(x2, w, b32, 0)[0].view(*x.shape[:-1], w.shape[0])
+        else:
+            y = torch.nn.functional.linear(x2, w, b).view(*x.shape[:-1], w.shape[0])
         ctx.save_for_backward(x, w)
         ctx.meta = (weight.dtype, None if bias is None else bias.dtype, gw, gb)
         ctx.wshape = weight.shape
@@ -792,21 +892,78 @@ class _Linear(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = torch.mm(dy2, w).view(x.shape)
-        if ctx.needs_input_grad[1]:
-            if gw is not None:
-                if dy2.dtype == torch.float32:
-                    torch.addmm(gw, dy2.t(), x2, out=gw)
-                else:
-                    torch.addmm(gw, dy2.t(), x2, out_dtype=torch.float32, out=gw)
+            if _tc_linear_ok(dy2, w) and w.shape[1] % 8 == 0 and _own_plain(dy2.shape[1]):
+                dx = gemm_dx(dy2, w).view(x.shape)
             else:
-                dw = torch.mm(dy2.t(), x2).to(wdt).view(ctx.wshape)
-        if bdt is not None and ctx.needs_input_grad[2]:
+                dx = torch.mm(dy2, w).view(x.shape)
+        want_db = bdt is not None and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1]:
+            dw, db = _accumulate_dw(dy2, x2, gw, gb, wdt, bdt, ctx.wshape, want_db)
+        elif want_db:
             if gb is not None:
                 colsum(dy2, out=gb)
             else:
                 db = colsum(dy2).to(bdt)
         return dx, dw, db, None, None, None, None
+
+
+class _MLP(torch.autograd.Function):
+    """z = act(x W1^T + b1) W2^T (+ b2): the two Linears of an FFN with the activation fused into the first GEMM's
+    epilogue and its gradient into the epilogue of the second GEMM's dX (csrc/gemm_tc.cu).  Replaces
+    Linear -> bias + activation kernel -> Linear of mmcv FFN (cfg :9-25 GELU, :34-50 ReLU)."""
+
+    @staticmethod
+    def forward(ctx, x, weight1, bias1, weight2, bias2, w1, w2, act, grads):
+        x2 = x.reshape(-1, x.shape[-1])
+        b1 = bias1.detach() if bias1.dtype == torch.float32 else bias1.detach().float()
+        y, h = gemm_fwd(x2, w1, b1, act)
+        b2 = None if bias2 is None else (bias2.detach() if bias2.dtype == torch.float32 else bias2.detach().float())
+        if _own_plain(y.shape[1]):
+            z = gemm_fwd(y, w2, b2, 0)[0]
+        else:
+            z = torch.nn.functional.linear(y, w2, None if b2 is None else b2.to(y.dtype))
+        ctx.save_for_backward(x2, w1, w2, y, h)
+        ctx.meta = (act, grads, weight1.dtype, bias1.dtype, weight2.dtype, None if bias2 is None else bias2.dtype,
+                    weight1.shape, weight2.shape, x.shape)
+        return z.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dz):
+        x2, w1, w2, y, h = ctx.saved_tensors
+        act, (gw1, gb1, gw2, gb2), w1dt, b1dt, w2dt, b2dt, w1shape, w2shape, xshape = ctx.meta
+        dz2 = dz.reshape(-1, dz.shape[-1])
+        if not dz2.is_contiguous():
+            dz2 = dz2.contiguous()
+        # second Linear: weight / bias gradient, then its input gradient with act' in the epilogue
+        dw2, db2 = _accumulate_dw(dz2, y, gw2, gb2, w2dt, b2dt, w2shape, b2dt is not None and ctx.needs_input_grad[4])
+        dh = gemm_dx(dz2, w2, h if act == 1 else y, act)
+        dw1, db1 = _accumulate_dw(dh, x2, gw1, gb1, w1dt, b1dt, w1shape, True)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = (gemm_dx(dh, w1) if _own_plain(dh.shape[1]) else torch.mm(dh, w1)).view(xshape)
+        return dx, dw1, db1, dw2, db2, None, None, None, None
+
+
+def mlp_supported(x, weight1, bias1, weight2):
+    """the fused FFN runs on bf16 CUDA activations with feature counts that are multiples of 8"""
+    if not (_OWN_GEMM and x.is_cuda and bias1 is not None and weight1.dim() == 2 and weight2.dim() == 2):
+        return False
+    dt = torch.get_autocast_dtype('cuda') if torch.is_autocast_enabled('cuda') else x.dtype
+    rows = x.numel() // x.shape[-1]
+    return dt == torch.bfloat16 and rows >= _TC_MIN_ROWS and all(d % 8 == 0 for d in (*weight1.shape, *weight2.shape))
+
+
+def mlp(x, weight1, bias1, weight2, bias2, act):
+    """act(x W1^T + b1) W2^T (+ b2); act = ACT_GELU (erf form) or ACT_RELU.  Call only when mlp_supported(...)."""
+    if torch.is_autocast_enabled('cuda'):
+        x = x.to(torch.get_autocast_dtype('cuda'))
+    x = x.contiguous()
+    grads = (_flat_grad(weight1), _flat_grad(bias1), _flat_grad(weight2), None if bias2 is None else _flat_grad(bias2))
+    if not torch.is_grad_enabled():
+        grads = (None, None, None, None)
+    # (either both views of a Linear are attached or neither)
+    w1, w2 = _compute_copy(weight1, None, torch.bfloat16), _compute_copy(weight2, None, torch.bfloat16)
+    return _MLP.apply(x, weight1, bias1, weight2, bias2, w1, w2, {ACT_GELU: 1, ACT_RELU: 2, ACT_GELU_SIG: 1}[act], grads)
 
 
 def _rows(t, rows):
