@@ -93,7 +93,7 @@ def check(status, name):
 _timer = None      # set by KernelTimer: collects (name, alg_bytes, start_event, end_event)
 
 
-def call(name, *args, alg_bytes=0):
+def call(name, *args, alg_bytes=0, alg_flops=0):
     if _timer is None:
         check(getattr(lib(), name)(*args), name)
         return
@@ -102,7 +102,7 @@ def call(name, *args, alg_bytes=0):
     e0.record()
     check(getattr(lib(), name)(*args), name)
     e1.record()
-    _timer.append((name, alg_bytes, e0, e1))
+    _timer.append((name, alg_bytes, e0, e1, alg_flops))
 
 
 class KernelTimer:
@@ -124,8 +124,8 @@ class KernelTimer:
         import torch
         torch.cuda.synchronize()
         out = {}
-        for name, nbytes, e0, e1 in self.records:
-            d = out.setdefault(name, dict(launches=0, ms=0.0, bytes=0, big_launches=0, big_ms=0.0, big_bytes=0))
+        for name, nbytes, e0, e1, nflops in self.records:
+            d = out.setdefault(name, dict(launches=0, ms=0.0, bytes=0, big_launches=0, big_ms=0.0, big_bytes=0, big_flops=0))
             t = e0.elapsed_time(e1)
             d['launches'] += 1
             d['ms'] += t
@@ -134,6 +134,7 @@ class KernelTimer:
                 d['big_launches'] += 1
                 d['big_ms'] += t
                 d['big_bytes'] += nbytes
+                d['big_flops'] += nflops
         for d in out.values():
             d['gbs'] = d['bytes'] / d['ms'] / 1e6 if d['ms'] > 0 else 0.0
             d['big_gbs'] = d['big_bytes'] / d['big_ms'] / 1e6 if d['big_ms'] > 0 else 0.0

@@ -148,69 +148,6 @@ __global__ void __launch_bounds__(LN_THREADS)
   }
 }
 
-// Opt-in variant (RSC_ADD_LN_LEAN=1): the per-channel parameters are re-read (L1 hits) at their point of use instead
-// of living in 3*EV*VW registers for the whole kernel -- the pass is latency-bound at 20 warps/SM (95 registers), the
-// issue slots are two thirds empty, so trading registers for a few cached loads buys occupancy.
-template <typename T, int VW, int EV, int L>
-__global__ void __launch_bounds__(LN_THREADS, 6)
-    add_ln_fwd_lean_kernel(const T *__restrict__ identity, const T *__restrict__ x, const float *__restrict__ bias,
-                           const float *__restrict__ scale, const float *__restrict__ gamma, const float *__restrict__ beta,
-                           T *__restrict__ r_out, T *__restrict__ n_out, float *__restrict__ mean, float *__restrict__ rstd,
-                           int64_t rows, int64_t rows_per_sample, float eps) {
-  constexpr int C = VW * EV * L, RPW = 32 / L;
-  const int lane = threadIdx.x & 31, sub = lane % L, rw = lane / L;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
-    const int64_t r = r0 + rw;
-    const bool ok = r < rows;
-    const float sc = (ok && scale) ? __ldg(scale + r / rows_per_sample) : 1.0f;
-    float v[EV][VW];
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < EV; ++k) {
-      float a[VW], b[VW], bi[VW];
-      if (ok) {
-        loadv<T, VW>(identity + r * C + (sub + k * L) * VW, a);
-        loadv<T, VW>(x + r * C + (sub + k * L) * VW, b);
-      }
-      if (bias) loadv<float, VW>(bias + (sub + k * L) * VW, bi);
-#pragma unroll
-      for (int e = 0; e < VW; ++e) {
-        v[k][e] = ok ? fmaf(b[e] + (bias ? bi[e] : 0.f), sc, a[e]) : 0.f;
-        v[k][e] = to_f<T>(from_f<T>(v[k][e]));
-        s += v[k][e];
-      }
-    }
-    const float mu = group_sum<L>(s) * (1.0f / C);
-    float q = 0.f;
-#pragma unroll
-    for (int k = 0; k < EV; ++k)
-#pragma unroll
-      for (int e = 0; e < VW; ++e) {
-        const float d = v[k][e] - mu;
-        q = fmaf(d, d, q);
-      }
-    const float rs = rsqrtf(group_sum<L>(q) * (1.0f / C) + eps);
-    if (ok) {
-      if (sub == 0) {
-        mean[r] = mu;
-        rstd[r] = rs;
-      }
-#pragma unroll
-      for (int k = 0; k < EV; ++k) {
-        float o[VW], ga[VW], be[VW];
-        loadv<float, VW>(gamma + (sub + k * L) * VW, ga);
-        loadv<float, VW>(beta + (sub + k * L) * VW, be);
-#pragma unroll
-        for (int e = 0; e < VW; ++e) o[e] = fmaf((v[k][e] - mu) * rs, ga[e], be[e]);
-        storev<T, VW>(r_out + r * C + (sub + k * L) * VW, v[k]);
-        storev<T, VW>(n_out + r * C + (sub + k * L) * VW, o);
-      }
-    }
-  }
-}
-
 // dr = dr_ext + LNbwd(dn) ; d_identity = dr ; dx = dr * scale ; dbias += colsum(dx) ; dgamma, dbeta
 template <typename T, int VW, int EV, int L>
 __global__ void __launch_bounds__(LN_THREADS)
@@ -490,14 +427,8 @@ extern "C" int rsc_add_ln_fwd(const void *identity, const void *x, const float *
   int64_t fb = (rows + rpb - 1) / rpb;
   const int grid = (int)(fb < kNumSMs * 12 ? fb : kNumSMs * 12);
   cudaStream_t st = (cudaStream_t)stream;
-  static const bool lean = [] { const char *e = getenv("RSC_ADD_LN_LEAN"); return e && e[0] == '1'; }();
 #define ALF(T, V, E, LL)                                                                                                \
   if (vw == V && ev == E && l == LL) {                                                                                  \
-    if (lean && V * E <= 16) /* (the 768 / 1024-wide shapes would spill at this register budget) */                       \
-      few::add_ln_fwd_lean_kernel<T, V, E, LL><<<grid, few::LN_THREADS, 0, st>>>(                                          \
-          (const T *)identity, (const T *)x, bias, scale, gamma, beta, (T *)r_out, (T *)n_out, mean, rstd, rows,        \
-          rows_per_sample, eps);                                                                                        \
-    else                                                                                                                \
       few::add_ln_fwd_kernel<T, V, E, LL><<<grid, few::LN_THREADS, 0, st>>>((const T *)identity, (const T *)x, bias, scale, \
                                                                           gamma, beta, (T *)r_out, (T *)n_out, mean, rstd, \
                                                                           rows, rows_per_sample, eps);                  \

@@ -159,6 +159,7 @@ struct Params {
 template <int BN, int STAGES, int EPI>
 struct Smem {
   static constexpr bool TWO = EPI == EPI_BIAS_GELU || EPI == EPI_DGELU || EPI == EPI_DRELU;
+  static constexpr bool DOUBLE = !TWO && BN < 256;            // BN = 256 spends the second buffer on a third pipeline stage
   static constexpr uint32_t A_BYTES = BM * BK * 2;            // 16 KB
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
@@ -166,7 +167,7 @@ struct Smem {
   static constexpr uint32_t STAGING = EPI_WARPS * WARP_STAGING;       // = one bf16 output tile
   static constexpr uint32_t OFF_STAGING = STAGES * STAGE;
   static constexpr uint32_t OFF_STAGING2 = OFF_STAGING + STAGING;     // second buffer / second output / aux input
-  static constexpr uint32_t OFF_BIAS = OFF_STAGING2 + STAGING;        // [2 tile parities][BN] floats
+  static constexpr uint32_t OFF_BIAS = OFF_STAGING2 + ((TWO || DOUBLE) ? STAGING : 0);   // [2 tile parities][BN] floats
   static constexpr uint32_t OFF_BAR = OFF_BIAS + 2 * BN * 4;
   static constexpr uint32_t TOTAL = OFF_BAR + 256;
 };
@@ -268,10 +269,10 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int acc = local & 1;
       const int m0 = (tile / n_blks) * BM + q * 32, n0 = (tile % n_blks) * BN + half * HC;   // this warp's part
       // which staging buffer; it is free once the stores that last read it are done reading
-      const uint32_t out = (!S::TWO && (local & 1)) ? stg1 : stg0;
+      const uint32_t out = (S::DOUBLE && (local & 1)) ? stg1 : stg0;
       if (lane == 0) {
-        if (S::TWO) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (S::DOUBLE) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
       __syncwarp();
       if (AUX_IN) {                                             // the saved H (or Y) values of this part
@@ -407,7 +408,7 @@ static int dispatch_bn(int BN, const CUtensorMap &tA, const CUtensorMap &tB, con
     case 64: return launch<64, 6, B_MN, EPI>(tA, tB, tD, tD2, p, st);
     case 128: return launch<128, 4, B_MN, EPI>(tA, tB, tD, tD2, p, st);
     case 192: return launch<192, 3, B_MN, EPI>(tA, tB, tD, tD2, p, st);
-    case 256: return launch<256, 2, B_MN, EPI>(tA, tB, tD, tD2, p, st);
+    case 256: return launch<256, Smem<256, 2, EPI>::TWO ? 2 : 3, B_MN, EPI>(tA, tB, tD, tD2, p, st);
   }
   return -1;
 }

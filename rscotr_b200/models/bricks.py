@@ -19,7 +19,7 @@ from ..config import MODELS, build_from_cfg
 
 _CONST_CACHE = {}
 _DEFER = __import__('os').environ.get('RSC_NO_DEFER') is None     # A/B switch for the fused post-norm pairs
-_CONST_ATTN_BIAS = __import__('os').environ.get('RSC_CONST_ATTN_BIAS') == '1'
+_CONST_ATTN_BIAS = __import__('os').environ.get('RSC_CONST_ATTN_BIAS', '1') != '0'    # A/B'd on B200 in round 2: promoted
 
 
 def const_tensor(values, dtype, device):
@@ -341,7 +341,7 @@ class MultiheadAttention(nn.Module):
         v = v.reshape(S, B, H, E // H).permute(1, 2, 0, 3)
         mask = None
         if attn_mask is not None and _CONST_ATTN_BIAS and key_padding_mask is None and hasattr(attn_mask, '_rsc_add'):
-            # opt-in (RSC_CONST_ATTN_BIAS=1): a shape-only constant mask (the denoising mask of the DINO decoder, the same
+            # (RSC_CONST_ATTN_BIAS=0 turns it off) a shape-only constant mask (the denoising mask of the DINO decoder, the same
             # object for all 6 layers of every step) is turned into the additive 0 / -inf bias ONCE per dtype instead of
             # an invert + masked_fill per layer call inside the attention op
             mask = attn_mask._rsc_add.get(q.dtype)

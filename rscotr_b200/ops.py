@@ -327,8 +327,9 @@ def add_ln(identity, x, bias, scale, gamma, beta, eps=1e-5):
 
 
 ACT_GELU, ACT_RELU, ACT_GELU_SIG = 0, 1, 2
-# opt-in (RSC_GELU_SIG=1): bf16 GELU through the logistic fit of the normal CDF (|error| < 2.6e-5, half the ALU work)
-_GELU_SIG = __import__('os').environ.get('RSC_GELU_SIG') == '1'
+# bf16 GELU through the logistic fit of the normal CDF (|error| < 2.6e-5, half the ALU work; the same function the GEMM
+# epilogue of csrc/gemm_tc.cu evaluates through one tanh).  A/B'd on B200 in round 2: promoted; RSC_GELU_SIG=0 restores erf.
+_GELU_SIG = __import__('os').environ.get('RSC_GELU_SIG', '1') != '0'
 
 
 class _BiasAct(torch.autograd.Function):
@@ -786,8 +787,11 @@ def _tc_linear_ok(x2, w):
 # Measured on B200 (profiles/r02_gbench_*.jsonl): the single-CTA kernels match or beat the library where the GEMM is
 # memory-bound and wherever an element-wise pass rides in the epilogue; a PLAIN GEMM with a long contraction
 # (>= 512) is tensor-bound and the library's 2-CTA kernels are ~1.5x faster there.
+_PLAIN_MAX_K = int(__import__('os').environ.get('RSC_GEMM_PLAIN_MAX_K', 512))
+
+
 def _own_plain(contraction):
-    return contraction < 512
+    return contraction < _PLAIN_MAX_K
 
 
 def _own_dw(M, N, K):
@@ -802,7 +806,7 @@ def gemm_fwd(x2, w, bias32, act=0):
     h = torch.empty_like(y) if act == 1 else None
     with torch.cuda.device(x2.device):
         call('rsc_linear_fwd', x2.data_ptr(), w.data_ptr(), _p(bias32), y.data_ptr(), _p(h), M, N, K, x2.stride(0),
-             w.stride(0), N, act, _stream(), alg_bytes=2 * (M * K + N * K + M * N * (2 if act == 1 else 1)))
+             w.stride(0), N, act, _stream(), alg_bytes=2 * (M * K + N * K + M * N * (2 if act == 1 else 1)), alg_flops=2 * M * N * K)
     return y, h
 
 
@@ -813,7 +817,7 @@ def gemm_dx(dy2, w, aux=None, act=0):
     dx = torch.empty(M, K, dtype=torch.bfloat16, device=dy2.device)
     with torch.cuda.device(dy2.device):
         call('rsc_linear_dx', dy2.data_ptr(), w.data_ptr(), _p(aux), dx.data_ptr(), M, N, K, dy2.stride(0), w.stride(0), K,
-             act, _stream(), alg_bytes=2 * (M * N + N * K + M * K * (2 if act else 1)))
+             act, _stream(), alg_bytes=2 * (M * N + N * K + M * K * (2 if act else 1)), alg_flops=2 * M * N * K)
     return dx
 
 
@@ -823,7 +827,7 @@ def gemm_dw(dy2, x2, dw32, db32):
     K = x2.shape[1]
     with torch.cuda.device(dy2.device):
         call('rsc_linear_dw', dy2.data_ptr(), x2.data_ptr(), dw32.data_ptr(), _p(db32), M, N, K, dy2.stride(0), x2.stride(0),
-             dw32.stride(0), _stream(), alg_bytes=2 * (M * N + M * K))
+             dw32.stride(0), _stream(), alg_bytes=2 * (M * N + M * K), alg_flops=2 * M * N * K)
 
 
 def _accumulate_dw(dy2, x2, gw, gb, wdt, bdt, wshape, want_db):

@@ -19,9 +19,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 DEVICES = ['cpu', pytest.param('cuda', marks=pytest.mark.gpu)]
-# CUDA variants that have not yet run on hardware stay opt-in (RSC_TEST_EXPERIMENTAL=1) until the next GPU session
-DEVICES_NEW = ['cpu', pytest.param('cuda', marks=[pytest.mark.gpu, pytest.mark.skipif(
-    os.environ.get('RSC_TEST_EXPERIMENTAL') != '1', reason='not yet validated on a GPU (RSC_TEST_EXPERIMENTAL=1)')])]
+DEVICES_NEW = DEVICES       # (the CUDA variants of the inference goldens were validated on a B200 in round 2)
 
 
 def _to(obj, device):
@@ -223,7 +221,10 @@ def test_seg_forward_head_matches_reference_run(device):
     with _ctx(device), torch.no_grad():
         seg_mask, attn_mask = Mask2FormerHead.forward_head(fake, c['decoder_out'], c['mask_feature'], tuple(c['target_size']))
     assert torch.allclose(seg_mask, c['seg_mask'], rtol=1e-5, atol=1e-5)
-    assert attn_mask.shape == c['attn_mask'].shape and attn_mask.dtype == torch.bool
+    assert attn_mask.dtype == torch.bool
+    if attn_mask.dim() == 4:    # the compact (B, 1, Q, K) mask (default since round 2): the reference's layout repeats it
+        attn_mask = attn_mask.repeat(1, c['num_heads'], 1, 1).flatten(0, 1)      # over the heads -> (B * heads, Q, K)
+    assert attn_mask.shape == c['attn_mask'].shape
     assert float((attn_mask != c['attn_mask']).float().mean()) <= 1e-3      # (values within 1e-6 of the 0.5 threshold)
 
 
@@ -235,12 +236,15 @@ def _tools():
 
 
 @pytest.mark.parametrize('device', DEVICES)
-def test_seg_head_forward_control_flow_matches_reference_run(device):
+def test_seg_head_forward_control_flow_matches_reference_run(device, monkeypatch):
     """row a18: Mask2FormerHead.forward of the reference (level cycling, reset of fully masked rows, forward_head after
-    every layer), run in place with toy decoder layers, against this repo's forward with the SAME toy parts."""
+    every layer), run in place with toy decoder layers, against this repo's forward with the SAME toy parts.  The toy
+    layers consume the reference's (B * heads, Q, K) mask layout, so the compact-mask default is switched off here
+    (its equality with that layout is test_host_units.py::test_compact_attention_mask_is_equivalent)."""
     import types
-    from rscotr_b200.models import bricks
+    from rscotr_b200.models import bricks, seg_head
     from rscotr_b200.models.seg_head import Mask2FormerHead
+    monkeypatch.setattr(seg_head, '_COMPACT_ATTN_MASK', False)
     from tests.cpu_ops_shim import cpu_ops
     mg = _tools()
     t = _to(mg.toy_seg_parts(), device)

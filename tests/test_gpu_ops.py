@@ -702,14 +702,10 @@ def test_bias_gelu_matches_eager(rows, C, dtype):
     assert_rel(gb2.grad, rb2.grad, 1e-5 if dtype == torch.float32 else 2e-2, 'relu dbias')
 
 
-EXPERIMENTAL = pytest.mark.skipif(__import__('os').environ.get('RSC_TEST_EXPERIMENTAL') != '1',
-                                  reason='opt-in kernel variants that are not on the default path (RSC_TEST_EXPERIMENTAL=1)')
-
-
-@EXPERIMENTAL
 @pytest.mark.parametrize('rows,C', [(50, 384), (1000, 768), (7, 8)])
 def test_bias_gelu_logistic_fit_variant(rows, C):
-    """act=2 (RSC_GELU_SIG=1): same tolerances as the default bf16 GELU; fp32 inputs are refused."""
+    """act=2, the bf16 default since round 2 (A/B on B200: profiles/r02_ab_switches.log): same tolerances as the erf
+    form; fp32 inputs are refused."""
     ops = _ops()
     g = torch.Generator().manual_seed(rows)
     h, bias, w = (torch.randn(rows, C, generator=g) * 3).bfloat16(), torch.randn(C, generator=g), torch.randn(rows, C, generator=g)
