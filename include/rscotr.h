@@ -316,6 +316,15 @@ int rsc_colsum(const void *x, float *y, int64_t rows, int C, int dtype, void *st
  * ---------------------------------------------------------------------- */
 int rsc_linear_fwd(const void *x, const void *w, const float *bias, void *y, void *h, int64_t M, int N, int K, int64_t ldx,
                    int64_t ldw, int64_t ldy, int act, void *stream);
+/* (r, n) = (identity + (X W^T + bias) * scale[row / rows_per_sample], LayerNorm(r) * gamma + beta): the Linear, the
+ * residual add with the DropPath scale of the row's sample, and the NEXT LayerNorm in one kernel (the pair
+ * nn.Linear -> rsc_add_ln_fwd of a Swin block's attention / MLP tail and of a post-norm transformer layer, SURVEY 8a rows
+ * a2 / a9).  N (the normalised width) must fit one tile: N % 32 == 0, N <= 256.  identity / r_out / n_out are (M,N)
+ * contiguous bf16; scale (M / rows_per_sample) float or NULL; mean / rstd (M) float are written for rsc_add_ln_bwd. */
+int rsc_linear_add_ln_fwd(const void *x, const void *w, const float *bias, const void *identity, const float *scale,
+                          const float *gamma, const float *beta, void *r_out, void *n_out, float *mean, float *rstd,
+                          int64_t M, int N, int K, int64_t ldx, int64_t ldw, int64_t rows_per_sample, float eps,
+                          void *stream);
 int rsc_linear_dx(const void *dy, const void *w, const void *aux, void *dx, int64_t M, int N, int K, int64_t lddy,
                   int64_t ldw, int64_t lddx, int act, void *stream);
 int rsc_linear_dw(const void *dy, const void *x, float *dw, float *db, int64_t M, int N, int K, int64_t lddy, int64_t ldx,

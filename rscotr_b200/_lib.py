@@ -53,6 +53,7 @@ _SIGS = {
     'rsc_sigmoid_focal_loss_fwd': [_P, _P, _P, _I, _I, _F, _F, _I, _P],
     'rsc_sigmoid_focal_loss_bwd': [_P, _P, _P, _I, _I, _F, _F, _I, _P],
     'rsc_linear_fwd': [_P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _I, _P],
+    'rsc_linear_add_ln_fwd': [_P] * 11 + [ctypes.c_int64, _I, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _F, _P],
     'rsc_linear_dx': [_P, _P, _P, _P, ctypes.c_int64, _I, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _I, _P],
     'rsc_linear_dw': [_P, _P, _P, _P, ctypes.c_int64, _I, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _P],
 }

@@ -28,7 +28,7 @@ using namespace tc;
 
 constexpr int BM = 128, BK = 64;
 constexpr int EPI_WARPS = 8, THREADS = 64 + EPI_WARPS * 32;
-enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RELU = 2, EPI_DGELU = 3, EPI_DRELU = 4 };
+enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RELU = 2, EPI_DGELU = 3, EPI_DRELU = 4, EPI_ADD_LN = 5 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
@@ -149,6 +149,11 @@ struct Params {
   int M, N, K;             // D (M,N) = sum_k A(m,k) B(n,k)
   const float *bias;       // (N) or null
   int n_store;             // outputs: 1 (D) or 2 (D and D2 = the pre-activation H of EPI_BIAS_GELU)
+  // EPI_ADD_LN: r = identity + (acc + bias) * scale[row / rows_per_sample];  n = LayerNorm(r) * gamma + beta
+  const float *scale, *gamma, *beta;
+  float *mean, *rstd;
+  int rows_per_sample;
+  float eps;
 };
 
 // smem carve-up (all tile bases 1024-byte aligned).  Every epilogue warp owns a private staging area for its
@@ -158,7 +163,7 @@ struct Params {
 // backward: aux in, dX out) keep one buffer per tile.
 template <int BN, int STAGES, int EPI>
 struct Smem {
-  static constexpr bool TWO = EPI == EPI_BIAS_GELU || EPI == EPI_DGELU || EPI == EPI_DRELU;
+  static constexpr bool TWO = EPI == EPI_BIAS_GELU || EPI == EPI_DGELU || EPI == EPI_DRELU || EPI == EPI_ADD_LN;
   static constexpr bool DOUBLE = !TWO && BN < 256;            // BN = 256 spends the second buffer on a third pipeline stage
   static constexpr uint32_t A_BYTES = BM * BK * 2;            // 16 KB
   static constexpr uint32_t B_BYTES = BN * BK * 2;
@@ -168,7 +173,7 @@ struct Smem {
   static constexpr uint32_t OFF_STAGING = STAGES * STAGE;
   static constexpr uint32_t OFF_STAGING2 = OFF_STAGING + STAGING;     // second buffer / second output / aux input
   static constexpr uint32_t OFF_BIAS = OFF_STAGING2 + ((TWO || DOUBLE) ? STAGING : 0);   // [2 tile parities][BN] floats
-  static constexpr uint32_t OFF_BAR = OFF_BIAS + 2 * BN * 4;
+  static constexpr uint32_t OFF_BAR = OFF_BIAS + (2 * BN * 4 > 2048 ? 2 * BN * 4 : 2048);   // (EPI_ADD_LN: the 2 KB row-statistics exchange)
   static constexpr uint32_t TOTAL = OFF_BAR + 256;
 };
 
@@ -176,7 +181,8 @@ struct Smem {
 template <int BN, int STAGES, bool B_MN, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, Params p) {
+                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
+                const __grid_constant__ CUtensorMap tmD3, Params p) {
   using S = Smem<BN, STAGES, EPI>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sb = smem_u32(smem);
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
-  constexpr bool AUX_IN = EPI == EPI_DGELU || EPI == EPI_DRELU;
+  constexpr bool AUX_IN = EPI == EPI_DGELU || EPI == EPI_DRELU || EPI == EPI_ADD_LN;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
@@ -279,7 +285,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (lane == 0) {
           mbar_expect_tx(&auxbar[e], S::WARP_STAGING);
 #pragma unroll
-          for (int j = 0; j < HC / 32; ++j) tma_load_2d(stg1 + j * 2048, &tmD2, &auxbar[e], n0 + j * 32, m0);
+          for (int j = 0; j < HC / 32; ++j)
+            tma_load_2d(stg1 + j * 2048, EPI == EPI_ADD_LN ? &tmD3 : &tmD2, &auxbar[e], n0 + j * 32, m0);
         }
       }
       mbar_wait(&tfull[acc], (local >> 1) & 1);
@@ -288,10 +295,110 @@ __global__ void __launch_bounds__(THREADS, 1)
       // with the tile parity: once this tile's accumulator is ready, every warp has drained the tile before last (the
       // MMA of this tile waited for that), i.e. nobody still reads this slot
       float *sbias = reinterpret_cast<float *>(smem + S::OFF_BIAS) + (local & 1) * BN + half * HC;
-      for (int c = lane; c < HC; c += 32) sbias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      if (EPI != EPI_ADD_LN) {
+        for (int c = lane; c < HC; c += 32) sbias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      }
       __syncwarp();
       if (AUX_IN) mbar_wait(&auxbar[e], local & 1);
       const uint32_t taddr = tm + ((uint32_t)(q * 32) << 16) + acc * BN + half * HC;
+      if (EPI == EPI_ADD_LN) {
+        // ---- residual add + LayerNorm over the full row (the row is split between this warp and its partner in the other
+        //      column half: per-half two-pass statistics, combined exactly (Chan) through a 64-thread named barrier) ----
+        const int row_g = m0 + lane;
+        const float sc = (p.scale && row_g < p.M) ? __ldg(p.scale + row_g / p.rows_per_sample) : 1.0f;
+        const int nh = max(0, min(HC, p.N - n0));               // valid columns of this half
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < nh; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t soff = (c0 >> 5) * 2048 + lane * 64 + ((j ^ ((lane >> 1) & 3)) * 16);
+            const uint4 iq = ld_shared16(stg1 + soff);
+            const uint32_t iw[4] = {iq.x, iq.y, iq.z, iq.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int col = n0 + c0 + j * 8 + 2 * k;
+              const float2 b2 = p.bias ? __ldg(reinterpret_cast<const float2 *>(p.bias + col)) : make_float2(0.f, 0.f);
+              float2 v = add2(make_float2(__uint_as_float(r[j * 8 + 2 * k]), __uint_as_float(r[j * 8 + 2 * k + 1])), b2);
+              v = fma2(v, make_float2(sc, sc), unpack_bf16(iw[k]));
+              ow[k] = pack_bf16(v.x, v.y);
+              // the stored residual is the bf16 value the rest of the network sees: normalise exactly that value
+              const float2 vr = unpack_bf16(ow[k]);
+              sum += vr.x + vr.y;
+            }
+            st_shared16(stg1 + soff, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+          }
+        }
+        // the accumulator is drained: hand it back before the statistics
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        const float mean_h = nh > 0 ? sum / nh : 0.f;
+        float m2 = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < nh; c0 += 32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 rq = ld_shared16(stg1 + (c0 >> 5) * 2048 + lane * 64 + ((j ^ ((lane >> 1) & 3)) * 16));
+            const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 v = unpack_bf16(rw[k]);
+              m2 = fmaf(v.x - mean_h, v.x - mean_h, m2);
+              m2 = fmaf(v.y - mean_h, v.y - mean_h, m2);
+            }
+          }
+        }
+        float2 *xch = reinterpret_cast<float2 *>(smem + S::OFF_BIAS);     // [quadrant][half][lane] (mean, M2)
+        xch[(q * 2 + half) * 32 + lane] = make_float2(mean_h, m2);
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        const float2 other = xch[(q * 2 + (half ^ 1)) * 32 + lane];
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");          // (both have read before the next tile writes)
+        const int no = p.N - nh;                                           // the partner's column count
+        const float delta = other.x - mean_h;
+        const float mean = mean_h + delta * ((float)no / (float)p.N);
+        const float var = (m2 + other.y + delta * delta * ((float)nh * (float)no / (float)p.N)) / (float)p.N;
+        const float rstd = rsqrtf(var + p.eps);
+        if (half == 0 && row_g < p.M) p.mean[row_g] = mean, p.rstd[row_g] = rstd;
+#pragma unroll 1
+        for (int c0 = 0; c0 < nh; c0 += 32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t soff = (c0 >> 5) * 2048 + lane * 64 + ((j ^ ((lane >> 1) & 3)) * 16);
+            const uint4 rq = ld_shared16(stg1 + soff);
+            const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int col = n0 + c0 + j * 8 + 2 * k;
+              const float2 g2 = __ldg(reinterpret_cast<const float2 *>(p.gamma + col));
+              const float2 be2 = __ldg(reinterpret_cast<const float2 *>(p.beta + col));
+              const float2 v = unpack_bf16(rw[k]);
+              ow[k] = pack_bf16(fmaf((v.x - mean) * rstd, g2.x, be2.x), fmaf((v.y - mean) * rstd, g2.y, be2.y));
+            }
+            st_shared16(stg0 + soff, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (m0 < p.M) {
+#pragma unroll
+            for (int j = 0; j < HC / 32; ++j) {
+              if (n0 + j * 32 < p.N) {
+                tma_store_2d(&tmD, stg1 + j * 2048, n0 + j * 32, m0);      // r
+                tma_store_2d(&tmD2, stg0 + j * 2048, n0 + j * 32, m0);     // n
+              }
+            }
+          }
+          tma_store_commit();
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < HC; c0 += 32) {
         if (n0 + c0 >= p.N) break;                              // ragged last tile: nothing to store from here on
@@ -389,26 +496,26 @@ static bool map2d(CUtensorMap *m, const void *base, int64_t rows, int64_t cols, 
 }
 
 template <int BN, int STAGES, bool B_MN, int EPI>
-static int launch(const CUtensorMap &tA, const CUtensorMap &tB, const CUtensorMap &tD, const CUtensorMap &tD2, const Params &p,
-                  cudaStream_t st) {
+static int launch(const CUtensorMap &tA, const CUtensorMap &tB, const CUtensorMap &tD, const CUtensorMap &tD2,
+                  const CUtensorMap &tD3, const Params &p, cudaStream_t st) {
   using S = Smem<BN, STAGES, EPI>;
   static_assert(S::TOTAL <= 227 * 1024, "shared memory");
   auto kern = gemm_kernel<BN, STAGES, B_MN, EPI>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  kern<<<grid, THREADS, S::TOTAL, st>>>(tA, tB, tD, tD2, p);
+  kern<<<grid, THREADS, S::TOTAL, st>>>(tA, tB, tD, tD2, tD3, p);
   return 0;
 }
 
 template <bool B_MN, int EPI>
 static int dispatch_bn(int BN, const CUtensorMap &tA, const CUtensorMap &tB, const CUtensorMap &tD, const CUtensorMap &tD2,
-                       const Params &p, cudaStream_t st) {
+                       const CUtensorMap &tD3, const Params &p, cudaStream_t st) {
   switch (BN) {
-    case 64: return launch<64, 6, B_MN, EPI>(tA, tB, tD, tD2, p, st);
-    case 128: return launch<128, 4, B_MN, EPI>(tA, tB, tD, tD2, p, st);
-    case 192: return launch<192, 3, B_MN, EPI>(tA, tB, tD, tD2, p, st);
-    case 256: return launch<256, Smem<256, 2, EPI>::TWO ? 2 : 3, B_MN, EPI>(tA, tB, tD, tD2, p, st);
+    case 64: return launch<64, 6, B_MN, EPI>(tA, tB, tD, tD2, tD3, p, st);
+    case 128: return launch<128, 4, B_MN, EPI>(tA, tB, tD, tD2, tD3, p, st);
+    case 192: return launch<192, 3, B_MN, EPI>(tA, tB, tD, tD2, tD3, p, st);
+    case 256: return launch<256, Smem<256, 2, EPI>::TWO ? 2 : 3, B_MN, EPI>(tA, tB, tD, tD2, tD3, p, st);
   }
   return -1;
 }
@@ -447,13 +554,43 @@ extern "C" int rsc_linear_fwd(const void *x, const void *w, const float *bias, v
             gemm::map2d(&tD, y, M, N, ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
             gemm::map2d(&tD2, act == 1 ? h : y, M, N, ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   RSC_CHECK_ARG(ok, "rsc_linear_fwd: cuTensorMapEncodeTiled failed");
-  gemm::Params p{(int)M, N, K, bias, act == 1 ? 2 : 1};
+  gemm::Params p{(int)M, N, K, bias, act == 1 ? 2 : 1, nullptr, nullptr, nullptr, nullptr, nullptr, 1, 0.f};
   int rc;
-  if (act == 1) rc = gemm::dispatch_bn<false, gemm::EPI_BIAS_GELU>(BN, tA, tB, tD, tD2, p, (cudaStream_t)stream);
-  else if (act == 2) rc = gemm::dispatch_bn<false, gemm::EPI_BIAS_RELU>(BN, tA, tB, tD, tD2, p, (cudaStream_t)stream);
-  else rc = gemm::dispatch_bn<false, gemm::EPI_BIAS>(BN, tA, tB, tD, tD2, p, (cudaStream_t)stream);
+  if (act == 1) rc = gemm::dispatch_bn<false, gemm::EPI_BIAS_GELU>(BN, tA, tB, tD, tD2, tD2, p, (cudaStream_t)stream);
+  else if (act == 2) rc = gemm::dispatch_bn<false, gemm::EPI_BIAS_RELU>(BN, tA, tB, tD, tD2, tD2, p, (cudaStream_t)stream);
+  else rc = gemm::dispatch_bn<false, gemm::EPI_BIAS>(BN, tA, tB, tD, tD2, tD2, p, (cudaStream_t)stream);
   RSC_CHECK_ARG(rc == 0, "rsc_linear_fwd: no tile shape for N = %d", N);
   RSC_CHECK_LAUNCH("rsc_linear_fwd");
+  return RSC_OK;
+}
+
+// (r, n) = (identity + (X W^T + bias) * scale[row / rows_per_sample], LayerNorm(r) * gamma + beta): the Linear, the residual
+// add (with the DropPath scale of the row's sample) and the NEXT LayerNorm in one kernel; N (= the normalised width) must
+// fit one tile: N % 32 == 0, N <= 256.  mean / rstd (M) float are written for the backward (rsc_add_ln_bwd).
+extern "C" int rsc_linear_add_ln_fwd(const void *x, const void *w, const float *bias, const void *identity, const float *scale,
+                                     const float *gamma, const float *beta, void *r_out, void *n_out, float *mean, float *rstd,
+                                     int64_t M, int N, int K, int64_t ldx, int64_t ldw, int64_t rows_per_sample, float eps,
+                                     void *stream) {
+  RSC_CHECK_ARG(x && w && identity && gamma && beta && r_out && n_out && mean && rstd && M > 0 && K > 0,
+                "rsc_linear_add_ln_fwd: null pointer / empty shape");
+  RSC_CHECK_ARG(N % 32 == 0 && N >= 32 && N <= 256, "rsc_linear_add_ln_fwd: N = %d must be a multiple of 32 in [32, 256]", N);
+  RSC_CHECK_ARG(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0 && M < (1ll << 31) && rows_per_sample > 0,
+                "rsc_linear_add_ln_fwd: K and the leading dimensions must be multiples of 8");
+  RSC_CHECK_ARG((((uintptr_t)x | (uintptr_t)w | (uintptr_t)identity | (uintptr_t)r_out | (uintptr_t)n_out) & 15) == 0 &&
+                    (((uintptr_t)bias | (uintptr_t)gamma | (uintptr_t)beta) & 7) == 0,
+                "rsc_linear_add_ln_fwd: alignment");
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : (N <= 192 ? 192 : 256));
+  CUtensorMap tA, tB, tR, tN, tI;
+  bool ok = gemm::map2d(&tA, x, M, K, ldx, gemm::BK, gemm::BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
+            gemm::map2d(&tB, w, N, K, ldw, gemm::BK, BN, CU_TENSOR_MAP_SWIZZLE_128B) &&
+            gemm::map2d(&tR, r_out, M, N, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+            gemm::map2d(&tN, n_out, M, N, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+            gemm::map2d(&tI, identity, M, N, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  RSC_CHECK_ARG(ok, "rsc_linear_add_ln_fwd: cuTensorMapEncodeTiled failed");
+  gemm::Params p{(int)M, N, K, bias, 2, scale, gamma, beta, mean, rstd, (int)rows_per_sample, eps};
+  const int rc = gemm::dispatch_bn<false, gemm::EPI_ADD_LN>(BN, tA, tB, tR, tN, tI, p, (cudaStream_t)stream);
+  RSC_CHECK_ARG(rc == 0, "rsc_linear_add_ln_fwd: no tile shape for N = %d", N);
+  RSC_CHECK_LAUNCH("rsc_linear_add_ln_fwd");
   return RSC_OK;
 }
 
@@ -474,11 +611,11 @@ extern "C" int rsc_linear_dx(const void *dy, const void *w, const void *aux, voi
             gemm::map2d(&tD, dx, M, K, lddx, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
             gemm::map2d(&tD2, act ? aux : dx, M, K, lddx, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   RSC_CHECK_ARG(ok, "rsc_linear_dx: cuTensorMapEncodeTiled failed");
-  gemm::Params p{(int)M, K, N, nullptr, 1};
+  gemm::Params p{(int)M, K, N, nullptr, 1, nullptr, nullptr, nullptr, nullptr, nullptr, 1, 0.f};
   int rc;
-  if (act == 1) rc = gemm::dispatch_bn<true, gemm::EPI_DGELU>(BN, tA, tB, tD, tD2, p, (cudaStream_t)stream);
-  else if (act == 2) rc = gemm::dispatch_bn<true, gemm::EPI_DRELU>(BN, tA, tB, tD, tD2, p, (cudaStream_t)stream);
-  else rc = gemm::dispatch_bn<true, gemm::EPI_BIAS>(BN, tA, tB, tD, tD2, p, (cudaStream_t)stream);
+  if (act == 1) rc = gemm::dispatch_bn<true, gemm::EPI_DGELU>(BN, tA, tB, tD, tD2, tD2, p, (cudaStream_t)stream);
+  else if (act == 2) rc = gemm::dispatch_bn<true, gemm::EPI_DRELU>(BN, tA, tB, tD, tD2, tD2, p, (cudaStream_t)stream);
+  else rc = gemm::dispatch_bn<true, gemm::EPI_BIAS>(BN, tA, tB, tD, tD2, tD2, p, (cudaStream_t)stream);
   RSC_CHECK_ARG(rc == 0, "rsc_linear_dx: no tile shape for K = %d", K);
   RSC_CHECK_LAUNCH("rsc_linear_dx");
   return RSC_OK;

@@ -254,6 +254,23 @@ class FFN(nn.Module):
             return None
         return ops.mlp(x, lin.weight, lin.bias, last.weight, last.bias if with_last_bias else None, code)
 
+    def fused_add_ln(self, x, identity, norm):
+        """(r, n) = (identity + FFN(x), norm(r)) through ops.mlp_add_ln (the residual add and the LayerNorm in the second
+        GEMM's epilogue), or None when that path does not apply (dropout active, widths, dtype, short sequences)."""
+        if len(self.layers) != 3 or not self.add_identity:
+            return None
+        (lin, act, drop), last = self.layers[0], self.layers[1]
+        code = ops.ACT_RELU if isinstance(act, nn.ReLU) else (
+            ops.ACT_GELU if isinstance(act, nn.GELU) and act.approximate == 'none' else None)
+        active = self.training and (drop.p > 0. or self.layers[2].p > 0. or (
+            isinstance(self.dropout_layer, nn.Dropout) and self.dropout_layer.p > 0.) or (
+            isinstance(self.dropout_layer, DropPath) and self.dropout_layer.drop_prob > 0.))
+        if code is None or active or last.bias is None or not ops.mlp_supported(x, lin.weight, lin.bias, last.weight) or \
+                not ops.linear_add_ln_supported(x, last.weight, identity):
+            return None
+        return ops.mlp_add_ln(x, lin.weight, lin.bias, last.weight, last.bias, identity, None, norm.weight, norm.bias, code,
+                              norm.eps)
+
     def _mlp(self, x):
         """self.layers(x) with Linear + bias + activation of the hidden layers as GEMM + ONE fused pass
         (ops.bias_relu / ops.bias_gelu: the bias gradient comes out of the activation's backward pass)."""
@@ -567,7 +584,13 @@ class BaseTransformerLayer(nn.Module):
                     attn_mask=attn_masks[attn_index], key_padding_mask=key_padding_mask, _defer=nxt_norm, **kwargs)
                 attn_index += 1
             elif layer == 'ffn':
-                out = self.ffns[ffn_index](query, identity if self.pre_norm else None, _defer=nxt_norm)
+                out = None
+                if nxt_norm:      # the whole sub-layer + residual + LayerNorm on the tcgen05 GEMMs when it applies
+                    fused = self.ffns[ffn_index].fused_add_ln(query, query, self.norms[norm_index])
+                    if fused is not None:
+                        query, skip_norm, out = fused[1], True, fused[1]
+                if out is None:
+                    out = self.ffns[ffn_index](query, identity if self.pre_norm else None, _defer=nxt_norm)
                 ffn_index += 1
             if isinstance(out, tuple):
                 x_, bias_, id_ = out

@@ -112,17 +112,26 @@ class SwinBlock(nn.Module):
         qkv = m.qkv(n1)
         a = ops.wmsa(qkv, m.qkv.bias, m.relative_position_bias_table, (H, W), m.num_heads, self.attn.window_size,
                      self.attn.shift_size, m.scale)
-        a = ops.linear(a, m.proj.weight, None)             # proj bias is added inside add_ln
-        x1, n2 = ops.add_ln(x, a, m.proj.bias, self.attn.drop.scale_vec(x), self.norm2.weight, self.norm2.bias,
-                            self.norm2.eps)
+        s1 = self.attn.drop.scale_vec(x)
+        if ops.linear_add_ln_supported(a, m.proj.weight, x):
+            # proj + bias + DropPath + residual + norm2 in ONE tcgen05 GEMM (the LayerNorm lives in its epilogue)
+            x1, n2 = ops.linear_add_ln(a, m.proj.weight, m.proj.bias, x, s1, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        else:
+            a = ops.linear(a, m.proj.weight, None)             # proj bias is added inside add_ln
+            x1, n2 = ops.add_ln(x, a, m.proj.bias, s1, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         fc1, fc2 = self.ffn.layers[0][0], self.ffn.layers[1]
-        if ops.mlp_supported(n2, fc1.weight, fc1.bias, fc2.weight):
+        s2 = self.ffn.dropout_layer.scale_vec(x)
+        fused_mlp = ops.mlp_supported(n2, fc1.weight, fc1.bias, fc2.weight)
+        if fused_mlp and next_norm is not None and ops.linear_add_ln_supported(n2, fc2.weight, x1):
+            # fc1 + GELU | fc2 + bias + DropPath + residual + the NEXT LayerNorm: two GEMM launches for the whole MLP tail
+            return ops.mlp_add_ln(n2, fc1.weight, fc1.bias, fc2.weight, fc2.bias, x1, s2, next_norm.weight, next_norm.bias,
+                                  ops.ACT_GELU, next_norm.eps)
+        if fused_mlp:
             # both Linears on the tcgen05 GEMMs: bias + GELU in fc1's epilogue, GELU' in the epilogue of fc2's dX
             f = ops.mlp(n2, fc1.weight, fc1.bias, fc2.weight, None, ops.ACT_GELU)
         else:
             g = ops.bias_gelu(ops.linear(n2, fc1.weight, None), fc1.bias)
             f = ops.linear(g, fc2.weight, None)
-        s2 = self.ffn.dropout_layer.scale_vec(x)
         if next_norm is not None:
             return ops.add_ln(x1, f, fc2.bias, s2, next_norm.weight, next_norm.bias, next_norm.eps)
         f = f + fc2.bias.to(f.dtype)

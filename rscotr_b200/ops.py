@@ -948,6 +948,168 @@ class _MLP(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2, None, None, None, None
 
 
+class _LinearAddLN(torch.autograd.Function):
+    """(r, n) = (identity + (x W^T + bias) * scale[sample], LayerNorm(r)): ops.linear + ops.add_ln with the add / LayerNorm in
+    the GEMM epilogue (rsc_linear_add_ln_fwd).  Backward = rsc_add_ln_bwd followed by the Linear's dX / dW kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, identity, scale, gamma, beta, w, eps, grads):
+        x2 = x.reshape(-1, x.shape[-1])
+        idc = identity.contiguous()
+        N = w.shape[0]
+        rows = x2.shape[0]
+        rps = rows // idc.shape[0]
+        b32 = None if bias is None else (bias.detach() if bias.dtype == torch.float32 else bias.detach().float())
+        s32, g32, be32 = _f32(scale), _f32(gamma), _f32(beta)
+        r = torch.empty(idc.shape, dtype=torch.bfloat16, device=x.device)
+        n = torch.empty_like(r)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        K = x2.shape[1]
+        with torch.cuda.device(x.device):
+            call('rsc_linear_add_ln_fwd', x2.data_ptr(), w.data_ptr(), _p(b32), idc.data_ptr(), _p(s32), g32.data_ptr(),
+                 be32.data_ptr(), r.data_ptr(), n.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, N, K, x2.stride(0),
+                 w.stride(0), rps, float(eps), _stream(), alg_bytes=2 * (rows * K + N * K + 3 * rows * N),
+                 alg_flops=2 * rows * N * K)
+        ctx.save_for_backward(x2, w, r, g32, mean, rstd, s32)
+        ctx.meta = (rows, rps, N, weight.dtype, None if bias is None else bias.dtype, gamma.dtype, beta.dtype, grads,
+                    weight.shape, x.shape)
+        return r, n
+
+    @staticmethod
+    def backward(ctx, dr_ext, dn):
+        x2, w, r, g32, mean, rstd, s32 = ctx.saved_tensors
+        rows, rps, C, wdt, bdt, gdt, bedt, (gw, gbias, gg, gb), wshape, xshape = ctx.meta
+        dev = r.device
+        if dn is None:
+            dn = torch.zeros_like(r)
+        dn = dn.contiguous()
+        dr_ext = None if dr_ext is None else dr_ext.contiguous()
+        d_id = torch.empty_like(r)
+        dy = torch.empty_like(r) if s32 is not None else None          # gradient of the Linear's output (scaled branch)
+        direct = gg is not None and gb is not None
+        dg = gg if direct else torch.zeros(C, dtype=torch.float32, device=dev)
+        db = gb if direct else torch.zeros(C, dtype=torch.float32, device=dev)
+        dbias = None
+        if bdt is not None:
+            dbias = gbias if gbias is not None else torch.zeros(C, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call('rsc_add_ln_bwd', r.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dn.data_ptr(),
+                 _p(dr_ext), _p(s32), d_id.data_ptr(), _p(dy), dg.data_ptr(), db.data_ptr(), _p(dbias), rows, rps, C,
+                 _dt(r), _stream(), alg_bytes=(4 + (dr_ext is not None) + (dy is not None)) * r.numel() * r.element_size())
+        dy2 = (dy if dy is not None else d_id).view(rows, C)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = (gemm_dx(dy2, w) if _own_plain(C) else torch.mm(dy2, w)).view(xshape)
+        if ctx.needs_input_grad[1]:
+            dw, _ = _accumulate_dw(dy2, x2, gw, None, wdt, None, wshape, False)       # (the bias gradient came out of add_ln_bwd)
+        return (dx, dw, None if (bdt is None or gbias is not None) else dbias.to(bdt), d_id, None,
+                None if direct else dg.to(gdt), None if direct else db.to(bedt), None, None, None)
+
+
+class _MLPAddLN(torch.autograd.Function):
+    """(r, n) = (identity + (act(x W1^T + b1) W2^T + b2) * scale[sample], LayerNorm(r)): a whole FFN sub-layer with its
+    residual add and the following LayerNorm in three kernels (GEMM + activation epilogue, GEMM + add / LayerNorm epilogue).
+    Backward: rsc_add_ln_bwd, then the kernels of _MLP.backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight1, bias1, weight2, bias2, identity, scale, gamma, beta, w1, w2, act, eps, grads):
+        x2 = x.reshape(-1, x.shape[-1])
+        idc = identity.contiguous()
+        rows, C = x2.shape[0], w2.shape[0]
+        rps = rows // idc.shape[0]
+        b1 = bias1.detach() if bias1.dtype == torch.float32 else bias1.detach().float()
+        y, h = gemm_fwd(x2, w1, b1, act)
+        b2 = None if bias2 is None else (bias2.detach() if bias2.dtype == torch.float32 else bias2.detach().float())
+        s32, g32, be32 = _f32(scale), _f32(gamma), _f32(beta)
+        r = torch.empty(idc.shape, dtype=torch.bfloat16, device=x.device)
+        n = torch.empty_like(r)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        Kh = y.shape[1]
+        with torch.cuda.device(x.device):
+            call('rsc_linear_add_ln_fwd', y.data_ptr(), w2.data_ptr(), _p(b2), idc.data_ptr(), _p(s32), g32.data_ptr(),
+                 be32.data_ptr(), r.data_ptr(), n.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C, Kh, y.stride(0),
+                 w2.stride(0), rps, float(eps), _stream(), alg_bytes=2 * (rows * Kh + C * Kh + 3 * rows * C),
+                 alg_flops=2 * rows * C * Kh)
+        ctx.save_for_backward(x2, w1, w2, y, h, r, g32, mean, rstd, s32)
+        ctx.meta = (act, rows, rps, C, grads, weight1.dtype, bias1.dtype, weight2.dtype, None if bias2 is None else bias2.dtype,
+                    gamma.dtype, beta.dtype, weight1.shape, weight2.shape, x.shape)
+        return r, n
+
+    @staticmethod
+    def backward(ctx, dr_ext, dn):
+        x2, w1, w2, y, h, r, g32, mean, rstd, s32 = ctx.saved_tensors
+        (act, rows, rps, C, (gw1, gb1, gw2, gb2, gg, gb), w1dt, b1dt, w2dt, b2dt, gdt, bedt, w1shape, w2shape,
+         xshape) = ctx.meta
+        dev = r.device
+        if dn is None:
+            dn = torch.zeros_like(r)
+        dn = dn.contiguous()
+        dr_ext = None if dr_ext is None else dr_ext.contiguous()
+        d_id = torch.empty_like(r)
+        dz = torch.empty_like(r) if s32 is not None else None
+        direct = gg is not None and gb is not None
+        dg = gg if direct else torch.zeros(C, dtype=torch.float32, device=dev)
+        db = gb if direct else torch.zeros(C, dtype=torch.float32, device=dev)
+        dbias2 = None
+        if b2dt is not None:
+            dbias2 = gb2 if gb2 is not None else torch.zeros(C, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call('rsc_add_ln_bwd', r.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dn.data_ptr(),
+                 _p(dr_ext), _p(s32), d_id.data_ptr(), _p(dz), dg.data_ptr(), db.data_ptr(), _p(dbias2), rows, rps, C,
+                 _dt(r), _stream(), alg_bytes=(4 + (dr_ext is not None) + (dz is not None)) * r.numel() * r.element_size())
+        dz2 = (dz if dz is not None else d_id).view(rows, C)
+        dw2, _ = _accumulate_dw(dz2, y, gw2, None, w2dt, None, w2shape, False)
+        dh = gemm_dx(dz2, w2, h if act == 1 else y, act)
+        dw1, db1 = _accumulate_dw(dh, x2, gw1, gb1, w1dt, b1dt, w1shape, True)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = (gemm_dx(dh, w1) if _own_plain(dh.shape[1]) else torch.mm(dh, w1)).view(xshape)
+        return (dx, dw1, db1, dw2, None if (b2dt is None or gb2 is not None) else dbias2.to(b2dt), d_id, None,
+                None if direct else dg.to(gdt), None if direct else db.to(bedt), None, None, None, None, None)
+
+
+def mlp_add_ln(x, weight1, bias1, weight2, bias2, identity, scale, gamma, beta, act, eps=1e-5):
+    """FFN sub-layer + residual + LayerNorm -> (r, n).  Call only when mlp_supported(x, W1, b1, W2) and
+    linear_add_ln_supported(x, W2, identity)."""
+    if torch.is_autocast_enabled('cuda'):
+        x = x.to(torch.get_autocast_dtype('cuda'))
+    x = x.contiguous()
+    grads = (_flat_grad(weight1), _flat_grad(bias1), _flat_grad(weight2), None if bias2 is None else _flat_grad(bias2),
+             _flat_grad(gamma), _flat_grad(beta))
+    if not torch.is_grad_enabled():
+        grads = (None,) * 6
+    w1, w2 = _compute_copy(weight1, None, torch.bfloat16), _compute_copy(weight2, None, torch.bfloat16)
+    return _MLPAddLN.apply(x, weight1, bias1, weight2, bias2, identity, scale, gamma, beta, w1, w2,
+                           {ACT_GELU: 1, ACT_RELU: 2, ACT_GELU_SIG: 1}[act], float(eps), grads)
+
+
+def linear_add_ln_supported(x, weight, identity):
+    """the fused Linear + residual + LayerNorm kernel: bf16, the normalised width fits one GEMM tile (<= 256)"""
+    if not (_OWN_GEMM and x.is_cuda and weight.dim() == 2):
+        return False
+    dt = torch.get_autocast_dtype('cuda') if torch.is_autocast_enabled('cuda') else x.dtype
+    N, K = weight.shape
+    rows = x.numel() // x.shape[-1]
+    # (a 256-wide tile leaves room for two pipeline stages only beside its two staging tiles: with a long contraction the
+    # library GEMM + rsc_add_ln_fwd pair is faster -- measured on the encoder FFN, K = 2048)
+    return (dt == torch.bfloat16 and identity.dtype == torch.bfloat16 and N % 32 == 0 and N <= 256 and K % 8 == 0 and
+            (N <= 192 or K < 512) and rows >= _TC_MIN_ROWS and rows % identity.shape[0] == 0 and bool(_lib.lib().rsc_add_ln_supported(N)))
+
+
+def linear_add_ln(x, weight, bias, identity, scale, gamma, beta, eps=1e-5):
+    """r = identity + (x W^T + bias) * scale[b]; n = LayerNorm(r); -> (r, n).  Call only when linear_add_ln_supported(...)."""
+    if torch.is_autocast_enabled('cuda'):
+        x = x.to(torch.get_autocast_dtype('cuda'))
+    x = x.contiguous()
+    grads = (_flat_grad(weight), None if bias is None else _flat_grad(bias), _flat_grad(gamma), _flat_grad(beta))
+    if not torch.is_grad_enabled():
+        grads = (None, None, None, None)
+    w = _compute_copy(weight, None, torch.bfloat16)
+    return _LinearAddLN.apply(x, weight, bias, identity, scale, gamma, beta, w, float(eps), grads)
+
+
 def mlp_supported(x, weight1, bias1, weight2):
     """the fused FFN runs on bf16 CUDA activations with feature counts that are multiples of 8"""
     if not (_OWN_GEMM and x.is_cuda and bias1 is not None and weight1.dim() == 2 and weight2.dim() == 2):

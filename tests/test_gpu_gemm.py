@@ -118,3 +118,37 @@ def test_linear_leading_dimensions():
     torch.cuda.synchronize()
     assert rel(y, x.float() @ w.float().t()) < 4e-3
     assert torch.count_nonzero(yw[:, :N]) == 0
+
+
+@pytest.mark.parametrize('B,L,N,K', [(2, 2500, 96, 96), (4, 1100, 96, 384), (2, 2100, 192, 768), (1, 13294, 256, 2048),
+                                     (3, 1400, 256, 256), (2, 2049, 128, 64), (1, 4096, 128, 96)])
+@pytest.mark.parametrize('with_scale', [True, False])
+def test_linear_add_ln_fused(B, L, N, K, with_scale):
+    """ops.linear_add_ln (Linear + residual add with the per-sample DropPath scale + LayerNorm in the GEMM epilogue) against
+    the fp32 composition, values and every gradient (x, weight, bias, identity, gamma, beta)."""
+    from rscotr_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + N + K)
+    x = torch.randn(B, L, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, generator=g) * 0.3
+    ident = (torch.randn(B, L, N, generator=g) * 2 + 0.5).bfloat16()
+    scale = (torch.rand(B, generator=g) > 0.3).float() / 0.7 if with_scale else None
+    gamma, beta = 1 + 0.2 * torch.randn(N, generator=g), 0.2 * torch.randn(N, generator=g)
+    wr, wn = torch.randn(B, L, N, generator=g), torch.randn(B, L, N, generator=g)
+    # fp32 composition on the same rounded operands
+    xr, wrf, br, ir, gr, ber = (t.float().clone().requires_grad_(True) for t in (x, w, bias, ident, gamma, beta))
+    y = F.linear(xr, wrf, br)
+    r_ref = ir + (y * scale.view(B, 1, 1) if with_scale else y)
+    n_ref = F.layer_norm(r_ref, (N,), gr, ber, 1e-5)
+    ((r_ref * wr).sum() + (n_ref * wn).sum()).backward()
+    xc, wc, bc, ic, gc, bec = (t.clone().cuda().requires_grad_(True) for t in (x, w, bias, ident, gamma, beta))
+    assert ops.linear_add_ln_supported(xc, wc, ic)
+    r, n = ops.linear_add_ln(xc, wc, bc, ic, scale.cuda() if with_scale else None, gc, bec, 1e-5)
+    ((r.float() * wr.cuda()).sum() + (n.float() * wn.cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    assert rel(r, r_ref) < 5e-3 and rel(n, n_ref) < 8e-3
+    assert rel(xc.grad, xr.grad) < 2e-2
+    assert rel(wc.grad, wrf.grad) < 2e-2
+    assert rel(bc.grad, br.grad) < 2e-2
+    assert rel(ic.grad, ir.grad) < 2e-2
+    assert rel(gc.grad, gr.grad) < 2e-2 and rel(bec.grad, ber.grad) < 2e-2
