@@ -330,6 +330,26 @@ int rsc_linear_dx(const void *dy, const void *w, const void *aux, void *dx, int6
 int rsc_linear_dw(const void *dy, const void *x, float *dw, float *db, int64_t M, int N, int K, int64_t lddy, int64_t ldx,
                   int64_t lddw, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Convolutions as im2col GEMMs and the PPM pooling, channels-last maps (B,H,W,C).
+ * Replaces nn.Conv2d (cuDNN) behind mmdet ChannelMapper (cfg MTL_slvlcls_...py:26-33),
+ * the lateral / output / mask-feature convs of seg_head/pixel_decoder.py:39-64,158-170 and
+ * mmseg UPerHead / PPM, and nn.AdaptiveAvgPool2d of PPM.
+ * A k x k convolution is rsc_im2col_fwd + rsc_linear_fwd on the gathered matrix with the
+ * weight laid out (Cout, kh, kw, Cin); a 1x1 convolution is rsc_linear_fwd alone on the
+ * (B*H*W, C) token matrix.  Backward: rsc_linear_dx / rsc_linear_dw, then rsc_im2col_bwd.
+ *   col  (B*Ho*Wo, kh*kw*C), column = (tap = i*kw + j, c); Ho = (H + 2 pad - kh)/stride + 1
+ *   rsc_im2col_bwd: dx (B,H,W,C) = adjoint gather, fully written (no atomics)
+ *   rsc_adaptive_avgpool_*: bins [floor(i H / S), ceil((i+1) H / S)) as torch
+ * C % 8 == 0 (bf16) / C % 4 == 0 (float); 16-byte aligned pointers.
+ * ---------------------------------------------------------------------- */
+int rsc_im2col_fwd(const void *x, void *col, int B, int H, int W, int C, int kh, int kw, int stride, int pad, int dtype,
+                   void *stream);
+int rsc_im2col_bwd(const void *dcol, void *dx, int B, int H, int W, int C, int kh, int kw, int stride, int pad, int dtype,
+                   void *stream);
+int rsc_adaptive_avgpool_fwd(const void *x, void *y, int B, int H, int W, int C, int S, int dtype, void *stream);
+int rsc_adaptive_avgpool_bwd(const void *dy, void *dx, int B, int H, int W, int C, int S, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

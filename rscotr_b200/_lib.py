@@ -52,6 +52,10 @@ _SIGS = {
     'rsc_bilinear_bwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     'rsc_sigmoid_focal_loss_fwd': [_P, _P, _P, _I, _I, _F, _F, _I, _P],
     'rsc_sigmoid_focal_loss_bwd': [_P, _P, _P, _I, _I, _F, _F, _I, _P],
+    'rsc_im2col_fwd': [_P, _P] + [_I] * 9 + [_P],
+    'rsc_im2col_bwd': [_P, _P] + [_I] * 9 + [_P],
+    'rsc_adaptive_avgpool_fwd': [_P, _P] + [_I] * 6 + [_P],
+    'rsc_adaptive_avgpool_bwd': [_P, _P] + [_I] * 6 + [_P],
     'rsc_linear_fwd': [_P, _P, _P, _P, _P, ctypes.c_int64, _I, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _I, _P],
     'rsc_linear_add_ln_fwd': [_P] * 11 + [ctypes.c_int64, _I, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _F, _P],
     'rsc_linear_dx': [_P, _P, _P, _P, ctypes.c_int64, _I, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _I, _P],

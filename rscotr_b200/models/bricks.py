@@ -721,6 +721,18 @@ def inverse_sigmoid(x, eps=1e-5):
     return torch.log(x1 / x2)
 
 
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d whose CUDA forward / backward is an im2col GEMM on this repo's kernels (ops.conv2d: rsc_im2col_* +
+    rsc_linear_*); same parameters / state-dict keys.  CPU tensors and the cases ops.conv2d does not cover (groups, dilation,
+    odd channel counts like the 3-channel image stem) use the stock implementation."""
+
+    def forward(self, x):
+        if self.padding_mode == 'zeros' and ops.conv2d_supported(x, self.weight, self.stride, self.padding, self.dilation,
+                                                                  self.groups):
+            return ops.conv2d(x, self.weight, self.bias, self.stride, self.padding)
+        return super().forward(x)
+
+
 class ConvModule(nn.Module):
     """mmcv ConvModule (conv -> norm -> act); conv bias only without norm."""
 
@@ -729,7 +741,7 @@ class ConvModule(nn.Module):
         super().__init__()
         if bias == 'auto':
             bias = norm_cfg is None
-        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=bias)
+        self.conv = Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=bias)
         self.norm_name = None
         if norm_cfg is not None:
             self.norm_name = norm_abbr(norm_cfg)

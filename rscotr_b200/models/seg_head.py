@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..config import MODELS, build_from_cfg
-from .bricks import (GeomCache, Linear, ConvModule, build_positional_encoding, build_transformer_layer_sequence,
+from .bricks import (GeomCache, Linear, Conv2d, ConvModule, build_positional_encoding, build_transformer_layer_sequence,
                      const_tensor)
 
 
@@ -103,7 +103,7 @@ class MlvlSegPixelDecoder(nn.Module):
                                                  norm_cfg=norm_cfg, act_cfg=None))
             self.output_convs.append(ConvModule(feat_channels, feat_channels, 3, stride=1, padding=1,
                                                 bias=self.use_bias, norm_cfg=norm_cfg, act_cfg=act_cfg))
-        self.mask_feature = nn.Conv2d(feat_channels, out_channels, kernel_size=1, stride=1, padding=0)
+        self.mask_feature = Conv2d(feat_channels, out_channels, kernel_size=1, stride=1, padding=0)
         self.num_outs = num_outs
 
     def init_weights(self):
@@ -147,7 +147,7 @@ class Mask2FormerHead(nn.Module):
         self.decoder_input_projs = nn.ModuleList()
         for _ in range(num_transformer_feat_level):
             if self.decoder_embed_dims != feat_channels or enforce_decoder_input_project:
-                self.decoder_input_projs.append(nn.Conv2d(feat_channels, self.decoder_embed_dims, kernel_size=1))
+                self.decoder_input_projs.append(Conv2d(feat_channels, self.decoder_embed_dims, kernel_size=1))
             else:
                 self.decoder_input_projs.append(nn.Identity())
         self.decoder_positional_encoding = build_positional_encoding(positional_encoding)

@@ -4,7 +4,8 @@ its own; the row follows mmseg 0.28 `UPerHead` / `PPM` / `FCNHead` / `EncoderDec
 mmseg's parameter names so its checkpoints load:
 `psp_modules.{k}.1.{conv,bn}`, `bottleneck`, `lateral_convs.{i}`, `fpn_convs.{i}`, `fpn_bottleneck`, `conv_seg`.
 
-The 3x3 convolutions are tensor-core implicit GEMMs of the vendor library (bf16, channels-last); the loss is
+The convolutions are im2col GEMMs on this repo's kernels (rsc_im2col_* gather + the tcgen05 rsc_linear_* GEMMs; 1x1
+convolutions are the GEMM alone), the PPM pooling is rsc_adaptive_avgpool_*; the loss is
 the fused bilinear-upsample + cross-entropy kernel shared with the Mask2Former head (rsc_upsample_ce_*), so
 the (B, C, 512, 512) up-sampled logits are never written.  BatchNorm is per rank (SyncBN would add a
 forward-time collective; the north star exchanges gradients only -- SURVEY D.5)."""
@@ -15,7 +16,19 @@ import torch.nn.functional as F
 from .. import ops
 from ..config import MODELS, build_from_cfg
 from .mtl import SingleTaskModel, add_prefix
+from .bricks import Conv2d
 from .seg_head import resize
+
+
+class AdaptiveAvgPool2d(nn.AdaptiveAvgPool2d):
+    """PPM pooling on rsc_adaptive_avgpool_* (channels-last) for CUDA fp32 / bf16 maps with C % 8 == 0"""
+
+    def forward(self, x):
+        s = self.output_size if isinstance(self.output_size, int) else (
+            self.output_size[0] if self.output_size[0] == self.output_size[1] else None)
+        if s is not None and x.is_cuda and x.dim() == 4 and x.shape[1] % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16):
+            return ops.adaptive_avg_pool2d(x, s)
+        return super().forward(x)
 
 
 class ConvModule(nn.Module):
@@ -23,7 +36,7 @@ class ConvModule(nn.Module):
 
     def __init__(self, cin, cout, kernel_size, padding=0, dilation=1, norm=True, act=True):
         super().__init__()
-        self.conv = nn.Conv2d(cin, cout, kernel_size, padding=padding, dilation=dilation, bias=not norm)
+        self.conv = Conv2d(cin, cout, kernel_size, padding=padding, dilation=dilation, bias=not norm)
         self.bn = nn.BatchNorm2d(cout) if norm else None
         self.act = act
         nn.init.kaiming_normal_(self.conv.weight, mode='fan_out', nonlinearity='relu')
@@ -64,7 +77,7 @@ class _DecodeHead(nn.Module):
         self.norm = norm_cfg is not None
         if norm_cfg is not None and norm_cfg.get('type') not in ('BN', 'SyncBN'):
             raise KeyError('norm %s is not supported by the UPerNet heads' % norm_cfg.get('type'))
-        self.conv_seg = nn.Conv2d(channels, num_classes, kernel_size=1)
+        self.conv_seg = Conv2d(channels, num_classes, kernel_size=1)
         self.dropout = nn.Dropout2d(dropout_ratio) if dropout_ratio > 0 else None
         nn.init.normal_(self.conv_seg.weight, mean=0, std=0.01)
         nn.init.zeros_(self.conv_seg.bias)
@@ -91,7 +104,7 @@ class UPerHead(_DecodeHead):
         top = self.in_channels[-1]
         # pyramid pooling on the coarsest map: pooled to s x s, 1x1 conv, bilinearly back up
         self.psp_modules = nn.ModuleList(
-            nn.Sequential(nn.AdaptiveAvgPool2d(s), ConvModule(top, channels, 1, norm=self.norm)) for s in pool_scales)
+            nn.Sequential(AdaptiveAvgPool2d(s), ConvModule(top, channels, 1, norm=self.norm)) for s in pool_scales)
         self.bottleneck = ConvModule(top + len(pool_scales) * channels, channels, 3, padding=1, norm=self.norm)
         self.lateral_convs = nn.ModuleList(ConvModule(c, channels, 1, norm=self.norm) for c in self.in_channels[:-1])
         self.fpn_convs = nn.ModuleList(ConvModule(channels, channels, 3, padding=1, norm=self.norm) for _ in self.in_channels[:-1])

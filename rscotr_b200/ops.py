@@ -1181,6 +1181,102 @@ def linear(x, weight, bias=None, rows=None):
     return torch.nn.functional.linear(x, _rows(weight, rows), _rows(bias, rows))
 
 
+# ---------------------------------------------------------------------------
+# convolutions as im2col GEMMs, PPM pooling          
+# ---------------------------------------------------------------------------
+class _Im2Col(torch.autograd.Function):
+    """channels-last (B,H,W,C) -> (B*Ho*Wo, kh*kw*C), column = (tap, c); backward = the adjoint gather"""
+
+    @staticmethod
+    def forward(ctx, x, kh, kw, stride, pad):
+        _cuda(x)
+        B, H, W, C = x.shape
+        Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+        col = torch.empty(B * Ho * Wo, kh * kw * C, dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            call('rsc_im2col_fwd', x.data_ptr(), col.data_ptr(), B, H, W, C, kh, kw, stride, pad, _dt(x), _stream(),
+                 alg_bytes=(x.numel() + col.numel()) * x.element_size())
+        ctx.meta = (B, H, W, C, kh, kw, stride, pad)
+        return col
+
+    @staticmethod
+    def backward(ctx, dcol):
+        B, H, W, C, kh, kw, stride, pad = ctx.meta
+        dcol = dcol.contiguous()
+        dx = torch.empty(B, H, W, C, dtype=dcol.dtype, device=dcol.device)
+        with torch.cuda.device(dcol.device):
+            call('rsc_im2col_bwd', dcol.data_ptr(), dx.data_ptr(), B, H, W, C, kh, kw, stride, pad, _dt(dcol), _stream(),
+                 alg_bytes=(dx.numel() + dcol.numel()) * dcol.element_size())
+        return dx, None, None, None, None
+
+
+def conv2d_supported(x, weight, stride=1, padding=0, dilation=1, groups=1):
+    """nn.Conv2d cases that run as (gather +) GEMM: CUDA, fp32 / bf16 compute, square stride / padding, no dilation / groups,
+    input channels a multiple of 8"""
+    if not (x.is_cuda and x.dim() == 4 and weight.dim() == 4 and groups == 1):
+        return False
+    one = lambda v: v if isinstance(v, int) else (v[0] if len(set(v)) == 1 else None)
+    if one(stride) is None or one(padding) is None or one(dilation) != 1:
+        return False
+    dt = torch.get_autocast_dtype('cuda') if torch.is_autocast_enabled('cuda') else x.dtype
+    return dt in (torch.float32, torch.bfloat16) and x.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0):
+    """F.conv2d(x, weight, bias, stride, padding) on a (B,C,H,W) tensor (any strides; channels-last is free) as an im2col
+    GEMM: the k x k gather is rsc_im2col_fwd (none for 1x1 / stride 1), the contraction ops.linear (the tcgen05 kernels in
+    bf16).  Returns a (B,Cout,Ho,Wo) tensor with channels-last strides."""
+    one = lambda v: v if isinstance(v, int) else v[0]
+    stride, padding = one(stride), one(padding)
+    Cout, Cin, kh, kw = weight.shape
+    if torch.is_autocast_enabled('cuda'):
+        x = x.to(torch.get_autocast_dtype('cuda'))
+    B, _, H, W = x.shape
+    xl = x.permute(0, 2, 3, 1)                    # (B,H,W,C): a view for channels-last inputs
+    if not xl.is_contiguous():
+        xl = xl.contiguous()
+    Ho, Wo = (H + 2 * padding - kh) // stride + 1, (W + 2 * padding - kw) // stride + 1
+    if kh == 1 and kw == 1 and stride == 1 and padding == 0:
+        # the (Cout, Cin, 1, 1) parameter IS the GEMM's weight matrix: the engine's bf16 shadow / flat gradient views apply
+        y = _linear_nd(xl.reshape(B * H * W, Cin), weight, bias)
+    else:
+        a = _Im2Col.apply(xl, kh, kw, stride, padding)
+        w2 = weight.permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin)      # (Cout, kh, kw, Cin): matches the gather's column order
+        y = linear(a, w2, bias)
+    return y.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
+
+
+class _AdaptiveAvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, S):
+        _cuda(x)
+        B, H, W, C = x.shape
+        y = torch.empty(B, S, S, C, dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            call('rsc_adaptive_avgpool_fwd', x.data_ptr(), y.data_ptr(), B, H, W, C, S, _dt(x), _stream(),
+                 alg_bytes=(x.numel() + y.numel()) * x.element_size())
+        ctx.meta = (B, H, W, C, S)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, C, S = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty(B, H, W, C, dtype=dy.dtype, device=dy.device)
+        with torch.cuda.device(dy.device):
+            call('rsc_adaptive_avgpool_bwd', dy.data_ptr(), dx.data_ptr(), B, H, W, C, S, _dt(dy), _stream(),
+                 alg_bytes=(dx.numel() + dy.numel()) * dy.element_size())
+        return dx, None
+
+
+def adaptive_avg_pool2d(x, size):
+    """nn.AdaptiveAvgPool2d(size) on a (B,C,H,W) CUDA tensor (fp32 / bf16, C % 8 == 0) -> (B,C,size,size), channels-last strides"""
+    xl = x.permute(0, 2, 3, 1)
+    if not xl.is_contiguous():
+        xl = xl.contiguous()
+    return _AdaptiveAvgPool.apply(xl, int(size)).permute(0, 3, 1, 2)
+
+
 KernelTimer = _lib.KernelTimer
 
 
