@@ -192,7 +192,14 @@ def oracle_step_fn(cfg, img_hw):
 
 
 def per_gpu_batch(cfg):
-    return {n: cfg.data[n]['config']['data']['samples_per_gpu'] for n in TASK_ORDER}
+    out = {}
+    for n, d in cfg.data.items():
+        sub = d.get('config')
+        bs = (d.get('data') or {}).get('samples_per_gpu')
+        if bs is None and hasattr(sub, 'get'):
+            bs = (sub.get('data') or {}).get('samples_per_gpu')
+        out[n] = int(bs or 1)
+    return out
 
 
 def _nvtx_range(name):
@@ -338,7 +345,9 @@ def main():
     T0 = time.time()
     cfg, model, engine, loader = build(args.config, args.dtype, device)
     it = iter(loader)
-    host_batches = [next(it) for _ in range(6)]                  # 2 distinct batches per task, pinned host memory
+    names = list(cfg.data.keys())                                # round-robin order of the datasets (one task each)
+    NB = 2 * len(names)
+    host_batches = [next(it) for _ in range(NB)]                 # 2 distinct batches per dataset, pinned host memory
     dev_batches = [_to_device(b, device) for b in host_batches]
     torch.cuda.synchronize()
 
@@ -354,10 +363,10 @@ def main():
 
     # ---- warm-up (also fixes the per-task all-reduce ranges, cuBLAS heuristics, allocator)
     # (with CUDA graphs every task needs 2 eager iterations + the capturing one before the timed region)
-    n_warm = max(args.warmup, 9 if engine.use_graphs else 3)
+    n_warm = max(args.warmup, 3 * len(names) if engine.use_graphs else 3)
     for i in range(n_warm):
-        trace('warm-up step %d (%s)' % (i, dev_batches[i % 6]['task']))
-        engine.train_iter(dev_batches[i % 6])
+        trace('warm-up step %d (%s)' % (i, dev_batches[i % NB]['task']))
+        engine.train_iter(dev_batches[i % NB])
         if os.environ.get('RSC_BENCH_TRACE'):
             torch.cuda.synchronize()
     trace('warm-up done')
@@ -378,10 +387,10 @@ def main():
     for i in range(args.steps):
         a = torch.cuda.Event(enable_timing=True)
         a.record()
-        out = engine.train_iter(dev_batches[i % 6])
+        out = engine.train_iter(dev_batches[i % NB])
         b = torch.cuda.Event(enable_timing=True)
         b.record()
-        evs.append((dev_batches[i % 6]['task'], a, b))
+        evs.append((dev_batches[i % NB]['task'], a, b))
     e1.record()
     nvtx()
     trace('timed region A enqueued')
@@ -396,7 +405,8 @@ def main():
     # timed region above is what --steps asks for; at 20-30 steps it lasts 0.3-0.4 s, i.e. it is a burst number)
     sustained = None
     if args.sustained_s > 0:
-        n_sus = max(90, int(1.1 * args.sustained_s / max(ms / args.steps / 1000.0, 1e-4)) // 3 * 3 + 3)
+        nn_ = len(names)
+        n_sus = max(30 * nn_, int(1.1 * args.sustained_s / max(ms / args.steps / 1000.0, 1e-4)) // nn_ * nn_ + nn_)
         s_sampler = ClockSampler(local)
         if rank == 0:
             s_sampler.start()
@@ -404,7 +414,7 @@ def main():
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for i in range(n_sus):
-            engine.train_iter(dev_batches[i % 6])
+            engine.train_iter(dev_batches[i % NB])
         s1.record()
         barrier()
         sus_ms = s0.elapsed_time(s1)
@@ -412,18 +422,18 @@ def main():
             t = torch.tensor([sus_ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sus_ms = float(t[0])
-        sustained = dict(value=world * n_sus / (sus_ms / 1000.0), unit='iters/s', steps=n_sus, cycles=n_sus // 3,
+        sustained = dict(value=world * n_sus / (sus_ms / 1000.0), unit='iters/s', steps=n_sus, cycles=n_sus // len(names),
                          seconds=sus_ms / 1000.0, ms_per_step=sus_ms / n_sus,
                          clocks=s_sampler.stop() if rank == 0 else None)
         trace('sustained leg done')
     # per-kernel CUDA-event timing of the same steps (two cycles).  The step engine runs eagerly while a
     # KernelTimer is active: events cannot be recorded per kernel inside a CUDA-graph replay.
     with ops.KernelTimer() as kt:
-        for i in range(6):
-            engine.train_iter(dev_batches[i % 6])
+        for i in range(NB):
+            engine.train_iter(dev_batches[i % NB])
         ksum = kt.summary()
     trace('kernel-timer pass done')
-    kscale = args.steps / 6.0                                       # normalise kernel ms to the timed region's steps
+    kscale = args.steps / float(NB)                                       # normalise kernel ms to the timed region's steps
     for d in ksum.values():
         for k in ('ms', 'bytes', 'big_ms', 'big_bytes', 'big_flops'):
             d[k] *= kscale
@@ -448,7 +458,7 @@ def main():
 
     engine.prefetch(host_batches[0])
     for i in range(args.steps):
-        batch = host_batches[i % 6]
+        batch = host_batches[i % NB]
         hb += h2d_bytes(batch)
         o = engine.train_iter(batch)
         loss_host[i:i + 1].copy_(o['loss'].detach().reshape(1).float(), non_blocking=True)   # D2H of the step's result
@@ -456,7 +466,7 @@ def main():
         read_ev[i].record()
         db += 4
         if i + 1 < args.steps:
-            engine.prefetch(host_batches[(i + 1) % 6])                    # next step's H2D overlaps this step's compute
+            engine.prefetch(host_batches[(i + 1) % NB])                    # next step's H2D overlaps this step's compute
         if i > 0:
             consume(i - 1)
     consume(args.steps - 1)
@@ -531,13 +541,16 @@ def main():
     out = dict(metric=METRIC, value=value, unit='iters/s', n_gpus=world, steps=args.steps, warmup=n_warm,
                ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                dtype=args.dtype if args.dtype != 'fp32' else 'f32', data='synthetic',
-               config=dict(workload='Swin-T MTL co-training (cls+seg+det round-robin) 3x800x800 (BASELINE configs[%d])'
-                                    % (1 if world == 1 else 2),
+               config=dict(workload=('Swin-T MTL co-training (cls+seg+det round-robin) 3x800x800 (BASELINE configs[%d])'
+                                     % (1 if world == 1 else 2)) if os.path.abspath(args.config) == os.path.abspath(CONFIG) else
+                           '%s: %s, synthetic %s' % (os.path.relpath(args.config, ROOT), cfg.model.get('type'),
+                                                     'x'.join(str(v) for v in dev_batches[0]['img'].shape[1:])),
                            per_gpu_batch=bs, global_batch={k: v * world for k, v in bs.items()},
                            parallelism='dp%d' % world, strategy='round_robin', config_file=os.path.relpath(args.config, ROOT),
                            l2='no flush: each step streams >1 GB of activations (inputs alone 123 MB fp32 for the cls '
                               'batch), far above the 126 MB L2',
-                           weights='random init, 62.6 M params', final_loss=final_loss),
+                           weights='random init, %.1f M params' % (sum(p.numel() for p in model.parameters()) / 1e6),
+                           final_loss=final_loss),
                clocks=clocks,
                e2e=dict(value=e2e, unit='iters/s', h2d_bytes_per_step=hb // args.steps, d2h_bytes_per_step=db // args.steps,
                         ms_per_step=ms_e2e / args.steps,
@@ -550,7 +563,7 @@ def main():
                                 big_launches=d['big_launches'], big_ms=round(d['big_ms'], 3),
                                 big_gbs=round(d['big_gbs'], 1), big_frac=round(d['big_gbs'] / peak, 4))
                         for k, d in sorted(ksum.items())})
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and os.path.abspath(args.config) == os.path.abspath(CONFIG):
         del engine, model, dev_batches
         torch.cuda.empty_cache()
         out['cpu_baseline'] = cpu_baseline(cfg)
