@@ -350,6 +350,39 @@ int rsc_im2col_bwd(const void *dcol, void *dx, int B, int H, int W, int C, int k
 int rsc_adaptive_avgpool_fwd(const void *x, void *y, int B, int H, int W, int C, int S, int dtype, void *stream);
 int rsc_adaptive_avgpool_bwd(const void *dy, void *dx, int B, int H, int W, int C, int S, int dtype, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Decoder attention core: O = softmax(Q K^T * scale + mask) V for nn.MultiheadAttention
+ * as mmcv's MultiheadAttention wrapper calls it from the DINO decoder's self-attention
+ * (models/multi/bbox_head/dino_head.py -> DinoTransformerDecoder; constant denoising mask
+ * of query_denoising.py:167-190) and from the Mask2Former-style seg decoder
+ * (models/multi/seg_head/mask2former_head.py:174-197; cross-attention masked by the previous
+ * layer's mask prediction, :111-139).  Replaces F.multi_head_attention_forward's bmm / softmax /
+ * bmm (8f rank 2).  bf16, head_dim 32, fp32 accumulation.
+ *   q (Lq,B,H,32) / k, v (Lk,B,H,32) / out (Lq,B,H,32): element strides *_sl (sequence) and
+ *   *_sb (batch), heads contiguous (32 apart); all strides multiples of 8.
+ *   mask_bits: NULL, or uint32 words [image (stride mask_sb words, 0 = shared)][Lq][ceil(Lk/32)];
+ *   bit (k & 31) of word k >> 5 set = key k masked for that query.  A fully masked row yields 0.
+ *   lse (B*H, Lq) float: log2-domain log-sum-exp (saved for the backward).
+ *   nsplit > 1 splits the keys over CTAs (use rsc_attn_nsplit); ws then holds
+ *   nsplit*B*H*Lq*34 floats.
+ * rsc_attn_bwd: dq32 (Lq,B,H,32) float, fully written; dk / dv bf16 with their own strides;
+ *   delta_ws (B*H*Lq) float scratch.  `out` / `dout` share the strides o_sl / o_sb.
+ * rsc_m2f_mask_bits: mask_pred (rows = B*Q, Hi, Wi) logits -> bits (rows, ceil(Ho*Wo/32)):
+ *   bilinear resize (align_corners=False) to the key grid (Ho,Wo), masked = sigmoid < 0.5,
+ *   rows with every key masked are cleared (mask2former_head.py:134-139, :177-178).
+ * rsc_pack_mask_bits: boolean mask (rows, Lk) bytes, non-zero = masked -> bits.
+ * ---------------------------------------------------------------------- */
+int rsc_attn_nsplit(int B, int H, int Lq, int Lk);
+int rsc_attn_fwd(const void *q, const void *k, const void *v, const void *mask_bits, void *out, float *lse, float *ws, int B,
+                 int H, int Lq, int Lk, int head_dim, int64_t q_sl, int64_t q_sb, int64_t k_sl, int64_t k_sb, int64_t v_sl,
+                 int64_t v_sb, int64_t o_sl, int64_t o_sb, int64_t mask_sb, int nsplit, float scale, void *stream);
+int rsc_attn_bwd(const void *q, const void *k, const void *v, const void *mask_bits, const void *out, const void *dout,
+                 const float *lse, float *delta_ws, float *dq32, void *dk, void *dv, int B, int H, int Lq, int Lk, int head_dim,
+                 int64_t q_sl, int64_t q_sb, int64_t k_sl, int64_t k_sb, int64_t v_sl, int64_t v_sb, int64_t o_sl, int64_t o_sb,
+                 int64_t dk_sl, int64_t dk_sb, int64_t dv_sl, int64_t dv_sb, int64_t mask_sb, float scale, void *stream);
+int rsc_m2f_mask_bits(const void *mask_pred, void *bits, int rows, int Hi, int Wi, int Ho, int Wo, int dtype, void *stream);
+int rsc_pack_mask_bits(const void *mask_u8, void *bits, int64_t rows, int Lk, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

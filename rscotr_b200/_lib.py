@@ -60,6 +60,11 @@ _SIGS = {
     'rsc_linear_add_ln_fwd': [_P] * 11 + [ctypes.c_int64, _I, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _F, _P],
     'rsc_linear_dx': [_P, _P, _P, _P, ctypes.c_int64, _I, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _I, _P],
     'rsc_linear_dw': [_P, _P, _P, _P, ctypes.c_int64, _I, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _P],
+    'rsc_attn_nsplit': [_I, _I, _I, _I],
+    'rsc_attn_fwd': [_P] * 7 + [_I] * 5 + [ctypes.c_int64] * 9 + [_I, _F, _P],
+    'rsc_attn_bwd': [_P] * 11 + [_I] * 5 + [ctypes.c_int64] * 13 + [_F, _P],
+    'rsc_m2f_mask_bits': [_P, _P] + [_I] * 6 + [_P],
+    'rsc_pack_mask_bits': [_P, _P, ctypes.c_int64, _I, _P],
 }
 
 

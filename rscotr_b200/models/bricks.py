@@ -19,6 +19,7 @@ from ..config import MODELS, build_from_cfg
 
 _CONST_CACHE = {}
 _DEFER = __import__('os').environ.get('RSC_NO_DEFER') is None     # A/B switch for the fused post-norm pairs
+_OWN_ATTN = __import__('os').environ.get('RSC_OWN_ATTN', '1') != '0'       # rsc_attn_* core (0: library SDPA)
 _CONST_ATTN_BIAS = __import__('os').environ.get('RSC_CONST_ATTN_BIAS', '1') != '0'    # A/B'd on B200 in round 2: promoted
 
 
@@ -341,18 +342,41 @@ class MultiheadAttention(nn.Module):
     def _attend(self, query, key, value, attn_mask, key_padding_mask, same_qk=False, defer=False):
         """nn.MultiheadAttention.forward(need_weights=False) on seq-first (L,B,E) tensors with the packed
         in_proj applied through ops.linear (bf16 shadow weights, gradients accumulated into the flat
-        buffer; q and k share one GEMM when they read the same tensor) and the library SDPA core."""
+        buffer; q and k share one GEMM when they read the same tensor) and the rsc_attn_{fwd,bwd} core (bf16, head
+        dim 32; anything else -- the fp32 parity path, attention dropout, key padding masks -- takes the library SDPA)."""
         m = self.attn
         E, H = self.embed_dims, self.num_heads
         L, B, _ = query.shape
         S = key.shape[0]
         W, bias = m.in_proj_weight, m.in_proj_bias
+        qk = None
         if same_qk or key is query:
             qk = ops.linear(query, W, bias, rows=(0, 2 * E))
             q, k = qk[..., :E], qk[..., E:]
         else:
             q, k = ops.linear(query, W, bias, rows=(0, E)), ops.linear(key, W, bias, rows=(E, 2 * E))
         v = ops.linear(value, W, bias, rows=(2 * E, 3 * E))
+        own = (_OWN_ATTN and ops.attention_supported(q, E, H) and key_padding_mask is None and
+               not (self.training and m.dropout > 0.) and
+               (attn_mask is None or isinstance(attn_mask, ops.MaskBits) or
+                (torch.is_tensor(attn_mask) and attn_mask.dtype == torch.bool and
+                 (attn_mask.dim() == 2 or (attn_mask.dim() == 4 and attn_mask.shape[1] == 1)))))
+        if own:
+            # rsc_attn_{fwd,bwd}: masks as bit words (one bit per (image | 1, query, key), shared by the heads)
+            bits = attn_mask
+            if torch.is_tensor(attn_mask):
+                cache = getattr(attn_mask, '_rsc_add', None)       # shape-only constant (DINO denoising mask): pack once
+                bits = cache.get('bits') if cache is not None else None
+                if bits is None:
+                    bits = ops.pack_mask_bits(attn_mask if attn_mask.dim() == 2 else attn_mask[:, 0])
+                    if cache is not None:
+                        cache['bits'] = bits
+            out = ops.attention(q, k, v.to(q.dtype), H, bits, packed_qk=qk if qk is not None and qk.dtype == v.dtype else None)
+            if defer:
+                return ops.linear(out, m.out_proj.weight, None)
+            return ops.linear(out, m.out_proj.weight, m.out_proj.bias)
+        if isinstance(attn_mask, ops.MaskBits):
+            raise RuntimeError('bit-packed attention masks need the rsc_attn kernels (bf16, head dim 32, no attention dropout)')
         q = q.reshape(L, B, H, E // H).permute(1, 2, 0, 3)
         k = k.reshape(S, B, H, E // H).permute(1, 2, 0, 3)
         v = v.reshape(S, B, H, E // H).permute(1, 2, 0, 3)

@@ -80,6 +80,7 @@ def encode_neck_levels(self, encoder, neck_feats, batch_size, num_input_levels):
     return outs
 
 
+_MASK_BITS = __import__('os').environ.get('RSC_MASK_BITS', '1') != '0'       # rsc_m2f_mask_bits + rsc_attn_* (0: boolean mask + library SDPA)
 _COMPACT_ATTN_MASK = __import__('os').environ.get('RSC_COMPACT_ATTN_MASK', '1') != '0'   # A/B'd on B200 in round 2 (+1.1 % it/s): promoted
 
 
@@ -172,19 +173,31 @@ class Mask2FormerHead(nn.Module):
             if p.dim() > 1:
                 nn.init.xavier_normal_(p)
 
-    def forward_head(self, decoder_out, mask_feature, attn_mask_target_size):
+    def forward_head(self, decoder_out, mask_feature, attn_mask_target_size, need_seg=True, need_mask=True):
+        """mask2former_head.py:111-139.  -> (seg_mask, attn_mask).  On the bf16 CUDA path attn_mask is an ops.MaskBits
+        (rsc_m2f_mask_bits: resize + threshold + the all-masked-row rule of :177-178 in one kernel, one bit per
+        (image, query, key)); otherwise the reference's boolean tensor.  need_seg / need_mask: the decoder loop uses only
+        the mask of the intermediate calls and only the segmentation of the last one (the reference computes and
+        discards the rest)."""
         decoder_out = self.transformer_decoder.post_norm(decoder_out)
         decoder_out = decoder_out.transpose(0, 1)
         mask_embed = self.mask_embed(decoder_out)
         mask_pred = torch.einsum('bqd,bdhw->bqhw', mask_embed, mask_feature)
-        if self.scheme == 1:
+        seg_mask = None
+        if not need_seg:
+            pass
+        elif self.scheme == 1:
             cls_pred = self.cls_embed(decoder_out)
             seg_mask = torch.einsum('bqc,bqhw->bchw', cls_pred, mask_pred)
         elif self.scheme == 2:
             seg_mask = mask_pred
         else:
             raise NotImplementedError
+        if not need_mask:
+            return seg_mask, None
         with torch.no_grad():
+            if _MASK_BITS and ops.attention_supported(mask_pred, getattr(self, "decoder_embed_dims", 0), self.num_heads):
+                return seg_mask, ops.m2f_attn_mask(mask_pred, attn_mask_target_size)
             attn_mask = resize(mask_pred.detach(), attn_mask_target_size)
             if _COMPACT_ATTN_MASK:
                 # (RSC_COMPACT_ATTN_MASK=0 restores the reference's layout) the reference repeats the resized logits over the heads BEFORE the
@@ -219,19 +232,27 @@ class Mask2FormerHead(nn.Module):
         decoder_positional_encodings = [p.to(adt) for p in decoder_positional_encodings]
         query_feat = self.query_feat.weight.to(adt).unsqueeze(1).repeat((1, batch_size, 1))
         query_embed = self.query_embed.weight.to(adt).unsqueeze(1).repeat((1, batch_size, 1))
-        mask_pred, attn_mask = self.forward_head(query_feat, mask_features, multi_scale_memorys[0].shape[-2:])
+        with torch.no_grad():
+            _, attn_mask = self.forward_head(query_feat, mask_features, multi_scale_memorys[0].shape[-2:], need_seg=False)
+        last = self.num_transformer_decoder_layers - 1
         for i in range(self.num_transformer_decoder_layers):
             level_idx = i % self.num_transformer_feat_level
-            # if a mask is all True (all background), set it all False (sync-free form of the reference's
-            # attn_mask[torch.where(attn_mask.sum(-1) == attn_mask.shape[-1])] = False)
-            attn_mask = attn_mask & ~attn_mask.all(-1, keepdim=True)
+            if not isinstance(attn_mask, ops.MaskBits):
+                # if a mask is all True (all background), set it all False (sync-free form of the reference's
+                # attn_mask[torch.where(attn_mask.sum(-1) == attn_mask.shape[-1])] = False); the bit-mask kernel has
+                # already applied the rule
+                attn_mask = attn_mask & ~attn_mask.all(-1, keepdim=True)
             layer = self.transformer_decoder.layers[i]
             query_feat = layer(query=query_feat, key=decoder_inputs[level_idx], value=decoder_inputs[level_idx],
                                query_pos=query_embed, key_pos=decoder_positional_encodings[level_idx],
                                attn_masks=[attn_mask, None], query_key_padding_mask=None, key_padding_mask=None)
-            mask_pred, attn_mask = self.forward_head(
-                query_feat, mask_features,
-                multi_scale_memorys[(i + 1) % self.num_transformer_feat_level].shape[-2:])
+            if i < last:      # only the mask feeds the next layer (it is detached: no gradient through these calls)
+                with torch.no_grad():
+                    _, attn_mask = self.forward_head(
+                        query_feat, mask_features,
+                        multi_scale_memorys[(i + 1) % self.num_transformer_feat_level].shape[-2:], need_seg=False)
+            else:
+                mask_pred, _ = self.forward_head(query_feat, mask_features, None, need_mask=False)
         return mask_pred
 
     def losses(self, seg_logit, seg_label):

@@ -286,11 +286,18 @@ class SwinTransformer(nn.Module):
                 self._drop_paths = [m for m in self.modules() if isinstance(m, DropPath)]
             draw_drop_paths(self._drop_paths, x.shape[0], x.device, torch.float32)
         outs = []
+        # data-parallel step engine (mtl/engine/step.py::_on_grad_ready): told from inside backward when the
+        # gradients of stage i and everything after it are final, so their all-reduce overlaps the earlier stages
+        ready = getattr(self, '_grad_ready_cb', None) if torch.is_grad_enabled() else None
         for i, stage in enumerate(self.stages):
+            if ready is not None and i > 0 and x.requires_grad:
+                x.register_hook(lambda g, i=i: ready(i))
             x, hw_shape, out, out_hw_shape = stage(x, hw_shape,
                                                    getattr(self, 'norm%d' % i) if i in self.out_indices else None)
             if i in self.out_indices:
                 # logical NCHW, channels-last strides: a view, no transpose copy
                 out = out.view(-1, *out_hw_shape, self.num_features[i]).permute(0, 3, 1, 2)
+                if ready is not None and out.requires_grad:
+                    out.register_hook(lambda g: ready('outs'))
                 outs.append(out)
         return outs

@@ -12,8 +12,10 @@ B200-first structure:
   * bf16 autocast for the GEMMs / kernels, fp32 master weights, fused AdamW.
   * inputs arrive in pinned host memory and are copied with non_blocking H2D.
 """
+import bisect
 import math
 import os
+import re
 
 import torch
 import torch.distributed as dist
@@ -22,6 +24,7 @@ from ... import _lib
 from ..utils.optimizer import build_optimizer
 
 _ORDER = ('backbone', 'cls_head', 'neck', 'shared_encoder', 'bbox_head', 'seg_head')
+_STAGE_RE = re.compile(r'backbone\.(?:stages\.(\d+)\.|norm(\d+)\.)')
 
 
 def _to_device(obj, device):
@@ -57,6 +60,16 @@ def h2d_bytes(obj):
     if isinstance(obj, dict):
         return sum(h2d_bytes(v) for v in obj.values())
     return 0
+
+
+class _DivAfter:
+    """async SUM all-reduce whose wait() finishes the mean (back ends without an averaging reduction)."""
+    def __init__(self, work, seg, world):
+        self.work, self.seg, self.world = work, seg, world
+
+    def wait(self):
+        self.work.wait()
+        self.seg.div_(self.world)
 
 
 class StepEngine:
@@ -101,7 +114,15 @@ class StepEngine:
         def rank(n):
             top = n.split('.')[0]
             return _ORDER.index(top) if top in _ORDER else len(_ORDER)
-        order = [i for i in sorted(range(len(named)), key=lambda i: (rank(named[i][0]), i)) if named[i][1].requires_grad]
+
+        def sub(n):
+            # backbone parameters in the order their gradients complete, last first: stage K's output norm sits
+            # with stage K, so "everything from stage K on" is ONE contiguous tail of the backbone range (the
+            # buckets of the overlapped exchange, _on_grad_ready)
+            m = _STAGE_RE.match(n)
+            return int(m.group(1) or m.group(2)) + 1 if m else 0
+        order = [i for i in sorted(range(len(named)), key=lambda i: (rank(named[i][0]), sub(named[i][0]), i))
+                 if named[i][1].requires_grad]
         self._spans = []          # (name, start, end)
         off = 0
         for i in order:
@@ -129,6 +150,22 @@ class StepEngine:
             p._rsc_g = self._grad_views[-1]
             p._rsc_lp = self.flat_param_lp[s0:e0].view_as(p) if lp else None
         self._grad_of = {id(p): v for p, v in zip(self._params, self._grad_views)}
+        self._span_starts = [s0 for _, s0, _ in self._spans]
+        # gradient-completion frontiers of the overlapped exchange: key -> flat offset from which every gradient is
+        # final once the backbone reports `key` during backward ('outs' = the whole backbone is still pending)
+        self._frontier_of = {}
+        tops = [n.split('.')[0] for n, _, _ in self._spans]
+        if 'backbone' in tops:
+            self._frontier_of['outs'] = max(e for (n, s, e), t in zip(self._spans, tops) if t == 'backbone')
+            for n, s0, _ in self._spans:
+                m = _STAGE_RE.match(n)
+                if m and m.group(1) is not None:
+                    self._frontier_of.setdefault(int(m.group(1)), s0)
+        self._min_bucket = int(os.environ.get('RSC_MIN_BUCKET', 1 << 20))     # elements; smaller pieces ride with the next
+        self._pending = None
+        bb = getattr(self.model, 'backbone', None)
+        if self.world > 1 and bb is not None and os.environ.get('RSC_OVERLAP_EXCHANGE', '1') != '0':
+            bb._grad_ready_cb = self._on_grad_ready
         if self.world > 1:
             # what the reference's DDP wrapper does at construction (mtl/apis/train.py:37-46): rank 0's weights
             # (and buffers) win, so per-rank init differences (--diff-seed, nondeterministic init) cannot leave the
@@ -148,11 +185,14 @@ class StepEngine:
         """the slice of the flat gradient buffer that belongs to `param`."""
         return self._grad_of[id(param)]
 
-    def _collect_grads(self):
+    def _collect_grads(self, lo=0, hi=None):
         """autograd's per-parameter gradients -> flat buffer (one multi-tensor copy instead of one
-        accumulate kernel per parameter); parameters the task did not touch keep their zero fill."""
+        accumulate kernel per parameter); parameters the task did not touch keep their zero fill.
+        `lo`, `hi`: only the parameters whose span starts inside that flat range."""
         dst, src = [], []
-        for p, v in zip(self._params, self._grad_views):
+        i0 = bisect.bisect_left(self._span_starts, lo)
+        i1 = len(self._params) if hi is None else bisect.bisect_left(self._span_starts, hi)
+        for p, v in zip(self._params[i0:i1], self._grad_views[i0:i1]):
             if p.grad is not None:
                 dst.append(v)
                 src.append(p.grad)
@@ -239,16 +279,68 @@ class StepEngine:
         else:
             self._graphs.clear()                                 # lr is baked into captured launches: re-capture
 
+    # -- gradient exchange (row 8e; reference: the DDP wrapper of mtl/apis/train.py:37-46) --------------------
+    def _all_reduce_mean(self, lo, hi, async_op):
+        """mean over ranks of flat_grad[lo:hi], in place.  NCCL averages inside the collective (ncclAvg: no separate
+        1/world pass over the gradients); gloo (CPU tests) sums and divides."""
+        seg = self.flat_grad[lo:hi]
+        if self.device.type == 'cuda':
+            return dist.all_reduce(seg, op=dist.ReduceOp.AVG, async_op=async_op)
+        work = dist.all_reduce(seg, async_op=async_op)
+        return _DivAfter(work, seg, self.world) if async_op else seg.div_(self.world)
+
+    def _on_grad_ready(self, key):
+        """Called by the backbone from inside backward (tensor hooks on its outputs / stage inputs): the engine runs
+        nodes in reverse creation order, so when the gradient of stage K's input is about to be consumed every
+        parameter used after it in forward -- flat offsets >= frontier(K) -- has its final gradient.  That tail of the
+        task's active range(s) is all-reduced NOW, asynchronously (NCCL's own stream; captured as a parallel branch
+        of the step's CUDA graph), while backward continues through the earlier stages."""
+        st = self._pending
+        if st is None or key not in self._frontier_of:
+            return
+        new = self._frontier_of[key]
+        if new >= st['frontier']:
+            return
+        pieces = [(max(lo, new), min(hi, st['frontier'])) for lo, hi in st['ranges']]
+        pieces = [(a, b) for a, b in pieces if b > a]
+        if sum(b - a for a, b in pieces) < self._min_bucket:
+            return                                    # too small to pay for a collective: rides with the next bucket
+        self._collect_grads(new, st['frontier'])
+        for a, b in pieces:
+            st['works'].append(self._all_reduce_mean(a, b, True))
+        st['frontier'] = new
+
+    def _exchange_grads(self, task):
+        """after backward: reduce what the in-backward buckets have not covered, then join them."""
+        st, self._pending = self._pending, None
+        if st is None:                                # first iteration of this task: the ranges are found now
+            self._collect_grads()
+            for lo, hi in self._active_ranges(task):
+                self._all_reduce_mean(lo, hi, False)
+            return
+        self._collect_grads(0, st['frontier'])
+        for lo, hi in st['ranges']:
+            if lo < st['frontier']:
+                st['works'].append(self._all_reduce_mean(lo, min(hi, st['frontier']), True))
+        self.last_buckets = len(st['works'])
+        for w in st['works']:
+            w.wait()
+
     # -- one co-training iteration ------------------------------------------
     def _backward_and_step(self, outputs, task):
         """OptimizerHook.after_train_iter: backward, gradient exchange, global-norm clip, AdamW."""
-        outputs['loss'].backward()
-        self._collect_grads()
         if self.world > 1:
-            for lo, hi in self._active_ranges(task):
-                seg = self.flat_grad[lo:hi]
-                dist.all_reduce(seg)
-                seg.div_(self.world)
+            ranges = self._task_ranges.get(task)
+            self._pending = dict(ranges=ranges, frontier=self.flat_grad.numel(), works=[]) if ranges else None
+            try:
+                outputs['loss'].backward()
+            except BaseException:
+                self._pending = None
+                raise
+            self._exchange_grads(task)
+        else:
+            outputs['loss'].backward()
+            self._collect_grads()
         clip_coef = None
         if self.grad_clip:
             max_norm = float(self.grad_clip['max_norm'])

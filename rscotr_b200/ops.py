@@ -1277,6 +1277,122 @@ def adaptive_avg_pool2d(x, size):
     return _AdaptiveAvgPool.apply(xl, int(size)).permute(0, 3, 1, 2)
 
 
+# ---------------------------------------------------------------------------
+# decoder attention core + bit masks              (8f rank 2)
+# ---------------------------------------------------------------------------
+class MaskBits:
+    """An attention mask as bit words (rsc_attn_*): `bits` int32 (Bm, Lq, ceil(Lk/32)), Bm = 1 (shared by the batch) or B;
+    bit set = that key is masked for that query, the same for every head."""
+
+    def __init__(self, bits, Lk):
+        self.bits, self.Lk = bits, Lk
+
+
+def pack_mask_bits(mask):
+    """boolean mask (Lq, Lk) or (B, Lq, Lk), True = masked (the torch MHA convention) -> MaskBits"""
+    _cuda(mask)
+    assert mask.dtype == torch.bool and mask.dim() in (2, 3)
+    m = mask.contiguous().view(torch.uint8)
+    Lk = m.shape[-1]
+    bits = torch.empty(m.shape[:-1] + ((Lk + 31) // 32,), dtype=torch.int32, device=m.device)
+    with torch.cuda.device(m.device):
+        call('rsc_pack_mask_bits', m.data_ptr(), bits.data_ptr(), m.numel() // Lk, Lk, _stream())
+    return MaskBits(bits.view((1,) * (3 - bits.dim()) + bits.shape), Lk)
+
+
+def m2f_attn_mask(mask_pred, size):
+    """The Mask2Former cross-attention mask of the next decoder layer from mask_pred (B, Q, Hi, Wi) logits: bilinear
+    resize to the key grid `size`, sigmoid < 0.5 = masked, rows with every key masked un-masked
+    (mask2former_head.py:134-139 + :177-178) -> MaskBits (B, Q, ceil(h*w/32)); one kernel, nothing else is materialised."""
+    _cuda(mask_pred)
+    x = mask_pred.detach().contiguous()
+    B, Q, Hi, Wi = x.shape
+    h, w = int(size[0]), int(size[1])
+    bits = torch.empty(B, Q, (h * w + 31) // 32, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        call('rsc_m2f_mask_bits', x.data_ptr(), bits.data_ptr(), B * Q, Hi, Wi, h, w, _dt(x), _stream(),
+             alg_bytes=x.numel() * x.element_size())
+    return MaskBits(bits, h * w)
+
+
+def attention_supported(x, embed_dims, heads):
+    return x.is_cuda and x.dtype == torch.bfloat16 and embed_dims == heads * 32
+
+
+def _sl_sb(t):
+    """(sequence, batch) element strides of a (L, B, E) view whose last dimension is contiguous"""
+    assert t.stride(2) == 1
+    return t.stride(0), t.stride(1)
+
+
+class _Attention(torch.autograd.Function):
+    """q / k / v: (L, B, E) bf16 views (last dim contiguous) of `srcs` = the projection outputs they were sliced from;
+    layout[i] = (index into srcs, column offset).  Gradients are written straight into tensors shaped like the
+    sources, so a packed q|k projection gets ONE (L, B, 2E) gradient without slice-backward zero fills."""
+
+    @staticmethod
+    def forward(ctx, heads, mask, layout, *srcs):
+        E = heads * 32
+        q, k, v = (srcs[i][..., c:c + E] for i, c in layout)
+        Lq, B, _ = q.shape
+        Lk = k.shape[0]
+        out = torch.empty(Lq, B, E, dtype=q.dtype, device=q.device)
+        lse = torch.empty(B * heads, Lq, dtype=torch.float32, device=q.device)
+        scale = 32 ** -0.5
+        with torch.cuda.device(q.device):
+            ns = _lib.lib().rsc_attn_nsplit(B, heads, Lq, Lk)
+            ws = torch.empty(ns * B * heads * Lq * 34, dtype=torch.float32, device=q.device) if ns > 1 else None
+            mb = mask.bits if mask is not None else None
+            if mb is not None:
+                assert mask.Lk == Lk and mb.shape[1] == Lq and mb.shape[0] in (1, B), 'mask bits do not match the attention shape'
+            call('rsc_attn_fwd', q.data_ptr(), k.data_ptr(), v.data_ptr(), _p(mb), out.data_ptr(), lse.data_ptr(), _p(ws),
+                 B, heads, Lq, Lk, 32, *_sl_sb(q), *_sl_sb(k), *_sl_sb(v), *_sl_sb(out),
+                 0 if mb is None or mb.shape[0] == 1 else mb.stride(0), ns, scale, _stream(),
+                 alg_bytes=(2 * q.numel() + 2 * k.numel()) * 2, alg_flops=4 * B * heads * Lq * Lk * 32)
+        ctx.save_for_backward(out, lse, *srcs)
+        ctx.meta = (heads, mask, layout, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        heads, mask, layout, scale = ctx.meta
+        out, lse, *srcs = ctx.saved_tensors
+        E = heads * 32
+        q, k, v = (srcs[i][..., c:c + E] for i, c in layout)
+        Lq, B, _ = q.shape
+        Lk = k.shape[0]
+        dout = dout.contiguous()
+        grads = [torch.empty_like(s) for s in srcs]
+        dk, dv = (grads[i][..., c:c + E] for i, c in layout[1:])
+        dq32 = torch.empty(Lq, B, E, dtype=torch.float32, device=q.device)
+        delta = torch.empty(B * heads * Lq, dtype=torch.float32, device=q.device)
+        mb = mask.bits if mask is not None else None
+        with torch.cuda.device(q.device):
+            call('rsc_attn_bwd', q.data_ptr(), k.data_ptr(), v.data_ptr(), _p(mb), out.data_ptr(), dout.data_ptr(),
+                 lse.data_ptr(), delta.data_ptr(), dq32.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, heads, Lq, Lk, 32,
+                 *_sl_sb(q), *_sl_sb(k), *_sl_sb(v), *_sl_sb(out), *_sl_sb(dk), *_sl_sb(dv),
+                 0 if mb is None or mb.shape[0] == 1 else mb.stride(0), scale, _stream(),
+                 alg_bytes=(3 * q.numel() + 4 * k.numel()) * 2, alg_flops=10 * B * heads * Lq * Lk * 32)
+        i, c = layout[0]
+        grads[i][..., c:c + E].copy_(dq32)
+        return (None, None, None) + tuple(grads)
+
+
+def attention(q, k, v, heads, mask=None, packed_qk=None):
+    """softmax(q k^T / sqrt(32) + mask) v per head.  q (Lq,B,E), k / v (Lk,B,E) bf16 CUDA tensors, E = heads*32.
+    packed_qk (L,B,2E): the output of ONE q|k projection (self-attention); q and k are then its column halves and its
+    gradient is produced in one piece (no slice-backward zero fills).  mask: MaskBits or None.  -> (Lq,B,E)."""
+    E = heads * 32
+
+    def ok(t):
+        return t if t.stride(2) == 1 and t.stride(0) % 8 == 0 and t.stride(1) % 8 == 0 else t.contiguous()
+    if packed_qk is not None:
+        _cuda(packed_qk, v)
+        return _Attention.apply(heads, mask, ((0, 0), (0, E), (1, 0)), ok(packed_qk), ok(v))
+    _cuda(q, k, v)
+    return _Attention.apply(heads, mask, ((0, 0), (1, 0), (2, 0)), ok(q), ok(k), ok(v))
+
+
 KernelTimer = _lib.KernelTimer
 
 

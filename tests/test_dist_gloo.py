@@ -33,6 +33,7 @@ def _worker(rank, world, port, out_dir):
     model = MODELS.build(small_cfg().model)
     model.init_weights()
     model.train()
+    os.environ['RSC_MIN_BUCKET'] = '1'                     # (tiny model: let every in-backward bucket fire)
     eng = StepEngine(model, dict(type='AdamW', lr=1e-3, weight_decay=1e-4), grad_clip=dict(max_norm=0.1, norm_type=2),
                      device='cpu', compute_dtype=torch.float32, use_graphs=False)
     assert eng.world == world
@@ -48,9 +49,20 @@ def _worker(rank, world, port, out_dir):
             local['loss'].backward()
             eng._collect_grads()
             g_local = eng.flat_grad.clone()
-            out = eng.train_iter(batch)
+            out = eng.train_iter(batch)            # first iteration of the task: ranges found, plain exchange
             res[task] = dict(g_local=g_local, loss=float(out['loss'].detach()), log=dict(out['log_vars'].items()),
                              ranges=list(eng._task_ranges[task]))
+            # second iteration: the overlapped exchange (buckets all-reduced from inside backward).  Its result must
+            # be the cross-rank mean of the local gradients at the same weights.
+            eng.flat_grad.zero_()
+            torch.manual_seed(7)
+            model.train_step(dict(batch), None)['loss'].backward()
+            eng._collect_grads()
+            res[task]['g_local2'] = eng.flat_grad.clone()
+            torch.manual_seed(7)
+            eng.train_iter(batch)
+            res[task]['g_mean2'] = eng.flat_grad.clone()
+            res[task]['buckets'] = eng.last_buckets
     # packed device-side averaging factors of the fused det loss (one all-reduce, no .item())
     res['factors'] = model.bbox_head._avg_factors_dev([2 + rank, 0], [10, 5], 'cpu').clone()
     res['sync'] = bool(model.bbox_head.sync_cls_avg_factor)
@@ -78,6 +90,12 @@ def test_two_rank_data_parallel_step(tmp_path):
         for k in r0[task]['log']:
             assert abs(r0[task]['log'][k] - r1[task]['log'][k]) < 1e-6, (task, k)
         assert r0[task]['ranges'] == r1[task]['ranges'] and len(r0[task]['ranges']) >= 1
+        # overlapped exchange == mean of the local gradients, on both ranks, from >= 3 buckets
+        want = (r0[task]['g_local2'] + r1[task]['g_local2']) / 2
+        want = want * torch.clamp(0.1 / (want.norm() + 1e-6), max=1.0)        # (the CPU optimizer path clips in place)
+        for r in (r0, r1):
+            assert torch.allclose(r[task]['g_mean2'], want, rtol=1e-5, atol=1e-7), task
+            assert r[task]['buckets'] >= 3, (task, r[task]['buckets'])
     # the cls task only touches backbone + cls_head: one contiguous range starting at 0
     assert r0['cls']['ranges'][0][0] == 0 and len(r0['cls']['ranges']) == 1
     assert len(r0['seg']['ranges']) == 2          # backbone..shared_encoder | seg_head (bbox_head skipped)

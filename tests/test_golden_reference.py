@@ -266,7 +266,7 @@ def test_seg_head_forward_control_flow_matches_reference_run(device, monkeypatch
         query_feat=emb(t['query_feat']), query_embed=emb(t['query_embed']), mask_embed=mask_embed.to(device),
         transformer_decoder=types.SimpleNamespace(post_norm=post_norm.to(device),
                                                   layers=[mg.ToyDecoderLayer() for _ in range(9)]))
-    fake.forward_head = lambda *a: Mask2FormerHead.forward_head(fake, *a)
+    fake.forward_head = lambda *a, **k: Mask2FormerHead.forward_head(fake, *a, **k)
     with _ctx(device), torch.no_grad():
         got = Mask2FormerHead.forward(fake, None, None, None, [{}] * t['B'])
     assert got.shape == want.shape
