@@ -383,6 +383,27 @@ int rsc_attn_bwd(const void *q, const void *k, const void *v, const void *mask_b
 int rsc_m2f_mask_bits(const void *mask_pred, void *bits, int rows, int Hi, int Wi, int Ho, int Wo, int dtype, void *stream);
 int rsc_pack_mask_bits(const void *mask_u8, void *bits, int64_t rows, int Lk, void *stream);
 
+/* ------------------------------------------------------------------------
+ * GroupNorm / BatchNorm (training statistics) on channels-last maps, optional fused ReLU.
+ * Replaces nn.GroupNorm / nn.BatchNorm2d (+ nn.ReLU) of mmcv ConvModule behind mmdet
+ * ChannelMapper (cfg MTL_slvlcls_...py:26-33, GN-32), seg_head/pixel_decoder.py:39-64
+ * (GN-32, ReLU on the output convs) and mmseg UPerHead / FCNHead (BN + ReLU)
+ * (SURVEY 8a rows a8, a17, a20).
+ *   x, y, dy, dx: (R, P, C), C innermost.  A statistic group = (row r, Cg consecutive channels)
+ *   over the P pixels.  GroupNorm(G) on (B,H,W,C): R = B, P = H*W, Cg = C/G.
+ *   BatchNorm2d (training): R = 1, P = B*H*W, Cg = 1; run_mean / run_var (C) are then updated
+ *   with `momentum` (unbiased variance), NULL otherwise.
+ *   stats (R, C/Cg, 2) float: mean, rstd (written by fwd, read by bwd).
+ *   ws: float scratch, R*C*2 (fwd) / R*C*2 + R*(C/Cg)*2 (bwd).  dgamma / dbeta (C) float, ACCUMULATED.
+ *   relu: y = max(norm(x), 0); the backward masks dy with the recomputed sign.
+ * rsc_norm_supported: C % (16 / element size) == 0, C <= 2048, 256 % (C / vector) == 0.
+ * ---------------------------------------------------------------------- */
+int rsc_norm_supported(int C, int dtype);
+int rsc_groupnorm_fwd(const void *x, const float *gamma, const float *beta, void *y, float *stats, float *ws, int R, int P, int C,
+                      int Cg, float eps, int relu, float *run_mean, float *run_var, float momentum, int dtype, void *stream);
+int rsc_groupnorm_bwd(const void *x, const void *dy, const float *gamma, const float *beta, const float *stats, void *dx,
+                      float *dgamma, float *dbeta, float *ws, int R, int P, int C, int Cg, int relu, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,9 @@ _SIGS = {
     'rsc_attn_bwd': [_P] * 11 + [_I] * 5 + [ctypes.c_int64] * 13 + [_F, _P],
     'rsc_m2f_mask_bits': [_P, _P] + [_I] * 6 + [_P],
     'rsc_pack_mask_bits': [_P, _P, ctypes.c_int64, _I, _P],
+    'rsc_norm_supported': [_I, _I],
+    'rsc_groupnorm_fwd': [_P] * 6 + [_I] * 4 + [_F, _I, _P, _P, _F, _I, _P],
+    'rsc_groupnorm_bwd': [_P] * 9 + [_I] * 6 + [_P],
 }
 
 

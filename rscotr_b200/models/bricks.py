@@ -137,15 +137,40 @@ class LayerNorm(nn.LayerNorm):
         return ops.layer_norm(x, self.weight, self.bias, self.eps)
 
 
+class GroupNorm(nn.GroupNorm):
+    """nn.GroupNorm parameters / state-dict keys, forward on rsc_groupnorm_{fwd,bwd} (channels-last, optional fused ReLU)"""
+
+    def forward(self, x, relu=False):
+        if self.affine and ops.norm_supported(x, self.num_channels):
+            return ops.group_norm(x, self.num_groups, self.weight, self.bias, self.eps, relu)
+        y = super().forward(x)
+        return F.relu(y) if relu else y
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d (per rank, as the reference's single-GPU configs); the training-mode forward runs on
+    rsc_groupnorm_{fwd,bwd} (one row, groups of one channel), evaluation uses the running statistics through torch"""
+
+    def forward(self, x, relu=False):
+        if (self.training and self.affine and self.track_running_stats and self.momentum is not None and
+                ops.norm_supported(x, self.num_features)):
+            if self.num_batches_tracked is not None:
+                self.num_batches_tracked.add_(1)
+            return ops.batch_norm_train(x, self.weight, self.bias, self.running_mean, self.running_var, self.momentum,
+                                        self.eps, relu)
+        y = super().forward(x)
+        return F.relu(y) if relu else y
+
+
 def build_norm(cfg, num_features):
     cfg = dict(cfg)
     t = cfg.pop('type')
     if t == 'LN':
         return LayerNorm(num_features, **cfg)
     if t == 'GN':
-        return nn.GroupNorm(cfg.pop('num_groups'), num_features, **cfg)
+        return GroupNorm(cfg.pop('num_groups'), num_features, **cfg)
     if t in ('BN', 'SyncBN'):      # per-rank BN (SURVEY D.5: no forward-time collectives)
-        return nn.BatchNorm2d(num_features, **{k: v for k, v in cfg.items() if k != 'requires_grad'})
+        return BatchNorm2d(num_features, **{k: v for k, v in cfg.items() if k != 'requires_grad'})
     raise KeyError('unsupported norm %s' % t)
 
 
@@ -775,7 +800,10 @@ class ConvModule(nn.Module):
     def forward(self, x):
         x = self.conv(x)
         if self.norm_name is not None:
-            x = getattr(self, self.norm_name)(x)
+            norm = getattr(self, self.norm_name)
+            if isinstance(self.activate, nn.ReLU) and isinstance(norm, (GroupNorm, BatchNorm2d)):
+                return norm(x, relu=True)          # conv -> (norm + ReLU in one pass)
+            x = norm(x)
         if self.activate is not None:
             x = self.activate(x)
         return x

@@ -37,7 +37,7 @@ class ConvModule(nn.Module):
     def __init__(self, cin, cout, kernel_size, padding=0, dilation=1, norm=True, act=True):
         super().__init__()
         self.conv = Conv2d(cin, cout, kernel_size, padding=padding, dilation=dilation, bias=not norm)
-        self.bn = nn.BatchNorm2d(cout) if norm else None
+        self.bn = BatchNorm2d(cout) if norm else None      # training forward: rsc_groupnorm_* with the ReLU fused
         self.act = act
         nn.init.kaiming_normal_(self.conv.weight, mode='fan_out', nonlinearity='relu')
         if self.conv.bias is not None:
@@ -46,7 +46,7 @@ class ConvModule(nn.Module):
     def forward(self, x):
         x = self.conv(x)
         if self.bn is not None:
-            x = self.bn(x)
+            return self.bn(x, relu=self.act)
         return F.relu(x) if self.act else x
 
 

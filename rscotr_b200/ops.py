@@ -1393,6 +1393,82 @@ def attention(q, k, v, heads, mask=None, packed_qk=None):
     return _Attention.apply(heads, mask, ((0, 0), (1, 0), (2, 0)), ok(q), ok(k), ok(v))
 
 
+# ---------------------------------------------------------------------------
+# GroupNorm / BatchNorm (+ReLU) on channels-last maps   
+# ---------------------------------------------------------------------------
+def norm_supported(x, num_channels):
+    return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16) and
+            bool(_lib.lib().rsc_norm_supported(int(num_channels), _dt(x))))
+
+
+class _GroupNorm(torch.autograd.Function):
+    """x (R, P, C) channels-last; groups of Cg channels per row (see include/rscotr.h: GroupNorm and training-mode
+    BatchNorm are the same reduction).  `running` = (running_mean, running_var, momentum) for BatchNorm."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, Cg, eps, relu, running, fg):
+        R, P, C = x.shape
+        g32, b32 = _f32(gamma), _f32(beta)
+        y = torch.empty_like(x)
+        stats = torch.empty(R, C // Cg, 2, dtype=torch.float32, device=x.device)
+        ws = torch.empty(R * C * 2, dtype=torch.float32, device=x.device)
+        rm, rv, mom = running if running is not None else (None, None, 0.0)
+        with torch.cuda.device(x.device):
+            call('rsc_groupnorm_fwd', x.data_ptr(), g32.data_ptr(), b32.data_ptr(), y.data_ptr(), stats.data_ptr(), ws.data_ptr(),
+                 R, P, C, Cg, float(eps), int(relu), _p(rm), _p(rv), float(mom), _dt(x), _stream(),
+                 alg_bytes=3 * x.numel() * x.element_size())
+        ctx.save_for_backward(x, g32, b32, stats)
+        ctx.meta = (Cg, relu, gamma.dtype, beta.dtype, fg[0], fg[1])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g32, b32, stats = ctx.saved_tensors
+        Cg, relu, gdt, bdt, gg, gb = ctx.meta
+        R, P, C = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        direct = gg is not None and gb is not None
+        dg = gg if direct else torch.zeros(C, dtype=torch.float32, device=x.device)
+        db = gb if direct else torch.zeros_like(dg)
+        ws = torch.empty(R * C * 2 + R * (C // Cg) * 2, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            call('rsc_groupnorm_bwd', x.data_ptr(), dy.data_ptr(), g32.data_ptr(), b32.data_ptr(), stats.data_ptr(), dx.data_ptr(),
+                 dg.data_ptr(), db.data_ptr(), ws.data_ptr(), R, P, C, Cg, int(relu), _dt(x), _stream(),
+                 alg_bytes=5 * x.numel() * x.element_size())
+        if direct:
+            return dx, None, None, None, None, None, None, None
+        return dx, dg.to(gdt), db.to(bdt), None, None, None, None, None
+
+
+def _channels_last_rows(x):
+    """(B,C,H,W) -> contiguous (B, H*W, C) (a view when x already has channels-last strides)"""
+    B, C, H, W = x.shape
+    xl = x.permute(0, 2, 3, 1)
+    if not xl.is_contiguous():
+        xl = xl.contiguous()
+    return xl.view(B, H * W, C)
+
+
+def group_norm(x, num_groups, gamma, beta, eps=1e-5, relu=False):
+    """nn.GroupNorm(num_groups) [+ ReLU] on (B,C,H,W) -> (B,C,H,W) with channels-last strides"""
+    _cuda(x, gamma, beta)
+    B, C, H, W = x.shape
+    y = _GroupNorm.apply(_channels_last_rows(x), gamma, beta, C // int(num_groups), eps, bool(relu), None,
+                         (_flat_grad(gamma), _flat_grad(beta)))
+    return y.view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+def batch_norm_train(x, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, relu=False):
+    """nn.BatchNorm2d in training mode (batch statistics, running statistics updated in place) [+ ReLU]"""
+    _cuda(x, gamma, beta)
+    B, C, H, W = x.shape
+    running = None if running_mean is None else (running_mean, running_var, momentum)
+    y = _GroupNorm.apply(_channels_last_rows(x).view(1, B * H * W, C), gamma, beta, 1, eps, bool(relu), running,
+                         (_flat_grad(gamma), _flat_grad(beta)))
+    return y.view(B, H, W, C).permute(0, 3, 1, 2)
+
+
 KernelTimer = _lib.KernelTimer
 
 
