@@ -404,6 +404,16 @@ int rsc_groupnorm_fwd(const void *x, const float *gamma, const float *beta, void
 int rsc_groupnorm_bwd(const void *x, const void *dy, const float *gamma, const float *beta, const float *stats, void *dx,
                       float *dgamma, float *dbeta, float *ws, int R, int P, int C, int Cg, int relu, int dtype, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Device half of a deferred Normalize (mmcv / mmcls / mmdet / mmseg `Normalize` on the loader side,
+ * configs/_base_/{cls,det,seg}/*.py img_norm_cfg): the loader ships uint8 batches (4x fewer H2D bytes),
+ * this kernel produces out[b][c] = (img[b][flip ? C-1-c : c] - mean[c]) * inv_std[c] for pixels inside the
+ * image's valid (h, w) = valid_hw[b] and 0 in the right / bottom padding (the reference pads AFTER normalising).
+ * img (B,C,H,W) uint8, out (B,C,H,W) float / bf16, W % 4 == 0; valid_hw (B,2) int32 or NULL.
+ * ---------------------------------------------------------------------- */
+int rsc_normalize_u8(const void *img, void *out, const float *mean, const float *inv_std, const int *valid_hw, int B, int C, int H,
+                     int W, int flip, int out_dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

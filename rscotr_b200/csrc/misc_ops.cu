@@ -383,6 +383,32 @@ static inline int ew_grid(int64_t n, int per_block) {
 
 using namespace rsc;
 
+// ===========================================================================
+// uint8 image batch -> normalised float batch (device half of a deferred Normalize): channel flip (BGR -> RGB),
+// (x - mean) / std per channel, zero outside each image's valid (h, w) -- the reference pads AFTER normalising
+// ===========================================================================
+template <typename TO>
+__global__ void normalize_u8_kernel(const unsigned char *__restrict__ img, TO *__restrict__ out, const float *__restrict__ mean,
+                                    const float *__restrict__ inv_std, const int *__restrict__ valid_hw, int64_t total4, int C,
+                                    int H, int W, int flip) {
+  const int W4 = W / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x4 = (int)(i % W4);
+    int64_t t = i / W4;
+    const int y = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C), b = (int)(t / C);
+    const int cs = flip ? C - 1 - c : c;
+    const uchar4 v = __ldg(reinterpret_cast<const uchar4 *>(img + (((int64_t)b * C + cs) * H + y) * W) + x4);
+    const float m = mean[c], is = inv_std[c];
+    const int vh = valid_hw ? valid_hw[2 * b] : H, vw = valid_hw ? valid_hw[2 * b + 1] : W;
+    const unsigned char px[4] = {v.x, v.y, v.z, v.w};
+    TO *o = out + i * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = from_f<TO>((y < vh && x4 * 4 + e < vw) ? ((float)px[e] - m) * is : 0.f);
+  }
+}
+
 #define DISPATCH_T(dtype, ...)                    \
   if (dtype == RSC_F32) {                         \
     using T = float;                              \
@@ -568,5 +594,21 @@ extern "C" int rsc_patchify4(const void *x, void *y, int B, int Cin, int H, int 
     patchify4_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y,
                                                                          total, Cin, H, W);
   RSC_CHECK_LAUNCH("rsc_patchify4");
+  return RSC_OK;
+}
+
+extern "C" int rsc_normalize_u8(const void *img, void *out, const float *mean, const float *inv_std, const int *valid_hw, int B, int C,
+                                int H, int W, int flip, int out_dtype, void *stream) {
+  RSC_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && W % 4 == 0, "rsc_normalize_u8: bad shape (B=%d,C=%d,H=%d,W=%d; W %% 4 == 0)", B, C, H, W);
+  RSC_CHECK_ARG(out_dtype == RSC_F32 || out_dtype == RSC_BF16, "rsc_normalize_u8: bad dtype %d", out_dtype);
+  RSC_CHECK_ARG(img && out && mean && inv_std, "rsc_normalize_u8: null pointer");
+  const int64_t total4 = (int64_t)B * C * H * (W / 4);
+  if (out_dtype == RSC_F32)
+    normalize_u8_kernel<float><<<ew_grid(total4, 256), 256, 0, (cudaStream_t)stream>>>((const unsigned char *)img, (float *)out, mean, inv_std,
+                                                                                      valid_hw, total4, C, H, W, flip);
+  else
+    normalize_u8_kernel<__nv_bfloat16><<<ew_grid(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned char *)img, (__nv_bfloat16 *)out, mean, inv_std, valid_hw, total4, C, H, W, flip);
+  RSC_CHECK_LAUNCH("rsc_normalize_u8");
   return RSC_OK;
 }

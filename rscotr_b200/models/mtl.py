@@ -34,12 +34,18 @@ def normalize_on_device(img, img_metas):
     if not torch.is_tensor(img) or img.dtype != torch.uint8:
         return img
     cfg = img_metas[0]['img_norm_cfg']
+    H, W = img.shape[-2:]
+    shapes = [tuple(m.get('img_shape', (H, W))[:2]) for m in img_metas]
+    if img.is_cuda and W % 4 == 0:            # one kernel: flip + normalise + padding re-zeroed (rsc_normalize_u8)
+        from .. import ops
+        valid = const_tensor([list(s) for s in shapes], torch.int32, img.device) if any(s != (H, W) for s in shapes) else None
+        return ops.normalize_u8(img, const_tensor([float(v) for v in cfg['mean']], torch.float32, img.device),
+                                const_tensor([1.0 / float(v) for v in cfg['std']], torch.float32, img.device), valid,
+                                cfg.get('to_rgb', True))
     mean = const_tensor([float(v) for v in cfg['mean']], torch.float32, img.device).view(1, -1, 1, 1)
     inv = const_tensor([1.0 / float(v) for v in cfg['std']], torch.float32, img.device).view(1, -1, 1, 1)
     x = img.flip(1) if cfg.get('to_rgb', True) else img
     x = (x.float() - mean) * inv
-    H, W = img.shape[-2:]
-    shapes = [tuple(m.get('img_shape', (H, W))[:2]) for m in img_metas]
     if any(s != (H, W) for s in shapes):
         hs = const_tensor([s[0] for s in shapes], torch.int64, img.device).view(-1, 1, 1, 1)
         ws = const_tensor([s[1] for s in shapes], torch.int64, img.device).view(-1, 1, 1, 1)

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from .. import ops
 from ..config import MODELS, build_from_cfg
 from .mtl import SingleTaskModel, add_prefix
-from .bricks import Conv2d
+from .bricks import BatchNorm2d, Conv2d
 from .seg_head import resize
 
 

@@ -1469,6 +1469,18 @@ def batch_norm_train(x, gamma, beta, running_mean, running_var, momentum=0.1, ep
     return y.view(B, H, W, C).permute(0, 3, 1, 2)
 
 
+def normalize_u8(img, mean, inv_std, valid_hw=None, to_rgb=True, out_dtype=torch.float32):
+    """uint8 (B,C,H,W) batch -> (img[channels flipped if to_rgb] - mean) * inv_std, zero outside valid_hw (B,2) int32"""
+    _cuda(img, mean, inv_std, valid_hw)
+    img = img.contiguous()
+    B, C, H, W = img.shape
+    out = torch.empty(B, C, H, W, dtype=out_dtype, device=img.device)
+    with torch.cuda.device(img.device):
+        call('rsc_normalize_u8', img.data_ptr(), out.data_ptr(), mean.data_ptr(), inv_std.data_ptr(), _p(valid_hw), B, C, H, W,
+             int(to_rgb), _dt(out), _stream(), alg_bytes=img.numel() + out.numel() * out.element_size())
+    return out
+
+
 KernelTimer = _lib.KernelTimer
 
 

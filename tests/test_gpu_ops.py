@@ -787,3 +787,25 @@ def test_patchify4_matches_unfold_and_conv(dtype, odt):
     ref = conv(x.float()).flatten(2).transpose(1, 2).reshape(-1, 96)
     y = F.linear(want, conv.weight.view(96, 48), conv.bias)
     assert_rel(y, ref, 1e-5, 'conv as gemm')
+
+
+@pytest.mark.parametrize('to_rgb', [True, False])
+def test_normalize_u8_equals_host_normalise_then_pad(to_rgb):
+    """rsc_normalize_u8 (device half of a deferred Normalize) == the libraries' host order: normalise each image at
+    its own size, then pad right / bottom with zeros; bit-for-bit the same fp32 arithmetic ((x - mean) * (1 / std))"""
+    from rscotr_b200.models.mtl import normalize_on_device
+    g = torch.Generator().manual_seed(0)
+    B, H, W = 3, 40, 52
+    img = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8)
+    shapes = [(40, 52), (33, 52), (40, 17)]
+    cfg = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=to_rgb)
+    metas = [dict(img_norm_cfg=cfg, img_shape=(h, w, 3)) for h, w in shapes]
+    want = torch.zeros(B, 3, H, W)
+    mean = torch.tensor(cfg['mean']).view(3, 1, 1)
+    inv = (1.0 / torch.tensor(cfg['std'], dtype=torch.float64)).float().view(3, 1, 1)
+    for b, (h, w) in enumerate(shapes):
+        x = img[b].flip(0) if to_rgb else img[b]
+        want[b, :, :h, :w] = ((x.float() - mean) * inv)[:, :h, :w]
+    got = normalize_on_device(img.cuda(), metas)
+    assert got.dtype == torch.float32 and torch.allclose(got.cpu(), want, rtol=1e-6, atol=1e-6)
+    assert float(got[1, :, 33:].abs().max()) == 0. and float(got[2, :, :, 17:].abs().max()) == 0.
