@@ -239,12 +239,13 @@ int rsc_det_loss_bwd(const void *cls, const float *box, const int *assign, const
  * scale <= 9.5.  fwd: stats[3] += {sum over non-ignored pixels of CE, #pixels whose
  * argmax == label, #non-ignored pixels}; lse (B,H,W) fp32 receives logsumexp per pixel
  * (+inf on ignored pixels) for the backward.  bwd: dlogits = gscale[0] *
- * d(sum CE)/d(logits), gscale a DEVICE float (upstream gradient x loss weight / #pixels).
+ * d(sum CE)/d(logits), gscale a DEVICE float (upstream gradient x loss weight / #pixels);
+ * ws: float scratch of B*h*w*4*C elements (per-cell tap sums, combined without atomics).
  * ---------------------------------------------------------------------- */
 int rsc_upsample_ce_fwd(const void *logits, const int64_t *label, float *lse, float *stats, int B, int C, int h, int w,
                         int H, int W, int ignore_index, int dtype, void *stream);
 int rsc_upsample_ce_bwd(const void *logits, const int64_t *label, const float *lse, const float *gscale, void *dlogits,
-                        int B, int C, int h, int w, int H, int W, int dtype, void *stream);
+                        float *ws, int B, int C, int h, int w, int H, int W, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------
  * Fused residual-stream passes of the Swin block (mmdet 2.25.1

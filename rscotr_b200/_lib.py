@@ -34,7 +34,7 @@ _SIGS = {
     'rsc_det_loss_fwd': [_P] * 9 + [_I] * 9 + [_F] * 6 + [_I, _P],
     'rsc_det_loss_bwd': [_P] * 11 + [_I] * 9 + [_F] * 6 + [_I, _P],
     'rsc_upsample_ce_fwd': [_P] * 4 + [_I] * 8 + [_P],
-    'rsc_upsample_ce_bwd': [_P] * 5 + [_I] * 7 + [_P],
+    'rsc_upsample_ce_bwd': [_P] * 6 + [_I] * 7 + [_P],
     'rsc_add_ln_supported': [_I],
     'rsc_add_ln_fwd': [_P] * 10 + [ctypes.c_int64, ctypes.c_int64, _I, _F, _I, _P],
     'rsc_add_ln_bwd': [_P] * 12 + [ctypes.c_int64, ctypes.c_int64, _I, _I, _P],

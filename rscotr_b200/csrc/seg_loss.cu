@@ -97,52 +97,57 @@ __global__ void __launch_bounds__(TX *TY)
   }
 }
 
-// one warp per low-resolution pixel, lanes over channels; the (<= FP x FP) footprint of output pixels that
-// read this pixel is staged per warp in shared memory (lse, label, per-axis tap geometry)
+// Backward.  Every output pixel interpolates between the SAME four low-resolution logits as its neighbours inside one
+// "cell" (cy, cx) = {output pixels whose upper-left tap is (cy, cx)}; the cells partition the output.  One warp per
+// cell, lanes over channels: softmax - onehot is evaluated ONCE per (output pixel, channel) (a gather per low-resolution
+// pixel visits every output pixel from its four neighbours: 4x the exponentials, and this pass is MUFU-bound), and the
+// four tap-weighted sums of the cell go to a workspace [B][h][w][4][C]; a second pass adds the <= 4 cells around each
+// low-resolution pixel (deterministic, no atomics).
 constexpr int BW = 8;     // warps per block
-constexpr int FP = 24;    // max footprint per axis (2*scale + 5 -> scale up to 9.5)
+constexpr int FP = 24;    // max output pixels per cell and axis (first / last cells hold the clamped border: 1.5 * scale + 1)
+
+__device__ __forceinline__ int tap0(int o, float scale, int in) {
+  int i0, i1;
+  float lam;
+  bil_src(o, scale, in, i0, i1, lam);
+  return i0;
+}
+// output index range [lo, hi] of the cell whose upper tap is k (tap0 is monotone in o)
+__device__ __forceinline__ void cell_range(int k, float scale, int in, int out, int &lo, int &hi) {
+  auto first_ge = [&](int kk) {      // first o with tap0(o) >= kk
+    int o = (int)ceilf((kk + 0.5f) / scale - 0.5f);
+    o = min(max(o, 0), out);
+    while (o > 0 && tap0(o - 1, scale, in) >= kk) --o;
+    while (o < out && tap0(o, scale, in) < kk) ++o;
+    return o;
+  };
+  lo = k == 0 ? 0 : first_ge(k);
+  hi = k == in - 1 ? out - 1 : first_ge(k + 1) - 1;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(BW * 32)
-    upsample_ce_bwd_kernel(const T *__restrict__ logits, const int64_t *__restrict__ label, const float *__restrict__ lse,
-                           const float *__restrict__ gscale, T *__restrict__ dlogits, int B, int C, int h, int w, int H,
-                           int W, float sh, float sw, int64_t npix) {
+    upsample_ce_bwd_cells_kernel(const T *__restrict__ logits, const int64_t *__restrict__ label, const float *__restrict__ lse,
+                                 float *__restrict__ ws, int B, int C, int h, int w, int H, int W, float sh, float sw,
+                                 int64_t ncell) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // per-warp staging: lse[FP*FP], lab[FP*FP], then per-axis {r0 (0/1), r1 (1/2), lam, wgt} for y and x
-  float *s_lse = sm + (size_t)warp * (2 * FP * FP + 8 * FP);
+  float *s_lse = sm + (size_t)warp * (2 * FP * FP + 2 * FP);
   int *s_lab = reinterpret_cast<int *>(s_lse + FP * FP);
-  float *s_y = s_lse + 2 * FP * FP;   // [4][FP]
-  float *s_x = s_y + 4 * FP;          // [4][FP]
-  const float g = gscale[0];
-  const float rh = 1.f / sh, rw = 1.f / sw;
-  for (int64_t sp = (int64_t)blockIdx.x * BW + warp; sp < npix; sp += (int64_t)gridDim.x * BW) {
-    const int sx = (int)(sp % w), sy = (int)((sp / w) % h), b = (int)(sp / ((int64_t)w * h));
-    int oy0 = (int)floorf((sy - 1 + 0.5f) * rh - 0.5f) - 1, oy1 = (int)ceilf((sy + 1 + 0.5f) * rh - 0.5f) + 1;
-    int ox0 = (int)floorf((sx - 1 + 0.5f) * rw - 0.5f) - 1, ox1 = (int)ceilf((sx + 1 + 0.5f) * rw - 0.5f) + 1;
-    if (sy == 0) oy0 = 0;
-    if (sx == 0) ox0 = 0;
-    if (sy == h - 1) oy1 = H - 1;
-    if (sx == w - 1) ox1 = W - 1;
-    oy0 = max(oy0, 0), ox0 = max(ox0, 0), oy1 = min(oy1, H - 1), ox1 = min(ox1, W - 1);
-    // trim the conservative range to the rows / columns that really read (sy, sx)
-    const int ny = oy1 - oy0 + 1, nx = ox1 - ox0 + 1;   // <= FP (checked on the host)
+  float *s_ly = s_lse + 2 * FP * FP, *s_lx = s_ly + FP;
+  for (int64_t cell = (int64_t)blockIdx.x * BW + warp; cell < ncell; cell += (int64_t)gridDim.x * BW) {
+    const int cx = (int)(cell % w), cy = (int)((cell / w) % h), b = (int)(cell / ((int64_t)w * h));
+    int oy0, oy1, ox0, ox1;
+    cell_range(cy, sh, h, H, oy0, oy1);
+    cell_range(cx, sw, w, W, ox0, ox1);
+    const int ny = oy1 - oy0 + 1, nx = ox1 - ox0 + 1;      // <= FP (checked on the host); 0 when the cell is empty
     __syncwarp();
     for (int k = lane; k < ny + nx; k += 32) {
       const bool isy = k < ny;
-      const int o = isy ? oy0 + k : ox0 + (k - ny);
       int i0, i1;
       float lam;
-      bil_src(o, isy ? sh : sw, isy ? h : w, i0, i1, lam);
-      const int s = isy ? sy : sx;
-      float wgt = 0.f;
-      if (i0 == s) wgt += 1.f - lam;
-      if (i1 == s) wgt += lam;
-      float *d = isy ? s_y + k : s_x + (k - ny);
-      d[0] = (float)(i0 - (s - 1));        // 0 or 1 when wgt != 0
-      d[FP] = (float)(i1 - (s - 1));       // 1 or 2
-      d[2 * FP] = lam;
-      d[3 * FP] = wgt;
+      bil_src(isy ? oy0 + k : ox0 + (k - ny), isy ? sh : sw, isy ? h : w, i0, i1, lam);
+      (isy ? s_ly : s_lx - ny)[k] = lam;
     }
     for (int k = lane; k < ny * nx; k += 32) {
       const int yy = k / nx, xx = k - yy * nx;
@@ -152,38 +157,52 @@ __global__ void __launch_bounds__(BW * 32)
       s_lab[yy * FP + xx] = l == INFINITY ? -1 : (int)label[pix];
     }
     __syncwarp();
-    const int ym = max(sy - 1, 0), yp = min(sy + 1, h - 1), xm = max(sx - 1, 0), xp = min(sx + 1, w - 1);
+    const int cy1 = min(cy + 1, h - 1), cx1 = min(cx + 1, w - 1);
+    float *out = ws + cell * 4 * C;
     for (int c = lane; c < C; c += 32) {
       const T *p = logits + ((int64_t)b * C + c) * h * w;
-      float L[3][3];
-      const int ys[3] = {ym, sy, yp}, xs[3] = {xm, sx, xp};
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) L[a][d] = to_f<T>(p[ys[a] * w + xs[d]]);
-      float acc = 0.f;
+      const float L00 = to_f<T>(p[cy * w + cx]), L01 = to_f<T>(p[cy * w + cx1]);
+      const float L10 = to_f<T>(p[cy1 * w + cx]), L11 = to_f<T>(p[cy1 * w + cx1]);
+      float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
       for (int yy = 0; yy < ny; ++yy) {
-        const float wy = s_y[3 * FP + yy];
-        if (wy == 0.f) continue;
-        const bool a0 = s_y[yy] != 0.f, a1 = s_y[FP + yy] == 2.f;
-        const float ly = s_y[2 * FP + yy];
-        float r[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) r[d] = (1.f - ly) * (a0 ? L[1][d] : L[0][d]) + ly * (a1 ? L[2][d] : L[1][d]);
-        float row = 0.f;
+        const float ly = s_ly[yy];
+        const float r0 = L00 + ly * (L10 - L00), r1 = L01 + ly * (L11 - L01);
+        float all = 0.f, right = 0.f;
         for (int xx = 0; xx < nx; ++xx) {
-          const float wx = s_x[3 * FP + xx];
-          if (wx == 0.f) continue;
-          const bool b0 = s_x[xx] != 0.f, b1 = s_x[FP + xx] == 2.f;
-          const float lx = s_x[2 * FP + xx];
-          const float v = (1.f - lx) * (b0 ? r[1] : r[0]) + lx * (b1 ? r[2] : r[1]);
-          const float pr = __expf(v - s_lse[yy * FP + xx]);            // 0 for ignored pixels (lse = +inf)
-          row = fmaf(wx, pr - (s_lab[yy * FP + xx] == c ? 1.f : 0.f), row);
+          const float lx = s_lx[xx];
+          const float v = fmaf(lx, r1 - r0, r0);
+          const float g = __expf(v - s_lse[yy * FP + xx]) - (s_lab[yy * FP + xx] == c ? 1.f : 0.f);   // 0 for ignored pixels
+          all += g;
+          right = fmaf(lx, g, right);
         }
-        acc = fmaf(wy, row, acc);
+        const float left = all - right;
+        a00 = fmaf(1.f - ly, left, a00);
+        a01 = fmaf(1.f - ly, right, a01);
+        a10 = fmaf(ly, left, a10);
+        a11 = fmaf(ly, right, a11);
       }
-      dlogits[((int64_t)b * C + c) * h * w + (int64_t)sy * w + sx] = from_f<T>(acc * g);
+      if (cy1 == cy) a00 += a10, a01 += a11, a10 = a11 = 0.f;      // clamped last row / column: both taps are the same pixel
+      if (cx1 == cx) a00 += a01, a10 += a11, a01 = a11 = 0.f;
+      out[c] = a00, out[C + c] = a01, out[2 * C + c] = a10, out[3 * C + c] = a11;
     }
+  }
+}
+
+// dlogits[b][c][y][x] = g * (cell(y,x).a00 + cell(y,x-1).a01 + cell(y-1,x).a10 + cell(y-1,x-1).a11); thread order (b,y,x,c)
+template <typename T>
+__global__ void upsample_ce_bwd_gather_kernel(const float *__restrict__ ws, const float *__restrict__ gscale, T *__restrict__ dlogits,
+                                              int C, int h, int w, int64_t total) {
+  const float g = gscale[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t pix = i / C;
+    const int x = (int)(pix % w), y = (int)((pix / w) % h);
+    const int64_t b = pix / ((int64_t)w * h);
+    float acc = ws[pix * 4 * C + c];
+    if (x > 0) acc += ws[(pix - 1) * 4 * C + C + c];
+    if (y > 0) acc += ws[(pix - w) * 4 * C + 2 * C + c];
+    if (x > 0 && y > 0) acc += ws[(pix - w - 1) * 4 * C + 3 * C + c];
+    dlogits[((b * C + c) * h + y) * w + x] = from_f<T>(acc * g);
   }
 }
 
@@ -228,25 +247,29 @@ extern "C" int rsc_upsample_ce_fwd(const void *logits, const int64_t *label, flo
 }
 
 extern "C" int rsc_upsample_ce_bwd(const void *logits, const int64_t *label, const float *lse, const float *gscale,
-                                   void *dlogits, int B, int C, int h, int w, int H, int W, int dtype, void *stream) {
+                                   void *dlogits, float *ws, int B, int C, int h, int w, int H, int W, int dtype, void *stream) {
   if (int e = uce_check("rsc_upsample_ce_bwd", B, C, h, w, H, W, dtype)) return e;
-  RSC_CHECK_ARG(logits && label && lse && gscale && dlogits, "rsc_upsample_ce_bwd: null pointer");
+  RSC_CHECK_ARG(logits && label && lse && gscale && dlogits && ws, "rsc_upsample_ce_bwd: null pointer");
   const float sh = (float)h / H, sw = (float)w / W;
-  const int64_t npix = (int64_t)B * h * w;
-  const size_t smem = (size_t)segl::BW * (2 * segl::FP * segl::FP + 8 * segl::FP) * sizeof(float);
-  int64_t blocks = (npix + segl::BW - 1) / segl::BW;
+  const int64_t ncell = (int64_t)B * h * w, total = ncell * C;
+  const size_t smem = (size_t)segl::BW * (2 * segl::FP * segl::FP + 2 * segl::FP) * sizeof(float);
+  int64_t blocks = (ncell + segl::BW - 1) / segl::BW;
   const int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
+  int64_t gb = (total + 255) / 256;
+  const int ggrid = (int)(gb < (int64_t)kNumSMs * 16 ? gb : (int64_t)kNumSMs * 16);
+  cudaStream_t st = (cudaStream_t)stream;
   if (dtype == RSC_F32) {
-    auto k = segl::upsample_ce_bwd_kernel<float>;
+    auto k = segl::upsample_ce_bwd_cells_kernel<float>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, segl::BW * 32, smem, (cudaStream_t)stream>>>((const float *)logits, label, lse, gscale, (float *)dlogits, B,
-                                                            C, h, w, H, W, sh, sw, npix);
+    k<<<grid, segl::BW * 32, smem, st>>>((const float *)logits, label, lse, ws, B, C, h, w, H, W, sh, sw, ncell);
+    segl::upsample_ce_bwd_gather_kernel<float><<<ggrid, 256, 0, st>>>(ws, gscale, (float *)dlogits, C, h, w, total);
   } else {
-    auto k = segl::upsample_ce_bwd_kernel<__nv_bfloat16>;
+    auto k = segl::upsample_ce_bwd_cells_kernel<__nv_bfloat16>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, segl::BW * 32, smem, (cudaStream_t)stream>>>((const __nv_bfloat16 *)logits, label, lse, gscale,
-                                                            (__nv_bfloat16 *)dlogits, B, C, h, w, H, W, sh, sw, npix);
+    k<<<grid, segl::BW * 32, smem, st>>>((const __nv_bfloat16 *)logits, label, lse, ws, B, C, h, w, H, W, sh, sw, ncell);
+    segl::upsample_ce_bwd_gather_kernel<__nv_bfloat16><<<ggrid, 256, 0, st>>>(ws, gscale, (__nv_bfloat16 *)dlogits, C, h, w, total);
   }
   RSC_CHECK_LAUNCH("rsc_upsample_ce_bwd");
+  count_launch(1);
   return RSC_OK;
 }

@@ -710,9 +710,10 @@ class _UpsampleCE(torch.autograd.Function):
         H, W = label.shape[-2:]
         g = dstats[:1].float().contiguous()
         dlogits = torch.empty_like(logits)
+        ws = torch.empty(B * h * w * 4 * C, dtype=torch.float32, device=logits.device)
         with torch.cuda.device(logits.device):
             call('rsc_upsample_ce_bwd', logits.data_ptr(), label.data_ptr(), lse.data_ptr(), g.data_ptr(),
-                 dlogits.data_ptr(), B, C, h, w, H, W, _dt(logits), _stream(),
+                 dlogits.data_ptr(), ws.data_ptr(), B, C, h, w, H, W, _dt(logits), _stream(),
                  alg_bytes=2 * logits.numel() * logits.element_size() + label.numel() * 8 + lse.numel() * 4)
         return dlogits, None, None
 
