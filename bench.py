@@ -431,7 +431,7 @@ def main():
     with ops.KernelTimer() as kt:
         for i in range(NB):
             engine.train_iter(dev_batches[i % NB])
-        ksum = kt.summary()
+        ksum = kt.summary(*peaks()[:2])
     trace('kernel-timer pass done')
     kscale = args.steps / float(NB)                                       # normalise kernel ms to the timed region's steps
     for d in ksum.values():
@@ -521,8 +521,11 @@ def main():
                  traffic=NCU_TRAFFIC.get(name), launches=d['big_launches'], avg_us=1000.0 * d['big_ms'] / d['big_launches'],
                  alg_bytes_per_launch=d['big_bytes'] / d['big_launches'], share_of_step=d['big_ms'] / ms)
         if d['big_flops']:
+            # the GEMMs straddle the ridge point (HBM-bound at the 96 / 192-wide Swin stages, tensor-bound at 384 / 768
+            # and in the encoder FFN): frac_per_launch_bound = sum over launches of the time AT that launch's own
+            # binding limit, max(bytes / HBM peak, flops / tensor peak), over the measured time
             r.update(alg_flops_per_launch=d['big_flops'] / d['big_launches'], hbm_gbs=d['big_bytes'] / t_s / 1e9,
-                     tflops=d['big_flops'] / t_s / 1e12)
+                     tflops=d['big_flops'] / t_s / 1e12, frac_per_launch_bound=d.get('big_roof_ms', 0.0) / d['big_ms'])
         return r
 
     # dominant kernel = most device time over launches that move >= 32 MB (for the many tiny launches of the

@@ -134,12 +134,15 @@ class KernelTimer:
         global _timer
         _timer = None
 
-    def summary(self):
+    def summary(self, peak_gbs=None, peak_tflops=None):
+        """peak_gbs / peak_tflops: when given, `big_roof_ms` sums per launch the slower of (bytes / HBM peak) and
+        (flops / tensor peak) -- the time a launch would take AT its own binding limit."""
         import torch
         torch.cuda.synchronize()
         out = {}
         for name, nbytes, e0, e1, nflops in self.records:
-            d = out.setdefault(name, dict(launches=0, ms=0.0, bytes=0, big_launches=0, big_ms=0.0, big_bytes=0, big_flops=0))
+            d = out.setdefault(name, dict(launches=0, ms=0.0, bytes=0, big_launches=0, big_ms=0.0, big_bytes=0, big_flops=0,
+                                          big_roof_ms=0.0))
             t = e0.elapsed_time(e1)
             d['launches'] += 1
             d['ms'] += t
@@ -149,6 +152,8 @@ class KernelTimer:
                 d['big_ms'] += t
                 d['big_bytes'] += nbytes
                 d['big_flops'] += nflops
+                if peak_gbs:
+                    d['big_roof_ms'] += 1e3 * max(nbytes / (peak_gbs * 1e9), nflops / (peak_tflops * 1e12) if peak_tflops else 0.0)
         for d in out.values():
             d['gbs'] = d['bytes'] / d['ms'] / 1e6 if d['ms'] > 0 else 0.0
             d['big_gbs'] = d['big_bytes'] / d['big_ms'] / 1e6 if d['big_ms'] > 0 else 0.0
