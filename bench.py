@@ -441,6 +441,11 @@ def main():
         d['big_launches'] = int(round(d['big_launches'] * kscale))
 
     # ---- timed region B: end to end through the public API, pinned host inputs, loss read back
+    # (untimed warm-up of THIS path first, one step per distinct host batch: the first prefetch of a (task, shapes)
+    # signature allocates its device staging buffers -- a one-off 70 ms that tools/e2e_probe.py found inside the timed region)
+    for i in range(NB):
+        engine.prefetch(host_batches[i])
+        engine.train_iter(host_batches[i])
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()

@@ -273,6 +273,7 @@ class _AddLN(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, identity, x, bias, scale, gamma, beta, eps, fg):
+        ctx.set_materialize_grads(False)      # an unused output (post-norm layers drop r) costs no zero fill / read
         _cuda(identity, x, gamma, beta)
         C = x.shape[-1]
         idc, xc = identity.contiguous(), x.contiguous()
@@ -955,6 +956,7 @@ class _LinearAddLN(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, identity, scale, gamma, beta, w, eps, grads):
+        ctx.set_materialize_grads(False)      # an unused output (post-norm layers drop r) costs no zero fill / read
         x2 = x.reshape(-1, x.shape[-1])
         idc = identity.contiguous()
         N = w.shape[0]
@@ -1015,6 +1017,7 @@ class _MLPAddLN(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight1, bias1, weight2, bias2, identity, scale, gamma, beta, w1, w2, act, eps, grads):
+        ctx.set_materialize_grads(False)      # an unused output (post-norm layers drop r) costs no zero fill / read
         x2 = x.reshape(-1, x.shape[-1])
         idc = identity.contiguous()
         rows, C = x2.shape[0], w2.shape[0]
