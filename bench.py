@@ -446,6 +446,7 @@ def main():
     for i in range(NB):
         engine.prefetch(host_batches[i])
         engine.train_iter(host_batches[i])
+    loss_host = torch.empty(args.steps, dtype=torch.float32).pin_memory()       # (page-locking allocates + synchronises: not in the timed region)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
@@ -453,7 +454,6 @@ def main():
     # The loss of every step is read back into pinned host memory (4 bytes, async D2H + event) and consumed ONE step
     # later, after the next step has been enqueued -- the logging lag of any real training loop -- so the host never
     # leaves the GPU idle between steps; the next batch's H2D copy runs on the copy stream meanwhile.
-    loss_host = torch.empty(args.steps, dtype=torch.float32).pin_memory()
     read_ev = [None] * args.steps
     losses_read = []
 

@@ -26,6 +26,11 @@ def _build(cfg):
     return build_from_cfg(dict(cfg), MODELS)
 
 
+# set to a list by the step engine (data-parallel CUDA runs): pending asynchronous log-value reductions of the current
+# iteration, joined by StepEngine._backward_and_step
+ASYNC_LOG_WORKS = None
+
+
 def normalize_on_device(img, img_metas):
     """Device half of a deferred `Normalize` (mtl/data/transforms.py, defer=True): the loader ships the batch
     as uint8 BGR (4x fewer H2D bytes than fp32); here (x[RGB] - mean) / std is applied on the device and the
@@ -291,6 +296,12 @@ class MTL(nn.Module):
         if dist.is_available() and dist.is_initialized():
             world = dist.get_world_size()
             n = torch.cat([const_tensor([float(len(keys))], torch.float32, packed.device), packed])
+            if ASYNC_LOG_WORKS is not None and n.is_cuda:
+                # nothing in the step reads the logged values: average on NCCL's stream (ncclAvg) and let the step engine
+                # join at the end of the iteration -- no mid-step rendezvous of the ranks for a logging collective
+                n._rsc_work = dist.all_reduce(n, op=dist.ReduceOp.AVG, async_op=True)
+                ASYNC_LOG_WORKS.append(n)
+                return n
             dist.all_reduce(n)
             return n / world
         return packed
@@ -330,6 +341,10 @@ class _LazyLogVars(OrderedDict):
 
     def _materialise(self):
         if not self._done:
+            w = getattr(self._packed, '_rsc_work', None)      # an asynchronous reduction nobody has joined (a step outside the
+            if w is not None:                                   # engine, e.g. validation): join before reading
+                w.wait()
+                self._packed._rsc_work = None
             vals = self._packed.tolist()
             if len(vals) == len(self._keys) + 1:      # distributed: element 0 = mean number of log vars
                 assert int(round(vals[0])) == len(self._keys), \

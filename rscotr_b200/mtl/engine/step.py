@@ -62,6 +62,14 @@ def h2d_bytes(obj):
     return 0
 
 
+_SKIP_EXCHANGE = os.environ.get('RSC_SKIP_EXCHANGE', '0') == '1'
+
+
+class _NoWork:
+    def wait(self):
+        pass
+
+
 class _DivAfter:
     """async SUM all-reduce whose wait() finishes the mean (back ends without an averaging reduction)."""
     def __init__(self, work, seg, world):
@@ -166,6 +174,9 @@ class StepEngine:
         bb = getattr(self.model, 'backbone', None)
         if self.world > 1 and bb is not None and os.environ.get('RSC_OVERLAP_EXCHANGE', '1') != '0':
             bb._grad_ready_cb = self._on_grad_ready
+        if self.world > 1 and self.device.type == 'cuda' and os.environ.get('RSC_ASYNC_LOG_REDUCE', '1') != '0':
+            from ...models import mtl as _mtl
+            _mtl.ASYNC_LOG_WORKS = []
         if self.world > 1:
             # what the reference's DDP wrapper does at construction (mtl/apis/train.py:37-46): rank 0's weights
             # (and buffers) win, so per-rank init differences (--diff-seed, nondeterministic init) cannot leave the
@@ -284,6 +295,8 @@ class StepEngine:
         """mean over ranks of flat_grad[lo:hi], in place.  NCCL averages inside the collective (ncclAvg: no separate
         1/world pass over the gradients); gloo (CPU tests) sums and divides."""
         seg = self.flat_grad[lo:hi]
+        if _SKIP_EXCHANGE:            # (diagnostic only: measures what a multi-GPU step costs WITHOUT its gradient exchange)
+            return _NoWork()
         if self.device.type == 'cuda':
             return dist.all_reduce(seg, op=dist.ReduceOp.AVG, async_op=async_op)
         work = dist.all_reduce(seg, async_op=async_op)
@@ -317,6 +330,7 @@ class StepEngine:
             self._collect_grads()
             for lo, hi in self._active_ranges(task):
                 self._all_reduce_mean(lo, hi, False)
+            self._join_log_works()
             return
         self._collect_grads(0, st['frontier'])
         for lo, hi in st['ranges']:
@@ -325,6 +339,15 @@ class StepEngine:
         self.last_buckets = len(st['works'])
         for w in st['works']:
             w.wait()
+        self._join_log_works()
+
+    def _join_log_works(self):
+        from ...models import mtl as _mtl
+        if _mtl.ASYNC_LOG_WORKS:
+            for t in _mtl.ASYNC_LOG_WORKS:
+                t._rsc_work.wait()
+                t._rsc_work = None
+            del _mtl.ASYNC_LOG_WORKS[:]
 
     # -- one co-training iteration ------------------------------------------
     def _backward_and_step(self, outputs, task):
