@@ -435,7 +435,7 @@ def main():
     trace('kernel-timer pass done')
     kscale = args.steps / float(NB)                                       # normalise kernel ms to the timed region's steps
     for d in ksum.values():
-        for k in ('ms', 'bytes', 'big_ms', 'big_bytes', 'big_flops'):
+        for k in ('ms', 'bytes', 'big_ms', 'big_bytes', 'big_flops', 'big_roof_ms'):
             d[k] *= kscale
         d['launches'] = int(round(d['launches'] * kscale))
         d['big_launches'] = int(round(d['big_launches'] * kscale))
@@ -443,19 +443,23 @@ def main():
     # ---- timed region B: end to end through the public API, pinned host inputs, loss read back
     # (untimed warm-up of THIS path first, one step per distinct host batch: the first prefetch of a (task, shapes)
     # signature allocates its device staging buffers -- a one-off 70 ms that tools/e2e_probe.py found inside the timed region)
-    for i in range(NB):
-        engine.prefetch(host_batches[i])
-        engine.train_iter(host_batches[i])
+    # (... and the per-kernel pass above ran eagerly, i.e. host-bound with a mostly idle GPU: three cycles bring the
+    # device back to the steady state the first timed region started from)
+    for i in range(3 * NB):
+        engine.prefetch(host_batches[i % NB])
+        engine.train_iter(host_batches[i % NB])
     loss_host = torch.empty(args.steps, dtype=torch.float32).pin_memory()       # (page-locking allocates + synchronises: not in the timed region)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     hb = db = 0
-    # The loss of every step is read back into pinned host memory (4 bytes, async D2H + event) and consumed ONE step
+    # The loss of every step is read back into pinned host memory (4 bytes, async D2H + event) and consumed LAG steps
     # later, after the next step has been enqueued -- the logging lag of any real training loop -- so the host never
     # leaves the GPU idle between steps; the next batch's H2D copy runs on the copy stream meanwhile.
     read_ev = [None] * args.steps
     losses_read = []
+    LAG = 2      # steps between enqueueing a step and reading its loss: with 1 the host is at most one step ahead of the GPU and
+                 # every host-side hiccup (the nvidia-smi clock sampler takes driver locks every 100 ms) idles the device
 
     def consume(k):
         read_ev[k].synchronize()
@@ -472,9 +476,10 @@ def main():
         db += 4
         if i + 1 < args.steps:
             engine.prefetch(host_batches[(i + 1) % NB])                    # next step's H2D overlaps this step's compute
-        if i > 0:
-            consume(i - 1)
-    consume(args.steps - 1)
+        if i >= LAG:
+            consume(i - LAG)
+    for k in range(max(args.steps - LAG, 0), args.steps):
+        consume(k)
     assert len(losses_read) == args.steps and all(v == v for v in losses_read), 'e2e: missing / NaN loss read-back'
     f1.record()
     barrier()
@@ -563,7 +568,7 @@ def main():
                e2e=dict(value=e2e, unit='iters/s', h2d_bytes_per_step=hb // args.steps, d2h_bytes_per_step=db // args.steps,
                         ms_per_step=ms_e2e / args.steps,
                         pipeline='pinned host inputs, H2D of step i+1 on a copy stream during step i; loss of step i '
-                                 'copied to pinned host memory and read after step i+1 is enqueued'),
+                                 'copied to pinned host memory and read after step i+2 is enqueued'),
                gpu_launches=launches, cuda_graphs=bool(engine.use_graphs), cuda_graph_capture_failures=engine.graph_failures,
                ms_per_task={k: sum(v) / len(v) for k, v in per_task.items()},
                roofline=roofline, roofline_also=roofline_also, sustained=sustained,

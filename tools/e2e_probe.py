@@ -49,12 +49,19 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / steps
 
-    for rep in range(2):
+    for rep in range(3):
+        sampler = None
+        if rep == 2:      # third pass: with bench.py's nvidia-smi clock sampler running
+            sampler = bench.ClockSampler(0)
+            sampler.start()
+            print('-- with the nvidia-smi sampler (-lms 100)')
         print('A device            %.3f ms/step' % run(dev, False, False))
         print('B host+pref+read    %.3f' % run(host, True, True))
         print('C host+pref         %.3f' % run(host, True, False))
         print('D host+read         %.3f' % run(host, False, True))
         print('E device+read       %.3f' % run(dev, False, True), flush=True)
+        if sampler is not None:
+            print(sampler.stop())
 
 
 if __name__ == '__main__':
