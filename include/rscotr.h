@@ -178,6 +178,11 @@ int rsc_gap_bwd(const void *dy, void *dx, int B, int C, int HW, int channels_las
  * ---------------------------------------------------------------------- */
 int rsc_bilinear_fwd(const void *x, void *y, int N, int Hi, int Wi, int Ho, int Wo, int dtype, void *stream);
 int rsc_bilinear_bwd(const void *dy, void *dx, int N, int Hi, int Wi, int Ho, int Wo, int dtype, void *stream);
+/* channels-last variants: x (B,Hi,Wi,C) -> y (B,Ho,Wo,C), C a multiple of the 16-byte channel vector (8 bf16 / 4 float);
+ * same arithmetic; the maps that the convolution / norm kernels produce need no NCHW transpose around the resize
+ * (mmseg `resize` in seg_head/pixel_decoder.py:55-64 and UPerHead's top-down path / fpn_outs resizes). */
+int rsc_bilinear_cl_fwd(const void *x, void *y, int B, int C, int Hi, int Wi, int Ho, int Wo, int dtype, void *stream);
+int rsc_bilinear_cl_bwd(const void *dy, void *dx, int B, int C, int Hi, int Wi, int Ho, int Wo, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------
  * Sigmoid focal loss.  Drop-in for mmcv ext_module.sigmoid_focal_loss_forward

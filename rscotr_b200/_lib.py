@@ -69,6 +69,8 @@ _SIGS = {
     'rsc_groupnorm_fwd': [_P] * 6 + [_I] * 4 + [_F, _I, _P, _P, _F, _I, _P],
     'rsc_groupnorm_bwd': [_P] * 9 + [_I] * 6 + [_P],
     'rsc_normalize_u8': [_P] * 5 + [_I] * 6 + [_P],
+    'rsc_bilinear_cl_fwd': [_P, _P] + [_I] * 7 + [_P],
+    'rsc_bilinear_cl_bwd': [_P, _P] + [_I] * 7 + [_P],
 }
 
 

@@ -326,6 +326,110 @@ __global__ void bilinear_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx
   }
 }
 
+// channels-last variants: x (B,Hi,Wi,C) -> y (B,Ho,Wo,C); a thread moves one 16-byte channel vector (VEC elements), a
+// warp covers consecutive channels of one pixel -> coalesced both ways, and the maps the convolutions / norms produce
+// (channels-last) need no transpose in front of the resize
+template <typename T, int VEC>
+__device__ __forceinline__ void ldvec(const T *p, float (&v)[VEC]);
+template <>
+__device__ __forceinline__ void ldvec<float, 4>(const float *p, float (&v)[4]) {
+  const float4 r = __ldg(reinterpret_cast<const float4 *>(p));
+  v[0] = r.x, v[1] = r.y, v[2] = r.z, v[3] = r.w;
+}
+template <>
+__device__ __forceinline__ void ldvec<__nv_bfloat16, 8>(const __nv_bfloat16 *p, float (&v)[8]) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[i]));
+    v[2 * i] = f.x, v[2 * i + 1] = f.y;
+  }
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void stvec(T *p, const float (&v)[VEC]);
+template <>
+__device__ __forceinline__ void stvec<float, 4>(float *p, const float (&v)[4]) {
+  *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void stvec<__nv_bfloat16, 8>(__nv_bfloat16 *p, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t *>(&h);
+  }
+  *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <typename T, int VEC>
+__global__ void bilinear_cl_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, int64_t total, int C, int Hi, int Wi, int Ho,
+                                       int Wo, float sh, float sw) {
+  const int CV = C / VEC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    int64_t t = i / CV;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int64_t b = t / Ho;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bil_src(oy, sh, Hi, y0, y1, ly);
+    bil_src(ox, sw, Wi, x0, x1, lx);
+    const T *p = x + b * Hi * Wi * C + cv * VEC;
+    float v00[VEC], v01[VEC], v10[VEC], v11[VEC], o[VEC];
+    ldvec<T, VEC>(p + ((int64_t)y0 * Wi + x0) * C, v00);
+    ldvec<T, VEC>(p + ((int64_t)y0 * Wi + x1) * C, v01);
+    ldvec<T, VEC>(p + ((int64_t)y1 * Wi + x0) * C, v10);
+    ldvec<T, VEC>(p + ((int64_t)y1 * Wi + x1) * C, v11);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+      o[e] = (1.f - ly) * ((1.f - lx) * v00[e] + lx * v01[e]) + ly * ((1.f - lx) * v10[e] + lx * v11[e]);
+    stvec<T, VEC>(y + i * VEC, o);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void bilinear_cl_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int64_t total, int C, int Hi, int Wi, int Ho,
+                                       int Wo, float sh, float sw) {
+  const int CV = C / VEC;
+  const float rh = 1.f / sh, rw = 1.f / sw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    int64_t t = i / CV;
+    const int ix = (int)(t % Wi);
+    t /= Wi;
+    const int iy = (int)(t % Hi);
+    const int64_t b = t / Hi;
+    int oy0 = (int)floorf((iy - 1 + 0.5f) * rh - 0.5f) - 1, oy1 = (int)ceilf((iy + 1 + 0.5f) * rh - 0.5f) + 1;
+    int ox0 = (int)floorf((ix - 1 + 0.5f) * rw - 0.5f) - 1, ox1 = (int)ceilf((ix + 1 + 0.5f) * rw - 0.5f) + 1;
+    if (iy == 0) oy0 = 0;
+    if (ix == 0) ox0 = 0;
+    if (iy == Hi - 1) oy1 = Ho - 1;
+    if (ix == Wi - 1) ox1 = Wo - 1;
+    oy0 = max(oy0, 0), ox0 = max(ox0, 0), oy1 = min(oy1, Ho - 1), ox1 = min(ox1, Wo - 1);
+    const T *p = dy + b * Ho * Wo * C + cv * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      const float wy = bil_w(oy, iy, sh, Hi);
+      if (wy == 0.f) continue;
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        const float wgt = wy * bil_w(ox, ix, sw, Wi);
+        if (wgt == 0.f) continue;
+        float v[VEC];
+        ldvec<T, VEC>(p + ((int64_t)oy * Wo + ox) * C, v);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = fmaf(wgt, v[e], acc[e]);
+      }
+    }
+    stvec<T, VEC>(dx + i * VEC, acc);
+  }
+}
+
 // ===========================================================================
 // Sigmoid focal loss (element-wise, mmcv semantics)
 // ===========================================================================
@@ -610,5 +714,47 @@ extern "C" int rsc_normalize_u8(const void *img, void *out, const float *mean, c
     normalize_u8_kernel<__nv_bfloat16><<<ew_grid(total4, 256), 256, 0, (cudaStream_t)stream>>>(
         (const unsigned char *)img, (__nv_bfloat16 *)out, mean, inv_std, valid_hw, total4, C, H, W, flip);
   RSC_CHECK_LAUNCH("rsc_normalize_u8");
+  return RSC_OK;
+}
+
+static int bil_cl_check(const char *fn, int B, int C, int Hi, int Wi, int Ho, int Wo, int dtype) {
+  RSC_CHECK_ARG(B > 0 && C > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "%s: empty tensor (B=%d, C=%d, %dx%d -> %dx%d)", fn, B, C,
+                Hi, Wi, Ho, Wo);
+  RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "%s: bad dtype %d", fn, dtype);
+  RSC_CHECK_ARG(C % (dtype == RSC_F32 ? 4 : 8) == 0, "%s: C=%d must be a multiple of the 16-byte channel vector", fn, C);
+  return RSC_OK;
+}
+
+extern "C" int rsc_bilinear_cl_fwd(const void *x, void *y, int B, int C, int Hi, int Wi, int Ho, int Wo, int dtype, void *stream) {
+  if (int e = bil_cl_check("rsc_bilinear_cl_fwd", B, C, Hi, Wi, Ho, Wo, dtype)) return e;
+  RSC_CHECK_ARG(x && y, "rsc_bilinear_cl_fwd: null pointer");
+  const float sh = (float)Hi / Ho, sw = (float)Wi / Wo;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RSC_F32) {
+    const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+    bilinear_cl_fwd_kernel<float, 4><<<ew_grid(total, 256), 256, 0, st>>>((const float *)x, (float *)y, total, C, Hi, Wi, Ho, Wo, sh, sw);
+  } else {
+    const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
+    bilinear_cl_fwd_kernel<__nv_bfloat16, 8>
+        <<<ew_grid(total, 256), 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, total, C, Hi, Wi, Ho, Wo, sh, sw);
+  }
+  RSC_CHECK_LAUNCH("rsc_bilinear_cl_fwd");
+  return RSC_OK;
+}
+
+extern "C" int rsc_bilinear_cl_bwd(const void *dy, void *dx, int B, int C, int Hi, int Wi, int Ho, int Wo, int dtype, void *stream) {
+  if (int e = bil_cl_check("rsc_bilinear_cl_bwd", B, C, Hi, Wi, Ho, Wo, dtype)) return e;
+  RSC_CHECK_ARG(dy && dx, "rsc_bilinear_cl_bwd: null pointer");
+  const float sh = (float)Hi / Ho, sw = (float)Wi / Wo;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RSC_F32) {
+    const int64_t total = (int64_t)B * Hi * Wi * (C / 4);
+    bilinear_cl_bwd_kernel<float, 4><<<ew_grid(total, 256), 256, 0, st>>>((const float *)dy, (float *)dx, total, C, Hi, Wi, Ho, Wo, sh, sw);
+  } else {
+    const int64_t total = (int64_t)B * Hi * Wi * (C / 8);
+    bilinear_cl_bwd_kernel<__nv_bfloat16, 8>
+        <<<ew_grid(total, 256), 256, 0, st>>>((const __nv_bfloat16 *)dy, (__nv_bfloat16 *)dx, total, C, Hi, Wi, Ho, Wo, sh, sw);
+  }
+  RSC_CHECK_LAUNCH("rsc_bilinear_cl_bwd");
   return RSC_OK;
 }

@@ -542,24 +542,43 @@ def global_avg_pool(x, channels_last=False):
 # bilinear resize, align_corners=False            
 # ---------------------------------------------------------------------------
 class _Bilinear(torch.autograd.Function):
+    """NCHW-contiguous planes -> rsc_bilinear_*; maps with channels-last strides (what the convolution / norm kernels
+    produce) -> rsc_bilinear_cl_*, output channels-last as well: no transpose copy on either side of the resize."""
+
     @staticmethod
     def forward(ctx, x, Ho, Wo):
         _cuda(x)
-        x = x.contiguous()
         B, C, Hi, Wi = x.shape
-        y = torch.empty(B, C, Ho, Wo, dtype=x.dtype, device=x.device)
+        vec = 16 // x.element_size()
+        cl = C % vec == 0 and C >= vec and not x.is_contiguous() and x.permute(0, 2, 3, 1).is_contiguous()
         with torch.cuda.device(x.device):
-            call('rsc_bilinear_fwd', x.data_ptr(), y.data_ptr(), B * C, Hi, Wi, Ho, Wo, _dt(x), _stream(),
-                 alg_bytes=(x.numel() + y.numel()) * x.element_size())
-        ctx.meta = (B, C, Hi, Wi, Ho, Wo)
+            if cl:
+                y = torch.empty(B, Ho, Wo, C, dtype=x.dtype, device=x.device)
+                call('rsc_bilinear_cl_fwd', x.data_ptr(), y.data_ptr(), B, C, Hi, Wi, Ho, Wo, _dt(x), _stream(),
+                     alg_bytes=(x.numel() + y.numel()) * x.element_size())
+                y = y.permute(0, 3, 1, 2)
+            else:
+                x = x.contiguous()
+                y = torch.empty(B, C, Ho, Wo, dtype=x.dtype, device=x.device)
+                call('rsc_bilinear_fwd', x.data_ptr(), y.data_ptr(), B * C, Hi, Wi, Ho, Wo, _dt(x), _stream(),
+                     alg_bytes=(x.numel() + y.numel()) * x.element_size())
+        ctx.meta = (B, C, Hi, Wi, Ho, Wo, cl)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        B, C, Hi, Wi, Ho, Wo = ctx.meta
-        dy = dy.contiguous()
-        dx = torch.empty(B, C, Hi, Wi, dtype=dy.dtype, device=dy.device)
+        B, C, Hi, Wi, Ho, Wo, cl = ctx.meta
         with torch.cuda.device(dy.device):
+            if cl:
+                dyl = dy.permute(0, 2, 3, 1)
+                if not dyl.is_contiguous():
+                    dyl = dyl.contiguous()
+                dx = torch.empty(B, Hi, Wi, C, dtype=dy.dtype, device=dy.device)
+                call('rsc_bilinear_cl_bwd', dyl.data_ptr(), dx.data_ptr(), B, C, Hi, Wi, Ho, Wo, _dt(dy), _stream(),
+                     alg_bytes=(dx.numel() + dy.numel()) * dy.element_size())
+                return dx.permute(0, 3, 1, 2), None, None
+            dy = dy.contiguous()
+            dx = torch.empty(B, C, Hi, Wi, dtype=dy.dtype, device=dy.device)
             call('rsc_bilinear_bwd', dy.data_ptr(), dx.data_ptr(), B * C, Hi, Wi, Ho, Wo, _dt(dy), _stream(),
                  alg_bytes=(dx.numel() + dy.numel()) * dy.element_size())
         return dx, None, None

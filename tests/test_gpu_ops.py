@@ -809,3 +809,28 @@ def test_normalize_u8_equals_host_normalise_then_pad(to_rgb):
     got = normalize_on_device(img.cuda(), metas)
     assert got.dtype == torch.float32 and torch.allclose(got.cpu(), want, rtol=1e-6, atol=1e-6)
     assert float(got[1, :, 33:].abs().max()) == 0. and float(got[2, :, :, 17:].abs().max()) == 0.
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape', [(2, 256, 25, 25, 50, 50), (1, 512, 16, 16, 128, 128), (2, 64, 13, 7, 20, 33), (1, 8, 6, 6, 6, 6),
+                                   (2, 256, 50, 50, 100, 100)])
+def test_bilinear_channels_last_matches_interpolate(shape, dtype):
+    """rsc_bilinear_cl_{fwd,bwd}: the resize on channels-last maps (no transpose copies) == F.interpolate(bilinear,
+    align_corners=False) forward and backward; the result keeps channels-last strides"""
+    ops = _ops()
+    B, C, Hi, Wi, Ho, Wo = shape
+    g = torch.Generator().manual_seed(Hi * Wo + C)
+    x = torch.randn(B, C, Hi, Wi, generator=g).to(dtype)
+    dy = torch.randn(B, C, Ho, Wo, generator=g).to(dtype)
+    xr = x.float().clone().requires_grad_(True)
+    want = F.interpolate(xr, size=(Ho, Wo), mode='bilinear', align_corners=False)
+    want.backward(dy.float())
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    got = ops.bilinear_resize(xc, (Ho, Wo))
+    assert got.shape == want.shape
+    if (Hi, Wi) != (1, 1) and C > 1:
+        assert got.permute(0, 2, 3, 1).is_contiguous()
+    got.backward(dy.cuda().contiguous(memory_format=torch.channels_last))
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    assert_rel(got, want, tol, 'y')
+    assert_rel(xc.grad, xr.grad, tol, 'dx')

@@ -62,6 +62,19 @@ def main():
         print('E device+read       %.3f' % run(dev, False, True), flush=True)
         if sampler is not None:
             print(sampler.stop())
+    # what bench.py does between its two timed regions: a sustained leg, then an eager per-kernel pass
+    for i in range(240):
+        engine.train_iter(dev[i % NB])
+    from rscotr_b200 import ops
+    with ops.KernelTimer() as kt:
+        for i in range(NB):
+            engine.train_iter(dev[i % NB])
+        kt.summary()
+    print('-- after a sustained leg + an eager KernelTimer pass')
+    print('B host+pref+read    %.3f' % run(host, True, True))
+    print('A device            %.3f' % run(dev, False, False))
+    print('B host+pref+read    %.3f' % run(host, True, True))
+    print('A device            %.3f' % run(dev, False, False), flush=True)
 
 
 if __name__ == '__main__':
