@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'rscotr_b200', 'librscotr_b200.so')
 KEYS = ['UTCHMMA', 'UTCQMMA', 'LDTM', 'STTM', 'UTCBAR', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'LDGSTS', 'SYNCS', 'FFMA2', 'FADD2', 'FMUL2',
-        'MUFU', 'HMMA', 'RED', 'ATOMS', 'ATOMG', 'STL', 'LDL']
+        'MUFU', 'HMMA', 'RED', 'REDG', 'ATOMS', 'ATOMG', 'STL', 'LDL']
 
 
 def main():
