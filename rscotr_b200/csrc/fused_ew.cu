@@ -9,12 +9,21 @@
 //   rsc_bias_gelu_{fwd,bwd} y = gelu(h + bias) (erf form) ; backward also yields d(bias) = column sums of dh,
 //       i.e. the bias gradient of the first FFN Linear without another pass over the 4C-wide tensor.
 #include <cstdlib>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rsc {
 namespace few {
 
 constexpr int LN_THREADS = 128;
+
+// CTAs per SM of the grid cap (tuning knob, read once from the environment)
+static int grid_mult(const char *env, int dflt) {
+  const char *v = getenv(env);
+  const int m = v ? atoi(v) : 0;
+  return m > 0 ? m : dflt;
+}
 
 template <typename T>
 __device__ __forceinline__ void load8(const T *p, float (&v)[8]);
@@ -425,7 +434,10 @@ extern "C" int rsc_add_ln_fwd(const void *identity, const void *x, const float *
   RSC_CHECK_ARG(identity && x && gamma && beta && r_out && n_out && mean && rstd, "rsc_add_ln_fwd: null pointer");
   const int rpb = (few::LN_THREADS / 32) * (32 / l);
   int64_t fb = (rows + rpb - 1) / rpb;
-  const int grid = (int)(fb < kNumSMs * 12 ? fb : kNumSMs * 12);
+  // 95 registers -> 5 resident CTAs / SM: for long tensors exactly one resident wave (measured +10 % at the stage-0 / stage-1
+  // cls shapes, tools/lnbench.py); short ones finish sooner with more, smaller CTAs
+  const int cap = kNumSMs * few::grid_mult("RSC_ADDLN_FWD_MULT", rows >= (1 << 17) ? 5 : 12);
+  const int grid = (int)(fb < cap ? fb : cap);
   cudaStream_t st = (cudaStream_t)stream;
 #define ALF(T, V, E, LL)                                                                                                \
   if (vw == V && ev == E && l == LL) {                                                                                  \
@@ -457,7 +469,8 @@ extern "C" int rsc_add_ln_bwd(const void *r, const float *gamma, const float *me
   int rpb = (few::LN_THREADS / 32) * (32 / l);
   if (rpb < 32) rpb = 32;
   int64_t fb = (rows + rpb - 1) / rpb;
-  const int grid = (int)(fb < kNumSMs * 8 ? fb : kNumSMs * 8);
+  const int cap = kNumSMs * few::grid_mult("RSC_ADDLN_BWD_MULT", 8);
+  const int grid = (int)(fb < cap ? fb : cap);
   cudaStream_t st = (cudaStream_t)stream;
 #define ALB(T, V, E, LL)                                                                                               \
   if (vw == V && ev == E && l == LL) {                                                                                 \
