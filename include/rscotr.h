@@ -420,6 +420,16 @@ int rsc_groupnorm_bwd(const void *x, const void *dy, const float *gamma, const f
 int rsc_normalize_u8(const void *img, void *out, const float *mean, const float *inv_std, const int *valid_hw, int B, int C, int H,
                      int W, int flip, int out_dtype, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Gradient all-reduce (mean) inside the NVSwitch: replaces the ncclAllReduce behind the reference's DDP wrapper
+ * (mtl/apis/train.py:37-46) when the flat gradient buffer lives in symmetric memory with an NVLS multicast
+ * mapping.  mc = multicast address of element 0; [lo, hi) float elements, multiples of 4.  Rank `rank` of `world`
+ * reduces its 1/world share: multimem.ld_reduce.add (sum over all GPUs, computed by the switch) -> x scale ->
+ * multimem.st (to every GPU).  The caller brackets the call with cross-GPU barriers (all ranks have written the range /
+ * all shares are stored).  ctas: CTAs of 512 threads (0 = 64).
+ * ---------------------------------------------------------------------- */
+int rsc_nvls_allreduce_mean(void *mc, int64_t lo, int64_t hi, int rank, int world, float scale, int ctas, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

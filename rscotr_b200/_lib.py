@@ -71,6 +71,7 @@ _SIGS = {
     'rsc_normalize_u8': [_P] * 5 + [_I] * 6 + [_P],
     'rsc_bilinear_cl_fwd': [_P, _P] + [_I] * 7 + [_P],
     'rsc_bilinear_cl_bwd': [_P, _P] + [_I] * 7 + [_P],
+    'rsc_nvls_allreduce_mean': [_P, ctypes.c_int64, ctypes.c_int64, _I, _I, _F, _I, _P],
 }
 
 

@@ -70,6 +70,15 @@ class _NoWork:
         pass
 
 
+class _StreamWork:
+    """work handle of an exchange that runs on the engine's own communication stream"""
+    def __init__(self, stream, device):
+        self.stream, self.device = stream, device
+
+    def wait(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+
 class _DivAfter:
     """async SUM all-reduce whose wait() finishes the mean (back ends without an averaging reduction)."""
     def __init__(self, work, seg, world):
@@ -141,6 +150,24 @@ class StepEngine:
         total = off
         self.flat_param = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        # In-switch gradient exchange (csrc/nvls.cu): the gradient buffer lives in symmetric memory with an NVLS
+        # multicast mapping, every rank reduces 1/world of a range with multimem.ld_reduce / multimem.st.
+        # RSC_NVLS=1 opts in; without multicast support (or on any set-up error, on every rank alike) NCCL is used.
+        self._nvls = None
+        if self.world > 1 and self.device.type == 'cuda' and os.environ.get('RSC_NVLS', '0') == '1':
+            try:
+                import torch.distributed._symmetric_memory as symm
+                fg = symm.empty(total, dtype=torch.float32, device=self.device)
+                hdl = symm.rendezvous(fg, dist.group.WORLD)
+                if not hdl.multicast_ptr:
+                    raise RuntimeError('no NVLS multicast mapping')
+                fg.zero_()
+                self.flat_grad = fg
+                self._nvls = dict(hdl=hdl, mc=int(hdl.multicast_ptr), stream=torch.cuda.Stream(self.device),
+                                  ctas=int(os.environ.get('RSC_NVLS_CTAS', 16)), rank=dist.get_rank())
+            except Exception as e:      # noqa: BLE001  (symmetric memory is an experimental torch API)
+                import warnings
+                warnings.warn('in-switch gradient exchange unavailable (%s: %s); using NCCL' % (type(e).__name__, e))
         # bf16 shadow of the master weights, refreshed by the AdamW kernel itself: the GEMMs read it
         # directly (ops.linear), so no fp32->bf16 weight cast kernel runs in the step
         lp = self.device.type == 'cuda' and self.compute_dtype == torch.bfloat16
@@ -297,6 +324,19 @@ class StepEngine:
         seg = self.flat_grad[lo:hi]
         if _SKIP_EXCHANGE:            # (diagnostic only: measures what a multi-GPU step costs WITHOUT its gradient exchange)
             return _NoWork()
+        if self._nvls is not None:
+            nv = self._nvls
+            cur, comm = torch.cuda.current_stream(self.device), nv['stream']
+            comm.wait_stream(cur)                      # the range is final on this rank ...
+            with torch.cuda.stream(comm):
+                nv['hdl'].barrier(channel=0)           # ... and on every other rank
+                _lib.call('rsc_nvls_allreduce_mean', nv['mc'], lo, (hi + 63) // 64 * 64, nv['rank'], self.world,
+                          1.0 / self.world, nv['ctas'], comm.cuda_stream, alg_bytes=8 * (hi - lo))
+                nv['hdl'].barrier(channel=0)           # every rank's share is stored everywhere
+            work = _StreamWork(comm, self.device)
+            if not async_op:
+                work.wait()
+            return work
         if self.device.type == 'cuda':
             return dist.all_reduce(seg, op=dist.ReduceOp.AVG, async_op=async_op)
         work = dist.all_reduce(seg, async_op=async_op)

@@ -65,6 +65,31 @@ def main():
         if rank == 0:
             print('%-14s %6.1f MB: multimem %7.1f us (%.0f GB/s algbw) | two_shot %7.1f us | nccl %7.1f us (%.0f GB/s)' % (
                 name, n * 4 / 1e6, t_nvls, n * 4 / t_nvls / 1e3, t_two, t_nccl, n * 4 / t_nccl / 1e3), flush=True)
+    # ---- the repo's own kernel: barrier -> rsc_nvls_allreduce_mean -> barrier
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from rscotr_b200 import _lib
+
+    def own(lo_, hi_, ctas):
+        hdl.barrier(channel=0)
+        _lib.call('rsc_nvls_allreduce_mean', mc, lo_, hi_, rank, world, 1.0 / world, ctas, torch.cuda.current_stream().cuda_stream)
+        hdl.barrier(channel=0)
+    buf.copy_(src)
+    plain.copy_(src)
+    own(lo, hi, 64)
+    dist.all_reduce(plain[lo:hi], op=dist.ReduceOp.AVG)
+    torch.cuda.synchronize()
+    err = float((buf[lo:hi] - plain[lo:hi]).abs().max() / plain[lo:hi].abs().max())
+    untouched = bool(torch.equal(buf[:lo], src[:lo]) and torch.equal(buf[hi:], src[hi:]))
+    if rank == 0:
+        print('own kernel, slice mean: max rel err vs NCCL AVG %.2e, outside the slice untouched: %s' % (err, untouched), flush=True)
+    for name, n in (('cls 27.6M', 27_600_000), ('det 48M', 48_000_000), ('stage3 14.2M', 14_200_000), ('1.6M', 1_600_000)):
+        n = n // 1024 * 1024
+        res = []
+        for ctas in (16, 32, 64, 128):
+            res.append('%d CTAs %7.1f us' % (ctas, timeit(lambda: own(0, n, ctas))))
+        t_nccl = timeit(lambda: dist.all_reduce(plain[:n], op=dist.ReduceOp.AVG))
+        if rank == 0:
+            print('%-14s %6.1f MB own: %s | nccl %7.1f us' % (name, n * 4 / 1e6, ' | '.join(res), t_nccl), flush=True)
     # CUDA-graph capture of the in-switch all-reduce on a side stream
     try:
         side = torch.cuda.Stream()
