@@ -430,6 +430,17 @@ int rsc_normalize_u8(const void *img, void *out, const float *mean, const float 
  * ---------------------------------------------------------------------- */
 int rsc_nvls_allreduce_mean(void *mc, int64_t lo, int64_t hi, int rank, int world, float scale, int ctas, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Iterative box refinement: out = sigmoid(tmp + inverse_sigmoid(ref, eps)), the chain
+ * `tmp + inverse_sigmoid(reference)` -> `.sigmoid()` of DinoTransformerDecoder.forward and DINOHead.forward
+ * (models/multi/bbox_head/dino_head.py; mmdet inverse_sigmoid: clamp(ref,0,1), log(max(x,eps) / max(1-x,eps))).
+ * tmp: `dtype` (the reg branch output), ref / out / dout / dref: float, n elements.  bwd: dtmp (`dtype`) =
+ * dout * out * (1 - out); dref (may be NULL) = dtmp * d inverse_sigmoid / d ref with torch's clamp conventions.
+ * ---------------------------------------------------------------------- */
+int rsc_box_refine_fwd(const void *tmp, const float *ref, float *out, int64_t n, float eps, int dtype, void *stream);
+int rsc_box_refine_bwd(const float *out, const float *ref, const float *dout, void *dtmp, float *dref, int64_t n, float eps,
+                       int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,8 @@ _SIGS = {
     'rsc_bilinear_cl_fwd': [_P, _P] + [_I] * 7 + [_P],
     'rsc_bilinear_cl_bwd': [_P, _P] + [_I] * 7 + [_P],
     'rsc_nvls_allreduce_mean': [_P, ctypes.c_int64, ctypes.c_int64, _I, _I, _F, _I, _P],
+    'rsc_box_refine_fwd': [_P, _P, _P, ctypes.c_int64, _F, _I, _P],
+    'rsc_box_refine_bwd': [_P, _P, _P, _P, _P, ctypes.c_int64, _F, _I, _P],
 }
 
 

@@ -431,6 +431,40 @@ __global__ void bilinear_cl_bwd_kernel(const T *__restrict__ dy, T *__restrict__
 }
 
 // ===========================================================================
+// Iterative box refinement of the DINO decoder / head: out = sigmoid(tmp + inverse_sigmoid(ref, eps)), fp32 out
+// (models/multi/bbox_head/dino_head.py forward + DinoTransformerDecoder.forward; mmdet inverse_sigmoid:
+//  x = clamp(ref, 0, 1); log(max(x, eps) / max(1 - x, eps))).  One launch instead of the 8-9 element-wise kernels of the
+// eager chain; the backward follows torch's clamp conventions (gradient passes where min <= x <= max).
+// ===========================================================================
+template <typename T>
+__global__ void box_refine_fwd_kernel(const T *__restrict__ tmp, const float *__restrict__ ref, float *__restrict__ out, int64_t n,
+                                      float eps) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = fminf(fmaxf(ref[i], 0.f), 1.f);
+    const float inv = logf(fmaxf(x, eps) / fmaxf(1.f - x, eps));
+    out[i] = 1.f / (1.f + expf(-(to_f<T>(tmp[i]) + inv)));
+  }
+}
+template <typename T>
+__global__ void box_refine_bwd_kernel(const float *__restrict__ out, const float *__restrict__ ref, const float *__restrict__ dout,
+                                      T *__restrict__ dtmp, float *__restrict__ dref, int64_t n, float eps) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float s = out[i], g = dout[i] * s * (1.f - s);
+    dtmp[i] = from_f<T>(g);
+    if (dref) {
+      const float r = ref[i];
+      float d = 0.f;
+      if (r >= 0.f && r <= 1.f) {
+        const float x = r, y = 1.f - r;
+        if (x >= eps) d += 1.f / x;
+        if (y >= eps) d += 1.f / y;
+      }
+      dref[i] = g * d;
+    }
+  }
+}
+
+// ===========================================================================
 // Sigmoid focal loss (element-wise, mmcv semantics)
 // ===========================================================================
 template <typename T, bool BWD>
@@ -756,5 +790,22 @@ extern "C" int rsc_bilinear_cl_bwd(const void *dy, void *dx, int B, int C, int H
         <<<ew_grid(total, 256), 256, 0, st>>>((const __nv_bfloat16 *)dy, (__nv_bfloat16 *)dx, total, C, Hi, Wi, Ho, Wo, sh, sw);
   }
   RSC_CHECK_LAUNCH("rsc_bilinear_cl_bwd");
+  return RSC_OK;
+}
+
+extern "C" int rsc_box_refine_fwd(const void *tmp, const float *ref, float *out, int64_t n, float eps, int dtype, void *stream) {
+  RSC_CHECK_ARG(n > 0 && tmp && ref && out, "rsc_box_refine_fwd: null pointer / empty tensor");
+  RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "rsc_box_refine_fwd: bad dtype %d", dtype);
+  DISPATCH_T(dtype, box_refine_fwd_kernel<T><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const T *)tmp, ref, out, n, eps));
+  RSC_CHECK_LAUNCH("rsc_box_refine_fwd");
+  return RSC_OK;
+}
+
+extern "C" int rsc_box_refine_bwd(const float *out, const float *ref, const float *dout, void *dtmp, float *dref, int64_t n, float eps,
+                                  int dtype, void *stream) {
+  RSC_CHECK_ARG(n > 0 && out && ref && dout && dtmp, "rsc_box_refine_bwd: null pointer / empty tensor");
+  RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "rsc_box_refine_bwd: bad dtype %d", dtype);
+  DISPATCH_T(dtype, box_refine_bwd_kernel<T><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(out, ref, dout, (T *)dtmp, dref, n, eps));
+  RSC_CHECK_LAUNCH("rsc_box_refine_bwd");
   return RSC_OK;
 }

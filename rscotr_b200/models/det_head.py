@@ -116,7 +116,10 @@ class DinoTransformerDecoder(TransformerLayerSequence):
             if reg_branches is not None:
                 tmp = reg_branches[lid](output)
                 assert reference_points.shape[-1] == 4
-                new_reference_points = (tmp.float() + inverse_sigmoid(reference_points, eps=1e-3)).sigmoid()
+                if tmp.is_cuda and tmp.dtype in (torch.float32, torch.bfloat16):
+                    new_reference_points = ops.box_refine(tmp, reference_points, 1e-3)     # one kernel (rsc_box_refine_*)
+                else:
+                    new_reference_points = (tmp.float() + inverse_sigmoid(reference_points, eps=1e-3)).sigmoid()
                 reference_points = new_reference_points.detach()
             output = output.permute(1, 0, 2)
             if self.return_intermediate:
@@ -629,15 +632,19 @@ class DINOHead(nn.Module):
         outputs_classes, outputs_coords = [], []
         # (unbind once: indexing per level would put one zero-fill + copy + add per level into the backward)
         for lvl, (hs_l, ref_l) in enumerate(zip(hs.unbind(0), inter_references.unbind(0)[:hs.shape[0]])):
-            reference = inverse_sigmoid(ref_l, eps=1e-3)
             outputs_class = self.cls_branches[lvl](hs_l)
-            tmp = self.reg_branches[lvl](hs_l).float()
+            tmp = self.reg_branches[lvl](hs_l)
+            outputs_classes.append(outputs_class)
+            if ref_l.shape[-1] == 4 and tmp.is_cuda and tmp.dtype in (torch.float32, torch.bfloat16):
+                outputs_coords.append(ops.box_refine(tmp, ref_l, 1e-3))      # sigmoid(tmp + inverse_sigmoid(ref)): one kernel
+                continue
+            reference = inverse_sigmoid(ref_l, eps=1e-3)
+            tmp = tmp.float()
             if reference.shape[-1] == 4:
                 tmp = tmp + reference
             else:
                 assert reference.shape[-1] == 2
                 tmp = torch.cat([tmp[..., :2] + reference, tmp[..., 2:]], -1)
-            outputs_classes.append(outputs_class)
             outputs_coords.append(tmp.sigmoid())
         return torch.stack(outputs_classes), torch.stack(outputs_coords), topk_score, topk_anchor
 

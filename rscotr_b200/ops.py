@@ -1504,6 +1504,41 @@ def normalize_u8(img, mean, inv_std, valid_hw=None, to_rgb=True, out_dtype=torch
     return out
 
 
+# ---------------------------------------------------------------------------
+# iterative box refinement of the DINO decoder / head   
+# ---------------------------------------------------------------------------
+class _BoxRefine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tmp, ref, eps):
+        _cuda(tmp, ref)
+        tmp = tmp.contiguous()
+        ref32 = ref.detach().float().contiguous()
+        out = torch.empty(tmp.shape, dtype=torch.float32, device=tmp.device)
+        with torch.cuda.device(tmp.device):
+            call('rsc_box_refine_fwd', tmp.data_ptr(), ref32.data_ptr(), out.data_ptr(), tmp.numel(), float(eps), _dt(tmp), _stream())
+        ctx.save_for_backward(out, ref32)
+        ctx.meta = (eps, tmp.dtype, ref.dtype, ctx.needs_input_grad[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        out, ref32 = ctx.saved_tensors
+        eps, tdt, rdt, need_ref = ctx.meta
+        dout = dout.float().contiguous()
+        dtmp = torch.empty(out.shape, dtype=tdt, device=out.device)
+        dref = torch.empty_like(out) if need_ref else None
+        with torch.cuda.device(out.device):
+            call('rsc_box_refine_bwd', out.data_ptr(), ref32.data_ptr(), dout.data_ptr(), dtmp.data_ptr(), _p(dref), out.numel(),
+                 float(eps), _dt(dtmp), _stream())
+        return dtmp, (dref.to(rdt) if need_ref else None), None
+
+
+def box_refine(tmp, ref, eps=1e-3):
+    """sigmoid(tmp.float() + inverse_sigmoid(ref, eps)) -> fp32, one kernel each way (tmp fp32 / bf16, same shape as ref)"""
+    assert tmp.shape == ref.shape
+    return _BoxRefine.apply(tmp, ref, eps)
+
+
 KernelTimer = _lib.KernelTimer
 
 

@@ -834,3 +834,30 @@ def test_bilinear_channels_last_matches_interpolate(shape, dtype):
     tol = 1e-5 if dtype == torch.float32 else 6e-3
     assert_rel(got, want, tol, 'y')
     assert_rel(xc.grad, xr.grad, tol, 'dx')
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_box_refine_matches_eager_chain(dtype):
+    """rsc_box_refine_{fwd,bwd} == (tmp.float() + inverse_sigmoid(ref, 1e-3)).sigmoid() of DinoTransformerDecoder.forward /
+    DINOHead.forward, values and both gradients, including references on and beyond the clamp boundaries"""
+    from rscotr_b200.models.bricks import inverse_sigmoid
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    ref = torch.rand(2, 1100, 4, generator=g)
+    ref[0, :6, 0] = torch.tensor([0.0, 1.0, 5e-4, 1 - 5e-4, 1e-3, 1 - 1e-3])
+    ref[0, 6:8, 1] = torch.tensor([-0.2, 1.3])
+    tmp = (torch.randn(2, 1100, 4, generator=g) * 2).to(dtype)
+    dout = torch.randn(2, 1100, 4, generator=g)
+    tr, rr = tmp.float().clone().requires_grad_(True), ref.clone().requires_grad_(True)
+    want = (tr + inverse_sigmoid(rr, eps=1e-3)).sigmoid()
+    want.backward(dout)
+    tc, rc = tmp.cuda().requires_grad_(True), ref.cuda().requires_grad_(True)
+    got = ops.box_refine(tc, rc, 1e-3)
+    assert got.dtype == torch.float32
+    got.backward(dout.cuda())
+    assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-6)
+    # (1 - s) cancels for saturated boxes: one ulp of s is 1e-3 of (1 - s) at s = 0.9999, so compare in norm and, element-wise,
+    # with the tolerance that one ulp of the sigmoid implies
+    assert_rel(rc.grad, rr.grad, 1e-4, 'dref')
+    assert torch.allclose(rc.grad.cpu(), rr.grad, rtol=2e-2, atol=1e-4)
+    assert_rel(tc.grad, tr.grad, 1e-5 if dtype == torch.float32 else 4e-3, 'dtmp')
