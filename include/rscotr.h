@@ -441,6 +441,16 @@ int rsc_box_refine_fwd(const void *tmp, const float *ref, float *out, int64_t n,
 int rsc_box_refine_bwd(const float *out, const float *ref, const float *dout, void *dtmp, float *dref, int64_t n, float eps,
                        int dtype, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Backward of a SMALL Linear layer (y = x W^T + b with fewer than ~4096 token rows: decoder projections, reg / cls
+ * branches, mask-embedding MLPs of dino_head.py / mask2former_head.py) in one launch instead of the library's three
+ * (mm, addmm, column sum):  dx (M,K) = dy (M,N) w (N,K) [bf16];  dw (N,K) += dy^T x [float, ACCUMULATED];
+ * db (N) += column sums of dy [float, ACCUMULATED].  All inputs bf16 row-major, leading dimensions in elements
+ * (multiples of 8), 16-byte aligned; dx / dw / db may be NULL (db needs dw).
+ * ---------------------------------------------------------------------- */
+int rsc_small_linear_bwd(const void *dy, const void *x, const void *w, void *dx, float *dw, float *db, int M, int N, int K,
+                         int64_t lddy, int64_t ldx, int64_t ldw, int64_t lddx, int64_t lddw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

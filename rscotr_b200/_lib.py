@@ -74,6 +74,7 @@ _SIGS = {
     'rsc_nvls_allreduce_mean': [_P, ctypes.c_int64, ctypes.c_int64, _I, _I, _F, _I, _P],
     'rsc_box_refine_fwd': [_P, _P, _P, ctypes.c_int64, _F, _I, _P],
     'rsc_box_refine_bwd': [_P, _P, _P, _P, _P, ctypes.c_int64, _F, _I, _P],
+    'rsc_small_linear_bwd': [_P] * 6 + [_I] * 3 + [ctypes.c_int64] * 5 + [_P],
 }
 
 

@@ -883,6 +883,29 @@ def _accumulate_dw(dy2, x2, gw, gb, wdt, bdt, wshape, want_db):
     return dw, db
 
 
+# RSC_SMALL_BWD=1: the small layers' backward (dX, dW +=, db +=) as ONE launch of rsc_small_linear_bwd instead of the library's
+# three.  A/B'd on B200 in round 2 (bench.py, same box): 81.5 vs 81.85 it/s with N, K <= 512 and 78.0 vs 82.1 without the limit
+# (one CTA walks a whole contraction; the library's split-K kernels are faster than the launches they cost) -> NOT promoted.
+_SMALL_BWD = __import__('os').environ.get('RSC_SMALL_BWD', '0') == '1'
+_SMALL_BWD_MAX = int(__import__('os').environ.get('RSC_SMALL_BWD_MAX', 512))
+
+
+def _small_bwd_ok(dy2, x2, w, gw, gb, want_db, want_dw):
+    """engine mode (gradients accumulate into the flat fp32 buffer), bf16, fewer rows than the tcgen05 kernels want"""
+    if not (_SMALL_BWD and want_dw and gw is not None and dy2.is_cuda and dy2.dtype == torch.bfloat16 and
+            x2.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and gw.dtype == torch.float32):
+        return False
+    if want_db and gb is None:
+        return False
+    M, N = dy2.shape
+    K = w.shape[1]
+    # (one CTA walks a whole contraction: beyond 512 the library's split-K kernels win, measured on B200)
+    return (M < _TC_MIN_ROWS and N % 8 == 0 and K % 8 == 0 and N <= _SMALL_BWD_MAX and K <= _SMALL_BWD_MAX and x2.dim() == 2 and x2.stride(1) == 1 and x2.stride(0) % 8 == 0 and
+            w.dim() == 2 and w.stride(1) == 1 and w.stride(0) % 8 == 0 and gw.dim() == 2 and gw.stride(1) == 1 and
+            gw.stride(0) % 2 == 0 and x2.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0 and dy2.data_ptr() % 16 == 0 and
+            gw.data_ptr() % 8 == 0)
+
+
 class _Linear(torch.autograd.Function):
     """y = x W^T + b.  bf16: the tcgen05 kernels of csrc/gemm_tc.cu (forward with the bias in the epilogue, dX with the
     weight read MN-major, dW + db in one kernel) where they are at least as fast as the library, see _own_plain;
@@ -916,6 +939,17 @@ class _Linear(torch.autograd.Function):
             dy2 = dy2.contiguous()
         x2 = x.reshape(-1, x.shape[-1])
         dx = dw = db = None
+        if _small_bwd_ok(dy2, x2, w, gw, gb, bdt is not None and ctx.needs_input_grad[2], ctx.needs_input_grad[1]):
+            # small layer in engine mode: dX, dW += and db += in ONE launch (rsc_small_linear_bwd)
+            M, N = dy2.shape
+            K = w.shape[1]
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(M, K, dtype=torch.bfloat16, device=dy2.device)
+            with torch.cuda.device(dy2.device):
+                call('rsc_small_linear_bwd', dy2.data_ptr(), x2.data_ptr(), w.data_ptr(), _p(dx), gw.data_ptr(), _p(gb), M, N, K,
+                     dy2.stride(0), x2.stride(0), w.stride(0), K, gw.stride(0), _stream(),
+                     alg_bytes=2 * (2 * M * N + 2 * M * K + N * K), alg_flops=4 * M * N * K)
+            return (dx.view(x.shape) if dx is not None else None), None, None, None, None, None, None
         if ctx.needs_input_grad[0]:
             if _tc_linear_ok(dy2, w) and w.shape[1] % 8 == 0 and _own_plain(dy2.shape[1]):
                 dx = gemm_dx(dy2, w).view(x.shape)

@@ -207,3 +207,34 @@ def test_adaptive_avg_pool(B, C, H, W, S, dtype):
     y.backward(gy.cuda().to(dtype))
     tol = 6e-3 if dtype == torch.bfloat16 else 1e-5
     assert y.shape == yr.shape and rel(y, yr) < tol and rel(xc.grad, xr.grad) < tol
+
+
+@pytest.mark.parametrize('M,N,K', [(1100, 256, 256), (1100, 512, 256), (100, 384, 256), (37, 8, 16), (2200, 2048, 256), (1100, 256, 2048),
+                                   (200, 256, 256), (900, 96, 264), (4000, 80, 256), (1, 256, 256)])
+@pytest.mark.parametrize('want', ['all', 'no_dx', 'no_db'])
+def test_small_linear_backward_one_launch(M, N, K, want):
+    """rsc_small_linear_bwd (dX, dW +=, db += of a small Linear layer in one launch) against fp32 torch on the same
+    bf16-rounded operands; dW / db are ACCUMULATED into pre-filled fp32 buffers (row stride of dW > K: a view of a wider buffer)"""
+    g = torch.Generator().manual_seed(M + N + K)
+    dy = torch.randn(M, N, generator=g).bfloat16()
+    x = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()
+    dw0 = torch.randn(N, K + 8, generator=g)
+    db0 = torch.randn(N, generator=g)
+    want_dx = dy.float() @ w.float()
+    want_dw = dw0[:, :K] + dy.float().t() @ x.float()
+    want_db = db0 + dy.float().sum(0)
+    dyc, xc, wc = dy.cuda(), x.cuda(), w.cuda()
+    dwc, dbc = dw0.cuda(), db0.cuda()
+    dxc = torch.empty(M, K, dtype=torch.bfloat16, device='cuda') if want != 'no_dx' else None
+    _call('rsc_small_linear_bwd', dyc.data_ptr(), xc.data_ptr(), wc.data_ptr(), None if dxc is None else dxc.data_ptr(),
+          dwc.data_ptr(), None if want == 'no_db' else dbc.data_ptr(), M, N, K, N, K, K, K, K + 8, _stream())
+    torch.cuda.synchronize()
+    if dxc is not None:
+        assert rel(dxc, want_dx) < 6e-3, rel(dxc, want_dx)
+    assert rel(dwc[:, :K], want_dw) < 1e-3, rel(dwc[:, :K], want_dw)
+    assert torch.equal(dwc[:, K:].cpu(), dw0[:, K:])                  # nothing written outside the (N, K) view
+    if want != 'no_db':
+        assert rel(dbc, want_db) < 1e-3
+    else:
+        assert torch.equal(dbc.cpu(), db0)
