@@ -335,6 +335,10 @@ int rsc_linear_dx(const void *dy, const void *w, const void *aux, void *dx, int6
                   int64_t ldw, int64_t lddx, int act, void *stream);
 int rsc_linear_dw(const void *dy, const void *x, float *dw, float *db, int64_t M, int N, int K, int64_t lddy, int64_t ldx,
                   int64_t lddw, void *stream);
+/* SMs the persistent rsc_linear_* kernels size their single wave for when the GEMM has fewer than `below_rows` token rows
+ * (0 = every GEMM); sms = 0 restores all 148.  Used by the data-parallel step engine to leave room for the gradient
+ * exchange that runs next to the small det / seg GEMMs. */
+int rsc_set_gemm_sms(int sms, int64_t below_rows);
 
 /* ------------------------------------------------------------------------
  * Convolutions as im2col GEMMs and the PPM pooling, channels-last maps (B,H,W,C).

@@ -26,6 +26,28 @@ namespace gemm {
 
 using namespace tc;
 
+// SMs the persistent kernels size their single wave for.  A data-parallel step overlaps its gradient exchange with
+// backward: while the collective's CTAs hold SMs, a persistent CTA that cannot become resident turns one wave into two.
+// rsc_set_gemm_sms(sms, below_rows) (called by the step engine when world > 1; RSC_GEMM_SMS / RSC_GEMM_SMS_BELOW override)
+// sizes the wave of the GEMMs with fewer than `below_rows` token rows for `sms` SMs.  Measured on 2 x B200: inside the
+// box-to-box spread for the det / seg steps, a loss for the tensor-bound cls GEMMs -> a tuning knob, off by default.
+static int g_sms_small = 0;
+static int64_t g_sms_below = 0;
+static int gemm_sms(int64_t rows) {
+  static const int env_sms = []() {
+    const char *e = getenv("RSC_GEMM_SMS");
+    const int n = e ? atoi(e) : 0;
+    return n > 0 && n <= kNumSMs ? n : 0;
+  }();
+  static const int64_t env_below = []() {
+    const char *e = getenv("RSC_GEMM_SMS_BELOW");
+    return e ? (int64_t)atoll(e) : (int64_t)-1;
+  }();
+  const int sms = env_sms ? env_sms : g_sms_small;
+  const int64_t below = env_below >= 0 ? env_below : g_sms_below;
+  return (sms > 0 && (below == 0 || rows < below)) ? sms : kNumSMs;
+}
+
 constexpr int BM = 128, BK = 64;
 constexpr int EPI_WARPS = 8, THREADS = 64 + EPI_WARPS * 32;
 enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RELU = 2, EPI_DGELU = 3, EPI_DRELU = 4, EPI_ADD_LN = 5 };
@@ -503,7 +525,8 @@ static int launch(const CUtensorMap &tA, const CUtensorMap &tB, const CUtensorMa
   auto kern = gemm_kernel<BN, STAGES, B_MN, EPI>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  const int sms = gemm_sms(p.M);
+  const int grid = tiles < sms ? tiles : sms;
   kern<<<grid, THREADS, S::TOTAL, st>>>(tA, tB, tD, tD2, tD3, p);
   return 0;
 }
@@ -766,7 +789,8 @@ static int launch_dw(const CUtensorMap &tA, const CUtensorMap &tB, float *dw, fl
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
   const int n_tiles = (N + BM - 1) / BM, k_tiles = (K + BN - 1) / BN, tiles = n_tiles * k_tiles;
   const int blocks_total = (M + BK - 1) / BK;
-  int chunks = tiles >= kNumSMs ? 1 : kNumSMs / tiles;            // one wave of CTAs
+  const int sms = gemm_sms(M);
+  int chunks = tiles >= sms ? 1 : sms / tiles;                    // one wave of CTAs
   if (chunks > blocks_total) chunks = blocks_total;
   kern<<<tiles * chunks, DW_THREADS, S::TOTAL, st>>>(tA, tB, dw, db, M, N, K, lddw, k_tiles, chunks);
   return 0;
@@ -792,5 +816,12 @@ extern "C" int rsc_linear_dw(const void *dy, const void *x, float *dw, float *db
   else rc = gemm::launch_dw<192, 4>(tA, tB, dw, db, (int)M, N, K, lddw, (cudaStream_t)stream);
   (void)rc;
   RSC_CHECK_LAUNCH("rsc_linear_dw");
+  return RSC_OK;
+}
+
+extern "C" int rsc_set_gemm_sms(int sms, int64_t below_rows) {
+  RSC_CHECK_ARG(sms >= 0 && sms <= kNumSMs && below_rows >= 0, "rsc_set_gemm_sms: sms must be in [0, %d] (0 = all)", kNumSMs);
+  rsc::gemm::g_sms_small = sms;
+  rsc::gemm::g_sms_below = below_rows;
   return RSC_OK;
 }

@@ -201,6 +201,12 @@ class StepEngine:
         bb = getattr(self.model, 'backbone', None)
         if self.world > 1 and bb is not None and os.environ.get('RSC_OVERLAP_EXCHANGE', '1') != '0':
             bb._grad_ready_cb = self._on_grad_ready
+        # data parallel, opt-in (RSC_DP_GEMM_SMS=120): size the persistent GEMMs of the small-batch (det / seg) steps for fewer SMs
+        # so that the exchange kernels running next to them do not push their last CTAs into a second wave
+        # (csrc/gemm_tc.cu::gemm_sms).  A/B'd on 2 x B200 in round 2: within the box-to-box spread (det 10.2 -> 9.7 ms on one box,
+        # 9.74 -> 9.77 ms on the next; the cls step loses 0.4-0.7 ms when it is included) -> off by default.
+        self._dp_gemm_sms = int(os.environ.get('RSC_DP_GEMM_SMS', 0)) if self.world > 1 and self.device.type == 'cuda' else 0
+        self._dp_gemm_max_batch = int(os.environ.get('RSC_DP_GEMM_SMS_MAX_BATCH', 4))
         if self.world > 1 and self.device.type == 'cuda' and os.environ.get('RSC_ASYNC_LOG_REDUCE', '1') != '0':
             from ...models import mtl as _mtl
             _mtl.ASYNC_LOG_WORKS = []
@@ -425,7 +431,15 @@ class StepEngine:
     def _autocast(self):
         return torch.autocast('cuda', dtype=self.compute_dtype, enabled=self.compute_dtype != torch.float32)
 
+    def _set_gemm_sms(self, batch):
+        """per step (the grid is baked into a captured graph, so this runs before eager steps and captures only)"""
+        if self._dp_gemm_sms:
+            img = batch.get('img') if isinstance(batch, dict) else None
+            n = img.shape[0] if torch.is_tensor(img) else (len(img) if isinstance(img, (list, tuple)) else 1 << 30)
+            _lib.call('rsc_set_gemm_sms', self._dp_gemm_sms if n <= self._dp_gemm_max_batch else 0, 0)
+
     def _train_iter_eager(self, data):
+        self._set_gemm_sms(data)
         self.flat_grad.zero_()
         with self._autocast():
             outputs = self.model.train_step(data, self.optimizer)
@@ -463,6 +477,7 @@ class StepEngine:
         losses + backward + clip + AdamW after the host-side Hungarian matching."""
         static = _static_copy(batch, self.device)
         task = static['task']
+        self._set_gemm_sms(static)
         torch.cuda.synchronize()
         n0 = _lib.launch_count()
         gA, gB = torch.cuda.CUDAGraph(), None
