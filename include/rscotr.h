@@ -151,14 +151,20 @@ int rsc_msda_bwd(const void *value, const int64_t *spatial_shapes, const int64_t
  * + offsets / P * ref_wh * 0.5 (4-d references) + the sampling op above, in one kernel each way.
  * offsets (B,Nq,heads,L,P,2) and logits (B,Nq,heads,L*P) are the raw outputs of the two Linears (`off_dtype`),
  * ref (B,Nq,L,ref_dim) fp32 with ref_dim 2 or 4 (no gradient is produced for it: the reference feeds detached /
- * constant reference points), L*P must be 16.  grad_value is fp32 and ACCUMULATED (zero it first). */
+ * constant reference points), L*P must be 16.  grad_value is fp32 and ACCUMULATED (zero it first).
+ * off_row_stride / logit_row_stride: elements between consecutive queries' rows of offsets / logits (and of their
+ * gradients); 0 = dense (heads*L*P*2 and heads*L*P).  With strides the two matrices can be column ranges of ONE
+ * (B*Nq, heads*L*P*3) matrix -- the output of a single GEMM over the stacked sampling_offsets / attention_weights
+ * weights -- and the two gradients column ranges of the matrix that GEMM's backward reads. */
 int rsc_msda_fused_fwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                        const void *offsets, const void *logits, const float *ref, void *out, int B, int Nv, int Nq,
-                       int heads, int L, int P, int ref_dim, int dtype, int off_dtype, void *stream);
+                       int heads, int L, int P, int ref_dim, int dtype, int off_dtype, int off_row_stride,
+                       int logit_row_stride, void *stream);
 int rsc_msda_fused_bwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                        const void *offsets, const void *logits, const float *ref, const void *grad_out,
                        float *grad_value, void *grad_offsets, void *grad_logits, int B, int Nv, int Nq, int heads,
-                       int L, int P, int ref_dim, int dtype, int off_dtype, void *stream);
+                       int L, int P, int ref_dim, int dtype, int off_dtype, int off_row_stride, int logit_row_stride,
+                       void *stream);
 
 /* ------------------------------------------------------------------------
  * Global average pool.  Replaces mmcls GlobalAveragePooling

@@ -44,8 +44,8 @@ _SIGS = {
     'rsc_colsum': [_P, _P, ctypes.c_int64, _I, _I, _P],
     'rsc_msda_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'rsc_msda_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    'rsc_msda_fused_fwd': [_P] * 7 + [_I] * 9 + [_P],
-    'rsc_msda_fused_bwd': [_P] * 10 + [_I] * 9 + [_P],
+    'rsc_msda_fused_fwd': [_P] * 7 + [_I] * 11 + [_P],
+    'rsc_msda_fused_bwd': [_P] * 10 + [_I] * 11 + [_P],
     'rsc_gap_fwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'rsc_gap_bwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'rsc_bilinear_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -192,6 +192,293 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------
+// Round-2 rewrite of the two kernels above (same arithmetic, same lane <-> channel mapping).  The first version
+// walked ONE token per warp step through load -> reduce -> reload -> store: three dependent memory round trips per
+// 2.3 KB, i.e. latency-bound at 0.16-0.28 of the HBM roofline (profiles/r02_ncu_launches_timed_region.csv.gz:
+// 288 us for the 369 MB stage-0 backward).  Here a warp step covers TPW tokens whose loads are all issued before the
+// first reduction, the operands stay in registers in their STORAGE type (bf16 pairs: half the registers of fp32)
+// for the second sweep instead of being re-read, and 128-thread CTAs let the register-heavy variants keep more
+// warps resident.  The cross-warp fold of d(gamma) / d(beta) is a plain shared-memory read-modify-write per warp
+// in turn (shared fp32 atomicAdd is a compare-and-swap loop on this architecture).
+// ---------------------------------------------------------------------------
+template <typename T>
+struct Raw4;
+template <>
+struct Raw4<float> {
+  float4 v;
+  __device__ __forceinline__ void load(const float *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void touch() {}
+  __device__ __forceinline__ float4 get() const { return v; }
+};
+template <>
+struct Raw4<__nv_bfloat16> {
+  uint2 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16 *p) { v = __ldg(reinterpret_cast<const uint2 *>(p)); }
+  __device__ __forceinline__ void zero() { v = make_uint2(0u, 0u); }
+  // opaque to the optimiser: a later get() is re-evaluated from the packed words instead of keeping the four fp32
+  // values of an earlier get() alive (registers decide how many warps stay resident)
+  __device__ __forceinline__ void touch() { asm volatile("" : "+r"(v.x), "+r"(v.y)); }
+  __device__ __forceinline__ float4 get() const {
+    // bf16 -> fp32 is a 16-bit shift
+    return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                       __uint_as_float(v.y & 0xffff0000u));
+  }
+};
+
+constexpr int PM_THREADS = 128;
+
+template <typename T, int ITER, int TPW>
+__global__ void __launch_bounds__(PM_THREADS)
+    patch_merge_ln_fwd2_kernel(const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+                               T *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd, PMGeom g,
+                               float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tokens = (int64_t)g.B * g.Ho * g.Wo;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float invn = 1.0f / (4 * g.C);
+  const int64_t rowC = (int64_t)g.W * g.C;
+  for (int64_t tok0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * TPW; tok0 < tokens;
+       tok0 += nwarps * TPW) {
+    Raw4<T> rx[TPW][ITER][4];
+    float s[TPW];
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      const int64_t tok = tok0 + t;
+      const bool valid = tok < tokens;
+      const int j = (int)(tok % g.Wo), i = (int)((tok / g.Wo) % g.Ho), b = (int)(tok / ((int64_t)g.Wo * g.Ho));
+      const T *xb = x + ((int64_t)b * g.H + 2 * i) * rowC + (int64_t)2 * j * g.C;
+      const bool h1 = 2 * i + 1 < g.H, w1 = 2 * j + 1 < g.W;
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        const int c = it * 128 + lane * 4;
+        const bool on = valid && c < g.C;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (on && ((k >> 1) == 0 || h1) && ((k & 1) == 0 || w1)) rx[t][it][k].load(xb + (k >> 1) * rowC + (k & 1) * g.C + c);
+          else rx[t][it][k].zero();
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      float a = 0.f;
+#pragma unroll
+      for (int it = 0; it < ITER; ++it)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 v = rx[t][it][k].get();
+          a += (v.x + v.y) + (v.z + v.w);
+        }
+      s[t] = a;
+    }
+    float mu[TPW], rs[TPW];
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) mu[t] = warp_sum(s[t]) * invn;
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      float q = 0.f;
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        if (it * 128 + lane * 4 < g.C) {      // (inactive lanes hold zeros, which are NOT zero after centring)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 v = rx[t][it][k].get();
+            const float a = v.x - mu[t], b2 = v.y - mu[t], c2 = v.z - mu[t], d = v.w - mu[t];
+            q += a * a + b2 * b2 + c2 * c2 + d * d;
+          }
+        }
+      }
+      s[t] = q;
+    }
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) rs[t] = rsqrtf(warp_sum(s[t]) * invn + eps);
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      const int64_t tok = tok0 + t;
+      if (tok >= tokens) break;
+      if (lane == 0) {
+        mean[tok] = mu[t];
+        rstd[tok] = rs[t];
+      }
+      T *yo = y + tok * 4 * g.C;
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        const int c = it * 128 + lane * 4;
+        if (c < g.C) {
+          float4 xv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xv[k] = rx[t][it][k].get();
+          const float *vf = reinterpret_cast<const float *>(&xv[0]);  // vf[k*4 + cc]
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int o = (c + cc) * 4;
+            const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma + o));
+            const float4 be = __ldg(reinterpret_cast<const float4 *>(beta + o));
+            float4 r;
+            r.x = (vf[0 * 4 + cc] - mu[t]) * rs[t] * ga.x + be.x;
+            r.y = (vf[1 * 4 + cc] - mu[t]) * rs[t] * ga.y + be.y;
+            r.z = (vf[2 * 4 + cc] - mu[t]) * rs[t] * ga.z + be.z;
+            r.w = (vf[3 * 4 + cc] - mu[t]) * rs[t] * ga.w + be.w;
+            store4<T>(yo + o, r);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int ITER, int TPW>
+__global__ void __launch_bounds__(PM_THREADS, ITER <= 3 ? 3 : 2)   // (3 CTAs: 168 registers, <= 152 B of spills)
+    patch_merge_ln_bwd2_kernel(const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ mean,
+                               const float *__restrict__ rstd, const T *__restrict__ dy, T *__restrict__ dx,
+                               float *__restrict__ dgamma, float *__restrict__ dbeta, PMGeom g) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tokens = (int64_t)g.B * g.Ho * g.Wo;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float invn = 1.0f / (4 * g.C);
+  const int64_t rowC = (int64_t)g.W * g.C;
+  float dg[ITER][16], db[ITER][16];  // [cc*4 + k] = output channel (c+cc)*4 + k
+#pragma unroll
+  for (int it = 0; it < ITER; ++it)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) dg[it][e] = 0.f, db[it][e] = 0.f;
+
+  for (int64_t tok0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * TPW; tok0 < tokens;
+       tok0 += nwarps * TPW) {
+    Raw4<T> rx[TPW][ITER][4], rd[TPW][ITER][4];   // rx[..][k]: source token k; rd[..][cc]: output channels (c+cc)*4 .. +3
+    float mu[TPW], rs[TPW], s1[TPW], s2[TPW];
+    // every load of the TPW tokens is in flight before the first use
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      const int64_t tok = tok0 + t;
+      const bool valid = tok < tokens;
+      const int j = (int)(tok % g.Wo), i = (int)((tok / g.Wo) % g.Ho), b = (int)(tok / ((int64_t)g.Wo * g.Ho));
+      const T *xb = x + ((int64_t)b * g.H + 2 * i) * rowC + (int64_t)2 * j * g.C;
+      const T *dyo = dy + tok * 4 * g.C;
+      const bool h1 = 2 * i + 1 < g.H, w1 = 2 * j + 1 < g.W;
+      mu[t] = valid ? __ldg(mean + tok) : 0.f;
+      rs[t] = valid ? __ldg(rstd + tok) : 0.f;
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        const int c = it * 128 + lane * 4;
+        const bool on = valid && c < g.C;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (on && ((k >> 1) == 0 || h1) && ((k & 1) == 0 || w1)) rx[t][it][k].load(xb + (k >> 1) * rowC + (k & 1) * g.C + c);
+          else rx[t][it][k].zero();
+          if (on) rd[t][it][k].load(dyo + (c + k) * 4);
+          else rd[t][it][k].zero();
+        }
+      }
+    }
+    // sweep 1: row sums of the LayerNorm backward + d(gamma) / d(beta) partials
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        const int c = it * 128 + lane * 4;
+        if (c < g.C) {
+          float4 xv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xv[k] = rx[t][it][k].get();
+          const float *xf = reinterpret_cast<const float *>(&xv[0]);  // xf[k*4 + cc]
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const float4 d4 = rd[t][it][cc].get();
+            const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma + (c + cc) * 4));
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float gv[4] = {ga.x, ga.y, ga.z, ga.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float xh = (xf[k * 4 + cc] - mu[t]) * rs[t];
+              const float dxh = dv[k] * gv[k];
+              a1 += dxh;
+              a2 = fmaf(dxh, xh, a2);
+              dg[it][cc * 4 + k] = fmaf(dv[k], xh, dg[it][cc * 4 + k]);
+              db[it][cc * 4 + k] += dv[k];
+            }
+          }
+        }
+      }
+      s1[t] = a1, s2[t] = a2;
+    }
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      s1[t] = warp_sum(s1[t]) * invn;
+      s2[t] = warp_sum(s2[t]) * invn;
+    }
+    // sweep 2 from the same registers: dx
+#pragma unroll
+    for (int t = 0; t < TPW; ++t) {
+      const int64_t tok = tok0 + t;
+      if (tok >= tokens) break;
+      const int j = (int)(tok % g.Wo), i = (int)((tok / g.Wo) % g.Ho), b = (int)(tok / ((int64_t)g.Wo * g.Ho));
+      T *dxb = dx + ((int64_t)b * g.H + 2 * i) * rowC + (int64_t)2 * j * g.C;
+      const bool h1 = 2 * i + 1 < g.H, w1 = 2 * j + 1 < g.W;
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        const int c = it * 128 + lane * 4;
+        if (c < g.C) {
+          float4 xv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            rx[t][it][k].touch();
+            rd[t][it][k].touch();
+            xv[k] = rx[t][it][k].get();
+          }
+          float *xf = reinterpret_cast<float *>(&xv[0]);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const float4 d4 = rd[t][it][cc].get();
+            const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma + (c + cc) * 4));
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float gv[4] = {ga.x, ga.y, ga.z, ga.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float xh = (xf[k * 4 + cc] - mu[t]) * rs[t];
+              xf[k * 4 + cc] = rs[t] * (dv[k] * gv[k] - s1[t] - xh * s2[t]);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (((k >> 1) == 0 || h1) && ((k & 1) == 0 || w1)) store4<T>(dxb + (k >> 1) * rowC + (k & 1) * g.C + c, xv[k]);
+        }
+      }
+    }
+  }
+  // per-lane partial sums -> per-CTA table (each warp in turn, plain read-modify-write: a lane owns its channels)
+  // -> ONE global atomic per channel per CTA
+  extern __shared__ float red[];   // [2][4C]
+  for (int i2 = threadIdx.x; i2 < 8 * g.C; i2 += blockDim.x) red[i2] = 0.f;
+  __syncthreads();
+  for (int w = 0; w < PM_THREADS / 32; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int it = 0; it < ITER; ++it) {
+        const int c = it * 128 + lane * 4;
+        if (c < g.C) {
+          float4 *rg = reinterpret_cast<float4 *>(red + c * 4), *rb = reinterpret_cast<float4 *>(red + 4 * g.C + c * 4);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            float4 a = rg[cc], b2 = rb[cc];
+            a.x += dg[it][cc * 4 + 0], a.y += dg[it][cc * 4 + 1], a.z += dg[it][cc * 4 + 2], a.w += dg[it][cc * 4 + 3];
+            b2.x += db[it][cc * 4 + 0], b2.y += db[it][cc * 4 + 1], b2.z += db[it][cc * 4 + 2], b2.w += db[it][cc * 4 + 3];
+            rg[cc] = a, rb[cc] = b2;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int i2 = threadIdx.x; i2 < 4 * g.C; i2 += blockDim.x) {
+    atomicAdd(dgamma + i2, red[i2]);
+    atomicAdd(dbeta + i2, red[4 * g.C + i2]);
+  }
+}
+
 // ===========================================================================
 // Global average pool
 // ===========================================================================
@@ -579,6 +866,52 @@ static void pm_bwd_launch(int iters, int grid, cudaStream_t st, const void *x, c
 #undef PM_CASE
 }
 
+// grid of the round-2 kernels: every resident CTA slot of the device, once (persistent warps), or fewer for few tokens
+template <typename K>
+static int pm_grid(K kernel, size_t smem, int64_t tokens, int tpw) {
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, PM_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+  const int64_t need = (tokens + (int64_t)tpw * (PM_THREADS / 32) - 1) / ((int64_t)tpw * (PM_THREADS / 32));
+  const int64_t cap = (int64_t)kNumSMs * occ;
+  return (int)(need < cap ? need : cap);
+}
+
+template <typename T>
+static void pm_fwd2_launch(int iters, cudaStream_t st, const void *x, const float *gamma, const float *beta, void *y,
+                           float *mean, float *rstd, PMGeom g, float eps) {
+  const int64_t tokens = (int64_t)g.B * g.Ho * g.Wo;
+#define PM_CASE(N, TPW)                                                                                             \
+  case N: {                                                                                                         \
+    auto k = patch_merge_ln_fwd2_kernel<T, N, TPW>;                                                                 \
+    k<<<pm_grid(k, 0, tokens, TPW), PM_THREADS, 0, st>>>((const T *)x, gamma, beta, (T *)y, mean, rstd, g, eps);    \
+  } break;
+  switch (iters) { PM_CASE(1, 4) PM_CASE(2, 4) PM_CASE(3, 2) PM_CASE(4, 2) }
+#undef PM_CASE
+}
+template <typename T>
+static void pm_bwd2_launch(int iters, cudaStream_t st, const void *x, const float *gamma, const float *mean,
+                           const float *rstd, const void *dy, void *dx, float *dgamma, float *dbeta, PMGeom g) {
+  const int64_t tokens = (int64_t)g.B * g.Ho * g.Wo;
+  const size_t smem = 8 * g.C * sizeof(float);
+#define PM_CASE(N, TPW)                                                                                             \
+  case N: {                                                                                                         \
+    auto k = patch_merge_ln_bwd2_kernel<T, N, TPW>;                                                                 \
+    k<<<pm_grid(k, smem, tokens, TPW), PM_THREADS, smem, st>>>((const T *)x, gamma, mean, rstd, (const T *)dy,      \
+                                                               (T *)dx, dgamma, dbeta, g);                          \
+  } break;
+  switch (iters) { PM_CASE(1, 4) PM_CASE(2, 2) PM_CASE(3, 1) PM_CASE(4, 1) }
+#undef PM_CASE
+}
+
+// RSC_PATCH_MERGE_V1=1: the round-1 kernels (one token per warp step), kept for A/B runs
+static bool pm_v1() {
+  static const bool v1 = [] {
+    const char *e = getenv("RSC_PATCH_MERGE_V1");
+    return e && e[0] == '1';
+  }();
+  return v1;
+}
+
 static int pm_check(const char *fn, int B, int H, int W, int C, int dtype) {
   RSC_CHECK_ARG(B > 0 && H > 0 && W > 0, "%s: empty tensor (B=%d,H=%d,W=%d)", fn, B, H, W);
   RSC_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 512, "%s: C must be a multiple of 4, <= 512 (got %d)", fn, C);
@@ -593,7 +926,11 @@ extern "C" int rsc_patch_merge_ln_fwd(const void *x, const float *gamma, const f
   PMGeom g{B, H, W, C, (H + 1) / 2, (W + 1) / 2};
   int64_t tokens = (int64_t)B * g.Ho * g.Wo;
   int grid = ew_grid(tokens, 8);
-  DISPATCH_T(dtype, pm_fwd_launch<T>((C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, beta, y, mean, rstd, g, eps));
+  if (pm_v1()) {
+    DISPATCH_T(dtype, pm_fwd_launch<T>((C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, beta, y, mean, rstd, g, eps));
+  } else {
+    DISPATCH_T(dtype, pm_fwd2_launch<T>((C + 127) / 128, (cudaStream_t)stream, x, gamma, beta, y, mean, rstd, g, eps));
+  }
   RSC_CHECK_LAUNCH("rsc_patch_merge_ln_fwd");
   return RSC_OK;
 }
@@ -607,8 +944,13 @@ extern "C" int rsc_patch_merge_ln_bwd(const void *x, const float *gamma, const f
   int64_t tokens = (int64_t)B * g.Ho * g.Wo;
   int64_t blocks = (tokens + 7) / 8;
   int grid = (int)(blocks < kNumSMs * 4 ? blocks : kNumSMs * 4);  // few warps -> few dgamma atomics
-  DISPATCH_T(dtype, pm_bwd_launch<T>((C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, mean, rstd, dy, dx, dgamma,
-                                     dbeta, g));
+  if (pm_v1()) {
+    DISPATCH_T(dtype, pm_bwd_launch<T>((C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, mean, rstd, dy, dx, dgamma,
+                                       dbeta, g));
+  } else {
+    DISPATCH_T(dtype, pm_bwd2_launch<T>((C + 127) / 128, (cudaStream_t)stream, x, gamma, mean, rstd, dy, dx, dgamma,
+                                        dbeta, g));
+  }
   RSC_CHECK_LAUNCH("rsc_patch_merge_ln_bwd");
   return RSC_OK;
 }

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     msda_fused_fwd_kernel(const T *__restrict__ value, const int64_t *__restrict__ shapes,
                           const int64_t *__restrict__ starts, const TO *__restrict__ offs, const TO *__restrict__ logits,
                           const float *__restrict__ ref, T *__restrict__ out, int B, int Nv, int Nq, int heads, int L,
-                          int P, int R) {
+                          int P, int R, int64_t ostride, int64_t lstride) {
   __shared__ Entry ent[WARPS][4 * GSTRIDE];
   __shared__ Levels lv;
   load_levels(lv, shapes, starts, L);
@@ -288,13 +288,14 @@ __global__ void __launch_bounds__(WARPS * 32)
     const int hg = (int)(item % hgroups);
     const int64_t bq = item / hgroups;
     const int b = (int)(bq / Nq);
-    const int64_t slab = (bq * heads + hg * 4) * LP;
+    // row strides: a query's offsets / logits may be column ranges of one wider matrix (the output of ONE GEMM)
+    const int64_t lrow = bq * lstride + hg * 4 * LP, orow = bq * ostride + hg * 8 * LP;
     // ---- phase 1: two (head, point) pairs per lane ----
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       const int q = lane + 32 * it, hq = q >> 4, lp = q & 15;
-      const float lg = ldf<TO>(logits, slab + q);
-      const float ox = ldf<TO>(offs, (slab + q) * 2), oy = ldf<TO>(offs, (slab + q) * 2 + 1);
+      const float lg = ldf<TO>(logits, lrow + q);
+      const float ox = ldf<TO>(offs, orow + q * 2), oy = ldf<TO>(offs, orow + q * 2 + 1);
       const float e = __expf(lg - half_max(lg));
       const float aw = e / half_sum(e);
       const Geo ge = pair_geo(lv, ref, bq, L, P, R, lp, ox, oy);
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(WARPS * 32)
                           const int64_t *__restrict__ starts, const TO *__restrict__ offs, const TO *__restrict__ logits,
                           const float *__restrict__ ref, const T *__restrict__ gout, float *__restrict__ gvalue,
                           TO *__restrict__ goffs, TO *__restrict__ glogits, int B, int Nv, int Nq, int heads, int L, int P,
-                          int R) {
+                          int R, int64_t ostride, int64_t lstride) {
   __shared__ Entry ent[WARPS][4 * GSTRIDE];
   __shared__ float red[WARPS][4 * LP][3];   // per pair: d/d(loc x), d/d(loc y), d/d(attention weight)
   __shared__ Levels lv;
@@ -347,14 +348,14 @@ __global__ void __launch_bounds__(WARPS * 32)
     const int hg = (int)(item % hgroups);
     const int64_t bq = item / hgroups;
     const int b = (int)(bq / Nq);
-    const int64_t slab = (bq * heads + hg * 4) * LP;
+    const int64_t lrow = bq * lstride + hg * 4 * LP, orow = bq * ostride + hg * 8 * LP;
     float aw_[2], sx_[2], sy_[2];
     // ---- phase 1 ----
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       const int q = lane + 32 * it, hq = q >> 4, lp = q & 15;
-      const float lg = ldf<TO>(logits, slab + q);
-      const float ox = ldf<TO>(offs, (slab + q) * 2), oy = ldf<TO>(offs, (slab + q) * 2 + 1);
+      const float lg = ldf<TO>(logits, lrow + q);
+      const float ox = ldf<TO>(offs, orow + q * 2), oy = ldf<TO>(offs, orow + q * 2 + 1);
       const float e = __expf(lg - half_max(lg));
       const float aw = e / half_sum(e);
       const Geo ge = pair_geo(lv, ref, bq, L, P, R, lp, ox, oy);
@@ -409,9 +410,9 @@ __global__ void __launch_bounds__(WARPS * 32)
       const int q = lane + 32 * it;
       const float *r = red[warp][q];
       const float dot = half_sum(aw_[it] * r[2]);
-      glogits[slab + q] = from_f<TO>(aw_[it] * (r[2] - dot));
-      goffs[(slab + q) * 2] = from_f<TO>(r[0] * sx_[it]);
-      goffs[(slab + q) * 2 + 1] = from_f<TO>(r[1] * sy_[it]);
+      glogits[lrow + q] = from_f<TO>(aw_[it] * (r[2] - dot));
+      goffs[orow + q * 2] = from_f<TO>(r[0] * sx_[it]);
+      goffs[orow + q * 2 + 1] = from_f<TO>(r[1] * sy_[it]);
     }
     __syncwarp();
   }
@@ -492,10 +493,23 @@ static int msda_fused_check(const char *fn, int B, int Nv, int Nq, int heads, in
   return RSC_OK;
 }
 
+// row strides (elements) of the offsets / logits matrices and of their gradients; 0 = dense rows.  In-place: the
+// defaults are substituted.
+static int msda_fused_strides(const char *fn, int heads, int &ostride, int &lstride) {
+  const int od = heads * msf::LP * 2, ld = heads * msf::LP;
+  if (ostride == 0) ostride = od;
+  if (lstride == 0) lstride = ld;
+  RSC_CHECK_ARG(ostride >= od && lstride >= ld, "%s: row strides (%d, %d) shorter than a row (%d, %d)", fn, ostride,
+                lstride, od, ld);
+  return RSC_OK;
+}
+
 extern "C" int rsc_msda_fused_fwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                                   const void *offsets, const void *logits, const float *ref, void *out, int B, int Nv,
-                                  int Nq, int heads, int L, int P, int ref_dim, int dtype, int off_dtype, void *stream) {
+                                  int Nq, int heads, int L, int P, int ref_dim, int dtype, int off_dtype,
+                                  int off_row_stride, int logit_row_stride, void *stream) {
   if (int e = msda_fused_check("rsc_msda_fused_fwd", B, Nv, Nq, heads, L, P, ref_dim, dtype, off_dtype)) return e;
+  if (int e = msda_fused_strides("rsc_msda_fused_fwd", heads, off_row_stride, logit_row_stride)) return e;
   RSC_CHECK_ARG(value && spatial_shapes && level_start_index && offsets && logits && ref && out,
                 "rsc_msda_fused_fwd: null pointer");
   const int64_t items = (int64_t)B * Nq * (heads / 4);
@@ -504,7 +518,8 @@ extern "C" int rsc_msda_fused_fwd(const void *value, const int64_t *spatial_shap
 #define MFF(T, TO)                                                                                                  \
   msf::msda_fused_fwd_kernel<T, TO><<<grid, msf::WARPS * 32, 0, st>>>((const T *)value, spatial_shapes, level_start_index, \
                                                                        (const TO *)offsets, (const TO *)logits, ref,  \
-                                                                       (T *)out, B, Nv, Nq, heads, L, P, ref_dim)
+                                                                       (T *)out, B, Nv, Nq, heads, L, P, ref_dim,     \
+                                                                       (int64_t)off_row_stride, (int64_t)logit_row_stride)
   if (dtype == RSC_F32) {
     if (off_dtype == RSC_F32) MFF(float, float); else MFF(float, __nv_bfloat16);
   } else {
@@ -518,8 +533,10 @@ extern "C" int rsc_msda_fused_fwd(const void *value, const int64_t *spatial_shap
 extern "C" int rsc_msda_fused_bwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                                   const void *offsets, const void *logits, const float *ref, const void *grad_out,
                                   float *grad_value, void *grad_offsets, void *grad_logits, int B, int Nv, int Nq,
-                                  int heads, int L, int P, int ref_dim, int dtype, int off_dtype, void *stream) {
+                                  int heads, int L, int P, int ref_dim, int dtype, int off_dtype, int off_row_stride,
+                                  int logit_row_stride, void *stream) {
   if (int e = msda_fused_check("rsc_msda_fused_bwd", B, Nv, Nq, heads, L, P, ref_dim, dtype, off_dtype)) return e;
+  if (int e = msda_fused_strides("rsc_msda_fused_bwd", heads, off_row_stride, logit_row_stride)) return e;
   RSC_CHECK_ARG(value && spatial_shapes && level_start_index && offsets && logits && ref && grad_out && grad_value &&
                     grad_offsets && grad_logits,
                 "rsc_msda_fused_bwd: null pointer");
@@ -529,7 +546,8 @@ extern "C" int rsc_msda_fused_bwd(const void *value, const int64_t *spatial_shap
 #define MFB(T, TO)                                                                                                    \
   msf::msda_fused_bwd_kernel<T, TO><<<grid, msf::WARPS * 32, 0, st>>>(                                                \
       (const T *)value, spatial_shapes, level_start_index, (const TO *)offsets, (const TO *)logits, ref,              \
-      (const T *)grad_out, grad_value, (TO *)grad_offsets, (TO *)grad_logits, B, Nv, Nq, heads, L, P, ref_dim)
+      (const T *)grad_out, grad_value, (TO *)grad_offsets, (TO *)grad_logits, B, Nv, Nq, heads, L, P, ref_dim,        \
+      (int64_t)off_row_stride, (int64_t)logit_row_stride)
   if (dtype == RSC_F32) {
     if (off_dtype == RSC_F32) MFB(float, float); else MFB(float, __nv_bfloat16);
   } else {

@@ -468,6 +468,9 @@ class MultiheadAttention(nn.Module):
 class MultiScaleDeformableAttention(nn.Module):
     """mmcv MultiScaleDeformableAttention; the sampling core is rsc_msda_{fwd,bwd}."""
 
+    # both read `query`: the step engine lays their parameters out back to back, one GEMM serves both (ops.linear_pair)
+    _rsc_linear_pairs = (('sampling_offsets', 'attention_weights'),)
+
     def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=4, im2col_step=64, dropout=0.1,
                  batch_first=False, norm_cfg=None, init_cfg=None):
         super().__init__()
@@ -542,6 +545,21 @@ class MultiScaleDeformableAttention(nn.Module):
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, self.num_heads, -1)
+        pv = self._pair_views()
+        if (ops.linear_pair_supported(query, pv) and reference_points is not None and
+                self.num_levels * self.num_points == 16 and self.embed_dims // self.num_heads == 32):
+            both = ops.linear_pair(query, self.sampling_offsets, self.attention_weights, pv)   # [offsets | logits]
+            if ops.msda_packed_supported(value, both, reference_points, self.num_levels, self.num_points):
+                output = ops.ms_deform_attn_fused_packed(value, spatial_shapes, level_start_index, both,
+                                                         reference_points, self.num_levels, self.num_points)
+                return self._project_out(output, identity, batch_first, kwargs)
+            n_off = self.sampling_offsets.out_features
+            sampling_offsets, attention_weights = both[..., :n_off], both[..., n_off:]
+            sampling_offsets = sampling_offsets.reshape(bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
+            attention_weights = attention_weights.reshape(bs, num_query, self.num_heads, self.num_levels * self.num_points)
+            output = self._sample_eager(value, sampling_offsets, attention_weights, reference_points, spatial_shapes,
+                                        level_start_index)
+            return self._project_out(output, identity, batch_first, kwargs)
         sampling_offsets = self.sampling_offsets(query).view(
             bs, num_query, self.num_heads, self.num_levels, self.num_points, 2)
         attention_weights = self.attention_weights(query).view(
@@ -553,6 +571,20 @@ class MultiScaleDeformableAttention(nn.Module):
         else:
             output = self._sample_eager(value, sampling_offsets, attention_weights, reference_points, spatial_shapes,
                                         level_start_index)
+        return self._project_out(output, identity, batch_first, kwargs)
+
+    def _pair_views(self):
+        """stacked parameter views for ops.linear_pair (None without the step engine's flat layout)"""
+        g = getattr(self.sampling_offsets.weight, '_rsc_g', None)
+        if g is None:
+            return None
+        key = (g.data_ptr(), self.sampling_offsets.weight.data_ptr())
+        cached = getattr(self, '_pair_cache', None)
+        if cached is None or cached[0] != key:
+            cached = self._pair_cache = (key, ops.linear_pair_views(self.sampling_offsets, self.attention_weights))
+        return cached[1]
+
+    def _project_out(self, output, identity, batch_first, kwargs):
         defer = kwargs.get('_defer', False) and not (self.training and self.dropout.p > 0.)
         output = ops.linear(output, self.output_proj.weight, None) if defer else self.output_proj(output)
         if not batch_first:

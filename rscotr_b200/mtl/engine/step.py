@@ -140,6 +140,7 @@ class StepEngine:
             return int(m.group(1) or m.group(2)) + 1 if m else 0
         order = [i for i in sorted(range(len(named)), key=lambda i: (rank(named[i][0]), sub(named[i][0]), i))
                  if named[i][1].requires_grad]
+        order = self._pair_linears(named, order)
         self._spans = []          # (name, start, end)
         off = 0
         for i in order:
@@ -219,6 +220,30 @@ class StepEngine:
                 dist.broadcast(b.data, src=0)
         self.sync_lp()
 
+    def _pair_linears(self, named, order):
+        """Sibling Linear layers that read the same input (a module lists them in `_rsc_linear_pairs`, e.g.
+        MultiScaleDeformableAttention: sampling_offsets / attention_weights) are laid out as
+        [weight1 | weight2 | bias1 | bias2], so that the stacked matrices are plain views of the flat buffers and ONE
+        GEMM serves both layers (ops.linear_pair).  Needs sizes that keep the 64-element alignment gap-free; anything
+        else is left as it was (the module then runs two GEMMs)."""
+        pos = {named[i][0]: k for k, i in enumerate(order)}
+        index = {n: i for i, (n, _) in enumerate(named)}
+        order = list(order)
+        for mod_name, mod in self.model.named_modules():
+            for a, b in getattr(mod, '_rsc_linear_pairs', ()):
+                pre = mod_name + '.' if mod_name else ''
+                names = [pre + a + '.weight', pre + b + '.weight', pre + a + '.bias', pre + b + '.bias']
+                if not all(n in pos for n in names):
+                    continue
+                ks = sorted(pos[n] for n in names)
+                if ks != list(range(ks[0], ks[0] + 4)):
+                    continue
+                if named[index[names[0]]][1].numel() % 64 or named[index[names[2]]][1].numel() % 64:
+                    continue
+                for k, n in zip(ks, names):
+                    order[k] = index[n]
+        return order
+
     def sync_lp(self):
         """refresh the bf16 shadow from the fp32 master weights (after init / load_state_dict / an optimizer
         other than the flat AdamW kernel)."""
@@ -233,6 +258,9 @@ class StepEngine:
         """autograd's per-parameter gradients -> flat buffer (one multi-tensor copy instead of one
         accumulate kernel per parameter); parameters the task did not touch keep their zero fill.
         `lo`, `hi`: only the parameters whose span starts inside that flat range."""
+        if self.device.type == 'cuda':
+            from ... import ops
+            ops.side_join(self.device)      # the small layers' dW / db branch (ops._SideBranch) is part of "backward is done"
         dst, src = [], []
         i0 = bisect.bisect_left(self._span_starts, lo)
         i1 = len(self._params) if hi is None else bisect.bisect_left(self._span_starts, hi)
@@ -405,10 +433,15 @@ class StepEngine:
                 outputs['loss'].backward()
             except BaseException:
                 self._pending = None
+                self._release_side()
                 raise
             self._exchange_grads(task)
         else:
-            outputs['loss'].backward()
+            try:
+                outputs['loss'].backward()
+            except BaseException:
+                self._release_side()
+                raise
             self._collect_grads()
         clip_coef = None
         if self.grad_clip:
@@ -427,6 +460,11 @@ class StepEngine:
             for p in self._params:
                 p.grad = None
             self.sync_lp()
+
+    def _release_side(self):
+        if self.device.type == 'cuda':
+            from ... import ops
+            ops.side_join(self.device)
 
     def _autocast(self):
         return torch.autocast('cuda', dtype=self.compute_dtype, enabled=self.compute_dtype != torch.float32)

@@ -463,7 +463,7 @@ class _MSDAFused(torch.autograd.Function):
         with torch.cuda.device(value.device):
             call('rsc_msda_fused_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                  logits.data_ptr(), ref.data_ptr(), out.data_ptr(), B, Nv, Nq, heads, L, P, ref.shape[-1], _dt(value),
-                 _dt(offsets), _stream(),
+                 _dt(offsets), 0, 0, _stream(),
                  alg_bytes=(value.numel() + out.numel()) * value.element_size() +
                  (offsets.numel() + logits.numel()) * offsets.element_size())
         ctx.save_for_backward(value, shapes, starts, offsets, logits, ref)
@@ -481,10 +481,59 @@ class _MSDAFused(torch.autograd.Function):
         with torch.cuda.device(value.device):
             call('rsc_msda_fused_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                  logits.data_ptr(), ref.data_ptr(), grad_output.data_ptr(), gv.data_ptr(), go.data_ptr(), gl.data_ptr(),
-                 B, Nv, Nq, heads, L, P, ref.shape[-1], _dt(value), _dt(offsets), _stream(),
+                 B, Nv, Nq, heads, L, P, ref.shape[-1], _dt(value), _dt(offsets), 0, 0, _stream(),
                  alg_bytes=(value.numel() + grad_output.numel()) * value.element_size() + 2 * value.numel() * 4 +
                  2 * (offsets.numel() + logits.numel()) * offsets.element_size())
         return gv.to(value.dtype), None, None, go, gl, None
+
+
+class _MSDAFusedPacked(torch.autograd.Function):
+    """_MSDAFused with the raw offsets and attention logits as column ranges of ONE matrix `both`
+    (B, Nq, heads*L*P*3) = [offsets | logits] -- the output of a single GEMM over the stacked sampling_offsets /
+    attention_weights weights (linear_pair); the kernels take row strides, and the backward writes both gradients
+    into one matrix for that GEMM's backward."""
+
+    @staticmethod
+    def forward(ctx, value, shapes, starts, both, ref, L, P):
+        _cuda(value, shapes, starts, both, ref)
+        B, Nv, heads, D = value.shape
+        Nq = both.shape[1]
+        n_off = heads * L * P * 2
+        W = both.shape[-1]
+        assert W == n_off + heads * L * P and both.is_contiguous()
+        value = value.contiguous()
+        ref = ref.float().contiguous()
+        shapes = shapes.to(torch.int64).contiguous()
+        starts = starts.to(torch.int64).contiguous()
+        out = torch.empty(B, Nq, heads * D, dtype=value.dtype, device=value.device)
+        es = both.element_size()
+        with torch.cuda.device(value.device):
+            call('rsc_msda_fused_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), both.data_ptr(),
+                 both.data_ptr() + n_off * es, ref.data_ptr(), out.data_ptr(), B, Nv, Nq, heads, L, P, ref.shape[-1],
+                 _dt(value), _dt(both), W, W, _stream(),
+                 alg_bytes=(value.numel() + out.numel()) * value.element_size() + both.numel() * es)
+        ctx.save_for_backward(value, shapes, starts, both, ref)
+        ctx.lp = (L, P)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        value, shapes, starts, both, ref = ctx.saved_tensors
+        L, P = ctx.lp
+        B, Nv, heads, D = value.shape
+        Nq, W = both.shape[1], both.shape[-1]
+        n_off = heads * L * P * 2
+        grad_output = grad_output.contiguous()
+        gv = torch.zeros(value.shape, dtype=torch.float32, device=value.device)
+        gboth = torch.empty_like(both)
+        es = both.element_size()
+        with torch.cuda.device(value.device):
+            call('rsc_msda_fused_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), both.data_ptr(),
+                 both.data_ptr() + n_off * es, ref.data_ptr(), grad_output.data_ptr(), gv.data_ptr(), gboth.data_ptr(),
+                 gboth.data_ptr() + n_off * es, B, Nv, Nq, heads, L, P, ref.shape[-1], _dt(value), _dt(both), W, W, _stream(),
+                 alg_bytes=(value.numel() + grad_output.numel()) * value.element_size() + 2 * value.numel() * 4 +
+                 2 * both.numel() * es)
+        return gv.to(value.dtype), None, None, gboth, None, None, None
 
 
 def msda_fused_supported(value, offsets, ref):
@@ -495,6 +544,17 @@ def msda_fused_supported(value, offsets, ref):
 
 def ms_deform_attn_fused(value, spatial_shapes, level_start_index, offsets, logits, reference_points):
     return _MSDAFused.apply(value, spatial_shapes, level_start_index, offsets, logits, reference_points)
+
+
+def ms_deform_attn_fused_packed(value, spatial_shapes, level_start_index, both, reference_points, num_levels, num_points):
+    """`both` (B, Nq, heads*L*P*3) = [raw offsets | attention logits] of linear_pair"""
+    return _MSDAFusedPacked.apply(value, spatial_shapes, level_start_index, both, reference_points, num_levels, num_points)
+
+
+def msda_packed_supported(value, both, ref, num_levels, num_points):
+    return (value.is_cuda and value.shape[-1] == 32 and value.shape[-2] % 4 == 0 and num_levels * num_points == 16 and
+            ref.shape[-1] in (2, 4) and not ref.requires_grad and value.dtype in (torch.float32, torch.bfloat16) and
+            both.dtype in (torch.float32, torch.bfloat16) and both.shape[-1] == value.shape[-2] * 48)
 
 
 def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step=64):
@@ -862,25 +922,106 @@ def _accumulate_dw(dy2, x2, gw, gb, wdt, bdt, wshape, want_db):
         tb = None
         if want_db:
             tb = gb if gb is not None else torch.zeros(N, dtype=torch.float32, device=dy2.device)
+        if gw is not None:
+            _side_sync_writer(gw)
         gemm_dw(dy2, x2, tw, tb)
         if gw is None:
             dw = tw.to(wdt).view(wshape)
         if want_db and gb is None:
             db = tb.to(bdt)
         return dw, db
+    if gw is not None and (gb is not None or not want_db) and _side_ok(dy2):
+        # engine mode, small layer: nothing downstream in backward reads dW / db, so both launches leave the critical
+        # path (a parallel branch of the step's CUDA graph); the step engine joins before it reads the flat buffer
+        with _SideBranch(dy2, x2, gw, gb):
+            _addmm_into(gw, dy2, x2)
+            if want_db:
+                colsum(dy2, out=gb)
+        return None, None
     if gw is not None:
-        if dy2.dtype == torch.float32:
-            torch.addmm(gw, dy2.t(), x2, out=gw)
-        else:
-            torch.addmm(gw, dy2.t(), x2, out_dtype=torch.float32, out=gw)
+        _side_sync_writer(gw)
+        _addmm_into(gw, dy2, x2)
     else:
         dw = torch.mm(dy2.t(), x2).to(wdt).view(wshape)
     if want_db:
         if gb is not None:
+            _side_sync_writer(gb)
             colsum(dy2, out=gb)
         else:
             db = colsum(dy2).to(bdt)
     return dw, db
+
+
+def _addmm_into(gw, dy2, x2):
+    if dy2.dtype == torch.float32:
+        torch.addmm(gw, dy2.t(), x2, out=gw)
+    else:
+        torch.addmm(gw, dy2.t(), x2, out_dtype=torch.float32, out=gw)
+
+
+# ---- side branch for the parameter gradients of the small Linear layers -----------------------------------
+# The det / seg steps are launch-latency-bound (1650 / 1370 kernels of a few microseconds each, every one waiting for
+# its predecessor on the single compute stream).  The weight / bias gradients of the decoders' and heads' small Linear
+# layers (library GEMM with beta = 1 into the flat fp32 gradient buffer + rsc_colsum) have no consumer until the
+# optimizer, so they run on a second stream: forked from the compute stream when dY exists, joined by the step engine
+# (side_join) before it touches the gradients.  Inside a captured step this is a parallel branch of the CUDA graph.
+# The operands are kept alive until the join, so the caching allocator cannot hand their memory to a later kernel on the
+# compute stream while the side stream still reads it.  RSC_SIDE_DW=0 keeps everything on the compute stream.
+_SIDE_DW = __import__('os').environ.get('RSC_SIDE_DW', '1') != '0'
+_SIDE_MAX_KEEP = 4096         # (safety valve: operands held by an un-joined branch, e.g. autograd use without the step engine)
+_side_state = {}              # device index -> dict(stream, keep, writes)
+
+
+def _side_ok(t):
+    return _SIDE_DW and t.is_cuda
+
+
+class _SideBranch:
+    """`with _SideBranch(*tensors):` -- the body's launches go to the device's side stream, after everything enqueued so
+    far on the current stream; `tensors` (operands and destinations) are held until side_join()."""
+
+    def __init__(self, *tensors):
+        self.tensors = tensors
+        dev = tensors[0].device
+        st = _side_state.get(dev.index)
+        if st is None:
+            st = _side_state[dev.index] = dict(stream=torch.cuda.Stream(dev), keep=[], writes=set(), device=dev)
+        self.st = st
+
+    def __enter__(self):
+        st = self.st
+        if len(st['keep']) >= _SIDE_MAX_KEEP:
+            side_join(st['device'])
+        st['stream'].wait_stream(torch.cuda.current_stream(st['device']))
+        st['keep'].append(self.tensors)
+        for t in self.tensors[2:]:
+            if t is not None:
+                st['writes'].add(t.data_ptr())
+        self.ctx = torch.cuda.stream(st['stream'])
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self.ctx.__exit__(*exc)
+
+
+def _side_sync_writer(dst):
+    """a compute-stream accumulation into a gradient the side stream may still be adding to: join first"""
+    if dst.is_cuda:
+        st = _side_state.get(dst.device.index)
+        if st is not None and dst.data_ptr() in st['writes']:
+            side_join(dst.device)
+
+
+def side_join(device=None):
+    """the current stream waits for the side branches (all devices, or `device`); their operands are released"""
+    for idx, st in _side_state.items():
+        if device is not None and torch.device(device).index not in (None, idx):
+            continue
+        if st['keep']:
+            torch.cuda.current_stream(st['device']).wait_stream(st['stream'])
+            st['keep'].clear()
+            st['writes'].clear()
 
 
 # RSC_SMALL_BWD=1: the small layers' backward (dX, dW +=, db +=) as ONE launch of rsc_small_linear_bwd instead of the library's
@@ -945,6 +1086,7 @@ class _Linear(torch.autograd.Function):
             K = w.shape[1]
             if ctx.needs_input_grad[0]:
                 dx = torch.empty(M, K, dtype=torch.bfloat16, device=dy2.device)
+            _side_sync_writer(gw)
             with torch.cuda.device(dy2.device):
                 call('rsc_small_linear_bwd', dy2.data_ptr(), x2.data_ptr(), w.data_ptr(), _p(dx), gw.data_ptr(), _p(gb), M, N, K,
                      dy2.stride(0), x2.stride(0), w.stride(0), K, gw.stride(0), _stream(),
@@ -959,11 +1101,95 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw, db = _accumulate_dw(dy2, x2, gw, gb, wdt, bdt, ctx.wshape, want_db)
         elif want_db:
-            if gb is not None:
+            if gb is not None and _side_ok(dy2):
+                with _SideBranch(dy2, None, gb):
+                    colsum(dy2, out=gb)
+            elif gb is not None:
                 colsum(dy2, out=gb)
             else:
                 db = colsum(dy2).to(bdt)
         return dx, dw, db, None, None, None, None
+
+
+class _LinearPair(torch.autograd.Function):
+    """[y1 | y2] = x [W1; W2]^T + [b1; b2] as ONE GEMM each way: two sibling Linear layers that read the same input
+    (mmcv MultiScaleDeformableAttention.sampling_offsets / attention_weights, ops/multi_scale_deform_attn.py) whose
+    parameters the step engine laid out back to back in its flat buffers (StepEngine._pair_linears), so the stacked
+    weight / bias / gradient matrices are plain views.  weight1 .. bias2 only tie the node to the parameters;
+    `pv` = dict(w, b: fp32 masters | w_lp, b_lp: bf16 shadows | gw, gb: fp32 gradient views), all stacked."""
+
+    @staticmethod
+    def forward(ctx, x, weight1, bias1, weight2, bias2, pv):
+        x2 = x.reshape(-1, x.shape[-1])
+        lp = x.dtype == torch.bfloat16
+        w = pv['w_lp'] if lp else pv['w']
+        if _tc_linear_ok(x2, w) and _own_plain(x2.shape[1]):
+            y = gemm_fwd(x2, w, pv['b'], 0)[0]
+        else:
+            y = torch.nn.functional.linear(x2, w, pv['b_lp'] if lp else pv['b'])
+        ctx.save_for_backward(x, w)
+        ctx.pv = pv
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        pv = ctx.pv
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        x2 = x.reshape(-1, x.shape[-1])
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if _tc_linear_ok(dy2, w) and w.shape[1] % 8 == 0 and _own_plain(dy2.shape[1]):
+                dx = gemm_dx(dy2, w).view(x.shape)
+            else:
+                dx = torch.mm(dy2, w).view(x.shape)
+        _accumulate_dw(dy2, x2, pv['gw'], pv['gb'], None, None, None, True)
+        return dx, None, None, None, None, None
+
+
+def linear_pair_views(m1, m2):
+    """the stacked views for _LinearPair if the step engine placed m1 / m2's parameters back to back, else None"""
+    ps = (m1.weight, m2.weight, m1.bias, m2.bias)
+    if any(p is None or not p.requires_grad for p in ps):
+        return None
+
+    def stacked(a, b, attr):
+        ta, tb = (getattr(p, attr, None) if attr else p.data for p in (a, b))
+        if ta is None or tb is None or not (ta.is_contiguous() and tb.is_contiguous()) or ta.dtype != tb.dtype:
+            return None
+        if tb.data_ptr() != ta.data_ptr() + ta.numel() * ta.element_size() or ta.shape[1:] != tb.shape[1:]:
+            return None
+        # one view over both: as_strided on the first tensor (same storage -- the engine's flat buffer)
+        shape = (ta.shape[0] + tb.shape[0],) + tuple(ta.shape[1:])
+        return ta.as_strided(shape, ta.stride(), ta.storage_offset())
+
+    pv = dict(w=stacked(m1.weight, m2.weight, None), b=stacked(m1.bias, m2.bias, None),
+              w_lp=stacked(m1.weight, m2.weight, '_rsc_lp'), b_lp=stacked(m1.bias, m2.bias, '_rsc_lp'),
+              gw=stacked(m1.weight, m2.weight, '_rsc_g'), gb=stacked(m1.bias, m2.bias, '_rsc_g'))
+    if pv['w'] is None or pv['b'] is None or pv['gw'] is None or pv['gb'] is None:
+        return None
+    return pv
+
+
+# RSC_LINEAR_PAIR=0: sampling_offsets / attention_weights as two GEMMs again (A/B switch)
+_LINEAR_PAIR = __import__('os').environ.get('RSC_LINEAR_PAIR', '1') != '0'
+
+
+def linear_pair(x, m1, m2, pv):
+    if torch.is_autocast_enabled('cuda') and x.is_cuda:
+        x = x.to(torch.get_autocast_dtype('cuda'))
+    return _LinearPair.apply(x, m1.weight, m1.bias, m2.weight, m2.bias, pv)
+
+
+def linear_pair_supported(x, pv):
+    if not (_LINEAR_PAIR and pv is not None and x.is_cuda and torch.is_grad_enabled()):
+        return False
+    dt = torch.get_autocast_dtype('cuda') if torch.is_autocast_enabled('cuda') else x.dtype
+    if dt == torch.bfloat16:
+        return pv['w_lp'] is not None and pv['b_lp'] is not None
+    return dt == torch.float32
 
 
 class _MLP(torch.autograd.Function):

@@ -238,3 +238,51 @@ def test_small_linear_backward_one_launch(M, N, K, want):
         assert rel(dbc, want_db) < 1e-3
     else:
         assert torch.equal(dbc.cpu(), db0)
+
+
+@pytest.mark.parametrize('M', [300, 5000, 13294])
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+def test_linear_pair_one_gemm_for_two_sibling_layers(M, dtype):
+    """ops.linear_pair: sampling_offsets (256 -> 256) and attention_weights (256 -> 128) of mmcv
+    MultiScaleDeformableAttention as ONE GEMM over parameter views stacked in flat buffers (the layout
+    StepEngine._pair_linears produces), forward and backward, against the two separate fp32 Linears.  M = 300 takes the
+    library GEMM + the side-stream dW / db branch, M >= 4096 the tcgen05 kernels."""
+    from rscotr_b200 import ops
+    g = torch.Generator().manual_seed(M)
+    K, N1, N2 = 256, 256, 128
+    sizes = [N1 * K, N2 * K, N1, N2]
+    total = sum(sizes)
+    flat = (torch.randn(total, generator=g) * 0.06).cuda()
+    flat_lp = flat.bfloat16()
+    flat_g = torch.zeros(total, device='cuda')
+    m1, m2 = torch.nn.Linear(K, N1).cuda(), torch.nn.Linear(K, N2).cuda()
+    offs = [0, N1 * K, (N1 + N2) * K, (N1 + N2) * K + N1]
+    for p, o, n in zip((m1.weight, m2.weight, m1.bias, m2.bias), offs, sizes):
+        p.data = flat[o:o + n].view_as(p)
+        p._rsc_lp = flat_lp[o:o + n].view_as(p)
+        p._rsc_g = flat_g[o:o + n].view_as(p)
+    pv = ops.linear_pair_views(m1, m2)
+    assert pv is not None and pv['w_lp'].shape == (N1 + N2, K) and pv['gb'].shape == (N1 + N2,)
+    x = torch.randn(2, M // 2, K, generator=g).to(dtype).cuda().requires_grad_(True)
+    assert ops.linear_pair_supported(x, pv)
+    wy = torch.randn(2, M // 2, N1 + N2, generator=g).cuda()
+    y = ops.linear_pair(x, m1, m2, pv)
+    assert y.shape == (2, M // 2, N1 + N2) and y.dtype == dtype
+    (y.float() * wy).sum().backward()
+    ops.side_join()
+    torch.cuda.synchronize()
+    # fp32 reference on the operands the GEMM read
+    wsrc = flat_lp.float() if dtype == torch.bfloat16 else flat
+    W = wsrc[:(N1 + N2) * K].view(N1 + N2, K).cpu()
+    b = flat[(N1 + N2) * K:].cpu()
+    xr = x.detach().float().cpu().requires_grad_(True)
+    Wr, br = W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.linear(xr, Wr, br)
+    dy = wy.cpu().to(dtype).float()        # the gradient arrives in the compute dtype
+    (yr * dy).sum().backward()
+    lo = dtype == torch.bfloat16
+    assert rel(y, yr) < (4e-3 if lo else 1e-5)
+    assert rel(x.grad, xr.grad) < (4e-3 if lo else 1e-5)
+    assert rel(flat_g[:(N1 + N2) * K].view(N1 + N2, K), Wr.grad) < (4e-3 if lo else 1e-4)
+    assert rel(flat_g[(N1 + N2) * K:], br.grad) < (4e-3 if lo else 1e-4)
+    assert m1.weight.grad is None and m2.bias.grad is None           # autograd saw no parameter gradient

@@ -142,6 +142,49 @@ def test_cuda_graph_replay_matches_eager(task):
         assert rel(p1[n], p0[n]) < 1e-4, n
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('task', ['det', 'seg'])
+def test_side_branch_and_linear_pair_leave_the_gradients_unchanged(task, dtype, monkeypatch):
+    """Two scheduling changes of the det / seg steps must not change what is computed: (1) the small Linear layers'
+    dW / db on a side stream (ops._SideBranch, joined by the step engine), (2) sampling_offsets + attention_weights
+    as ONE GEMM over stacked parameter views (ops.linear_pair + the row-strided fused ms_deform_attn).  Same model,
+    same batch, switches on vs off: losses and the whole flat gradient buffer, eagerly and through a captured graph."""
+    from rscotr_b200 import ops
+    from rscotr_b200.mtl.engine import StepEngine
+    res = []
+    for on in (True, False):
+        monkeypatch.setattr(ops, '_SIDE_DW', on)
+        monkeypatch.setattr(ops, '_LINEAR_PAIR', on)
+        model, batch = _setup(task, seed=11)
+        if task == 'det':
+            noise = oh.cdn_noise(batch['gt_labels'], num_dn=10, generator=torch.Generator().manual_seed(5))
+            model.bbox_head.dn_generator.forced_noise = {k: v.cuda() for k, v in noise.items()}
+        eng = StepEngine(model, dict(type='SGD', lr=0.0), grad_clip=dict(max_norm=0.1, norm_type=2), device='cuda',
+                         compute_dtype=dtype, use_graphs=True)
+        if on:
+            from rscotr_b200.models.bricks import MultiScaleDeformableAttention
+            msda = [m for m in model.modules() if isinstance(m, MultiScaleDeformableAttention)]
+            assert msda and all(m._pair_views() is not None for m in msda)
+        ops.reset_launch_count()
+        grads, losses = [], []
+        for _ in range(4):                      # 2 eager warm-up iterations, then capture + replay (lr = 0: same step)
+            losses.append(float(eng.train_iter(batch)['loss'].detach()))
+            torch.cuda.synchronize()
+            grads.append(eng.flat_grad.clone())
+        assert eng.replayed_launches > 0
+        assert not any(st['keep'] for st in ops._side_state.values())        # every branch was joined
+        res.append((losses, grads, {n: (s0, e0) for n, s0, e0 in eng._spans}))
+    (l_on, g_on, sp_on), (l_off, g_off, sp_off) = res
+    assert sp_on == sp_off
+    tol = 2e-4 if dtype == torch.float32 else 5e-2
+    for a, b in zip(l_on, l_off):
+        assert abs(a - b) <= tol * max(1.0, abs(b)), (l_on, l_off)
+    for k, (a, b) in enumerate(zip(g_on, g_off)):
+        assert rel(a, b) < tol, (k, rel(a, b))
+    for a in g_on[1:]:                          # eager and replayed steps of the same variant agree as well
+        assert rel(a, g_on[0]) < tol
+
+
 def test_flat_adamw_matches_torch():
     """rsc_adamw_step (flat, fused clip) == clip_grad_norm_ + torch.optim.AdamW with the same groups."""
     import copy

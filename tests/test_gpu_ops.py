@@ -260,6 +260,34 @@ def test_patch_merge_ln(B, H, W, C, dtype):
     assert_rel(bg.grad, sd['d.norm.bias'].grad, tol, 'dbeta')
 
 
+@pytest.mark.parametrize('B,H,W,C', [(2, 151, 151, 96), (1, 151, 149, 192), (1, 100, 100, 384)])
+def test_patch_merge_ln_persistent_loop(B, H, W, C):
+    """more tokens than one pass of the resident warps covers (several TPW-token steps per warp, a ragged last step) and
+    odd H / W (the zero-padded last row / column of mmdet's PatchMerging), bf16, against the fp32 oracle; the round-1
+    kernels (RSC_PATCH_MERGE_V1) are held to the same numbers by test_patch_merge_ln."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, H * W, C, generator=g).bfloat16().float()
+    gamma = 1 + 0.1 * torch.randn(4 * C, generator=g)
+    beta = 0.1 * torch.randn(4 * C, generator=g)
+    sd = {'d.norm.weight': gamma.clone().requires_grad_(True), 'd.norm.bias': beta.clone().requires_grad_(True),
+          'd.reduction.weight': torch.eye(4 * C).requires_grad_(True)}          # (identity: the LayerNorm output itself)
+    xo = x.clone().requires_grad_(True)
+    yo, hw = osw.patch_merging(sd, 'd.', xo, (H, W))
+    gy = torch.randn(yo.shape, generator=g).bfloat16().float()
+    yo.backward(gy)
+    xg = x.clone().cuda().bfloat16().requires_grad_(True)
+    gg, bg = gamma.clone().cuda().requires_grad_(True), beta.clone().cuda().requires_grad_(True)
+    y = ops.patch_merge_ln(xg, (H, W), gg, bg)
+    y.backward(gy.cuda().bfloat16())
+    assert tuple(y.shape) == tuple(yo.shape)
+    assert_rel(y, yo, 4e-3, 'y')
+    assert (y.float().cpu() - yo).abs().max() <= 2 ** -7 * yo.abs().max()     # every token was written (bf16 rounding only)
+    assert_rel(xg.grad, xo.grad, 6e-3, 'dx')
+    assert_rel(gg.grad, sd['d.norm.weight'].grad, 2e-3, 'dgamma')
+    assert_rel(bg.grad, sd['d.norm.bias'].grad, 2e-3, 'dbeta')
+
+
 # ---------------------------------------------------------------------------
 # a11: ms_deform_attn
 # ---------------------------------------------------------------------------
@@ -767,6 +795,68 @@ def test_msda_fused_matches_oracle_chain(ref_dim, dtype):
     assert_rel(gv.grad, rv.grad, 1e-4 if f32 else 1e-2, 'd value')
     assert_rel(go.grad, ro.grad, 1e-4 if f32 else 1.5e-2, 'd offsets')
     assert_rel(gl.grad, rl.grad, 1e-4 if f32 else 1.5e-2, 'd logits')
+
+
+@pytest.mark.parametrize('ref_dim', [2, 4])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_msda_fused_packed_rows_match_oracle_chain(ref_dim, dtype):
+    """the same kernels with ROW STRIDES: offsets and logits as column ranges of one (B, Nq, 384) matrix (the output of
+    the single GEMM over the stacked sampling_offsets / attention_weights weights), both gradients into one matrix.
+    Compared with the oracle chain and, bit for bit, with the dense-row call."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(17 + ref_dim)
+    shapes = [(11, 13), (6, 7), (3, 4), (2, 2)]
+    B, heads, L, P = 2, 8, 4, 4
+    Nv = sum(h * w for h, w in shapes)
+    Nq = 53
+    value = torch.randn(B, Nv, heads, 32, generator=g).to(dtype)
+    both = torch.randn(B, Nq, heads * L * P * 3, generator=g)
+    both[..., :heads * L * P * 2] *= 3
+    both = both.to(dtype)
+    n_off = heads * L * P * 2
+    ref = torch.rand(B, Nq, L, ref_dim, generator=g)
+    if ref_dim == 4:
+        ref[..., 2:] = ref[..., 2:] * 0.5 + 0.05
+    wout = torch.randn(B, Nq, heads * 32, generator=g)
+    rv, rb = (t.float().clone().requires_grad_(True) for t in (value, both))
+    ro = rb[..., :n_off].reshape(B, Nq, heads, L, P, 2)
+    aw = rb[..., n_off:].reshape(B, Nq, heads, L * P).softmax(-1).view(B, Nq, heads, L, P)
+    if ref_dim == 2:
+        norm = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32)
+        loc = ref[:, :, None, :, None, :] + ro / norm[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None, :, None, :2] + ro / P * ref[:, :, None, :, None, 2:] * 0.5
+    want = otr.ms_deform_attn_core(rv, shapes, loc, aw)
+    (want * wout).sum().backward()
+    ss = torch.tensor(shapes).cuda()
+    st = torch.tensor([0] + list(torch.tensor([h * w for h, w in shapes]).cumsum(0)[:-1])).cuda()
+    gv, gb = (t.detach().cuda().requires_grad_(True) for t in (value, both))
+    assert ops.msda_packed_supported(gv, gb, ref.cuda(), L, P)
+    got = ops.ms_deform_attn_fused_packed(gv, ss, st, gb, ref.cuda(), L, P)
+    (got.float() * wout.cuda()).sum().backward()
+    f32 = dtype == torch.float32
+    assert_rel(got, want, 1e-5 if f32 else 6e-3, 'out')
+    assert_rel(gv.grad, rv.grad, 1e-4 if f32 else 1e-2, 'd value')
+    assert_rel(gb.grad[..., :n_off], rb.grad[..., :n_off], 1e-4 if f32 else 1.5e-2, 'd offsets')
+    assert_rel(gb.grad[..., n_off:], rb.grad[..., n_off:], 1e-4 if f32 else 1.5e-2, 'd logits')
+    # dense rows: same arithmetic, so the same bits (the value gradient is an atomic sum: tolerance)
+    dv = value.cuda().requires_grad_(True)
+    do = both[..., :n_off].reshape(B, Nq, heads, L, P, 2).contiguous().cuda().requires_grad_(True)
+    dl = both[..., n_off:].reshape(B, Nq, heads, L * P).contiguous().cuda().requires_grad_(True)
+    dense = ops.ms_deform_attn_fused(dv, ss, st, do, dl, ref.cuda())
+    (dense.float() * wout.cuda()).sum().backward()
+    assert torch.equal(dense, got)
+    assert torch.equal(do.grad.reshape(B, Nq, -1), gb.grad[..., :n_off])
+    assert torch.equal(dl.grad.reshape(B, Nq, -1), gb.grad[..., n_off:])
+    assert_rel(dv.grad, gv.grad, 1e-5 if f32 else 1e-2, 'd value, dense vs packed')
+
+
+def test_msda_fused_rejects_short_row_strides():
+    from rscotr_b200 import _lib
+    z = torch.zeros(8, device='cuda')
+    with pytest.raises(RuntimeError, match='row strides'):
+        _lib.call('rsc_msda_fused_fwd', z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(),
+                  z.data_ptr(), 1, 4, 1, 8, 4, 4, 2, 0, 0, 100, 0, 0)
 
 
 # ---------------------------------------------------------------------------

@@ -95,6 +95,42 @@ def test_step_engine_flat_layout_and_cpu_prefetch_noop():
     eng.prefetch(dict(task='cls'))                 # no copy stream on CPU: must be a no-op, not an error
 
 
+def test_step_engine_pairs_sibling_linears():
+    """StepEngine._pair_linears: sampling_offsets / attention_weights of every MultiScaleDeformableAttention sit back to
+    back in the flat buffers ([w1 | w2 | b1 | b2]), so ops.linear_pair_views returns stacked VIEWS (one GEMM serves both
+    layers); values and gradient aliasing checked here, the GEMM itself in the -m gpu tests."""
+    from rscotr_b200 import ops
+    from rscotr_b200.config import MODELS
+    from rscotr_b200.models.bricks import MultiScaleDeformableAttention
+    from rscotr_b200.mtl.engine import StepEngine
+    from tests.test_host_model import small_cfg
+    torch.manual_seed(0)
+    model = MODELS.build(small_cfg().model)
+    model.init_weights()
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    eng = StepEngine(model, dict(type='AdamW', lr=1e-3, weight_decay=1e-4), device='cpu',
+                     compute_dtype=torch.float32, use_graphs=False)
+    for n, p in model.named_parameters():              # the re-ordering moved no values
+        assert torch.equal(p.detach(), before[n]), n
+    mods = [m for m in model.modules() if isinstance(m, MultiScaleDeformableAttention)]
+    assert mods
+    for m in mods:
+        pv = ops.linear_pair_views(m.sampling_offsets, m.attention_weights)
+        assert pv is not None and pv['w_lp'] is None          # (the bf16 shadow exists on CUDA only)
+        n1, n2 = m.sampling_offsets.out_features, m.attention_weights.out_features
+        assert pv['w'].shape == (n1 + n2, m.embed_dims) and pv['b'].shape == (n1 + n2,)
+        assert torch.equal(pv['w'], torch.cat([m.sampling_offsets.weight.detach(), m.attention_weights.weight.detach()]))
+        assert torch.equal(pv['b'], torch.cat([m.sampling_offsets.bias.detach(), m.attention_weights.bias.detach()]))
+        pv['gw'].fill_(1.0)
+        pv['gb'].fill_(2.0)
+        for lin in (m.sampling_offsets, m.attention_weights):
+            assert float(eng.grad_view(lin.weight).min()) == 1.0 and float(eng.grad_view(lin.bias).min()) == 2.0
+        assert m._pair_views() is not None
+    eng.flat_grad.zero_()
+    # parameters that are NOT adjacent (any other two Linears) give no views
+    assert ops.linear_pair_views(mods[0].value_proj, mods[0].output_proj) is None
+
+
 def test_eval_hook_on_synthetic_loaders():
     """MultiDatasetsEvalHook / single_gpu_test over the synthetic val loaders (what a GPU box without data runs)."""
     from rscotr_b200.config import MODELS
