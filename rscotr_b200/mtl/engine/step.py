@@ -258,9 +258,6 @@ class StepEngine:
         """autograd's per-parameter gradients -> flat buffer (one multi-tensor copy instead of one
         accumulate kernel per parameter); parameters the task did not touch keep their zero fill.
         `lo`, `hi`: only the parameters whose span starts inside that flat range."""
-        if self.device.type == 'cuda':
-            from ... import ops
-            ops.side_join(self.device)      # the small layers' dW / db branch (ops._SideBranch) is part of "backward is done"
         dst, src = [], []
         i0 = bisect.bisect_left(self._span_starts, lo)
         i1 = len(self._params) if hi is None else bisect.bisect_left(self._span_starts, hi)
@@ -433,15 +430,10 @@ class StepEngine:
                 outputs['loss'].backward()
             except BaseException:
                 self._pending = None
-                self._release_side()
                 raise
             self._exchange_grads(task)
         else:
-            try:
-                outputs['loss'].backward()
-            except BaseException:
-                self._release_side()
-                raise
+            outputs['loss'].backward()
             self._collect_grads()
         clip_coef = None
         if self.grad_clip:
@@ -460,11 +452,6 @@ class StepEngine:
             for p in self._params:
                 p.grad = None
             self.sync_lp()
-
-    def _release_side(self):
-        if self.device.type == 'cuda':
-            from ... import ops
-            ops.side_join(self.device)
 
     def _autocast(self):
         return torch.autocast('cuda', dtype=self.compute_dtype, enabled=self.compute_dtype != torch.float32)

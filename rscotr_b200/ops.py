@@ -922,30 +922,18 @@ def _accumulate_dw(dy2, x2, gw, gb, wdt, bdt, wshape, want_db):
         tb = None
         if want_db:
             tb = gb if gb is not None else torch.zeros(N, dtype=torch.float32, device=dy2.device)
-        if gw is not None:
-            _side_sync_writer(gw)
         gemm_dw(dy2, x2, tw, tb)
         if gw is None:
             dw = tw.to(wdt).view(wshape)
         if want_db and gb is None:
             db = tb.to(bdt)
         return dw, db
-    if gw is not None and (gb is not None or not want_db) and _side_ok(dy2):
-        # engine mode, small layer: nothing downstream in backward reads dW / db, so both launches leave the critical
-        # path (a parallel branch of the step's CUDA graph); the step engine joins before it reads the flat buffer
-        with _SideBranch(dy2, x2, gw, gb):
-            _addmm_into(gw, dy2, x2)
-            if want_db:
-                colsum(dy2, out=gb)
-        return None, None
     if gw is not None:
-        _side_sync_writer(gw)
         _addmm_into(gw, dy2, x2)
     else:
         dw = torch.mm(dy2.t(), x2).to(wdt).view(wshape)
     if want_db:
         if gb is not None:
-            _side_sync_writer(gb)
             colsum(dy2, out=gb)
         else:
             db = colsum(dy2).to(bdt)
@@ -957,71 +945,6 @@ def _addmm_into(gw, dy2, x2):
         torch.addmm(gw, dy2.t(), x2, out=gw)
     else:
         torch.addmm(gw, dy2.t(), x2, out_dtype=torch.float32, out=gw)
-
-
-# ---- side branch for the parameter gradients of the small Linear layers -----------------------------------
-# The det / seg steps are launch-latency-bound (1650 / 1370 kernels of a few microseconds each, every one waiting for
-# its predecessor on the single compute stream).  The weight / bias gradients of the decoders' and heads' small Linear
-# layers (library GEMM with beta = 1 into the flat fp32 gradient buffer + rsc_colsum) have no consumer until the
-# optimizer, so they run on a second stream: forked from the compute stream when dY exists, joined by the step engine
-# (side_join) before it touches the gradients.  Inside a captured step this is a parallel branch of the CUDA graph.
-# The operands are kept alive until the join, so the caching allocator cannot hand their memory to a later kernel on the
-# compute stream while the side stream still reads it.  RSC_SIDE_DW=0 keeps everything on the compute stream.
-_SIDE_DW = __import__('os').environ.get('RSC_SIDE_DW', '1') != '0'
-_SIDE_MAX_KEEP = 4096         # (safety valve: operands held by an un-joined branch, e.g. autograd use without the step engine)
-_side_state = {}              # device index -> dict(stream, keep, writes)
-
-
-def _side_ok(t):
-    return _SIDE_DW and t.is_cuda
-
-
-class _SideBranch:
-    """`with _SideBranch(*tensors):` -- the body's launches go to the device's side stream, after everything enqueued so
-    far on the current stream; `tensors` (operands and destinations) are held until side_join()."""
-
-    def __init__(self, *tensors):
-        self.tensors = tensors
-        dev = tensors[0].device
-        st = _side_state.get(dev.index)
-        if st is None:
-            st = _side_state[dev.index] = dict(stream=torch.cuda.Stream(dev), keep=[], writes=set(), device=dev)
-        self.st = st
-
-    def __enter__(self):
-        st = self.st
-        if len(st['keep']) >= _SIDE_MAX_KEEP:
-            side_join(st['device'])
-        st['stream'].wait_stream(torch.cuda.current_stream(st['device']))
-        st['keep'].append(self.tensors)
-        for t in self.tensors[2:]:
-            if t is not None:
-                st['writes'].add(t.data_ptr())
-        self.ctx = torch.cuda.stream(st['stream'])
-        self.ctx.__enter__()
-        return self
-
-    def __exit__(self, *exc):
-        return self.ctx.__exit__(*exc)
-
-
-def _side_sync_writer(dst):
-    """a compute-stream accumulation into a gradient the side stream may still be adding to: join first"""
-    if dst.is_cuda:
-        st = _side_state.get(dst.device.index)
-        if st is not None and dst.data_ptr() in st['writes']:
-            side_join(dst.device)
-
-
-def side_join(device=None):
-    """the current stream waits for the side branches (all devices, or `device`); their operands are released"""
-    for idx, st in _side_state.items():
-        if device is not None and torch.device(device).index not in (None, idx):
-            continue
-        if st['keep']:
-            torch.cuda.current_stream(st['device']).wait_stream(st['stream'])
-            st['keep'].clear()
-            st['writes'].clear()
 
 
 # RSC_SMALL_BWD=1: the small layers' backward (dX, dW +=, db +=) as ONE launch of rsc_small_linear_bwd instead of the library's
@@ -1086,7 +1009,6 @@ class _Linear(torch.autograd.Function):
             K = w.shape[1]
             if ctx.needs_input_grad[0]:
                 dx = torch.empty(M, K, dtype=torch.bfloat16, device=dy2.device)
-            _side_sync_writer(gw)
             with torch.cuda.device(dy2.device):
                 call('rsc_small_linear_bwd', dy2.data_ptr(), x2.data_ptr(), w.data_ptr(), _p(dx), gw.data_ptr(), _p(gb), M, N, K,
                      dy2.stride(0), x2.stride(0), w.stride(0), K, gw.stride(0), _stream(),
@@ -1101,10 +1023,7 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw, db = _accumulate_dw(dy2, x2, gw, gb, wdt, bdt, ctx.wshape, want_db)
         elif want_db:
-            if gb is not None and _side_ok(dy2):
-                with _SideBranch(dy2, None, gb):
-                    colsum(dy2, out=gb)
-            elif gb is not None:
+            if gb is not None:
                 colsum(dy2, out=gb)
             else:
                 db = colsum(dy2).to(bdt)

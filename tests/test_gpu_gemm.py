@@ -246,7 +246,7 @@ def test_linear_pair_one_gemm_for_two_sibling_layers(M, dtype):
     """ops.linear_pair: sampling_offsets (256 -> 256) and attention_weights (256 -> 128) of mmcv
     MultiScaleDeformableAttention as ONE GEMM over parameter views stacked in flat buffers (the layout
     StepEngine._pair_linears produces), forward and backward, against the two separate fp32 Linears.  M = 300 takes the
-    library GEMM + the side-stream dW / db branch, M >= 4096 the tcgen05 kernels."""
+    library GEMMs, M >= 4096 the tcgen05 kernels."""
     from rscotr_b200 import ops
     g = torch.Generator().manual_seed(M)
     K, N1, N2 = 256, 256, 128
@@ -269,7 +269,6 @@ def test_linear_pair_one_gemm_for_two_sibling_layers(M, dtype):
     y = ops.linear_pair(x, m1, m2, pv)
     assert y.shape == (2, M // 2, N1 + N2) and y.dtype == dtype
     (y.float() * wy).sum().backward()
-    ops.side_join()
     torch.cuda.synchronize()
     # fp32 reference on the operands the GEMM read
     wsrc = flat_lp.float() if dtype == torch.bfloat16 else flat

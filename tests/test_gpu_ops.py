@@ -704,6 +704,34 @@ def test_add_ln_matches_eager(C, dtype, with_scale):
         assert_rel(got.grad, want.grad, 2e-4 if dtype == torch.float32 else 2e-2, what)
 
 
+@pytest.mark.parametrize('C,L', [(96, 200003), (192, 35003), (256, 13294), (384, 20001)])
+def test_add_ln_many_rows(C, L):
+    """more rows than one pass of the resident warps covers (several steps of two row groups per warp, ragged tail),
+    per-sample DropPath scale incl. a dropped sample, bf16 against the fp32 eager chain."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(C)
+    B = 2
+    ident, x = torch.randn(B, L, C, generator=g).bfloat16(), torch.randn(B, L, C, generator=g).bfloat16()
+    bias, gamma, beta = torch.randn(C, generator=g) * .1, torch.rand(C, generator=g) + .5, torch.randn(C, generator=g) * .1
+    scale = torch.tensor([1.25, 0.0])
+    w_r, w_n = torch.randn(B, L, C, generator=g).bfloat16().float(), torch.randn(B, L, C, generator=g).bfloat16().float()
+    ri, rx = ident.float().clone().requires_grad_(True), x.float().clone().requires_grad_(True)
+    rb, rg, rbe = bias.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    r = ri + (rx + rb) * scale.view(B, 1, 1)
+    r = r + (r.detach().bfloat16().float() - r.detach())      # the stored residual is bf16
+    n = F.layer_norm(r, (C,), rg, rbe, 1e-5)
+    ((r * w_r).sum() + (n * w_n).sum()).backward()
+    ins = [t.detach().cuda().requires_grad_(True) for t in (ident, x, bias, gamma, beta)]
+    gr, gn = ops.add_ln(ins[0], ins[1], ins[2], scale.cuda(), ins[3], ins[4], 1e-5)
+    ((gr.float() * w_r.cuda()).sum() + (gn.float() * w_n.cuda()).sum()).backward()
+    assert_rel(gr, r, 1e-3, 'r')
+    assert (gr.float().cpu() - r.detach()).abs().max() <= 2 ** -7 * float(r.detach().abs().max())
+    assert_rel(gn, n, 4e-3, 'n')
+    assert (gn.float().cpu() - n.detach()).abs().max() <= 2 ** -7 * float(n.detach().abs().max())    # every row was written
+    for got, want, what in zip(ins, (ri, rx, rb, rg, rbe), ('d_identity', 'dx', 'dbias', 'dgamma', 'dbeta')):
+        assert_rel(got.grad, want.grad, 6e-3, what)
+
+
 @pytest.mark.parametrize('rows,C', [(50, 384), (1000, 768), (33, 3072), (7, 8)])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_bias_gelu_matches_eager(rows, C, dtype):
