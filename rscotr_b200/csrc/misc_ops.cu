@@ -227,6 +227,35 @@ struct Raw4<__nv_bfloat16> {
   }
 };
 
+// 16 consecutive elements (a lane's output channels of one merged token) <-> four Raw4: bf16 moves them as two 16-byte
+// vectors (four 8-byte accesses per lane, 32 bytes apart between lanes, would touch every 32-byte sector four times)
+template <typename T>
+__device__ __forceinline__ void load_row16(const T *p, Raw4<T> (&r)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r[k].load(p + 4 * k);
+}
+template <>
+__device__ __forceinline__ void load_row16<__nv_bfloat16>(const __nv_bfloat16 *p, Raw4<__nv_bfloat16> (&r)[4]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p)), b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+  r[0].v = make_uint2(a.x, a.y), r[1].v = make_uint2(a.z, a.w), r[2].v = make_uint2(b.x, b.y), r[3].v = make_uint2(b.z, b.w);
+}
+template <typename T>
+__device__ __forceinline__ void store_row16(T *p, const float4 (&r)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) store4<T>(p + 4 * k, r[k]);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+template <>
+__device__ __forceinline__ void store_row16<__nv_bfloat16>(__nv_bfloat16 *p, const float4 (&r)[4]) {
+  reinterpret_cast<uint4 *>(p)[0] = make_uint4(pack_bf16x2(r[0].x, r[0].y), pack_bf16x2(r[0].z, r[0].w),
+                                               pack_bf16x2(r[1].x, r[1].y), pack_bf16x2(r[1].z, r[1].w));
+  reinterpret_cast<uint4 *>(p)[1] = make_uint4(pack_bf16x2(r[2].x, r[2].y), pack_bf16x2(r[2].z, r[2].w),
+                                               pack_bf16x2(r[3].x, r[3].y), pack_bf16x2(r[3].z, r[3].w));
+}
+
 constexpr int PM_THREADS = 128;
 
 template <typename T, int ITER, int TPW>
@@ -311,18 +340,18 @@ __global__ void __launch_bounds__(PM_THREADS)
 #pragma unroll
           for (int k = 0; k < 4; ++k) xv[k] = rx[t][it][k].get();
           const float *vf = reinterpret_cast<const float *>(&xv[0]);  // vf[k*4 + cc]
+          float4 r[4];
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             const int o = (c + cc) * 4;
             const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma + o));
             const float4 be = __ldg(reinterpret_cast<const float4 *>(beta + o));
-            float4 r;
-            r.x = (vf[0 * 4 + cc] - mu[t]) * rs[t] * ga.x + be.x;
-            r.y = (vf[1 * 4 + cc] - mu[t]) * rs[t] * ga.y + be.y;
-            r.z = (vf[2 * 4 + cc] - mu[t]) * rs[t] * ga.z + be.z;
-            r.w = (vf[3 * 4 + cc] - mu[t]) * rs[t] * ga.w + be.w;
-            store4<T>(yo + o, r);
+            r[cc].x = (vf[0 * 4 + cc] - mu[t]) * rs[t] * ga.x + be.x;
+            r[cc].y = (vf[1 * 4 + cc] - mu[t]) * rs[t] * ga.y + be.y;
+            r[cc].z = (vf[2 * 4 + cc] - mu[t]) * rs[t] * ga.z + be.z;
+            r[cc].w = (vf[3 * 4 + cc] - mu[t]) * rs[t] * ga.w + be.w;
           }
+          store_row16<T>(yo + c * 4, r);
         }
       }
     }
@@ -368,8 +397,11 @@ __global__ void __launch_bounds__(PM_THREADS, ITER <= 3 ? 3 : 2)   // (3 CTAs: 1
         for (int k = 0; k < 4; ++k) {
           if (on && ((k >> 1) == 0 || h1) && ((k & 1) == 0 || w1)) rx[t][it][k].load(xb + (k >> 1) * rowC + (k & 1) * g.C + c);
           else rx[t][it][k].zero();
-          if (on) rd[t][it][k].load(dyo + (c + k) * 4);
-          else rd[t][it][k].zero();
+        }
+        if (on) load_row16<T>(dyo + c * 4, rd[t][it]);
+        else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rd[t][it][k].zero();
         }
       }
     }
@@ -912,6 +944,11 @@ static bool pm_v1() {
   return v1;
 }
 
+// the round-2 kernels move the merged-token side as 16-byte vectors
+static bool pm_aligned16(const void *a, const void *b, const void *c) {
+  return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
+}
+
 static int pm_check(const char *fn, int B, int H, int W, int C, int dtype) {
   RSC_CHECK_ARG(B > 0 && H > 0 && W > 0, "%s: empty tensor (B=%d,H=%d,W=%d)", fn, B, H, W);
   RSC_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 512, "%s: C must be a multiple of 4, <= 512 (got %d)", fn, C);
@@ -926,7 +963,7 @@ extern "C" int rsc_patch_merge_ln_fwd(const void *x, const float *gamma, const f
   PMGeom g{B, H, W, C, (H + 1) / 2, (W + 1) / 2};
   int64_t tokens = (int64_t)B * g.Ho * g.Wo;
   int grid = ew_grid(tokens, 8);
-  if (pm_v1()) {
+  if (pm_v1() || !pm_aligned16(x, y, nullptr)) {
     DISPATCH_T(dtype, pm_fwd_launch<T>((C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, beta, y, mean, rstd, g, eps));
   } else {
     DISPATCH_T(dtype, pm_fwd2_launch<T>((C + 127) / 128, (cudaStream_t)stream, x, gamma, beta, y, mean, rstd, g, eps));
@@ -944,7 +981,7 @@ extern "C" int rsc_patch_merge_ln_bwd(const void *x, const float *gamma, const f
   int64_t tokens = (int64_t)B * g.Ho * g.Wo;
   int64_t blocks = (tokens + 7) / 8;
   int grid = (int)(blocks < kNumSMs * 4 ? blocks : kNumSMs * 4);  // few warps -> few dgamma atomics
-  if (pm_v1()) {
+  if (pm_v1() || !pm_aligned16(x, dy, dx)) {
     DISPATCH_T(dtype, pm_bwd_launch<T>((C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, mean, rstd, dy, dx, dgamma,
                                        dbeta, g));
   } else {
