@@ -325,8 +325,30 @@ __global__ void __launch_bounds__(WARPS * 32)
   }
 }
 
-template <typename T, typename TO>
-__global__ void __launch_bounds__(WARPS * 32)
+// four elements of T as loaded (bf16: two packed words -- half the registers of four floats)
+template <typename T>
+struct RawV;
+template <>
+struct RawV<float> {
+  float4 v;
+  __device__ __forceinline__ void load(const float *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }
+  __device__ __forceinline__ float4 get() const { return v; }
+};
+template <>
+struct RawV<__nv_bfloat16> {
+  uint2 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16 *p) { v = __ldg(reinterpret_cast<const uint2 *>(p)); }
+  __device__ __forceinline__ float4 get() const {
+    return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                       __uint_as_float(v.y & 0xffff0000u));
+  }
+};
+
+// BF = branch-free point loop, two points per trip: every corner's value load is issued unconditionally (an invalid
+// corner points at the level's first token and carries zero weights), so the eight loads of two points are in flight
+// together instead of one point's four behind a divergent `if (mask)`; only the reductions stay predicated.
+template <typename T, typename TO, bool BF>
+__global__ void __launch_bounds__(WARPS * 32, 4)
     msda_fused_bwd_kernel(const T *__restrict__ value, const int64_t *__restrict__ shapes,
                           const int64_t *__restrict__ starts, const TO *__restrict__ offs, const TO *__restrict__ logits,
                           const float *__restrict__ ref, const T *__restrict__ gout, float *__restrict__ gvalue,
@@ -371,6 +393,51 @@ __global__ void __launch_bounds__(WARPS * 32)
     const int head = hg * 4 + g;
     const int64_t vbase = (int64_t)b * Nv * vstride + head * 32 + t * 4;
     const float4 go = load4<T>(gout + bq * vstride + head * 32 + t * 4);
+    if (BF) {
+      for (int lp0 = 0; lp0 < LP; lp0 += 2) {
+        // the eight value loads of two points first (kept in storage type), then the arithmetic and the reductions:
+        // written out by hand because the compiler does not move loads across the atomics
+        Entry en[2];
+        RawV<T> rv[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          en[u] = my[g * GSTRIDE + lp0 + u];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rv[u][k].load(value + vbase + (int64_t)en[u].off[k] * vstride);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float lh = en[u].w[0], lw = en[u].w[1], aw = en[u].w[2], hh = 1.f - lh, hw = 1.f - lw;
+          const unsigned mask = __float_as_uint(en[u].w[3]);
+          const float4 tw = make_float4(go.x * aw, go.y * aw, go.z * aw, go.w * aw);   // top_grad * attention weight
+          const float wc[4] = {hh * hw, hh * lw, lh * hw, lh * lw};
+          const float dh[4] = {-hw, -lw, hw, lw}, dw[4] = {-hh, hh, -lh, lh};
+          float gh_w = 0.f, gw_w = 0.f;
+          float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool on = (mask >> k) & 1u;
+            const float4 v = rv[u][k].get();
+            const float w = on ? wc[k] : 0.f;
+            const float tv = on ? dot4(tw, v) : 0.f;
+            gh_w = fmaf(dh[k], tv, gh_w);
+            gw_w = fmaf(dw[k], tv, gw_w);
+            fma4(val, w, v);
+            if (on)
+              atomicAdd(reinterpret_cast<float4 *>(gvalue + vbase + (int64_t)en[u].off[k] * vstride),
+                        make_float4(w * tw.x, w * tw.y, w * tw.z, w * tw.w));
+          }
+          float ga = dot4(go, val);
+          gw_w = group_sum8(gw_w);
+          gh_w = group_sum8(gh_w);
+          ga = group_sum8(ga);
+          if (t == 0) {
+            float *r = red[warp][g * LP + lp0 + u];
+            r[0] = gw_w, r[1] = gh_w, r[2] = ga;
+          }
+        }
+      }
+    } else
     for (int lp = 0; lp < LP; ++lp) {
       const Entry en = my[g * GSTRIDE + lp];
       const float lh = en.w[0], lw = en.w[1], aw = en.w[2], hh = 1.f - lh, hw = 1.f - lw;
@@ -543,17 +610,27 @@ extern "C" int rsc_msda_fused_bwd(const void *value, const int64_t *spatial_shap
   const int64_t items = (int64_t)B * Nq * (heads / 4);
   const int grid = msda_grid(items);
   cudaStream_t st = (cudaStream_t)stream;
-#define MFB(T, TO)                                                                                                    \
-  msf::msda_fused_bwd_kernel<T, TO><<<grid, msf::WARPS * 32, 0, st>>>(                                                \
+  static const bool bf = [] {       // RSC_MSDA_BWD_BF=0: the branching one-point loop (A/B switch)
+    const char *e = getenv("RSC_MSDA_BWD_BF");
+    return !(e && e[0] == '0');
+  }();
+#define MFB_(T, TO, BF)                                                                                               \
+  msf::msda_fused_bwd_kernel<T, TO, BF><<<grid, msf::WARPS * 32, 0, st>>>(                                            \
       (const T *)value, spatial_shapes, level_start_index, (const TO *)offsets, (const TO *)logits, ref,              \
       (const T *)grad_out, grad_value, (TO *)grad_offsets, (TO *)grad_logits, B, Nv, Nq, heads, L, P, ref_dim,        \
       (int64_t)off_row_stride, (int64_t)logit_row_stride)
+#define MFB(T, TO)                                                                                                    \
+  do {                                                                                                                \
+    if (bf) MFB_(T, TO, true);                                                                                        \
+    else MFB_(T, TO, false);                                                                                          \
+  } while (0)
   if (dtype == RSC_F32) {
     if (off_dtype == RSC_F32) MFB(float, float); else MFB(float, __nv_bfloat16);
   } else {
     if (off_dtype == RSC_F32) MFB(__nv_bfloat16, float); else MFB(__nv_bfloat16, __nv_bfloat16);
   }
 #undef MFB
+#undef MFB_
   RSC_CHECK_LAUNCH("rsc_msda_fused_bwd");
   return RSC_OK;
 }
