@@ -104,6 +104,10 @@ int rsc_patch_merge_ln_fwd(const void *x, const float *gamma, const float *beta,
 int rsc_patch_merge_ln_bwd(const void *x, const float *gamma, const float *mean, const float *rstd, const void *dy,
                            void *dx, float *dgamma, float *dbeta, int B, int H, int W, int C, int dtype,
                            void *stream);
+/* Which kernels serve rsc_patch_merge_ln_*: 1 = one token per warp step (default), 2 = several tokens in flight per warp,
+ * operands kept in registers (faster, opt-in: see DESIGN.md section 9), 0 = as the environment says
+ * (RSC_PATCH_MERGE_V2=1 selects 2).  Results agree to fp32 rounding. */
+int rsc_set_patch_merge_variant(int variant);
 
 /* ------------------------------------------------------------------------
  * LayerNorm over the last dimension.  Replaces ATen native_layer_norm(+backward)

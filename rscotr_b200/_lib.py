@@ -76,6 +76,7 @@ _SIGS = {
     'rsc_box_refine_bwd': [_P, _P, _P, _P, _P, ctypes.c_int64, _F, _I, _P],
     'rsc_small_linear_bwd': [_P] * 6 + [_I] * 3 + [ctypes.c_int64] * 5 + [_P],
     'rsc_set_gemm_sms': [_I, ctypes.c_int64],
+    'rsc_set_patch_merge_variant': [_I],
 }
 
 

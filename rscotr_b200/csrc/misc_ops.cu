@@ -258,6 +258,16 @@ __device__ __forceinline__ void store_row16<__nv_bfloat16>(__nv_bfloat16 *p, con
 
 constexpr int PM_THREADS = 128;
 
+// merged token index -> (image, row, column) with two 32-bit divisions (the 64-bit `%` / `/` of the first version were
+// most of the kernels' instructions: three emulated divisions per token, per lane); tokens < 2^31 is checked at launch
+__device__ __forceinline__ void pm_decompose(unsigned tok, const PMGeom &g, int &b, int &i, int &j) {
+  const unsigned q = tok / (unsigned)g.Wo;
+  j = (int)(tok - q * (unsigned)g.Wo);
+  const unsigned bb = q / (unsigned)g.Ho;
+  i = (int)(q - bb * (unsigned)g.Ho);
+  b = (int)bb;
+}
+
 template <typename T, int ITER, int TPW>
 __global__ void __launch_bounds__(PM_THREADS)
     patch_merge_ln_fwd2_kernel(const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
@@ -276,7 +286,8 @@ __global__ void __launch_bounds__(PM_THREADS)
     for (int t = 0; t < TPW; ++t) {
       const int64_t tok = tok0 + t;
       const bool valid = tok < tokens;
-      const int j = (int)(tok % g.Wo), i = (int)((tok / g.Wo) % g.Ho), b = (int)(tok / ((int64_t)g.Wo * g.Ho));
+      int b, i, j;
+      pm_decompose((unsigned)tok, g, b, i, j);
       const T *xb = x + ((int64_t)b * g.H + 2 * i) * rowC + (int64_t)2 * j * g.C;
       const bool h1 = 2 * i + 1 < g.H, w1 = 2 * j + 1 < g.W;
 #pragma unroll
@@ -378,15 +389,20 @@ __global__ void __launch_bounds__(PM_THREADS, ITER <= 3 ? 3 : 2)   // (3 CTAs: 1
        tok0 += nwarps * TPW) {
     Raw4<T> rx[TPW][ITER][4], rd[TPW][ITER][4];   // rx[..][k]: source token k; rd[..][cc]: output channels (c+cc)*4 .. +3
     float mu[TPW], rs[TPW], s1[TPW], s2[TPW];
+    int64_t xoff[TPW];      // offset of the 2x2 patch's first source token (x and dx share the layout)
+    unsigned edge[TPW];     // bit 0: the patch has a second row, bit 1: a second column
     // every load of the TPW tokens is in flight before the first use
 #pragma unroll
     for (int t = 0; t < TPW; ++t) {
       const int64_t tok = tok0 + t;
       const bool valid = tok < tokens;
-      const int j = (int)(tok % g.Wo), i = (int)((tok / g.Wo) % g.Ho), b = (int)(tok / ((int64_t)g.Wo * g.Ho));
-      const T *xb = x + ((int64_t)b * g.H + 2 * i) * rowC + (int64_t)2 * j * g.C;
+      int b, i, j;
+      pm_decompose((unsigned)tok, g, b, i, j);
+      xoff[t] = ((int64_t)b * g.H + 2 * i) * rowC + (int64_t)2 * j * g.C;
+      const T *xb = x + xoff[t];
       const T *dyo = dy + tok * 4 * g.C;
       const bool h1 = 2 * i + 1 < g.H, w1 = 2 * j + 1 < g.W;
+      edge[t] = (h1 ? 1u : 0u) | (w1 ? 2u : 0u);
       mu[t] = valid ? __ldg(mean + tok) : 0.f;
       rs[t] = valid ? __ldg(rstd + tok) : 0.f;
 #pragma unroll
@@ -447,9 +463,8 @@ __global__ void __launch_bounds__(PM_THREADS, ITER <= 3 ? 3 : 2)   // (3 CTAs: 1
     for (int t = 0; t < TPW; ++t) {
       const int64_t tok = tok0 + t;
       if (tok >= tokens) break;
-      const int j = (int)(tok % g.Wo), i = (int)((tok / g.Wo) % g.Ho), b = (int)(tok / ((int64_t)g.Wo * g.Ho));
-      T *dxb = dx + ((int64_t)b * g.H + 2 * i) * rowC + (int64_t)2 * j * g.C;
-      const bool h1 = 2 * i + 1 < g.H, w1 = 2 * j + 1 < g.W;
+      T *dxb = dx + xoff[t];
+      const bool h1 = edge[t] & 1u, w1 = edge[t] & 2u;
 #pragma unroll
       for (int it = 0; it < ITER; ++it) {
         const int c = it * 128 + lane * 4;
@@ -935,24 +950,40 @@ static void pm_bwd2_launch(int iters, cudaStream_t st, const void *x, const floa
 #undef PM_CASE
 }
 
-// RSC_PATCH_MERGE_V1=1: the round-1 kernels (one token per warp step), kept for A/B runs
+// RSC_PATCH_MERGE_V2=1 selects the round-2 kernels.  They are 2x faster on the backward (+1.5 % on the whole step,
+// profiles/r02_ab_round2b.log), pass every parity test and compute-sanitizer (initcheck, racecheck, memcheck), but two
+// fp32 trainings of the small models that should agree to 2e-7 -- and do with the round-1 kernels -- land on one of TWO
+// outcomes ~5e-4 apart in single iterations when they run (tools/replay_diag*.py, profiles/r02_replay_diag_*.log).
+// The cause was not found before the round's GPU budget ended, so the default stays with the kernels whose runs
+// reproduce.
+static int g_pm_variant = 0;   // 0 = environment, 1 / 2 = set by rsc_set_patch_merge_variant
 static bool pm_v1() {
-  static const bool v1 = [] {
-    const char *e = getenv("RSC_PATCH_MERGE_V1");
-    return e && e[0] == '1';
+  static const bool env_v1 = [] {
+    const char *e = getenv("RSC_PATCH_MERGE_V2");
+    return !(e && e[0] == '1');
   }();
-  return v1;
+  return g_pm_variant ? g_pm_variant == 1 : env_v1;
 }
 
 // the round-2 kernels move the merged-token side as 16-byte vectors
 static bool pm_aligned16(const void *a, const void *b, const void *c) {
   return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
 }
+// ... and decompose token indices in 32 bits
+static bool pm_v2_ok(int64_t tokens, const void *a, const void *b, const void *c) {
+  return !pm_v1() && tokens < ((int64_t)1 << 31) && pm_aligned16(a, b, c);
+}
 
 static int pm_check(const char *fn, int B, int H, int W, int C, int dtype) {
   RSC_CHECK_ARG(B > 0 && H > 0 && W > 0, "%s: empty tensor (B=%d,H=%d,W=%d)", fn, B, H, W);
   RSC_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 512, "%s: C must be a multiple of 4, <= 512 (got %d)", fn, C);
   RSC_CHECK_ARG(dtype == RSC_F32 || dtype == RSC_BF16, "%s: bad dtype %d", fn, dtype);
+  return RSC_OK;
+}
+
+extern "C" int rsc_set_patch_merge_variant(int variant) {
+  RSC_CHECK_ARG(variant >= 0 && variant <= 2, "rsc_set_patch_merge_variant: 0 (environment), 1 or 2 (got %d)", variant);
+  g_pm_variant = variant;
   return RSC_OK;
 }
 
@@ -963,7 +994,7 @@ extern "C" int rsc_patch_merge_ln_fwd(const void *x, const float *gamma, const f
   PMGeom g{B, H, W, C, (H + 1) / 2, (W + 1) / 2};
   int64_t tokens = (int64_t)B * g.Ho * g.Wo;
   int grid = ew_grid(tokens, 8);
-  if (pm_v1() || !pm_aligned16(x, y, nullptr)) {
+  if (!pm_v2_ok(tokens, x, y, nullptr)) {
     DISPATCH_T(dtype, pm_fwd_launch<T>((C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, beta, y, mean, rstd, g, eps));
   } else {
     DISPATCH_T(dtype, pm_fwd2_launch<T>((C + 127) / 128, (cudaStream_t)stream, x, gamma, beta, y, mean, rstd, g, eps));
@@ -981,7 +1012,7 @@ extern "C" int rsc_patch_merge_ln_bwd(const void *x, const float *gamma, const f
   int64_t tokens = (int64_t)B * g.Ho * g.Wo;
   int64_t blocks = (tokens + 7) / 8;
   int grid = (int)(blocks < kNumSMs * 4 ? blocks : kNumSMs * 4);  // few warps -> few dgamma atomics
-  if (pm_v1() || !pm_aligned16(x, dy, dx)) {
+  if (!pm_v2_ok(tokens, x, dy, dx)) {
     DISPATCH_T(dtype, pm_bwd_launch<T>((C + 127) / 128, grid, (cudaStream_t)stream, x, gamma, mean, rstd, dy, dx, dgamma,
                                        dbeta, g));
   } else {

@@ -138,11 +138,11 @@ def test_cuda_graph_replay_matches_eager(task):
     (l0, p0), (l1, p1) = finals
     for a, b in zip(l0, l1):
         assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (l0, l1)
-    # cls / det: the order of the fp32 atomic sums (different on every run) is all that separates the two trainings.
-    # seg: the head's forward THRESHOLDS mask logits (sigmoid < 0.5 -> attention-mask bits, mask2former_head.py:174-197);
-    # a logit within that noise of 0 flips between runs, eager or replayed alike, and moves the gradients by ~1e-3
-    # (tools/replay_diag.py, profiles/r02_replay_diag_seg.log: two eager runs differ exactly as eager and replay do,
-    # up to 3.2e-3 on a zero-initialised norm bias after five steps) -- a bound for gross errors is all seg can carry
+    # cls / det: the order of the fp32 atomic sums (different on every run) is all that separates the two trainings
+    # (3e-6 measured, tools/replay_diag.py).  seg: the head's forward THRESHOLDS mask logits (sigmoid < 0.5 ->
+    # attention-mask bits, mask2former_head.py:174-197); a logit within that noise of 0 flips between runs, eager or
+    # replayed alike (one 4.7e-4 excursion of the gradient in 12 runs, profiles/r02_replay_diag_seg.log) -- seg carries
+    # a bound for gross errors (a kernel missing from the graph, a stale buffer: O(1)) rather than a rounding bound
     tol = 2e-2 if task == 'seg' else 5e-4
     for n in p0:
         assert rel(p1[n], p0[n]) < tol, n

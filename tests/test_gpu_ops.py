@@ -233,8 +233,10 @@ def test_wmsa_large_property():
 @pytest.mark.parametrize('B,H,W,C', [(2, 8, 8, 96), (1, 9, 7, 96), (2, 10, 6, 192), (1, 5, 5, 384), (1, 4, 4, 512),
                                      (1, 6, 6, 128)])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
-def test_patch_merge_ln(B, H, W, C, dtype):
+@pytest.mark.parametrize('variant', [1, 2])
+def test_patch_merge_ln(B, H, W, C, dtype, variant, pm_variant):
     ops = _ops()
+    pm_variant(variant)
     g = torch.Generator().manual_seed(C + H)
     x = torch.randn(B, H * W, C, generator=g)
     gamma = 1 + 0.1 * torch.randn(4 * C, generator=g)
@@ -260,12 +262,25 @@ def test_patch_merge_ln(B, H, W, C, dtype):
     assert_rel(bg.grad, sd['d.norm.bias'].grad, tol, 'dbeta')
 
 
+@pytest.fixture
+def pm_variant():
+    """rsc_set_patch_merge_variant for one test, restored afterwards"""
+    from rscotr_b200 import _lib
+
+    def choose(v):
+        _lib.call('rsc_set_patch_merge_variant', v)
+    yield choose
+    _lib.call('rsc_set_patch_merge_variant', 0)
+
+
 @pytest.mark.parametrize('B,H,W,C', [(2, 151, 151, 96), (1, 151, 149, 192), (1, 100, 100, 384)])
-def test_patch_merge_ln_persistent_loop(B, H, W, C):
-    """more tokens than one pass of the resident warps covers (several TPW-token steps per warp, a ragged last step) and
-    odd H / W (the zero-padded last row / column of mmdet's PatchMerging), bf16, against the fp32 oracle; the round-1
-    kernels (RSC_PATCH_MERGE_V1) are held to the same numbers by test_patch_merge_ln."""
+@pytest.mark.parametrize('variant', [1, 2])
+def test_patch_merge_ln_persistent_loop(B, H, W, C, variant, pm_variant):
+    """more tokens than one pass of the resident warps covers (several steps per warp, a ragged last step) and odd
+    H / W (the zero-padded last row / column of mmdet's PatchMerging), bf16, against the fp32 oracle; both kernel
+    variants (include/rscotr.h: rsc_set_patch_merge_variant)."""
     ops = _ops()
+    pm_variant(variant)
     g = torch.Generator().manual_seed(C + H)
     x = torch.randn(B, H * W, C, generator=g).bfloat16().float()
     gamma = 1 + 0.1 * torch.randn(4 * C, generator=g)

@@ -1,7 +1,7 @@
 """How far apart do two fp32 trainings of the small seg / det model end up after 5 SGD steps -- eager vs eager (the floor
 set by the order of the fp32 atomic sums, amplified by thresholded masks / assignments) and eager vs CUDA-graph replay --
 with the round's switches on and off?  Diagnostic for tests/test_gpu_model.py::test_cuda_graph_replay_matches_eager.
-    python tools/replay_diag.py [task ...]        (RSC_PATCH_MERGE_V1=1 selects the round-1 PatchMerging kernels)"""
+    python tools/replay_diag.py [task ...]        (RSC_PATCH_MERGE_V2=1 selects the round-2 PatchMerging kernels)"""
 import os
 import sys
 
@@ -45,8 +45,8 @@ def main():
             gr, g2 = run(task, True)
             for tag, (a, ga) in (('eager-eager', (e1, g1)), ('eager-graph', (gr, g2))):
                 worst = max((rel(a[n], e0[n]), n) for n in e0)
-                print('%s pm_v1=%s pair=%d %s: worst param rel %.2e (%s); flat grad rel per iter %s' % (
-                    task, os.environ.get('RSC_PATCH_MERGE_V1', '0'), pair, tag, worst[0], worst[1],
+                print('%s pm_v2=%s pair=%d %s: worst param rel %.2e (%s); flat grad rel per iter %s' % (
+                    task, os.environ.get("RSC_PATCH_MERGE_V2", "0"), pair, tag, worst[0], worst[1],
                     ' '.join('%.1e' % rel(x, y) for x, y in zip(ga, g0))), flush=True)
 
 

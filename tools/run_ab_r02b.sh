@@ -25,5 +25,5 @@ PY
 run all_on RSC_X=0
 run side_off RSC_SIDE_DW=0
 run pair_off RSC_LINEAR_PAIR=0
-run pm_v1 RSC_PATCH_MERGE_V1=1
+run pm_v1 RSC_PATCH_MERGE_V1=1   # (at that commit v2 was the default; now: RSC_PATCH_MERGE_V2=1 opts in)
 run all_on2 RSC_X=0

@@ -8,11 +8,12 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from rscotr_b200 import ops  # noqa: E402
+from rscotr_b200 import _lib, ops  # noqa: E402
 
 
 def main():
     dev = 'cuda'
+    _lib.call('rsc_set_patch_merge_variant', 2)        # the round-2 PatchMerging kernels (opt-in)
     g = torch.Generator().manual_seed(0)
     for dtype in (torch.float32, torch.bfloat16):
         for B, H, W, C in [(2, 16, 16, 96), (2, 8, 8, 192), (2, 4, 4, 384), (1, 9, 7, 96), (1, 4, 4, 512), (3, 37, 41, 96)]:
