@@ -1,4 +1,6 @@
 #!/bin/bash
+# (record of a measurement: RSC_ADDLN_UNROLL existed only at the commit this was run on -- the two-row-group variant lost
+# 1.3 % and was reverted, profiles/r02_ab_round2b.log)
 # second A/B of the round on one B200: new parity tests, add+LayerNorm micro-benchmark with one / two row groups per warp step,
 # bench.py with the switch both ways.  Outputs: gpurun_out/ab3_*
 set -u
