@@ -951,11 +951,13 @@ static void pm_bwd2_launch(int iters, cudaStream_t st, const void *x, const floa
 }
 
 // RSC_PATCH_MERGE_V2=1 selects the round-2 kernels.  They are 2x faster on the backward (+1.5 % on the whole step,
-// profiles/r02_ab_round2b.log), pass every parity test and compute-sanitizer (initcheck, racecheck, memcheck), but two
-// fp32 trainings of the small models that should agree to 2e-7 -- and do with the round-1 kernels -- land on one of TWO
-// outcomes ~5e-4 apart in single iterations when they run (tools/replay_diag*.py, profiles/r02_replay_diag_*.log).
-// The cause was not found before the round's GPU budget ended, so the default stays with the kernels whose runs
-// reproduce.
+// profiles/r02_ab_round2b.log), pass every parity test and compute-sanitizer (initcheck, racecheck, memcheck), return
+// bit-identical y / dx on repeated calls and equal the round-1 kernels to 1e-8 (tools/pm_determinism.py,
+// profiles/r02_pm_determinism.log).  Still, repeated fp32 trainings of the small test models, which agree to 2e-7 with
+// the round-1 kernels, land on one of TWO outcomes ~5e-4 apart in single iterations with these
+// (tools/replay_diag*.py, profiles/r02_replay_diag_*.log): their different last bits put those trainings next to
+// something that amplifies last-bit differences, and what that is was not found before the round's GPU budget ended.
+// The default stays with the kernels under which the replay tests reproduce.
 static int g_pm_variant = 0;   // 0 = environment, 1 / 2 = set by rsc_set_patch_merge_variant
 static bool pm_v1() {
   static const bool env_v1 = [] {
