@@ -186,7 +186,9 @@ def test_linear_pair_leaves_the_step_unchanged(task, dtype, monkeypatch):
     tol = 2e-4 if f32 else 5e-2
     for a, b in zip(l_on, l_off):
         assert abs(a - b) <= tol * max(1.0, abs(b)), (l_on, l_off)
-    gtol = tol if f32 else 0.35
+    # (fp32 seg: a thresholded mask logit can flip between any two runs -- one 4.7e-4 excursion of the gradient in 60
+    # iterations, profiles/r02_replay_diag_seg.log -- so its bound leaves room for that; a logic error is O(1))
+    gtol = (5e-3 if task == 'seg' else tol) if f32 else 0.35
     for k, (a, b) in enumerate(zip(g_on, g_off)):
         assert rel(a, b) < gtol, (k, rel(a, b))
 
