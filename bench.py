@@ -571,6 +571,11 @@ def main():
                         pipeline='pinned host inputs, H2D of step i+1 on a copy stream during step i; loss of step i '
                                  'copied to pinned host memory and read after step i+2 is enqueued'),
                gpu_launches=launches, cuda_graphs=bool(engine.use_graphs), cuda_graph_capture_failures=engine.graph_failures,
+               # which of the A/B'd variants this run used (defaults unless the environment says otherwise; DESIGN.md sections 4 / 9)
+               switches=dict(patch_merge_kernels=2 if os.environ.get('RSC_PATCH_MERGE_V2') == '1' else 1,
+                             linear_pair=os.environ.get('RSC_LINEAR_PAIR', '1') != '0',
+                             msda_bwd_branch_free=os.environ.get('RSC_MSDA_BWD_BF', '1') != '0',
+                             own_gemm=os.environ.get('RSC_OWN_GEMM', '1') != '0'),
                ms_per_task={k: sum(v) / len(v) for k, v in per_task.items()},
                roofline=roofline, roofline_also=roofline_also, sustained=sustained,
                kernels={k: dict(launches=d['launches'], ms=round(d['ms'], 3), gbs=round(d['gbs'], 1),
